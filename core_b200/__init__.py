@@ -1,0 +1,18 @@
+"""core_b200 — B200-native implementation of Cherab's per-ray emission-integration and ray-transfer hot path.
+
+CUDA sm_100a kernels behind the C ABI of include/cherab_b200.h (core_b200/csrc/libcherab_b200.so), with a host-side
+mirror of the reference's operator interface for this path (Plasma, Species, Maxwellian, ExcitationLine,
+RecombinationLine, Bremsstrahlung, line shapes, RayTransferCylinder/Box and the RayTransferPipelines).
+No CPU fallback: calls fail loudly if the CUDA library or a GPU is missing.
+"""
+from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, SyntheticADAS, carbon, deuterium, helium,
+                     hydrogen, neon, nitrogen, tritium)
+from .flatten import FlatScene, RayBatch, flatten_scene
+from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
+from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
+                     RecombinationLine, StarkBroadenedLine, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
+from .plasma import (AxisymBlend, AxisymBlendVector, AxisymContext, Constant3D, ConstantVector3D, EFITEquilibrium,
+                     EFITMagneticField, GaussianVolume, Maxwellian, NumericalIntegrator, Plasma, SlabIonFunction,
+                     SlabNeutralFunction, Species)
+
+__version__ = "0.1.0"

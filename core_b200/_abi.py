@@ -1,0 +1,153 @@
+"""ctypes mirror of include/cherab_b200.h (the C ABI of the hot path) and the loader of the CUDA library.
+
+The product library is ``core_b200/csrc/libcherab_b200.so`` (built in-tree by ``__graft_entry__.build()``).
+There is NO CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+ABI_VERSION = 1
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+# status codes -> the exception type the reference raises at the same point (include/cherab_b200.h cb2_status)
+STATUS_EXC = {-1: ValueError, -2: RuntimeError, -3: TypeError, -4: NotImplementedError,
+              -5: RuntimeError, -6: MemoryError, -7: OverflowError}
+
+FIELD_CONSTANT, FIELD_GAUSSIAN_VOLUME, FIELD_AXISYM_BLEND, FIELD_SLAB_ION, FIELD_SLAB_NEUTRAL = range(5)
+SHAPE_GAUSSIAN, SHAPE_MULTIPLET, SHAPE_ZEEMAN_TRIPLET, SHAPE_PARAM_ZEEMAN, SHAPE_ZEEMAN_MULTIPLET, SHAPE_STARK = range(6)
+POL_PI, POL_SIGMA, POL_NO = range(3)
+MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG = range(3)
+RT_CYLINDRICAL, RT_CARTESIAN = range(2)
+
+
+class SpectralGrid(C.Structure):
+    _fields_ = [("min_wavelength", C.c_double), ("max_wavelength", C.c_double), ("bins", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ScalarField(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("c", C.c_double * 8), ("edge", c_double_p), ("core", c_double_p)]
+
+
+class VectorField(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("c", C.c_double * 8),
+                ("core_vtor", c_double_p), ("core_vpol", c_double_p), ("core_vnorm", c_double_p)]
+
+
+class Equilibrium(C.Structure):
+    _fields_ = [("nr", C.c_int32), ("nz", C.c_int32), ("r", c_double_p), ("z", c_double_p), ("psi", c_double_p),
+                ("psi_axis", C.c_double), ("psi_lcfs", C.c_double), ("n_f", C.c_int32), ("n_lcfs", C.c_int32),
+                ("f_psin", c_double_p), ("f_value", c_double_p), ("lcfs_polygon", c_double_p),
+                ("b_vacuum_radius", C.c_double), ("b_vacuum_magnitude", C.c_double)]
+
+
+class Axisym(C.Structure):
+    _fields_ = [("eq", Equilibrium), ("n_vertices", C.c_int32), ("n_triangles", C.c_int32),
+                ("vertices", c_double_p), ("triangles", c_int32_p), ("n_core", C.c_int32), ("n_mask", C.c_int32),
+                ("core_psin", c_double_p), ("mask_x", c_double_p), ("mask_y", c_double_p)]
+
+
+class SpeciesDesc(C.Structure):
+    _fields_ = [("charge", C.c_int32), ("_pad", C.c_int32), ("atomic_weight", C.c_double),
+                ("density", ScalarField), ("temperature", ScalarField), ("velocity", VectorField)]
+
+
+class Rate2D(C.Structure):
+    _fields_ = [("n_ne", C.c_int32), ("n_te", C.c_int32), ("ne", c_double_p), ("te", c_double_p), ("rate", c_double_p),
+                ("constant", C.c_double), ("extrapolate", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Gaunt(C.Structure):
+    _fields_ = [("n_u", C.c_int32), ("n_gamma2", C.c_int32), ("u", c_double_p), ("gamma2", c_double_p), ("gaunt", c_double_p)]
+
+
+class LineShape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("polarisation", C.c_int32), ("param", C.c_double * 3),
+                ("n_components", C.c_int32), ("n_b", C.c_int32), ("multiplet", c_double_p),
+                ("n_pi", C.c_int32), ("n_sigma_plus", C.c_int32), ("n_sigma_minus", C.c_int32), ("_pad", C.c_int32),
+                ("b_grid", c_double_p), ("zeeman_wavelength", c_double_p), ("zeeman_ratio", c_double_p)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("species", C.c_int32), ("wavelength", C.c_double), ("atomic_weight", C.c_double),
+                ("pec", Rate2D), ("shape", LineShape)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_species", C.c_int32), ("n_models", C.c_int32), ("min_samples", C.c_int32),
+                ("step", C.c_double), ("grid", SpectralGrid), ("world_to_plasma", C.c_double * 12),
+                ("electron_density", ScalarField), ("electron_temperature", ScalarField),
+                ("species", C.POINTER(SpeciesDesc)), ("models", C.POINTER(ModelDesc)), ("axisym", C.POINTER(Axisym)),
+                ("b_field_kind", C.c_int32), ("brems_quadrature", C.c_int32), ("b_field", C.c_double * 3),
+                ("gaunt", Gaunt), ("quad_rtol", C.c_double), ("quad_max_order", C.c_int32), ("quad_min_order", C.c_int32)]
+
+
+class Rays(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_segments", C.c_int64), ("origin", c_double_p), ("direction", c_double_p),
+                ("seg_offset", c_int64_p), ("seg_t0", c_double_p), ("seg_t1", c_double_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_int64), ("gaussian_bin_evals", C.c_int64), ("lorentzian_bin_evals", C.c_int64),
+                ("brems_bin_evals", C.c_int64), ("rt_steps", C.c_int64), ("out_of_domain", C.c_int64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class RTDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("kind", C.c_int32), ("grid_shape", C.c_int32 * 3), ("min_samples", C.c_int32),
+                ("grid_steps", C.c_double * 3), ("rmin", C.c_double), ("period", C.c_double), ("step", C.c_double),
+                ("world_to_local", C.c_double * 12), ("voxel_map", c_int32_p), ("bins", C.c_int32), ("_pad", C.c_int32)]
+
+
+# every symbol include/cherab_b200.h declares for the product library
+PRODUCT_SYMBOLS = [
+    "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_scene_create", "cb2_scene_destroy",
+    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width",
+    "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
+]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcherab_b200.so")
+_lib = None
+
+
+def load_library():
+    """Load libcherab_b200.so; fail loudly (no fallback) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("core_b200: CUDA library %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.cb2_abi_version.restype = C.c_int
+    lib.cb2_last_error.restype = C.c_char_p
+    lib.cb2_device_count.restype = C.c_int
+    lib.cb2_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
+    lib.cb2_scene_destroy.argtypes = [vp]
+    lib.cb2_emission_render.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, C.POINTER(Stats)]
+    lib.cb2_emission_render_device.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, vp, vp]
+    lib.cb2_sample_state.argtypes = [vp, c_double_p, C.c_int64, c_double_p]
+    lib.cb2_state_width.argtypes = [vp]
+    lib.cb2_rt_create.argtypes = [C.POINTER(RTDesc), C.c_int, C.POINTER(vp)]
+    lib.cb2_rt_destroy.argtypes = [vp]
+    lib.cb2_rt_render_dense.argtypes = [vp, C.POINTER(Rays), c_double_p, C.c_int, C.POINTER(Stats)]
+    lib.cb2_rt_render_csr.argtypes = [vp, C.POINTER(Rays), c_int64_p, c_int32_p, c_double_p, C.c_int64, C.POINTER(Stats)]
+    lib.cb2_rt_render_csr_device.argtypes = [vp, C.POINTER(Rays), vp, vp, vp, C.c_int64, c_int64_p, vp, vp]
+    for name in PRODUCT_SYMBOLS:
+        getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+    if lib.cb2_abi_version() != ABI_VERSION:
+        raise RuntimeError("core_b200: ABI version mismatch between Python and libcherab_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(lib, rc, errfn="cb2_last_error"):
+    if rc != 0:
+        msg = getattr(lib, errfn)()
+        msg = msg.decode() if msg else "error %d" % rc
+        raise STATUS_EXC.get(rc, RuntimeError)(msg)

@@ -1,0 +1,163 @@
+"""Atomic-data side of the hot path: elements, lines and ADAS-format rate providers.
+
+Host-side mirror of the parts of ``cherab.core.atomic`` / ``cherab.openadas`` the emission path touches
+(cherab/core/atomic/elements.pyx:243-402, line.pyx:20-80, interface.pyx:24-207; cherab/openadas/rates/pec.pyx:27-140).
+Rates stay in their on-disk ADAS/OpenADAS shape ({'ne','te','rate'} in m^-3, eV, photon m^3/s) until the
+scene flattener hands them to the CUDA library, which builds the log10-log10 bicubic tables.
+"""
+import json
+import os
+
+import numpy as np
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+class Element:
+    """cherab/core/atomic/elements.pyx Element/Isotope: name, symbol, atomic_number, atomic_weight."""
+
+    def __init__(self, name, symbol, atomic_number, atomic_weight, element=None):
+        self.name, self.symbol = name, symbol
+        self.atomic_number, self.atomic_weight = int(atomic_number), float(atomic_weight)
+        self.element = element or self  # isotopes point at their element (elements.pyx:364)
+
+    def __repr__(self):
+        return "<Element: %s>" % self.name
+
+
+hydrogen = Element("hydrogen", "H", 1, (1.00784 + 1.00811) / 2)
+helium = Element("helium", "He", 2, 4.002602)
+beryllium = Element("beryllium", "Be", 4, 9.0121831)
+carbon = Element("carbon", "C", 6, (12.0096 + 12.0116) / 2)
+nitrogen = Element("nitrogen", "N", 7, (14.00643 + 14.00728) / 2)
+oxygen = Element("oxygen", "O", 8, (15.99903 + 15.99977) / 2)
+neon = Element("neon", "Ne", 10, 20.1797)
+argon = Element("argon", "Ar", 18, (39.792 + 39.963) / 2)
+deuterium = Element("deuterium", "D", 1, 2.0141017778, hydrogen)
+tritium = Element("tritium", "T", 1, 3.0160492777, hydrogen)
+
+
+class Line:
+    """cherab/core/atomic/line.pyx:20-80."""
+
+    def __init__(self, element, charge, transition):
+        if charge > element.atomic_number - 1:
+            raise ValueError("Charge state cannot be larger than one less than the atomic number.")
+        if charge < 0:
+            raise ValueError("Charge state cannot be less than zero.")
+        self.element, self.charge, self.transition = element, int(charge), tuple(transition)
+
+    def __repr__(self):
+        return "<Line: %s, %d, %s>" % (self.element.name, self.charge, self.transition)
+
+    def __hash__(self):
+        return hash((self.element.name, self.charge, self.transition))
+
+    def __eq__(self, other):
+        return isinstance(other, Line) and (self.element.name, self.charge, self.transition) == \
+            (other.element.name, other.charge, other.transition)
+
+
+class RateTable:
+    """An ADF15-shaped PEC block: the ``data`` dict ImpactExcitationPEC/RecombinationPEC take (pec.pyx:48-68)."""
+
+    def __init__(self, ne, te, rate, extrapolate=False):
+        self.ne = np.ascontiguousarray(ne, dtype=np.float64)
+        self.te = np.ascontiguousarray(te, dtype=np.float64)
+        self.rate = np.ascontiguousarray(rate, dtype=np.float64)
+        if self.rate.shape != (self.ne.size, self.te.size):
+            raise ValueError("rate must have shape (len(ne), len(te))")
+        self.extrapolate = bool(extrapolate)
+
+
+class ConstantRate:
+    """Constant-valued rate in W m^3, as the mock AtomicData of core/tests/test_line_emission.py:32-88 returns."""
+
+    def __init__(self, value):
+        self.value = float(value)
+
+
+class AtomicData:
+    """The subset of cherab/core/atomic/interface.pyx:24-207 the emission path calls."""
+
+    def wavelength(self, ion, charge, transition):
+        raise NotImplementedError("The wavelength() virtual method is not implemented for this atomic data source.")
+
+    def impact_excitation_pec(self, ion, charge, transition):
+        raise NotImplementedError("The impact_excitation() virtual method is not implemented for this atomic data source.")
+
+    def recombination_pec(self, ion, charge, transition):
+        raise NotImplementedError("The recombination() virtual method is not implemented for this atomic data source.")
+
+    def free_free_gaunt_factor(self):
+        """MaxwellianFreeFreeGauntFactor table (cherab/core/atomic/gaunt.pyx:143-158): (u, gamma2, gaunt_factor)."""
+        t = np.load(os.path.join(_DATA, "atomic_tables.npz"))
+        return t["gaunt_u"], t["gaunt_gamma2"], t["gaunt_factor"]
+
+    def stark_model_coefficients(self, line):
+        """(c_ij, a_ij, b_ij) — cherab/core/atomic/interface.pyx:176-196."""
+        t = np.load(os.path.join(_DATA, "atomic_tables.npz"))
+        data = json.loads(str(t["stark_json"]))
+        sym = line.element.symbol.lower()
+        if sym not in data:
+            raise ValueError("Stark broadening coefficients for {} is not currently available.".format(line))
+        key = "%s -> %s" % (line.transition[0], line.transition[1])
+        try:
+            return tuple(data[sym][str(line.charge)][key])
+        except KeyError:
+            raise ValueError("Stark broadening coefficients for {} is not currently available.".format(line))
+
+    def zeeman_triplet_parameters(self, line):
+        """(alpha, beta, gamma) — cherab/core/atomic/interface.pyx:154-174."""
+        t = np.load(os.path.join(_DATA, "atomic_tables.npz"))
+        data = json.loads(str(t["zeeman_parametrised_json"]))
+        sym = line.element.symbol.lower()
+        key = "%s -> %s" % (line.transition[0], line.transition[1])
+        try:
+            return tuple(data[sym][str(line.charge)][key])
+        except KeyError:
+            raise ValueError("Data for {} is not available.".format(line))
+
+
+# Balmer wavelengths the OpenADAS repository ships for hydrogen (cherab/openadas/repository/create.py:224-241)
+_H_BALMER = {(3, 2): 656.279, (4, 2): 486.135, (5, 2): 434.047, (6, 2): 410.173, (7, 2): 397.008}
+# deuterium: reduced-mass scaled from H0, with the observed NIST values where the repository overrides them (create.py:296-311)
+_D_BALMER = {(3, 2): 656.101, (4, 2): 486.000, (5, 2): 433.928, (6, 2): 410.062, (7, 2): 396.899}
+
+
+class SyntheticADAS(AtomicData):
+    """Deterministic synthetic rates with exactly the OpenADAS JSON shapes: no repository is present
+    in this environment (it is downloaded by cherab.openadas.repository.populate()).
+
+    excitation   : 1e-14 (te/10)^-0.5 exp(-E_n/te) (1 + 0.1 log10(ne/1e19))  photon m^3/s
+    recombination: 3e-19 (te/10)^-0.7                                         photon m^3/s
+    on ne = logspace(13.7, 21.3, 24) m^-3, te = logspace(-0.7, 4, 29) eV, scaled per upper level n.
+    """
+
+    def __init__(self, permit_extrapolation=True):
+        self.permit_extrapolation = permit_extrapolation
+        self.ne = np.logspace(13.7, 21.3, 24)
+        self.te = np.logspace(-0.7, 4.0, 29)
+
+    def wavelength(self, ion, charge, transition):
+        table = _D_BALMER if ion.name == "deuterium" else _H_BALMER
+        try:
+            return table[(int(transition[0]), int(transition[1]))]
+        except (KeyError, ValueError, TypeError):
+            raise RuntimeError("Requested wavelength is not available: %s %d %s" % (ion.name, charge, transition))
+
+    def _scale(self, transition):
+        n = int(transition[0])
+        return (3.0 / n) ** 3, 13.605693122994 * (1.0 - 1.0 / n ** 2)
+
+    def impact_excitation_pec(self, ion, charge, transition):
+        s, e_n = self._scale(transition)
+        ne, te = self.ne[:, None], self.te[None, :]
+        rate = s * 1e-14 * (te / 10.0) ** -0.5 * np.exp(-e_n / te) * (1.0 + 0.1 * np.log10(ne / 1e19))
+        return RateTable(self.ne, self.te, rate, self.permit_extrapolation)
+
+    def recombination_pec(self, ion, charge, transition):
+        s, _ = self._scale(transition)
+        ne, te = self.ne[:, None], self.te[None, :]
+        rate = s * 3e-19 * (te / 10.0) ** -0.7 * np.ones_like(ne)
+        return RateTable(self.ne, self.te, rate, self.permit_extrapolation)

@@ -1,0 +1,350 @@
+/*
+ * cherab_b200.h — C ABI of the B200-native Cherab hot path.
+ *
+ * One data-parallel path: the per-ray line-of-sight integration of plasma
+ * emission (Raysect NumericalIntegrator -> PlasmaMaterial.emission_function ->
+ * PlasmaModel.emission -> LineShapeModel.add_line) and the sibling ray-transfer
+ * (geometry-matrix) path-length sampler.  There is no FFI in the reference: the
+ * seams these entry points replace are the Cython virtual interfaces listed in
+ * SURVEY.md section 8(b); every declaration below cites the reference interface
+ * (file:line, relative to the cherab/core checkout) whose work it takes over.
+ *
+ * The SAME descriptor structs are consumed by two independent implementations:
+ *   - libcherab_b200.so   (core_b200/csrc, CUDA sm_100a, fp32 math / fp64 accumulation) — the product
+ *   - libcb2_oracle.so    (oracle/, plain C, fp64, scalar restatement of the reference) — test infrastructure
+ * Entry points of the product are prefixed cb2_, those of the oracle cb2o_.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays C-contiguous, caller-owned, read-only for the call;
+ *   - descriptor data is HOST memory and is copied at cb2_scene_create();
+ *   - every function returns CB2_OK (0) or a negative cb2_status; cb2_last_error() gives the message
+ *     (mirrors the reference's `except -1` / `except? -1e999` Cython conventions and the Python
+ *     exception type it would raise: see cb2_status);
+ *   - a scene handle is not thread-safe (one CUDA stream per call); one handle per GPU.
+ */
+#ifndef CHERAB_B200_H
+#define CHERAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB2_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------
+ * status codes.  Python shim maps them to the exception the reference raises at the same point.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_status {
+    CB2_OK = 0,
+    CB2_ERR_VALUE = -1,        /* ValueError: bad argument / out-of-range interpolation (interpolators 'none' extrapolation) */
+    CB2_ERR_RUNTIME = -2,      /* RuntimeError: missing species / rates (impact_excitation.pyx:105-118) */
+    CB2_ERR_TYPE = -3,         /* TypeError: unsupported model / lineshape / field kind (impact_excitation.pyx:60-61) */
+    CB2_ERR_NOT_IMPLEMENTED = -4,
+    CB2_ERR_CUDA = -5,         /* CUDA runtime failure (no CPU fallback exists) */
+    CB2_ERR_MEMORY = -6,
+    CB2_ERR_OVERFLOW = -7      /* a caller-provided output buffer is too small */
+} cb2_status;
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral grid — raysect Spectrum(min_wavelength, max_wavelength, bins); delta=(max-min)/bins.
+ * Used as in cherab/core/model/lineshape/gaussian.pyx:65-85.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cb2_spectral_grid {
+    double  min_wavelength;   /* nm */
+    double  max_wavelength;   /* nm */
+    int32_t bins;
+    int32_t _pad;
+} cb2_spectral_grid;
+
+/* ------------------------------------------------------------------------------------------------
+ * Scalar / vector fields: the flattened Function3D trees behind
+ * Maxwellian.density / effective_temperature / bulk_velocity (cherab/core/distribution.pyx:254-301).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_field_kind {
+    CB2_FIELD_CONSTANT        = 0, /* c[0]                                   (Constant3D; build_constant_slab_plasma, tools/plasmas/slab.pyx:198-260) */
+    CB2_FIELD_GAUSSIAN_VOLUME = 1, /* c[0] + c[1]*exp(-|p-(c[3],c[4],c[5])|^2/(2 c[2]^2))  (tools/plasmas/gaussian_volume.pyx:24-59, demos/balmer_series.py:55-60) */
+    CB2_FIELD_AXISYM_BLEND    = 2, /* AxisymmetricMapper(Blend2D(edge mesh, equilibrium.map2d(core 1-D cubic), mask)) — generomak/plasma/plasma.py:580-638 */
+    CB2_FIELD_SLAB_ION        = 3, /* IonFunction along +x (tools/plasmas/slab.pyx:63-110): c = t_core, t_lcfs, p, q, pedestal_top */
+    CB2_FIELD_SLAB_NEUTRAL    = 4  /* NeutralFunction along +x (tools/plasmas/slab.pyx:20-60): c = peak, sigma */
+} cb2_field_kind;
+
+typedef struct cb2_scalar_field {
+    int32_t       kind;      /* cb2_field_kind */
+    int32_t       _pad;
+    double        c[8];
+    const double* edge;      /* AXISYM_BLEND: per-triangle values [n_triangles] (Discrete2DMesh data), NULL -> 0 */
+    const double* core;      /* AXISYM_BLEND: values on the core psi_n grid [n_core] (Interpolator1DArray 'cubic','nearest'), NULL -> 0 */
+} cb2_scalar_field;
+
+typedef struct cb2_vector_field {
+    int32_t       kind;      /* CONSTANT: cartesian (c[0],c[1],c[2]); AXISYM_BLEND: edge vector (R,phi,Z)=(c[0],c[1],c[2]) */
+    int32_t       _pad;
+    double        c[8];
+    const double* core_vtor; /* AXISYM_BLEND: flux-function velocities on the core psi_n grid [n_core] (efit.pyx:521-546) */
+    const double* core_vpol;
+    const double* core_vnorm;
+} cb2_vector_field;
+
+/* EFITEquilibrium inputs (cherab/tools/equilibrium/efit.pyx:92-142) */
+typedef struct cb2_equilibrium {
+    int32_t       nr, nz;
+    const double* r;               /* [nr] */
+    const double* z;               /* [nz] */
+    const double* psi;             /* [nr][nz] poloidal flux */
+    double        psi_axis, psi_lcfs;
+    int32_t       n_f;             /* f_profile points */
+    int32_t       n_lcfs;          /* LCFS polygon vertices */
+    const double* f_psin;          /* [n_f] */
+    const double* f_value;         /* [n_f] */
+    const double* lcfs_polygon;    /* [n_lcfs][2] (R,Z) */
+    double        b_vacuum_radius, b_vacuum_magnitude;
+} cb2_equilibrium;
+
+/* Shared context of all AXISYM_BLEND fields of a scene (generomak/plasma/plasma.py:96-129,233-272,610) */
+typedef struct cb2_axisym {
+    cb2_equilibrium eq;
+    int32_t         n_vertices, n_triangles;
+    const double*   vertices;     /* [n_vertices][2] (R,Z) */
+    const int32_t*  triangles;    /* [n_triangles][3] */
+    int32_t         n_core;       /* core psi_n grid */
+    int32_t         n_mask;       /* blend-mask table (Interpolator1DArray 'linear' of psi_n) */
+    const double*   core_psin;    /* [n_core] */
+    const double*   mask_x;       /* [n_mask] */
+    const double*   mask_y;       /* [n_mask] */
+} cb2_axisym;
+
+/* Species(element, charge, Maxwellian(n, T, v, mass)) — cherab/core/species.pyx:26-80 */
+typedef struct cb2_species {
+    int32_t          charge;
+    int32_t          _pad;
+    double           atomic_weight;   /* element.atomic_weight (amu) */
+    cb2_scalar_field density;
+    cb2_scalar_field temperature;
+    cb2_vector_field velocity;
+} cb2_species;
+
+/* ------------------------------------------------------------------------------------------------
+ * Rates in ADAS/OpenADAS repository shape.
+ * ---------------------------------------------------------------------------------------------- */
+/* ImpactExcitationPEC / RecombinationPEC data dict {'ne','te','rate'} (cherab/openadas/rates/pec.pyx:48-77,111-140).
+ * n_ne == 0 -> constant rate `constant` in W m^3 (mock AtomicData of core/tests/test_line_emission.py:32-88). */
+typedef struct cb2_rate2d {
+    int32_t       n_ne, n_te;
+    const double* ne;          /* [n_ne] m^-3 */
+    const double* te;          /* [n_te] eV */
+    const double* rate;        /* [n_ne][n_te] photon m^3 s^-1 (converted with PhotonToJ at scene build, conversion.py:44-52) */
+    double        constant;
+    int32_t       extrapolate; /* 1: 'nearest' (permit_extrapolation=True), 0: 'none' -> out-of-domain samples are counted and clamped */
+    int32_t       _pad;
+} cb2_rate2d;
+
+/* Free-free Gaunt factor table (cherab/core/atomic/gaunt.pyx:87-140; data/maxwellian_free_free_gaunt_factor.json) */
+typedef struct cb2_gaunt {
+    int32_t       n_u, n_gamma2;
+    const double* u;           /* [n_u] */
+    const double* gamma2;      /* [n_gamma2] */
+    const double* gaunt;       /* [n_u][n_gamma2] */
+} cb2_gaunt;
+
+/* ------------------------------------------------------------------------------------------------
+ * Line shapes (cherab/core/model/lineshape/ *.pyx)
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_lineshape_kind {
+    CB2_SHAPE_GAUSSIAN          = 0, /* GaussianLine            gaussian.pyx:122-139 */
+    CB2_SHAPE_MULTIPLET         = 1, /* MultipletLineShape      multiplet.pyx:93-117 */
+    CB2_SHAPE_ZEEMAN_TRIPLET    = 2, /* ZeemanTriplet           zeeman.pyx:113-162 */
+    CB2_SHAPE_PARAM_ZEEMAN      = 3, /* ParametrisedZeemanTriplet zeeman.pyx:219-268 */
+    CB2_SHAPE_ZEEMAN_MULTIPLET  = 4, /* ZeemanMultiplet         zeeman.pyx:308-365 */
+    CB2_SHAPE_STARK             = 5  /* StarkBroadenedLine      stark.pyx:251-348 */
+} cb2_lineshape_kind;
+
+typedef enum cb2_polarisation { CB2_POL_PI = 0, CB2_POL_SIGMA = 1, CB2_POL_NO = 2 } cb2_polarisation; /* zeeman.pyx:35-39 */
+
+typedef struct cb2_lineshape {
+    int32_t       kind;           /* cb2_lineshape_kind */
+    int32_t       polarisation;   /* cb2_polarisation (Zeeman family, Stark) */
+    double        param[3];       /* PARAM_ZEEMAN: alpha,beta,gamma; STARK: c_ij,a_ij,b_ij (interface.pyx:154-196) */
+    int32_t       n_components;   /* MULTIPLET: number of lines */
+    int32_t       n_b;            /* ZEEMAN_MULTIPLET: points of the |B| grid the component functions are tabulated on */
+    const double* multiplet;      /* MULTIPLET: [2][n_components] wavelengths then ratios (multiplet.pyx:75-88) */
+    /* ZEEMAN_MULTIPLET (atomic/zeeman.pyx:87-129): n_pi + n_sigma_plus + n_sigma_minus component functions, each
+       tabulated (linear, clamped) on b_grid: zeeman_wavelength[comp][n_b], zeeman_ratio[comp][n_b] */
+    int32_t       n_pi, n_sigma_plus, n_sigma_minus, _pad;
+    const double* b_grid;
+    const double* zeeman_wavelength;
+    const double* zeeman_ratio;
+} cb2_lineshape;
+
+/* ------------------------------------------------------------------------------------------------
+ * Emission models (cherab/core/model/plasma/ *.pyx)
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_model_kind {
+    CB2_MODEL_EXCITATION_LINE    = 0, /* ExcitationLine.emission     impact_excitation.pyx:78-100 */
+    CB2_MODEL_RECOMBINATION_LINE = 1, /* RecombinationLine.emission  recombination.pyx:78-100 */
+    CB2_MODEL_BREMSSTRAHLUNG     = 2  /* Bremsstrahlung.emission     bremsstrahlung.pyx:169-208 */
+} cb2_model_kind;
+
+typedef struct cb2_model {
+    int32_t       kind;            /* cb2_model_kind */
+    int32_t       species;         /* index into scene species: density n_target AND lineshape target species
+                                      (excitation: (element,charge); recombination: (element,charge+1) — recombination.pyx:113-121) */
+    double        wavelength;      /* rest wavelength nm (atomic_data.wavelength) */
+    double        atomic_weight;   /* line.element.atomic_weight (gaussian.pyx:137 uses the LINE's element) */
+    cb2_rate2d    pec;
+    cb2_lineshape shape;
+} cb2_model;
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene = Plasma node + models + integrator (cherab/core/plasma/node.pyx:201-554, material.pyx:25-63)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cb2_scene_desc {
+    int32_t            abi_version;         /* CB2_ABI_VERSION */
+    int32_t            n_species;
+    int32_t            n_models;
+    int32_t            min_samples;         /* NumericalIntegrator(step, min_samples=5) [raysect]; plasma/node.pyx:318 */
+    double             step;                /* m; default 0.001 */
+    cb2_spectral_grid  grid;
+    double             world_to_plasma[12]; /* row-major 3x4 affine: primitive/world -> plasma space (material.pyx:55-57) */
+    cb2_scalar_field   electron_density;
+    cb2_scalar_field   electron_temperature;
+    const cb2_species* species;             /* [n_species] plasma.composition, in composition order */
+    const cb2_model*   models;              /* [n_models]  plasma.models, in order */
+    const cb2_axisym*  axisym;              /* NULL unless some field is AXISYM_BLEND */
+    int32_t            b_field_kind;        /* 0: constant b_field[3]; 1: EFIT MagneticField of axisym->eq (efit.pyx:437-461) */
+    int32_t            brems_quadrature;    /* CUDA path: Gauss-Legendre points per bin for Bremsstrahlung (0 = choose from error bound) */
+    double             b_field[3];
+    cb2_gaunt          gaunt;               /* needed iff a BREMSSTRAHLUNG model is present */
+    /* oracle-only knobs of GaussianQuadrature (integrators1d.pyx:73-92): relative_tolerance, max_order, min_order */
+    double             quad_rtol;
+    int32_t            quad_max_order, quad_min_order;
+} cb2_scene_desc;
+
+/* Ray segments: what Raysect's tracer hands to VolumeIntegrator.integrate(start_point, end_point)
+ * (SURVEY 8(b) seam S1).  Ray r owns segments [seg_offset[r], seg_offset[r+1]); a segment is the
+ * interval [t0, t1] along origin + t*direction (direction normalised), in world space. */
+typedef struct cb2_rays {
+    int64_t        n_rays;
+    int64_t        n_segments;
+    const double*  origin;      /* [n_rays][3] */
+    const double*  direction;   /* [n_rays][3] unit vectors, observer -> scene */
+    const int64_t* seg_offset;  /* [n_rays+1] */
+    const double*  seg_t0;      /* [n_segments] */
+    const double*  seg_t1;      /* [n_segments] */
+} cb2_rays;
+
+/* work counters: exactly the units of SURVEY 8(d) */
+typedef struct cb2_stats {
+    int64_t samples;              /* emission_function evaluations: sum over segments of intervals+1 */
+    int64_t gaussian_bin_evals;   /* E: sum over (sample, Gaussian component) of (end-start)+1 */
+    int64_t lorentzian_bin_evals; /* L */
+    int64_t brems_bin_evals;      /* samples with ne,te>0 times bins */
+    int64_t rt_steps;             /* ray-transfer midpoint steps */
+    int64_t out_of_domain;        /* samples clamped where the reference would raise ValueError ('none' extrapolation) */
+} cb2_stats;
+
+typedef struct cb2_scene cb2_scene; /* opaque, owns device tables */
+
+/* Library identification / error channel */
+int         cb2_abi_version(void);
+const char* cb2_last_error(void);
+/* number of CUDA devices visible, <0 on error (never falls back to the CPU) */
+int         cb2_device_count(void);
+
+/* Build device-resident tables from a flattened scene.  Replaces PlasmaMaterial.__init__ + the lazy
+ * _populate_cache of every model (plasma/material.pyx:37-46; impact_excitation.pyx:102-128). */
+int cb2_scene_create(const cb2_scene_desc* desc, int device, cb2_scene** out);
+int cb2_scene_destroy(cb2_scene* scene);
+
+/* Emission render, HOST buffers (the reference-facing call): for every ray, trapezium-integrate the emission of all
+ * models over each segment exactly as NumericalIntegrator.integrate [raysect] does
+ * (intervals = max(min_samples-1, ceil(L/step)), samples at t0 + k*L/intervals), and write
+ *     out[r][bin] = (accumulate ? out[r][bin] : 0) + scale * spectrum_r[bin]     W/m^2/sr/nm
+ * out is double[n_rays][bins] if out_f64 else float[n_rays][bins].  Host<->device copies happen inside. */
+int cb2_emission_render(cb2_scene* scene, const cb2_rays* rays, void* out, int out_f64,
+                        double scale, int accumulate, cb2_stats* stats);
+
+/* Same, DEVICE buffers (torch tensors): every pointer in `rays` and `out` is device memory on the scene's device;
+ * launches on `stream` (a cudaStream_t passed as void*), does not synchronise. stats may be NULL;
+ * if not NULL it must be device memory (filled asynchronously). */
+int cb2_emission_render_device(cb2_scene* scene, const cb2_rays* rays, void* out, int out_f64,
+                               double scale, int accumulate, cb2_stats* stats_dev, void* stream);
+
+/* Per-sample plasma state, for parity tests of the flattened function tree:
+ * points[n][3] (world space) -> out[n][n_quantities] with quantity order
+ * ne, te, then per species (density, temperature, vx, vy, vz), then Bx, By, Bz.  HOST buffers. */
+int cb2_sample_state(cb2_scene* scene, const double* points, int64_t n, double* out);
+int cb2_state_width(const cb2_scene* scene);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray transfer (cherab/tools/raytransfer/emitters.pyx:88-224, raytransfer.py:183-268)
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_rt_kind { CB2_RT_CYLINDRICAL = 0, CB2_RT_CARTESIAN = 1 } cb2_rt_kind;
+
+typedef struct cb2_rt_desc {
+    int32_t        abi_version;
+    int32_t        kind;              /* cb2_rt_kind */
+    int32_t        grid_shape[3];     /* (n_r, n_phi, n_z) or (nx, ny, nz) — RayTransferEmitter.grid_shape emitters.pyx:261-266 */
+    int32_t        min_samples;       /* RayTransferIntegrator(step, min_samples=2) emitters.pyx:48 */
+    double         grid_steps[3];     /* (dr, dphi [deg], dz) or (dx, dy, dz) */
+    double         rmin;              /* cylindrical: radius_inner */
+    double         period;            /* cylindrical: degrees */
+    double         step;              /* integration step m (raytransfer.py:195,262) */
+    double         world_to_local[12];/* row-major 3x4 affine world -> primitive-local (z in [0,height]) */
+    const int32_t* voxel_map;         /* [shape0][shape1][shape2], -1 = unmapped */
+    int32_t        bins;              /* voxel_map.max()+1 */
+    int32_t        _pad;
+} cb2_rt_desc;
+
+typedef struct cb2_rt_scene cb2_rt_scene;
+
+int cb2_rt_create(const cb2_rt_desc* desc, int device, cb2_rt_scene** out);
+int cb2_rt_destroy(cb2_rt_scene* scene);
+
+/* Dense geometry-matrix rows, HOST buffers: out[r][source] (+)= path length (m) of ray r in light source `source`
+ * (the Spectrum the reference integrator fills, emitters.pyx:137-150).  Only for small `bins`. */
+int cb2_rt_render_dense(cb2_rt_scene* scene, const cb2_rays* rays, double* out, int accumulate, cb2_stats* stats);
+
+/* Sparse (CSR) rows, HOST buffers.  row_offset[n_rays+1]; columns/lengths capacity `capacity` entries.
+ * Within a row every source appears once, in order of first visit.  Returns CB2_ERR_OVERFLOW (and the required
+ * capacity in row_offset[n_rays]) if capacity is too small. */
+int cb2_rt_render_csr(cb2_rt_scene* scene, const cb2_rays* rays, int64_t* row_offset,
+                      int32_t* columns, double* lengths, int64_t capacity, cb2_stats* stats);
+
+/* DEVICE buffers variant: rays/out pointers are device memory; row_offset[n_rays+1] int64, columns int32,
+ * lengths float64 on device; launches on `stream`; *nnz_host receives the total after an internal sync on the stream. */
+int cb2_rt_render_csr_device(cb2_rt_scene* scene, const cb2_rays* rays, int64_t* row_offset,
+                             int32_t* columns, double* lengths, int64_t capacity, int64_t* nnz_host,
+                             cb2_stats* stats_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Oracle (libcb2_oracle.so) — same descriptors, fp64 scalar restatement of the reference. TEST INFRASTRUCTURE.
+ * ---------------------------------------------------------------------------------------------- */
+int         cb2o_abi_version(void);
+const char* cb2o_last_error(void);
+int cb2o_emission_render(const cb2_scene_desc* desc, const cb2_rays* rays, double* out,
+                         double scale, int accumulate, int n_threads, cb2_stats* stats);
+int cb2o_sample_state(const cb2_scene_desc* desc, const double* points, int64_t n, double* out);
+int cb2o_state_width(const cb2_scene_desc* desc);
+int cb2o_rt_render_dense(const cb2_rt_desc* desc, const cb2_rays* rays, double* out, int accumulate,
+                         int n_threads, cb2_stats* stats);
+/* building blocks exposed so the reference's own unit tests can be replayed against the oracle */
+int cb2o_add_gaussian_line(double radiance, double wavelength, double sigma,
+                           const cb2_spectral_grid* grid, double* samples);              /* gaussian.pyx:40-90 */
+int cb2o_add_lorentzian_line(double radiance, double wavelength, double lambda_1_2,
+                             const cb2_spectral_grid* grid, double* samples,
+                             double rtol, int min_order, int max_order);                  /* stark.pyx:88-147 */
+double cb2o_interp1d_cubic(const double* x, const double* f, int n, double px, int extrapolate);       /* raysect Interpolator1DArray 'cubic' */
+double cb2o_interp2d_cubic(const double* x, const double* y, const double* f, int nx, int ny,
+                           double px, double py, int extrapolate);                                       /* raysect Interpolator2DArray 'cubic' */
+double cb2o_gauss_legendre(double (*fn)(double, void*), void* ctx, double a, double b,
+                           double rtol, int min_order, int max_order);                                   /* integrators1d.pyx:189-224 */
+double cb2o_gaunt_factor(const cb2_gaunt* g, double z, double te, double wavelength);                   /* gaunt.pyx:109-140 */
+double cb2o_pec_evaluate(const cb2_rate2d* pec, double wavelength, double ne, double te);               /* pec.pyx:70-77 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHERAB_B200_H */

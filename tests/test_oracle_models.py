@@ -1,0 +1,177 @@
+"""Pin the oracle's emission models + integrators against the reference's known-answer tests:
+cherab/core/tests/test_line_emission.py:99-200 (slab, constant PEC), test_bremsstrahlung.py:41-95,
+cherab/core/math/tests/test_integrators.py:68-76."""
+import ctypes as C
+
+import numpy as np
+from scipy import constants as const
+from scipy.special import erf, roots_legendre
+
+import core_b200 as cb
+from core_b200 import _abi
+from core_b200.slab import build_constant_slab_plasma
+from oracle import oracle
+from helpers import ATOMIC_MASS, ELEMENTARY_CHARGE, SPEED_OF_LIGHT
+
+
+class MockAtomicData(cb.AtomicData):
+    """core/tests/test_line_emission.py:32-97."""
+
+    def impact_excitation_pec(self, ion, charge, transition):
+        return cb.ConstantRate(1.4e-39)
+
+    def recombination_pec(self, ion, charge, transition):
+        return cb.ConstantRate(8.e-40)
+
+    def wavelength(self, ion, charge, transition):
+        return 529.27
+
+
+def _slab():
+    plasma = build_constant_slab_plasma(length=1.2, width=1, height=1, electron_density=1e19, electron_temperature=1000.,
+                                        plasma_species=[(cb.carbon, 5, 2.e18, 800., (0, 0, 0)), (cb.carbon, 6, 3.e18, 900., (0, 0, 0))],
+                                        b_field=(0, 10., 0))
+    plasma.atomic_data = MockAtomicData()
+    return plasma
+
+
+def _trace(plasma, lo, hi, bins):
+    fs = cb.flatten_scene(plasma, lo, hi, bins)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    assert rays.n_segments == 1 and abs(rays.seg_t1[0] - rays.seg_t0[0] - 1.2) < 1e-12
+    return oracle.emission_render(fs, rays)
+
+
+def _gauss_ref(radiance, wavelength, temperature, weight, lo, hi, bins):
+    sigma = np.sqrt(temperature * ELEMENTARY_CHARGE / (weight * ATOMIC_MASS)) * wavelength / SPEED_OF_LIGHT
+    wl, delta = np.linspace(lo, hi, bins + 1, retstep=True)
+    erfs = erf((wl - wavelength) / (np.sqrt(2.) * sigma))
+    return 0.5 * radiance * (erfs[1:] - erfs[:-1]) / delta
+
+
+def test_excitation_line_default_lineshape():
+    plasma = _slab()
+    line = cb.Line(cb.carbon, 5, (8, 7))
+    plasma.models = [cb.ExcitationLine(line)]
+    got, _ = _trace(plasma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    radiance = 0.25 / np.pi * 1.4e-39 * 2.e18 * 1e19 * 1.2
+    ref = _gauss_ref(radiance, 529.27, 800., cb.carbon.atomic_weight, 529.27 - 1.5, 529.27 + 1.5, 512)
+    assert np.max(np.abs(got[0] - ref)) < 1e-8
+    assert np.max(np.abs(got[0] - ref)) < 1e-12 * ref.max()
+
+
+def test_recombination_line_uses_charge_plus_one():
+    plasma = _slab()
+    line = cb.Line(cb.carbon, 5, (8, 7))
+    plasma.models = [cb.RecombinationLine(line)]
+    got, _ = _trace(plasma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    radiance = 0.25 / np.pi * 8.e-40 * 3.e18 * 1e19 * 1.2   # density AND temperature of C6+ (recombination.pyx:113-128)
+    ref = _gauss_ref(radiance, 529.27, 900., cb.carbon.atomic_weight, 529.27 - 1.5, 529.27 + 1.5, 512)
+    assert np.max(np.abs(got[0] - ref)) < 1e-12 * ref.max()
+
+
+def test_models_add_not_overwrite():
+    plasma = _slab()
+    line = cb.Line(cb.carbon, 5, (8, 7))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    both, _ = _trace(plasma, 528, 531, 128)
+    plasma.models = [cb.ExcitationLine(line)]
+    a, _ = _trace(plasma, 528, 531, 128)
+    plasma.models = [cb.RecombinationLine(line)]
+    b, _ = _trace(plasma, 528, 531, 128)
+    assert np.allclose(both, a + b, rtol=1e-13, atol=0)
+
+
+def test_missing_species_raises_runtime_error():
+    plasma = _slab()
+    plasma.models = [cb.ExcitationLine(cb.Line(cb.carbon, 3, (8, 7)))]
+    try:
+        cb.flatten_scene(plasma, 528, 531, 16)
+    except RuntimeError as e:
+        assert "does not contain the ion species" in str(e)
+    else:
+        raise AssertionError("expected RuntimeError (impact_excitation.pyx:110-118)")
+
+
+def _gauss_legendre_scipy(f, a, b, rtol=1e-5, min_order=1, max_order=50):
+    """integrators1d.pyx:189-224 restated with scipy.special.roots_legendre."""
+    old, new = np.inf, 0.0
+    c, d = 0.5 * (a + b), 0.5 * (b - a)
+    for order in range(min_order, max_order + 1):
+        x, w = roots_legendre(order)
+        new = d * sum(wi * f(c + d * xi) for xi, wi in zip(x, w))
+        err = abs(new - old)
+        old = new
+        if err < rtol * abs(new):
+            break
+    return new
+
+
+def test_gaussian_quadrature_erf():
+    # core/math/tests/test_integrators.py:68-76
+    cb_t = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+    fn = cb_t(lambda x, ctx: 2 / np.sqrt(np.pi) * np.exp(-x * x))
+    l = oracle.lib()
+    l.cb2o_gauss_legendre.restype = C.c_double
+    l.cb2o_gauss_legendre.argtypes = [cb_t, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    val = l.cb2o_gauss_legendre(fn, None, -0.5, 3.0, 1e-8, 1, 50)
+    assert abs(val - (erf(3.0) - erf(-0.5))) < 1e-8
+    ref = _gauss_legendre_scipy(lambda x: 2 / np.sqrt(np.pi) * np.exp(-x * x), -0.5, 3.0, 1e-8)
+    assert abs(val - ref) < 1e-14
+
+
+def _gaunt_struct():
+    u, g2, gff = (np.ascontiguousarray(a, dtype=np.float64) for a in cb.AtomicData().free_free_gaunt_factor())
+    g = _abi.Gaunt(u.size, g2.size, u.ctypes.data_as(_abi.c_double_p), g2.ctypes.data_as(_abi.c_double_p),
+                   gff.ctypes.data_as(_abi.c_double_p))
+    return g, (u, g2, gff)
+
+
+def test_gaunt_factor_limits_and_table():
+    g, (u, g2, gff) = _gaunt_struct()
+    l = oracle.lib()
+    # knots are reproduced exactly by a Hermite interpolant
+    for i in (2, 4, 6):
+        for j in (10, 40, 80):
+            te = 1.0 * 13.605693122994 / g2[j]                 # z = 1 -> gamma2 = Ry/te
+            wl = 1239.8419738620933 / (te * u[i])
+            assert abs(l.cb2o_gaunt_factor(C.byref(g), 1.0, te, wl) - gff[i, j]) < 1e-9
+    assert l.cb2o_gaunt_factor(C.byref(g), 0.0, 10.0, 500.0) == 0.0                    # gaunt.pyx:123
+    assert l.cb2o_gaunt_factor(C.byref(g), 1.0, 1e-4, 1e3) == 1.0                      # classical limit :130
+    te, wl = 1e12, 500.0                                                              # Born limit :134
+    uu = 1239.8419738620933 / (te * wl)
+    assert abs(l.cb2o_gaunt_factor(C.byref(g), 1.0, te, wl) - np.sqrt(3) / np.pi * (np.log(4 / uu) - 0.5772156649015329)) < 1e-12
+
+
+def test_bremsstrahlung_slab():
+    # core/tests/test_bremsstrahlung.py:41-95 (D+ 1e19, N7+ 1e18, Te 2 keV, 400-800 nm, 128 bins, 1 m slab)
+    plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=1e19, electron_temperature=2000.,
+                                        plasma_species=[(cb.deuterium, 1, 1.e19, 2000., (0, 0, 0)), (cb.nitrogen, 7, 1.e18, 2000., (0, 0, 0))])
+    plasma.atomic_data = cb.AtomicData()
+    plasma.models = [cb.Bremsstrahlung()]
+    fs = cb.flatten_scene(plasma, 400., 800., 128)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    got, stats = oracle.emission_render(fs, rays)
+    assert stats["brems_bin_evals"] == 128 * 1001
+
+    brems_const = (const.e ** 2 * 0.25 / np.pi / const.epsilon_0) ** 3
+    brems_const *= 32 * np.pi ** 2 / (3 * np.sqrt(3) * const.m_e ** 2 * const.c ** 3)
+    brems_const *= np.sqrt(2 * const.m_e / (np.pi * const.e))
+    brems_const *= const.c * 1e9 * 0.25 / np.pi
+    exp_factor = const.h * const.c * 1.e9 / const.e
+    ne = te = None
+    ne, te = 1e19, 2000.
+    g, _keep = _gaunt_struct()
+    l = oracle.lib()
+
+    def brems_func(wvl):
+        s = 0
+        for z, ni in ((1, 1e19), (7, 1e18)):
+            s += ni * l.cb2o_gaunt_factor(C.byref(g), float(z), te, wvl) * z * z
+        return brems_const * s * ne / (np.sqrt(te) * wvl * wvl) * np.exp(-exp_factor / (te * wvl))
+
+    wl, delta = np.linspace(400., 800., 129, retstep=True)
+    ref = np.array([_gauss_legendre_scipy(brems_func, wl[i], wl[i + 1]) / delta for i in range(128)])
+    assert np.max(np.abs(got[0] - ref)) < 1e-10
+    # scipy.constants (CODATA 2022) vs the reference's hard-coded CODATA 2018 values differ by 4e-9 relative
+    assert np.max(np.abs(got[0] / ref - 1)) < 2e-8
