@@ -1,0 +1,918 @@
+// cb2_api.cu — C ABI entry points and the host-side scene builder of libcherab_b200.so.
+//
+// cb2_scene_create turns the flat descriptor (include/cherab_b200.h) into device-resident fp32 tables: this is the
+// "interpolators flattened into device-resident tables" step of the north star.  The cubic tables restate Raysect's
+// Interpolator1DArray/2DArray 'cubic' (local Hermite, 2nd-order finite-difference knot derivatives — SURVEY
+// Appendix B.4); the coefficients are computed here in fp64 and only then rounded to fp32.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cb2_internal.h"
+
+// ------------------------------------------------------------------------------------------------------------------
+// error channel
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int cb2_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cb2_cuda_check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return CB2_OK;
+    return cb2_fail(CB2_ERR_CUDA, "CUDA error %s in %s (libcherab_b200 has no CPU fallback)", cudaGetErrorString(e), what);
+}
+
+extern "C" const char* cb2_last_error(void) { return g_err; }
+extern "C" int cb2_abi_version(void) { return CB2_ABI_VERSION; }
+extern "C" int cb2_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cb2_cuda_check(e, "cudaGetDeviceCount");
+        return -1;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device arena
+// ------------------------------------------------------------------------------------------------------------------
+struct Arena {
+    std::vector<void*> ptrs;
+    int rc = CB2_OK;
+    template <typename T>
+    const T* upload(const std::vector<T>& v) {
+        if (rc != CB2_OK) return nullptr;
+        void* p = nullptr;
+        size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+        rc = cb2_cuda_check(cudaMalloc(&p, bytes), "cudaMalloc(table)");
+        if (rc != CB2_OK) return nullptr;
+        ptrs.push_back(p);
+        if (!v.empty()) rc = cb2_cuda_check(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(table)");
+        return (const T*)p;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// cubic table construction (Raysect semantics restated, fp64)
+// ------------------------------------------------------------------------------------------------------------------
+// first derivative at knot i of samples f[i*stride] on an uneven grid: 3-point 2nd-order in the interior,
+// one-sided first difference at the ends
+static double d1(const double* x, const double* f, int n, int stride, int i) {
+    if (n < 2) return 0.0;
+    if (i == 0) return (f[stride] - f[0]) / (x[1] - x[0]);
+    if (i == n - 1) return (f[(size_t)(n - 1) * stride] - f[(size_t)(n - 2) * stride]) / (x[n - 1] - x[n - 2]);
+    const double a = x[i] - x[i - 1], b = x[i + 1] - x[i];
+    const double fm = f[(size_t)(i - 1) * stride], f0 = f[(size_t)i * stride], fp = f[(size_t)(i + 1) * stride];
+    return (a * a * fp - b * b * fm + (b * b - a * a) * f0) / (a * b * (a + b));
+}
+
+// mixed derivative at knot (i,j): four-corner difference over the neighbours that exist
+static double d2(const double* x, const double* y, const double* f, int nx, int ny, int i, int j) {
+    const int i0 = std::max(i - 1, 0), i1 = std::min(i + 1, nx - 1), j0 = std::max(j - 1, 0), j1 = std::min(j + 1, ny - 1);
+    if (i0 == i1 || j0 == j1) return 0.0;
+    return (f[(size_t)i1 * ny + j1] - f[(size_t)i1 * ny + j0] - f[(size_t)i0 * ny + j1] + f[(size_t)i0 * ny + j0]) /
+           ((x[i1] - x[i0]) * (y[j1] - y[j0]));
+}
+
+static bool is_uniform(const double* x, int n) {
+    if (n < 2) return true;
+    const double h = (x[n - 1] - x[0]) / (n - 1);
+    for (int i = 0; i < n; i++)
+        if (fabs(x[i] - (x[0] + i * h)) > 1e-9 * fabs(h)) return false;
+    return true;
+}
+
+// Hermite basis matrix: p(t) = sum_k a_k t^k with (f0, f1, d0, d1) -> a = H * (f0, f1, d0, d1)
+static void hermite_coef(double f0, double f1, double e0, double e1, double a[4]) {
+    a[0] = f0;
+    a[1] = e0;
+    a[2] = 3.0 * (f1 - f0) - 2.0 * e0 - e1;
+    a[3] = 2.0 * (f0 - f1) + e0 + e1;
+}
+
+static DevTable1D make_knots1d(Arena& A, const double* x, int n) {
+    DevTable1D t;
+    memset(&t, 0, sizeof t);
+    t.n = n;
+    std::vector<float> xs(n), iw(std::max(n - 1, 1));
+    for (int i = 0; i < n; i++) xs[i] = (float)x[i];
+    for (int i = 0; i + 1 < n; i++) iw[i] = (float)(1.0 / (x[i + 1] - x[i]));
+    t.xmin = (float)x[0];
+    t.xmax = (float)x[n - 1];
+    t.x = A.upload(xs);
+    t.inv_w = A.upload(iw);
+    return t;
+}
+
+static const float4* make_coef1d(Arena& A, const double* x, const double* f, int n, double scale) {
+    std::vector<float4> c(std::max(n - 1, 1));
+    if (n == 1) c[0] = make_float4((float)(f[0] * scale), 0, 0, 0);
+    for (int i = 0; i + 1 < n; i++) {
+        const double h = x[i + 1] - x[i];
+        double a[4];
+        hermite_coef(f[i], f[i + 1], d1(x, f, n, 1, i) * h, d1(x, f, n, 1, i + 1) * h, a);
+        c[i] = make_float4((float)(a[0] * scale), (float)(a[1] * scale), (float)(a[2] * scale), (float)(a[3] * scale));
+    }
+    return A.upload(c);
+}
+
+static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const double* f, int nx, int ny) {
+    DevTable2D t;
+    memset(&t, 0, sizeof t);
+    t.nx = nx;
+    t.ny = ny;
+    std::vector<float> xs(nx), ys(ny), iwx(std::max(nx - 1, 1)), iwy(std::max(ny - 1, 1));
+    for (int i = 0; i < nx; i++) xs[i] = (float)x[i];
+    for (int j = 0; j < ny; j++) ys[j] = (float)y[j];
+    for (int i = 0; i + 1 < nx; i++) iwx[i] = (float)(1.0 / (x[i + 1] - x[i]));
+    for (int j = 0; j + 1 < ny; j++) iwy[j] = (float)(1.0 / (y[j + 1] - y[j]));
+    t.uniform = is_uniform(x, nx) && is_uniform(y, ny);
+    t.x0 = (float)x[0];
+    t.y0 = (float)y[0];
+    t.inv_dx = (float)((nx - 1) / (x[nx - 1] - x[0]));
+    t.inv_dy = (float)((ny - 1) / (y[ny - 1] - y[0]));
+    t.xmin = (float)x[0];
+    t.xmax = (float)x[nx - 1];
+    t.ymin = (float)y[0];
+    t.ymax = (float)y[ny - 1];
+    // knot derivatives
+    std::vector<double> fx((size_t)nx * ny), fy((size_t)nx * ny), fxy((size_t)nx * ny);
+    for (int i = 0; i < nx; i++)
+        for (int j = 0; j < ny; j++) {
+            fx[(size_t)i * ny + j] = d1(x, f + j, nx, ny, i);
+            fy[(size_t)i * ny + j] = d1(y, f + (size_t)i * ny, ny, 1, j);
+            fxy[(size_t)i * ny + j] = d2(x, y, f, nx, ny, i, j);
+        }
+    std::vector<float4> coef((size_t)(nx - 1) * (ny - 1) * 4);
+    for (int i = 0; i + 1 < nx; i++)
+        for (int j = 0; j + 1 < ny; j++) {
+            const double hx = x[i + 1] - x[i], hy = y[j + 1] - y[j];
+            // For every power of t, a Hermite cubic in u: first reduce along x for the four "u-quantities"
+            // (value and u-derivative at u=0 and u=1), then along u.
+            double cx[4][4];  // [quantity q][power of t]; q: 0 f(.,j) 1 f(.,j+1) 2 fy*hy(.,j) 3 fy*hy(.,j+1)
+            for (int q = 0; q < 4; q++) {
+                const int jj = j + (q & 1);
+                double v0, v1, e0, e1;
+                if (q < 2) {
+                    v0 = f[(size_t)i * ny + jj];
+                    v1 = f[(size_t)(i + 1) * ny + jj];
+                    e0 = fx[(size_t)i * ny + jj] * hx;
+                    e1 = fx[(size_t)(i + 1) * ny + jj] * hx;
+                } else {
+                    v0 = fy[(size_t)i * ny + jj] * hy;
+                    v1 = fy[(size_t)(i + 1) * ny + jj] * hy;
+                    e0 = fxy[(size_t)i * ny + jj] * hx * hy;
+                    e1 = fxy[(size_t)(i + 1) * ny + jj] * hx * hy;
+                }
+                hermite_coef(v0, v1, e0, e1, cx[q]);
+            }
+            for (int p = 0; p < 4; p++) {  // power of t
+                double a[4];
+                hermite_coef(cx[0][p], cx[1][p], cx[2][p], cx[3][p], a);
+                coef[((size_t)i * (ny - 1) + j) * 4 + p] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+            }
+        }
+    t.x = A.upload(xs);
+    t.y = A.upload(ys);
+    t.inv_wx = A.upload(iwx);
+    t.inv_wy = A.upload(iwy);
+    t.coef = A.upload(coef);
+    return t;
+}
+
+// np.gradient(f, edge_order=2) along a strided line with unit spacing (efit.pyx:187-189)
+static void np_gradient_unit(const double* f, int n, int stride, double* out, int ostride) {
+    for (int i = 0; i < n; i++) {
+        double v;
+        if (n == 1) v = 0;
+        else if (n == 2) v = f[stride] - f[0];
+        else if (i == 0) v = -(3.0 * f[0] - 4.0 * f[stride] + f[2 * (size_t)stride]) / 2.0;
+        else if (i == n - 1) v = (3.0 * f[(size_t)(n - 1) * stride] - 4.0 * f[(size_t)(n - 2) * stride] + f[(size_t)(n - 3) * stride]) / 2.0;
+        else v = (f[(size_t)(i + 1) * stride] - f[(size_t)(i - 1) * stride]) / 2.0;
+        out[(size_t)i * ostride] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// field conversion
+// ------------------------------------------------------------------------------------------------------------------
+static int convert_scalar(Arena& A, const cb2_scalar_field& f, const cb2_axisym* ax, double scale, DevScalar& o) {
+    memset(&o, 0, sizeof o);
+    o.kind = f.kind;
+    switch (f.kind) {
+    case CB2_FIELD_CONSTANT: o.c[0] = (float)(f.c[0] * scale); break;
+    case CB2_FIELD_GAUSSIAN_VOLUME:
+        if (f.c[2] <= 0) return cb2_fail(CB2_ERR_VALUE, "GaussianVolume sigma must be positive");
+        o.c[0] = (float)(f.c[0] * scale);
+        o.c[1] = (float)(f.c[1] * scale);
+        o.c[2] = (float)(-1.0 / (2.0 * f.c[2] * f.c[2]) * 1.4426950408889634);  // exponent coefficient for exp2
+        o.c[3] = (float)f.c[3];
+        o.c[4] = (float)f.c[4];
+        o.c[5] = (float)f.c[5];
+        break;
+    case CB2_FIELD_SLAB_ION:
+        o.c[0] = (float)(f.c[0] * scale);
+        o.c[1] = (float)(f.c[1] * scale);
+        o.c[2] = (float)f.c[2];
+        o.c[3] = (float)f.c[3];
+        o.c[4] = (float)(1.0 / f.c[4]);
+        break;
+    case CB2_FIELD_SLAB_NEUTRAL:
+        o.c[0] = (float)(f.c[0] * scale);
+        o.c[1] = (float)(-1.0 / (2.0 * f.c[1] * f.c[1]) * 1.4426950408889634);
+        break;
+    case CB2_FIELD_AXISYM_BLEND: {
+        if (!ax) return cb2_fail(CB2_ERR_RUNTIME, "AXISYM_BLEND field without an axisym context");
+        if (f.edge) {
+            std::vector<float> e(ax->n_triangles);
+            for (int i = 0; i < ax->n_triangles; i++) e[i] = (float)(f.edge[i] * scale);
+            o.edge = A.upload(e);
+        }
+        if (f.core) o.core = make_coef1d(A, ax->core_psin, f.core, ax->n_core, scale);
+        break;
+    }
+    default: return cb2_fail(CB2_ERR_TYPE, "unsupported scalar field kind %d", f.kind);
+    }
+    return A.rc;
+}
+
+static int convert_vector(Arena& A, const cb2_vector_field& f, const cb2_axisym* ax, DevVector& o) {
+    memset(&o, 0, sizeof o);
+    o.kind = f.kind;
+    o.c[0] = (float)f.c[0];
+    o.c[1] = (float)f.c[1];
+    o.c[2] = (float)f.c[2];
+    if (f.kind == CB2_FIELD_CONSTANT) return CB2_OK;
+    if (f.kind != CB2_FIELD_AXISYM_BLEND) return cb2_fail(CB2_ERR_TYPE, "unsupported vector field kind %d", f.kind);
+    if (!ax) return cb2_fail(CB2_ERR_RUNTIME, "AXISYM_BLEND field without an axisym context");
+    if (f.core_vtor) o.vtor = make_coef1d(A, ax->core_psin, f.core_vtor, ax->n_core, 1.0);
+    if (f.core_vpol) o.vpol = make_coef1d(A, ax->core_psin, f.core_vpol, ax->n_core, 1.0);
+    if (f.core_vnorm) o.vnorm = make_coef1d(A, ax->core_psin, f.core_vnorm, ax->n_core, 1.0);
+    return A.rc;
+}
+
+static bool vec_has_pol(const cb2_vector_field& f, const cb2_axisym* ax) {
+    if (f.kind != CB2_FIELD_AXISYM_BLEND || !ax) return false;
+    for (int which = 0; which < 2; which++) {
+        const double* p = which ? f.core_vnorm : f.core_vpol;
+        if (!p) continue;
+        for (int i = 0; i < ax->n_core; i++)
+            if (p[i] != 0.0) return true;
+    }
+    return false;
+}
+
+static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
+    memset(&o, 0, sizeof o);
+    o.present = 1;
+    const cb2_equilibrium& e = ax.eq;
+    const int nr = e.nr, nz = e.nz;
+    if (nr < 2 || nz < 2) return cb2_fail(CB2_ERR_VALUE, "equilibrium grid must be at least 2x2");
+    std::vector<double> psin((size_t)nr * nz), dr((size_t)nr * nz), dz((size_t)nr * nz), dr_di(nr), dz_di(nz);
+    for (size_t k = 0; k < psin.size(); k++) psin[k] = (e.psi[k] - e.psi_axis) / (e.psi_lcfs - e.psi_axis);
+    np_gradient_unit(e.r, nr, 1, dr_di.data(), 1);
+    np_gradient_unit(e.z, nz, 1, dz_di.data(), 1);
+    for (int j = 0; j < nz; j++) np_gradient_unit(e.psi + j, nr, nz, dr.data() + j, nz);
+    for (int i = 0; i < nr; i++) np_gradient_unit(e.psi + (size_t)i * nz, nz, 1, dz.data() + (size_t)i * nz, 1);
+    for (int i = 0; i < nr; i++)
+        for (int j = 0; j < nz; j++) {
+            dr[(size_t)i * nz + j] *= 1.0 / dr_di[i];
+            dz[(size_t)i * nz + j] *= 1.0 / dz_di[j];
+        }
+    o.psin = make_table2d(A, e.r, e.z, psin.data(), nr, nz);
+    o.dpsi_dr = make_table2d(A, e.r, e.z, dr.data(), nr, nz);
+    o.dpsi_dz = make_table2d(A, e.r, e.z, dz.data(), nr, nz);
+    o.core = make_knots1d(A, ax.core_psin, ax.n_core);
+    o.fprof = make_knots1d(A, e.f_psin, e.n_f);
+    o.fprof_coef = make_coef1d(A, e.f_psin, e.f_value, e.n_f, 1.0);
+    o.b_vac = (float)(e.b_vacuum_magnitude * e.b_vacuum_radius);
+    // polygon edges (even-odd crossing test, mask.pyx:53-67)
+    o.n_poly = e.n_lcfs;
+    std::vector<float4> edges(std::max(e.n_lcfs, 1));
+    double pxmin = INFINITY, pxmax = -INFINITY, pymin = INFINITY, pymax = -INFINITY;
+    for (int i = 0, j = e.n_lcfs - 1; i < e.n_lcfs; j = i++) {
+        const double xi = e.lcfs_polygon[2 * i], yi = e.lcfs_polygon[2 * i + 1];
+        const double xj = e.lcfs_polygon[2 * j], yj = e.lcfs_polygon[2 * j + 1];
+        const double slope = (yj != yi) ? (xj - xi) / (yj - yi) : 0.0;
+        edges[i] = make_float4((float)xi, (float)yi, (float)yj, (float)slope);
+        pxmin = fmin(pxmin, xi); pxmax = fmax(pxmax, xi); pymin = fmin(pymin, yi); pymax = fmax(pymax, yi);
+    }
+    o.poly = A.upload(edges);
+    o.poly_xmin = (float)pxmin; o.poly_xmax = (float)pxmax; o.poly_ymin = (float)pymin; o.poly_ymax = (float)pymax;
+    if (ax.n_mask < 1 || ax.n_mask > 8) return cb2_fail(CB2_ERR_VALUE, "blend mask table must have 1..8 points");
+    o.n_mask = ax.n_mask;
+    for (int i = 0; i < ax.n_mask; i++) { o.mask_x[i] = (float)ax.mask_x[i]; o.mask_y[i] = (float)ax.mask_y[i]; }
+    // mesh buckets
+    o.n_tri = ax.n_triangles;
+    if (ax.n_triangles > 0) {
+        double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        for (int i = 0; i < ax.n_vertices; i++) {
+            xmin = fmin(xmin, ax.vertices[2 * i]); xmax = fmax(xmax, ax.vertices[2 * i]);
+            ymin = fmin(ymin, ax.vertices[2 * i + 1]); ymax = fmax(ymax, ax.vertices[2 * i + 1]);
+        }
+        const double aspect = (ymax - ymin) / (xmax - xmin);
+        int gx = (int)ceil(sqrt(2.0 * ax.n_triangles / aspect));
+        gx = std::min(std::max(gx, 8), 1024);
+        int gy = std::min(std::max((int)ceil(gx * aspect), 8), 2048);
+        o.gx = gx; o.gy = gy;
+        o.mx0 = (float)xmin; o.my0 = (float)ymin;
+        const double icx = gx / (xmax - xmin) * (1.0 - 1e-7), icy = gy / (ymax - ymin) * (1.0 - 1e-7);
+        o.inv_cx = (float)icx; o.inv_cy = (float)icy;
+        std::vector<int> count((size_t)gx * gy + 1, 0), start((size_t)gx * gy + 1, 0), tris;
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) {
+                int acc = 0;
+                for (size_t k = 0; k < (size_t)gx * gy; k++) { start[k] = acc; acc += count[k]; count[k] = 0; }
+                start[(size_t)gx * gy] = acc;
+                tris.resize(std::max(acc, 1));
+            }
+            for (int t = 0; t < ax.n_triangles; t++) {
+                const int32_t* tr = ax.triangles + 3 * t;
+                double txmin = INFINITY, txmax = -INFINITY, tymin = INFINITY, tymax = -INFINITY;
+                for (int k = 0; k < 3; k++) {
+                    if (tr[k] < 0 || tr[k] >= ax.n_vertices) return cb2_fail(CB2_ERR_VALUE, "triangle vertex index out of range");
+                    const double vx = ax.vertices[2 * tr[k]], vy = ax.vertices[2 * tr[k] + 1];
+                    txmin = fmin(txmin, vx); txmax = fmax(txmax, vx); tymin = fmin(tymin, vy); tymax = fmax(tymax, vy);
+                }
+                // conservative: one extra cell all round absorbs the fp32 rounding of the device-side bucket index
+                int i0 = (int)floor((txmin - xmin) * icx) - 1, i1 = (int)floor((txmax - xmin) * icx) + 1;
+                int j0 = (int)floor((tymin - ymin) * icy) - 1, j1 = (int)floor((tymax - ymin) * icy) + 1;
+                i0 = std::max(i0, 0); j0 = std::max(j0, 0); i1 = std::min(i1, gx - 1); j1 = std::min(j1, gy - 1);
+                for (int i = i0; i <= i1; i++)
+                    for (int j = j0; j <= j1; j++) {
+                        const size_t cell = (size_t)i * gy + j;
+                        if (pass == 1) tris[start[cell] + count[cell]] = t;
+                        count[cell]++;
+                    }
+            }
+        }
+        std::vector<float2> tv((size_t)ax.n_triangles * 3);
+        for (int t = 0; t < ax.n_triangles; t++)
+            for (int k = 0; k < 3; k++) {
+                const int v = ax.triangles[3 * t + k];
+                tv[(size_t)t * 3 + k] = make_float2((float)ax.vertices[2 * v], (float)ax.vertices[2 * v + 1]);
+            }
+        o.cell_start = A.upload(start);
+        o.cell_tris = A.upload(tris);
+        o.tri = A.upload(tv);
+    }
+    return A.rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// models
+// ------------------------------------------------------------------------------------------------------------------
+static const double SPEED_OF_LIGHT = 299792458.0, ATOMIC_MASS = 1.66053906660e-27, ELEMENTARY_CHARGE = 1.602176634e-19;
+static const double PLANCK_CONSTANT = 6.62607015e-34, ELECTRON_REST_MASS = 9.1093837015e-31, VACUUM_PERMITTIVITY = 8.8541878128e-12;
+static const double HC_EV_NM = 1239.8419738620933;
+
+static void set_comp(DevScene& S, int slot, double lambda, int type) {
+    const double c0 = (lambda - S.min_wavelength_d) / S.delta_d;
+    const double ci = floor(c0);
+    S.comps[slot].c0_int = (int)fmin(fmax(ci, -1.0e9), 1.0e9);
+    S.comps[slot].c0_frac = (float)(c0 - ci);
+    S.comps[slot].dlambda = 0.f;
+    S.comps[slot].type = type;
+}
+
+static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, DevScene& S, DevModel& o) {
+    memset(&o, 0, sizeof o);
+    o.kind = m.kind;
+    o.species = m.species;
+    o.shape = m.shape.kind;
+    o.polarisation = m.shape.polarisation;
+    if (m.kind == CB2_MODEL_BREMSSTRAHLUNG) return CB2_OK;
+    if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE)
+        return cb2_fail(CB2_ERR_TYPE, "unsupported model kind %d", m.kind);
+    if (m.species < 0 || m.species >= d.n_species)
+        return cb2_fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified line");
+    if (!(m.wavelength > 0)) return cb2_fail(CB2_ERR_VALUE, "line wavelength must be positive");
+    o.wavelength = (float)m.wavelength;
+    o.inv_delta = (float)(1.0 / S.delta_d);
+    o.inv_c = (float)(1.0 / SPEED_OF_LIGHT);
+    o.sigma_coef = (float)(sqrt(ELEMENTARY_CHARGE / (m.atomic_weight * ATOMIC_MASS)) * m.wavelength / SPEED_OF_LIGHT / S.delta_d);
+    for (int k = 0; k < 3; k++) o.param[k] = (float)m.shape.param[k];
+    // rate table: log10(PhotonToJ(rate, wavelength)) + 38 on (log10 ne, log10 te)   (pec.pyx:59-68)
+    if (m.pec.n_ne <= 0) {
+        o.pec_const = 1;
+        o.pec_value = (m.pec.constant > 0) ? (float)(log10(m.pec.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+    } else {
+        const int nn = m.pec.n_ne, nt = m.pec.n_te;
+        if (nn < 2 || nt < 2) return cb2_fail(CB2_ERR_VALUE, "rate tables need at least 2x2 points");
+        std::vector<double> lne(nn), lte(nt), lr((size_t)nn * nt);
+        for (int i = 0; i < nn; i++) lne[i] = log10(m.pec.ne[i]);
+        for (int j = 0; j < nt; j++) lte[j] = log10(m.pec.te[j]);
+        const double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9;
+        for (size_t k = 0; k < lr.size(); k++) {
+            if (!(m.pec.rate[k] > 0)) return cb2_fail(CB2_ERR_VALUE, "rate table values must be positive (log10 interpolation)");
+            lr[k] = log10(m.pec.rate[k] / m.wavelength * conv) + CB2_PEC_LOG_OFFSET;
+        }
+        for (int i = 0; i + 1 < nn; i++)
+            if (!(lne[i + 1] > lne[i])) return cb2_fail(CB2_ERR_VALUE, "rate table ne grid must be increasing");
+        for (int j = 0; j + 1 < nt; j++)
+            if (!(lte[j + 1] > lte[j])) return cb2_fail(CB2_ERR_VALUE, "rate table te grid must be increasing");
+        o.pec = make_table2d(A, lne.data(), lte.data(), lr.data(), nn, nt);
+        o.pec_extrapolate = m.pec.extrapolate;
+    }
+    // component slots
+    o.comp0 = S.n_comp;
+    int n = 0;
+    switch (m.shape.kind) {
+    case CB2_SHAPE_GAUSSIAN: n = 1; break;
+    case CB2_SHAPE_MULTIPLET: n = m.shape.n_components; break;
+    case CB2_SHAPE_ZEEMAN_TRIPLET:
+    case CB2_SHAPE_PARAM_ZEEMAN: n = 3; break;
+    case CB2_SHAPE_ZEEMAN_MULTIPLET: n = m.shape.n_pi + m.shape.n_sigma_plus + m.shape.n_sigma_minus; break;
+    case CB2_SHAPE_STARK: return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "StarkBroadenedLine is not implemented on the device yet");
+    default: return cb2_fail(CB2_ERR_TYPE, "unsupported line shape kind %d", m.shape.kind);
+    }
+    if (n < 1) return cb2_fail(CB2_ERR_VALUE, "line shape has no components");
+    if (S.n_comp + n > CB2_MAX_COMP) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components (max %d)", CB2_MAX_COMP);
+    o.ncomp = n;
+    S.n_comp += n;
+    for (int k = 0; k < n; k++) set_comp(S, o.comp0 + k, m.wavelength, (m.shape.kind == CB2_SHAPE_STARK && k >= 3) ? 1 : 0);
+    if (m.shape.kind == CB2_SHAPE_MULTIPLET) {
+        std::vector<float> ratio(n), lam(n);
+        for (int k = 0; k < n; k++) {
+            set_comp(S, o.comp0 + k, m.shape.multiplet[k], 0);
+            lam[k] = (float)m.shape.multiplet[k];
+            ratio[k] = (float)m.shape.multiplet[n + k];
+        }
+        o.n_mult = n;
+        o.mult_ratio = A.upload(ratio);
+        o.mult_lambda = A.upload(lam);
+    }
+    if (m.shape.kind == CB2_SHAPE_ZEEMAN_MULTIPLET) {
+        const int nb = m.shape.n_b;
+        if (nb < 2) return cb2_fail(CB2_ERR_VALUE, "ZeemanStructure tables need at least two |B| points");
+        if (!is_uniform(m.shape.b_grid, nb)) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ZeemanStructure |B| grid must be uniform");
+        o.n_b = nb; o.n_pi = m.shape.n_pi; o.n_sp = m.shape.n_sigma_plus; o.n_sm = m.shape.n_sigma_minus;
+        o.b0 = (float)m.shape.b_grid[0];
+        o.inv_db = (float)((nb - 1) / (m.shape.b_grid[nb - 1] - m.shape.b_grid[0]));
+        std::vector<float> dl((size_t)n * nb), ra((size_t)n * nb);
+        for (size_t k = 0; k < dl.size(); k++) {
+            dl[k] = (float)(m.shape.zeeman_wavelength[k] - m.wavelength);
+            ra[k] = (float)m.shape.zeeman_ratio[k];
+        }
+        o.zee_dlambda = A.upload(dl);
+        o.zee_ratio = A.upload(ra);
+    }
+    if (m.shape.kind == CB2_SHAPE_STARK) {
+        // c_ij * ne^a / te^b with ne in units of 1e19 m^-3 on device
+        o.param[0] = (float)(m.shape.param[0] * pow(1.0 / CB2_DENSITY_SCALE, m.shape.param[1]));
+    }
+    return A.rc;
+}
+
+// Gauss-Legendre nodes on [-1,1] for n = 1..4
+static void gl_nodes(int n, double* x, double* w) {
+    switch (n) {
+    case 1: x[0] = 0; w[0] = 2; break;
+    case 2: x[0] = -0.5773502691896257; x[1] = -x[0]; w[0] = w[1] = 1; break;
+    case 3: x[0] = -0.7745966692414834; x[1] = 0; x[2] = -x[0]; w[0] = w[2] = 5.0 / 9; w[1] = 8.0 / 9; break;
+    default:
+        x[0] = -0.8611363115940526; x[1] = -0.3399810435848563; x[2] = -x[1]; x[3] = -x[0];
+        w[0] = w[3] = 0.3478548451374538; w[1] = w[2] = 0.6521451548625461;
+    }
+}
+
+static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
+    DevBrems& b = S.brems;
+    memset(&b, 0, sizeof b);
+    bool present = false;
+    for (int m = 0; m < d.n_models; m++) present |= d.models[m].kind == CB2_MODEL_BREMSSTRAHLUNG;
+    if (!present) return CB2_OK;
+    const cb2_gaunt& g = d.gaunt;
+    if (g.n_u < 2 || g.n_gamma2 < 2) return cb2_fail(CB2_ERR_RUNTIME, "Bremsstrahlung needs a free-free Gaunt factor table");
+    b.present = 1;
+    const double lmin = d.grid.min_wavelength, lmax = d.grid.max_wavelength, delta = S.delta_d;
+    if (!(lmin > 0)) return cb2_fail(CB2_ERR_VALUE, "Bremsstrahlung needs min_wavelength > 0");
+    if (lmax / lmin >= 100.0) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral windows spanning more than two decades are not supported");
+    // quadrature order from a midpoint/Gauss error bound at Te = 0.1 eV, lambda = lambda_min (kernel K1)
+    int nq = d.brems_quadrature;
+    if (nq <= 0) {
+        const double a = HC_EV_NM / 0.1, dlog = fabs(a / (lmin * lmin) - 2.0 / lmin) + 0.05 / lmin;
+        const double h = 0.5 * delta * dlog;
+        nq = 4;
+        const double bound[5] = {0, h * h / 6.0, pow(h, 4) / 270.0, pow(h, 6) / 31500.0, 0.0};
+        for (int n = 1; n <= 3; n++)
+            if (bound[n] < 2e-6) { nq = n; break; }
+    }
+    if (nq > 4) nq = 4;
+    b.nq = nq;
+    double gx[4], gw[4];
+    gl_nodes(nq, gx, gw);
+    const double lref = log10(0.5 * (lmin + lmax));
+    std::vector<float4> tab((size_t)S.bins_padded * nq);
+    for (int i = 0; i < S.bins_padded; i++)
+        for (int q = 0; q < nq; q++) {
+            const double lam = lmin + delta * (i + 0.5 + 0.5 * gx[q]);
+            const double rho = 1.0 / lam;
+            tab[(size_t)i * nq + q] = make_float4((float)rho, (float)(2.0 * log2(rho)), (float)(log10(lam) - lref), (float)(0.5 * gw[q]));
+        }
+    b.bin_tab = A.upload(tab);
+    b.lref = (float)lref;
+    b.log_hc = (float)log10(HC_EV_NM);
+    b.exp_coef = (float)(PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9 / ELEMENTARY_CHARGE * 1.4426950408889634);
+    double bc = pow(ELEMENTARY_CHARGE * ELEMENTARY_CHARGE / (4.0 * M_PI) / VACUUM_PERMITTIVITY, 3);
+    bc *= 32 * M_PI * M_PI / (3 * sqrt(3.0) * ELECTRON_REST_MASS * ELECTRON_REST_MASS * SPEED_OF_LIGHT * SPEED_OF_LIGHT * SPEED_OF_LIGHT);
+    bc *= sqrt(2 * ELECTRON_REST_MASS / (M_PI * ELEMENTARY_CHARGE));
+    bc *= SPEED_OF_LIGHT * 1e9 / (4.0 * M_PI);
+    b.pref = (float)(bc / (CB2_DENSITY_SCALE * CB2_DENSITY_SCALE));
+    b.rho_min = (float)(1.0 / lmax);
+    b.rho_max = (float)(1.0 / lmin);
+    b.lp_min = (float)(log10(lmin) - lref);
+    b.lp_max = (float)(log10(lmax) - lref);
+    std::vector<double> lu(g.n_u), lg(g.n_gamma2);
+    for (int i = 0; i < g.n_u; i++) lu[i] = log10(g.u[i]);
+    for (int i = 0; i < g.n_gamma2; i++) lg[i] = log10(g.gamma2[i]);
+    for (int i = 0; i + 1 < g.n_u; i++)
+        if (!(lu[i + 1] > lu[i])) return cb2_fail(CB2_ERR_VALUE, "Gaunt table u grid must be increasing");
+    for (int i = 0; i + 1 < g.n_gamma2; i++)
+        if (!(lg[i + 1] > lg[i])) return cb2_fail(CB2_ERR_VALUE, "Gaunt table gamma2 grid must be increasing");
+    b.gaunt = make_table2d(A, lu.data(), lg.data(), g.gaunt, g.n_u, g.n_gamma2);
+    b.lu_min = (float)lu[0]; b.lu_max = (float)lu[g.n_u - 1];
+    b.lg_min = (float)lg[0]; b.lg_max = (float)lg[g.n_gamma2 - 1];
+    b.n_charged = 0;
+    for (int i = 0; i < d.n_species; i++)
+        if (d.species[i].charge > 0) b.charged[b.n_charged++] = i;
+    return A.rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// scene create / destroy
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene** out) {
+    if (!d || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (d->abi_version != CB2_ABI_VERSION) return cb2_fail(CB2_ERR_VALUE, "abi_version mismatch (header %d, descriptor %d)", CB2_ABI_VERSION, d->abi_version);
+    if (d->n_species > CB2_MAX_SPECIES) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many species (max %d)", CB2_MAX_SPECIES);
+    if (d->n_models > CB2_MAX_MODELS) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many models (max %d)", CB2_MAX_MODELS);
+    if (d->grid.bins < 1 || !(d->grid.max_wavelength > d->grid.min_wavelength)) return cb2_fail(CB2_ERR_VALUE, "invalid spectral grid");
+    if (!(d->step > 0)) return cb2_fail(CB2_ERR_VALUE, "Numerical integration step size can not be less than or equal to zero");
+    if (d->min_samples < 2) return cb2_fail(CB2_ERR_VALUE, "At least two samples are required to perform the numerical integration.");
+    int ndev = cb2_device_count();
+    if (ndev <= 0) return ndev < 0 ? CB2_ERR_CUDA : cb2_fail(CB2_ERR_CUDA, "no CUDA device visible (libcherab_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return cb2_fail(CB2_ERR_VALUE, "device %d out of range (%d visible)", device, ndev);
+    CB2_CUDA(cudaSetDevice(device));
+
+    cb2_scene* sc = (cb2_scene*)calloc(1, sizeof(cb2_scene));
+    if (!sc) return cb2_fail(CB2_ERR_MEMORY, "out of host memory");
+    sc->device = device;
+    DevScene& S = sc->host;
+    Arena A;
+    int rc = CB2_OK;
+    do {
+        S.n_species = d->n_species;
+        S.n_models = d->n_models;
+        S.bins = d->grid.bins;
+        S.min_wavelength_d = d->grid.min_wavelength;
+        S.delta_d = (d->grid.max_wavelength - d->grid.min_wavelength) / d->grid.bins;
+        S.min_wavelength = (float)S.min_wavelength_d;
+        S.delta = (float)S.delta_d;
+        S.step = d->step;
+        S.min_samples = d->min_samples;
+        for (int k = 0; k < 12; k++) S.w2p[k] = d->world_to_plasma[k];
+        if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded
+        if ((rc = convert_scalar(A, d->electron_density, d->axisym, CB2_DENSITY_SCALE, S.ne)) != CB2_OK) break;
+        if ((rc = convert_scalar(A, d->electron_temperature, d->axisym, 1.0, S.te)) != CB2_OK) break;
+        bool need_pol = false;
+        for (int i = 0; i < d->n_species && rc == CB2_OK; i++) {
+            S.species[i].charge = d->species[i].charge;
+            S.species[i].z2 = (float)(d->species[i].charge * (double)d->species[i].charge);
+            if ((rc = convert_scalar(A, d->species[i].density, d->axisym, CB2_DENSITY_SCALE, S.species[i].density)) != CB2_OK) break;
+            if ((rc = convert_scalar(A, d->species[i].temperature, d->axisym, 1.0, S.species[i].temperature)) != CB2_OK) break;
+            if ((rc = convert_vector(A, d->species[i].velocity, d->axisym, S.species[i].velocity)) != CB2_OK) break;
+            need_pol |= vec_has_pol(d->species[i].velocity, d->axisym);
+        }
+        if (rc != CB2_OK) break;
+        if (d->axisym && (rc = convert_axisym(A, *d->axisym, S.ax)) != CB2_OK) break;
+        S.b_kind = d->b_field_kind;
+        if (S.b_kind == 1 && !d->axisym) { rc = cb2_fail(CB2_ERR_RUNTIME, "EFIT b_field needs an axisym context"); break; }
+        for (int k = 0; k < 3; k++) S.b_const[k] = (float)d->b_field[k];
+        S.n_comp = 0;
+        bool need_b = false;
+        for (int m = 0; m < d->n_models; m++) {
+            if ((rc = convert_model(A, *d, d->models[m], S, S.models[m])) != CB2_OK) break;
+            const int sh = d->models[m].shape.kind;
+            if (d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && sh != CB2_SHAPE_GAUSSIAN && sh != CB2_SHAPE_MULTIPLET) need_b = true;
+        }
+        if (rc != CB2_OK) break;
+        S.need_b = need_b;
+        S.need_pol = need_pol || (need_b && S.b_kind == 1);
+        if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;
+        if ((rc = A.rc) != CB2_OK) break;
+        void* p = nullptr;
+        if ((rc = cb2_cuda_check(cudaMalloc(&p, sizeof(DevScene)), "cudaMalloc(scene)")) != CB2_OK) break;
+        A.ptrs.push_back(p);
+        sc->dev = (DevScene*)p;
+        if ((rc = cb2_cuda_check(cudaMemcpy(p, &S, sizeof(DevScene), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) != CB2_OK) break;
+        if ((rc = cb2_cuda_check(cudaMalloc(&p, sizeof(cb2_stats)), "cudaMalloc(stats)")) != CB2_OK) break;
+        A.ptrs.push_back(p);
+        sc->stats_dev = (unsigned long long*)p;
+    } while (0);
+    if (rc != CB2_OK) {
+        A.release();
+        free(sc);
+        return rc;
+    }
+    sc->n_allocs = (int)A.ptrs.size();
+    sc->allocs = (void**)malloc(sizeof(void*) * A.ptrs.size());
+    memcpy(sc->allocs, A.ptrs.data(), sizeof(void*) * A.ptrs.size());
+    *out = sc;
+    return CB2_OK;
+}
+
+static void free_stage(void** stage, size_t* bytes) {
+    for (int i = 0; i < 8; i++) {
+        if (stage[i]) cudaFree(stage[i]);
+        stage[i] = nullptr;
+        bytes[i] = 0;
+    }
+}
+
+extern "C" int cb2_scene_destroy(cb2_scene* sc) {
+    if (!sc) return CB2_OK;
+    cudaSetDevice(sc->device);
+    for (int i = 0; i < sc->n_allocs; i++) cudaFree(sc->allocs[i]);
+    free(sc->allocs);
+    free_stage(sc->stage, sc->stage_bytes);
+    free(sc);
+    return CB2_OK;
+}
+
+// grow-only device staging buffer
+static int stage_reserve(void** stage, size_t* bytes, int slot, size_t need) {
+    if (bytes[slot] >= need && stage[slot]) return CB2_OK;
+    if (stage[slot]) cudaFree(stage[slot]);
+    stage[slot] = nullptr;
+    bytes[slot] = 0;
+    size_t cap = need + need / 4 + 256;
+    CB2_CUDA(cudaMalloc(&stage[slot], cap));
+    bytes[slot] = cap;
+    return CB2_OK;
+}
+
+static int check_rays(const cb2_rays* r) {
+    if (!r) return cb2_fail(CB2_ERR_VALUE, "null rays");
+    if (r->n_rays < 0 || r->n_segments < 0) return cb2_fail(CB2_ERR_VALUE, "negative ray count");
+    if (r->n_rays > 0 && (!r->origin || !r->direction || !r->seg_offset)) return cb2_fail(CB2_ERR_VALUE, "null ray arrays");
+    return CB2_OK;
+}
+
+// upload host rays into staging slots 0..4
+static int upload_rays(void** stage, size_t* bytes, const cb2_rays* r, DevRays& dr, cudaStream_t st) {
+    const size_t n = (size_t)r->n_rays, ns = (size_t)r->n_segments;
+    int rc;
+    if ((rc = stage_reserve(stage, bytes, 0, n * 3 * sizeof(double))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(stage, bytes, 1, n * 3 * sizeof(double))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(stage, bytes, 2, (n + 1) * sizeof(int64_t))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(stage, bytes, 3, ns * sizeof(double))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(stage, bytes, 4, ns * sizeof(double))) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(stage[0], r->origin, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CB2_CUDA(cudaMemcpyAsync(stage[1], r->direction, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CB2_CUDA(cudaMemcpyAsync(stage[2], r->seg_offset, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (ns) {
+        CB2_CUDA(cudaMemcpyAsync(stage[3], r->seg_t0, ns * sizeof(double), cudaMemcpyHostToDevice, st));
+        CB2_CUDA(cudaMemcpyAsync(stage[4], r->seg_t1, ns * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    dr.n_rays = r->n_rays;
+    dr.origin = (const double*)stage[0];
+    dr.direction = (const double*)stage[1];
+    dr.seg_offset = (const int64_t*)stage[2];
+    dr.seg_t0 = (const double*)stage[3];
+    dr.seg_t1 = (const double*)stage[4];
+    return CB2_OK;
+}
+
+static DevRays as_dev_rays(const cb2_rays* r) {
+    DevRays dr;
+    dr.n_rays = r->n_rays;
+    dr.origin = r->origin;
+    dr.direction = r->direction;
+    dr.seg_offset = r->seg_offset;
+    dr.seg_t0 = r->seg_t0;
+    dr.seg_t1 = r->seg_t1;
+    return dr;
+}
+
+extern "C" int cb2_emission_render_device(cb2_scene* sc, const cb2_rays* rays, void* out, int out_f64, double scale,
+                                          int accumulate, cb2_stats* stats_dev, void* stream) {
+    if (!sc || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    int rc = check_rays(rays);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    if (rays->n_rays == 0) return CB2_OK;
+    return cb2_launch_emission(sc, as_dev_rays(rays), out, out_f64, scale, accumulate, (unsigned long long*)stats_dev, (cudaStream_t)stream);
+}
+
+extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* out, int out_f64, double scale, int accumulate,
+                                   cb2_stats* stats) {
+    if (!sc || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    int rc = check_rays(rays);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (rays->n_rays == 0) return CB2_OK;
+    cudaStream_t st = 0;
+    DevRays dr;
+    if ((rc = upload_rays(sc->stage, sc->stage_bytes, rays, dr, st)) != CB2_OK) return rc;
+    const size_t esz = out_f64 ? sizeof(double) : sizeof(float);
+    const size_t obytes = (size_t)rays->n_rays * sc->host.bins * esz;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 5, obytes)) != CB2_OK) return rc;
+    if (accumulate) CB2_CUDA(cudaMemcpyAsync(sc->stage[5], out, obytes, cudaMemcpyHostToDevice, st));
+    CB2_CUDA(cudaMemsetAsync(sc->stats_dev, 0, sizeof(cb2_stats), st));
+    if ((rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st)) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(out, sc->stage[5], obytes, cudaMemcpyDeviceToHost, st));
+    if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA(cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
+extern "C" int cb2_state_width(const cb2_scene* sc) { return sc ? 2 + 5 * sc->host.n_species + 3 : 0; }
+
+extern "C" int cb2_sample_state(cb2_scene* sc, const double* points, int64_t n, double* out) {
+    if (!sc || !points || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    if (n <= 0) return CB2_OK;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    const int w = cb2_state_width(sc);
+    int rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 6, (size_t)n * 3 * sizeof(double))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 7, (size_t)n * w * sizeof(double))) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpy(sc->stage[6], points, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    if ((rc = cb2_launch_sample_state(sc, (const double*)sc->stage[6], n, (double*)sc->stage[7], 0)) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpy(out, sc->stage[7], (size_t)n * w * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ray transfer
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int cb2_rt_create(const cb2_rt_desc* d, int device, cb2_rt_scene** out) {
+    if (!d || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (d->abi_version != CB2_ABI_VERSION) return cb2_fail(CB2_ERR_VALUE, "abi_version mismatch");
+    if (d->kind != CB2_RT_CYLINDRICAL && d->kind != CB2_RT_CARTESIAN) return cb2_fail(CB2_ERR_TYPE, "unsupported ray-transfer grid kind %d", d->kind);
+    for (int k = 0; k < 3; k++) {
+        if (d->grid_shape[k] < 1) return cb2_fail(CB2_ERR_VALUE, "Number of grid cells must be > 0.");
+        if (!(d->grid_steps[k] > 0)) return cb2_fail(CB2_ERR_VALUE, "Grid steps must be > 0.");
+    }
+    if (!(d->step > 0)) return cb2_fail(CB2_ERR_VALUE, "Numerical integration step size can not be less than or equal to zero.");
+    if (d->min_samples < 2) return cb2_fail(CB2_ERR_VALUE, "At least two samples are required to perform the numerical integration.");
+    if (!d->voxel_map || d->bins < 0) return cb2_fail(CB2_ERR_VALUE, "voxel_map missing");
+    int ndev = cb2_device_count();
+    if (ndev <= 0) return ndev < 0 ? CB2_ERR_CUDA : cb2_fail(CB2_ERR_CUDA, "no CUDA device visible (libcherab_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return cb2_fail(CB2_ERR_VALUE, "device %d out of range (%d visible)", device, ndev);
+    CB2_CUDA(cudaSetDevice(device));
+    cb2_rt_scene* sc = (cb2_rt_scene*)calloc(1, sizeof(cb2_rt_scene));
+    if (!sc) return cb2_fail(CB2_ERR_MEMORY, "out of host memory");
+    sc->device = device;
+    DevRT& r = sc->rt;
+    r.kind = d->kind;
+    r.n0 = d->grid_shape[0]; r.n1 = d->grid_shape[1]; r.n2 = d->grid_shape[2];
+    r.min_samples = d->min_samples;
+    r.bins = d->bins;
+    r.s0 = d->grid_steps[0]; r.s1 = d->grid_steps[1]; r.s2 = d->grid_steps[2];
+    r.rmin = d->rmin; r.period = d->period; r.step = d->step;
+    for (int k = 0; k < 12; k++) r.w2l[k] = d->world_to_local[k];
+    const size_t ncell = (size_t)r.n0 * r.n1 * r.n2;
+    for (size_t k = 0; k < ncell; k++)
+        if (d->voxel_map[k] >= d->bins) { free(sc); return cb2_fail(CB2_ERR_VALUE, "voxel_map entry exceeds bins"); }
+    int rc = CB2_OK;
+    do {
+        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->voxel_map_dev, ncell * sizeof(int32_t)), "cudaMalloc(voxel_map)")) != CB2_OK) break;
+        if ((rc = cb2_cuda_check(cudaMemcpy(sc->voxel_map_dev, d->voxel_map, ncell * sizeof(int32_t), cudaMemcpyHostToDevice), "cudaMemcpy(voxel_map)")) != CB2_OK) break;
+        r.voxel_map = sc->voxel_map_dev;
+        cudaDeviceProp prop;
+        if ((rc = cb2_cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) != CB2_OK) break;
+        // persistent warps: each owns a dense double[bins] scratch row; budget 8 GiB
+        const size_t per_warp = std::max<size_t>(r.bins, 1) * sizeof(double);
+        size_t warps = (size_t)prop.multiProcessorCount * 32;
+        const size_t budget = (size_t)8 << 30;
+        while (warps > (size_t)prop.multiProcessorCount && warps * per_warp > budget) warps /= 2;
+        sc->n_warps = (int)warps;
+        // distinct sources one ray can touch: bounded by cell-boundary crossings and by bins
+        size_t cross = (size_t)2 * r.n0 + r.n2 + 4;
+        if (r.kind == CB2_RT_CYLINDRICAL) cross += (size_t)2 * r.n1 * (size_t)ceil(360.0 / r.period) + 2;
+        else cross = (size_t)r.n0 + r.n1 + r.n2 + 4;
+        sc->touch_cap = (int)std::min<size_t>(std::max<size_t>(r.bins, 1), cross * 2);
+        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->scratch, warps * per_warp), "cudaMalloc(rt scratch)")) != CB2_OK) break;
+        if ((rc = cb2_cuda_check(cudaMemset(sc->scratch, 0, warps * per_warp), "cudaMemset(rt scratch)")) != CB2_OK) break;
+        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->touched, warps * sc->touch_cap * sizeof(int32_t)), "cudaMalloc(rt touched)")) != CB2_OK) break;
+        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->stats_dev, sizeof(cb2_stats)), "cudaMalloc(stats)")) != CB2_OK) break;
+    } while (0);
+    if (rc != CB2_OK) {
+        cb2_rt_destroy(sc);
+        return rc;
+    }
+    *out = sc;
+    return CB2_OK;
+}
+
+extern "C" int cb2_rt_destroy(cb2_rt_scene* sc) {
+    if (!sc) return CB2_OK;
+    cudaSetDevice(sc->device);
+    if (sc->voxel_map_dev) cudaFree(sc->voxel_map_dev);
+    if (sc->scratch) cudaFree(sc->scratch);
+    if (sc->touched) cudaFree(sc->touched);
+    if (sc->stats_dev) cudaFree(sc->stats_dev);
+    free_stage(sc->stage, sc->stage_bytes);
+    free(sc);
+    return CB2_OK;
+}
+
+extern "C" int cb2_rt_render_dense(cb2_rt_scene* sc, const cb2_rays* rays, double* out, int accumulate, cb2_stats* stats) {
+    if (!sc || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    int rc = check_rays(rays);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (rays->n_rays == 0 || sc->rt.bins == 0) return CB2_OK;
+    cudaStream_t st = 0;
+    DevRays dr;
+    if ((rc = upload_rays(sc->stage, sc->stage_bytes, rays, dr, st)) != CB2_OK) return rc;
+    const size_t obytes = (size_t)rays->n_rays * sc->rt.bins * sizeof(double);
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 5, obytes)) != CB2_OK) return rc;
+    if (accumulate) CB2_CUDA(cudaMemcpyAsync(sc->stage[5], out, obytes, cudaMemcpyHostToDevice, st));
+    else CB2_CUDA(cudaMemsetAsync(sc->stage[5], 0, obytes, st));
+    CB2_CUDA(cudaMemsetAsync(sc->stats_dev, 0, sizeof(cb2_stats), st));
+    if ((rc = cb2_launch_rt(sc, dr, 0, (double*)sc->stage[5], accumulate, nullptr, nullptr, nullptr, sc->stats_dev, st)) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(out, sc->stage[5], obytes, cudaMemcpyDeviceToHost, st));
+    if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA(cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
+extern "C" int cb2_rt_render_csr_device(cb2_rt_scene* sc, const cb2_rays* rays, int64_t* row_offset, int32_t* columns,
+                                        double* lengths, int64_t capacity, int64_t* nnz_host, cb2_stats* stats_dev, void* stream) {
+    if (!sc || !row_offset || !nnz_host) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    int rc = check_rays(rays);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevRays dr = as_dev_rays(rays);
+    *nnz_host = 0;
+    if (rays->n_rays == 0) {
+        CB2_CUDA(cudaMemsetAsync(row_offset, 0, sizeof(int64_t), st));
+        return CB2_OK;
+    }
+    // pass 1: distinct sources per ray -> row_offset[r]; exclusive scan; pass 2: fill
+    if ((rc = cb2_launch_rt(sc, dr, 1, nullptr, 0, row_offset, nullptr, nullptr, nullptr, st)) != CB2_OK) return rc;
+    if ((rc = cb2_launch_scan(row_offset, rays->n_rays + 1, st)) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(nnz_host, row_offset + rays->n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA(cudaStreamSynchronize(st));
+    if (*nnz_host > capacity) return cb2_fail(CB2_ERR_OVERFLOW, "CSR capacity %lld too small, need %lld", (long long)capacity, (long long)*nnz_host);
+    if (*nnz_host == 0) return CB2_OK;
+    if (!columns || !lengths) return cb2_fail(CB2_ERR_VALUE, "null CSR arrays");
+    return cb2_launch_rt(sc, dr, 2, nullptr, 0, row_offset, columns, lengths, (unsigned long long*)stats_dev, st);
+}
+
+extern "C" int cb2_rt_render_csr(cb2_rt_scene* sc, const cb2_rays* rays, int64_t* row_offset, int32_t* columns, double* lengths,
+                                 int64_t capacity, cb2_stats* stats) {
+    if (!sc || !row_offset) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    int rc = check_rays(rays);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (rays->n_rays == 0) { row_offset[0] = 0; return CB2_OK; }
+    cudaStream_t st = 0;
+    DevRays dr;
+    if ((rc = upload_rays(sc->stage, sc->stage_bytes, rays, dr, st)) != CB2_OK) return rc;
+    const size_t n = (size_t)rays->n_rays;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 5, (n + 1) * sizeof(int64_t))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 6, (size_t)std::max<int64_t>(capacity, 1) * sizeof(int32_t))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 7, (size_t)std::max<int64_t>(capacity, 1) * sizeof(double))) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemsetAsync(sc->stats_dev, 0, sizeof(cb2_stats), st));
+    cb2_rays drays;
+    drays.n_rays = rays->n_rays; drays.n_segments = rays->n_segments;
+    drays.origin = dr.origin; drays.direction = dr.direction; drays.seg_offset = dr.seg_offset; drays.seg_t0 = dr.seg_t0; drays.seg_t1 = dr.seg_t1;
+    int64_t nnz = 0;
+    rc = cb2_rt_render_csr_device(sc, &drays, (int64_t*)sc->stage[5], (int32_t*)sc->stage[6], (double*)sc->stage[7], capacity, &nnz,
+                                  (cb2_stats*)sc->stats_dev, st);
+    if (rc == CB2_ERR_OVERFLOW) { row_offset[n] = nnz; return rc; }
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(row_offset, sc->stage[5], (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (nnz > 0) {
+        CB2_CUDA(cudaMemcpyAsync(columns, sc->stage[6], (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CB2_CUDA(cudaMemcpyAsync(lengths, sc->stage[7], (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA(cudaStreamSynchronize(st));
+    return CB2_OK;
+}

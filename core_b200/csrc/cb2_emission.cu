@@ -1,0 +1,859 @@
+// cb2_emission.cu — the emission hot path on sm_100a.
+//
+// One CTA integrates one ray (all of its segments).  Work is organised in chunks of NT = blockDim.x samples:
+//
+//   STATE phase   (one thread per sample)  position -> (R, Z) -> psi_n / LCFS mask / blend weight / mesh triangle,
+//                 each evaluated ONCE per sample (the reference re-walks the function tree for every quantity,
+//                 SURVEY 0.5) -> species profiles -> PEC bicubics -> per line component a compact record
+//                 (centre, width, amplitude, series coefficients, bin range) in shared memory; for Bremsstrahlung
+//                 the per-sample cubic of sum_i n_i Z_i^2 g_ff(Z_i, Te, lambda) in log10(lambda).
+//   BIN phase     (one warp per spectral tile)  warp w owns bins [w*32*BPL, (w+1)*32*BPL), lane l owns bins
+//                 tile + 32 j + l (interleaved so narrow lines still fill the warp); accumulators live in
+//                 registers (fp32 per chunk, flushed into fp64 per-ray accumulators after every chunk: "fp32 math,
+//                 fp64 per-ray accumulation").  Every warp sweeps the chunk's records and adds the bin integrals
+//                 of the components that touch its tile.  No atomics, no cross-warp reduction.
+//
+// Gaussian bin integrals I = 1/2 [erf(x_hi) - erf(x_lo)] are evaluated in fp32 with RELATIVE accuracy
+// (tools/proto_gauss_fp32.py: <= 1e-5 everywhere the acceptance floor allows):
+//   h = half bin width in units of sqrt(2) sigma
+//   h <  1/16 : I = kb/sqrt(pi) exp(-m^2) [1 + h^2 H2(m)/6 + h^4 H4(m)/120], one MUFU.EX2 per bin, no cancellation;
+//   h >= 1/16 : differences of 1/2 erfc(|x|) = s Q(s) exp(-x^2), s = 1/(1 + |x|/2) (degree-9 minimax Q), the lower
+//               edge value taken from the neighbouring lane by warp shuffle (the reference's lower=upper recurrence).
+// Follows: cherab/core/plasma/material.pyx:48-63, model/plasma/impact_excitation.pyx:78-100, recombination.pyx:78-100,
+// bremsstrahlung.pyx:70-90,169-208, model/lineshape/gaussian.pyx:40-139, doppler.pyx:29-59, multiplet.pyx:93-117,
+// zeeman.pyx:113-365, atomic/gaunt.pyx:109-140, tools/equilibrium/efit.pyx:219-546, generomak/plasma/plasma.py:580-638,
+// and Raysect's NumericalIntegrator.
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+#include "cb2_internal.h"
+
+#define FULL 0xffffffffu
+#define L2E 1.4426950408889634f
+#define RECIP_4_PI 0.07957747154594767f
+#define INV_SQRT_PI 0.5641895835477563f
+#define H_SERIES_MAX 0.0625f
+#define RYDBERG_EV 13.605693122994f
+#define BOHR_MAGNETON 5.78838180123e-5f
+#define HC_EV_NM_F 1239.8419738620933f
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 1/2 erfc(a), a >= 0, relative error ~5e-7: s Q(s) exp(-a^2) with s = 1/(1 + a/2)
+__device__ __forceinline__ float half_erfc(float a) {
+    const float s = rcp_approx(fmaf(0.5f, a, 1.0f));
+    float q = 0.01022576f;
+    q = fmaf(q, s, -0.08354225f);
+    q = fmaf(q, s, 0.26529264f);
+    q = fmaf(q, s, -0.40173006f);
+    q = fmaf(q, s, 0.26512444f);
+    q = fmaf(q, s, -0.07779776f);
+    q = fmaf(q, s, 0.12243541f);
+    q = fmaf(q, s, 0.11730774f);
+    q = fmaf(q, s, 0.1416635f);
+    q = fmaf(q, s, 0.14102058f);
+    return q * s * ex2_approx(a * a * -L2E);
+}
+
+__device__ __forceinline__ float horner4(const float4 c, float t) { return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// table lookups
+// ------------------------------------------------------------------------------------------------------------------
+struct Cell2 {
+    int i, j;
+    float t, u;
+    bool inside;
+};
+
+__device__ __forceinline__ int search_knots(const float* __restrict__ x, int n, float v) {
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(x + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ Cell2 locate2d(const DevTable2D& T, float x, float y) {
+    Cell2 c;
+    c.inside = (x >= T.xmin) && (x <= T.xmax) && (y >= T.ymin) && (y <= T.ymax);
+    x = fminf(fmaxf(x, T.xmin), T.xmax);
+    y = fminf(fmaxf(y, T.ymin), T.ymax);
+    if (T.uniform) {
+        const float fx = (x - T.x0) * T.inv_dx, fy = (y - T.y0) * T.inv_dy;
+        c.i = min(max((int)fx, 0), T.nx - 2);
+        c.j = min(max((int)fy, 0), T.ny - 2);
+        c.t = fx - (float)c.i;
+        c.u = fy - (float)c.j;
+    } else {
+        c.i = search_knots(T.x, T.nx, x);
+        c.j = search_knots(T.y, T.ny, y);
+        c.t = (x - __ldg(T.x + c.i)) * __ldg(T.inv_wx + c.i);
+        c.u = (y - __ldg(T.y + c.j)) * __ldg(T.inv_wy + c.j);
+    }
+    return c;
+}
+
+__device__ __forceinline__ float eval2d(const DevTable2D& T, const Cell2& c) {
+    const float4* q = T.coef + ((size_t)c.i * (T.ny - 1) + c.j) * 4;
+    const float p0 = horner4(__ldg(q), c.u), p1 = horner4(__ldg(q + 1), c.u);
+    const float p2 = horner4(__ldg(q + 2), c.u), p3 = horner4(__ldg(q + 3), c.u);
+    return fmaf(fmaf(fmaf(p3, c.t, p2), c.t, p1), c.t, p0);
+}
+
+// coefficients e_p(u) of t^p for a fixed second coordinate (used to turn the Gaunt bicubic into a cubic in log10 u)
+__device__ __forceinline__ float4 eval2d_rows(const DevTable2D& T, int i, int j, float u) {
+    const float4* q = T.coef + ((size_t)i * (T.ny - 1) + j) * 4;
+    return make_float4(horner4(__ldg(q), u), horner4(__ldg(q + 1), u), horner4(__ldg(q + 2), u), horner4(__ldg(q + 3), u));
+}
+
+__device__ __forceinline__ void locate1d(const DevTable1D& T, float x, int& i, float& t) {
+    x = fminf(fmaxf(x, T.xmin), T.xmax);
+    i = (T.n > 1) ? search_knots(T.x, T.n, x) : 0;
+    t = (T.n > 1) ? (x - __ldg(T.x + i)) * __ldg(T.inv_w + i) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-sample shared context of the axisymmetric (Generomak-type) function tree — SURVEY Appendix C
+// ------------------------------------------------------------------------------------------------------------------
+struct AxCtx {
+    float R, Z, cphi, sphi;
+    float m;        // blend weight (plasma.py:610)
+    int tri;        // edge-mesh triangle or -1
+    int ci;         // core psi_n interval
+    float ct;
+    float psi;
+    bool in_lcfs;
+    float br, bt, bz;
+};
+
+__device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py) {
+    if (px < A.poly_xmin || px > A.poly_xmax || py < A.poly_ymin || py > A.poly_ymax) return false;
+    int crossings = 0;
+    for (int i = 0; i < A.n_poly; i++) {
+        const float4 e = __ldg(A.poly + i);  // (xi, yi, yj, slope)
+        if (((e.y > py) != (e.z > py)) && (px < fmaf(py - e.y, e.w, e.x))) crossings++;
+    }
+    return crossings & 1;
+}
+
+__device__ __forceinline__ int mesh_locate(const DevAxisym& A, float r, float z) {
+    if (A.n_tri <= 0) return -1;
+    const float fx = (r - A.mx0) * A.inv_cx, fy = (z - A.my0) * A.inv_cy;
+    if (!(fx >= 0.f) || !(fy >= 0.f)) return -1;
+    const int i = (int)fx, j = (int)fy;
+    if (i >= A.gx || j >= A.gy) return -1;
+    const int cell = i * A.gy + j;
+    int best = -1;
+    const int k1 = __ldg(A.cell_start + cell + 1);
+    for (int k = __ldg(A.cell_start + cell); k < k1; k++) {
+        const int t = __ldg(A.cell_tris + k);
+        const float2 a = __ldg(A.tri + 3 * t), b = __ldg(A.tri + 3 * t + 1), c = __ldg(A.tri + 3 * t + 2);
+        const float d1 = (r - b.x) * (a.y - b.y) - (a.x - b.x) * (z - b.y);
+        const float d2 = (r - c.x) * (b.y - c.y) - (b.x - c.x) * (z - c.y);
+        const float d3 = (r - a.x) * (c.y - a.y) - (c.x - a.x) * (z - a.y);
+        const bool neg = (d1 < 0) || (d2 < 0) || (d3 < 0), pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
+        if (!(neg && pos) && (best < 0 || t < best)) best = t;
+    }
+    return best;
+}
+
+__device__ __forceinline__ void ax_setup(const DevScene& S, float x, float y, float z, AxCtx& c, unsigned& ood) {
+    const DevAxisym& A = S.ax;
+    c.R = sqrtf(x * x + y * y);
+    c.Z = z;
+    const float inv_r = c.R > 0.f ? 1.0f / c.R : 0.f;
+    c.cphi = c.R > 0.f ? x * inv_r : 1.f;
+    c.sphi = y * inv_r;
+    c.m = 0.f; c.tri = -1; c.ci = 0; c.ct = 0.f; c.psi = 0.f; c.in_lcfs = false;
+    c.br = c.bt = c.bz = 0.f;
+    if (!A.present) return;
+    const bool in_poly = polygon_contains(A, c.R, c.Z);
+    Cell2 cell;
+    bool have_cell = false;
+    if (in_poly) {
+        cell = locate2d(A.psin, c.R, c.Z);
+        have_cell = true;
+        if (!cell.inside) ood++;
+        c.psi = fmaxf(eval2d(A.psin, cell), 0.f);   // ClampOutput2D(min=0), efit.pyx:116
+        c.in_lcfs = c.psi <= 1.0f;                  // EFITLCFSMask, efit.pyx:405-410
+    }
+    if (c.in_lcfs) {
+        // Interpolator1DArray(mask_x, mask_y, 'linear') of psi_n (plasma.py:610)
+        float m = A.mask_y[0];
+        const float p = fminf(fmaxf(c.psi, A.mask_x[0]), A.mask_x[A.n_mask - 1]);
+        for (int k = 0; k + 1 < A.n_mask; k++)
+            if (p >= A.mask_x[k] && p <= A.mask_x[k + 1]) {
+                m = A.mask_y[k] + (p - A.mask_x[k]) / (A.mask_x[k + 1] - A.mask_x[k]) * (A.mask_y[k + 1] - A.mask_y[k]);
+                break;
+            }
+        c.m = m;
+    }
+    if (c.m < 1.0f) c.tri = mesh_locate(A, c.R, c.Z);
+    if (c.m > 0.0f) locate1d(A.core, c.psi, c.ci, c.ct);
+    const bool want_pol = (S.need_pol && c.m > 0.f) || S.need_b;
+    if (want_pol) {
+        if (!have_cell) {
+            cell = locate2d(A.psin, c.R, c.Z);
+            if (!cell.inside) ood++;
+        }
+        c.br = -eval2d(A.dpsi_dz, cell) * inv_r;   // MagneticField.evaluate, efit.pyx:443-445
+        c.bz = eval2d(A.dpsi_dr, cell) * inv_r;
+        if (S.need_b) {
+            if (c.in_lcfs) {
+                int fi; float ft;
+                locate1d(A.fprof, c.psi, fi, ft);
+                c.bt = horner4(__ldg(A.fprof_coef + fi), ft) * inv_r;
+            } else {
+                c.bt = A.b_vac * inv_r;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float eval_scalar(const DevScalar& f, const AxCtx& c, float x, float y, float z) {
+    switch (f.kind) {
+    case CB2_FIELD_CONSTANT: return f.c[0];
+    case CB2_FIELD_GAUSSIAN_VOLUME: {
+        const float dx = x - f.c[3], dy = y - f.c[4], dz = z - f.c[5];
+        return fmaf(f.c[1], exp2f((dx * dx + dy * dy + dz * dz) * f.c[2]), f.c[0]);
+    }
+    case CB2_FIELD_SLAB_ION: {
+        const float xn = x * f.c[4];
+        if (xn >= 0.f && xn <= 1.f) return (f.c[0] - f.c[1]) * powf(1.f - powf(1.f - xn, f.c[2]), f.c[3]) + f.c[1];
+        return xn >= 1.f ? f.c[0] : 0.f;
+    }
+    case CB2_FIELD_SLAB_NEUTRAL: return x >= 0.f ? f.c[0] * exp2f(x * x * f.c[1]) : f.c[0];
+    case CB2_FIELD_AXISYM_BLEND: {
+        // Blend2D(edge, map2d(core), mask): m <= 0 -> edge, m >= 1 -> core, else (1-m) edge + m core
+        float edge = 0.f, core = 0.f;
+        if (c.m < 1.f && c.tri >= 0 && f.edge) edge = __ldg(f.edge + c.tri);
+        if (c.m > 0.f && f.core) core = horner4(__ldg(f.core + c.ci), c.ct);
+        if (c.m <= 0.f) return edge;
+        if (c.m >= 1.f) return core;
+        return fmaf(c.m, core, (1.f - c.m) * edge);
+    }
+    }
+    return 0.f;
+}
+
+// cartesian velocity in plasma space
+__device__ __forceinline__ float3 eval_vector(const DevVector& f, const AxCtx& c) {
+    if (f.kind == CB2_FIELD_CONSTANT) return make_float3(f.c[0], f.c[1], f.c[2]);
+    float vr = f.c[0], vp = f.c[1], vz = f.c[2];  // edge vector (R, phi, Z)
+    if (c.m > 0.f) {
+        // FluxCoordToCartesian.evaluate (efit.pyx:521-546) inside the LCFS
+        float cr = 0.f, cp = 0.f, cz = 0.f;
+        if (c.in_lcfs) {
+            cp = f.vtor ? horner4(__ldg(f.vtor + c.ci), c.ct) : 0.f;
+            if (!(c.br == 0.f && c.bz == 0.f)) {
+                const float inv = rsqrtf(c.br * c.br + c.bz * c.bz);
+                const float vpol = f.vpol ? horner4(__ldg(f.vpol + c.ci), c.ct) : 0.f;
+                const float vnorm = f.vnorm ? horner4(__ldg(f.vnorm + c.ci), c.ct) : 0.f;
+                cr = (c.br * vpol - c.bz * vnorm) * inv;
+                cz = (c.bz * vpol + c.br * vnorm) * inv;
+            }
+        }
+        if (c.m >= 1.f) { vr = cr; vp = cp; vz = cz; }
+        else { vr = fmaf(c.m, cr, (1.f - c.m) * vr); vp = fmaf(c.m, cp, (1.f - c.m) * vp); vz = fmaf(c.m, cz, (1.f - c.m) * vz); }
+    }
+    // VectorAxisymmetricMapper: rotate by phi about z (mappers.pyx:302-312)
+    return make_float3(vr * c.cphi - vp * c.sphi, vr * c.sphi + vp * c.cphi, vz);
+}
+
+__device__ __forceinline__ float3 eval_b_field(const DevScene& S, const AxCtx& c) {
+    if (S.b_kind == 0) return make_float3(S.b_const[0], S.b_const[1], S.b_const[2]);
+    return make_float3(c.br * c.cphi - c.bt * c.sphi, c.br * c.sphi + c.bt * c.cphi, c.bz);
+}
+
+// ImpactExcitationPEC.evaluate (pec.pyx:70-77) in log space: returns log10(PEC [W m^3]) + 38
+__device__ __forceinline__ float eval_pec_log(const DevModel& M, float lne, float lte, unsigned& ood) {
+    if (M.pec_const) return M.pec_value;
+    const Cell2 c = locate2d(M.pec, lne, lte);
+    if (!c.inside && !M.pec_extrapolate) ood++;
+    return eval2d(M.pec, c);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// STATE phase helpers
+// ------------------------------------------------------------------------------------------------------------------
+struct RecWriter {
+    float4* rec;      // [ncomp][2][NT]
+    int* rng;         // [ncomp][2] (lo, hi) bounding bin ranges of this chunk, relative bins
+    int nt, tid;
+    int bins;
+    unsigned long long gauss_evals;
+};
+
+// Write one Gaussian component: centre cf (bins, relative to the slot's integer origin c0_int), width sigma_b (bins),
+// amplitude amp = weight * radiance / delta_wavelength.   (add_gaussian_line, gaussian.pyx:40-90)
+__device__ __forceinline__ void put_gaussian(RecWriter& W, const DevComp& cs, int slot, float cf, float sigma_b, float amp) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (amp > 0.f && sigma_b > 0.f) {
+        const float cut = 10.0f * sigma_b;                       // GAUSSIAN_CUTOFF_SIGMA
+        const float win_lo = (float)(-cs.c0_int), win_hi = (float)(W.bins - cs.c0_int);
+        const float flo = floorf(cf - cut), fhi = ceilf(cf + cut);
+        if (fhi > win_lo && flo < win_hi) {
+            const int lo = (int)fmaxf(flo, win_lo), hi = (int)fminf(fhi, win_hi);
+            if (hi > lo) {
+                const float kb = 0.70710678f / sigma_b;          // delta / (sqrt(2) sigma), per bin
+                const float h = 0.5f * kb;
+                a.x = kb;
+                if (h < H_SERIES_MAX) {
+                    const float h2 = h * h, h4 = h2 * h2;
+                    a.y = (0.5f - cf) * kb;                      // x at bin centre = rel * kb + a.y
+                    a.z = amp * kb * INV_SQRT_PI;
+                    a.w = 1.0f - h2 * (1.0f / 3.0f) + h4 * 0.1f; // s0 >= 0 marks the series path
+                    b.x = h2 * (2.0f / 3.0f) - h4 * 0.4f;
+                    b.y = h4 * (4.0f / 30.0f);
+                } else {
+                    a.y = (1.0f - cf) * kb;                      // x at the bin's upper edge
+                    a.z = amp;
+                    a.w = -1.0f;                                 // erfc-difference path
+                }
+                b.z = __int_as_float(lo);
+                b.w = __int_as_float(hi);
+                atomicMin(&W.rng[2 * slot], lo);
+                atomicMax(&W.rng[2 * slot + 1], hi);
+                W.gauss_evals += (unsigned long long)(hi - lo) + 1ull;
+            }
+        }
+    }
+    W.rec[(2 * slot) * W.nt + W.tid] = a;
+    W.rec[(2 * slot + 1) * W.nt + W.tid] = b;
+}
+
+__device__ __forceinline__ void put_empty(RecWriter& W, int slot) {
+    W.rec[(2 * slot) * W.nt + W.tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+struct SampleIn {
+    float x, y, z;       // plasma-space position
+    float dx, dy, dz;    // unit ray direction in plasma space
+    float weight;        // trapezium weight (h or h/2), metres
+};
+
+// All line models at one sample (PlasmaMaterial.emission_function loop, material.pyx:59-61).
+__device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, RecWriter& W, unsigned& ood) {
+    const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+    float lne = 0.f, lte = 0.f;
+    if (live) {
+        lne = log10f(ne) + 19.0f;     // densities are stored in units of 1e19 m^-3
+        lte = log10f(te);
+    }
+    int cur = -1;
+    float ni = 0.f, ts = 0.f, vd = 0.f;
+    float3 bf = make_float3(0.f, 0.f, 0.f);
+    float bm = 0.f, cos_sqr = 0.f;
+    bool have_b = false;
+    for (int m = 0; m < S.n_models; m++) {
+        const DevModel& M = S.models[m];
+        if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
+        bool on = live;
+        if (on && M.species != cur) {
+            cur = M.species;
+            const DevSpecies& sp = S.species[cur];
+            ni = eval_scalar(sp.density, ctx, in.x, in.y, in.z);
+            ts = eval_scalar(sp.temperature, ctx, in.x, in.y, in.z);
+            const float3 v = eval_vector(sp.velocity, ctx);
+            vd = v.x * in.dx + v.y * in.dy + v.z * in.dz;   // velocity projected on the (unit) ray direction
+        }
+        on = on && ni > 0.f;
+        float radiance = 0.f;
+        if (on) {
+            // radiance = 1/(4 pi) PEC ne ni  (impact_excitation.pyx:99); exp10 of (log PEC + 38) * (ne ni * 1e-38)
+            radiance = RECIP_4_PI * exp10f(eval_pec_log(M, lne, lte, ood)) * ne * ni;
+        }
+        const float amp = radiance * in.weight * M.inv_delta;
+        // all Gaussian-family shapes return before touching the spectrum if ts <= 0 (gaussian.pyx:127-129)
+        const bool shape_on = on && ts > 0.f && amp > 0.f;
+        if (!shape_on || M.shape == CB2_SHAPE_STARK) {
+            for (int k = 0; k < M.ncomp; k++) put_empty(W, M.comp0 + k);
+            continue;
+        }
+        float sigma_b = M.sigma_coef * sqrtf(ts);                      // thermal_broadening, doppler.pyx:48-59, in bins
+        const float dop = vd * M.inv_c;                                 // doppler_shift: lambda (1 + v.d/c)
+        const float shift0 = M.wavelength * dop * M.inv_delta;          // Doppler shift of the rest wavelength, in bins
+        if (M.shape == CB2_SHAPE_GAUSSIAN) {
+            const DevComp& cs = S.comps[M.comp0];
+            put_gaussian(W, cs, M.comp0, cs.c0_frac + shift0, sigma_b, amp);
+            continue;
+        }
+        if (M.shape == CB2_SHAPE_MULTIPLET) {                           // multiplet.pyx:108-115
+            for (int k = 0; k < M.ncomp; k++) {
+                const DevComp& cs = S.comps[M.comp0 + k];
+                const float sh = __ldg(M.mult_lambda + k) * dop * M.inv_delta;
+                put_gaussian(W, cs, M.comp0 + k, cs.c0_frac + sh, sigma_b, amp * __ldg(M.mult_ratio + k));
+            }
+            continue;
+        }
+        // Zeeman family (zeeman.pyx)
+        if (!have_b) {
+            bf = eval_b_field(S, ctx);
+            bm = sqrtf(bf.x * bf.x + bf.y * bf.y + bf.z * bf.z);
+            const float c = bm > 0.f ? (bf.x * in.dx + bf.y * in.dy + bf.z * in.dz) / bm : 0.f;
+            cos_sqr = c * c;
+            have_b = true;
+        }
+        if (M.shape == CB2_SHAPE_PARAM_ZEEMAN) sigma_b *= sqrtf(1.0f + M.param[1] * M.param[1] * powf(ts, 2.0f * M.param[2]));
+        const float sin_sqr = 1.0f - cos_sqr;
+        const bool pol_pi = M.polarisation != CB2_POL_SIGMA, pol_sigma = M.polarisation != CB2_POL_PI;
+        if (bm == 0.f) {
+            // no splitting: single Gaussian, halved if a polarisation filter is set (zeeman.pyx:132-136)
+            const DevComp& cs = S.comps[M.comp0];
+            put_gaussian(W, cs, M.comp0, cs.c0_frac + shift0, sigma_b, M.polarisation == CB2_POL_NO ? amp : 0.5f * amp);
+            for (int k = 1; k < M.ncomp; k++) put_empty(W, M.comp0 + k);
+            continue;
+        }
+        const float a_pi = 0.5f * sin_sqr * amp, a_sigma = (0.25f * sin_sqr + 0.5f * cos_sqr) * amp;
+        if (M.shape == CB2_SHAPE_ZEEMAN_TRIPLET || M.shape == CB2_SHAPE_PARAM_ZEEMAN) {
+            float dl_plus, dl_minus;  // wavelength offsets of the sigma components from the rest wavelength
+            if (M.shape == CB2_SHAPE_ZEEMAN_TRIPLET) {
+                // hc/(hc/l0 -+ muB B) - l0 = +- l0 e/(1 -+ e), e = muB B l0 / hc   (zeeman.pyx:152-158)
+                const float e = BOHR_MAGNETON * bm * M.wavelength * (1.0f / HC_EV_NM_F);
+                dl_plus = M.wavelength * e / (1.0f - e);
+                dl_minus = -M.wavelength * e / (1.0f + e);
+            } else {
+                dl_plus = 0.5f * M.param[0] * bm;                      // zeeman.pyx:260-264
+                dl_minus = -dl_plus;
+            }
+            const DevComp& c0 = S.comps[M.comp0];
+            if (pol_pi) put_gaussian(W, c0, M.comp0, c0.c0_frac + shift0, sigma_b, a_pi); else put_empty(W, M.comp0);
+            if (pol_sigma) {
+                put_gaussian(W, c0, M.comp0 + 1, c0.c0_frac + (dl_plus + (M.wavelength + dl_plus) * dop) * M.inv_delta, sigma_b, a_sigma);
+                put_gaussian(W, c0, M.comp0 + 2, c0.c0_frac + (dl_minus + (M.wavelength + dl_minus) * dop) * M.inv_delta, sigma_b, a_sigma);
+            } else {
+                put_empty(W, M.comp0 + 1);
+                put_empty(W, M.comp0 + 2);
+            }
+            continue;
+        }
+        if (M.shape == CB2_SHAPE_ZEEMAN_MULTIPLET) {                    // zeeman.pyx:340-363, atomic/zeeman.pyx:87-129
+            float fb = (bm - M.b0) * M.inv_db;
+            fb = fminf(fmaxf(fb, 0.f), (float)(M.n_b - 1));
+            const int ib = min((int)fb, M.n_b - 2);
+            const float tb = fb - (float)ib;
+            const int offs[4] = {0, M.n_pi, M.n_pi + M.n_sp, M.n_pi + M.n_sp + M.n_sm};
+            for (int g = 0; g < 3; g++) {
+                const bool gon = g == 0 ? pol_pi : pol_sigma;
+                float rsum = 0.f;
+                for (int k = offs[g]; k < offs[g + 1]; k++) {
+                    const float* r = M.zee_ratio + (size_t)k * M.n_b + ib;
+                    rsum += fmaf(tb, __ldg(r + 1) - __ldg(r), __ldg(r));
+                }
+                const float rnorm = rsum > 0.f ? 1.0f / rsum : 1.0f;
+                for (int k = offs[g]; k < offs[g + 1]; k++) {
+                    const DevComp& cs = S.comps[M.comp0 + k];
+                    if (!gon) { put_empty(W, M.comp0 + k); continue; }
+                    const float* r = M.zee_ratio + (size_t)k * M.n_b + ib;
+                    const float* l = M.zee_dlambda + (size_t)k * M.n_b + ib;
+                    const float ratio = fmaf(tb, __ldg(r + 1) - __ldg(r), __ldg(r)) * rnorm;
+                    const float dl = fmaf(tb, __ldg(l + 1) - __ldg(l), __ldg(l));
+                    put_gaussian(W, cs, M.comp0 + k, cs.c0_frac + (dl + (M.wavelength + dl) * dop) * M.inv_delta, sigma_b,
+                                 (g == 0 ? a_pi : a_sigma) * ratio);
+                }
+            }
+            continue;
+        }
+        for (int k = 0; k < M.ncomp; k++) put_empty(W, M.comp0 + k);
+    }
+}
+
+// Bremsstrahlung at one sample: cubic(s) in l' = log10(lambda) - lref of  A * sum_i n_i Z_i^2 g_ff(Z_i, Te, lambda),
+// A = weight * BREMS_CONST * ne / sqrt(Te); up to three pieces when the window crosses knots of the Gaunt table's u grid.
+// record: r0 = (a2, n_pieces, rho_c1, rho_c2), r1..r3 = piece coefficients (c0..c3).
+__device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
+                             unsigned long long& brems_evals, unsigned& ood) {
+    const DevBrems& B = S.brems;
+    float4 r0 = make_float4(0.f, 0.f, FLT_MAX, FLT_MAX);
+    float4 pc[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    if (ne > 0.f && te > 0.f && in.weight > 0.f) {
+        const float lte = log10f(te);
+        const float L0 = B.log_hc - lte - B.lref;            // log10 u = L0 - l'
+        const float lu_lo = L0 - B.lp_max, lu_hi = L0 - B.lp_min;
+        const DevTable2D& G = B.gaunt;
+        // interval index: -1 Born (u < u_min), nx-1 classical (u >= u_max), else table cell
+        auto interval = [&](float lu) -> int {
+            if (lu < B.lu_min) return -1;
+            if (lu >= B.lu_max) return G.nx - 1;
+            return search_knots(G.x, G.nx, lu);
+        };
+        const int i_lo = interval(lu_lo);
+        int i_hi = interval(lu_hi);
+        if (i_hi > i_lo + 2) { i_hi = i_lo + 2; ood++; }
+        const int np = i_hi - i_lo + 1;
+        // wavelength (1/lambda) thresholds where the piece changes: u = knot  <=>  rho = knot * Te / hc
+        if (np > 1) r0.z = exp10f(__ldg(G.x + i_lo + 1) - B.log_hc + lte);
+        if (np > 2) r0.w = exp10f(__ldg(G.x + i_lo + 2) - B.log_hc + lte);
+        const float k1 = 0.5513288954217921f * 2.302585092994046f;            // sqrt(3)/pi * ln 10
+        const float k0 = 0.5513288954217921f * (1.3862943611198906f - 0.5772156649015329f);  // sqrt(3)/pi (ln 4 - gamma_E)
+        for (int s = 0; s < B.n_charged; s++) {
+            const DevSpecies& sp = S.species[B.charged[s]];
+            const float ni = eval_scalar(sp.density, ctx, in.x, in.y, in.z);
+            if (!(ni > 0.f)) continue;
+            const float w = ni * sp.z2;
+            const float lg = log10f(sp.z2 * RYDBERG_EV / te);                  // log10 gamma^2
+            int jg = 0; float ug = 0.f;
+            const bool g_hi = lg >= B.lg_max, g_lo = lg < B.lg_min;
+            if (!g_hi && !g_lo) {
+                jg = search_knots(G.y, G.ny, lg);
+                ug = (lg - __ldg(G.y + jg)) * __ldg(G.inv_wy + jg);
+            }
+            for (int p = 0; p < np; p++) {
+                const int iu = i_lo + p;
+                float c0, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                if (g_hi || iu >= G.nx - 1) c0 = 1.0f;                          // classical limit (gaunt.pyx:129-130)
+                else if (g_lo || iu < 0) { c0 = k0 - k1 * L0; c1 = k1; }        // Born approximation (gaunt.pyx:133-134)
+                else {
+                    const float4 e = eval2d_rows(G, iu, jg, ug);                // g = sum_p e_p t^p, t = alpha - beta l'
+                    const float beta = __ldg(G.inv_wx + iu), alpha = (L0 - __ldg(G.x + iu)) * beta;
+                    c0 = fmaf(fmaf(fmaf(e.w, alpha, e.z), alpha, e.y), alpha, e.x);
+                    c1 = -beta * fmaf(fmaf(3.0f * e.w, alpha, 2.0f * e.z), alpha, e.y);
+                    c2 = beta * beta * fmaf(3.0f * e.w, alpha, e.z);
+                    c3 = -beta * beta * beta * e.w;
+                }
+                pc[p].x = fmaf(w, c0, pc[p].x); pc[p].y = fmaf(w, c1, pc[p].y);
+                pc[p].z = fmaf(w, c2, pc[p].z); pc[p].w = fmaf(w, c3, pc[p].w);
+            }
+        }
+        const float A = in.weight * B.pref * ne * rsqrtf(te);
+        for (int p = 0; p < 3; p++) { pc[p].x *= A; pc[p].y *= A; pc[p].z *= A; pc[p].w *= A; }
+        r0.x = B.exp_coef / te;
+        r0.y = (float)np;
+        brems_evals += (unsigned long long)S.bins;
+    }
+    brec[tid] = r0;
+    brec[nt + tid] = pc[0];
+    brec[2 * nt + tid] = pc[1];
+    brec[3 * nt + tid] = pc[2];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+template <int NW, int BPL, int BREMS>
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 4 : 2))
+emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict__ out, int out_f64, double scale, int accumulate,
+                unsigned long long* __restrict__ stats) {
+    constexpr int NT = NW * 32;
+    constexpr int TB = 32 * BPL;
+    extern __shared__ float4 smem[];
+    __shared__ int s_rng[2][2 * CB2_MAX_COMP];
+    const DevScene& S = *Sp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncomp = S.n_comp;
+    float4* rec = smem;
+    float4* brec = smem + (size_t)2 * ncomp * NT;
+
+    for (int i = tid; i < 4 * CB2_MAX_COMP; i += NT) (&s_rng[0][0])[i] = (i & 1) ? INT_MIN : INT_MAX;
+
+    const int64_t ray = blockIdx.x;
+    // ray in plasma space (fp64 once per ray)
+    double o[3], d[3];
+    {
+        const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+        const double dx = rays.direction[3 * ray], dy = rays.direction[3 * ray + 1], dz = rays.direction[3 * ray + 2];
+        for (int k = 0; k < 3; k++) {
+            o[k] = S.w2p[4 * k] * ox + S.w2p[4 * k + 1] * oy + S.w2p[4 * k + 2] * oz + S.w2p[4 * k + 3];
+            d[k] = S.w2p[4 * k] * dx + S.w2p[4 * k + 1] * dy + S.w2p[4 * k + 2] * dz;
+        }
+    }
+    const double dlen = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    SampleIn in;
+    in.dx = (float)(d[0] / dlen); in.dy = (float)(d[1] / dlen); in.dz = (float)(d[2] / dlen);
+
+    float acc[BPL];
+    double racc[BPL];
+#pragma unroll
+    for (int j = 0; j < BPL; j++) { acc[j] = 0.f; racc[j] = 0.0; }
+
+    // Bremsstrahlung per-bin constants (1/lambda, 2 log2(1/lambda), log10(lambda) - lref) for one-point quadrature
+    float b_rho[BPL], b_cb[BPL], b_lp[BPL];
+    if (BREMS == 1) {
+#pragma unroll
+        for (int j = 0; j < BPL; j++) {
+            const float4 t = __ldg(S.brems.bin_tab + (warp * TB + 32 * j + lane));
+            b_rho[j] = t.x; b_cb[j] = t.y; b_lp[j] = t.z;
+        }
+    }
+
+    unsigned long long n_samples = 0, n_gauss = 0, n_brems = 0;
+    unsigned ood = 0;
+    int parity = 0;
+    __syncthreads();
+
+    const int64_t s_begin = rays.seg_offset[ray], s_end = rays.seg_offset[ray + 1];
+    for (int64_t sg = s_begin; sg < s_end; sg++) {
+        const double t0 = rays.seg_t0[sg], t1 = rays.seg_t1[sg];
+        const double length = (t1 - t0) * dlen;
+        if (!(length > 0.0)) continue;
+        int iv = (int)ceil(length / S.step);                       // NumericalIntegrator: intervals
+        iv = max(iv, max(S.min_samples - 1, 1));
+        const double h = length / iv;
+        const float hf = (float)h;
+        // marching from the far end towards the observer, like Raysect (start_point = far end)
+        const float fx = (float)(o[0] + t1 * d[0]), fy = (float)(o[1] + t1 * d[1]), fz = (float)(o[2] + t1 * d[2]);
+        if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
+
+        for (int k0 = 0; k0 <= iv; k0 += NT) {
+            // ---------------- STATE phase ----------------
+            const int k = k0 + tid;
+            const bool active = k <= iv;
+            const float tk = (float)k * hf;
+            in.x = fmaf(-tk, in.dx, fx); in.y = fmaf(-tk, in.dy, fy); in.z = fmaf(-tk, in.dz, fz);
+            in.weight = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
+            {
+                AxCtx ctx;
+                float ne = 0.f, te = 0.f;
+                if (active) {
+                    ax_setup(S, in.x, in.y, in.z, ctx, ood);
+                    ne = eval_scalar(S.ne, ctx, in.x, in.y, in.z);
+                    te = eval_scalar(S.te, ctx, in.x, in.y, in.z);
+                } else {
+                    ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false;
+                }
+                RecWriter W;
+                W.rec = rec; W.rng = s_rng[parity]; W.nt = NT; W.tid = tid; W.bins = S.bins; W.gauss_evals = 0;
+                sample_lines(S, in, ctx, ne, te, W, ood);
+                n_gauss += W.gauss_evals;
+                if (BREMS) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
+            }
+            __syncthreads();
+            // ---------------- BIN phase ----------------
+            for (int i = tid; i < 2 * ncomp; i += NT) s_rng[parity ^ 1][i] = (i & 1) ? INT_MIN : INT_MAX;
+            const int nact = min(NT, iv - k0 + 1);
+            for (int c = 0; c < ncomp; c++) {
+                const int tlo = warp * TB - S.comps[c].c0_int;            // relative index of this warp's first bin
+                if (s_rng[parity][2 * c + 1] <= tlo || s_rng[parity][2 * c] >= tlo + TB) continue;
+                float relf[BPL];
+#pragma unroll
+                for (int j = 0; j < BPL; j++) relf[j] = (float)(tlo + 32 * j + lane);
+                const float4* ra = rec + (size_t)(2 * c) * NT;
+                const float4* rb = ra + NT;
+                for (int s = 0; s < nact; s++) {
+                    const float4 a = ra[s];
+                    if (a.z == 0.f) continue;
+                    const float4 b = rb[s];
+                    const int lo = __float_as_int(b.z), hi = __float_as_int(b.w);
+                    if (hi <= tlo || lo >= tlo + TB) continue;
+                    if (a.w >= 0.f) {
+                        // series path: amp' exp(-m^2) (s0 + s1 m^2 + s2 m^4)
+#pragma unroll
+                        for (int j = 0; j < BPL; j++) {
+                            const int r0 = tlo + 32 * j;
+                            if (hi > r0 && lo < r0 + 32) {
+                                const float x = fmaf(relf[j], a.x, a.y);
+                                const float m2 = x * x;
+                                const float e = ex2_approx(m2 * -L2E);
+                                const float sx = fmaf(fmaf(b.y, m2, b.x), m2, a.w);
+                                acc[j] = fmaf(a.z * e, sx, acc[j]);
+                            }
+                        }
+                    } else {
+                        // erfc-difference path with the lower-edge value handed over by the neighbouring lane
+                        bool have = false;
+                        float carry = 0.f;
+#pragma unroll
+                        for (int j = 0; j < BPL; j++) {
+                            const int r0 = tlo + 32 * j;
+                            if (hi > r0 && lo < r0 + 32) {
+                                const float xu = fmaf(relf[j], a.x, a.y);
+                                const float xl = xu - a.x;
+                                const float tu = half_erfc(fabsf(xu));
+                                float tl = __shfl_up_sync(FULL, tu, 1);
+                                if (lane == 0) tl = have ? carry : half_erfc(fabsf(xl));
+                                carry = __shfl_sync(FULL, tu, 31);
+                                have = true;
+                                const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
+                                acc[j] = fmaf(a.z, dd, acc[j]);
+                            } else {
+                                have = false;
+                            }
+                        }
+                    }
+                }
+            }
+            if (BREMS) {
+                for (int s = 0; s < nact; s++) {
+                    const float4 r0 = brec[s];
+                    if (r0.x == 0.f) continue;
+                    const float na2 = -r0.x;
+                    const float4 p0 = brec[NT + s];
+                    if (BREMS == 1 && r0.y < 1.5f) {
+#pragma unroll
+                        for (int j = 0; j < BPL; j++) {
+                            const float e = ex2_approx(fmaf(na2, b_rho[j], b_cb[j]));
+                            acc[j] = fmaf(horner4(p0, b_lp[j]), e, acc[j]);
+                        }
+                    } else {
+                        const float4 p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
+                        const int nq = S.brems.nq;
+#pragma unroll
+                        for (int j = 0; j < BPL; j++) {
+                            const float4* tb = S.brems.bin_tab + (size_t)(warp * TB + 32 * j + lane) * nq;
+                            float v = 0.f;
+                            for (int q = 0; q < nq; q++) {
+                                const float4 t = __ldg(tb + q);
+                                float4 pc = p0;
+                                if (t.x >= r0.z) pc = p1;
+                                if (t.x >= r0.w) pc = p2;
+                                v = fmaf(t.w * horner4(pc, t.z), ex2_approx(fmaf(na2, t.x, t.y)), v);
+                            }
+                            acc[j] += v;
+                        }
+                    }
+                }
+            }
+            // fp32 chunk sums -> fp64 per-ray accumulators
+#pragma unroll
+            for (int j = 0; j < BPL; j++) { racc[j] += (double)acc[j]; acc[j] = 0.f; }
+            parity ^= 1;
+            __syncthreads();
+        }
+    }
+
+    // write the ray's spectrum: lane-consecutive bins -> coalesced 128-byte rows
+#pragma unroll
+    for (int j = 0; j < BPL; j++) {
+        const int bin = warp * TB + 32 * j + lane;
+        if (bin < S.bins) {
+            const size_t idx = (size_t)ray * S.bins + bin;
+            if (out_f64) {
+                double* p = (double*)out + idx;
+                *p = (accumulate ? *p : 0.0) + scale * racc[j];
+            } else {
+                float* p = (float*)out + idx;
+                *p = (float)((accumulate ? (double)*p : 0.0) + scale * racc[j]);
+            }
+        }
+    }
+
+    if (stats) {
+        // warp-reduce the work counters, one atomic per warp
+        unsigned long long oodl = ood;
+        for (int off = 16; off > 0; off >>= 1) {
+            n_gauss += __shfl_down_sync(FULL, n_gauss, off);
+            n_brems += __shfl_down_sync(FULL, n_brems, off);
+            oodl += __shfl_down_sync(FULL, oodl, off);
+        }
+        if (lane == 0) {
+            if (n_gauss) atomicAdd(stats + 1, n_gauss);
+            if (n_brems) atomicAdd(stats + 3, n_brems);
+            if (oodl) atomicAdd(stats + 5, oodl);
+        }
+        if (tid == 0 && n_samples) atomicAdd(stats + 0, n_samples);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch configuration
+// ------------------------------------------------------------------------------------------------------------------
+int cb2_emission_config(cb2_scene* sc) {
+    const int bins = sc->host.bins;
+    int nw, bpl;
+    if (bins <= 128) { nw = 4; bpl = 1; }
+    else if (bins <= 256) { nw = 4; bpl = 2; }
+    else if (bins <= 512) { nw = 4; bpl = 4; }
+    else if (bins <= 1024) { nw = 8; bpl = 4; }
+    else if (bins <= 2048) { nw = 8; bpl = 8; }
+    else if (bins <= 4096) { nw = 8; bpl = 16; }
+    else return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
+    sc->nw = nw;
+    sc->bpl = bpl;
+    sc->host.bins_padded = nw * 32 * bpl;
+    return CB2_OK;
+}
+
+template <int NW, int BPL>
+static int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                      unsigned long long* stats, cudaStream_t st) {
+    const DevScene& S = sc->host;
+    const int NT = NW * 32;
+    const size_t smem = ((size_t)2 * S.n_comp * NT + (S.brems.present ? 4 * NT : 0)) * sizeof(float4);
+    const int mode = !S.brems.present ? 0 : ((S.brems.nq == 1 && BPL <= 8) ? 1 : 2);
+    if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
+    dim3 grid((unsigned)rays.n_rays), block(NT);
+#define CB2_LAUNCH(MODE)                                                                                                   \
+    do {                                                                                                                   \
+        auto kern = emission_kernel<NW, BPL, MODE>;                                                                        \
+        if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, block, smem, st>>>(sc->dev, rays, out, out_f64, scale, accumulate, stats);                            \
+    } while (0)
+    if (smem > 200 * 1024) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components for shared memory (%zu bytes)", smem);
+    if (mode == 0) CB2_LAUNCH(0);
+    else if (mode == 1) CB2_LAUNCH(1);
+    else CB2_LAUNCH(2);
+#undef CB2_LAUNCH
+    return cb2_cuda_check(cudaGetLastError(), "emission_kernel launch");
+}
+
+int cb2_launch_emission(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                        unsigned long long* stats, cudaStream_t st) {
+#define CB2_CASE(NW, BPL) \
+    if (sc->nw == NW && sc->bpl == BPL) return launch_cfg<NW, BPL>(sc, rays, out, out_f64, scale, accumulate, stats, st)
+    CB2_CASE(4, 1);
+    CB2_CASE(4, 2);
+    CB2_CASE(4, 4);
+    CB2_CASE(8, 4);
+    CB2_CASE(8, 8);
+    CB2_CASE(8, 16);
+#undef CB2_CASE
+    return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "no kernel instance for nw=%d bpl=%d", sc->nw, sc->bpl);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-point plasma state (parity tests of the flattened function tree)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void sample_state_kernel(const DevScene* __restrict__ Sp, const double* __restrict__ pts, int64_t n, double* __restrict__ out) {
+    const DevScene& S = *Sp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    float p[3];
+    for (int k = 0; k < 3; k++) p[k] = (float)(S.w2p[4 * k] * px + S.w2p[4 * k + 1] * py + S.w2p[4 * k + 2] * pz + S.w2p[4 * k + 3]);
+    AxCtx ctx;
+    unsigned ood = 0;
+    ax_setup(S, p[0], p[1], p[2], ctx, ood);
+    const int w = 2 + 5 * S.n_species + 3;
+    double* o = out + i * w;
+    const double inv_scale = 1.0 / CB2_DENSITY_SCALE;
+    o[0] = (double)eval_scalar(S.ne, ctx, p[0], p[1], p[2]) * inv_scale;
+    o[1] = (double)eval_scalar(S.te, ctx, p[0], p[1], p[2]);
+    for (int s = 0; s < S.n_species; s++) {
+        o[2 + 5 * s] = (double)eval_scalar(S.species[s].density, ctx, p[0], p[1], p[2]) * inv_scale;
+        o[3 + 5 * s] = (double)eval_scalar(S.species[s].temperature, ctx, p[0], p[1], p[2]);
+        const float3 v = eval_vector(S.species[s].velocity, ctx);
+        o[4 + 5 * s] = v.x; o[5 + 5 * s] = v.y; o[6 + 5 * s] = v.z;
+    }
+    const float3 b = eval_b_field(S, ctx);
+    o[2 + 5 * S.n_species] = b.x; o[3 + 5 * S.n_species] = b.y; o[4 + 5 * S.n_species] = b.z;
+}
+
+int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t st) {
+    // the state probe always wants B and the poloidal direction: use a scene copy with the flags forced on
+    DevScene tmp = sc->host;
+    tmp.need_b = 1;
+    tmp.need_pol = 1;
+    DevScene* dtmp = nullptr;
+    CB2_CUDA(cudaMalloc((void**)&dtmp, sizeof(DevScene)));
+    int rc = cb2_cuda_check(cudaMemcpyAsync(dtmp, &tmp, sizeof(DevScene), cudaMemcpyHostToDevice, st), "cudaMemcpy(scene)");
+    if (rc == CB2_OK) {
+        const int bs = 128;
+        sample_state_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(dtmp, points_dev, n, out_dev);
+        rc = cb2_cuda_check(cudaGetLastError(), "sample_state_kernel launch");
+        if (rc == CB2_OK) rc = cb2_cuda_check(cudaStreamSynchronize(st), "sample_state sync");
+    }
+    cudaFree(dtmp);
+    return rc;
+}

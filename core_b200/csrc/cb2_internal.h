@@ -1,0 +1,214 @@
+// cb2_internal.h — device-resident scene layout shared by the host builder and the kernels.
+//
+// Data layout in HBM (all tables fp32, built once at cb2_scene_create from the fp64 descriptor):
+//   * 2-D cubic tables (psi_n, dpsi/dR, dpsi/dZ, every PEC, Gaunt): per-cell 16 polynomial coefficients as 4 float4
+//     (row i = coefficients of t^i * u^0..3), knots + reciprocal cell widths for the (rare) non-uniform search;
+//   * 1-D cubic tables (core profiles on the psi_n grid, f-profile): per-interval float4 (a0..a3 in t in [0,1]);
+//   * edge mesh: per-triangle vertex coordinates (6 floats) + uniform bucket grid (cell_start / cell_tris);
+//   * densities are stored scaled by 1e-19 and PEC tables as log10(W m^3) + 38 so that every product stays in
+//     fp32 range (ne*ni reaches 1e42 m^-6 on Generomak).
+// A scene is a few MB: it lives in L2 (126 MB) for the whole frame; the hot per-sample records are in shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cherab_b200.h"
+
+#define CB2_MAX_SPECIES 24
+#define CB2_MAX_MODELS 32
+#define CB2_MAX_COMP 96
+#define CB2_DENSITY_SCALE 1e-19
+#define CB2_PEC_LOG_OFFSET 38.0
+
+struct DevTable2D {
+    int nx, ny;             // knots
+    int uniform;            // 1: both axes uniform -> direct index
+    float x0, inv_dx, y0, inv_dy;
+    float xmin, xmax, ymin, ymax;
+    const float* x;         // [nx]
+    const float* y;         // [ny]
+    const float* inv_wx;    // [nx-1] reciprocal cell widths
+    const float* inv_wy;    // [ny-1]
+    const float4* coef;     // [(nx-1)*(ny-1)*4]
+};
+
+struct DevTable1D {          // knots shared, coefficients per quantity
+    int n;
+    float xmin, xmax;
+    const float* x;          // [n]
+    const float* inv_w;      // [n-1]
+};
+
+struct DevScalar {
+    int kind;
+    float c[6];
+    const float* edge;       // [n_triangles]
+    const float4* core;      // [n_core-1]
+};
+
+struct DevVector {
+    int kind;
+    float c[3];
+    const float4* vtor;
+    const float4* vpol;
+    const float4* vnorm;
+};
+
+struct DevSpecies {
+    int charge;
+    float z2;
+    DevScalar density, temperature;
+    DevVector velocity;
+};
+
+struct DevAxisym {
+    int present;
+    DevTable2D psin, dpsi_dr, dpsi_dz;
+    DevTable1D core;                 // core psi_n knots
+    DevTable1D fprof;                // f-profile knots
+    const float4* fprof_coef;
+    float b_vac;                     // b_vacuum_magnitude * b_vacuum_radius
+    int n_poly;
+    const float4* poly;              // per edge: (xi, yi, yj, slope = (xj-xi)/(yj-yi))
+    float poly_xmin, poly_xmax, poly_ymin, poly_ymax;
+    int n_mask;
+    float mask_x[8], mask_y[8];
+    // mesh
+    int n_tri, gx, gy;
+    float mx0, my0, inv_cx, inv_cy;
+    const int* cell_start;
+    const int* cell_tris;
+    const float2* tri;               // [n_tri*3]
+};
+
+// static part of one line component slot (Gaussian or Lorentzian)
+struct DevComp {
+    int c0_int;       // integer part of (lambda_component - lambda_min)/delta
+    float c0_frac;    // fractional part
+    float dlambda;    // static wavelength offset from the model's rest wavelength already included in c0 (0)
+    int type;         // 0 gaussian, 1 lorentzian
+};
+
+struct DevModel {
+    int kind, species, shape, polarisation;
+    float wavelength;     // rest wavelength (nm)
+    float sigma_coef;     // sigma[bins] = sigma_coef * sqrt(T[eV])
+    float inv_delta;      // 1/delta_wavelength
+    float inv_c;          // 1/SPEED_OF_LIGHT
+    float param[3];
+    int comp0, ncomp;     // component slots
+    int pec_const;        // 1: constant rate
+    float pec_value;      // log10(rate) + 38 for constant rates
+    int pec_extrapolate;
+    DevTable2D pec;       // log10 ne[m^-3], log10 te -> log10(W m^3) + 38
+    // multiplet
+    int n_mult;
+    const float* mult_ratio;      // [n_mult]
+    const float* mult_lambda;     // [n_mult] component rest wavelengths
+    // zeeman multiplet tables
+    int n_b, n_pi, n_sp, n_sm;
+    float b0, inv_db;             // uniform |B| grid
+    const float* zee_dlambda;     // [ncomp][n_b]  lambda_j(B) - lambda0
+    const float* zee_ratio;       // [ncomp][n_b]
+};
+
+struct DevBrems {
+    int present;
+    int nq;                       // Gauss-Legendre points per bin
+    const float4* bin_tab;        // [bins_padded][nq]: (1/lambda, 2*log2(1/lambda), log10(lambda) - lref, weight)
+    float lref;                   // log10 of the window centre
+    float log_hc;                 // log10(HC_EV_NM)
+    float exp_coef;               // EXP_FACTOR * log2(e)
+    float pref;                   // BREMS_CONST * 1e38
+    float rho_min, rho_max;       // 1/lambda_max, 1/lambda_min
+    float lp_min, lp_max;         // log10(lambda_min) - lref, log10(lambda_max) - lref
+    // gaunt table in (log10 u, log10 gamma2)
+    DevTable2D gaunt;
+    float lu_min, lu_max, lg_min, lg_max;
+    int n_charged;
+    int charged[CB2_MAX_SPECIES];
+};
+
+struct DevScene {
+    int n_species, n_models, n_comp;
+    int bins, bins_padded;
+    float min_wavelength, delta;
+    double min_wavelength_d, delta_d;
+    double step;
+    int min_samples;
+    double w2p[12];
+    int need_b, need_pol;          // which expensive shared quantities any model needs
+    int b_kind;
+    float b_const[3];
+    DevScalar ne, te;
+    DevSpecies species[CB2_MAX_SPECIES];
+    DevModel models[CB2_MAX_MODELS];
+    DevComp comps[CB2_MAX_COMP];
+    DevAxisym ax;
+    DevBrems brems;
+};
+
+struct DevRays {
+    int64_t n_rays;
+    const double* origin;
+    const double* direction;
+    const int64_t* seg_offset;
+    const double* seg_t0;
+    const double* seg_t1;
+};
+
+// ---- ray transfer ----
+struct DevRT {
+    int kind;
+    int n0, n1, n2;
+    int min_samples;
+    int bins;
+    double s0, s1, s2;      // grid steps
+    double rmin, period, step;
+    double w2l[12];
+    const int32_t* voxel_map;
+};
+
+struct cb2_scene {
+    int device;
+    DevScene host;           // host copy (pointers are device pointers)
+    DevScene* dev;           // device copy
+    void** allocs;           // device allocations to free
+    int n_allocs, cap_allocs;
+    // launch configuration
+    int nw, bpl, smem_bytes;
+    // staging buffers for the host-buffer entry point
+    void* stage[8];
+    size_t stage_bytes[8];
+    unsigned long long* stats_dev;
+};
+
+struct cb2_rt_scene {
+    int device;
+    DevRT rt;
+    int32_t* voxel_map_dev;
+    double* scratch;         // [n_warps][bins] per-warp dense accumulators
+    int32_t* touched;        // [n_warps][touch_cap]
+    int n_warps, touch_cap;
+    void* stage[8];
+    size_t stage_bytes[8];
+    unsigned long long* stats_dev;
+};
+
+// error channel (cb2_api.cu)
+int cb2_fail(int code, const char* fmt, ...);
+int cb2_cuda_check(cudaError_t e, const char* what);
+#define CB2_CUDA(call)                                         \
+    do {                                                       \
+        int _rc = cb2_cuda_check((call), #call);               \
+        if (_rc != CB2_OK) return _rc;                         \
+    } while (0)
+
+// kernels (cb2_emission.cu / cb2_raytransfer.cu)
+int cb2_launch_emission(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                        unsigned long long* stats_dev, cudaStream_t stream);
+int cb2_emission_config(cb2_scene* sc);
+int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t stream);
+int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate,
+                  int64_t* row_offset, int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t stream);
+int cb2_launch_scan(int64_t* counts_inout, int64_t n, cudaStream_t stream);

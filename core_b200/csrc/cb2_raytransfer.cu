@@ -1,0 +1,193 @@
+// cb2_raytransfer.cu — ray-transfer (geometry matrix) path-length sampler on sm_100a.
+//
+// Restates CylindricalRayTransferIntegrator.integrate / CartesianRayTransferIntegrator.integrate
+// (cherab/tools/raytransfer/emitters.pyx:88-224): fixed-step midpoint sampling t = (it + 1/2) dt with
+// n = max(min_samples, int(L/step)), cell index by C truncation, `res += dt` per step spent in a mapped cell.
+// The per-source result is dt * (number of steps whose cell maps to that source), so the sequential run detection of
+// the reference becomes a histogram: one warp per ray, 32 consecutive steps per iteration, lanes that start a run of
+// equal sources add run_length * dt to that source with one atomic.
+//
+// Index decisions must match the reference bit for bit (a flipped step moves a whole dt between voxels),
+// so the position -> index arithmetic is IEEE float64 with explicit _rn intrinsics in the reference's expression
+// order (no FMA contraction: the reference is compiled for x86-64 without FMA).
+//
+// Output modes: 0 dense rows (small `bins`), 1 count distinct sources per ray, 2 fill CSR rows.  Modes 1/2 use a
+// per-warp dense double[bins] scratch row in HBM (only touched entries are visited; a touched list resets them).
+#include <math.h>
+
+#include "cb2_internal.h"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// m[0]*x + m[1]*y + m[2]*z + m[3], left to right
+__device__ __forceinline__ double row_point(const double* m, double x, double y, double z) {
+    return add_rn(add_rn(add_rn(mul_rn(m[0], x), mul_rn(m[1], y)), mul_rn(m[2], z)), m[3]);
+}
+
+__device__ __forceinline__ int rt_source(const DevRT& R, const double* st, const double* dir, double dt, int it) {
+    const double t = mul_rn(add_rn((double)it, 0.5), dt);
+    const double x = add_rn(st[0], mul_rn(dir[0], t));
+    const double y = add_rn(st[1], mul_rn(dir[1], t));
+    const double z = add_rn(st[2], mul_rn(dir[2], t));
+    int i0, i1, i2;
+    if (R.kind == CB2_RT_CYLINDRICAL) {
+        i2 = (int)__ddiv_rn(z, R.s2);
+        const double r = __dsqrt_rn(add_rn(mul_rn(x, x), mul_rn(y, y)));
+        i0 = (int)__ddiv_rn(add_rn(r, -R.rmin), R.s0);
+        if (R.n1 == 1) i1 = 0;
+        else {
+            double phi = mul_rn(180.0 / M_PI, atan2(y, x));
+            phi = fmod(add_rn(phi, 360.0), R.period);
+            i1 = (int)__ddiv_rn(phi, R.s1);
+        }
+    } else {
+        i0 = (int)__ddiv_rn(x, R.s0);
+        i1 = (int)__ddiv_rn(y, R.s1);
+        i2 = (int)__ddiv_rn(z, R.s2);
+    }
+    // the reference would raise IndexError outside the grid; such steps are skipped
+    if (i0 < 0 || i0 >= R.n0 || i1 < 0 || i1 >= R.n1 || i2 < 0 || i2 >= R.n2) return -1;
+    return __ldg(R.voxel_map + ((size_t)i0 * R.n1 + i1) * R.n2 + i2);
+}
+
+__global__ void __launch_bounds__(256)
+rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* __restrict__ row_offset,
+          int32_t* __restrict__ columns, double* __restrict__ lengths, double* __restrict__ scratch_all,
+          int32_t* __restrict__ touched_all, int touch_cap, unsigned long long* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double* scratch = scratch_all ? scratch_all + (size_t)gw * R.bins : nullptr;
+    int32_t* touched = touched_all ? touched_all + (size_t)gw * touch_cap : nullptr;
+    unsigned long long steps = 0, overflow = 0;
+
+    for (int64_t ray = gw; ray < rays.n_rays; ray += nwarps) {
+        double* row = (mode == 0) ? dense + (size_t)ray * R.bins : scratch;
+        int count = 0;
+        const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+        const double dx = rays.direction[3 * ray], dy = rays.direction[3 * ray + 1], dz = rays.direction[3 * ray + 2];
+        for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+            const double t0 = rays.seg_t0[sg], t1 = rays.seg_t1[sg];
+            // start_point = far end, end_point = near end (Raysect convention), both to local space
+            const double swx = add_rn(ox, mul_rn(t1, dx)), swy = add_rn(oy, mul_rn(t1, dy)), swz = add_rn(oz, mul_rn(t1, dz));
+            const double ewx = add_rn(ox, mul_rn(t0, dx)), ewy = add_rn(oy, mul_rn(t0, dy)), ewz = add_rn(oz, mul_rn(t0, dz));
+            double st[3], en[3], dir[3];
+            for (int k = 0; k < 3; k++) {
+                st[k] = row_point(R.w2l + 4 * k, swx, swy, swz);
+                en[k] = row_point(R.w2l + 4 * k, ewx, ewy, ewz);
+                dir[k] = add_rn(en[k], -st[k]);
+            }
+            const double length = __dsqrt_rn(add_rn(add_rn(mul_rn(dir[0], dir[0]), mul_rn(dir[1], dir[1])), mul_rn(dir[2], dir[2])));
+            if (length < mul_rn(0.1, R.step)) continue;                // emitters.pyx:104-105
+            for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+            int n = (int)__ddiv_rn(length, R.step);
+            if (n < R.min_samples) n = R.min_samples;
+            const double dt = __ddiv_rn(length, (double)n);
+            if (lane == 0) steps += (unsigned long long)n;
+            for (int it0 = 0; it0 < n; it0 += 32) {
+                const int it = it0 + lane;
+                const int src = (it < n) ? rt_source(R, st, dir, dt, it) : -2;
+                int prev = __shfl_up_sync(FULL, src, 1);
+                const bool head = (lane == 0) || (src != prev);
+                const unsigned heads = __ballot_sync(FULL, head);
+                bool first = false;
+                if (head && src >= 0) {
+                    const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+                    const int next = higher ? (__ffs(higher) - 1) : 32;
+                    const double add = mul_rn((double)(next - lane), dt);
+                    const double old = atomicAdd(row + src, add);
+                    first = (mode != 0) && (old == 0.0);
+                }
+                if (mode != 0) {
+                    const unsigned fm = __ballot_sync(FULL, first);
+                    if (first) {
+                        const int pos = count + __popc(fm & ((1u << lane) - 1u));
+                        if (pos < touch_cap) touched[pos] = src; else overflow++;
+                    }
+                    count += __popc(fm);
+                }
+            }
+        }
+        if (mode != 0) {
+            __threadfence();
+            __syncwarp();
+            const int cnt = min(count, touch_cap);
+            const int64_t off = (mode == 2) ? row_offset[ray] : 0;
+            for (int pos = lane; pos < cnt; pos += 32) {
+                const int src = touched[pos];
+                const double v = __ldcg(scratch + src);
+                __stcg(scratch + src, 0.0);
+                if (mode == 2) { columns[off + pos] = src; lengths[off + pos] = v; }
+            }
+            if (mode == 1 && lane == 0) row_offset[ray] = cnt;
+            __syncwarp();
+        }
+    }
+    if (mode == 1 && gw == 0 && lane == 0) row_offset[rays.n_rays] = 0;
+    if (stats) {
+        for (int off = 16; off > 0; off >>= 1) overflow += __shfl_down_sync(FULL, overflow, off);
+        if (lane == 0) {
+            if (steps) atomicAdd(stats + 4, steps);
+            if (overflow) atomicAdd(stats + 5, overflow);
+        }
+    }
+}
+
+int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate, int64_t* row_offset,
+                  int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t st) {
+    (void)accumulate;
+    const int threads = 256;
+    int64_t warps_needed = rays.n_rays;
+    int64_t warps = mode == 0 ? warps_needed : (warps_needed < sc->n_warps ? warps_needed : sc->n_warps);
+    if (mode == 0 && warps > (int64_t)sc->n_warps * 4) warps = (int64_t)sc->n_warps * 4;
+    int64_t blocks = (warps * 32 + threads - 1) / threads;
+    if (mode != 0 && blocks * (threads / 32) > sc->n_warps) blocks = sc->n_warps / (threads / 32);
+    if (blocks < 1) blocks = 1;
+    rt_kernel<<<(unsigned)blocks, threads, 0, st>>>(sc->rt, rays, mode, dense_out, row_offset, columns, lengths,
+                                                    mode == 0 ? nullptr : sc->scratch, mode == 0 ? nullptr : sc->touched,
+                                                    sc->touch_cap, stats_dev);
+    return cb2_cuda_check(cudaGetLastError(), "rt_kernel launch");
+}
+
+// in-place exclusive scan of int64 counts (single block; n is at most a few million rays)
+__global__ void __launch_bounds__(1024) scan_kernel(int64_t* __restrict__ a, int64_t n) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + tid;
+        const int64_t v = (i < n) ? a[i] : 0;
+        int64_t x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t y = __shfl_up_sync(FULL, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                const int64_t y = __shfl_up_sync(FULL, w, off);
+                if (lane >= off) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t incl = x + (warp ? warp_sums[warp - 1] : 0) + carry;
+        if (i < n) a[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = incl;
+        __syncthreads();
+    }
+}
+
+int cb2_launch_scan(int64_t* counts_inout, int64_t n, cudaStream_t st) {
+    scan_kernel<<<1, 1024, 0, st>>>(counts_inout, n);
+    return cb2_cuda_check(cudaGetLastError(), "scan_kernel launch");
+}

@@ -97,7 +97,7 @@ class RayTransferObject:
         return [np.where(self._voxel_map == i) for i in range(self._bins)]
 
     def descriptor(self):
-        """(cb2_rt_desc, keepalive) for the CUDA library / oracle."""
+        """(cb2_rt_desc, keepalive) in the layout of include/cherab_b200.h."""
         d = _abi.RTDesc()
         d.abi_version = _abi.ABI_VERSION
         d.kind = self.kind

