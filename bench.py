@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement: Generomak camera spectral ray samples/s.
+
+Workload (BASELINE.json configs[2]): Generomak full blended plasma, 1024x1024 pinhole camera at
+(2.3, 0, 1.25) looking at (1.0, 0.8, -0.5), 2048 bins on [390, 700] nm, models = H alpha..delta x {Excitation,
+Recombination} (GaussianLine) + Bremsstrahlung, synthetic ADF15-shaped rates, step 1 mm.  One "step" = one pass of the
+whole camera with one of the 16 stratified sub-pixel sample positions (16 steps = the 16 samples/pixel frame); the
+pass accumulates into the device-resident frame.  With N > 1 (torchrun) the 16x16-pixel image tiles are dealt
+round-robin to the ranks (fixed total work: strong scaling); NCCL is used only to gather the frame (e2e leg).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pixels P] [--bins B]
+
+One JSON line on stdout (rank 0).  `value` is device-timed (CUDA events, inputs resident in HBM); `e2e` is the same
+metric through the host-buffer C-ABI call (ray segments H2D + kernel + frame D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Generomak camera spectral ray samples/s (M)"
+UNIT = "Msamples/s"
+CAMERA_POS, CAMERA_TARGET = (2.3, 0.0, 1.25), (1.0, 0.8, -0.5)
+TILE = 16
+
+# Algorithmic work per unit (DESIGN.md "Measurement"): minimal formulation, counted from the kernel's own counters
+F_GAUSS_BIN = 14.0      # flop per Gaussian bin evaluation (5-term series form: 7 FMA-class) + 1 SFU
+F_BREMS_BIN = 10.0      # flop per (sample, bin, quadrature point) + 1 SFU
+F_FIXED_BASE = 20.0 + 3 * 40.0 + 30.0   # transform/R, three bicubics, masks/blend
+
+
+def build_scene(bins, lo=390.0, hi=700.0):
+    import core_b200 as cb
+    from core_b200 import generomak
+    plasma = generomak.get_plasma()
+    lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4, 5, 6)]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.RecombinationLine(l) for l in lines] + [cb.Bremsstrahlung()]
+    flat = cb.flatten_scene(plasma, lo, hi, bins)
+    return plasma, flat
+
+
+def fixed_flops_per_sample(flat):
+    d = flat.desc
+    n_line = sum(1 for i in range(d.n_models) if d.models[i].kind != 2)
+    species = {d.models[i].species for i in range(d.n_models) if d.models[i].kind != 2}
+    n_charged = sum(1 for i in range(d.n_species) if d.species[i].charge > 0) if n_line < d.n_models else 0
+    p = 2 + 4 * len(species) + n_charged
+    return F_FIXED_BASE + 10.0 * p + 60.0 * n_line
+
+
+def rank_pixels(pixels, rank, world):
+    """Pixel indices (ix * ny + iy) of the 16x16 tiles dealt round-robin to `rank`, tile-major order."""
+    nx = ny = pixels
+    tx, ty = (nx + TILE - 1) // TILE, (ny + TILE - 1) // TILE
+    tiles = np.arange(tx * ty)[rank::world]
+    ox, oy = np.meshgrid(np.arange(TILE), np.arange(TILE), indexing="ij")
+    ix = (tiles // ty)[:, None] * TILE + ox.ravel()[None, :]
+    iy = (tiles % ty)[:, None] * TILE + oy.ravel()[None, :]
+    ok = (ix < nx) & (iy < ny)
+    return (ix * ny + iy)[ok]
+
+
+def make_rays(plasma, pixels, pixel_index, sample_id):
+    import core_b200 as cb
+    sx, sy = cb.stratified_offsets(4)[sample_id % 16]
+    cam = cb.PinholeCamera((pixels, pixels), fov=45, transform=cb.look_at(CAMERA_POS, CAMERA_TARGET))
+    o, d = cam.rays(sx, sy, pixel_index)
+    return cb.ray_segments(plasma.geometry, o, d, plasma.geometry_to_world())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(flat, plasma, pixels, n_rays, threads, seed=1234):
+    """Oracle (CPU restatement, fp64) timed on a bounded sample of the same workload."""
+    from oracle import oracle
+    rng = np.random.default_rng(seed)
+    pix = np.sort(rng.choice(pixels * pixels, size=n_rays, replace=False))
+    rays = make_rays(plasma, pixels, pix, 0)
+    t0 = time.perf_counter()
+    _, st = oracle.emission_render(flat, rays, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return st["samples"] / dt * 1e-6, st["samples"], dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the real Cython/Raysect path cannot be built here —
+    raysect is absent) on the box's host cores, same config/metric, each step a bounded sample."""
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    from oracle import oracle
+    oracle.build()
+    plasma, flat = build_scene(args.bins)
+    threads = os.cpu_count() or 1
+    n_rays = args.ref_rays
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, samples, dt = cpu_baseline(flat, plasma, args.pixels, n_rays, threads, seed=1234 + k)
+        if k >= args.warmup:
+            vals.append((samples, dt))
+    tot_s = sum(s for s, _ in vals)
+    tot_t = sum(t for _, t in vals)
+    value = tot_s / tot_t * 1e-6
+    sample = "%d rays of the %dx%d frame per step (random pixels, seeded), %d bins, all models" % (n_rays, args.pixels, args.pixels, args.bins)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_t / max(len(vals), 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "Generomak full-frame %dx%d pinhole camera, H alpha..delta x {excitation, recombination} + Bremsstrahlung, "
+                        "%d bins on [390,700] nm, 1 of 16 stratified samples/pixel per step, step 1 mm" % (args.pixels, args.pixels, args.bins),
+            "pixels": [args.pixels, args.pixels], "bins": args.bins, "models": 9, "tiles": "16x16 px round-robin over %d rank(s)" % world,
+            "l2": "the %0.1f GB fp32 frame written per step exceeds L2; scene tables (few MB) are L2-resident by design"
+                  % (args.pixels * args.pixels * args.bins * 4 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pixels", type=int, default=1024)
+    ap.add_argument("--bins", type=int, default=2048)
+    ap.add_argument("--ref-rays", type=int, default=8)
+    ap.add_argument("--cpu-rays", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from core_b200.engine import DeviceRays, EmissionScene, measure_peaks
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    plasma, flat = build_scene(args.bins)
+    scene = EmissionScene(flat, device=local_rank)
+    pix = rank_pixels(args.pixels, rank, world)
+    n_pass = args.warmup + args.steps
+    host_rays = [make_rays(plasma, args.pixels, pix, k) for k in range(min(n_pass, 16))]
+    dev_rays = [DeviceRays(r, device=dev) for r in host_rays]
+    frame = torch.zeros((pix.size, args.bins), dtype=torch.float32, device=dev)
+    stats = torch.zeros(6, dtype=torch.int64, device=dev)
+
+    peaks = measure_peaks(local_rank) if rank == 0 else None
+
+    def step(k):
+        scene.render_device(dev_rays[k % len(dev_rays)], frame, scale=1.0 / 16.0, accumulate=(k % 16) != 0, stats=stats)
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    stats.zero_()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.warmup, args.warmup + args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    st = stats.clone()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    st = st.cpu().numpy()
+    samples, gauss, brems, ood = int(st[0]), int(st[1]), int(st[3]), int(st[5])
+    value = samples / (ms * 1e-3) * 1e-6
+
+    # ---- e2e: host buffers through the C-ABI call (H2D rays + kernel + [NCCL gather] + D2H frame) ----
+    e2e = None
+    if not args.no_e2e:
+        host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
+        e2e_steps = args.steps
+        # warm the staging buffers once
+        scene.render(host_rays[0], out=host_frame)
+        gathered = None
+        if world > 1:
+            counts = [rank_pixels(args.pixels, r, world).size for r in range(world)]
+            gathered = [torch.empty((c, args.bins), dtype=torch.float32, device=dev) for c in counts] if rank == 0 else None
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_samples = 0
+        for k in range(e2e_steps):
+            r = host_rays[(args.warmup + k) % len(host_rays)]
+            if world == 1:
+                _, s = scene.render(r, out=host_frame)
+                e2e_samples += s["samples"]
+            else:
+                # per rank: rays H2D + kernel on device, gather tiles to rank 0 over NCCL, rank 0 reads the frame back
+                dr = DeviceRays(r, device=dev)
+                scene.render_device(dr, frame, scale=1.0, accumulate=False, stats=stats)
+                dist.gather(frame, gathered, dst=0)
+                if rank == 0:
+                    host_frame[:] = gathered[0].cpu().numpy()
+                torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            e2e_samples = samples * e2e_steps // max(args.steps, 1)
+        h2d = sum(host_rays[(args.warmup + k) % len(host_rays)].origin.nbytes * 2 + host_rays[(args.warmup + k) % len(host_rays)].seg_offset.nbytes
+                  + host_rays[(args.warmup + k) % len(host_rays)].seg_t0.nbytes * 2 for k in range(e2e_steps)) // max(e2e_steps, 1)
+        e2e = {"value": e2e_samples / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(pix.size * args.bins * 4 + 48), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+
+    if rank == 0:
+        fixed = fixed_flops_per_sample(flat)
+        nq = 1
+        flops = F_GAUSS_BIN * gauss + F_BREMS_BIN * brems * nq + fixed * samples
+        sfu = gauss + brems * nq
+        launch_ms = ms / args.steps
+        ach_fp32 = flops / world / (ms * 1e-3) * 1e-12          # per GPU
+        ach_sfu = sfu / world / (ms * 1e-3) * 1e-12
+        frame_bytes = pix.size * args.bins * 4.0
+        peaks_file = {}
+        try:
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+        r_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
+                  "frac": ach_fp32 / peaks["fp32_tflops"], "traffic": None}
+        r_sfu = {"bound": "sfu", "achieved": ach_sfu, "peak": peaks["sfu_tops"], "unit": "Tops/s",
+                 "frac": ach_sfu / peaks["sfu_tops"], "traffic": None}
+        roofline = dict(r_sfu if r_sfu["frac"] > r_fp32["frac"] else r_fp32)
+        roofline.update({"kernel": "emission_kernel<NW=8,BPL=8,BREMS=1>", "launch_ms": launch_ms,
+                         "peak_source": "measured live (cb2_measure_peaks: FFMA / MUFU.EX2 issue-rate microbenchmarks)",
+                         "algorithmic": {"samples": samples, "gaussian_bin_evals": gauss, "brems_bin_evals": brems,
+                                         "flop_per_gauss_bin": F_GAUSS_BIN, "flop_per_brems_bin": F_BREMS_BIN,
+                                         "fixed_flop_per_sample": fixed, "flop_per_sample": flops / max(samples, 1)},
+                         "fp32": r_fp32, "sfu": r_sfu,
+                         "hbm": {"achieved": frame_bytes * (2 if True else 1) / (launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                                 "note": "frame read-modify-write only; " + ("of measured" if "hbm_gbs" in peaks_file else "of fallback")}})
+        threads = os.cpu_count() or 1
+        cpu_v, cpu_s, cpu_t = cpu_baseline(flat, plasma, args.pixels, args.cpu_rays, threads)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "gpu_launches": args.steps,
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": "%d rays (random pixels, seeded) of the same frame, %d samples in %.1f s" % (args.cpu_rays, cpu_s, cpu_t)},
+                "out_of_domain_samples": ood}
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

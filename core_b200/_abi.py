@@ -105,7 +105,7 @@ class RTDesc(C.Structure):
 
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
-    "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_scene_create", "cb2_scene_destroy",
+    "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
     "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
 ]
@@ -127,6 +127,7 @@ def load_library():
     lib.cb2_abi_version.restype = C.c_int
     lib.cb2_last_error.restype = C.c_char_p
     lib.cb2_device_count.restype = C.c_int
+    lib.cb2_measure_peaks.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p]
     lib.cb2_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_scene_destroy.argtypes = [vp]
     lib.cb2_emission_render.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, C.POINTER(Stats)]

@@ -315,6 +315,36 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
     }
     o.poly = A.upload(edges);
     o.poly_xmin = (float)pxmin; o.poly_xmax = (float)pxmax; o.poly_ymin = (float)pymin; o.poly_ymax = (float)pymax;
+    {
+        // classification grid: cells overlapped by the bounding box of any edge (grown by one cell) are boundary cells,
+        // the others take the exact even-odd result of their centre
+        const int gx = 96, gy = 160;
+        o.pgx = gx; o.pgy = gy;
+        const double icx = gx / (pxmax - pxmin), icy = gy / (pymax - pymin);
+        o.p_icx = (float)icx; o.p_icy = (float)icy;
+        std::vector<unsigned char> cls((size_t)gx * gy, 0);
+        for (int i = 0; i < gx; i++)
+            for (int j = 0; j < gy; j++) {
+                const double cx = pxmin + (i + 0.5) / icx, cy = pymin + (j + 0.5) / icy;
+                bool in = false;
+                for (int a = 0, b = e.n_lcfs - 1; a < e.n_lcfs; b = a++) {
+                    const double xi = e.lcfs_polygon[2 * a], yi = e.lcfs_polygon[2 * a + 1];
+                    const double xj = e.lcfs_polygon[2 * b], yj = e.lcfs_polygon[2 * b + 1];
+                    if (((yi > cy) != (yj > cy)) && (cx < (xj - xi) * (cy - yi) / (yj - yi) + xi)) in = !in;
+                }
+                cls[(size_t)i * gy + j] = in ? 1 : 0;
+            }
+        for (int a = 0, b = e.n_lcfs - 1; a < e.n_lcfs; b = a++) {
+            const double xi = e.lcfs_polygon[2 * a], yi = e.lcfs_polygon[2 * a + 1];
+            const double xj = e.lcfs_polygon[2 * b], yj = e.lcfs_polygon[2 * b + 1];
+            int i0 = (int)floor((fmin(xi, xj) - pxmin) * icx) - 1, i1 = (int)floor((fmax(xi, xj) - pxmin) * icx) + 1;
+            int j0 = (int)floor((fmin(yi, yj) - pymin) * icy) - 1, j1 = (int)floor((fmax(yi, yj) - pymin) * icy) + 1;
+            i0 = std::max(i0, 0); j0 = std::max(j0, 0); i1 = std::min(i1, gx - 1); j1 = std::min(j1, gy - 1);
+            for (int i = i0; i <= i1; i++)
+                for (int j = j0; j <= j1; j++) cls[(size_t)i * gy + j] = 2;
+        }
+        o.poly_cls = A.upload(cls);
+    }
     if (ax.n_mask < 1 || ax.n_mask > 8) return cb2_fail(CB2_ERR_VALUE, "blend mask table must have 1..8 points");
     o.n_mask = ax.n_mask;
     for (int i = 0; i < ax.n_mask; i++) { o.mask_x[i] = (float)ax.mask_x[i]; o.mask_y[i] = (float)ax.mask_y[i]; }
@@ -332,8 +362,10 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
         int gy = std::min(std::max((int)ceil(gx * aspect), 8), 2048);
         o.gx = gx; o.gy = gy;
         o.mx0 = (float)xmin; o.my0 = (float)ymin;
+        o.mx0_d = xmin; o.my0_d = ymin;
         const double icx = gx / (xmax - xmin) * (1.0 - 1e-7), icy = gy / (ymax - ymin) * (1.0 - 1e-7);
         o.inv_cx = (float)icx; o.inv_cy = (float)icy;
+        o.inv_cx_d = icx; o.inv_cy_d = icy;
         std::vector<int> count((size_t)gx * gy + 1, 0), start((size_t)gx * gy + 1, 0), tris;
         for (int pass = 0; pass < 2; pass++) {
             if (pass == 1) {
@@ -362,11 +394,11 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
                     }
             }
         }
-        std::vector<float2> tv((size_t)ax.n_triangles * 3);
+        std::vector<double2> tv((size_t)ax.n_triangles * 3);
         for (int t = 0; t < ax.n_triangles; t++)
             for (int k = 0; k < 3; k++) {
                 const int v = ax.triangles[3 * t + k];
-                tv[(size_t)t * 3 + k] = make_float2((float)ax.vertices[2 * v], (float)ax.vertices[2 * v + 1]);
+                tv[(size_t)t * 3 + k] = make_double2(ax.vertices[2 * v], ax.vertices[2 * v + 1]);
             }
         o.cell_start = A.upload(start);
         o.cell_tris = A.upload(tris);
@@ -385,8 +417,11 @@ static const double HC_EV_NM = 1239.8419738620933;
 static void set_comp(DevScene& S, int slot, double lambda, int type) {
     const double c0 = (lambda - S.min_wavelength_d) / S.delta_d;
     const double ci = floor(c0);
-    S.comps[slot].c0_int = (int)fmin(fmax(ci, -1.0e9), 1.0e9);
-    S.comps[slot].c0_frac = (float)(c0 - ci);
+    // bin ranges are stored relative to c0_int as packed int16 pairs: keep |c0_int| <= 28000 (a line that far outside
+    // the window only matters if it is thousands of bins wide; the fraction then absorbs the remainder)
+    const double cic = fmin(fmax(ci, -28000.0), 28000.0);
+    S.comps[slot].c0_int = (int)cic;
+    S.comps[slot].c0_frac = (float)(c0 - cic);
     S.comps[slot].dlambda = 0.f;
     S.comps[slot].type = type;
 }
@@ -515,7 +550,12 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
             if (bound[n] < 2e-6) { nq = n; break; }
     }
     if (nq > 4) nq = 4;
+    // per-sample choice on the device: the one-point (bin centre) rule wherever its error model is below 2e-6,
+    // otherwise this nq-point Gauss-Legendre rule (at least 2 points unless the caller forces 1)
+    if (d.brems_quadrature <= 0 && nq < 2) nq = 2;
     b.nq = nq;
+    b.mid_c1 = (float)(0.5 * delta * HC_EV_NM / (lmin * lmin));
+    b.mid_c0 = (float)(0.5 * delta * 2.0 / lmin);
     double gx[4], gw[4];
     gl_nodes(nq, gx, gw);
     const double lref = log10(0.5 * (lmin + lmax));
@@ -527,6 +567,14 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
             tab[(size_t)i * nq + q] = make_float4((float)rho, (float)(2.0 * log2(rho)), (float)(log10(lam) - lref), (float)(0.5 * gw[q]));
         }
     b.bin_tab = A.upload(tab);
+    {
+        std::vector<float4> tab1((size_t)S.bins_padded);
+        for (int i = 0; i < S.bins_padded; i++) {
+            const double lam = lmin + delta * (i + 0.5), rho = 1.0 / lam;
+            tab1[i] = make_float4((float)rho, (float)(2.0 * log2(rho)), (float)(log10(lam) - lref), 1.0f);
+        }
+        b.bin_tab1 = A.upload(tab1);
+    }
     b.lref = (float)lref;
     b.log_hc = (float)log10(HC_EV_NM);
     b.exp_coef = (float)(PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9 / ELEMENTARY_CHARGE * 1.4426950408889634);

@@ -33,7 +33,7 @@
 #define L2E 1.4426950408889634f
 #define RECIP_4_PI 0.07957747154594767f
 #define INV_SQRT_PI 0.5641895835477563f
-#define H_SERIES_MAX 0.0625f
+#define H_SERIES_MAX 0.36f
 #define RYDBERG_EV 13.605693122994f
 #define BOHR_MAGNETON 5.78838180123e-5f
 #define HC_EV_NM_F 1239.8419738620933f
@@ -140,6 +140,10 @@ struct AxCtx {
 
 __device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py) {
     if (px < A.poly_xmin || px > A.poly_xmax || py < A.poly_ymin || py > A.poly_ymax) return false;
+    // coarse grid: only boundary cells need the edge loop (even-odd crossing test, mask.pyx:53-67)
+    const int gi = min((int)((px - A.poly_xmin) * A.p_icx), A.pgx - 1), gj = min((int)((py - A.poly_ymin) * A.p_icy), A.pgy - 1);
+    const int cls = __ldg(A.poly_cls + gi * A.pgy + gj);
+    if (cls != 2) return cls == 1;
     int crossings = 0;
     for (int i = 0; i < A.n_poly; i++) {
         const float4 e = __ldg(A.poly + i);  // (xi, yi, yj, slope)
@@ -148,10 +152,12 @@ __device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, f
     return crossings & 1;
 }
 
-__device__ __forceinline__ int mesh_locate(const DevAxisym& A, float r, float z) {
+// Discrete2DMesh lookup in float64 with the reference's operation order (no FMA contraction): the edge data is
+// piecewise constant, so a sample that lands on the other side of a triangle edge changes a pixel visibly.
+__device__ __forceinline__ int mesh_locate(const DevAxisym& A, double r, double z) {
     if (A.n_tri <= 0) return -1;
-    const float fx = (r - A.mx0) * A.inv_cx, fy = (z - A.my0) * A.inv_cy;
-    if (!(fx >= 0.f) || !(fy >= 0.f)) return -1;
+    const double fx = (r - A.mx0_d) * A.inv_cx_d, fy = (z - A.my0_d) * A.inv_cy_d;
+    if (!(fx >= 0.0) || !(fy >= 0.0)) return -1;
     const int i = (int)fx, j = (int)fy;
     if (i >= A.gx || j >= A.gy) return -1;
     const int cell = i * A.gy + j;
@@ -159,19 +165,22 @@ __device__ __forceinline__ int mesh_locate(const DevAxisym& A, float r, float z)
     const int k1 = __ldg(A.cell_start + cell + 1);
     for (int k = __ldg(A.cell_start + cell); k < k1; k++) {
         const int t = __ldg(A.cell_tris + k);
-        const float2 a = __ldg(A.tri + 3 * t), b = __ldg(A.tri + 3 * t + 1), c = __ldg(A.tri + 3 * t + 2);
-        const float d1 = (r - b.x) * (a.y - b.y) - (a.x - b.x) * (z - b.y);
-        const float d2 = (r - c.x) * (b.y - c.y) - (b.x - c.x) * (z - c.y);
-        const float d3 = (r - a.x) * (c.y - a.y) - (c.x - a.x) * (z - a.y);
+        const double2 a = __ldg(A.tri + 3 * t), b = __ldg(A.tri + 3 * t + 1), c = __ldg(A.tri + 3 * t + 2);
+        const double d1 = __dsub_rn(__dmul_rn(__dsub_rn(r, b.x), __dsub_rn(a.y, b.y)), __dmul_rn(__dsub_rn(a.x, b.x), __dsub_rn(z, b.y)));
+        const double d2 = __dsub_rn(__dmul_rn(__dsub_rn(r, c.x), __dsub_rn(b.y, c.y)), __dmul_rn(__dsub_rn(b.x, c.x), __dsub_rn(z, c.y)));
+        const double d3 = __dsub_rn(__dmul_rn(__dsub_rn(r, a.x), __dsub_rn(c.y, a.y)), __dmul_rn(__dsub_rn(c.x, a.x), __dsub_rn(z, a.y)));
         const bool neg = (d1 < 0) || (d2 < 0) || (d3 < 0), pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
         if (!(neg && pos) && (best < 0 || t < best)) best = t;
     }
     return best;
 }
 
-__device__ __forceinline__ void ax_setup(const DevScene& S, float x, float y, float z, AxCtx& c, unsigned& ood) {
+__device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd, double zd, AxCtx& c, unsigned& ood) {
     const DevAxisym& A = S.ax;
-    c.R = sqrtf(x * x + y * y);
+    const float x = (float)xd, y = (float)yd, z = (float)zd;
+    // R in float64 exactly as AxisymmetricMapper computes it (mappers.pyx:264): it feeds the exact triangle test
+    const double r64 = A.present ? __dsqrt_rn(__dadd_rn(__dmul_rn(xd, xd), __dmul_rn(yd, yd))) : 0.0;
+    c.R = A.present ? (float)r64 : sqrtf(x * x + y * y);
     c.Z = z;
     const float inv_r = c.R > 0.f ? 1.0f / c.R : 0.f;
     c.cphi = c.R > 0.f ? x * inv_r : 1.f;
@@ -200,7 +209,7 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, float x, float y, fl
             }
         c.m = m;
     }
-    if (c.m < 1.0f) c.tri = mesh_locate(A, c.R, c.Z);
+    if (c.m < 1.0f) c.tri = mesh_locate(A, r64, zd);
     if (c.m > 0.0f) locate1d(A.core, c.psi, c.ci, c.ct);
     const bool want_pol = (S.need_pol && c.m > 0.f) || S.need_b;
     if (want_pol) {
@@ -290,14 +299,29 @@ __device__ __forceinline__ float eval_pec_log(const DevModel& M, float lne, floa
 // ------------------------------------------------------------------------------------------------------------------
 struct RecWriter {
     float4* rec;      // [ncomp][2][NT]
-    int* rng;         // [ncomp][2] (lo, hi) bounding bin ranges of this chunk, relative bins
-    int nt, tid;
+    int* rng;         // [ncomp][NG][2] (lo, hi) bounding bin ranges per group of 32 samples, relative bins
+    int nt, tid, ng, group;
     int bins;
     unsigned long long gauss_evals;
 };
 
+#define SQRT_L2E 1.2011224087864498f
+#define INV_L2E 0.6931471805599453f
+
+__device__ __forceinline__ float pack_range(int lo, int hi) { return __int_as_float((lo & 0xffff) | (hi << 16)); }
+__device__ __forceinline__ void unpack_range(float p, int& lo, int& hi) {
+    const int v = __float_as_int(p);
+    lo = (int)(short)(v & 0xffff);
+    hi = v >> 16;
+}
+
 // Write one Gaussian component: centre cf (bins, relative to the slot's integer origin c0_int), width sigma_b (bins),
 // amplitude amp = weight * radiance / delta_wavelength.   (add_gaussian_line, gaussian.pyx:40-90)
+// record a = (kx, xoff, s0, s1), b = (s2, s3, s4, packed [lo, hi)):
+//   series path (s1 >= 0): x' = rel*kx + xoff = sqrt(log2 e) * (bin centre - line centre)/(sqrt2 sigma), m = x'^2,
+//                          value = exp2(-m) * (s0 + m (s1 + m (s2 + m (s3 + m s4))))   [amplitude and 1/log2 e folded in]
+//                          = amp * kb/sqrt(pi) exp(-x^2) sum_{n<=4} H_2n(x) h^2n/(2n+1)!,  h = kb/2 <= 0.36
+//   erfc path   (s1 <  0): x = rel*kx + xoff at the bin's UPPER edge, s0 = amplitude  (sub-bin lines, sigma < 1 bin)
 __device__ __forceinline__ void put_gaussian(RecWriter& W, const DevComp& cs, int slot, float cf, float sigma_b, float amp) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (amp > 0.f && sigma_b > 0.f) {
@@ -309,24 +333,32 @@ __device__ __forceinline__ void put_gaussian(RecWriter& W, const DevComp& cs, in
             if (hi > lo) {
                 const float kb = 0.70710678f / sigma_b;          // delta / (sqrt(2) sigma), per bin
                 const float h = 0.5f * kb;
-                a.x = kb;
-                if (h < H_SERIES_MAX) {
-                    const float h2 = h * h, h4 = h2 * h2;
-                    a.y = (0.5f - cf) * kb;                      // x at bin centre = rel * kb + a.y
-                    a.z = amp * kb * INV_SQRT_PI;
-                    a.w = 1.0f - h2 * (1.0f / 3.0f) + h4 * 0.1f; // s0 >= 0 marks the series path
-                    b.x = h2 * (2.0f / 3.0f) - h4 * 0.4f;
-                    b.y = h4 * (4.0f / 30.0f);
+                if (h <= H_SERIES_MAX) {
+                    const float h2 = h * h;
+                    const float t1 = h2 * (1.0f / 6.0f), t2 = h2 * h2 * (1.0f / 120.0f), t3 = h2 * h2 * h2 * (1.0f / 5040.0f),
+                                t4 = h2 * h2 * h2 * h2 * (1.0f / 362880.0f);
+                    const float A = amp * kb * INV_SQRT_PI;
+                    a.x = kb * SQRT_L2E;
+                    a.y = (0.5f - cf) * a.x;
+                    a.z = A * (1.0f - 2.0f * t1 + 12.0f * t2 - 120.0f * t3 + 1680.0f * t4);
+                    a.w = A * (4.0f * t1 - 48.0f * t2 + 720.0f * t3 - 13440.0f * t4) * INV_L2E;
+                    b.x = A * (16.0f * t2 - 480.0f * t3 + 13440.0f * t4) * (INV_L2E * INV_L2E);
+                    b.y = A * (64.0f * t3 - 3584.0f * t4) * (INV_L2E * INV_L2E * INV_L2E);
+                    b.z = A * (256.0f * t4) * (INV_L2E * INV_L2E * INV_L2E * INV_L2E);
                 } else {
+                    a.x = kb;
                     a.y = (1.0f - cf) * kb;                      // x at the bin's upper edge
                     a.z = amp;
                     a.w = -1.0f;                                 // erfc-difference path
                 }
-                b.z = __int_as_float(lo);
-                b.w = __int_as_float(hi);
-                atomicMin(&W.rng[2 * slot], lo);
-                atomicMax(&W.rng[2 * slot + 1], hi);
-                W.gauss_evals += (unsigned long long)(hi - lo) + 1ull;
+                if (a.z > 0.f) {
+                    b.w = pack_range(lo, hi);
+                    atomicMin(&W.rng[2 * (slot * W.ng + W.group)], lo);
+                    atomicMax(&W.rng[2 * (slot * W.ng + W.group) + 1], hi);
+                    W.gauss_evals += (unsigned long long)(hi - lo) + 1ull;
+                } else {
+                    a = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
         }
     }
@@ -472,12 +504,13 @@ __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx&
 
 // Bremsstrahlung at one sample: cubic(s) in l' = log10(lambda) - lref of  A * sum_i n_i Z_i^2 g_ff(Z_i, Te, lambda),
 // A = weight * BREMS_CONST * ne / sqrt(Te); up to three pieces when the window crosses knots of the Gaunt table's u grid.
-// record: r0 = (a2, n_pieces, rho_c1, rho_c2), r1..r3 = piece coefficients (c0..c3).
+// record: r0 = (a2, n_pieces (+8 if the one-point rule is not accurate enough for this sample), rho_c1, rho_c2),
+//         r1..r3 = piece coefficients (c0..c3).
 __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
                              unsigned long long& brems_evals, unsigned& ood) {
     const DevBrems& B = S.brems;
     float4 r0 = make_float4(0.f, 0.f, FLT_MAX, FLT_MAX);
-    float4 pc[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    float4 pc0 = make_float4(0, 0, 0, 0), pc1 = pc0, pc2 = pc0;
     if (ne > 0.f && te > 0.f && in.weight > 0.f) {
         const float lte = log10f(te);
         const float L0 = B.log_hc - lte - B.lref;            // log10 u = L0 - l'
@@ -510,80 +543,167 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
                 jg = search_knots(G.y, G.ny, lg);
                 ug = (lg - __ldg(G.y + jg)) * __ldg(G.inv_wy + jg);
             }
-            for (int p = 0; p < np; p++) {
-                const int iu = i_lo + p;
-                float c0, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                if (g_hi || iu >= G.nx - 1) c0 = 1.0f;                          // classical limit (gaunt.pyx:129-130)
-                else if (g_lo || iu < 0) { c0 = k0 - k1 * L0; c1 = k1; }        // Born approximation (gaunt.pyx:133-134)
-                else {
-                    const float4 e = eval2d_rows(G, iu, jg, ug);                // g = sum_p e_p t^p, t = alpha - beta l'
-                    const float beta = __ldg(G.inv_wx + iu), alpha = (L0 - __ldg(G.x + iu)) * beta;
-                    c0 = fmaf(fmaf(fmaf(e.w, alpha, e.z), alpha, e.y), alpha, e.x);
-                    c1 = -beta * fmaf(fmaf(3.0f * e.w, alpha, 2.0f * e.z), alpha, e.y);
-                    c2 = beta * beta * fmaf(3.0f * e.w, alpha, e.z);
-                    c3 = -beta * beta * beta * e.w;
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                if (p < np) {
+                    const int iu = i_lo + p;
+                    float c0, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                    if (g_hi || iu >= G.nx - 1) c0 = 1.0f;                          // classical limit (gaunt.pyx:129-130)
+                    else if (g_lo || iu < 0) { c0 = k0 - k1 * L0; c1 = k1; }        // Born approximation (gaunt.pyx:133-134)
+                    else {
+                        const float4 e = eval2d_rows(G, iu, jg, ug);                // g = sum_p e_p t^p, t = alpha - beta l'
+                        const float beta = __ldg(G.inv_wx + iu), alpha = (L0 - __ldg(G.x + iu)) * beta;
+                        c0 = fmaf(fmaf(fmaf(e.w, alpha, e.z), alpha, e.y), alpha, e.x);
+                        c1 = -beta * fmaf(fmaf(3.0f * e.w, alpha, 2.0f * e.z), alpha, e.y);
+                        c2 = beta * beta * fmaf(3.0f * e.w, alpha, e.z);
+                        c3 = -beta * beta * beta * e.w;
+                    }
+                    float4& pc = p == 0 ? pc0 : (p == 1 ? pc1 : pc2);
+                    pc.x = fmaf(w, c0, pc.x); pc.y = fmaf(w, c1, pc.y);
+                    pc.z = fmaf(w, c2, pc.z); pc.w = fmaf(w, c3, pc.w);
                 }
-                pc[p].x = fmaf(w, c0, pc[p].x); pc[p].y = fmaf(w, c1, pc[p].y);
-                pc[p].z = fmaf(w, c2, pc[p].z); pc[p].w = fmaf(w, c3, pc[p].w);
             }
         }
         const float A = in.weight * B.pref * ne * rsqrtf(te);
-        for (int p = 0; p < 3; p++) { pc[p].x *= A; pc[p].y *= A; pc[p].z *= A; pc[p].w *= A; }
+        pc0.x *= A; pc0.y *= A; pc0.z *= A; pc0.w *= A;
+        pc1.x *= A; pc1.y *= A; pc1.z *= A; pc1.w *= A;
+        pc2.x *= A; pc2.y *= A; pc2.z *= A; pc2.w *= A;
+        // one-point (bin centre) rule: relative error ~ h^2/6 with h = delta/2 * |d ln eps / d lambda| at lambda_min
+        const float hh = fabsf(B.mid_c1 / te - B.mid_c0) + 0.1f * B.mid_c0;
+        const bool multi = (B.nq > 1) && (hh * hh * (1.0f / 6.0f) > 2e-6f);
         r0.x = B.exp_coef / te;
-        r0.y = (float)np;
+        r0.y = (float)(np + (multi ? 8 : 0));
         brems_evals += (unsigned long long)S.bins;
     }
     brec[tid] = r0;
-    brec[nt + tid] = pc[0];
-    brec[2 * nt + tid] = pc[1];
-    brec[3 * nt + tid] = pc[2];
+    brec[nt + tid] = pc0;
+    brec[2 * nt + tid] = pc1;
+    brec[3 * nt + tid] = pc2;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
+// Bin integrals of one NARROW component for one group of <= 32 consecutive samples (lanes = samples).  Each lane walks
+// the group's window of bin edges once (the reference's lower = upper recurrence, gaussian.pyx:78-88) and adds
+// amp * D into its private part[w]; the 32 partial vectors are then summed across lanes with a transpose-reduce
+// (31 shuffles) so that lane w holds window bin w, and added to the fp64 per-ray accumulators.
+__device__ __forceinline__ void narrow_group(const float4* __restrict__ ra, const float4* __restrict__ rb, int n, int rlo, int rhi,
+                                             int c0_int, int bins, double* __restrict__ racc, int lane) {
+    float part[32];
+#pragma unroll
+    for (int w = 0; w < 32; w++) part[w] = 0.f;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+    int lo = 0, hi = 0;
+    if (lane < n) {
+        a = ra[lane];
+        if (a.z != 0.f) { bq = rb[lane]; unpack_range(bq.w, lo, hi); lo -= rlo; hi -= rlo; }
+    }
+    const bool live = hi > lo;
+    const bool series = live && a.w >= 0.f;
+    const int whi = rhi - rlo;                                        // window = [0, whi), whi <= 32
+    {
+        // erfc-difference form; the record holds x at a bin's UPPER edge: x(rel) = rel * kx + xoff
+        const float xbase = fmaf((float)(rlo - 1), a.x, a.y);         // x at the lower edge of window bin 0
+        const float amp = series ? 0.f : a.z;
+        float xl = xbase;
+        float tl = half_erfc(fabsf(xl));
+#pragma unroll
+        for (int w = 0; w < 32; w++) {
+            if (w < whi) {                                              // warp-uniform
+                const float xu = fmaf((float)(w + 1), a.x, xbase);
+                const float tu = half_erfc(fabsf(xu));
+                const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
+                if (w >= lo && w < hi) part[w] = fmaf(amp, dd, part[w]);
+                xl = xu; tl = tu;
+            }
+        }
+    }
+    if (__any_sync(FULL, series)) {
+        // series-form record (a broad line clipped to a few bins by the window edge): x' at the bin centre
+#pragma unroll
+        for (int w = 0; w < 32; w++) {
+            if (w < whi) {
+                const float x = fmaf((float)(rlo + w), a.x, a.y);
+                const float m2 = x * x;
+                const float v = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(bq.z, m2, bq.y), m2, bq.x), m2, a.w), m2, a.z);
+                if (series && w >= lo && w < hi) part[w] += v;
+            }
+        }
+    }
+    // transpose-reduce: after the step with offset o a lane keeps the half of its vector selected by (lane & o)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float send = upper ? part[i] : part[i + o];
+            const float keep = upper ? part[i + o] : part[i];
+            part[i] = keep + __shfl_xor_sync(FULL, send, o);
+        }
+    }
+    const int bin = c0_int + rlo + lane;
+    if (lane < whi && part[0] != 0.f && bin >= 0 && bin < bins) atomicAdd(&racc[bin], (double)part[0]);
+}
+
+__device__ __forceinline__ double xform_row(const double* m, double x, double y, double z, bool point) {
+    // ((m0 x + m1 y) + m2 z) (+ m3), separate roundings like the reference's compiled C
+    double v = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z));
+    return point ? __dadd_rn(v, m[3]) : v;
+}
+
+#ifndef CB2_MIN_BLOCKS_NW4
+#define CB2_MIN_BLOCKS_NW4 4
+#endif
+#ifndef CB2_MIN_BLOCKS_NW8
+#define CB2_MIN_BLOCKS_NW8 2
+#endif
+
 template <int NW, int BPL, int BREMS>
-__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 4 : 2))
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? CB2_MIN_BLOCKS_NW4 : CB2_MIN_BLOCKS_NW8))
 emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict__ out, int out_f64, double scale, int accumulate,
                 unsigned long long* __restrict__ stats) {
     constexpr int NT = NW * 32;
     constexpr int TB = 32 * BPL;
-    extern __shared__ float4 smem[];
-    __shared__ int s_rng[2][2 * CB2_MAX_COMP];
+    constexpr int NG = NW;   // groups of 32 samples per chunk
+    extern __shared__ double smem_d[];
     const DevScene& S = *Sp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncomp = S.n_comp;
-    float4* rec = smem;
-    float4* brec = smem + (size_t)2 * ncomp * NT;
+    // dynamic shared memory: fp64 per-ray accumulators [NT*BPL], records, Bremsstrahlung records, per-group bin ranges
+    double* racc = smem_d;
+    float4* rec = reinterpret_cast<float4*>(smem_d + (size_t)NT * BPL);
+    float4* brec = rec + (size_t)2 * ncomp * NT;
+    int* s_rng = reinterpret_cast<int*>(brec + (BREMS ? 4 * NT : 0));   // [2][ncomp][NG][2]
+    const int rng_stride = 2 * ncomp * NG;
 
-    for (int i = tid; i < 4 * CB2_MAX_COMP; i += NT) (&s_rng[0][0])[i] = (i & 1) ? INT_MIN : INT_MAX;
+    for (int i = tid; i < 2 * rng_stride; i += NT) s_rng[i] = (i & 1) ? INT_MIN : INT_MAX;
+#pragma unroll
+    for (int j = 0; j < BPL; j++) racc[warp * TB + 32 * j + lane] = 0.0;
 
     const int64_t ray = blockIdx.x;
-    // ray in plasma space (fp64 once per ray)
-    double o[3], d[3];
-    {
-        const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
-        const double dx = rays.direction[3 * ray], dy = rays.direction[3 * ray + 1], dz = rays.direction[3 * ray + 2];
-        for (int k = 0; k < 3; k++) {
-            o[k] = S.w2p[4 * k] * ox + S.w2p[4 * k + 1] * oy + S.w2p[4 * k + 2] * oz + S.w2p[4 * k + 3];
-            d[k] = S.w2p[4 * k] * dx + S.w2p[4 * k + 1] * dy + S.w2p[4 * k + 2] * dz;
-        }
-    }
-    const double dlen = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+    const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
     SampleIn in;
-    in.dx = (float)(d[0] / dlen); in.dy = (float)(d[1] / dlen); in.dz = (float)(d[2] / dlen);
+    {
+        // ray direction in plasma space (direction.transform(local_to_plasma), normalised inside doppler_shift)
+        const double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
+                     d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        const double dl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        in.dx = (float)(d0 / dl); in.dy = (float)(d1 / dl); in.dz = (float)(d2 / dl);
+    }
 
     float acc[BPL];
-    double racc[BPL];
 #pragma unroll
-    for (int j = 0; j < BPL; j++) { acc[j] = 0.f; racc[j] = 0.0; }
+    for (int j = 0; j < BPL; j++) acc[j] = 0.f;
 
-    // Bremsstrahlung per-bin constants (1/lambda, 2 log2(1/lambda), log10(lambda) - lref) for one-point quadrature
-    float b_rho[BPL], b_cb[BPL], b_lp[BPL];
+    // Bremsstrahlung per-bin constants (1/lambda, 2 log2(1/lambda), log10(lambda) - lref) for the one-point rule
+    float b_rho[BREMS == 1 ? BPL : 1], b_cb[BREMS == 1 ? BPL : 1], b_lp[BREMS == 1 ? BPL : 1];
     if (BREMS == 1) {
 #pragma unroll
         for (int j = 0; j < BPL; j++) {
-            const float4 t = __ldg(S.brems.bin_tab + (warp * TB + 32 * j + lane));
+            const float4 t = __ldg(S.brems.bin_tab1 + (warp * TB + 32 * j + lane));
             b_rho[j] = t.x; b_cb[j] = t.y; b_lp[j] = t.z;
         }
     }
@@ -595,69 +715,91 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
 
     const int64_t s_begin = rays.seg_offset[ray], s_end = rays.seg_offset[ray + 1];
     for (int64_t sg = s_begin; sg < s_end; sg++) {
+        // NumericalIntegrator.integrate [raysect]: start_point = far end of the segment, end_point = near end, both taken to
+        // plasma space; float64 with the reference's operation order so that step positions are bit-identical
         const double t0 = rays.seg_t0[sg], t1 = rays.seg_t1[sg];
-        const double length = (t1 - t0) * dlen;
+        const double swx = __dadd_rn(ox, __dmul_rn(t1, dwx)), swy = __dadd_rn(oy, __dmul_rn(t1, dwy)), swz = __dadd_rn(oz, __dmul_rn(t1, dwz));
+        const double ewx = __dadd_rn(ox, __dmul_rn(t0, dwx)), ewy = __dadd_rn(oy, __dmul_rn(t0, dwy)), ewz = __dadd_rn(oz, __dmul_rn(t0, dwz));
+        const double sx = xform_row(S.w2p, swx, swy, swz, true), sy = xform_row(S.w2p + 4, swx, swy, swz, true), sz = xform_row(S.w2p + 8, swx, swy, swz, true);
+        double ivx = __dsub_rn(xform_row(S.w2p, ewx, ewy, ewz, true), sx), ivy = __dsub_rn(xform_row(S.w2p + 4, ewx, ewy, ewz, true), sy),
+               ivz = __dsub_rn(xform_row(S.w2p + 8, ewx, ewy, ewz, true), sz);
+        const double length = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ivx, ivx), __dmul_rn(ivy, ivy)), __dmul_rn(ivz, ivz)));
         if (!(length > 0.0)) continue;
-        int iv = (int)ceil(length / S.step);                       // NumericalIntegrator: intervals
+        ivx = __ddiv_rn(ivx, length); ivy = __ddiv_rn(ivy, length); ivz = __ddiv_rn(ivz, length);
+        int iv = (int)ceil(__ddiv_rn(length, S.step));             // intervals = max(min_samples - 1, ceil(L / step))
         iv = max(iv, max(S.min_samples - 1, 1));
-        const double h = length / iv;
+        const double h = __ddiv_rn(length, (double)iv);
         const float hf = (float)h;
-        // marching from the far end towards the observer, like Raysect (start_point = far end)
-        const float fx = (float)(o[0] + t1 * d[0]), fy = (float)(o[1] + t1 * d[1]), fz = (float)(o[2] + t1 * d[2]);
         if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
 
         for (int k0 = 0; k0 <= iv; k0 += NT) {
             // ---------------- STATE phase ----------------
             const int k = k0 + tid;
             const bool active = k <= iv;
-            const float tk = (float)k * hf;
-            in.x = fmaf(-tk, in.dx, fx); in.y = fmaf(-tk, in.dy, fy); in.z = fmaf(-tk, in.dz, fz);
+            const double tk = __dmul_rn((double)k, h);
+            const double pxd = __dadd_rn(sx, __dmul_rn(tk, ivx)), pyd = __dadd_rn(sy, __dmul_rn(tk, ivy)), pzd = __dadd_rn(sz, __dmul_rn(tk, ivz));
+            in.x = (float)pxd; in.y = (float)pyd; in.z = (float)pzd;
             in.weight = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
             {
                 AxCtx ctx;
                 float ne = 0.f, te = 0.f;
                 if (active) {
-                    ax_setup(S, in.x, in.y, in.z, ctx, ood);
+                    ax_setup(S, pxd, pyd, pzd, ctx, ood);
                     ne = eval_scalar(S.ne, ctx, in.x, in.y, in.z);
                     te = eval_scalar(S.te, ctx, in.x, in.y, in.z);
                 } else {
                     ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false;
                 }
                 RecWriter W;
-                W.rec = rec; W.rng = s_rng[parity]; W.nt = NT; W.tid = tid; W.bins = S.bins; W.gauss_evals = 0;
+                W.rec = rec; W.rng = s_rng + parity * rng_stride; W.nt = NT; W.tid = tid; W.ng = NG; W.group = warp;
+                W.bins = S.bins; W.gauss_evals = 0;
                 sample_lines(S, in, ctx, ne, te, W, ood);
                 n_gauss += W.gauss_evals;
                 if (BREMS) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
             }
             __syncthreads();
             // ---------------- BIN phase ----------------
-            for (int i = tid; i < 2 * ncomp; i += NT) s_rng[parity ^ 1][i] = (i & 1) ? INT_MIN : INT_MAX;
+            for (int i = tid; i < rng_stride; i += NT) s_rng[(parity ^ 1) * rng_stride + i] = (i & 1) ? INT_MIN : INT_MAX;
             const int nact = min(NT, iv - k0 + 1);
+            const int* rng = s_rng + parity * rng_stride;
             for (int c = 0; c < ncomp; c++) {
-                const int tlo = warp * TB - S.comps[c].c0_int;            // relative index of this warp's first bin
-                if (s_rng[parity][2 * c + 1] <= tlo || s_rng[parity][2 * c] >= tlo + TB) continue;
+                const int c0_int = S.comps[c].c0_int;
+                const int tlo = warp * TB - c0_int;                       // relative index of this warp's first bin
                 float relf[BPL];
 #pragma unroll
                 for (int j = 0; j < BPL; j++) relf[j] = (float)(tlo + 32 * j + lane);
                 const float4* ra = rec + (size_t)(2 * c) * NT;
                 const float4* rb = ra + NT;
-                for (int s = 0; s < nact; s++) {
+                for (int g = 0; g * 32 < nact; g++) {
+                  const int rlo = rng[2 * (c * NG + g)], rhi = rng[2 * (c * NG + g) + 1];   // union of the group's bin ranges
+                  if (rhi <= rlo) continue;
+                  const int s_beg = g * 32, s_end = min(nact, s_beg + 32);
+                  if (rhi - rlo <= 32) {
+                      // NARROW: the whole group fits a 32-bin window -> one warp takes it with lanes = samples
+                      if (warp == (c + g) % NW) narrow_group(ra + s_beg, rb + s_beg, s_end - s_beg, rlo, rhi, c0_int, S.bins, racc, lane);
+                      continue;
+                  }
+                  if (rhi <= tlo || rlo >= tlo + TB) continue;
+                  for (int s = s_beg; s < s_end; s++) {
                     const float4 a = ra[s];
                     if (a.z == 0.f) continue;
                     const float4 b = rb[s];
-                    const int lo = __float_as_int(b.z), hi = __float_as_int(b.w);
-                    if (hi <= tlo || lo >= tlo + TB) continue;
+                    int lo, hi;
+                    unpack_range(b.w, lo, hi);
+                    lo -= tlo; hi -= tlo;                                                       // relative to the tile
+                    if (hi <= 0 || lo >= TB) continue;
+                    // rows j (32 bins each) that the component touches: [jlo, jhi)
+                    const int jlo = max(lo, 0) >> 5, jhi = (min(hi, TB) + 31) >> 5;
+                    const unsigned rows = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
                     if (a.w >= 0.f) {
-                        // series path: amp' exp(-m^2) (s0 + s1 m^2 + s2 m^4)
+                        // series path: exp2(-m) (s0 + m (s1 + m (s2 + m (s3 + m s4)))), m = x'^2
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
-                            const int r0 = tlo + 32 * j;
-                            if (hi > r0 && lo < r0 + 32) {
+                            if (rows & (1u << j)) {
                                 const float x = fmaf(relf[j], a.x, a.y);
                                 const float m2 = x * x;
-                                const float e = ex2_approx(m2 * -L2E);
-                                const float sx = fmaf(fmaf(b.y, m2, b.x), m2, a.w);
-                                acc[j] = fmaf(a.z * e, sx, acc[j]);
+                                const float e = ex2_approx(-m2);
+                                acc[j] = fmaf(e, fmaf(fmaf(fmaf(fmaf(b.z, m2, b.y), m2, b.x), m2, a.w), m2, a.z), acc[j]);
                             }
                         }
                     } else {
@@ -666,8 +808,7 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                         float carry = 0.f;
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
-                            const int r0 = tlo + 32 * j;
-                            if (hi > r0 && lo < r0 + 32) {
+                            if (rows & (1u << j)) {
                                 const float xu = fmaf(relf[j], a.x, a.y);
                                 const float xl = xu - a.x;
                                 const float tu = half_erfc(fabsf(xu));
@@ -682,26 +823,46 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                             }
                         }
                     }
+                  }
                 }
             }
             if (BREMS) {
+                const float4* btab = S.brems.bin_tab;
+                const float4* btab1 = S.brems.bin_tab1;
+                const int nq = S.brems.nq;
                 for (int s = 0; s < nact; s++) {
                     const float4 r0 = brec[s];
                     if (r0.x == 0.f) continue;
                     const float na2 = -r0.x;
                     const float4 p0 = brec[NT + s];
-                    if (BREMS == 1 && r0.y < 1.5f) {
+                    if (r0.y < 1.5f) {
+                        // one piece, one-point rule: exp2(-a2/lambda + 2 log2(1/lambda)) * cubic(log10 lambda)
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
-                            const float e = ex2_approx(fmaf(na2, b_rho[j], b_cb[j]));
-                            acc[j] = fmaf(horner4(p0, b_lp[j]), e, acc[j]);
+                            float rho, cb, lp;
+                            if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
+                            else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
+                            acc[j] = fmaf(horner4(p0, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
+                        }
+                    } else if (r0.y < 7.5f) {
+                        // the window crosses a knot of the Gaunt table's u grid: pick the piece per bin
+                        const float4 p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
+#pragma unroll
+                        for (int j = 0; j < BPL; j++) {
+                            float rho, cb, lp;
+                            if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
+                            else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
+                            float4 pc = p0;
+                            if (rho >= r0.z) pc = p1;
+                            if (rho >= r0.w) pc = p2;
+                            acc[j] = fmaf(horner4(pc, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
                         }
                     } else {
+                        // cold sample: nq-point Gauss-Legendre rule from the table
                         const float4 p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
-                        const int nq = S.brems.nq;
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
-                            const float4* tb = S.brems.bin_tab + (size_t)(warp * TB + 32 * j + lane) * nq;
+                            const float4* tb = btab + (size_t)(warp * TB + 32 * j + lane) * nq;
                             float v = 0.f;
                             for (int q = 0; q < nq; q++) {
                                 const float4 t = __ldg(tb + q);
@@ -715,9 +876,12 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                     }
                 }
             }
-            // fp32 chunk sums -> fp64 per-ray accumulators
+            // fp32 chunk sums -> fp64 per-ray accumulators (shared memory, each bin owned by exactly one lane)
 #pragma unroll
-            for (int j = 0; j < BPL; j++) { racc[j] += (double)acc[j]; acc[j] = 0.f; }
+            for (int j = 0; j < BPL; j++) {
+                if (acc[j] != 0.f) atomicAdd(&racc[warp * TB + 32 * j + lane], (double)acc[j]);   // narrow path adds concurrently
+                acc[j] = 0.f;
+            }
             parity ^= 1;
             __syncthreads();
         }
@@ -729,12 +893,13 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
         const int bin = warp * TB + 32 * j + lane;
         if (bin < S.bins) {
             const size_t idx = (size_t)ray * S.bins + bin;
+            const double v = scale * racc[bin];
             if (out_f64) {
                 double* p = (double*)out + idx;
-                *p = (accumulate ? *p : 0.0) + scale * racc[j];
+                *p = (accumulate ? *p : 0.0) + v;
             } else {
                 float* p = (float*)out + idx;
-                *p = (float)((accumulate ? (double)*p : 0.0) + scale * racc[j]);
+                *p = (float)((accumulate ? (double)*p : 0.0) + v);
             }
         }
     }
@@ -780,8 +945,9 @@ static int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int o
                       unsigned long long* stats, cudaStream_t st) {
     const DevScene& S = sc->host;
     const int NT = NW * 32;
-    const size_t smem = ((size_t)2 * S.n_comp * NT + (S.brems.present ? 4 * NT : 0)) * sizeof(float4);
-    const int mode = !S.brems.present ? 0 : ((S.brems.nq == 1 && BPL <= 8) ? 1 : 2);
+    const size_t smem = (size_t)NT * BPL * sizeof(double) + ((size_t)2 * S.n_comp * NT + (S.brems.present ? 4 * NT : 0)) * sizeof(float4)
+                        + (size_t)2 * 2 * S.n_comp * NW * sizeof(int);
+    const int mode = !S.brems.present ? 0 : (BPL <= 8 ? 1 : 2);
     if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
     dim3 grid((unsigned)rays.n_rays), block(NT);
 #define CB2_LAUNCH(MODE)                                                                                                   \
@@ -820,11 +986,12 @@ __global__ void sample_state_kernel(const DevScene* __restrict__ Sp, const doubl
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    float p[3];
-    for (int k = 0; k < 3; k++) p[k] = (float)(S.w2p[4 * k] * px + S.w2p[4 * k + 1] * py + S.w2p[4 * k + 2] * pz + S.w2p[4 * k + 3]);
+    double pd[3];
+    for (int k = 0; k < 3; k++) pd[k] = xform_row(S.w2p + 4 * k, px, py, pz, true);
+    const float p[3] = {(float)pd[0], (float)pd[1], (float)pd[2]};
     AxCtx ctx;
     unsigned ood = 0;
-    ax_setup(S, p[0], p[1], p[2], ctx, ood);
+    ax_setup(S, pd[0], pd[1], pd[2], ctx, ood);
     const int w = 2 + 5 * S.n_species + 3;
     double* o = out + i * w;
     const double inv_scale = 1.0 / CB2_DENSITY_SCALE;

@@ -71,6 +71,10 @@ struct DevAxisym {
     int n_poly;
     const float4* poly;              // per edge: (xi, yi, yj, slope = (xj-xi)/(yj-yi))
     float poly_xmin, poly_xmax, poly_ymin, poly_ymax;
+    // coarse classification grid over the polygon bounding box: 0 outside, 1 inside, 2 boundary cell (run the edge loop)
+    int pgx, pgy;
+    float p_icx, p_icy;
+    const unsigned char* poly_cls;
     int n_mask;
     float mask_x[8], mask_y[8];
     // mesh
@@ -78,7 +82,8 @@ struct DevAxisym {
     float mx0, my0, inv_cx, inv_cy;
     const int* cell_start;
     const int* cell_tris;
-    const float2* tri;               // [n_tri*3]
+    const double2* tri;              // [n_tri*3] fp64 vertices: the containment test must decide exactly like the fp64 reference
+    double mx0_d, my0_d, inv_cx_d, inv_cy_d;
 };
 
 // static part of one line component slot (Gaussian or Lorentzian)
@@ -116,6 +121,8 @@ struct DevBrems {
     int present;
     int nq;                       // Gauss-Legendre points per bin
     const float4* bin_tab;        // [bins_padded][nq]: (1/lambda, 2*log2(1/lambda), log10(lambda) - lref, weight)
+    const float4* bin_tab1;       // [bins_padded] one-point (bin centre) version of the same
+    float mid_c1, mid_c0;         // one-point rule error model: h = |mid_c1/Te - mid_c0|, relative error ~ h^2/6
     float lref;                   // log10 of the window centre
     float log_hc;                 // log10(HC_EV_NM)
     float exp_coef;               // EXP_FACTOR * log2(e)

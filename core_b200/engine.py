@@ -161,3 +161,11 @@ class RayTransferScene:
                                                                  C.c_void_p(columns.data_ptr()), C.c_void_p(lengths.data_ptr()),
                                                                  int(capacity), C.byref(nnz), None, C.c_void_p(stream)))
         return row_offset, columns[:nnz.value], lengths[:nnz.value]
+
+
+def measure_peaks(device=0):
+    """Live FP32-FMA and MUFU.EX2 issue-rate microbenchmarks -> dict(fp32_tflops, sfu_tops, sm_clock_mhz)."""
+    lib = _abi.load_library()
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _abi.check(lib, lib.cb2_measure_peaks(int(device), C.byref(a), C.byref(b), C.byref(c)))
+    return {"fp32_tflops": a.value, "sfu_tops": b.value, "sm_clock_mhz": c.value}

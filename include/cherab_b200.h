@@ -253,6 +253,9 @@ const char* cb2_last_error(void);
 /* number of CUDA devices visible, <0 on error (never falls back to the CPU) */
 int         cb2_device_count(void);
 
+/* Roofline denominators measured live (FFMA and MUFU.EX2 issue-rate microbenchmarks): TFLOP/s, Tops/s, nominal SM MHz. */
+int         cb2_measure_peaks(int device, double* fp32_tflops, double* sfu_tops, double* sm_clock_mhz);
+
 /* Build device-resident tables from a flattened scene.  Replaces PlasmaMaterial.__init__ + the lazy
  * _populate_cache of every model (plasma/material.pyx:37-46; impact_excitation.pyx:102-128). */
 int cb2_scene_create(const cb2_scene_desc* desc, int device, cb2_scene** out);

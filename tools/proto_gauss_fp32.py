@@ -87,3 +87,41 @@ if __name__ == "__main__":
                 err = np.abs(v-r)/(np.abs(r)+floor/1e-4)   # in units where 1e-4 is the tolerance
                 worst[name] = max(worst.get(name, 0), err.max())
         print("sigma_b=%6.1f h=%.4f" % (sigma_b, h), {k: "%.1e" % v for k, v in worst.items()})
+
+
+def bins_series5(cf, kb, nb):
+    """5-term series (through h^8 H_8(m)/9!) with the sqrt(log2 e) folding used on the device."""
+    rel = np.arange(nb).astype(f32)
+    kbf = f32(kb)
+    SQ = f32(1.2011224087864498); IL = f32(0.6931471805599453)
+    kx = kbf*SQ
+    xo = f32(0.5-cf)*kx
+    x = fma(rel, np.full_like(rel, kx), np.full_like(rel, xo))
+    h2 = f32(0.25)*kbf*kbf
+    t1 = h2/f32(6); t2 = h2*h2/f32(120); t3 = h2*h2*h2/f32(5040); t4 = h2*h2*h2*h2/f32(362880)
+    A = kbf*f32(0.5641895835477563)
+    s0 = A*(f32(1) - f32(2)*t1 + f32(12)*t2 - f32(120)*t3 + f32(1680)*t4)
+    s1 = A*(f32(4)*t1 - f32(48)*t2 + f32(720)*t3 - f32(13440)*t4)*IL
+    s2 = A*(f32(16)*t2 - f32(480)*t3 + f32(13440)*t4)*IL*IL
+    s3 = A*(f32(64)*t3 - f32(3584)*t4)*IL*IL*IL
+    s4 = A*(f32(256)*t4)*IL*IL*IL*IL
+    m2 = x*x
+    e = ex2(-m2)
+    S = np.full_like(m2, s4)
+    for c in (s3, s2, s1, s0):
+        S = fma(S, m2, np.full_like(m2, c))
+    return e*S
+
+
+if __name__ == "__main__":
+    print("5-term series")
+    rng = np.random.default_rng(1)
+    for sigma_b in [1.0, 1.41, 2.0, 2.83, 4.0, 5.66, 8, 20]:
+        kb = 1/(np.sqrt(2)*sigma_b)
+        worst = 0
+        for trial in range(20):
+            nb = int(min(2048, 22*sigma_b+4)); cf = nb/2 + rng.uniform(0, 1)
+            r = ref(cf, kb, nb); floor = 1e-9*r.max()
+            v = bins_series5(cf, kb, nb).astype(np.float64)
+            worst = max(worst, (np.abs(v-r)/(np.abs(r)+floor/1e-4)).max())
+        print("sigma_b=%5.2f h=%.4f worst %.1e" % (sigma_b, kb/2, worst))
