@@ -26,6 +26,7 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "cb2_internal.h"
 
@@ -504,12 +505,13 @@ __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx&
 
 // Bremsstrahlung at one sample: cubic(s) in l' = log10(lambda) - lref of  A * sum_i n_i Z_i^2 g_ff(Z_i, Te, lambda),
 // A = weight * BREMS_CONST * ne / sqrt(Te); up to three pieces when the window crosses knots of the Gaunt table's u grid.
-// record: r0 = (a2, n_pieces (+8 if the one-point rule is not accurate enough for this sample), rho_c1, rho_c2),
+// record: r0 = (a2, n_pieces (+8 if the one-point rule is not accurate enough for this sample), bc1, bc2) where piece 0
+//         (lowest u, longest wavelengths) covers bins [bc1, bins), piece 1 [bc2, bc1), piece 2 [0, bc2),
 //         r1..r3 = piece coefficients (c0..c3).
 __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
                              unsigned long long& brems_evals, unsigned& ood) {
     const DevBrems& B = S.brems;
-    float4 r0 = make_float4(0.f, 0.f, FLT_MAX, FLT_MAX);
+    float4 r0 = make_float4(0.f, 0.f, -1.0f, -1.0f);
     float4 pc0 = make_float4(0, 0, 0, 0), pc1 = pc0, pc2 = pc0;
     if (ne > 0.f && te > 0.f && in.weight > 0.f) {
         const float lte = log10f(te);
@@ -527,8 +529,10 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
         if (i_hi > i_lo + 2) { i_hi = i_lo + 2; ood++; }
         const int np = i_hi - i_lo + 1;
         // wavelength (1/lambda) thresholds where the piece changes: u = knot  <=>  rho = knot * Te / hc
-        if (np > 1) r0.z = exp10f(__ldg(G.x + i_lo + 1) - B.log_hc + lte);
-        if (np > 2) r0.w = exp10f(__ldg(G.x + i_lo + 2) - B.log_hc + lte);
+        // bins whose centre wavelength is <= lambda_knot (1/lambda >= knot Te/hc) belong to the next piece:
+        // store the first bin of the lower piece, bc = floor(xc - 1/2) + 1 with xc = (lambda_knot - lambda_min)/delta
+        if (np > 1) r0.z = floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 1)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f;
+        if (np > 2) r0.w = floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 2)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f;
         const float k1 = 0.5513288954217921f * 2.302585092994046f;            // sqrt(3)/pi * ln 10
         const float k0 = 0.5513288954217921f * (1.3862943611198906f - 0.5772156649015329f);  // sqrt(3)/pi (ln 4 - gamma_E)
         for (int s = 0; s < B.n_charged; s++) {
@@ -584,51 +588,53 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-// Bin integrals of one NARROW component for one group of <= 32 consecutive samples (lanes = samples).  Each lane walks
-// the group's window of bin edges once (the reference's lower = upper recurrence, gaussian.pyx:78-88) and adds
-// amp * D into its private part[w]; the 32 partial vectors are then summed across lanes with a transpose-reduce
-// (31 shuffles) so that lane w holds window bin w, and added to the fp64 per-ray accumulators.
-__device__ __forceinline__ void narrow_group(const float4* __restrict__ ra, const float4* __restrict__ rb, int n, int rlo, int rhi,
-                                             int c0_int, int bins, double* __restrict__ racc, int lane) {
+// WINDOW PASS — bin integrals of one line component over one 32-bin window for one group of <= 32 consecutive
+// samples, lanes = samples.  Every lane evaluates its own sample's Gaussian at the window's 32 bins (series form: no
+// cross-bin dependence; erfc form: the reference's lower = upper recurrence along the window, gaussian.pyx:78-88) and
+// adds into its private part[w]; the 32 partial vectors are summed across lanes with a transpose-reduce (31 shuffles)
+// so that lane w holds window bin w, which is added to the fp64 per-ray accumulator.  Lane utilisation is 100% however
+// narrow the line is, and the per-sample bookkeeping is paid once per 32 bins.
+__device__ __forceinline__ void window_pass(const float4* __restrict__ ra, const float4* __restrict__ rb, int n, int wbase, int wcount,
+                                            int c0_int, int bins, double* __restrict__ racc, int lane) {
     float part[32];
 #pragma unroll
     for (int w = 0; w < 32; w++) part[w] = 0.f;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = make_float4(0.f, 0.f, 0.f, 0.f);
     int lo = 0, hi = 0;
     if (lane < n) {
         a = ra[lane];
-        if (a.z != 0.f) { bq = rb[lane]; unpack_range(bq.w, lo, hi); lo -= rlo; hi -= rlo; }
+        if (a.z != 0.f) { bq = rb[lane]; unpack_range(bq.w, lo, hi); lo -= wbase; hi -= wbase; }
     }
-    const bool live = hi > lo;
-    const bool series = live && a.w >= 0.f;
-    const int whi = rhi - rlo;                                        // window = [0, whi), whi <= 32
-    {
-        // erfc-difference form; the record holds x at a bin's UPPER edge: x(rel) = rel * kx + xoff
-        const float xbase = fmaf((float)(rlo - 1), a.x, a.y);         // x at the lower edge of window bin 0
-        const float amp = series ? 0.f : a.z;
+    const bool live = hi > 0 && lo < wcount && a.z != 0.f;           // this sample touches the window
+    const bool series = live && a.w >= 0.f, erfc = live && a.w < 0.f;
+    if (__any_sync(FULL, series)) {
+        // exp2(-m) (s0 + m (s1 + m (s2 + m (s3 + m s4)))), m = x'^2, x' = (wbase + w) kx + xoff  (bin centres)
+        const float x0 = fmaf((float)wbase, a.x, a.y);
+        const float s0 = series ? a.z : 0.f, s1 = series ? a.w : 0.f, s2 = series ? bq.x : 0.f, s3 = series ? bq.y : 0.f,
+                    s4 = series ? bq.z : 0.f;
+#pragma unroll
+        for (int w = 0; w < 32; w++) {
+            if (w < wcount) {                                          // warp-uniform
+                const float x = fmaf((float)w, a.x, x0);
+                const float m2 = fminf(x * x, 126.0f);                 // exp2(-126) ~ 1e-38: keeps far-off bins finite
+                part[w] = fmaf(ex2_approx(-m2), fmaf(fmaf(fmaf(fmaf(s4, m2, s3), m2, s2), m2, s1), m2, s0), part[w]);
+            }
+        }
+    }
+    if (__any_sync(FULL, erfc)) {
+        // sub-bin lines: 1/2 erfc differences; the record holds x at a bin's UPPER edge: x(rel) = rel * kx + xoff
+        const float xbase = fmaf((float)(wbase - 1), a.x, a.y);       // x at the lower edge of window bin 0
+        const float amp = erfc ? a.z : 0.f;
         float xl = xbase;
         float tl = half_erfc(fabsf(xl));
 #pragma unroll
         for (int w = 0; w < 32; w++) {
-            if (w < whi) {                                              // warp-uniform
+            if (w < wcount) {
                 const float xu = fmaf((float)(w + 1), a.x, xbase);
                 const float tu = half_erfc(fabsf(xu));
                 const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
                 if (w >= lo && w < hi) part[w] = fmaf(amp, dd, part[w]);
                 xl = xu; tl = tu;
-            }
-        }
-    }
-    if (__any_sync(FULL, series)) {
-        // series-form record (a broad line clipped to a few bins by the window edge): x' at the bin centre
-#pragma unroll
-        for (int w = 0; w < 32; w++) {
-            if (w < whi) {
-                const float x = fmaf((float)(rlo + w), a.x, a.y);
-                const float m2 = x * x;
-                const float v = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(bq.z, m2, bq.y), m2, bq.x), m2, a.w), m2, a.z);
-                if (series && w >= lo && w < hi) part[w] += v;
             }
         }
     }
@@ -643,8 +649,8 @@ __device__ __forceinline__ void narrow_group(const float4* __restrict__ ra, cons
             part[i] = keep + __shfl_xor_sync(FULL, send, o);
         }
     }
-    const int bin = c0_int + rlo + lane;
-    if (lane < whi && part[0] != 0.f && bin >= 0 && bin < bins) atomicAdd(&racc[bin], (double)part[0]);
+    const int bin = c0_int + wbase + lane;
+    if (lane < wcount && part[0] != 0.f && bin >= 0 && bin < bins) atomicAdd(&racc[bin], (double)part[0]);
 }
 
 __device__ __forceinline__ double xform_row(const double* m, double x, double y, double z, bool point) {
@@ -661,7 +667,7 @@ __device__ __forceinline__ double xform_row(const double* m, double x, double y,
 #endif
 
 template <int NW, int BPL, int BREMS>
-__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? CB2_MIN_BLOCKS_NW4 : CB2_MIN_BLOCKS_NW8))
+__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32))
 emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict__ out, int out_f64, double scale, int accumulate,
                 unsigned long long* __restrict__ stats) {
     constexpr int NT = NW * 32;
@@ -762,68 +768,20 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
             for (int i = tid; i < rng_stride; i += NT) s_rng[(parity ^ 1) * rng_stride + i] = (i & 1) ? INT_MIN : INT_MAX;
             const int nact = min(NT, iv - k0 + 1);
             const int* rng = s_rng + parity * rng_stride;
+            // LINES: lanes = samples.  For every (component, group of 32 samples) the union of the bin ranges is cut into
+            // 32-bin windows, dealt round-robin to the warps.
             for (int c = 0; c < ncomp; c++) {
                 const int c0_int = S.comps[c].c0_int;
-                const int tlo = warp * TB - c0_int;                       // relative index of this warp's first bin
-                float relf[BPL];
-#pragma unroll
-                for (int j = 0; j < BPL; j++) relf[j] = (float)(tlo + 32 * j + lane);
                 const float4* ra = rec + (size_t)(2 * c) * NT;
                 const float4* rb = ra + NT;
                 for (int g = 0; g * 32 < nact; g++) {
-                  const int rlo = rng[2 * (c * NG + g)], rhi = rng[2 * (c * NG + g) + 1];   // union of the group's bin ranges
-                  if (rhi <= rlo) continue;
-                  const int s_beg = g * 32, s_end = min(nact, s_beg + 32);
-                  if (rhi - rlo <= 32) {
-                      // NARROW: the whole group fits a 32-bin window -> one warp takes it with lanes = samples
-                      if (warp == (c + g) % NW) narrow_group(ra + s_beg, rb + s_beg, s_end - s_beg, rlo, rhi, c0_int, S.bins, racc, lane);
-                      continue;
-                  }
-                  if (rhi <= tlo || rlo >= tlo + TB) continue;
-                  for (int s = s_beg; s < s_end; s++) {
-                    const float4 a = ra[s];
-                    if (a.z == 0.f) continue;
-                    const float4 b = rb[s];
-                    int lo, hi;
-                    unpack_range(b.w, lo, hi);
-                    lo -= tlo; hi -= tlo;                                                       // relative to the tile
-                    if (hi <= 0 || lo >= TB) continue;
-                    // rows j (32 bins each) that the component touches: [jlo, jhi)
-                    const int jlo = max(lo, 0) >> 5, jhi = (min(hi, TB) + 31) >> 5;
-                    const unsigned rows = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
-                    if (a.w >= 0.f) {
-                        // series path: exp2(-m) (s0 + m (s1 + m (s2 + m (s3 + m s4)))), m = x'^2
-#pragma unroll
-                        for (int j = 0; j < BPL; j++) {
-                            if (rows & (1u << j)) {
-                                const float x = fmaf(relf[j], a.x, a.y);
-                                const float m2 = x * x;
-                                const float e = ex2_approx(-m2);
-                                acc[j] = fmaf(e, fmaf(fmaf(fmaf(fmaf(b.z, m2, b.y), m2, b.x), m2, a.w), m2, a.z), acc[j]);
-                            }
-                        }
-                    } else {
-                        // erfc-difference path with the lower-edge value handed over by the neighbouring lane
-                        bool have = false;
-                        float carry = 0.f;
-#pragma unroll
-                        for (int j = 0; j < BPL; j++) {
-                            if (rows & (1u << j)) {
-                                const float xu = fmaf(relf[j], a.x, a.y);
-                                const float xl = xu - a.x;
-                                const float tu = half_erfc(fabsf(xu));
-                                float tl = __shfl_up_sync(FULL, tu, 1);
-                                if (lane == 0) tl = have ? carry : half_erfc(fabsf(xl));
-                                carry = __shfl_sync(FULL, tu, 31);
-                                have = true;
-                                const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
-                                acc[j] = fmaf(a.z, dd, acc[j]);
-                            } else {
-                                have = false;
-                            }
-                        }
-                    }
-                  }
+                    const int rlo = rng[2 * (c * NG + g)], rhi = rng[2 * (c * NG + g) + 1];   // union of the group's bin ranges
+                    if (rhi <= rlo) continue;
+                    const int n = min(32, nact - g * 32);
+                    int k = (warp - c - g) % NW;                          // first window of this (c, g) that is mine
+                    if (k < 0) k += NW;
+                    for (int wbase = rlo + 32 * k; wbase < rhi; wbase += 32 * NW)
+                        window_pass(ra + g * 32, rb + g * 32, n, wbase, min(32, rhi - wbase), c0_int, S.bins, racc, lane);
                 }
             }
             if (BREMS) {
@@ -834,41 +792,53 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                     const float4 r0 = brec[s];
                     if (r0.x == 0.f) continue;
                     const float na2 = -r0.x;
-                    const float4 p0 = brec[NT + s];
-                    if (r0.y < 1.5f) {
-                        // one piece, one-point rule: exp2(-a2/lambda + 2 log2(1/lambda)) * cubic(log10 lambda)
+                    if (r0.y < 7.5f) {
+                        // one-point rule.  Pieces (window crossing a knot of the Gaunt table's u grid) are contiguous in bin
+                        // index: piece 0 = bins [bc1, end), piece 1 = [bc2, bc1), piece 2 = [0, bc2).  A warp tile lies in
+                        // one piece unless the knot falls inside it.
+                        const int np = (int)r0.y;
+                        const int t_first = warp * TB, t_last = warp * TB + TB - 1;
+                        const int bc1 = (int)r0.z, bc2 = (int)r0.w;
+                        const int pf = (np > 1 && t_first < bc1) ? ((np > 2 && t_first < bc2) ? 2 : 1) : 0;
+                        const int pl = (np > 1 && t_last < bc1) ? ((np > 2 && t_last < bc2) ? 2 : 1) : 0;
+                        if (pf == pl) {
+                            const float4 pc = brec[(1 + pf) * NT + s];
 #pragma unroll
-                        for (int j = 0; j < BPL; j++) {
-                            float rho, cb, lp;
-                            if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
-                            else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
-                            acc[j] = fmaf(horner4(p0, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
-                        }
-                    } else if (r0.y < 7.5f) {
-                        // the window crosses a knot of the Gaunt table's u grid: pick the piece per bin
-                        const float4 p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
+                            for (int j = 0; j < BPL; j++) {
+                                float rho, cb, lp;
+                                if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
+                                else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
+                                acc[j] = fmaf(horner4(pc, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
+                            }
+                        } else {
+                            const float4 p0 = brec[NT + s], p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
 #pragma unroll
-                        for (int j = 0; j < BPL; j++) {
-                            float rho, cb, lp;
-                            if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
-                            else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
-                            float4 pc = p0;
-                            if (rho >= r0.z) pc = p1;
-                            if (rho >= r0.w) pc = p2;
-                            acc[j] = fmaf(horner4(pc, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
+                            for (int j = 0; j < BPL; j++) {
+                                float rho, cb, lp;
+                                if (BREMS == 1) { rho = b_rho[j]; cb = b_cb[j]; lp = b_lp[j]; }
+                                else { const float4 t = __ldg(btab1 + (warp * TB + 32 * j + lane)); rho = t.x; cb = t.y; lp = t.z; }
+                                const int bin = warp * TB + 32 * j + lane;
+                                float4 pc = p0;
+                                if (bin < bc1) pc = p1;
+                                if (np > 2 && bin < bc2) pc = p2;
+                                acc[j] = fmaf(horner4(pc, lp), ex2_approx(fmaf(na2, rho, cb)), acc[j]);
+                            }
                         }
                     } else {
-                        // cold sample: nq-point Gauss-Legendre rule from the table
-                        const float4 p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
+                        // cold sample: nq-point Gauss-Legendre rule from the table, piece chosen per quadrature point
+                        const int np = (int)r0.y - 8;
+                        const float4 p0 = brec[NT + s], p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
+                        const float xc1 = np > 1 ? r0.z : -1.0f, xc2 = np > 2 ? r0.w : -1.0f;
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
-                            const float4* tb = btab + (size_t)(warp * TB + 32 * j + lane) * nq;
+                            const int bin = warp * TB + 32 * j + lane;
+                            const float4* tb = btab + (size_t)bin * nq;
+                            float4 pc = p0;
+                            if ((float)bin < xc1) pc = p1;
+                            if ((float)bin < xc2) pc = p2;
                             float v = 0.f;
                             for (int q = 0; q < nq; q++) {
                                 const float4 t = __ldg(tb + q);
-                                float4 pc = p0;
-                                if (t.x >= r0.z) pc = p1;
-                                if (t.x >= r0.w) pc = p2;
                                 v = fmaf(t.w * horner4(pc, t.z), ex2_approx(fmaf(na2, t.x, t.y)), v);
                             }
                             acc[j] += v;
@@ -934,6 +904,12 @@ int cb2_emission_config(cb2_scene* sc) {
     else if (bins <= 2048) { nw = 8; bpl = 8; }
     else if (bins <= 4096) { nw = 8; bpl = 16; }
     else return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
+    // tuning override (experiments): CB2_NW x CB2_BPL must cover the bins and be an instantiated pair
+    const char *env_nw = getenv("CB2_NW"), *env_bpl = getenv("CB2_BPL");
+    if (env_nw && env_bpl) {
+        const int enw = atoi(env_nw), ebpl = atoi(env_bpl);
+        if (enw * 32 * ebpl >= bins) { nw = enw; bpl = ebpl; }
+    }
     sc->nw = nw;
     sc->bpl = bpl;
     sc->host.bins_padded = nw * 32 * bpl;
@@ -974,6 +950,11 @@ int cb2_launch_emission(const cb2_scene* sc, const DevRays& rays, void* out, int
     CB2_CASE(8, 4);
     CB2_CASE(8, 8);
     CB2_CASE(8, 16);
+    CB2_CASE(2, 8);
+    CB2_CASE(1, 16);
+    CB2_CASE(4, 16);
+    CB2_CASE(2, 16);
+    CB2_CASE(4, 8);
 #undef CB2_CASE
     return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "no kernel instance for nw=%d bpl=%d", sc->nw, sc->bpl);
 }

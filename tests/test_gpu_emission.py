@@ -160,8 +160,10 @@ def test_generomak_state_vs_oracle(generomak_halpha):
     vec_starts = [4 + 5 * k for k in range(ns)] + [2 + 5 * ns]
     for c in vec_starts:
         norm = np.linalg.norm(ref[:, c:c + 3], axis=1)
-        verr = np.linalg.norm(got[:, c:c + 3] - ref[:, c:c + 3], axis=1) / (norm + 1e-6 * norm.max() + 1e-300)
-        assert (verr > 2e-5).mean() < 1e-3, (c, (verr > 2e-5).mean())
+        # in the blend shell (psi_n -> 1) v = m * v_core with m -> 0: fp32 psi_n bounds the ABSOLUTE error (0.1 m/s here,
+        # i.e. a Doppler shift of 2e-10 nm), so the criterion is |dv| <= 2e-5 |v| + 1e-5 max|v|
+        verr = np.linalg.norm(got[:, c:c + 3] - ref[:, c:c + 3], axis=1) / (2e-5 * norm + 1e-5 * norm.max() + 1e-300)
+        assert (verr > 1.0).mean() < 1e-3, (c, (verr > 1.0).mean())
 
 
 def test_generomak_halpha_camera(generomak_halpha):
@@ -200,7 +202,8 @@ def test_output_modes(generomak_halpha):
     out = torch.zeros((rays.n_rays, 512), dtype=torch.float64, device="cuda:0")
     scene.render_device(dr, out)
     torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy(), a)
+    # same kernel, but the fp64 shared-memory accumulation order is not deterministic: equal to rounding, not bitwise
+    assert np.allclose(out.cpu().numpy(), a, rtol=1e-12, atol=0)
     scene.close()
 
 

@@ -85,3 +85,10 @@ if "prof_brems" in what:
     one_launch("brems", 2048, 390., 700., 48)
 if "prof_lines8" in what:
     one_launch("lines8", 2048, 390., 700., 48)
+if "tune" in what:
+    for nw, bpl in ((4, 4), (2, 8), (1, 16)):
+        os.environ["CB2_NW"], os.environ["CB2_BPL"] = str(nw), str(bpl)
+        print("NW=%d BPL=%d" % (nw, bpl)); timeit("c1", 512, 651.279, 661.279)
+    for nw, bpl in ((8, 8), (4, 16), (2, 16)):
+        os.environ["CB2_NW"], os.environ["CB2_BPL"] = str(nw), str(bpl)
+        print("NW=%d BPL=%d" % (nw, bpl)); timeit("lines8", 2048, 390., 700.); timeit("brems", 2048, 390., 700.); timeit("c3", 2048, 390., 700.)
