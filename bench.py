@@ -58,15 +58,8 @@ def fixed_flops_per_sample(flat):
 
 
 def rank_pixels(pixels, rank, world):
-    """Pixel indices (ix * ny + iy) of the 16x16 tiles dealt round-robin to `rank`, tile-major order."""
-    nx = ny = pixels
-    tx, ty = (nx + TILE - 1) // TILE, (ny + TILE - 1) // TILE
-    tiles = np.arange(tx * ty)[rank::world]
-    ox, oy = np.meshgrid(np.arange(TILE), np.arange(TILE), indexing="ij")
-    ix = (tiles // ty)[:, None] * TILE + ox.ravel()[None, :]
-    iy = (tiles % ty)[:, None] * TILE + oy.ravel()[None, :]
-    ok = (ix < nx) & (iy < ny)
-    return (ix * ny + iy)[ok]
+    from core_b200.sharding import tile_pixels
+    return tile_pixels(pixels, rank, world)
 
 
 def make_rays(plasma, pixels, pixel_index, sample_id):

@@ -474,7 +474,7 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     case CB2_SHAPE_ZEEMAN_TRIPLET:
     case CB2_SHAPE_PARAM_ZEEMAN: n = 3; break;
     case CB2_SHAPE_ZEEMAN_MULTIPLET: n = m.shape.n_pi + m.shape.n_sigma_plus + m.shape.n_sigma_minus; break;
-    case CB2_SHAPE_STARK: return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "StarkBroadenedLine is not implemented on the device yet");
+    case CB2_SHAPE_STARK: n = 6; break;   /* pi, sigma+, sigma-: Gaussian slots 0-2, modified-Lorentzian slots 3-5 */
     default: return cb2_fail(CB2_ERR_TYPE, "unsupported line shape kind %d", m.shape.kind);
     }
     if (n < 1) return cb2_fail(CB2_ERR_VALUE, "line shape has no components");
@@ -603,6 +603,59 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
     return A.rc;
 }
 
+// Universal cumulative profile of the modified Lorentzian of StarkBroadenedLine (stark.pyx:52-81) in u = (x - x0)/FWHM:
+// s(u) = K / (|u|^2.5 + A), K = 0.5^1.5 / C, A = 0.5^2.5, C = 4*50*2F1(0.4, 1, 1.4, -(100)^2.5) so that the integral over
+// [-50, 50] is 1.  Phi(u) = int_0^u s; table on [0, 4] (step 1/512, composite 16-point Gauss-Legendre per interval).
+#define CB2_STARK_NORM 2.641279471021934
+#define CB2_LORENTZ_KNOTS 2048
+#define CB2_LORENTZ_UMAX 4.0
+
+static double lorentz_density(double u) {
+    const double K = pow(0.5, 1.5) / CB2_STARK_NORM, A = pow(0.5, 2.5);
+    return K / (pow(fabs(u), 2.5) + A);
+}
+
+// tail mass int_u^inf s(v) dv for u >= 4: K sum_n (-A)^n u^-(2.5 n + 1.5) / (2.5 n + 1.5)
+static double lorentz_tail(double u) {
+    const double K = pow(0.5, 1.5) / CB2_STARK_NORM, A = pow(0.5, 2.5);
+    const double r = pow(u, -2.5);
+    double term = pow(u, -1.5), sum = 0.0;
+    for (int n = 0; n < 12; n++) {
+        sum += term / (2.5 * n + 1.5);
+        term *= -A * r;
+    }
+    return K * sum;
+}
+
+static int build_lorentz(Arena& A, DevScene& S) {
+    static const double gx[8] = {0.0950125098376374, 0.2816035507792589, 0.4580167776572274, 0.6178762444026438,
+                                 0.7554044083550030, 0.8656312023878318, 0.9445750230732326, 0.9894009349916499};
+    static const double gw[8] = {0.1894506104550685, 0.1826034150449236, 0.1691565193950025, 0.1495959888165767,
+                                 0.1246289712555339, 0.0951585116824928, 0.0622535239386479, 0.0271524594117541};
+    std::vector<double2> tab(CB2_LORENTZ_KNOTS + 1);
+    const double h = CB2_LORENTZ_UMAX / CB2_LORENTZ_KNOTS;
+    double acc = 0.0;
+    tab[0] = make_double2(0.0, lorentz_density(0.0));
+    for (int k = 0; k < CB2_LORENTZ_KNOTS; k++) {
+        // the integrand has a |u|^2.5 cusp at 0: split the first intervals finer
+        const int sub = k < 8 ? 64 : 1;
+        for (int q = 0; q < sub; q++) {
+            const double a = (k + (double)q / sub) * h, b = (k + (double)(q + 1) / sub) * h, c = 0.5 * (a + b), d = 0.5 * (b - a);
+            double v = 0.0;
+            for (int i = 0; i < 8; i++) v += gw[i] * (lorentz_density(c + d * gx[i]) + lorentz_density(c - d * gx[i]));
+            acc += v * d;
+        }
+        tab[k + 1] = make_double2(acc, lorentz_density((k + 1) * h));
+    }
+    S.has_lorentz = 1;
+    S.lorentz_tab = A.upload(tab);
+    S.lorentz_phi_inf = acc + lorentz_tail(CB2_LORENTZ_UMAX);
+    // self-check of the normalisation: the profile integrates to 1 over [-50, 50] FWHM (stark.pyx:62-66)
+    if (fabs(2.0 * (S.lorentz_phi_inf - lorentz_tail(50.0)) - 1.0) > 1e-9)
+        return cb2_fail(CB2_ERR_RUNTIME, "internal error: modified-Lorentzian table is not normalised");
+    return A.rc;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // scene create / destroy
 // ------------------------------------------------------------------------------------------------------------------
@@ -637,7 +690,6 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         S.step = d->step;
         S.min_samples = d->min_samples;
         for (int k = 0; k < 12; k++) S.w2p[k] = d->world_to_plasma[k];
-        if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded
         if ((rc = convert_scalar(A, d->electron_density, d->axisym, CB2_DENSITY_SCALE, S.ne)) != CB2_OK) break;
         if ((rc = convert_scalar(A, d->electron_temperature, d->axisym, 1.0, S.te)) != CB2_OK) break;
         bool need_pol = false;
@@ -664,7 +716,15 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         if (rc != CB2_OK) break;
         S.need_b = need_b;
         S.need_pol = need_pol || (need_b && S.b_kind == 1);
+        bool has_brems = false;
+        for (int m = 0; m < d->n_models; m++) has_brems |= d->models[m].kind == CB2_MODEL_BREMSSTRAHLUNG;
+        S.brems.present = has_brems;
+        if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp for the shared-memory budget)
         if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;
+        bool any_stark = false;
+        for (int m = 0; m < d->n_models; m++)
+            any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].shape.kind == CB2_SHAPE_STARK;
+        if (any_stark && (rc = build_lorentz(A, S)) != CB2_OK) break;
         if ((rc = A.rc) != CB2_OK) break;
         void* p = nullptr;
         if ((rc = cb2_cuda_check(cudaMalloc(&p, sizeof(DevScene)), "cudaMalloc(scene)")) != CB2_OK) break;

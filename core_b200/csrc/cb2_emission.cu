@@ -303,7 +303,7 @@ struct RecWriter {
     int* rng;         // [ncomp][NG][2] (lo, hi) bounding bin ranges per group of 32 samples, relative bins
     int nt, tid, ng, group;
     int bins;
-    unsigned long long gauss_evals;
+    unsigned long long gauss_evals, lorentz_evals;
 };
 
 #define SQRT_L2E 1.2011224087864498f
@@ -367,6 +367,31 @@ __device__ __forceinline__ void put_gaussian(RecWriter& W, const DevComp& cs, in
     W.rec[(2 * slot + 1) * W.nt + W.tid] = b;
 }
 
+// Write one modified-Lorentzian component (add_lorentzian_line, stark.pyx:88-147): centre cf (relative bins), FWHM
+// lam_b (bins), amplitude amp.  record a = (1/lam_b, -cf/lam_b, amp, 0), b.w = packed [lo, hi) of the +-50 FWHM cut-off.
+__device__ __forceinline__ void put_lorentzian(RecWriter& W, const DevComp& cs, int slot, float cf, float lam_b, float amp) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (amp > 0.f && lam_b > 0.f) {
+        const float cut = 50.0f * lam_b;                         // LORENTZIAN_CUTOFF_GAMMA
+        const float win_lo = (float)(-cs.c0_int), win_hi = (float)(W.bins - cs.c0_int);
+        const float flo = floorf(cf - cut), fhi = ceilf(cf + cut);
+        if (fhi > win_lo && flo < win_hi) {
+            const int lo = (int)fmaxf(flo, win_lo), hi = (int)fminf(fhi, win_hi);
+            if (hi > lo) {
+                a.x = 1.0f / lam_b;
+                a.y = -cf * a.x;
+                a.z = amp;
+                b.w = pack_range(lo, hi);
+                atomicMin(&W.rng[2 * (slot * W.ng + W.group)], lo);
+                atomicMax(&W.rng[2 * (slot * W.ng + W.group) + 1], hi);
+                W.lorentz_evals += (unsigned long long)(hi - lo) + 1ull;
+            }
+        }
+    }
+    W.rec[(2 * slot) * W.nt + W.tid] = a;
+    W.rec[(2 * slot + 1) * W.nt + W.tid] = b;
+}
+
 __device__ __forceinline__ void put_empty(RecWriter& W, int slot) {
     W.rec[(2 * slot) * W.nt + W.tid] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -409,9 +434,81 @@ __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx&
             radiance = RECIP_4_PI * exp10f(eval_pec_log(M, lne, lte, ood)) * ne * ni;
         }
         const float amp = radiance * in.weight * M.inv_delta;
+        if (M.shape == CB2_SHAPE_STARK) {
+            // StarkBroadenedLine.add_line (stark.pyx:251-348): pseudo-Voigt = (1-eta) Gaussian + eta modified Lorentzian per
+            // Zeeman component; does NOT return early on ts <= 0
+            bool done = !(on && amp > 0.f);
+            float sigma_b = 0.f, lam_b = 0.f, eta = 0.f;
+            if (!done) {
+                const float SIGMA2FWHM = 2.3548200450309493f;
+                const float fl = M.param[0] * powf(ne, M.param[1]) / powf(te, M.param[2]);      // nm (ne in 1e19 m^-3 folded in)
+                const float fg = ts > 0.f ? SIGMA2FWHM * M.sigma_coef * sqrtf(ts) / M.inv_delta : 0.f;   // nm
+                if (fl == 0.f && fg == 0.f) done = true;
+                else {
+                    float full;
+                    if (fg <= fl) {
+                        const float r = fg / fl;
+                        full = fl * (1.f + r * r * (0.57575f + r * (0.37902f + r * (-0.42519f + r * (-0.31525f + r * 0.31718f)))));
+                    } else {
+                        const float r = fl / fg;
+                        full = fg * (1.f + r * (0.15882f + r * (1.04388f + r * (-1.38281f + r * (0.46251f + r * (0.82325f + r * -0.58026f))))));
+                    }
+                    float sigma = full / SIGMA2FWHM;
+                    const float l2t = fl / full;
+                    if (l2t < 0.01f) { eta = 0.f; full = 0.f; }
+                    else if (l2t > 0.999f) { eta = 1.f; sigma = 0.f; }
+                    else {
+                        const float lg = logf(l2t);
+                        eta = expf(5.14820e-04f + lg * (1.38821e+00f + lg * (-9.60424e-02f + lg * (-3.83995e-02f + lg * (-7.40042e-03f + lg * -5.47626e-04f)))));
+                    }
+                    sigma_b = sigma * M.inv_delta;
+                    lam_b = full * M.inv_delta;
+                }
+            }
+            if (done) {
+                for (int k = 0; k < M.ncomp; k++) put_empty(W, M.comp0 + k);
+                continue;
+            }
+            if (!have_b) {
+                bf = eval_b_field(S, ctx);
+                bm = sqrtf(bf.x * bf.x + bf.y * bf.y + bf.z * bf.z);
+                const float c = bm > 0.f ? (bf.x * in.dx + bf.y * in.dy + bf.z * in.dz) / bm : 0.f;
+                cos_sqr = c * c;
+                have_b = true;
+            }
+            const DevComp& c0 = S.comps[M.comp0];
+            const float dop = vd * M.inv_c;
+            const float shift0 = M.wavelength * dop * M.inv_delta;
+            const float wg = 1.f - eta;
+            if (bm == 0.f) {
+                const float r = M.polarisation == CB2_POL_NO ? amp : 0.5f * amp;
+                put_gaussian(W, c0, M.comp0, c0.c0_frac + shift0, sigma_b, wg * r);
+                put_lorentzian(W, c0, M.comp0 + 3, c0.c0_frac + shift0, lam_b, eta * r);
+                put_empty(W, M.comp0 + 1); put_empty(W, M.comp0 + 2); put_empty(W, M.comp0 + 4); put_empty(W, M.comp0 + 5);
+                continue;
+            }
+            const float sin_sqr = 1.0f - cos_sqr;
+            if (M.polarisation != CB2_POL_SIGMA) {
+                const float r = 0.5f * sin_sqr * amp;
+                put_gaussian(W, c0, M.comp0, c0.c0_frac + shift0, sigma_b, wg * r);
+                put_lorentzian(W, c0, M.comp0 + 3, c0.c0_frac + shift0, lam_b, eta * r);
+            } else { put_empty(W, M.comp0); put_empty(W, M.comp0 + 3); }
+            if (M.polarisation != CB2_POL_PI) {
+                const float r = (0.25f * sin_sqr + 0.5f * cos_sqr) * amp;
+                const float e = BOHR_MAGNETON * bm * M.wavelength * (1.0f / HC_EV_NM_F);
+                const float dlp = M.wavelength * e / (1.0f - e), dlm = -M.wavelength * e / (1.0f + e);
+                const float cp = c0.c0_frac + (dlp + (M.wavelength + dlp) * dop) * M.inv_delta;
+                const float cm = c0.c0_frac + (dlm + (M.wavelength + dlm) * dop) * M.inv_delta;
+                put_gaussian(W, c0, M.comp0 + 1, cp, sigma_b, wg * r);
+                put_lorentzian(W, c0, M.comp0 + 4, cp, lam_b, eta * r);
+                put_gaussian(W, c0, M.comp0 + 2, cm, sigma_b, wg * r);
+                put_lorentzian(W, c0, M.comp0 + 5, cm, lam_b, eta * r);
+            } else { put_empty(W, M.comp0 + 1); put_empty(W, M.comp0 + 2); put_empty(W, M.comp0 + 4); put_empty(W, M.comp0 + 5); }
+            continue;
+        }
         // all Gaussian-family shapes return before touching the spectrum if ts <= 0 (gaussian.pyx:127-129)
         const bool shape_on = on && ts > 0.f && amp > 0.f;
-        if (!shape_on || M.shape == CB2_SHAPE_STARK) {
+        if (!shape_on) {
             for (int k = 0; k < M.ncomp; k++) put_empty(W, M.comp0 + k);
             continue;
         }
@@ -511,7 +608,7 @@ __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx&
 __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
                              unsigned long long& brems_evals, unsigned& ood) {
     const DevBrems& B = S.brems;
-    float4 r0 = make_float4(0.f, 0.f, -1.0f, -1.0f);
+    float4 r0 = make_float4(0.f, 0.f, __int_as_float(-1), __int_as_float(-1));
     float4 pc0 = make_float4(0, 0, 0, 0), pc1 = pc0, pc2 = pc0;
     if (ne > 0.f && te > 0.f && in.weight > 0.f) {
         const float lte = log10f(te);
@@ -531,8 +628,9 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
         // wavelength (1/lambda) thresholds where the piece changes: u = knot  <=>  rho = knot * Te / hc
         // bins whose centre wavelength is <= lambda_knot (1/lambda >= knot Te/hc) belong to the next piece:
         // store the first bin of the lower piece, bc = floor(xc - 1/2) + 1 with xc = (lambda_knot - lambda_min)/delta
-        if (np > 1) r0.z = floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 1)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f;
-        if (np > 2) r0.w = floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 2)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f;
+        // (integers are stored bit-cast: float<->int conversions run on the same XU pipe as MUFU.EX2, the binding pipe of the BIN phase)
+        if (np > 1) r0.z = __int_as_float((int)fminf(fmaxf(floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 1)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f, -1.0f), 1.0e6f));
+        if (np > 2) r0.w = __int_as_float((int)fminf(fmaxf(floorf((exp10f(B.log_hc - lte - __ldg(G.x + i_lo + 2)) - S.min_wavelength) / S.delta - 0.5f) + 1.0f, -1.0f), 1.0e6f));
         const float k1 = 0.5513288954217921f * 2.302585092994046f;            // sqrt(3)/pi * ln 10
         const float k0 = 0.5513288954217921f * (1.3862943611198906f - 0.5772156649015329f);  // sqrt(3)/pi (ln 4 - gamma_E)
         for (int s = 0; s < B.n_charged; s++) {
@@ -576,7 +674,7 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
         const float hh = fabsf(B.mid_c1 / te - B.mid_c0) + 0.1f * B.mid_c0;
         const bool multi = (B.nq > 1) && (hh * hh * (1.0f / 6.0f) > 2e-6f);
         r0.x = B.exp_coef / te;
-        r0.y = (float)(np + (multi ? 8 : 0));
+        r0.y = __int_as_float(np + (multi ? 8 : 0));
         brems_evals += (unsigned long long)S.bins;
     }
     brec[tid] = r0;
@@ -588,17 +686,15 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-// WINDOW PASS — bin integrals of one line component over one 32-bin window for one group of <= 32 consecutive
-// samples, lanes = samples.  Every lane evaluates its own sample's Gaussian at the window's 32 bins (series form: no
-// cross-bin dependence; erfc form: the reference's lower = upper recurrence along the window, gaussian.pyx:78-88) and
-// adds into its private part[w]; the 32 partial vectors are summed across lanes with a transpose-reduce (31 shuffles)
-// so that lane w holds window bin w, which is added to the fp64 per-ray accumulator.  Lane utilisation is 100% however
-// narrow the line is, and the per-sample bookkeeping is paid once per 32 bins.
-__device__ __forceinline__ void window_pass(const float4* __restrict__ ra, const float4* __restrict__ rb, int n, int wbase, int wcount,
-                                            int c0_int, int bins, double* __restrict__ racc, int lane) {
-    float part[32];
-#pragma unroll
-    for (int w = 0; w < 32; w++) part[w] = 0.f;
+// WINDOW PASS — bin integrals of one line component over one 32-bin window, lanes = samples.  Every lane evaluates its
+// own sample's Gaussian at the window's bins (series form: no cross-bin dependence; erfc form: the reference's
+// lower = upper recurrence along the window, gaussian.pyx:78-88) and adds into its private part[w].  After all groups
+// of the chunk have been accumulated the 32 partial vectors are summed across lanes with a transpose-reduce
+// (31 shuffles) so that lane w holds window bin w, which is added to the fp64 per-ray accumulator.  Lane utilisation is
+// 100% however narrow the line is, and the per-sample bookkeeping is paid once per 32 bins.
+template <bool FULL_WINDOW>
+__device__ __forceinline__ void window_accumulate(float (&part)[32], const float4* __restrict__ ra, const float4* __restrict__ rb, int n,
+                                                  int wbase, int wcount, int lane) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = make_float4(0.f, 0.f, 0.f, 0.f);
     int lo = 0, hi = 0;
     if (lane < n) {
@@ -614,9 +710,9 @@ __device__ __forceinline__ void window_pass(const float4* __restrict__ ra, const
                     s4 = series ? bq.z : 0.f;
 #pragma unroll
         for (int w = 0; w < 32; w++) {
-            if (w < wcount) {                                          // warp-uniform
+            if (FULL_WINDOW || w < wcount) {                           // warp-uniform
                 const float x = fmaf((float)w, a.x, x0);
-                const float m2 = fminf(x * x, 126.0f);                 // exp2(-126) ~ 1e-38: keeps far-off bins finite
+                const float m2 = x * x;
                 part[w] = fmaf(ex2_approx(-m2), fmaf(fmaf(fmaf(fmaf(s4, m2, s3), m2, s2), m2, s1), m2, s0), part[w]);
             }
         }
@@ -629,7 +725,7 @@ __device__ __forceinline__ void window_pass(const float4* __restrict__ ra, const
         float tl = half_erfc(fabsf(xl));
 #pragma unroll
         for (int w = 0; w < 32; w++) {
-            if (w < wcount) {
+            if (FULL_WINDOW || w < wcount) {
                 const float xu = fmaf((float)(w + 1), a.x, xbase);
                 const float tu = half_erfc(fabsf(xu));
                 const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
@@ -638,19 +734,98 @@ __device__ __forceinline__ void window_pass(const float4* __restrict__ ra, const
             }
         }
     }
-    // transpose-reduce: after the step with offset o a lane keeps the half of its vector selected by (lane & o)
+}
+
+// Phi(u) = int_0^u s(v) dv of the modified Lorentzian (odd in u), float64: cubic Hermite on the [0, 4] table, asymptotic
+// tail series beyond (K sum_n (-A)^n u^-(2.5 n + 1.5)/(2.5 n + 1.5)).
+__device__ __forceinline__ double lorentz_cdf(const double2* __restrict__ tab, double phi_inf, double u) {
+    const double au = fabs(u);
+    double v;
+    if (au < 4.0) {
+        const double f = au * 512.0;
+        const int i = min((int)f, 2047);
+        const double t = f - (double)i, h = 1.0 / 512.0;
+        const double2 p0 = __ldg(tab + i), p1 = __ldg(tab + i + 1);
+        const double d0 = p0.y * h, d1 = p1.y * h;
+        const double a2 = 3.0 * (p1.x - p0.x) - 2.0 * d0 - d1, a3 = 2.0 * (p0.x - p1.x) + d0 + d1;
+        v = p0.x + t * (d0 + t * (a2 + t * a3));
+    } else {
+        const double K = 0.13385686538368502, A = 0.1767766952966369;     // 0.5^1.5 / C, 0.5^2.5
+        const double sq = sqrt(au), r = 1.0 / (au * au * sq);              // u^-2.5
+        double term = 1.0 / (au * sq), sum = 0.0;                          // u^-1.5
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const bool upper = (lane & o) != 0;
+        for (int n = 0; n < 8; n++) { sum += term * (1.0 / (2.5 * n + 1.5)); term *= -A * r; }
+        v = phi_inf - K * sum;
+    }
+    return u < 0.0 ? -v : v;
+}
+
+// window pass for a modified-Lorentzian component (lanes = samples): float64 CDF differences along the window's edges
+template <bool FULL_WINDOW>
+__device__ __forceinline__ void window_accumulate_lorentz(float (&part)[32], const float4* __restrict__ ra, const float4* __restrict__ rb,
+                                                          int n, int wbase, int wcount, int lane, const double2* __restrict__ tab,
+                                                          double phi_inf) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int lo = 0, hi = 0;
+    if (lane < n) {
+        a = ra[lane];
+        if (a.z != 0.f) { const float4 bq = rb[lane]; unpack_range(bq.w, lo, hi); lo -= wbase; hi -= wbase; }
+    }
+    const bool live = hi > 0 && lo < wcount && a.z != 0.f;
+    if (!__any_sync(FULL, live)) return;
+    // u at bin edge e (relative bins): u = e / lam_b - cf / lam_b
+    const double inv_l = (double)a.x, off = (double)a.y;
+    double pl = live ? lorentz_cdf(tab, phi_inf, (double)wbase * inv_l + off) : 0.0;
 #pragma unroll
-        for (int i = 0; i < o; i++) {
-            const float send = upper ? part[i] : part[i + o];
-            const float keep = upper ? part[i + o] : part[i];
-            part[i] = keep + __shfl_xor_sync(FULL, send, o);
+    for (int w = 0; w < 32; w++) {
+        if (FULL_WINDOW || w < wcount) {
+            if (live && w >= lo - 0 && w < hi) {
+                if (w == lo && lo > 0) pl = lorentz_cdf(tab, phi_inf, (double)(wbase + w) * inv_l + off);
+                const double pu = lorentz_cdf(tab, phi_inf, (double)(wbase + w + 1) * inv_l + off);
+                part[w] = fmaf(a.z, (float)(pu - pl), part[w]);
+                pl = pu;
+            }
         }
     }
-    const int bin = c0_int + wbase + lane;
-    if (lane < wcount && part[0] != 0.f && bin >= 0 && bin < bins) atomicAdd(&racc[bin], (double)part[0]);
+}
+
+// all windows of component c that belong to this warp, for one chunk
+template <int NW, int NG, int NT>
+__device__ __forceinline__ void line_windows(const float4* __restrict__ ra, const float4* __restrict__ rb, const int* __restrict__ rng,
+                                             int nact, int c, int c0_int, int bins, double* __restrict__ racc, int warp, int lane,
+                                             int type, const double2* __restrict__ ltab, double phi_inf) {
+    int Rlo = INT_MAX, Rhi = INT_MIN;                                  // union over the chunk
+#pragma unroll
+    for (int g = 0; g < NG; g++) { Rlo = min(Rlo, rng[2 * g]); Rhi = max(Rhi, rng[2 * g + 1]); }
+    if (Rhi <= Rlo) return;
+    int k = (warp - c) % NW;
+    if (k < 0) k += NW;
+    for (int wbase = Rlo + 32 * k; wbase < Rhi; wbase += 32 * NW) {
+        const int wcount = min(32, Rhi - wbase);
+        float part[32];
+#pragma unroll
+        for (int w = 0; w < 32; w++) part[w] = 0.f;
+        for (int g = 0; g * 32 < nact; g++) {
+            if (rng[2 * g + 1] <= wbase || rng[2 * g] >= wbase + wcount) continue;   // group does not touch the window
+            const int n = min(32, nact - g * 32);
+            if (type == 1) window_accumulate_lorentz<false>(part, ra + g * 32, rb + g * 32, n, wbase, wcount, lane, ltab, phi_inf);
+            else if (wcount == 32) window_accumulate<true>(part, ra + g * 32, rb + g * 32, n, wbase, 32, lane);
+            else window_accumulate<false>(part, ra + g * 32, rb + g * 32, n, wbase, wcount, lane);
+        }
+        // transpose-reduce: after the step with offset o a lane keeps the half of its vector selected by (lane & o)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; i++) {
+                const float send = upper ? part[i] : part[i + o];
+                const float keep = upper ? part[i + o] : part[i];
+                part[i] = keep + __shfl_xor_sync(FULL, send, o);
+            }
+        }
+        const int bin = c0_int + wbase + lane;
+        if (lane < wcount && part[0] != 0.f && bin >= 0 && bin < bins) atomicAdd(&racc[bin], (double)part[0]);
+    }
 }
 
 __device__ __forceinline__ double xform_row(const double* m, double x, double y, double z, bool point) {
@@ -659,6 +834,9 @@ __device__ __forceinline__ double xform_row(const double* m, double x, double y,
     return point ? __dadd_rn(v, m[3]) : v;
 }
 
+#ifndef CB2_TARGET_THREADS
+#define CB2_TARGET_THREADS 512
+#endif
 #ifndef CB2_MIN_BLOCKS_NW4
 #define CB2_MIN_BLOCKS_NW4 4
 #endif
@@ -667,7 +845,7 @@ __device__ __forceinline__ double xform_row(const double* m, double x, double y,
 #endif
 
 template <int NW, int BPL, int BREMS>
-__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32))
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 768 : 512) / (NW * 32))
 emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict__ out, int out_f64, double scale, int accumulate,
                 unsigned long long* __restrict__ stats) {
     constexpr int NT = NW * 32;
@@ -714,7 +892,7 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
         }
     }
 
-    unsigned long long n_samples = 0, n_gauss = 0, n_brems = 0;
+    unsigned long long n_samples = 0, n_gauss = 0, n_brems = 0, n_lorentz = 0;
     unsigned ood = 0;
     int parity = 0;
     __syncthreads();
@@ -758,9 +936,10 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                 }
                 RecWriter W;
                 W.rec = rec; W.rng = s_rng + parity * rng_stride; W.nt = NT; W.tid = tid; W.ng = NG; W.group = warp;
-                W.bins = S.bins; W.gauss_evals = 0;
+                W.bins = S.bins; W.gauss_evals = 0; W.lorentz_evals = 0;
                 sample_lines(S, in, ctx, ne, te, W, ood);
                 n_gauss += W.gauss_evals;
+                n_lorentz += W.lorentz_evals;
                 if (BREMS) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
             }
             __syncthreads();
@@ -768,22 +947,11 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
             for (int i = tid; i < rng_stride; i += NT) s_rng[(parity ^ 1) * rng_stride + i] = (i & 1) ? INT_MIN : INT_MAX;
             const int nact = min(NT, iv - k0 + 1);
             const int* rng = s_rng + parity * rng_stride;
-            // LINES: lanes = samples.  For every (component, group of 32 samples) the union of the bin ranges is cut into
-            // 32-bin windows, dealt round-robin to the warps.
-            for (int c = 0; c < ncomp; c++) {
-                const int c0_int = S.comps[c].c0_int;
-                const float4* ra = rec + (size_t)(2 * c) * NT;
-                const float4* rb = ra + NT;
-                for (int g = 0; g * 32 < nact; g++) {
-                    const int rlo = rng[2 * (c * NG + g)], rhi = rng[2 * (c * NG + g) + 1];   // union of the group's bin ranges
-                    if (rhi <= rlo) continue;
-                    const int n = min(32, nact - g * 32);
-                    int k = (warp - c - g) % NW;                          // first window of this (c, g) that is mine
-                    if (k < 0) k += NW;
-                    for (int wbase = rlo + 32 * k; wbase < rhi; wbase += 32 * NW)
-                        window_pass(ra + g * 32, rb + g * 32, n, wbase, min(32, rhi - wbase), c0_int, S.bins, racc, lane);
-                }
-            }
+            // LINES: lanes = samples.  The union of a component's bin ranges over the chunk is cut into 32-bin windows,
+            // dealt round-robin to the warps.
+            for (int c = 0; c < ncomp; c++)
+                line_windows<NW, NG, NT>(rec + (size_t)(2 * c) * NT, rec + (size_t)(2 * c + 1) * NT, rng + 2 * c * NG, nact, c,
+                                         S.comps[c].c0_int, S.bins, racc, warp, lane, S.comps[c].type, S.lorentz_tab, S.lorentz_phi_inf);
             if (BREMS) {
                 const float4* btab = S.brems.bin_tab;
                 const float4* btab1 = S.brems.bin_tab1;
@@ -792,15 +960,19 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                     const float4 r0 = brec[s];
                     if (r0.x == 0.f) continue;
                     const float na2 = -r0.x;
-                    if (r0.y < 7.5f) {
+                    const int flags = __float_as_int(r0.y);
+                    if (flags < 8) {
                         // one-point rule.  Pieces (window crossing a knot of the Gaunt table's u grid) are contiguous in bin
                         // index: piece 0 = bins [bc1, end), piece 1 = [bc2, bc1), piece 2 = [0, bc2).  A warp tile lies in
                         // one piece unless the knot falls inside it.
-                        const int np = (int)r0.y;
-                        const int t_first = warp * TB, t_last = warp * TB + TB - 1;
-                        const int bc1 = (int)r0.z, bc2 = (int)r0.w;
-                        const int pf = (np > 1 && t_first < bc1) ? ((np > 2 && t_first < bc2) ? 2 : 1) : 0;
-                        const int pl = (np > 1 && t_last < bc1) ? ((np > 2 && t_last < bc2) ? 2 : 1) : 0;
+                        const int np = flags;
+                        const int bc1 = __float_as_int(r0.z), bc2 = __float_as_int(r0.w);
+                        int pf = 0, pl = 0;
+                        if (np > 1) {
+                            const int t_first = warp * TB, t_last = warp * TB + TB - 1;
+                            pf = (t_first < bc1) ? ((np > 2 && t_first < bc2) ? 2 : 1) : 0;
+                            pl = (t_last < bc1) ? ((np > 2 && t_last < bc2) ? 2 : 1) : 0;
+                        }
                         if (pf == pl) {
                             const float4 pc = brec[(1 + pf) * NT + s];
 #pragma unroll
@@ -826,16 +998,16 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                         }
                     } else {
                         // cold sample: nq-point Gauss-Legendre rule from the table, piece chosen per quadrature point
-                        const int np = (int)r0.y - 8;
+                        const int np = flags - 8;
                         const float4 p0 = brec[NT + s], p1 = brec[2 * NT + s], p2 = brec[3 * NT + s];
-                        const float xc1 = np > 1 ? r0.z : -1.0f, xc2 = np > 2 ? r0.w : -1.0f;
+                        const int xc1 = np > 1 ? __float_as_int(r0.z) : -1, xc2 = np > 2 ? __float_as_int(r0.w) : -1;
 #pragma unroll
                         for (int j = 0; j < BPL; j++) {
                             const int bin = warp * TB + 32 * j + lane;
                             const float4* tb = btab + (size_t)bin * nq;
                             float4 pc = p0;
-                            if ((float)bin < xc1) pc = p1;
-                            if ((float)bin < xc2) pc = p2;
+                            if (bin < xc1) pc = p1;
+                            if (bin < xc2) pc = p2;
                             float v = 0.f;
                             for (int q = 0; q < nq; q++) {
                                 const float4 t = __ldg(tb + q);
@@ -880,11 +1052,13 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
         for (int off = 16; off > 0; off >>= 1) {
             n_gauss += __shfl_down_sync(FULL, n_gauss, off);
             n_brems += __shfl_down_sync(FULL, n_brems, off);
+            n_lorentz += __shfl_down_sync(FULL, n_lorentz, off);
             oodl += __shfl_down_sync(FULL, oodl, off);
         }
         if (lane == 0) {
             if (n_gauss) atomicAdd(stats + 1, n_gauss);
             if (n_brems) atomicAdd(stats + 3, n_brems);
+            if (n_lorentz) atomicAdd(stats + 2, n_lorentz);
             if (oodl) atomicAdd(stats + 5, oodl);
         }
         if (tid == 0 && n_samples) atomicAdd(stats + 0, n_samples);
@@ -894,16 +1068,28 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
 // ------------------------------------------------------------------------------------------------------------------
 // launch configuration
 // ------------------------------------------------------------------------------------------------------------------
+static size_t emission_smem_bytes(int nw, int bpl, int n_comp, bool brems) {
+    const size_t nt = (size_t)nw * 32;
+    return nt * bpl * sizeof(double) + ((size_t)2 * n_comp * nt + (brems ? 4 * nt : 0)) * sizeof(float4) + (size_t)2 * 2 * n_comp * nw * sizeof(int);
+}
+
 int cb2_emission_config(cb2_scene* sc) {
+    // (warps per CTA, bins per lane) instances in order of preference per spectral size; the per-sample records live in
+    // shared memory (32 B x components x samples per chunk), so scenes with many components fall back to fewer warps
+    static const int cand[][2] = {{4, 1}, {4, 2}, {4, 4}, {2, 8}, {1, 16}, {8, 4}, {4, 8}, {2, 16}, {8, 8}, {4, 16}, {8, 16}};
     const int bins = sc->host.bins;
-    int nw, bpl;
-    if (bins <= 128) { nw = 4; bpl = 1; }
-    else if (bins <= 256) { nw = 4; bpl = 2; }
-    else if (bins <= 512) { nw = 4; bpl = 4; }
-    else if (bins <= 1024) { nw = 8; bpl = 4; }
-    else if (bins <= 2048) { nw = 8; bpl = 8; }
-    else if (bins <= 4096) { nw = 8; bpl = 16; }
-    else return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
+    const size_t budget = 100 * 1024;
+    int nw = 0, bpl = 0;
+    size_t best = (size_t)-1;
+    for (auto& c : cand) {
+        if (c[0] * 32 * c[1] < bins) continue;
+        const size_t need = emission_smem_bytes(c[0], c[1], sc->host.n_comp, sc->host.brems.present);
+        if (need <= budget) { nw = c[0]; bpl = c[1]; break; }          // first (preferred) instance that fits
+        if (need < best) { best = need; nw = c[0]; bpl = c[1]; }        // otherwise the leanest one
+    }
+    if (!nw) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
+    if (emission_smem_bytes(nw, bpl, sc->host.n_comp, sc->host.brems.present) > 200 * 1024)
+        return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components (%d) for %d spectral bins", sc->host.n_comp, bins);
     // tuning override (experiments): CB2_NW x CB2_BPL must cover the bins and be an instantiated pair
     const char *env_nw = getenv("CB2_NW"), *env_bpl = getenv("CB2_BPL");
     if (env_nw && env_bpl) {
@@ -921,8 +1107,7 @@ static int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int o
                       unsigned long long* stats, cudaStream_t st) {
     const DevScene& S = sc->host;
     const int NT = NW * 32;
-    const size_t smem = (size_t)NT * BPL * sizeof(double) + ((size_t)2 * S.n_comp * NT + (S.brems.present ? 4 * NT : 0)) * sizeof(float4)
-                        + (size_t)2 * 2 * S.n_comp * NW * sizeof(int);
+    const size_t smem = emission_smem_bytes(NW, BPL, S.n_comp, S.brems.present);
     const int mode = !S.brems.present ? 0 : (BPL <= 8 ? 1 : 2);
     if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
     dim3 grid((unsigned)rays.n_rays), block(NT);

@@ -153,6 +153,11 @@ struct DevScene {
     DevComp comps[CB2_MAX_COMP];
     DevAxisym ax;
     DevBrems brems;
+    // modified-Lorentzian (Stark) cumulative profile, universal in u = (x - centre)/FWHM (stark.pyx:52-81):
+    // knots u_k = k/512 on [0, 4]: (Phi(u_k), dPhi/du(u_k)); beyond u = 4 an asymptotic tail series is used
+    int has_lorentz;
+    const double2* lorentz_tab;
+    double lorentz_phi_inf;
 };
 
 struct DevRays {

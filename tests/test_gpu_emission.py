@@ -242,3 +242,49 @@ def test_generomak_c3_mix():
     rays = generomak_camera_rays(plasma, (3, 3))
     got, ref, stats, rstats = both(flat, rays)
     assert_parity(got, ref, what="generomak C3 mix")
+
+
+def test_stark_broadened_line_slab():
+    # core/tests/test_lineshapes.py:316-389 inputs through the CUDA path (float64 Lorentzian CDF on the device)
+    line = cb.Line(cb.deuterium, 0, (6, 2))
+    for pol in ("no", "pi", "sigma"):
+        got, ref, stats, rstats = _lineshape_case(cb.StarkBroadenedLine, kwargs={"polarisation": pol}, line=line,
+                                                  lo=656.104 - 0.2, hi=656.104 + 0.2, bins=512)
+        assert stats["lorentzian_bin_evals"] == rstats["lorentzian_bin_evals"] > 0
+        assert_parity(got, ref, what="stark %s" % pol)
+
+
+def balmer_series_scene(bins=1024, lo=380.0, hi=680.0):
+    """BASELINE config C2 (demos/balmer_series.py:40-93 shape): Gaussian-volume deuterium plasma in a sphere, B = (1,1,1) T,
+    flow (-1e5, 0, 0) m/s, 5 Balmer lines x {excitation, recombination} with Stark + Doppler + Zeeman line shapes."""
+    sigma = 0.25
+    plasma = cb.Plasma()
+    plasma.geometry = cb.Sphere(sigma * 5.0)
+    plasma.integrator = cb.NumericalIntegrator(step=sigma / 5.0)
+    d_density = cb.GaussianVolume(0.5e19, sigma * 10000)
+    e_density = cb.GaussianVolume(1e19, sigma * 10000)
+    temperature = cb.GaussianVolume(79, sigma, offset=1.0)
+    v = (-1e5, 0, 0)
+    d_dist = cb.Maxwellian(d_density, temperature, v, cb.deuterium.atomic_weight * 1.66053906660e-27)
+    plasma.electron_distribution = cb.Maxwellian(e_density, temperature, v, 9.1093837015e-31)
+    plasma.composition = [cb.Species(cb.deuterium, 0, d_dist), cb.Species(cb.deuterium, 1, d_dist)]
+    plasma.b_field = (1.0, 1.0, 1.0)
+    plasma.atomic_data = cb.SyntheticADAS()
+    lines = [cb.Line(cb.deuterium, 0, (n, 2)) for n in (3, 4, 5, 6, 7)]
+    plasma.models = [cb.ExcitationLine(l, lineshape=cb.StarkBroadenedLine) for l in lines] + \
+                    [cb.RecombinationLine(l, lineshape=cb.StarkBroadenedLine) for l in lines]
+    return plasma, cb.flatten_scene(plasma, lo, hi, bins)
+
+
+def test_c2_balmer_series_stark():
+    plasma, flat = balmer_series_scene()
+    # 64 lines of sight fanned in the x-z plane through the origin
+    xs = np.linspace(-5, 5, 64)
+    o = np.stack([xs, np.zeros(64), np.full(64, -5.0)], axis=1)
+    d = -o / np.linalg.norm(o, axis=1, keepdims=True)
+    rays = cb.ray_segments(plasma.geometry, o, d)
+    assert rays.n_segments == 64
+    got, ref, stats, rstats = both(flat, rays)
+    assert stats["samples"] == rstats["samples"]
+    assert stats["lorentzian_bin_evals"] == rstats["lorentzian_bin_evals"] > 0
+    assert_parity(got, ref, what="C2 balmer series (Stark)")
