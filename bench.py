@@ -207,6 +207,11 @@ def main():
     stats = torch.zeros(6, dtype=torch.int64, device=dev)
 
     peaks = measure_peaks(local_rank) if rank == 0 else None
+    plan = scene.info()
+    launches_per_step = 1
+    if plan["brems_mode"] == "moments":
+        # per moment batch: emission_kernel (lines + moments) and contract_kernel (moments . phi)
+        launches_per_step = 2 * -(-pix.size // max(plan["moment_batch_rays"], 1))
 
     def step(k):
         scene.render_device(dev_rays[k % len(dev_rays)], frame, scale=1.0 / 16.0, accumulate=(k % 16) != 0, stats=stats)
@@ -316,11 +321,11 @@ def main():
         cpu_v, cpu_s, cpu_t = cpu_baseline(flat, plasma, args.pixels, args.cpu_rays, threads)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "gpu_launches": args.steps,
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": "%d rays (random pixels, seeded) of the same frame, %d samples in %.1f s" % (args.cpu_rays, cpu_s, cpu_t)},
-                "out_of_domain_samples": ood}
+                "out_of_domain_samples": ood, "plan": plan}
         if e2e:
             line["e2e"] = e2e
         print(json.dumps(line), flush=True)

@@ -132,26 +132,8 @@ static const float4* make_coef1d(Arena& A, const double* x, const double* f, int
     return A.upload(c);
 }
 
-static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const double* f, int nx, int ny) {
-    DevTable2D t;
-    memset(&t, 0, sizeof t);
-    t.nx = nx;
-    t.ny = ny;
-    std::vector<float> xs(nx), ys(ny), iwx(std::max(nx - 1, 1)), iwy(std::max(ny - 1, 1));
-    for (int i = 0; i < nx; i++) xs[i] = (float)x[i];
-    for (int j = 0; j < ny; j++) ys[j] = (float)y[j];
-    for (int i = 0; i + 1 < nx; i++) iwx[i] = (float)(1.0 / (x[i + 1] - x[i]));
-    for (int j = 0; j + 1 < ny; j++) iwy[j] = (float)(1.0 / (y[j + 1] - y[j]));
-    t.uniform = is_uniform(x, nx) && is_uniform(y, ny);
-    t.x0 = (float)x[0];
-    t.y0 = (float)y[0];
-    t.inv_dx = (float)((nx - 1) / (x[nx - 1] - x[0]));
-    t.inv_dy = (float)((ny - 1) / (y[ny - 1] - y[0]));
-    t.xmin = (float)x[0];
-    t.xmax = (float)x[nx - 1];
-    t.ymin = (float)y[0];
-    t.ymax = (float)y[ny - 1];
-    // knot derivatives
+// fp64 per-cell polynomial coefficients of the bicubic: c[cell*16 + 4*p + q] multiplies t^p u^q (t along x, u along y)
+static void build_coef2d(const double* x, const double* y, const double* f, int nx, int ny, std::vector<double>& coef) {
     std::vector<double> fx((size_t)nx * ny), fy((size_t)nx * ny), fxy((size_t)nx * ny);
     for (int i = 0; i < nx; i++)
         for (int j = 0; j < ny; j++) {
@@ -159,7 +141,7 @@ static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const
             fy[(size_t)i * ny + j] = d1(y, f + (size_t)i * ny, ny, 1, j);
             fxy[(size_t)i * ny + j] = d2(x, y, f, nx, ny, i, j);
         }
-    std::vector<float4> coef((size_t)(nx - 1) * (ny - 1) * 4);
+    coef.assign((size_t)(nx - 1) * (ny - 1) * 16, 0.0);
     for (int i = 0; i + 1 < nx; i++)
         for (int j = 0; j + 1 < ny; j++) {
             const double hx = x[i + 1] - x[i], hy = y[j + 1] - y[j];
@@ -185,9 +167,35 @@ static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const
             for (int p = 0; p < 4; p++) {  // power of t
                 double a[4];
                 hermite_coef(cx[0][p], cx[1][p], cx[2][p], cx[3][p], a);
-                coef[((size_t)i * (ny - 1) + j) * 4 + p] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+                for (int q = 0; q < 4; q++) coef[((size_t)i * (ny - 1) + j) * 16 + 4 * p + q] = a[q];
             }
         }
+}
+
+static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const double* f, int nx, int ny) {
+    DevTable2D t;
+    memset(&t, 0, sizeof t);
+    t.nx = nx;
+    t.ny = ny;
+    std::vector<float> xs(nx), ys(ny), iwx(std::max(nx - 1, 1)), iwy(std::max(ny - 1, 1));
+    for (int i = 0; i < nx; i++) xs[i] = (float)x[i];
+    for (int j = 0; j < ny; j++) ys[j] = (float)y[j];
+    for (int i = 0; i + 1 < nx; i++) iwx[i] = (float)(1.0 / (x[i + 1] - x[i]));
+    for (int j = 0; j + 1 < ny; j++) iwy[j] = (float)(1.0 / (y[j + 1] - y[j]));
+    t.uniform = is_uniform(x, nx) && is_uniform(y, ny);
+    t.x0 = (float)x[0];
+    t.y0 = (float)y[0];
+    t.inv_dx = (float)((nx - 1) / (x[nx - 1] - x[0]));
+    t.inv_dy = (float)((ny - 1) / (y[ny - 1] - y[0]));
+    t.xmin = (float)x[0];
+    t.xmax = (float)x[nx - 1];
+    t.ymin = (float)y[0];
+    t.ymax = (float)y[ny - 1];
+    std::vector<double> c64;
+    build_coef2d(x, y, f, nx, ny, c64);
+    std::vector<float4> coef((size_t)(nx - 1) * (ny - 1) * 4);
+    for (size_t k = 0; k < coef.size(); k++)
+        coef[k] = make_float4((float)c64[4 * k], (float)c64[4 * k + 1], (float)c64[4 * k + 2], (float)c64[4 * k + 3]);
     t.x = A.upload(xs);
     t.y = A.upload(ys);
     t.inv_wx = A.upload(iwx);
@@ -527,6 +535,195 @@ static void gl_nodes(int n, double* x, double* w) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Bremsstrahlung moment formulation: host-side table (fp64) — see DevBrems in cb2_internal.h and DESIGN.md
+// ------------------------------------------------------------------------------------------------------------------
+// range of the positive values a scalar field can take; false if it cannot be bounded away from zero / infinity
+static bool scalar_bounds(const cb2_scalar_field& f, const cb2_axisym* ax, double& lo, double& hi) {
+    lo = INFINITY; hi = -INFINITY;
+    auto add = [&](double v) { if (v > 0) { lo = fmin(lo, v); hi = fmax(hi, v); } };
+    switch (f.kind) {
+    case CB2_FIELD_CONSTANT: add(f.c[0]); break;
+    case CB2_FIELD_GAUSSIAN_VOLUME:
+        if (!(f.c[0] > 0) || f.c[1] < 0) return false;      // decays to the bias: needs a positive bias
+        add(f.c[0]); add(f.c[0] + f.c[1]);
+        break;
+    case CB2_FIELD_SLAB_ION:
+        if (!(f.c[0] > 0) || !(f.c[1] > 0)) return false;
+        add(f.c[0]); add(f.c[1]);
+        break;
+    case CB2_FIELD_AXISYM_BLEND: {
+        if (!ax) return false;
+        if (f.edge)
+            for (int i = 0; i < ax->n_triangles; i++) {
+                if (!(f.edge[i] > 0)) return false;           // a zero edge value blends to arbitrarily small positives
+                add(f.edge[i]);
+            }
+        if (f.core) {
+            const int n = ax->n_core;
+            for (int i = 0; i + 1 < n; i++) {
+                const double h = ax->core_psin[i + 1] - ax->core_psin[i];
+                double a[4];
+                hermite_coef(f.core[i], f.core[i + 1], d1(ax->core_psin, f.core, n, 1, i) * h, d1(ax->core_psin, f.core, n, 1, i + 1) * h, a);
+                for (int q = 0; q <= 16; q++) {
+                    const double t = q / 16.0, v = a[0] + t * (a[1] + t * (a[2] + t * a[3]));
+                    if (!(v > 0)) return false;
+                    add(v);
+                }
+            }
+            if (n == 1) add(f.core[0]);
+        }
+        break;
+    }
+    default: return false;                                   // SLAB_NEUTRAL decays to zero
+    }
+    return lo <= hi;
+}
+
+struct HostGaunt {
+    int nu, ng;
+    std::vector<double> lu, lg, coef;
+    double u_min, u_max, g_min, g_max;
+    // InterpolatedFreeFreeGauntFactor.evaluate (gaunt.pyx:109-140), fp64
+    double eval(double z, double te, double wavelength) const {
+        if (z == 0) return 0.0;
+        const double gamma2 = z * z * 13.605693122994 / te, u = HC_EV_NM / (te * wavelength);
+        if (u >= u_max || gamma2 >= g_max) return 1.0;
+        if (u < u_min || gamma2 < g_min) return sqrt(3.0) / M_PI * (log(4.0 / u) - 0.5772156649015329);
+        const double x = log10(u), y = log10(gamma2);
+        int i = (int)(std::upper_bound(lu.begin(), lu.end(), x) - lu.begin()) - 1;
+        int j = (int)(std::upper_bound(lg.begin(), lg.end(), y) - lg.begin()) - 1;
+        i = std::min(std::max(i, 0), nu - 2);
+        j = std::min(std::max(j, 0), ng - 2);
+        const double t = (x - lu[i]) / (lu[i + 1] - lu[i]), w = (y - lg[j]) / (lg[j + 1] - lg[j]);
+        const double* c = &coef[((size_t)i * (ng - 1) + j) * 16];
+        double v = 0.0;
+        for (int p = 3; p >= 0; p--) v = v * t + (c[4 * p] + w * (c[4 * p + 1] + w * (c[4 * p + 2] + w * c[4 * p + 3])));
+        return v;
+    }
+};
+
+// s = ln(tau) + tau/tau_c: logarithmic where the Gaunt factor varies with ln(T), linear in 1/T where exp(-x/T) does
+static double node_map(double tau, double tau_c) { return log(tau) + tau / tau_c; }
+static double node_map_inverse(double s, double tau_c) {
+    double tau = exp(fmin(s, log(tau_c)));
+    for (int it = 0; it < 100; it++) {
+        const double d = (node_map(tau, tau_c) - s) / (1.0 / tau + 1.0 / tau_c);
+        tau = fmax(tau - d, 1e-300);
+        if (fabs(d) <= 1e-15 * tau) break;
+    }
+    return tau;
+}
+
+// Decide whether the moment formulation applies to this scene and, if so, build its table.
+static int build_brems_moments(Arena& A, const cb2_scene_desc& d, DevScene& S) {
+    DevBrems& b = S.brems;
+    b.mode = 0;
+    const char* env = getenv("CB2_BREMS_MODE");
+    const bool force_direct = d.brems_quadrature > 0 || (env && !strcmp(env, "direct"));
+    const bool force_moments = d.brems_quadrature < 0;
+    if (force_direct) return CB2_OK;
+    const cb2_gaunt& g = d.gaunt;
+    const double lmin = d.grid.min_wavelength, lmax = d.grid.max_wavelength, delta = S.delta_d;
+    const char* why = nullptr;
+    // distinct charges
+    int zval[CB2_MAX_BREMS_Z], nz = 0;
+    for (int s = 0; s < b.n_charged && !why; s++) {
+        const int z = d.species[b.charged[s]].charge;
+        int k = 0;
+        while (k < nz && zval[k] != z) k++;
+        if (k == nz) {
+            if (nz == CB2_MAX_BREMS_Z) { why = "more than 8 distinct ion charges"; break; }
+            zval[nz++] = z;
+        }
+        b.zidx[s] = k;
+    }
+    if (!why && nz == 0) why = "no charged species";
+    double tlo = 0, thi = 0;
+    if (!why && !scalar_bounds(d.electron_temperature, d.axisym, tlo, thi)) why = "electron temperature field is not bounded away from zero";
+    if (!why) {
+        // the node interpolation must not straddle the discontinuities of the reference's Gaunt factor (classical limit
+        // u >= u_max or gamma2 >= g2_max, Born approximation u < u_min or gamma2 < g2_min; gaunt.pyx:129-134)
+        const double xmin = HC_EV_NM / lmax, xmax = HC_EV_NM / lmin;
+        int zmin = zval[0], zmax = zval[0];
+        for (int k = 1; k < nz; k++) { zmin = std::min(zmin, zval[k]); zmax = std::max(zmax, zval[k]); }
+        const double ry = 13.605693122994;
+        double safe_hi = fmin(xmin / g.u[0], zmin * (double)zmin * ry / g.gamma2[0]);
+        double safe_lo = fmax(xmax / g.u[g.n_u - 1], zmax * (double)zmax * ry / g.gamma2[g.n_gamma2 - 1]);
+        tlo *= 0.98; thi *= 1.02;                               // fp32 evaluation of the profiles on the device
+        if (!(thi < 0.98 * safe_hi) || !(tlo > 1.02 * safe_lo)) why = "temperature range reaches a Gaunt-factor limit switch";
+        else if (tlo < 0.02) why = "electron temperature below 0.02 eV";
+    }
+    // node spacing: ds in s resolves the Gaunt factor's dependence on ln(T) (error ~1e-5 at 0.06, tools/proto_brems_moments.py);
+    // in the cold, linear-in-tau part the spacing ds*tau_c must resolve exp(-(x - x_ref) tau): ((x - x_ref) ds tau_c)^4/24 <= 1e-5
+    double ds = 0.06;
+    if (const char* e = getenv("CB2_BREMS_DS")) { const double v = atof(e); if (v > 1e-3 && v < 1.0) ds = v; }
+    const double dx_max = 0.5 * (HC_EV_NM / lmin - HC_EV_NM / lmax);
+    const double tau_c = fmin(4.0, 0.125 / (ds * fmax(dx_max, 1e-6)));
+    int M = 0;
+    double s0 = 0;
+    if (!why) {
+        const double sa = node_map(1.0 / thi, tau_c), sb = node_map(1.0 / tlo, tau_c);
+        M = (int)ceil((sb - sa) / ds) + 4;                      // stencil i-1..i+2 with 1 <= i <= M-3
+        s0 = sa - ds;
+        if ((long)M * nz > 6144) why = "temperature range needs too many nodes";
+    }
+    if (why) {
+        if (force_moments) return cb2_fail(CB2_ERR_VALUE, "Bremsstrahlung moment formulation not applicable: %s", why);
+        return CB2_OK;
+    }
+    HostGaunt hg;
+    hg.nu = g.n_u; hg.ng = g.n_gamma2;
+    hg.lu.resize(g.n_u); hg.lg.resize(g.n_gamma2);
+    for (int i = 0; i < g.n_u; i++) hg.lu[i] = log10(g.u[i]);
+    for (int i = 0; i < g.n_gamma2; i++) hg.lg[i] = log10(g.gamma2[i]);
+    hg.u_min = g.u[0]; hg.u_max = g.u[g.n_u - 1]; hg.g_min = g.gamma2[0]; hg.g_max = g.gamma2[g.n_gamma2 - 1];
+    build_coef2d(hg.lu.data(), hg.lg.data(), g.gaunt, g.n_u, g.n_gamma2, hg.coef);
+
+    const int bins = S.bins;
+    const int n_pad = (bins + 127) / 128 * 128, k_pad = (nz * M + 15) / 16 * 16;
+    const double x_ref = 0.5 * (HC_EV_NM / lmin + HC_EV_NM / lmax);
+    static const double gx[5] = {-0.9061798459386640, -0.5384693101056831, 0.0, 0.5384693101056831, 0.9061798459386640};
+    static const double gw[5] = {0.2369268850561891, 0.4786286704993665, 0.5688888888888889, 0.4786286704993665, 0.2369268850561891};
+    std::vector<float> phi((size_t)k_pad * n_pad, 0.f);
+    std::vector<double> lam((size_t)bins * 5), geom((size_t)bins * 5);
+    for (int j = 0; j < bins; j++)
+        for (int q = 0; q < 5; q++) {
+            const double l = lmin + delta * (j + 0.5 + 0.5 * gx[q]);
+            lam[(size_t)j * 5 + q] = l;
+            geom[(size_t)j * 5 + q] = 0.5 * gw[q] / (l * l);
+        }
+    for (int m = 0; m < M; m++) {
+        const double tau = node_map_inverse(s0 + m * ds, tau_c), te = 1.0 / tau;
+        for (int k = 0; k < nz; k++) {
+            float* row = &phi[(size_t)(k * M + m) * n_pad];
+            const double z = zval[k], z2 = z * z;
+            for (int j = 0; j < bins; j++) {
+                double v = 0.0;
+                for (int q = 0; q < 5; q++) {
+                    const double l = lam[(size_t)j * 5 + q];
+                    v += geom[(size_t)j * 5 + q] * hg.eval(z, te, l) * exp(-(HC_EV_NM / l - x_ref) * tau);
+                }
+                row[j] = (float)(v * z2);
+            }
+        }
+    }
+    b.phi = A.upload(phi);
+    b.mode = 3;
+    b.n_z = nz;
+    b.n_nodes = M;
+    b.k_pad = k_pad;
+    b.n_pad = n_pad;
+    b.s0 = (float)s0;
+    b.inv_ds = (float)(1.0 / ds);
+    b.inv_tau_c = (float)(1.0 / tau_c);
+    b.x_ref = (float)x_ref;
+    b.te_lo = (float)(1.0 / node_map_inverse(s0 + (M - 2) * ds, tau_c));
+    b.te_hi = (float)(1.0 / node_map_inverse(s0 + 1 * ds, tau_c));
+    return A.rc;
+}
+
 static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
     DevBrems& b = S.brems;
     memset(&b, 0, sizeof b);
@@ -559,8 +756,11 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
     double gx[4], gw[4];
     gl_nodes(nq, gx, gw);
     const double lref = log10(0.5 * (lmin + lmax));
-    std::vector<float4> tab((size_t)S.bins_padded * nq);
-    for (int i = 0; i < S.bins_padded; i++)
+    // the tables are padded to the largest CTA tile (8 warps x 32 lanes x 16 bins) so that they do not depend on the
+    // launch configuration, which is chosen after the Bremsstrahlung mode is known
+    const int tab_bins = std::max(4096, (S.bins + 4095) / 4096 * 4096);
+    std::vector<float4> tab((size_t)tab_bins * nq);
+    for (int i = 0; i < tab_bins; i++)
         for (int q = 0; q < nq; q++) {
             const double lam = lmin + delta * (i + 0.5 + 0.5 * gx[q]);
             const double rho = 1.0 / lam;
@@ -568,8 +768,8 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
         }
     b.bin_tab = A.upload(tab);
     {
-        std::vector<float4> tab1((size_t)S.bins_padded);
-        for (int i = 0; i < S.bins_padded; i++) {
+        std::vector<float4> tab1((size_t)tab_bins);
+        for (int i = 0; i < tab_bins; i++) {
             const double lam = lmin + delta * (i + 0.5), rho = 1.0 / lam;
             tab1[i] = make_float4((float)rho, (float)(2.0 * log2(rho)), (float)(log10(lam) - lref), 1.0f);
         }
@@ -600,7 +800,8 @@ static int convert_brems(Arena& A, const cb2_scene_desc& d, DevScene& S) {
     b.n_charged = 0;
     for (int i = 0; i < d.n_species; i++)
         if (d.species[i].charge > 0) b.charged[b.n_charged++] = i;
-    return A.rc;
+    if (A.rc != CB2_OK) return A.rc;
+    return build_brems_moments(A, d, S);
 }
 
 // Universal cumulative profile of the modified Lorentzian of StarkBroadenedLine (stark.pyx:52-81) in u = (x - x0)/FWHM:
@@ -719,8 +920,8 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         bool has_brems = false;
         for (int m = 0; m < d->n_models; m++) has_brems |= d->models[m].kind == CB2_MODEL_BREMSSTRAHLUNG;
         S.brems.present = has_brems;
-        if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp for the shared-memory budget)
-        if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;
+        if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;  // decides the Bremsstrahlung mode (direct / moments)
+        if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)
         bool any_stark = false;
         for (int m = 0; m < d->n_models; m++)
             any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].shape.kind == CB2_SHAPE_STARK;
@@ -761,6 +962,7 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     for (int i = 0; i < sc->n_allocs; i++) cudaFree(sc->allocs[i]);
     free(sc->allocs);
     free_stage(sc->stage, sc->stage_bytes);
+    if (sc->mom) cudaFree(sc->mom);
     free(sc);
     return CB2_OK;
 }
@@ -851,6 +1053,21 @@ extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* ou
     if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
     CB2_CUDA(cudaStreamSynchronize(st));
     return CB2_OK;
+}
+
+extern "C" int64_t cb2_scene_info(const cb2_scene* sc, int key) {
+    if (!sc) return -1;
+    const DevBrems& b = sc->host.brems;
+    switch (key) {
+    case 0: return sc->nw;
+    case 1: return sc->bpl;
+    case 2: return !b.present ? 0 : (b.mode == 3 ? 3 : 1);
+    case 3: return b.present && b.mode == 3 ? b.k_pad : 0;
+    case 4: return b.present && b.mode == 3 ? b.n_nodes : 0;
+    case 5: return b.present && b.mode == 3 ? b.n_z : 0;
+    case 6: return b.present && b.mode == 3 ? cb2_moment_batch(b.k_pad) : 0;
+    }
+    return -1;
 }
 
 extern "C" int cb2_state_width(const cb2_scene* sc) { return sc ? 2 + 5 * sc->host.n_species + 3 : 0; }

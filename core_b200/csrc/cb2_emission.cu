@@ -28,6 +28,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "cb2_internal.h"
 
 #define FULL 0xffffffffu
@@ -403,7 +405,7 @@ struct SampleIn {
 };
 
 // All line models at one sample (PlasmaMaterial.emission_function loop, material.pyx:59-61).
-__device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, RecWriter& W, unsigned& ood) {
+static __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, RecWriter& W, unsigned& ood) {
     const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
     float lne = 0.f, lte = 0.f;
     if (live) {
@@ -605,7 +607,7 @@ __device__ void sample_lines(const DevScene& S, const SampleIn& in, const AxCtx&
 // record: r0 = (a2, n_pieces (+8 if the one-point rule is not accurate enough for this sample), bc1, bc2) where piece 0
 //         (lowest u, longest wavelengths) covers bins [bc1, bins), piece 1 [bc2, bc1), piece 2 [0, bc2),
 //         r1..r3 = piece coefficients (c0..c3).
-__device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
+static __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float4* brec, int nt, int tid,
                              unsigned long long& brems_evals, unsigned& ood) {
     const DevBrems& B = S.brems;
     float4 r0 = make_float4(0.f, 0.f, __int_as_float(-1), __int_as_float(-1));
@@ -681,6 +683,76 @@ __device__ void sample_brems(const DevScene& S, const SampleIn& in, const AxCtx&
     brec[nt + tid] = pc0;
     brec[2 * nt + tid] = pc1;
     brec[3 * nt + tid] = pc2;
+}
+
+
+// Bremsstrahlung, moment formulation (DevBrems mode 3): instead of evaluating the continuum at every (sample, bin) the
+// sample adds W_s N_{z,s} L_m(Te_s) to the ray's moments on the temperature-node grid (4 nodes per distinct charge z);
+// the spectrum follows from one dense contraction mom . phi after the ray is finished (cb2_contract.cu).
+// Lanes = samples.  Consecutive samples mostly share the node interval, so the warp loops over the distinct intervals it
+// holds and transpose-reduces the 4 n_z (<= 32) values of each; lane 4 z + k then owns node (i - 1 + k) of charge z.
+__device__ __forceinline__ void sample_brems_moments(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te,
+                                                     double* __restrict__ mom, int lane, unsigned long long& brems_evals, unsigned& ood) {
+    const DevBrems& B = S.brems;
+    const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+    int node = -1;
+    float val[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) val[i] = 0.f;
+    if (live) {
+        float tc = te;
+        if (tc < B.te_lo || tc > B.te_hi) { ood++; tc = fminf(fmaxf(tc, B.te_lo), B.te_hi); }
+        const float tau = 1.0f / tc;
+        const float sv = fmaf(tau, B.inv_tau_c, -logf(tc));                 // ln(tau) + tau/tau_c
+        float f = (sv - B.s0) * B.inv_ds;
+        f = fminf(fmaxf(f, 1.0f), (float)(B.n_nodes - 3) + 0.9999f);
+        node = (int)f;
+        const float t = f - (float)node;
+        // cubic Lagrange weights on the nodes -1, 0, 1, 2
+        const float tm1 = t - 1.0f, tm2 = t - 2.0f, tp1 = t + 1.0f;
+        const float l0 = -t * tm1 * tm2 * (1.0f / 6.0f), l1 = tp1 * tm1 * tm2 * 0.5f, l2 = -tp1 * t * tm2 * 0.5f, l3 = tp1 * t * tm1 * (1.0f / 6.0f);
+        const float W = in.weight * B.pref * ne * rsqrtf(te) * __expf(-B.x_ref * tau);
+        // per distinct charge: N_z = sum of the densities of the species with that charge
+        float nzv[CB2_MAX_BREMS_Z];
+#pragma unroll
+        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] = 0.f;
+        for (int s = 0; s < B.n_charged; s++) {
+            const float ni = eval_scalar(S.species[B.charged[s]].density, ctx, in.x, in.y, in.z);
+            const int zi = B.zidx[s];
+            if (ni > 0.f) {
+#pragma unroll
+                for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] += (z == zi) ? ni : 0.f;
+            }
+        }
+#pragma unroll
+        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
+            const float v = W * nzv[z];
+            val[4 * z] = v * l0; val[4 * z + 1] = v * l1; val[4 * z + 2] = v * l2; val[4 * z + 3] = v * l3;
+        }
+        brems_evals += (unsigned long long)S.bins;
+    }
+    unsigned todo = __ballot_sync(FULL, live);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int nd = __shfl_sync(FULL, node, leader);
+        const bool mine = node == nd;
+        todo &= ~__ballot_sync(FULL, mine);
+        float part[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) part[i] = mine ? val[i] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; i++) {
+                const float send = upper ? part[i] : part[i + o];
+                const float keep = upper ? part[i + o] : part[i];
+                part[i] = keep + __shfl_xor_sync(FULL, send, o);
+            }
+        }
+        const int z = lane >> 2, k = lane & 3;
+        if (z < B.n_z && part[0] != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (double)part[0]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -847,7 +919,7 @@ __device__ __forceinline__ double xform_row(const double* m, double x, double y,
 template <int NW, int BPL, int BREMS>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 768 : 512) / (NW * 32))
 emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict__ out, int out_f64, double scale, int accumulate,
-                unsigned long long* __restrict__ stats) {
+                unsigned long long* __restrict__ stats, float* __restrict__ mom_out) {
     constexpr int NT = NW * 32;
     constexpr int TB = 32 * BPL;
     constexpr int NG = NW;   // groups of 32 samples per chunk
@@ -857,14 +929,18 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
     const int ncomp = S.n_comp;
     // dynamic shared memory: fp64 per-ray accumulators [NT*BPL], records, Bremsstrahlung records, per-group bin ranges
     double* racc = smem_d;
-    float4* rec = reinterpret_cast<float4*>(smem_d + (size_t)NT * BPL);
+    double* mom = smem_d + (size_t)NT * BPL;                            // [k_pad] (BREMS == 3 only)
+    const int k_pad = BREMS == 3 ? S.brems.k_pad : 0;
+    float4* rec = reinterpret_cast<float4*>(mom + k_pad);
     float4* brec = rec + (size_t)2 * ncomp * NT;
-    int* s_rng = reinterpret_cast<int*>(brec + (BREMS ? 4 * NT : 0));   // [2][ncomp][NG][2]
+    int* s_rng = reinterpret_cast<int*>(brec + ((BREMS == 1 || BREMS == 2) ? 4 * NT : 0));   // [2][ncomp][NG][2]
     const int rng_stride = 2 * ncomp * NG;
 
     for (int i = tid; i < 2 * rng_stride; i += NT) s_rng[i] = (i & 1) ? INT_MIN : INT_MAX;
 #pragma unroll
     for (int j = 0; j < BPL; j++) racc[warp * TB + 32 * j + lane] = 0.0;
+    if (BREMS == 3)
+        for (int i = tid; i < k_pad; i += NT) mom[i] = 0.0;
 
     const int64_t ray = blockIdx.x;
     const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
@@ -940,7 +1016,8 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                 sample_lines(S, in, ctx, ne, te, W, ood);
                 n_gauss += W.gauss_evals;
                 n_lorentz += W.lorentz_evals;
-                if (BREMS) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
+                if (BREMS == 1 || BREMS == 2) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
+                if (BREMS == 3) sample_brems_moments(S, in, ctx, ne, te, mom, lane, n_brems, ood);
             }
             __syncthreads();
             // ---------------- BIN phase ----------------
@@ -952,7 +1029,7 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
             for (int c = 0; c < ncomp; c++)
                 line_windows<NW, NG, NT>(rec + (size_t)(2 * c) * NT, rec + (size_t)(2 * c + 1) * NT, rng + 2 * c * NG, nact, c,
                                          S.comps[c].c0_int, S.bins, racc, warp, lane, S.comps[c].type, S.lorentz_tab, S.lorentz_phi_inf);
-            if (BREMS) {
+            if (BREMS == 1 || BREMS == 2) {
                 const float4* btab = S.brems.bin_tab;
                 const float4* btab1 = S.brems.bin_tab1;
                 const int nq = S.brems.nq;
@@ -1046,6 +1123,12 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
         }
     }
 
+    if (BREMS == 3) {
+        // the ray's moment row (fp32) for the contraction kernel; the last __syncthreads of the chunk loop made it final
+        float* row = mom_out + (size_t)ray * k_pad;
+        for (int i = tid; i < k_pad; i += NT) row[i] = (float)mom[i];
+    }
+
     if (stats) {
         // warp-reduce the work counters, one atomic per warp
         unsigned long long oodl = ood;
@@ -1068,11 +1151,78 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
 // ------------------------------------------------------------------------------------------------------------------
 // launch configuration
 // ------------------------------------------------------------------------------------------------------------------
-static size_t emission_smem_bytes(int nw, int bpl, int n_comp, bool brems) {
+static size_t emission_smem_bytes(int nw, int bpl, int n_comp, const DevBrems& b) {
     const size_t nt = (size_t)nw * 32;
-    return nt * bpl * sizeof(double) + ((size_t)2 * n_comp * nt + (brems ? 4 * nt : 0)) * sizeof(float4) + (size_t)2 * 2 * n_comp * nw * sizeof(int);
+    const bool direct = b.present && b.mode != 3;
+    const size_t mom = (b.present && b.mode == 3) ? (size_t)b.k_pad * sizeof(double) : 0;
+    return nt * bpl * sizeof(double) + mom + ((size_t)2 * n_comp * nt + (direct ? 4 * nt : 0)) * sizeof(float4) +
+           (size_t)2 * 2 * n_comp * nw * sizeof(int);
 }
 
+// The (NW, BPL) instances are compiled in CB2_N_GROUPS translation units from this one source (-DCB2_GROUP=g) so that the
+// build parallelises; group 0 also holds the dispatcher and the helper kernels.
+#ifndef CB2_GROUP
+#define CB2_GROUP -1   // single translation unit: everything
+#endif
+#define CB2_IN_GROUP(g) (CB2_GROUP < 0 || CB2_GROUP == (g))
+
+template <int NW, int BPL>
+int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+               unsigned long long* stats, float* mom, cudaStream_t st) {
+    const DevScene& S = sc->host;
+    const int NT = NW * 32;
+    const size_t smem = emission_smem_bytes(NW, BPL, S.n_comp, S.brems);
+    const int mode = !S.brems.present ? 0 : (S.brems.mode == 3 ? 3 : (BPL <= 8 ? 1 : 2));
+    if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
+    dim3 grid((unsigned)rays.n_rays), block(NT);
+#define CB2_LAUNCH(MODE)                                                                                                   \
+    do {                                                                                                                   \
+        auto kern = emission_kernel<NW, BPL, MODE>;                                                                        \
+        if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, block, smem, st>>>(sc->dev, rays, out, out_f64, scale, accumulate, stats, mom);                       \
+    } while (0)
+    if (smem > 200 * 1024) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components for shared memory (%zu bytes)", smem);
+    if (mode == 0) CB2_LAUNCH(0);
+    else if (mode == 1) CB2_LAUNCH(1);
+    else if (mode == 2) CB2_LAUNCH(2);
+    else CB2_LAUNCH(3);
+#undef CB2_LAUNCH
+    return cb2_cuda_check(cudaGetLastError(), "emission_kernel launch");
+}
+
+#define CB2_INSTANCES(X) X(4, 1, 0) X(4, 2, 0) X(4, 4, 0) X(4, 8, 0) X(8, 4, 1) X(8, 8, 1) X(8, 16, 2) X(2, 8, 2) X(1, 16, 3) X(4, 16, 3) X(2, 16, 3)
+#define CB2_SIG(NW, BPL) \
+    int launch_cfg<NW, BPL>(const cb2_scene*, const DevRays&, void*, int, double, int, unsigned long long*, float*, cudaStream_t);
+#if CB2_GROUP >= 0
+#define CB2_DECL(NW, BPL, G) extern template CB2_SIG(NW, BPL)
+CB2_INSTANCES(CB2_DECL)
+#endif
+#define CB2_DEFN(NW, BPL) template CB2_SIG(NW, BPL)
+#define CB2_SKIP(NW, BPL)
+#if CB2_GROUP < 0 || CB2_GROUP == 0
+#define CB2_INST_0 CB2_DEFN
+#else
+#define CB2_INST_0 CB2_SKIP
+#endif
+#if CB2_GROUP < 0 || CB2_GROUP == 1
+#define CB2_INST_1 CB2_DEFN
+#else
+#define CB2_INST_1 CB2_SKIP
+#endif
+#if CB2_GROUP < 0 || CB2_GROUP == 2
+#define CB2_INST_2 CB2_DEFN
+#else
+#define CB2_INST_2 CB2_SKIP
+#endif
+#if CB2_GROUP < 0 || CB2_GROUP == 3
+#define CB2_INST_3 CB2_DEFN
+#else
+#define CB2_INST_3 CB2_SKIP
+#endif
+#define CB2_INST(NW, BPL, G) CB2_INST_##G(NW, BPL)
+CB2_INSTANCES(CB2_INST)
+
+#if CB2_IN_GROUP(0)
 int cb2_emission_config(cb2_scene* sc) {
     // (warps per CTA, bins per lane) instances in order of preference per spectral size; the per-sample records live in
     // shared memory (32 B x components x samples per chunk), so scenes with many components fall back to fewer warps
@@ -1083,12 +1233,12 @@ int cb2_emission_config(cb2_scene* sc) {
     size_t best = (size_t)-1;
     for (auto& c : cand) {
         if (c[0] * 32 * c[1] < bins) continue;
-        const size_t need = emission_smem_bytes(c[0], c[1], sc->host.n_comp, sc->host.brems.present);
+        const size_t need = emission_smem_bytes(c[0], c[1], sc->host.n_comp, sc->host.brems);
         if (need <= budget) { nw = c[0]; bpl = c[1]; break; }          // first (preferred) instance that fits
         if (need < best) { best = need; nw = c[0]; bpl = c[1]; }        // otherwise the leanest one
     }
     if (!nw) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
-    if (emission_smem_bytes(nw, bpl, sc->host.n_comp, sc->host.brems.present) > 200 * 1024)
+    if (emission_smem_bytes(nw, bpl, sc->host.n_comp, sc->host.brems) > 200 * 1024)
         return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components (%d) for %d spectral bins", sc->host.n_comp, bins);
     // tuning override (experiments): CB2_NW x CB2_BPL must cover the bins and be an instantiated pair
     const char *env_nw = getenv("CB2_NW"), *env_bpl = getenv("CB2_BPL");
@@ -1102,44 +1252,47 @@ int cb2_emission_config(cb2_scene* sc) {
     return CB2_OK;
 }
 
-template <int NW, int BPL>
-static int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
-                      unsigned long long* stats, cudaStream_t st) {
-    const DevScene& S = sc->host;
-    const int NT = NW * 32;
-    const size_t smem = emission_smem_bytes(NW, BPL, S.n_comp, S.brems.present);
-    const int mode = !S.brems.present ? 0 : (BPL <= 8 ? 1 : 2);
-    if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
-    dim3 grid((unsigned)rays.n_rays), block(NT);
-#define CB2_LAUNCH(MODE)                                                                                                   \
-    do {                                                                                                                   \
-        auto kern = emission_kernel<NW, BPL, MODE>;                                                                        \
-        if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, block, smem, st>>>(sc->dev, rays, out, out_f64, scale, accumulate, stats);                            \
-    } while (0)
-    if (smem > 200 * 1024) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components for shared memory (%zu bytes)", smem);
-    if (mode == 0) CB2_LAUNCH(0);
-    else if (mode == 1) CB2_LAUNCH(1);
-    else CB2_LAUNCH(2);
-#undef CB2_LAUNCH
-    return cb2_cuda_check(cudaGetLastError(), "emission_kernel launch");
+static int emission_batch(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                          unsigned long long* stats, float* mom, cudaStream_t st);
+
+int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                        unsigned long long* stats, cudaStream_t st) {
+    const DevBrems& B = sc->host.brems;
+    const bool moments = B.present && B.mode == 3;
+    if (!moments) return emission_batch(sc, rays, out, out_f64, scale, accumulate, stats, nullptr, st);
+    // moment matrix [rays][k_pad] fp32: grow-only, owned by the scene handle (one stream per handle); rays are processed in
+    // batches that bound it to ~1.5 GB
+    const int64_t batch = std::min(cb2_moment_batch(B.k_pad), rays.n_rays);
+    const size_t need = (size_t)batch * B.k_pad * sizeof(float);
+    if (need > sc->mom_bytes) {
+        CB2_CUDA(cudaStreamSynchronize(st));
+        if (sc->mom) cudaFree(sc->mom);
+        sc->mom = nullptr;
+        sc->mom_bytes = 0;
+        CB2_CUDA(cudaMalloc((void**)&sc->mom, need));
+        sc->mom_bytes = need;
+    }
+    const size_t esz = out_f64 ? sizeof(double) : sizeof(float);
+    for (int64_t r0 = 0; r0 < rays.n_rays; r0 += batch) {
+        DevRays sub = rays;
+        sub.n_rays = std::min(batch, rays.n_rays - r0);
+        sub.origin = rays.origin + 3 * r0;
+        sub.direction = rays.direction + 3 * r0;
+        sub.seg_offset = rays.seg_offset + r0;      // entries are absolute segment indices
+        void* o = (char*)out + (size_t)r0 * sc->host.bins * esz;
+        int rc = emission_batch(sc, sub, o, out_f64, scale, accumulate, stats, sc->mom, st);
+        if (rc != CB2_OK) return rc;
+        rc = cb2_launch_contract(sc->mom, B.phi, sub.n_rays, B.k_pad, B.n_pad, sc->host.bins, o, out_f64, scale, st);
+        if (rc != CB2_OK) return rc;
+    }
+    return CB2_OK;
 }
 
-int cb2_launch_emission(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
-                        unsigned long long* stats, cudaStream_t st) {
-#define CB2_CASE(NW, BPL) \
-    if (sc->nw == NW && sc->bpl == BPL) return launch_cfg<NW, BPL>(sc, rays, out, out_f64, scale, accumulate, stats, st)
-    CB2_CASE(4, 1);
-    CB2_CASE(4, 2);
-    CB2_CASE(4, 4);
-    CB2_CASE(8, 4);
-    CB2_CASE(8, 8);
-    CB2_CASE(8, 16);
-    CB2_CASE(2, 8);
-    CB2_CASE(1, 16);
-    CB2_CASE(4, 16);
-    CB2_CASE(2, 16);
-    CB2_CASE(4, 8);
+static int emission_batch(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                          unsigned long long* stats, float* mom, cudaStream_t st) {
+#define CB2_CASE(NW, BPL, G) \
+    if (sc->nw == NW && sc->bpl == BPL) return launch_cfg<NW, BPL>(sc, rays, out, out_f64, scale, accumulate, stats, mom, st);
+    CB2_INSTANCES(CB2_CASE)
 #undef CB2_CASE
     return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "no kernel instance for nw=%d bpl=%d", sc->nw, sc->bpl);
 }
@@ -1190,3 +1343,4 @@ int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64
     cudaFree(dtmp);
     return rc;
 }
+#endif  // CB2_IN_GROUP(0)

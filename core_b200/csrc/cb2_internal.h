@@ -134,7 +134,23 @@ struct DevBrems {
     float lu_min, lu_max, lg_min, lg_max;
     int n_charged;
     int charged[CB2_MAX_SPECIES];
+    // ---- moment formulation (mode 3): the per-(sample, bin) work is replaced by per-ray moments on a
+    // temperature-node grid followed by one dense contraction with a per-scene table.
+    //   bin average of eps_s = W_s sum_z N_{z,s} Phi_z(Te_s; bin),  Phi_z(T; j) = Z^2 <g_ff(Z,T,l) l^-2 exp(-(hc/l - x_ref)/T)>_j
+    //   Phi_z(Te_s; j) ~= sum_m L_m(s(Te_s)) Phi_z(T_m; j)   (4-point Lagrange on nodes uniform in s = ln(tau) + tau/tau_c, tau = 1/T)
+    //   mom[z][m] = sum_s W_s N_{z,s} L_m(s_s),  W_s = weight pref ne/sqrt(Te) exp(-x_ref/Te);   spectrum = mom . Phi
+    int mode;                     // 1/2: direct per-(sample, bin) path, 3: moments
+    int n_z;                      // distinct charges (<= CB2_MAX_BREMS_Z)
+    int zidx[CB2_MAX_SPECIES];    // charged[s] -> index into the distinct-charge list
+    int n_nodes;                  // temperature nodes M
+    int k_pad;                    // n_z * M rounded up to a multiple of 16 (row length of the moment matrix)
+    int n_pad;                    // bins rounded up to a multiple of 128 (row length of phi)
+    float s0, inv_ds, inv_tau_c;  // node k sits at s = s0 + k ds
+    float x_ref;                  // reference photon energy (eV) factored out of the table
+    float te_lo, te_hi;           // temperatures covered by the node grid (samples outside are clamped and counted)
+    const float* phi;             // [k_pad][n_pad]
 };
+#define CB2_MAX_BREMS_Z 8
 
 struct DevScene {
     int n_species, n_models, n_comp;
@@ -193,6 +209,9 @@ struct cb2_scene {
     void* stage[8];
     size_t stage_bytes[8];
     unsigned long long* stats_dev;
+    // Bremsstrahlung moment matrix [rays][k_pad] fp32 (grow-only)
+    float* mom;
+    size_t mom_bytes;
 };
 
 struct cb2_rt_scene {
@@ -217,10 +236,19 @@ int cb2_cuda_check(cudaError_t e, const char* what);
     } while (0)
 
 // kernels (cb2_emission.cu / cb2_raytransfer.cu)
-int cb2_launch_emission(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                         unsigned long long* stats_dev, cudaStream_t stream);
 int cb2_emission_config(cb2_scene* sc);
 int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t stream);
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate,
                   int64_t* row_offset, int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t stream);
 int cb2_launch_scan(int64_t* counts_inout, int64_t n, cudaStream_t stream);
+// rays per moment batch: bounds the moment matrix [batch][k_pad] fp32 to ~1.5 GB
+static inline int64_t cb2_moment_batch(int k_pad) {
+    int64_t batch = ((int64_t)3 << 29) / ((int64_t)k_pad * (int64_t)sizeof(float));
+    batch = batch / 128 * 128;
+    return batch < 128 ? 128 : batch;
+}
+// out[ray][bin] += scale * sum_k mom[ray][k] phi[k][bin]   (cb2_contract.cu)
+int cb2_launch_contract(const float* mom, const float* phi, int64_t n_rays, int k_pad, int n_pad, int bins, void* out, int out_f64,
+                        double scale, cudaStream_t stream);

@@ -58,6 +58,13 @@ class EmissionScene:
                                                                    C.c_void_p(stream)))
         return out
 
+    def info(self):
+        """Launch plan of this scene: CTA shape and the Bremsstrahlung formulation in use (cb2_scene_info)."""
+        keys = ("warps_per_cta", "bins_per_lane", "brems_mode", "moment_row", "temperature_nodes", "distinct_charges", "moment_batch_rays")
+        d = {k: int(self._lib.cb2_scene_info(self._h, i)) for i, k in enumerate(keys)}
+        d["brems_mode"] = {0: "none", 1: "direct", 3: "moments"}[d["brems_mode"]]
+        return d
+
     def sample_state(self, points):
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         w = self._lib.cb2_state_width(self._h)

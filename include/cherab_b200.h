@@ -281,6 +281,12 @@ int cb2_emission_render_device(cb2_scene* scene, const cb2_rays* rays, void* out
 int cb2_sample_state(cb2_scene* scene, const double* points, int64_t n, double* out);
 int cb2_state_width(const cb2_scene* scene);
 
+/* Launch-plan introspection (no reference counterpart; used by the benchmark and the parity tests to report which
+ * formulation a scene runs).  key: 0 warps per CTA, 1 bins per lane, 2 Bremsstrahlung formulation (0 none, 1 direct
+ * per-(sample, bin) evaluation, 3 per-ray temperature moments + contraction), 3 moment row length k_pad,
+ * 4 temperature nodes, 5 distinct ion charges, 6 rays per moment batch.  Returns -1 for an unknown key. */
+int64_t cb2_scene_info(const cb2_scene* scene, int key);
+
 /* ------------------------------------------------------------------------------------------------
  * Ray transfer (cherab/tools/raytransfer/emitters.pyx:88-224, raytransfer.py:183-268)
  * ---------------------------------------------------------------------------------------------- */

@@ -27,8 +27,10 @@ def assert_parity(got, ref, rtol=RTOL, floor=FLOOR, what=""):
     return worst
 
 
-def both(flat, rays, **kw):
+def both(flat, rays, expect_brems=None, **kw):
     scene = EmissionScene(flat)
+    if expect_brems is not None:
+        assert scene.info()["brems_mode"] == expect_brems
     got, stats = scene.render(rays, **kw)
     ref, rstats = oracle.emission_render(flat, rays)
     scene.close()
@@ -207,7 +209,18 @@ def test_output_modes(generomak_halpha):
     scene.close()
 
 
-def test_bremsstrahlung_slab():
+@pytest.fixture(params=["moments", "direct"])
+def brems_mode(request, monkeypatch):
+    """Both Bremsstrahlung formulations of the CUDA library: per-ray temperature moments + contraction (default where the
+    scene allows it) and the direct per-(sample, bin) evaluation."""
+    if request.param == "direct":
+        monkeypatch.setenv("CB2_BREMS_MODE", "direct")
+    else:
+        monkeypatch.delenv("CB2_BREMS_MODE", raising=False)
+    return request.param
+
+
+def test_bremsstrahlung_slab(brems_mode):
     # core/tests/test_bremsstrahlung.py:41-95 inputs
     plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=1e19, electron_temperature=2000.,
                                         plasma_species=[(cb.deuterium, 1, 1.e19, 2000., (0, 0, 0)), (cb.nitrogen, 7, 1.e18, 2000., (0, 0, 0))])
@@ -215,24 +228,62 @@ def test_bremsstrahlung_slab():
     plasma.models = [cb.Bremsstrahlung()]
     flat = cb.flatten_scene(plasma, 400., 800., 128)
     rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
-    got, ref, stats, rstats = both(flat, rays)
+    got, ref, stats, rstats = both(flat, rays, expect_brems=brems_mode)
     assert stats["brems_bin_evals"] == rstats["brems_bin_evals"]
     assert_parity(got, ref, what="brems slab")
 
 
+def test_bremsstrahlung_hot_slab_falls_back_to_direct():
+    # 40 keV: the reference's Gaunt factor is the Born approximation over the whole window (u < 1e-4, gaunt.pyx:133); the
+    # switch is a discontinuity the temperature-node interpolation must not straddle, so scenes whose temperature range
+    # reaches it have to choose the direct formulation
+    plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=1e19, electron_temperature=40000.,
+                                        plasma_species=[(cb.deuterium, 1, 1.e19, 40000., (0, 0, 0))])
+    plasma.atomic_data = cb.AtomicData()
+    plasma.models = [cb.Bremsstrahlung()]
+    flat = cb.flatten_scene(plasma, 400., 800., 128)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    got, ref, stats, rstats = both(flat, rays, expect_brems="direct")
+    assert_parity(got, ref, what="hot brems slab")
+    with pytest.raises(ValueError):
+        EmissionScene(cb.flatten_scene(plasma, 400., 800., 128, brems_quadrature=-1))   # forcing moments must refuse
+
+
+def test_bremsstrahlung_moments_f32_and_accumulate():
+    # the contraction kernel's fp32 and accumulate paths, and odd bin counts (scalar epilogue)
+    plasma = generomak.get_plasma()
+    plasma.models = [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.02)
+    rays = generomak_camera_rays(plasma, (12, 12))          # 144 rays: one full 128-row tile and a ragged one
+    for bins in (130, 257):
+        flat = cb.flatten_scene(plasma, 500.0, 600.0, bins)
+        scene = EmissionScene(flat)
+        assert scene.info()["brems_mode"] == "moments"
+        a64, _ = scene.render(rays)
+        a32, _ = scene.render(rays, dtype=np.float32)
+        twice = a64.copy()
+        scene.render(rays, out=twice, scale=0.5, accumulate=True)
+        scene.close()
+        ref, _ = oracle.emission_render(flat, rays)
+        assert_parity(a64, ref, what="moments f64 bins=%d" % bins)
+        assert_parity(a32.astype(np.float64), ref, rtol=2e-4, what="moments f32 bins=%d" % bins)
+        assert_parity(twice, 1.5 * ref, what="moments accumulate bins=%d" % bins)
+
+
 @pytest.mark.parametrize("window", [(390.0, 700.0, 2048), (100.0, 1000.0, 512), (650.0, 660.0, 64)])
-def test_bremsstrahlung_generomak(window):
+def test_bremsstrahlung_generomak(window, brems_mode):
     plasma = generomak.get_plasma()
     plasma.models = [cb.Bremsstrahlung()]
     plasma.integrator = cb.NumericalIntegrator(step=0.02)     # the oracle's adaptive quadrature is slow: coarse step
     flat = cb.flatten_scene(plasma, *window)
     rays = generomak_camera_rays(plasma, (4, 4))
-    got, ref, stats, rstats = both(flat, rays)
+    got, ref, stats, rstats = both(flat, rays, expect_brems=brems_mode)
     assert stats["brems_bin_evals"] == rstats["brems_bin_evals"]
-    assert_parity(got, ref, what="generomak brems %s" % (window,))
+    assert stats["out_of_domain"] == 0
+    assert_parity(got, ref, what="generomak brems %s %s" % (window, brems_mode))
 
 
-def test_generomak_c3_mix():
+def test_generomak_c3_mix(brems_mode):
     # BASELINE config C3 model mix at tiny size: 8 Balmer lines + Bremsstrahlung, 2048 bins on [390, 700] nm
     plasma = generomak.get_plasma()
     lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4, 5, 6)]
@@ -240,8 +291,8 @@ def test_generomak_c3_mix():
     plasma.integrator = cb.NumericalIntegrator(step=0.01)
     flat = cb.flatten_scene(plasma, 390.0, 700.0, 2048)
     rays = generomak_camera_rays(plasma, (3, 3))
-    got, ref, stats, rstats = both(flat, rays)
-    assert_parity(got, ref, what="generomak C3 mix")
+    got, ref, stats, rstats = both(flat, rays, expect_brems=brems_mode)
+    assert_parity(got, ref, what="generomak C3 mix " + brems_mode)
 
 
 def test_stark_broadened_line_slab():
