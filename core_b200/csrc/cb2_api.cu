@@ -115,6 +115,9 @@ static DevTable1D make_knots1d(Arena& A, const double* x, int n) {
     for (int i = 0; i + 1 < n; i++) iw[i] = (float)(1.0 / (x[i + 1] - x[i]));
     t.xmin = (float)x[0];
     t.xmax = (float)x[n - 1];
+    t.uniform = n > 1 && is_uniform(x, n);
+    t.x0 = (float)x[0];
+    t.inv_dx = n > 1 ? (float)((n - 1) / (x[n - 1] - x[0])) : 0.f;
     t.x = A.upload(xs);
     t.inv_w = A.upload(iw);
     return t;
@@ -452,6 +455,7 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     o.sigma_coef = (float)(sqrt(ELEMENTARY_CHARGE / (m.atomic_weight * ATOMIC_MASS)) * m.wavelength / SPEED_OF_LIGHT / S.delta_d);
     for (int k = 0; k < 3; k++) o.param[k] = (float)m.shape.param[k];
     // rate table: log10(PhotonToJ(rate, wavelength)) + 38 on (log10 ne, log10 te)   (pec.pyx:59-68)
+    o.pec_grid = -1;
     if (m.pec.n_ne <= 0) {
         o.pec_const = 1;
         o.pec_value = (m.pec.constant > 0) ? (float)(log10(m.pec.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
@@ -472,6 +476,14 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
             if (!(lte[j + 1] > lte[j])) return cb2_fail(CB2_ERR_VALUE, "rate table te grid must be increasing");
         o.pec = make_table2d(A, lne.data(), lte.data(), lr.data(), nn, nt);
         o.pec_extrapolate = m.pec.extrapolate;
+        // share the cell search between models tabulated on identical knots (ADF15 blocks of one file usually are)
+        const int self = (int)(&m - d.models);
+        o.pec_grid = self;
+        for (int p = 0; p < self; p++) {
+            const cb2_rate2d& q = d.models[p].pec;
+            if (d.models[p].kind == CB2_MODEL_BREMSSTRAHLUNG || q.n_ne != nn || q.n_te != nt) continue;
+            if (!memcmp(q.ne, m.pec.ne, sizeof(double) * nn) && !memcmp(q.te, m.pec.te, sizeof(double) * nt)) { o.pec_grid = S.models[p].pec_grid; break; }
+        }
     }
     // component slots
     o.comp0 = S.n_comp;
@@ -963,6 +975,9 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     free(sc->allocs);
     free_stage(sc->stage, sc->stage_bytes);
     if (sc->mom) cudaFree(sc->mom);
+    if (sc->gbase) cudaFree(sc->gbase);
+    if (sc->gmask) cudaFree(sc->gmask);
+    if (sc->rec) cudaFree(sc->rec);
     free(sc);
     return CB2_OK;
 }
@@ -1065,7 +1080,8 @@ extern "C" int64_t cb2_scene_info(const cb2_scene* sc, int key) {
     case 3: return b.present && b.mode == 3 ? b.k_pad : 0;
     case 4: return b.present && b.mode == 3 ? b.n_nodes : 0;
     case 5: return b.present && b.mode == 3 ? b.n_z : 0;
-    case 6: return b.present && b.mode == 3 ? cb2_moment_batch(b.k_pad) : 0;
+    case 6: return sc->warp_kernel ? cb2_warp_batch_rays(sc) : 0;
+    case 7: return sc->warp_kernel;
     }
     return -1;
 }

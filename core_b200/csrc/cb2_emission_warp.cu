@@ -1,0 +1,738 @@
+// cb2_emission_warp.cu — K1: the line-emission hot path on sm_100a as two kernels per ray batch.
+//
+//   state_kernel  (K1a, latency-bound: table gathers)   one CTA per ray, warps take the ray's 32-sample groups round-robin,
+//                 a thread owns one sample: position (fp64, reference operation order) -> (R, Z) -> psi_n / LCFS mask /
+//                 blend weight / mesh triangle ONCE per sample (the reference re-walks the function tree for every
+//                 quantity) -> species profiles -> PEC bicubics (cell search shared between models on the
+//                 same knots) -> per line component (centre, width, amplitude) written as coalesced 128-byte rows;
+//                 Bremsstrahlung goes to the ray's temperature-node moments (cb2_device.cuh; contraction cb2_contract.cu).
+//                 The flattened scene travels as a __grid_constant__ kernel parameter (constant bank, no dependent loads).
+//   bin_kernel    (K1b, FP32/SFU-bound)                 one CTA per ray, warps take the groups round-robin, lanes = samples:
+//                 the union of the group's bin ranges is cut into 32-bin windows; lane l evaluates ITS sample at the
+//                 window's bins in the lane-permuted order bin = r XOR l for register r, so that the 31-shuffle
+//                 butterfly part[i] += shfl_xor(part[i + o], o) needs no selects and leaves window bin l on lane l, which
+//                 adds it to the warp's private per-ray accumulator in shared memory (plain load/add/store, no atomics);
+//                 tails use 16/8-bin windows, sub-bin lines a rolled 4-bin loop with the reference's lower = upper
+//                 recurrence.  One barrier at the end, fp64 sum of the private accumulators, coalesced rows out.
+//
+// Why two kernels: fused, the hot instruction footprint (~100 KB) thrashes the 32 KB L1.5 instruction cache and the
+// kernel is fetch-bound (ncu: no_instruction 4.1 stall cycles per issue, profiles/r1b_*); split, each half fits, the
+// state half gets the whole L1 for table data and the bin half a small register footprint.  The records cost 384 B per
+// live (group, component) through L2/HBM.
+//
+// Gaussian bin integrals (gaussian.pyx:40-90) in fp32 with RELATIVE accuracy (tools/proto_gauss_fp32.py):
+//   sigma >= 0.98 bin: kb/sqrt(pi) e^{-m} sum_{n<=4} H_2n h^2n/(2n+1)! as exp2(-m') (s0 + m'(s1 + m'(s2 + m'(s3 + m' s4)))),
+//                      one MUFU.EX2 + 7 FMA-pipe instructions per bin, no cancellation;
+//   sub-bin lines:     differences of 1/2 erfc(|x|) along the bin edges.
+// Bins beyond 7 sigma are not evaluated: e^{-24.5} = 2e-11 of the sample's peak, two decades under the acceptance floor
+// (1e-9 of the ray's largest bin); the reference's own cut-off is 10 sigma and the work counter E still uses it.
+// Follows: cherab/core/plasma/material.pyx:48-63, model/plasma/impact_excitation.pyx:78-100, recombination.pyx:78-100,
+// model/lineshape/gaussian.pyx:40-139, doppler.pyx:29-59, multiplet.pyx:93-117, zeeman.pyx:113-365, stark.pyx:88-348,
+// tools/equilibrium/efit.pyx:219-546, generomak/plasma/plasma.py:580-638, Raysect's NumericalIntegrator.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "cb2_device.cuh"
+
+#define EVAL_CUTOFF_SIGMA 7.0f
+
+// per-sample state shared by the line models of one sample
+struct LineCache {
+    float lne, lte;
+    int cur;                 // species whose (ni, ts, vd) are cached
+    float ni, ts, vd;
+    bool have_b;
+    float bm, cos_sqr;
+    int grid;                // PEC knot set whose cell is cached
+    Cell2 cell;
+};
+
+// per-(sample, model) quantities every component of the model's line shape needs
+struct ModelCtx {
+    bool on;                 // the model emits at this sample and its shape has something to add
+    float amp;               // radiance * trapezium weight / delta_wavelength
+    float sigma_b;           // Gaussian sigma in bins
+    float lam_b, eta;        // Stark: pseudo-Voigt FWHM in bins, Lorentzian fraction
+    float dop;               // v.d / c
+    float shift0;            // Doppler shift of the rest wavelength in bins
+    bool bzero;              // |B| == 0: no splitting
+    float a_pi, a_sigma;     // polarisation-weighted amplitudes
+    float dl_plus, dl_minus; // sigma+- wavelength offsets (triplets, Stark)
+    int ib; float tb;        // ZeemanStructure |B| interval
+    float rnorm[3];          // ZeemanStructure ratio normalisation per polarisation group
+};
+
+__device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, const AxCtx& ctx, LineCache& lc) {
+    if (lc.have_b) return;
+    const float3 bf = eval_b_field(S, ctx);
+    lc.bm = sqrtf(bf.x * bf.x + bf.y * bf.y + bf.z * bf.z);
+    const float c = lc.bm > 0.f ? (bf.x * in.dx + bf.y * in.dy + bf.z * in.dz) / lc.bm : 0.f;
+    lc.cos_sqr = c * c;
+    lc.have_b = true;
+}
+
+// ExcitationLine / RecombinationLine .emission up to the add_line call (impact_excitation.pyx:86-100) plus the
+// component-independent part of LineShapeModel.add_line
+__device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M, const SampleIn& in, const AxCtx& ctx, float ne, float te,
+                                            bool live, LineCache& lc, ModelCtx& mc, unsigned& ood) {
+    mc.on = false;
+    bool on = live;
+    if (on && M.species != lc.cur) {
+        lc.cur = M.species;
+        const DevSpecies& sp = S.species[lc.cur];
+        lc.ni = eval_scalar(sp.density, ctx, in.x, in.y, in.z);
+        lc.ts = eval_scalar(sp.temperature, ctx, in.x, in.y, in.z);
+        const float3 v = eval_vector(sp.velocity, ctx);
+        lc.vd = v.x * in.dx + v.y * in.dy + v.z * in.dz;   // velocity projected on the (unit) ray direction
+    }
+    on = on && lc.ni > 0.f;
+    if (!on) return;
+    // radiance = 1/(4 pi) PEC ne ni (impact_excitation.pyx:99): exp10 of (log PEC + 38) times (ne ni 1e-38)
+    float lp;
+    if (M.pec_const) lp = M.pec_value;
+    else {
+        if (M.pec_grid != lc.grid) { lc.cell = locate2d(M.pec, lc.lne, lc.lte); lc.grid = M.pec_grid; }
+        if (!lc.cell.inside && !M.pec_extrapolate) ood++;
+        lp = eval2d(M.pec, lc.cell);
+    }
+    const float radiance = RECIP_4_PI * exp10f(lp) * ne * lc.ni;
+    mc.amp = radiance * in.weight * M.inv_delta;
+    if (!(mc.amp > 0.f)) return;
+    mc.dop = lc.vd * M.inv_c;                                  // doppler_shift: lambda (1 + v.d/c), doppler.pyx:29-44
+    mc.shift0 = M.wavelength * mc.dop * M.inv_delta;
+    const float ts = lc.ts;
+    if (M.shape == CB2_SHAPE_STARK) {
+        // StarkBroadenedLine.add_line (stark.pyx:251-348): does NOT return early on ts <= 0
+        const float SIGMA2FWHM = 2.3548200450309493f;
+        const float fl = M.param[0] * powf(ne, M.param[1]) / powf(te, M.param[2]);          // nm (ne in 1e19 m^-3 folded in)
+        const float fg = ts > 0.f ? SIGMA2FWHM * M.sigma_coef * sqrtf(ts) / M.inv_delta : 0.f; // nm
+        if (fl == 0.f && fg == 0.f) return;
+        float full;
+        if (fg <= fl) {
+            const float r = fg / fl;
+            full = fl * (1.f + r * r * (0.57575f + r * (0.37902f + r * (-0.42519f + r * (-0.31525f + r * 0.31718f)))));
+        } else {
+            const float r = fl / fg;
+            full = fg * (1.f + r * (0.15882f + r * (1.04388f + r * (-1.38281f + r * (0.46251f + r * (0.82325f + r * -0.58026f))))));
+        }
+        float sigma = full / SIGMA2FWHM, eta;
+        const float l2t = fl / full;
+        if (l2t < 0.01f) { eta = 0.f; full = 0.f; }
+        else if (l2t > 0.999f) { eta = 1.f; sigma = 0.f; }
+        else {
+            const float lg = logf(l2t);
+            eta = expf(5.14820e-04f + lg * (1.38821e+00f + lg * (-9.60424e-02f + lg * (-3.83995e-02f + lg * (-7.40042e-03f + lg * -5.47626e-04f)))));
+        }
+        mc.sigma_b = sigma * M.inv_delta;
+        mc.lam_b = full * M.inv_delta;
+        mc.eta = eta;
+    } else {
+        // all Gaussian-family shapes return before touching the spectrum if ts <= 0 (gaussian.pyx:127-129)
+        if (!(ts > 0.f)) return;
+        mc.sigma_b = M.sigma_coef * sqrtf(ts);                 // thermal_broadening, doppler.pyx:48-59, in bins
+        if (M.shape == CB2_SHAPE_GAUSSIAN || M.shape == CB2_SHAPE_MULTIPLET) { mc.on = true; return; }
+    }
+    // Zeeman family and Stark: field strength and angle to the line of sight (zeeman.pyx:125-131)
+    need_b(S, in, ctx, lc);
+    mc.bzero = lc.bm == 0.f;
+    const float cos_sqr = lc.cos_sqr, sin_sqr = 1.0f - cos_sqr;
+    mc.a_pi = 0.5f * sin_sqr * mc.amp;
+    mc.a_sigma = (0.25f * sin_sqr + 0.5f * cos_sqr) * mc.amp;
+    if (M.shape == CB2_SHAPE_PARAM_ZEEMAN) {
+        mc.sigma_b *= sqrtf(1.0f + M.param[1] * M.param[1] * powf(ts, 2.0f * M.param[2]));
+        mc.dl_plus = 0.5f * M.param[0] * lc.bm;                // zeeman.pyx:260-264
+        mc.dl_minus = -mc.dl_plus;
+    } else if (M.shape == CB2_SHAPE_ZEEMAN_TRIPLET || M.shape == CB2_SHAPE_STARK) {
+        // hc/(hc/l0 -+ muB B) - l0 = +- l0 e/(1 -+ e), e = muB B l0 / hc   (zeeman.pyx:152-158)
+        const float e = BOHR_MAGNETON * lc.bm * M.wavelength * (1.0f / HC_EV_NM_F);
+        mc.dl_plus = M.wavelength * e / (1.0f - e);
+        mc.dl_minus = -M.wavelength * e / (1.0f + e);
+    } else if (M.shape == CB2_SHAPE_ZEEMAN_MULTIPLET && !mc.bzero) {  // zeeman.pyx:340-363, atomic/zeeman.pyx:87-129
+        float fb = (lc.bm - M.b0) * M.inv_db;
+        fb = fminf(fmaxf(fb, 0.f), (float)(M.n_b - 1));
+        mc.ib = min((int)fb, M.n_b - 2);
+        mc.tb = fb - (float)mc.ib;
+        const int offs[4] = {0, M.n_pi, M.n_pi + M.n_sp, M.n_pi + M.n_sp + M.n_sm};
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+            float rsum = 0.f;
+            for (int k = offs[g]; k < offs[g + 1]; k++) {
+                const float* r = M.zee_ratio + (size_t)k * M.n_b + mc.ib;
+                rsum += fmaf(mc.tb, __ldg(r + 1) - __ldg(r), __ldg(r));
+            }
+            mc.rnorm[g] = rsum > 0.f ? 1.0f / rsum : 1.0f;
+        }
+    }
+    mc.on = true;
+}
+
+// component k of model M at this sample: type (0 Gaussian, 1 modified Lorentzian), centre cf in bins relative to the
+// component slot's integer origin, width (sigma or FWHM) in bins, amplitude; amp == 0 means "nothing to add"
+__device__ __forceinline__ void model_component(const DevScene& S, const DevModel& M, int k, const ModelCtx& mc, int& type, float& cf,
+                                                float& width, float& amp) {
+    const DevComp& cs = S.comps[M.comp0 + k];
+    type = cs.type;
+    cf = cs.c0_frac + mc.shift0;
+    width = mc.sigma_b;
+    amp = 0.f;
+    if (!mc.on) return;
+    const bool pol_pi = M.polarisation != CB2_POL_SIGMA, pol_sigma = M.polarisation != CB2_POL_PI;
+    switch (M.shape) {
+    case CB2_SHAPE_GAUSSIAN: amp = mc.amp; return;
+    case CB2_SHAPE_MULTIPLET:                                   // multiplet.pyx:108-115
+        cf = cs.c0_frac + __ldg(M.mult_lambda + k) * mc.dop * M.inv_delta;
+        amp = mc.amp * __ldg(M.mult_ratio + k);
+        return;
+    case CB2_SHAPE_ZEEMAN_MULTIPLET:
+        if (!mc.bzero) {
+            const int g = k < M.n_pi ? 0 : (k < M.n_pi + M.n_sp ? 1 : 2);
+            if (!(g == 0 ? pol_pi : pol_sigma)) return;
+            const float* r = M.zee_ratio + (size_t)k * M.n_b + mc.ib;
+            const float* l = M.zee_dlambda + (size_t)k * M.n_b + mc.ib;
+            const float ratio = fmaf(mc.tb, __ldg(r + 1) - __ldg(r), __ldg(r)) * mc.rnorm[g];
+            const float dl = fmaf(mc.tb, __ldg(l + 1) - __ldg(l), __ldg(l));
+            cf = cs.c0_frac + (dl + (M.wavelength + dl) * mc.dop) * M.inv_delta;
+            amp = (g == 0 ? mc.a_pi : mc.a_sigma) * ratio;
+            return;
+        }
+        // no splitting: single Gaussian, halved if a polarisation filter is set (zeeman.pyx:132-136)
+        if (k == 0) amp = M.polarisation == CB2_POL_NO ? mc.amp : 0.5f * mc.amp;
+        return;
+    case CB2_SHAPE_ZEEMAN_TRIPLET:
+    case CB2_SHAPE_PARAM_ZEEMAN:
+    case CB2_SHAPE_STARK: {
+        const int kk = (M.shape == CB2_SHAPE_STARK && k >= 3) ? k - 3 : k;   // 0 pi, 1 sigma+, 2 sigma-
+        float a;
+        if (mc.bzero) {
+            if (kk != 0) return;
+            a = M.polarisation == CB2_POL_NO ? mc.amp : 0.5f * mc.amp;
+        } else if (kk == 0) {
+            if (!pol_pi) return;
+            a = mc.a_pi;
+        } else {
+            if (!pol_sigma) return;
+            a = mc.a_sigma;
+            const float dl = kk == 1 ? mc.dl_plus : mc.dl_minus;
+            cf = cs.c0_frac + (dl + (M.wavelength + dl) * mc.dop) * M.inv_delta;
+        }
+        if (M.shape == CB2_SHAPE_STARK) {
+            // pseudo-Voigt: (1 - eta) Gaussian + eta modified Lorentzian per Zeeman component (stark.pyx:305-346)
+            if (k >= 3) { a *= mc.eta; width = mc.lam_b; }
+            else a *= 1.0f - mc.eta;
+        }
+        amp = a;
+        return;
+    }
+    }
+}
+
+static __device__ __noinline__ double lorentz_cdf_call(const double2* __restrict__ tab, double phi_inf, double u) {
+    return lorentz_cdf(tab, phi_inf, u);
+}
+
+// what a lane knows about its sample's line component while the windows are evaluated
+struct LineRec {
+    float kx, xoff;          // series: x'(rel) = rel kx + xoff at the bin CENTRE; erfc: x at the bin's UPPER edge; Lorentzian: u at edge rel
+    float s0, s1, s2, s3, s4;// series coefficients, or s0 = amplitude
+    int lo, hi;              // evaluated bins [lo, hi), relative to the slot origin
+    int kind;                // 0 nothing, 1 series, 2 erfc differences, 3 modified Lorentzian
+};
+
+// 32-bin window, series lanes, lane-permuted bin order (register r of lane l holds bin r ^ l) so that the butterfly needs
+// no selects; lane l ends up with window bin l.
+template <typename AccT>
+__device__ __forceinline__ void window_series_xor(const LineRec& R, int wbase, int c0_int, int bins, AccT* __restrict__ wacc, int lane) {
+    const bool mine = R.kind == 1 && R.hi > wbase && R.lo < wbase + 32;
+    const float c0 = mine ? R.s0 : 0.f, c1 = mine ? R.s1 : 0.f, c2 = mine ? R.s2 : 0.f, c3 = mine ? R.s3 : 0.f, c4 = mine ? R.s4 : 0.f;
+    // per-lane steps of the XOR-ordered walk: r ^ l = l + sum_{b in r} (+-)2^b
+    float db[5];
+#pragma unroll
+    for (int b = 0; b < 5; b++) db[b] = ((lane >> b) & 1) ? -(float)(1 << b) * R.kx : (float)(1 << b) * R.kx;
+    const float xb = fmaf((float)(wbase + lane), R.kx, R.xoff);
+    float part[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        float x = xb;
+#pragma unroll
+        for (int b = 0; b < 5; b++)
+            if (r & (1 << b)) x += db[b];
+        const float m2 = x * x;
+        part[r] = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(c4, m2, c3), m2, c2), m2, c1), m2, c0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < o; i++) part[i] += __shfl_xor_sync(FULL, part[i + o], o);
+    const int bin = c0_int + wbase + lane;
+    if (bin >= 0 && bin < bins && part[0] != 0.f) wacc[bin] += (AccT)part[0];
+}
+
+// transpose-reduce WB registers over the warp: inside each group of WB lanes a lane keeps, after the step with offset o,
+// the half selected by (lane & o); the 32 / WB groups are then folded, so lane l < WB holds window bin l
+template <int WB>
+__device__ __forceinline__ float reduce_window(float (&part)[WB], int lane) {
+#pragma unroll
+    for (int o = WB / 2; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float send = upper ? part[i] : part[i + o];
+            const float keep = upper ? part[i + o] : part[i];
+            part[i] = keep + __shfl_xor_sync(FULL, send, o);
+        }
+    }
+#pragma unroll
+    for (int o = WB; o < 32; o <<= 1) part[0] += __shfl_xor_sync(FULL, part[0], o);
+    return part[0];
+}
+
+// WB-bin tail window for series lanes in natural bin order
+template <int WB, typename AccT>
+__device__ __forceinline__ void window_series_tail(const LineRec& R, int wbase, int c0_int, int bins, AccT* __restrict__ wacc, int lane) {
+    const bool mine = R.kind == 1 && R.hi > wbase && R.lo < wbase + WB;
+    const float c0 = mine ? R.s0 : 0.f, c1 = mine ? R.s1 : 0.f, c2 = mine ? R.s2 : 0.f, c3 = mine ? R.s3 : 0.f, c4 = mine ? R.s4 : 0.f;
+    const float x0 = fmaf((float)wbase, R.kx, R.xoff);
+    float part[WB];
+#pragma unroll
+    for (int w = 0; w < WB; w++) {
+        const float x = fmaf((float)w, R.kx, x0);
+        const float m2 = x * x;
+        part[w] = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(c4, m2, c3), m2, c2), m2, c1), m2, c0);
+    }
+    const float v = reduce_window<WB>(part, lane);
+    const int bin = c0_int + wbase + lane;
+    if (lane < WB && bin >= 0 && bin < bins && v != 0.f) wacc[bin] += (AccT)v;
+}
+
+// erfc-difference (sub-bin Gaussian) and modified-Lorentzian lanes: rolled loop over 4-bin steps with the reference's
+// lower = upper recurrence along the bin edges (gaussian.pyx:78-88, stark.pyx:139-146).  Small code, any range length.
+template <typename AccT, int LOR>
+__device__ __forceinline__ void edges_pass(const LineRec& R, int c0_int, int bins, AccT* __restrict__ wacc, int lane,
+                                           const double2* __restrict__ ltab, double phi_inf) {
+    const bool is_e = R.kind == 2, is_l = LOR && R.kind == 3;
+    const int lo = (is_e || is_l) ? R.lo : INT_MAX, hi = (is_e || is_l) ? R.hi : INT_MIN;
+    const int Elo = __reduce_min_sync(FULL, lo), Ehi = __reduce_max_sync(FULL, hi);
+    if (Ehi <= Elo) return;
+    const float amp = (is_e || is_l) ? R.s0 : 0.f;
+    // value of the cumulative profile at the lower edge of bin Elo
+    float xl = fmaf((float)(Elo - 1), R.kx, R.xoff), tl = is_e ? half_erfc(fabsf(xl)) : 0.f;
+    double pl = 0.0;
+    const double inv_l = (double)R.kx, off = (double)R.xoff;
+    bool have_pl = false;
+    for (int wbase = Elo; wbase < Ehi; wbase += 4) {
+        float part[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const int rel = wbase + w;
+            float v = 0.f;
+            if (is_e) {
+                const float xu = fmaf((float)rel, R.kx, R.xoff);                  // x at the upper edge of bin rel
+                const float tu = half_erfc(fabsf(xu));
+                const float dd = (xl >= 0.f) ? (tl - tu) : ((xu <= 0.f) ? (tu - tl) : (1.0f - tl - tu));
+                if (rel >= lo && rel < hi) v = amp * dd;
+                xl = xu; tl = tu;
+            }
+            if (LOR && is_l && rel >= lo && rel < hi) {
+                if (!have_pl) { pl = lorentz_cdf_call(ltab, phi_inf, (double)rel * inv_l + off); have_pl = true; }
+                const double pu = lorentz_cdf_call(ltab, phi_inf, (double)(rel + 1) * inv_l + off);
+                v = amp * (float)(pu - pl);
+                pl = pu;
+            }
+            part[w] = v;
+        }
+        const float v = reduce_window<4>(part, lane);
+        const int bin = c0_int + wbase + lane;
+        if (lane < 4 && bin >= 0 && bin < bins && v != 0.f) wacc[bin] += (AccT)v;
+    }
+}
+
+// One line component of one 32-sample group (lanes = samples): bin integrals into the warp's private accumulator.
+template <typename AccT, int LOR>
+__device__ __forceinline__ void component_pass(int type, float cf, float width, float amp, int c0_int, int bins, AccT* __restrict__ wacc,
+                                               int lane, const double2* __restrict__ ltab, double phi_inf,
+                                               unsigned& gauss_evals, unsigned& lorentz_evals) {
+    LineRec R;
+    R.kx = R.xoff = R.s0 = R.s1 = R.s2 = R.s3 = R.s4 = 0.f;
+    R.lo = INT_MAX; R.hi = INT_MIN; R.kind = 0;
+    if (amp > 0.f && width > 0.f) {
+        const float win_lo = (float)(-c0_int), win_hi = (float)(bins - c0_int);
+        // the reference's range (GAUSSIAN_CUTOFF_SIGMA = 10, LORENTZIAN_CUTOFF_GAMMA = 50) defines the work counters
+        const float cut = (type == 1 ? 50.0f : 10.0f) * width;
+        const float flo = floorf(cf - cut), fhi = ceilf(cf + cut);
+        if (fhi > win_lo && flo < win_hi) {
+            const int l = (int)fmaxf(flo, win_lo), h = (int)fminf(fhi, win_hi);
+            if (h > l) {
+                if (type == 1) {
+                    lorentz_evals += (unsigned)(h - l) + 1u;
+                    if (LOR) { R.kind = 3; R.lo = l; R.hi = h; R.kx = 1.0f / width; R.xoff = -cf * R.kx; R.s0 = amp; }  // u at edge e: e kx + xoff
+                } else {
+                    gauss_evals += (unsigned)(h - l) + 1u;
+                    const float ecut = EVAL_CUTOFF_SIGMA * width;            // evaluated range: 7 sigma
+                    R.lo = max(l, (int)fmaxf(floorf(cf - ecut), win_lo));
+                    R.hi = min(h, (int)fminf(ceilf(cf + ecut), win_hi));
+                    const float kb = 0.70710678f / width;                    // delta / (sqrt(2) sigma), per bin
+                    const float hh = 0.5f * kb;
+                    if (hh <= H_SERIES_MAX) {
+                        const float h2 = hh * hh;
+                        const float t1 = h2 * (1.0f / 6.0f), t2 = h2 * h2 * (1.0f / 120.0f), t3 = h2 * h2 * h2 * (1.0f / 5040.0f),
+                                    t4 = h2 * h2 * h2 * h2 * (1.0f / 362880.0f);
+                        const float A = amp * kb * INV_SQRT_PI;
+                        R.kind = 1;
+                        R.kx = kb * SQRT_L2E;
+                        R.xoff = (0.5f - cf) * R.kx;                          // x' at the centre of relative bin 0
+                        R.s0 = A * (1.0f - 2.0f * t1 + 12.0f * t2 - 120.0f * t3 + 1680.0f * t4);
+                        R.s1 = A * (4.0f * t1 - 48.0f * t2 + 720.0f * t3 - 13440.0f * t4) * INV_L2E;
+                        R.s2 = A * (16.0f * t2 - 480.0f * t3 + 13440.0f * t4) * (INV_L2E * INV_L2E);
+                        R.s3 = A * (64.0f * t3 - 3584.0f * t4) * (INV_L2E * INV_L2E * INV_L2E);
+                        R.s4 = A * (256.0f * t4) * (INV_L2E * INV_L2E * INV_L2E * INV_L2E);
+                        if (!(R.s0 > 0.f)) R.kind = 0;
+                    } else {
+                        R.kind = 2;
+                        R.kx = kb;
+                        R.xoff = (1.0f - cf) * kb;                            // x at the UPPER edge of relative bin 0
+                        R.s0 = amp;
+                    }
+                    if (R.hi <= R.lo || R.kind == 0) { R.kind = 0; R.lo = INT_MAX; R.hi = INT_MIN; }
+                }
+            }
+        }
+    }
+    const unsigned any_series = __ballot_sync(FULL, R.kind == 1), any_edges = __ballot_sync(FULL, R.kind >= 2);
+    if (any_series) {
+        // windows start at the union's first bin; the last (or only) one uses the narrowest width class that covers it
+        const int Rlo = __reduce_min_sync(FULL, R.kind == 1 ? R.lo : INT_MAX), Rhi = __reduce_max_sync(FULL, R.kind == 1 ? R.hi : INT_MIN);
+        for (int wbase = Rlo; wbase < Rhi; wbase += 32) {
+            const int left = Rhi - wbase;
+            if (left <= 8) { window_series_tail<8, AccT>(R, wbase, c0_int, bins, wacc, lane); break; }
+            if (left <= 16) { window_series_tail<16, AccT>(R, wbase, c0_int, bins, wacc, lane); break; }
+            window_series_xor<AccT>(R, wbase, c0_int, bins, wacc, lane);
+        }
+    }
+    if (any_edges) edges_pass<AccT, LOR>(R, c0_int, bins, wacc, lane, ltab, phi_inf);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ray / segment geometry shared by the kernels: NumericalIntegrator.integrate [raysect] takes start_point = far end of the
+// segment, end_point = near end, both to plasma space; float64 with the reference's operation order so that step positions
+// are bit-identical
+// ------------------------------------------------------------------------------------------------------------------
+struct SegGeom {
+    double sx, sy, sz, ivx, ivy, ivz, h;
+    int iv;                                           // intervals; samples k = 0..iv; 0 for a degenerate segment (skipped)
+};
+
+__device__ __forceinline__ SegGeom segment_geometry(const double* __restrict__ w2p, double step, int min_samples, double ox, double oy,
+                                                    double oz, double dwx, double dwy, double dwz, double t0, double t1) {
+    SegGeom g;
+    const double swx = __dadd_rn(ox, __dmul_rn(t1, dwx)), swy = __dadd_rn(oy, __dmul_rn(t1, dwy)), swz = __dadd_rn(oz, __dmul_rn(t1, dwz));
+    const double ewx = __dadd_rn(ox, __dmul_rn(t0, dwx)), ewy = __dadd_rn(oy, __dmul_rn(t0, dwy)), ewz = __dadd_rn(oz, __dmul_rn(t0, dwz));
+    g.sx = xform_row(w2p, swx, swy, swz, true); g.sy = xform_row(w2p + 4, swx, swy, swz, true); g.sz = xform_row(w2p + 8, swx, swy, swz, true);
+    g.ivx = __dsub_rn(xform_row(w2p, ewx, ewy, ewz, true), g.sx);
+    g.ivy = __dsub_rn(xform_row(w2p + 4, ewx, ewy, ewz, true), g.sy);
+    g.ivz = __dsub_rn(xform_row(w2p + 8, ewx, ewy, ewz, true), g.sz);
+    const double length = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.ivx, g.ivx), __dmul_rn(g.ivy, g.ivy)), __dmul_rn(g.ivz, g.ivz)));
+    g.iv = 0; g.h = 0.0;
+    if (!(length > 0.0)) return g;
+    g.ivx = __ddiv_rn(g.ivx, length); g.ivy = __ddiv_rn(g.ivy, length); g.ivz = __ddiv_rn(g.ivz, length);
+    int iv = (int)ceil(__ddiv_rn(length, step));      // intervals = max(min_samples - 1, ceil(L / step))
+    iv = max(iv, max(min_samples - 1, 1));
+    g.iv = iv;
+    g.h = __ddiv_rn(length, (double)iv);
+    return g;
+}
+
+// groups of 32 samples per ray (each segment starts a new group) -> counts[ray]; counts[n_rays] = 0 for the scan
+__global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays rays, int64_t* __restrict__ counts) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray > rays.n_rays) return;
+    if (ray == rays.n_rays) { counts[ray] = 0; return; }
+    const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+    const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
+    int64_t n = 0;
+    for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+        const SegGeom g = segment_geometry(S.w2p, S.step, S.min_samples, ox, oy, oz, dwx, dwy, dwz, rays.seg_t0[sg], rays.seg_t1[sg]);
+        if (g.iv > 0) n += g.iv / 32 + 1;
+    }
+    counts[ray] = n;
+}
+
+// record layout: rec[((group * n_comp + comp) * 3 + field) * 32 + lane], field 0 centre, 1 width, 2 amplitude
+#define REC_FLOATS_PER_COMP 96
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1a: per-sample plasma state -> line records + Bremsstrahlung moments
+// ------------------------------------------------------------------------------------------------------------------
+template <int NW, int MOM>
+__global__ void __launch_bounds__(NW * 32, 640 / (NW * 32))
+state_kernel(const __grid_constant__ DevScene S, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
+             float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int dbg_skip) {
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_pad = MOM ? S.brems.k_pad : 0;
+    double* mom = smem_d;
+    if (MOM)
+        for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
+
+    const int64_t ray = blockIdx.x;
+    const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+    const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
+    SampleIn in;
+    {
+        // ray direction in plasma space (direction.transform(local_to_plasma), normalised inside doppler_shift)
+        const double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
+                     d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        const double dl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        in.dx = (float)(d0 / dl); in.dy = (float)(d1 / dl); in.dz = (float)(d2 / dl);
+    }
+    unsigned long long n_samples = 0;
+    unsigned n_brems = 0, ood = 0;
+    const int n_comp = S.n_comp;
+    if (MOM) __syncthreads();
+
+    int64_t G0 = gbase[ray];                          // first group of the current segment
+    int g_rot = 0;                                    // keeps the round-robin going across segments
+    for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+        const SegGeom sgm = segment_geometry(S.w2p, S.step, S.min_samples, ox, oy, oz, dwx, dwy, dwz, rays.seg_t0[sg], rays.seg_t1[sg]);
+        const int iv = sgm.iv;
+        if (iv <= 0) continue;
+        const float hf = (float)sgm.h;
+        if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
+        const int n_groups = iv / 32 + 1;
+        int first = (warp - g_rot) % NW;
+        if (first < 0) first += NW;
+        g_rot = (g_rot + n_groups) % NW;
+
+        for (int g = first; g < n_groups; g += NW) {
+            const int k = g * 32 + lane;
+            const bool active = k <= iv;
+            const double tk = __dmul_rn((double)k, sgm.h);
+            const double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
+                         pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
+            in.x = (float)pxd; in.y = (float)pyd; in.z = (float)pzd;
+            in.weight = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
+            AxCtx ctx;
+            float ne = 0.f, te = 0.f;
+            if (active) {
+                ax_setup(S, pxd, pyd, pzd, ctx, ood);
+                ne = eval_scalar(S.ne, ctx, in.x, in.y, in.z);
+                te = eval_scalar(S.te, ctx, in.x, in.y, in.z);
+            } else {
+                ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false;
+            }
+            const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+            const unsigned live_mask = __ballot_sync(FULL, live);
+            const int64_t G = G0 + g;
+            if (lane == 0) gmask[G] = live_mask;
+            if (!live_mask) continue;                              // the whole group is in vacuum
+            if (MOM && dbg_skip != 2) sample_brems_moments(S, in, ctx, ne, te, mom, lane, n_brems, ood);
+            LineCache lc;
+            lc.cur = -1; lc.ni = lc.ts = lc.vd = 0.f; lc.have_b = false; lc.bm = lc.cos_sqr = 0.f; lc.grid = -2;
+            lc.lne = lc.lte = 0.f;
+            if (live) {
+                lc.lne = log10f(ne) + 19.0f;                       // densities are stored in units of 1e19 m^-3
+                lc.lte = log10f(te);
+            }
+            float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
+            for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
+                const DevModel& M = S.models[m];
+                if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
+                ModelCtx mc;
+                model_setup(S, M, in, ctx, ne, te, live, lc, mc, ood);
+                const bool any_on = __any_sync(FULL, mc.on);
+                for (int kc = 0; kc < M.ncomp; kc++) {
+                    float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
+                    int type; float cf = 0.f, width = 0.f, amp = 0.f;
+                    if (any_on) model_component(S, M, kc, mc, type, cf, width, amp);
+                    r[64] = amp;
+                    if (__any_sync(FULL, amp > 0.f)) { r[0] = cf; r[32] = width; }
+                }
+            }
+        }
+        G0 += n_groups;
+    }
+    if (MOM) {
+        __syncthreads();
+        float* row = mom_out + (size_t)ray * k_pad;
+        for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
+    }
+    if (stats) {
+        unsigned long long nb = n_brems, oodl = ood;
+        for (int off = 16; off > 0; off >>= 1) {
+            nb += __shfl_down_sync(FULL, nb, off);
+            oodl += __shfl_down_sync(FULL, oodl, off);
+        }
+        if (lane == 0) {
+            if (nb) atomicAdd(stats + 3, nb);
+            if (oodl) atomicAdd(stats + 5, oodl);
+        }
+        if (tid == 0 && n_samples) atomicAdd(stats + 0, n_samples);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1b: line records -> spectral bins
+// ------------------------------------------------------------------------------------------------------------------
+template <int NW, typename AccT, int LOR>
+__global__ void __launch_bounds__(NW * 32, 768 / (NW * 32))
+bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __restrict__ gbase, const unsigned* __restrict__ gmask,
+           const float* __restrict__ rec, void* __restrict__ out, int out_f64, double scale, int accumulate,
+           unsigned long long* __restrict__ stats) {
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bins = S.bins, bins_pad = (bins + 31) & ~31;
+    AccT* wall = reinterpret_cast<AccT*>(smem_d);
+    AccT* wacc = wall + (size_t)warp * bins_pad;
+    for (int i = lane; i < bins_pad; i += 32) wacc[i] = (AccT)0;
+    __syncwarp();
+    const int64_t ray = blockIdx.x;
+    const int n_comp = S.n_comp;
+    unsigned n_gauss = 0, n_lorentz = 0;
+    const int64_t G0 = gbase[ray], G1 = gbase[ray + 1];
+    for (int64_t G = G0 + warp; G < G1; G += NW) {
+        if (!__ldg(gmask + G)) continue;
+        const float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
+        for (int c = 0; c < n_comp; c++) {
+            const float* r = grec + (size_t)c * REC_FLOATS_PER_COMP;
+            const float amp = __ldg(r + 64);
+            if (!__any_sync(FULL, amp > 0.f)) continue;
+            const float cf = __ldg(r), width = __ldg(r + 32);
+            component_pass<AccT, LOR>(S.comps[c].type, cf, width, amp, S.comps[c].c0_int, bins, wacc, lane, S.lorentz_tab,
+                                      S.lorentz_phi_inf, n_gauss, n_lorentz);
+        }
+    }
+    __syncthreads();
+    // the ray's spectrum: fp64 sum of the NW private accumulators, lane-consecutive bins -> coalesced rows
+    for (int bin = tid; bin < bins; bin += NW * 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) v += (double)wall[(size_t)w * bins_pad + bin];
+        v *= scale;
+        const size_t idx = (size_t)ray * bins + bin;
+        if (out_f64) {
+            double* p = (double*)out + idx;
+            *p = (accumulate ? *p : 0.0) + v;
+        } else {
+            float* p = (float*)out + idx;
+            *p = (float)((accumulate ? (double)*p : 0.0) + v);
+        }
+    }
+    if (stats) {
+        unsigned long long ng = n_gauss, nl = n_lorentz;
+        for (int off = 16; off > 0; off >>= 1) {
+            ng += __shfl_down_sync(FULL, ng, off);
+            nl += __shfl_down_sync(FULL, nl, off);
+        }
+        if (lane == 0) {
+            if (ng) atomicAdd(stats + 1, ng);
+            if (nl) atomicAdd(stats + 2, nl);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch: per batch of rays  count groups -> scan -> state_kernel -> bin_kernel -> contraction of the moments
+// ------------------------------------------------------------------------------------------------------------------
+size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins) {
+    const size_t bins_pad = ((size_t)bins + 31) & ~(size_t)31;
+    return (size_t)nw * bins_pad * (acc_f64 ? sizeof(double) : sizeof(float));
+}
+
+int64_t cb2_warp_batch_rays(const cb2_scene* sc) {
+    int64_t b = 16384;
+    if (const char* e = getenv("CB2_BATCH_RAYS")) { const long v = atol(e); if (v >= 128) b = v / 128 * 128; }
+    if (sc->host.brems.present && sc->host.brems.mode == 3) b = std::min(b, cb2_moment_batch(sc->host.brems.k_pad));
+    return b;
+}
+
+template <typename T>
+static int reserve(T** p, size_t* have, size_t need, cudaStream_t st) {
+    if (*have >= need && *p) return CB2_OK;
+    CB2_CUDA(cudaStreamSynchronize(st));
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    const size_t cap = need + need / 8 + 256;
+    CB2_CUDA(cudaMalloc((void**)p, cap));
+    *have = cap;
+    return CB2_OK;
+}
+
+template <int NW, typename AccT>
+static int launch_bin(const cb2_scene* sc, int64_t n_rays, void* out, int out_f64, double scale, int accumulate, unsigned long long* stats,
+                      cudaStream_t st) {
+    const DevScene& S = sc->host;
+    const size_t smem = cb2_warp_smem_bytes(NW, sizeof(AccT) == 8, S.bins);
+    if (S.has_lorentz) {
+        auto kern = bin_kernel<NW, AccT, 1>;
+        if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, out, out_f64, scale, accumulate, stats);
+    } else {
+        auto kern = bin_kernel<NW, AccT, 0>;
+        if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, out, out_f64, scale, accumulate, stats);
+    }
+    return cb2_cuda_check(cudaGetLastError(), "bin_kernel launch");
+}
+
+int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                             unsigned long long* stats, cudaStream_t st) {
+    const DevScene& S = sc->host;
+    const DevBrems& B = S.brems;
+    const bool moments = B.present && B.mode == 3;
+    const int n_comp = S.n_comp;
+    static const int dbg = getenv("CB2_DBG_SKIP") ? atoi(getenv("CB2_DBG_SKIP")) : 0;
+    const size_t esz = out_f64 ? sizeof(double) : sizeof(float);
+    const size_t rec_cap_bytes = (size_t)24 << 30;            // bound on the record buffer; batches shrink to respect it
+    int64_t batch = std::min(cb2_warp_batch_rays(sc), rays.n_rays);
+    int rc;
+    for (int64_t r0 = 0; r0 < rays.n_rays;) {
+        DevRays sub = rays;
+        sub.n_rays = std::min(batch, rays.n_rays - r0);
+        sub.origin = rays.origin + 3 * r0;
+        sub.direction = rays.direction + 3 * r0;
+        sub.seg_offset = rays.seg_offset + r0;                  // entries are absolute segment indices
+        void* o = (char*)out + (size_t)r0 * S.bins * esz;
+        // groups per ray -> offsets
+        if ((rc = reserve(&sc->gbase, &sc->gbase_bytes, (size_t)(sub.n_rays + 1) * sizeof(int64_t), st)) != CB2_OK) return rc;
+        count_groups_kernel<<<(unsigned)((sub.n_rays + 1 + 127) / 128), 128, 0, st>>>(S, sub, sc->gbase);
+        if ((rc = cb2_cuda_check(cudaGetLastError(), "count_groups_kernel launch")) != CB2_OK) return rc;
+        if ((rc = cb2_launch_scan(sc->gbase, sub.n_rays + 1, st)) != CB2_OK) return rc;
+        int64_t n_groups = 0;
+        CB2_CUDA(cudaMemcpyAsync(&n_groups, sc->gbase + sub.n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CB2_CUDA(cudaStreamSynchronize(st));
+        const size_t rec_bytes = (size_t)n_groups * std::max(n_comp, 1) * REC_FLOATS_PER_COMP * sizeof(float);
+        if (rec_bytes > rec_cap_bytes && sub.n_rays > 128) {     // too many samples in this batch: halve it and retry
+            batch = std::max<int64_t>(128, (sub.n_rays / 2 + 127) / 128 * 128);
+            continue;
+        }
+        if ((rc = reserve(&sc->gmask, &sc->gmask_bytes, (size_t)std::max<int64_t>(n_groups, 1) * sizeof(unsigned), st)) != CB2_OK) return rc;
+        if ((rc = reserve(&sc->rec, &sc->rec_bytes, std::max<size_t>(rec_bytes, 256), st)) != CB2_OK) return rc;
+        if (moments && (rc = reserve(&sc->mom, &sc->mom_bytes, (size_t)sub.n_rays * B.k_pad * sizeof(float), st)) != CB2_OK) return rc;
+        // K1a
+        {
+            const size_t smem = moments ? (size_t)B.k_pad * sizeof(double) : 0;
+            if (moments) {
+                auto kern = state_kernel<4, 1>;
+                if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, dbg);
+            } else {
+                state_kernel<4, 0><<<dim3((unsigned)sub.n_rays), dim3(128), 0, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, nullptr, dbg);
+            }
+            if ((rc = cb2_cuda_check(cudaGetLastError(), "state_kernel launch")) != CB2_OK) return rc;
+        }
+        // K1b
+        if (sc->nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
+                                          : launch_bin<8, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
+        else if (sc->nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
+                                               : launch_bin<2, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
+        else rc = sc->acc_f64 ? launch_bin<4, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
+                              : launch_bin<4, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
+        if (rc != CB2_OK) return rc;
+        // K2
+        if (moments && (rc = cb2_launch_contract(sc->mom, B.phi, sub.n_rays, B.k_pad, B.n_pad, S.bins, o, out_f64, scale, st)) != CB2_OK) return rc;
+        r0 += sub.n_rays;
+    }
+    return CB2_OK;
+}

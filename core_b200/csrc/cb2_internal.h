@@ -34,6 +34,8 @@ struct DevTable2D {
 
 struct DevTable1D {          // knots shared, coefficients per quantity
     int n;
+    int uniform;             // 1: uniform knots -> direct index, no dependent loads
+    float x0, inv_dx;
     float xmin, xmax;
     const float* x;          // [n]
     const float* inv_w;      // [n-1]
@@ -105,6 +107,7 @@ struct DevModel {
     int pec_const;        // 1: constant rate
     float pec_value;      // log10(rate) + 38 for constant rates
     int pec_extrapolate;
+    int pec_grid;         // models with the same id share the (ne, te) knots: the cell search is done once per sample
     DevTable2D pec;       // log10 ne[m^-3], log10 te -> log10(W m^3) + 38
     // multiplet
     int n_mult;
@@ -205,6 +208,8 @@ struct cb2_scene {
     int n_allocs, cap_allocs;
     // launch configuration
     int nw, bpl, smem_bytes;
+    int warp_kernel;         // 1: warp-autonomous kernel (cb2_emission_warp.cu), 0: CTA-phased kernel with the direct Bremsstrahlung path
+    int acc_f64;             // warp kernel: private accumulators in fp64 (else fp32)
     // staging buffers for the host-buffer entry point
     void* stage[8];
     size_t stage_bytes[8];
@@ -212,6 +217,14 @@ struct cb2_scene {
     // Bremsstrahlung moment matrix [rays][k_pad] fp32 (grow-only)
     float* mom;
     size_t mom_bytes;
+    // two-kernel line path (cb2_emission_warp.cu), grow-only: per-ray group offsets [batch+1], per-group live masks, and
+    // the per-(group, component) line records [3][32] fp32 (centre, width, amplitude)
+    int64_t* gbase;
+    size_t gbase_bytes;
+    unsigned* gmask;
+    size_t gmask_bytes;
+    float* rec;
+    size_t rec_bytes;
 };
 
 struct cb2_rt_scene {
@@ -239,6 +252,10 @@ int cb2_cuda_check(cudaError_t e, const char* what);
 int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                         unsigned long long* stats_dev, cudaStream_t stream);
 int cb2_emission_config(cb2_scene* sc);
+size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
+int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
+                             unsigned long long* stats, cudaStream_t stream);
+int64_t cb2_warp_batch_rays(const cb2_scene* sc);
 int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t stream);
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate,
                   int64_t* row_offset, int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t stream);
