@@ -32,10 +32,11 @@ UNIT = "Msamples/s"
 CAMERA_POS, CAMERA_TARGET = (2.3, 0.0, 1.25), (1.0, 0.8, -0.5)
 TILE = 16
 
-# Algorithmic work per unit (DESIGN.md "Measurement"): minimal formulation, counted from the kernel's own counters
-F_GAUSS_BIN = 14.0      # flop per Gaussian bin evaluation (5-term series form: 7 FMA-class) + 1 SFU
-F_BREMS_BIN = 10.0      # flop per (sample, bin, quadrature point) + 1 SFU
-F_FIXED_BASE = 20.0 + 3 * 40.0 + 30.0   # transform/R, three bicubics, masks/blend
+# Algorithmic work per unit: minimal formulation, counted from the kernels' own counters
+F_GAUSS_BIN = 14.0      # flop per Gaussian bin evaluation (5-term series form: 7 FMA-class) + 1 SFU            [bin_kernel]
+F_FIXED_BASE = 20.0 + 3 * 40.0 + 30.0   # transform/R, three bicubics, masks/blend                [state_kernel]
+F_MOMENT = 80.0         # flop per live sample for the Bremsstrahlung moment update (weights + 4 nodes x charges) [state_kernel]
+REC_BYTES = 384.0       # bytes per live (32-sample group, line component) record row, written once and read once
 
 
 def build_scene(bins, lo=390.0, hi=700.0):
@@ -208,10 +209,6 @@ def main():
 
     peaks = measure_peaks(local_rank) if rank == 0 else None
     plan = scene.info()
-    launches_per_step = 1
-    if plan["brems_mode"] == "moments":
-        # per moment batch: emission_kernel (lines + moments) and contract_kernel (moments . phi)
-        launches_per_step = 2 * -(-pix.size // max(plan["moment_batch_rays"], 1))
 
     def step(k):
         scene.render_device(dev_rays[k % len(dev_rays)], frame, scale=1.0 / 16.0, accumulate=(k % 16) != 0, stats=stats)
@@ -246,6 +243,16 @@ def main():
     st = st.cpu().numpy()
     samples, gauss, brems, ood = int(st[0]), int(st[1]), int(st[3]), int(st[5])
     value = samples / (ms * 1e-3) * 1e-6
+
+    # ---- per-kernel split: one extra pass bracketed by CUDA events inside the library (cb2_scene_profile) ----
+    kernel_ms = None
+    if rank == 0 and plan["two_kernel_line_path"]:
+        scratch_stats = torch.zeros(6, dtype=torch.int64, device=dev)
+        scene.profile(True)
+        scene.render_device(dev_rays[args.warmup % len(dev_rays)], frame, scale=1.0 / 16.0, accumulate=True, stats=scratch_stats)
+        torch.cuda.synchronize()
+        kernel_ms = scene.profile(False)
+    launches_per_step = sum(v[1] for v in kernel_ms.values()) if kernel_ms else 1
 
     # ---- e2e: host buffers through the C-ABI call (H2D rays + kernel + [NCCL gather] + D2H frame) ----
     e2e = None
@@ -291,32 +298,62 @@ def main():
 
     if rank == 0:
         fixed = fixed_flops_per_sample(flat)
-        nq = 1
-        flops = F_GAUSS_BIN * gauss + F_BREMS_BIN * brems * nq + fixed * samples
-        sfu = gauss + brems * nq
-        launch_ms = ms / args.steps
-        ach_fp32 = flops / world / (ms * 1e-3) * 1e-12          # per GPU
-        ach_sfu = sfu / world / (ms * 1e-3) * 1e-12
-        frame_bytes = pix.size * args.bins * 4.0
+        n_line = sum(1 for i in range(flat.desc.n_models) if flat.desc.models[i].kind != 2)
+        step_s = ms * 1e-3 / args.steps
+        per_step = lambda x: x / args.steps / world                      # counters are summed over steps and ranks
+        live = brems / max(args.bins, 1)                                   # samples with ne, te > 0 (Bremsstrahlung counter / bins)
         peaks_file = {}
         try:
             peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        r_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
-                  "frac": ach_fp32 / peaks["fp32_tflops"], "traffic": None}
-        r_sfu = {"bound": "sfu", "achieved": ach_sfu, "peak": peaks["sfu_tops"], "unit": "Tops/s",
-                 "frac": ach_sfu / peaks["sfu_tops"], "traffic": None}
-        roofline = dict(r_sfu if r_sfu["frac"] > r_fp32["frac"] else r_fp32)
-        roofline.update({"kernel": "emission_kernel<NW=8,BPL=8,BREMS=1>", "launch_ms": launch_ms,
-                         "peak_source": "measured live (cb2_measure_peaks: FFMA / MUFU.EX2 issue-rate microbenchmarks)",
-                         "algorithmic": {"samples": samples, "gaussian_bin_evals": gauss, "brems_bin_evals": brems,
-                                         "flop_per_gauss_bin": F_GAUSS_BIN, "flop_per_brems_bin": F_BREMS_BIN,
-                                         "fixed_flop_per_sample": fixed, "flop_per_sample": flops / max(samples, 1)},
-                         "fp32": r_fp32, "sfu": r_sfu,
-                         "hbm": {"achieved": frame_bytes * (2 if True else 1) / (launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                                 "note": "frame read-modify-write only; " + ("of measured" if "hbm_gbs" in peaks_file else "of fallback")}})
+        hbm_src = "of measured" if "hbm_gbs" in peaks_file else "of fallback"
+        kernels = {}
+        if kernel_ms:
+            tot = sum(v[0] for v in kernel_ms.values()) or 1.0
+            k_pad, n_pad = plan["moment_row"], -(-args.bins // 128) * 128
+            work = {
+                # (flop, sfu ops) per step on this GPU, algorithmic
+                "state_kernel": (per_step(fixed * samples + F_MOMENT * live), per_step((4.0 + 2.0 * n_line) * live)),
+                "bin_kernel": (per_step(F_GAUSS_BIN * gauss), per_step(gauss)),
+                "contract_kernel": (2.0 * pix.size * k_pad * n_pad, 0.0),
+                "helpers": (0.0, 0.0)}
+            for name, (kms, n) in kernel_ms.items():
+                flop, sfu = work[name]
+                t = kms * 1e-3
+                e = {"ms_per_step": kms, "share": kms / tot, "launches_per_step": n}
+                if t > 0 and flop > 0:
+                    e["fp32"] = {"achieved": flop / t * 1e-12, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": flop / t * 1e-12 / peaks["fp32_tflops"]}
+                if t > 0 and sfu > 0:
+                    e["sfu"] = {"achieved": sfu / t * 1e-12, "peak": peaks["sfu_tops"], "unit": "Tops/s", "frac": sfu / t * 1e-12 / peaks["sfu_tops"]}
+                kernels[name] = e
+            dom = max((k for k in kernels if k != "helpers"), key=lambda k: kernels[k]["ms_per_step"])
+        else:
+            dom = "emission_kernel"
+            kernels[dom] = {"ms_per_step": step_s * 1e3, "share": 1.0, "launches_per_step": 1,
+                            "fp32": {"achieved": per_step(fixed * samples + F_GAUSS_BIN * gauss + 10.0 * brems) / step_s * 1e-12,
+                                     "peak": peaks["fp32_tflops"], "unit": "TFLOP/s"},
+                            "sfu": {"achieved": per_step(gauss + brems) / step_s * 1e-12, "peak": peaks["sfu_tops"], "unit": "Tops/s"}}
+            for kk in ("fp32", "sfu"):
+                kernels[dom][kk]["frac"] = kernels[dom][kk]["achieved"] / kernels[dom][kk]["peak"]
+        d = kernels[dom]
+        cands = [("fp32", d.get("fp32")), ("sfu", d.get("sfu"))]
+        bound, best = max(((b_, r_) for b_, r_ in cands if r_), key=lambda x: x[1]["frac"])
+        # whole-step view: all algorithmic flops of the step over the step time
+        step_flop = per_step(fixed * samples + F_MOMENT * live + F_GAUSS_BIN * gauss) + (2.0 * pix.size * plan["moment_row"] * (-(-args.bins // 128) * 128) if kernel_ms else per_step(10.0 * brems))
+        frame_bytes = pix.size * args.bins * 4.0
+        roofline = {"bound": bound, "achieved": best["achieved"], "peak": best["peak"], "unit": best["unit"], "frac": best["frac"],
+                    "traffic": None, "kernel": dom, "launch_ms": d["ms_per_step"] / max(d["launches_per_step"], 1),
+                    "peak_source": "measured live (cb2_measure_peaks: FFMA / MUFU.EX2 issue-rate microbenchmarks, same process)",
+                    "kernels": kernels,
+                    "step": {"ms": step_s * 1e3, "fp32_tflops": step_flop / step_s * 1e-12, "fp32_frac": step_flop / step_s * 1e-12 / peaks["fp32_tflops"],
+                             "flop_per_sample": step_flop / max(per_step(samples), 1)},
+                    "algorithmic": {"samples": samples, "live_samples": int(live), "gaussian_bin_evals": gauss,
+                                    "flop_per_gauss_bin": F_GAUSS_BIN, "fixed_flop_per_sample": fixed, "moment_flop_per_live_sample": F_MOMENT,
+                                    "contraction_flop_per_ray": 2.0 * plan["moment_row"] * (-(-args.bins // 128) * 128)},
+                    "hbm": {"achieved": frame_bytes * 3.0 / step_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                            "note": "frame written by bin_kernel and read-modify-written by contract_kernel; not a bound; " + hbm_src}}
         threads = os.cpu_count() or 1
         cpu_v, cpu_s, cpu_t = cpu_baseline(flat, plasma, args.pixels, args.cpu_rays, threads)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -106,7 +106,7 @@ class RTDesc(C.Structure):
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
-    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info",
+    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
 ]
 
@@ -136,6 +136,7 @@ def load_library():
     lib.cb2_state_width.argtypes = [vp]
     lib.cb2_scene_info.argtypes = [vp, C.c_int]
     lib.cb2_scene_info.restype = C.c_int64
+    lib.cb2_scene_profile.argtypes = [vp, C.c_int, c_double_p, c_int64_p]
     lib.cb2_rt_create.argtypes = [C.POINTER(RTDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_rt_destroy.argtypes = [vp]
     lib.cb2_rt_render_dense.argtypes = [vp, C.POINTER(Rays), c_double_p, C.c_int, C.POINTER(Stats)]

@@ -329,7 +329,7 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
     {
         // classification grid: cells overlapped by the bounding box of any edge (grown by one cell) are boundary cells,
         // the others take the exact even-odd result of their centre
-        const int gx = 96, gy = 160;
+        const int gx = 192, gy = 320;
         o.pgx = gx; o.pgy = gy;
         const double icx = gx / (pxmax - pxmin), icy = gy / (pymax - pymin);
         o.p_icx = (float)icx; o.p_icy = (float)icy;
@@ -393,9 +393,13 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
                     const double vx = ax.vertices[2 * tr[k]], vy = ax.vertices[2 * tr[k] + 1];
                     txmin = fmin(txmin, vx); txmax = fmax(txmax, vx); tymin = fmin(tymin, vy); tymax = fmax(tymax, vy);
                 }
-                // conservative: one extra cell all round absorbs the fp32 rounding of the device-side bucket index
-                int i0 = (int)floor((txmin - xmin) * icx) - 1, i1 = (int)floor((txmax - xmin) * icx) + 1;
-                int j0 = (int)floor((tymin - ymin) * icy) - 1, j1 = (int)floor((tymax - ymin) * icy) + 1;
+                // the device computes the bucket index with the same float64 expression (monotone in the coordinate), so a
+                // point inside the triangle's bounding box lands in this cell range: no safety margin needed.  Triangles are
+                // visited in ascending order, which keeps every bucket list sorted (first hit = lowest triangle id).
+                // (the box is grown by 1e-9 of the mesh extent for points the rounded containment test accepts on an edge)
+                const double ex = 1e-9 * (xmax - xmin), ey = 1e-9 * (ymax - ymin);
+                int i0 = (int)floor((txmin - ex - xmin) * icx), i1 = (int)floor((txmax + ex - xmin) * icx);
+                int j0 = (int)floor((tymin - ey - ymin) * icy), j1 = (int)floor((tymax + ey - ymin) * icy);
                 i0 = std::max(i0, 0); j0 = std::max(j0, 0); i1 = std::min(i1, gx - 1); j1 = std::min(j1, gy - 1);
                 for (int i = i0; i <= i1; i++)
                     for (int j = j0; j <= j1; j++) {
@@ -978,6 +982,8 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     if (sc->gbase) cudaFree(sc->gbase);
     if (sc->gmask) cudaFree(sc->gmask);
     if (sc->rec) cudaFree(sc->rec);
+    for (int i = 0; i < 10; i++)
+        if (sc->prof_ev[i]) cudaEventDestroy(sc->prof_ev[i]);
     free(sc);
     return CB2_OK;
 }
@@ -1084,6 +1090,24 @@ extern "C" int64_t cb2_scene_info(const cb2_scene* sc, int key) {
     case 7: return sc->warp_kernel;
     }
     return -1;
+}
+
+extern "C" int cb2_scene_profile(cb2_scene* sc, int enable, double* ms_out, int64_t* launches_out) {
+    if (!sc) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    CB2_CUDA(cudaSetDevice(sc->device));
+    if (enable) {
+        for (int i = 0; i < 4; i++) { sc->prof_ms[i] = 0.0; sc->prof_launches[i] = 0; }
+        for (int i = 0; i < 10; i++)
+            if (!sc->prof_ev[i]) CB2_CUDA(cudaEventCreate(&sc->prof_ev[i]));
+        sc->prof_on = 1;
+        return CB2_OK;
+    }
+    sc->prof_on = 0;
+    for (int i = 0; i < 4; i++) {
+        if (ms_out) ms_out[i] = sc->prof_ms[i];
+        if (launches_out) launches_out[i] = sc->prof_launches[i];
+    }
+    return CB2_OK;
 }
 
 extern "C" int cb2_state_width(const cb2_scene* sc) { return sc ? 2 + 5 * sc->host.n_species + 3 : 0; }

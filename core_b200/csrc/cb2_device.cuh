@@ -145,7 +145,8 @@ __device__ __forceinline__ int mesh_locate(const DevAxisym& A, double r, double 
     const int i = (int)fx, j = (int)fy;
     if (i >= A.gx || j >= A.gy) return -1;
     const int cell = i * A.gy + j;
-    int best = -1;
+    // the bucket lists are in ascending triangle order, so the first hit is the lowest-numbered triangle containing the
+    // point (the tie rule for points on shared edges)
     const int k1 = __ldg(A.cell_start + cell + 1);
     for (int k = __ldg(A.cell_start + cell); k < k1; k++) {
         const int t = __ldg(A.cell_tris + k);
@@ -154,9 +155,9 @@ __device__ __forceinline__ int mesh_locate(const DevAxisym& A, double r, double 
         const double d2 = __dsub_rn(__dmul_rn(__dsub_rn(r, c.x), __dsub_rn(b.y, c.y)), __dmul_rn(__dsub_rn(b.x, c.x), __dsub_rn(z, c.y)));
         const double d3 = __dsub_rn(__dmul_rn(__dsub_rn(r, a.x), __dsub_rn(c.y, a.y)), __dmul_rn(__dsub_rn(c.x, a.x), __dsub_rn(z, a.y)));
         const bool neg = (d1 < 0) || (d2 < 0) || (d3 < 0), pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
-        if (!(neg && pos) && (best < 0 || t < best)) best = t;
+        if (!(neg && pos)) return t;
     }
-    return best;
+    return -1;
 }
 
 __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd, double zd, AxCtx& c, unsigned& ood) {
@@ -349,6 +350,7 @@ __device__ __forceinline__ void sample_brems_moments(const DevScene& S, const Sa
         float nzv[CB2_MAX_BREMS_Z];
 #pragma unroll
         for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] = 0.f;
+#pragma unroll 4
         for (int s = 0; s < B.n_charged; s++) {
             const float ni = eval_scalar(S.species[B.charged[s]].density, ctx, in.x, in.y, in.z);
             const int zi = B.zidx[s];

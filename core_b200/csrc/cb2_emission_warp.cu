@@ -466,14 +466,24 @@ __global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays 
 // ------------------------------------------------------------------------------------------------------------------
 template <int NW, int MOM>
 __global__ void __launch_bounds__(NW * 32, 640 / (NW * 32))
-state_kernel(const __grid_constant__ DevScene S, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
+state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int dbg_skip) {
     extern __shared__ double smem_d[];
+    // the flattened scene (13 KB of model / species / table descriptors, indexed with run-time model and species numbers)
+    // is staged in shared memory: indexed constant-bank loads miss the small constant cache and stall (ncu: short scoreboard)
+    __shared__ __align__(16) unsigned char scene_s[sizeof(DevScene)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_pad = MOM ? S.brems.k_pad : 0;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&Sparam);
+        uint4* dst = reinterpret_cast<uint4*>(scene_s);
+        for (int i = tid; i < (int)(sizeof(DevScene) / sizeof(uint4)); i += NW * 32) dst[i] = src[i];
+    }
+    const DevScene& S = *reinterpret_cast<const DevScene*>(scene_s);
+    const int k_pad = MOM ? Sparam.brems.k_pad : 0;
     double* mom = smem_d;
     if (MOM)
         for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
+    __syncthreads();
 
     const int64_t ray = blockIdx.x;
     const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
@@ -489,7 +499,6 @@ state_kernel(const __grid_constant__ DevScene S, DevRays rays, const int64_t* __
     unsigned long long n_samples = 0;
     unsigned n_brems = 0, ood = 0;
     const int n_comp = S.n_comp;
-    if (MOM) __syncthreads();
 
     int64_t G0 = gbase[ray];                          // first group of the current segment
     int g_rot = 0;                                    // keeps the round-robin going across segments
@@ -694,6 +703,8 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         sub.direction = rays.direction + 3 * r0;
         sub.seg_offset = rays.seg_offset + r0;                  // entries are absolute segment indices
         void* o = (char*)out + (size_t)r0 * S.bins * esz;
+        const bool prof = sc->prof_on != 0;
+        if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[0], st));
         // groups per ray -> offsets
         if ((rc = reserve(&sc->gbase, &sc->gbase_bytes, (size_t)(sub.n_rays + 1) * sizeof(int64_t), st)) != CB2_OK) return rc;
         count_groups_kernel<<<(unsigned)((sub.n_rays + 1 + 127) / 128), 128, 0, st>>>(S, sub, sc->gbase);
@@ -710,6 +721,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         if ((rc = reserve(&sc->gmask, &sc->gmask_bytes, (size_t)std::max<int64_t>(n_groups, 1) * sizeof(unsigned), st)) != CB2_OK) return rc;
         if ((rc = reserve(&sc->rec, &sc->rec_bytes, std::max<size_t>(rec_bytes, 256), st)) != CB2_OK) return rc;
         if (moments && (rc = reserve(&sc->mom, &sc->mom_bytes, (size_t)sub.n_rays * B.k_pad * sizeof(float), st)) != CB2_OK) return rc;
+        if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[1], st));
         // K1a
         {
             const size_t smem = moments ? (size_t)B.k_pad * sizeof(double) : 0;
@@ -722,6 +734,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
             }
             if ((rc = cb2_cuda_check(cudaGetLastError(), "state_kernel launch")) != CB2_OK) return rc;
         }
+        if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[2], st));
         // K1b
         if (sc->nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
                                           : launch_bin<8, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
@@ -730,8 +743,20 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         else rc = sc->acc_f64 ? launch_bin<4, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
                               : launch_bin<4, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
         if (rc != CB2_OK) return rc;
+        if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[3], st));
         // K2
         if (moments && (rc = cb2_launch_contract(sc->mom, B.phi, sub.n_rays, B.k_pad, B.n_pad, S.bins, o, out_f64, scale, st)) != CB2_OK) return rc;
+        if (prof) {
+            CB2_CUDA(cudaEventRecord(sc->prof_ev[4], st));
+            CB2_CUDA(cudaEventSynchronize(sc->prof_ev[4]));
+            const int slot[4] = {3, 0, 1, 2};                   // helpers, state, bin, contract
+            for (int i = 0; i < 4; i++) {
+                float ms = 0.f;
+                CB2_CUDA(cudaEventElapsedTime(&ms, sc->prof_ev[i], sc->prof_ev[i + 1]));
+                sc->prof_ms[slot[i]] += ms;
+            }
+            sc->prof_launches[3] += 2; sc->prof_launches[0] += 1; sc->prof_launches[1] += 1; sc->prof_launches[2] += moments ? 1 : 0;
+        }
         r0 += sub.n_rays;
     }
     return CB2_OK;

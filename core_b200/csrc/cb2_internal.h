@@ -155,7 +155,7 @@ struct DevBrems {
 };
 #define CB2_MAX_BREMS_Z 8
 
-struct DevScene {
+struct alignas(16) DevScene {
     int n_species, n_models, n_comp;
     int bins, bins_padded;
     float min_wavelength, delta;
@@ -178,6 +178,8 @@ struct DevScene {
     const double2* lorentz_tab;
     double lorentz_phi_inf;
 };
+
+static_assert(sizeof(DevScene) % 16 == 0, "DevScene is copied to shared memory as uint4");
 
 struct DevRays {
     int64_t n_rays;
@@ -225,6 +227,11 @@ struct cb2_scene {
     size_t gmask_bytes;
     float* rec;
     size_t rec_bytes;
+    // optional per-kernel timing (cb2_scene_profile)
+    int prof_on;
+    double prof_ms[4];
+    int64_t prof_launches[4];
+    cudaEvent_t prof_ev[10];
 };
 
 struct cb2_rt_scene {

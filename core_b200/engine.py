@@ -60,10 +60,23 @@ class EmissionScene:
 
     def info(self):
         """Launch plan of this scene: CTA shape and the Bremsstrahlung formulation in use (cb2_scene_info)."""
-        keys = ("warps_per_cta", "bins_per_lane", "brems_mode", "moment_row", "temperature_nodes", "distinct_charges", "moment_batch_rays")
+        keys = ("warps_per_cta", "bins_per_lane", "brems_mode", "moment_row", "temperature_nodes", "distinct_charges", "batch_rays",
+                "two_kernel_line_path")
         d = {k: int(self._lib.cb2_scene_info(self._h, i)) for i, k in enumerate(keys)}
         d["brems_mode"] = {0: "none", 1: "direct", 3: "moments"}[d["brems_mode"]]
         return d
+
+    def profile(self, enable):
+        """Per-kernel device timing (cb2_scene_profile).  profile(True) starts; profile(False) stops and returns
+        {kernel: (milliseconds, launches)} accumulated since the start."""
+        if enable:
+            _abi.check(self._lib, self._lib.cb2_scene_profile(self._h, 1, None, None))
+            return None
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _abi.check(self._lib, self._lib.cb2_scene_profile(self._h, 0, ms, n))
+        names = ("state_kernel", "bin_kernel", "contract_kernel", "helpers")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
 
     def sample_state(self, points):
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)

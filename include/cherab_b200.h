@@ -284,8 +284,16 @@ int cb2_state_width(const cb2_scene* scene);
 /* Launch-plan introspection (no reference counterpart; used by the benchmark and the parity tests to report which
  * formulation a scene runs).  key: 0 warps per CTA, 1 bins per lane, 2 Bremsstrahlung formulation (0 none, 1 direct
  * per-(sample, bin) evaluation, 3 per-ray temperature moments + contraction), 3 moment row length k_pad,
- * 4 temperature nodes, 5 distinct ion charges, 6 rays per moment batch.  Returns -1 for an unknown key. */
+ * 4 temperature nodes, 5 distinct ion charges, 6 rays per batch of the two-kernel line path, 7 line path (1 two-kernel
+ * state/bin path, 0 CTA-phased kernel with the direct Bremsstrahlung evaluation).  Returns -1 for an unknown key. */
 int64_t cb2_scene_info(const cb2_scene* scene, int key);
+
+/* Per-kernel device timing for the benchmark's roofline section (no reference counterpart).  enable != 0: reset the
+ * accumulators and bracket every kernel of the following emission renders with CUDA events on the launching stream
+ * (adds one stream synchronisation per ray batch — not for production use); enable == 0: stop and, if ms_out is not
+ * NULL, return the accumulated milliseconds: [0] state_kernel, [1] bin_kernel, [2] contract_kernel,
+ * [3] count/scan helpers, and launches_out[0..3] the launch counts. */
+int cb2_scene_profile(cb2_scene* scene, int enable, double* ms_out, int64_t* launches_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Ray transfer (cherab/tools/raytransfer/emitters.pyx:88-224, raytransfer.py:183-268)
