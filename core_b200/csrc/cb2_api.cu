@@ -936,6 +936,12 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         bool has_brems = false;
         for (int m = 0; m < d->n_models; m++) has_brems |= d->models[m].kind == CB2_MODEL_BREMSSTRAHLUNG;
         S.brems.present = has_brems;
+        {
+            bool ax_only = d->axisym && d->electron_density.kind == CB2_FIELD_AXISYM_BLEND && d->electron_temperature.kind == CB2_FIELD_AXISYM_BLEND;
+            for (int i = 0; i < d->n_species; i++)
+                ax_only = ax_only && d->species[i].density.kind == CB2_FIELD_AXISYM_BLEND && d->species[i].temperature.kind == CB2_FIELD_AXISYM_BLEND;
+            sc->ax_only = ax_only;
+        }
         if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;  // decides the Bremsstrahlung mode (direct / moments)
         if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)
         bool any_stark = false;

@@ -120,6 +120,9 @@ struct AxCtx {
     float psi;
     bool in_lcfs;
     float br, bt, bz;
+    // branch-free Blend2D: value = we * edge[tri_c] + wc * core(ci, ct)
+    float we, wc;
+    int tri_c;
 };
 
 __device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py) {
@@ -196,6 +199,9 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd
     }
     if (c.m < 1.0f) c.tri = mesh_locate(A, r64, zd);
     if (c.m > 0.0f) locate1d(A.core, c.psi, c.ci, c.ct);
+    c.tri_c = max(c.tri, 0);
+    c.we = (c.m < 1.0f && c.tri >= 0) ? (c.m <= 0.f ? 1.0f : 1.0f - c.m) : 0.f;
+    c.wc = c.m > 0.f ? (c.m >= 1.0f ? 1.0f : c.m) : 0.f;
     const bool want_pol = (S.need_pol && c.m > 0.f) || S.need_b;
     if (want_pol) {
         if (!have_cell) {
@@ -214,6 +220,14 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd
             }
         }
     }
+}
+
+// Blend2D(edge, map2d(core), mask) without branches: m <= 0 -> edge, m >= 1 -> core, else (1-m) edge + m core (plasma.py:622-636)
+__device__ __forceinline__ float eval_blend(const DevScalar& f, const AxCtx& c) {
+    const float e = f.edge ? __ldg(f.edge + c.tri_c) : 0.f;
+    float cv = 0.f;
+    if (f.core) cv = horner4(__ldg(f.core + c.ci), c.ct);
+    return fmaf(c.wc, cv, c.we * e);
 }
 
 __device__ __forceinline__ float eval_scalar(const DevScalar& f, const AxCtx& c, float x, float y, float z) {
@@ -240,6 +254,13 @@ __device__ __forceinline__ float eval_scalar(const DevScalar& f, const AxCtx& c,
     }
     }
     return 0.f;
+}
+
+// AXONLY: every scalar field of the scene is an AXISYM_BLEND (decided on the host), so the kind switch disappears
+template <int AXONLY>
+__device__ __forceinline__ float eval_scalar_t(const DevScalar& f, const AxCtx& c, float x, float y, float z) {
+    if (AXONLY) return eval_blend(f, c);
+    return eval_scalar(f, c, x, y, z);
 }
 
 // cartesian velocity in plasma space
@@ -324,7 +345,7 @@ __device__ __forceinline__ double lorentz_cdf(const double2* __restrict__ tab, d
 // the spectrum follows from one dense contraction mom . phi after the ray is finished (cb2_contract.cu).
 // Lanes = samples.  Consecutive samples mostly share the node interval, so the warp loops over the distinct intervals it
 // holds and transpose-reduces the 4 n_z (<= 32) values of each; lane 4 z + k then owns node (i - 1 + k) of charge z.
-template <typename CntT>
+template <typename CntT, int AXONLY = 0>
 __device__ __forceinline__ void sample_brems_moments(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te,
                                                      double* __restrict__ mom, int lane, CntT& brems_evals, unsigned& ood) {
     const DevBrems& B = S.brems;
@@ -352,7 +373,7 @@ __device__ __forceinline__ void sample_brems_moments(const DevScene& S, const Sa
         for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] = 0.f;
 #pragma unroll 4
         for (int s = 0; s < B.n_charged; s++) {
-            const float ni = eval_scalar(S.species[B.charged[s]].density, ctx, in.x, in.y, in.z);
+            const float ni = eval_scalar_t<AXONLY>(S.species[B.charged[s]].density, ctx, in.x, in.y, in.z);
             const int zi = B.zidx[s];
             if (ni > 0.f) {
 #pragma unroll

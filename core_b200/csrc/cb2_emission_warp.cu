@@ -75,6 +75,7 @@ __device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, co
 
 // ExcitationLine / RecombinationLine .emission up to the add_line call (impact_excitation.pyx:86-100) plus the
 // component-independent part of LineShapeModel.add_line
+template <int AXONLY>
 __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M, const SampleIn& in, const AxCtx& ctx, float ne, float te,
                                             bool live, LineCache& lc, ModelCtx& mc, unsigned& ood) {
     mc.on = false;
@@ -82,8 +83,8 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
     if (on && M.species != lc.cur) {
         lc.cur = M.species;
         const DevSpecies& sp = S.species[lc.cur];
-        lc.ni = eval_scalar(sp.density, ctx, in.x, in.y, in.z);
-        lc.ts = eval_scalar(sp.temperature, ctx, in.x, in.y, in.z);
+        lc.ni = eval_scalar_t<AXONLY>(sp.density, ctx, in.x, in.y, in.z);
+        lc.ts = eval_scalar_t<AXONLY>(sp.temperature, ctx, in.x, in.y, in.z);
         const float3 v = eval_vector(sp.velocity, ctx);
         lc.vd = v.x * in.dx + v.y * in.dy + v.z * in.dz;   // velocity projected on the (unit) ray direction
     }
@@ -464,7 +465,7 @@ __global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays 
 // ------------------------------------------------------------------------------------------------------------------
 // K1a: per-sample plasma state -> line records + Bremsstrahlung moments
 // ------------------------------------------------------------------------------------------------------------------
-template <int NW, int MOM>
+template <int NW, int MOM, int AXONLY>
 __global__ void __launch_bounds__(NW * 32, 640 / (NW * 32))
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int dbg_skip) {
@@ -525,8 +526,8 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             float ne = 0.f, te = 0.f;
             if (active) {
                 ax_setup(S, pxd, pyd, pzd, ctx, ood);
-                ne = eval_scalar(S.ne, ctx, in.x, in.y, in.z);
-                te = eval_scalar(S.te, ctx, in.x, in.y, in.z);
+                ne = eval_scalar_t<AXONLY>(S.ne, ctx, in.x, in.y, in.z);
+                te = eval_scalar_t<AXONLY>(S.te, ctx, in.x, in.y, in.z);
             } else {
                 ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false;
             }
@@ -535,7 +536,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             const int64_t G = G0 + g;
             if (lane == 0) gmask[G] = live_mask;
             if (!live_mask) continue;                              // the whole group is in vacuum
-            if (MOM && dbg_skip != 2) sample_brems_moments(S, in, ctx, ne, te, mom, lane, n_brems, ood);
+            if (MOM && dbg_skip != 2) sample_brems_moments<unsigned, AXONLY>(S, in, ctx, ne, te, mom, lane, n_brems, ood);
             LineCache lc;
             lc.cur = -1; lc.ni = lc.ts = lc.vd = 0.f; lc.have_b = false; lc.bm = lc.cos_sqr = 0.f; lc.grid = -2;
             lc.lne = lc.lte = 0.f;
@@ -548,7 +549,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
                 ModelCtx mc;
-                model_setup(S, M, in, ctx, ne, te, live, lc, mc, ood);
+                model_setup<AXONLY>(S, M, in, ctx, ne, te, live, lc, mc, ood);
                 const bool any_on = __any_sync(FULL, mc.on);
                 for (int kc = 0; kc < M.ncomp; kc++) {
                     float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
@@ -599,14 +600,18 @@ bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __
     const int n_comp = S.n_comp;
     unsigned n_gauss = 0, n_lorentz = 0;
     const int64_t G0 = gbase[ray], G1 = gbase[ray + 1];
-    for (int64_t G = G0 + warp; G < G1; G += NW) {
+    for (int64_t G = G0 + warp; G < G1 && n_comp > 0; G += NW) {
         if (!__ldg(gmask + G)) continue;
         const float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
+        // software pipeline: the next component's record is in flight while this one is binned (records come from HBM/L2)
+        float amp_n = __ldg(grec + 64), cf_n = __ldg(grec), width_n = __ldg(grec + 32);
         for (int c = 0; c < n_comp; c++) {
-            const float* r = grec + (size_t)c * REC_FLOATS_PER_COMP;
-            const float amp = __ldg(r + 64);
+            const float amp = amp_n, cf = cf_n, width = width_n;
+            if (c + 1 < n_comp) {
+                const float* r = grec + (size_t)(c + 1) * REC_FLOATS_PER_COMP;
+                amp_n = __ldg(r + 64); cf_n = __ldg(r); width_n = __ldg(r + 32);
+            }
             if (!__any_sync(FULL, amp > 0.f)) continue;
-            const float cf = __ldg(r), width = __ldg(r + 32);
             component_pass<AccT, LOR>(S.comps[c].type, cf, width, amp, S.comps[c].c0_int, bins, wacc, lane, S.lorentz_tab,
                                       S.lorentz_phi_inf, n_gauss, n_lorentz);
         }
@@ -725,13 +730,17 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         // K1a
         {
             const size_t smem = moments ? (size_t)B.k_pad * sizeof(double) : 0;
-            if (moments) {
-                auto kern = state_kernel<4, 1>;
-                if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, dbg);
-            } else {
-                state_kernel<4, 0><<<dim3((unsigned)sub.n_rays), dim3(128), 0, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, nullptr, dbg);
-            }
+#define CB2_STATE(MOM, AX)                                                                                                        \
+    do {                                                                                                                          \
+        auto kern = state_kernel<4, MOM, AX>;                                                                                     \
+        if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, dbg);   \
+    } while (0)
+            if (moments && sc->ax_only) CB2_STATE(1, 1);
+            else if (moments) CB2_STATE(1, 0);
+            else if (sc->ax_only) CB2_STATE(0, 1);
+            else CB2_STATE(0, 0);
+#undef CB2_STATE
             if ((rc = cb2_cuda_check(cudaGetLastError(), "state_kernel launch")) != CB2_OK) return rc;
         }
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[2], st));

@@ -211,6 +211,7 @@ struct cb2_scene {
     // launch configuration
     int nw, bpl, smem_bytes;
     int warp_kernel;         // 1: warp-autonomous kernel (cb2_emission_warp.cu), 0: CTA-phased kernel with the direct Bremsstrahlung path
+    int ax_only;             // every scalar field of the scene is an AXISYM_BLEND: branch-free field evaluation
     int acc_f64;             // warp kernel: private accumulators in fp64 (else fp32)
     // staging buffers for the host-buffer entry point
     void* stage[8];
