@@ -990,6 +990,8 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     if (sc->rec) cudaFree(sc->rec);
     for (int i = 0; i < 10; i++)
         if (sc->prof_ev[i]) cudaEventDestroy(sc->prof_ev[i]);
+    if (sc->copy_ev) cudaEventDestroy(sc->copy_ev);
+    if (sc->copy_stream) cudaStreamDestroy(sc->copy_stream);
     free(sc);
     return CB2_OK;
 }
@@ -1075,8 +1077,19 @@ extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* ou
     if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 5, obytes)) != CB2_OK) return rc;
     if (accumulate) CB2_CUDA(cudaMemcpyAsync(sc->stage[5], out, obytes, cudaMemcpyHostToDevice, st));
     CB2_CUDA(cudaMemsetAsync(sc->stats_dev, 0, sizeof(cb2_stats), st));
-    if ((rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st)) != CB2_OK) return rc;
-    CB2_CUDA(cudaMemcpyAsync(out, sc->stage[5], obytes, cudaMemcpyDeviceToHost, st));
+    if (sc->warp_kernel) {
+        // the two-kernel path works in ray batches: each batch's rows go back to the host while the next batch computes
+        if (!sc->copy_stream) CB2_CUDA(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+        if (!sc->copy_ev) CB2_CUDA(cudaEventCreateWithFlags(&sc->copy_ev, cudaEventDisableTiming));
+        sc->d2h_host = out;
+        rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st);
+        sc->d2h_host = nullptr;
+        if (rc != CB2_OK) { cudaStreamSynchronize(sc->copy_stream); return rc; }
+        CB2_CUDA(cudaStreamSynchronize(sc->copy_stream));
+    } else {
+        if ((rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st)) != CB2_OK) return rc;
+        CB2_CUDA(cudaMemcpyAsync(out, sc->stage[5], obytes, cudaMemcpyDeviceToHost, st));
+    }
     if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
     CB2_CUDA(cudaStreamSynchronize(st));
     return CB2_OK;

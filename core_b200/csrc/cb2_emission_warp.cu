@@ -766,6 +766,13 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
             }
             sc->prof_launches[3] += 2; sc->prof_launches[0] += 1; sc->prof_launches[1] += 1; sc->prof_launches[2] += moments ? 1 : 0;
         }
+        if (sc->d2h_host) {
+            // overlap the device -> host copy of this batch's rows with the next batch's kernels
+            CB2_CUDA(cudaEventRecord(sc->copy_ev, st));
+            CB2_CUDA(cudaStreamWaitEvent(sc->copy_stream, sc->copy_ev, 0));
+            CB2_CUDA(cudaMemcpyAsync((char*)sc->d2h_host + (size_t)r0 * S.bins * esz, o, (size_t)sub.n_rays * S.bins * esz,
+                                     cudaMemcpyDeviceToHost, sc->copy_stream));
+        }
         r0 += sub.n_rays;
     }
     return CB2_OK;

@@ -228,6 +228,11 @@ struct cb2_scene {
     size_t gmask_bytes;
     float* rec;
     size_t rec_bytes;
+    // host-buffer entry point: rows of finished ray batches are copied to the caller's buffer on a second stream while
+    // the next batch computes (set for the duration of cb2_emission_render only)
+    void* d2h_host;
+    cudaStream_t copy_stream;
+    cudaEvent_t copy_ev;
     // optional per-kernel timing (cb2_scene_profile)
     int prof_on;
     double prof_ms[4];
