@@ -1077,7 +1077,8 @@ extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* ou
     if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 5, obytes)) != CB2_OK) return rc;
     if (accumulate) CB2_CUDA(cudaMemcpyAsync(sc->stage[5], out, obytes, cudaMemcpyHostToDevice, st));
     CB2_CUDA(cudaMemsetAsync(sc->stats_dev, 0, sizeof(cb2_stats), st));
-    if (sc->warp_kernel) {
+    static const bool overlap = !(getenv("CB2_D2H_OVERLAP") && atoi(getenv("CB2_D2H_OVERLAP")) == 0);
+    if (sc->warp_kernel && overlap) {
         // the two-kernel path works in ray batches: each batch's rows go back to the host while the next batch computes
         if (!sc->copy_stream) CB2_CUDA(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
         if (!sc->copy_ev) CB2_CUDA(cudaEventCreateWithFlags(&sc->copy_ev, cudaEventDisableTiming));

@@ -701,6 +701,8 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     const size_t rec_cap_bytes = (size_t)24 << 30;            // bound on the record buffer; batches shrink to respect it
     int64_t batch = std::min(cb2_warp_batch_rays(sc), rays.n_rays);
     int rc;
+    void *pend_dst = nullptr, *pend_src = nullptr;          // deferred device -> host copy of the previous batch
+    size_t pend_bytes = 0;
     for (int64_t r0 = 0; r0 < rays.n_rays;) {
         DevRays sub = rays;
         sub.n_rays = std::min(batch, rays.n_rays - r0);
@@ -718,6 +720,12 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         int64_t n_groups = 0;
         CB2_CUDA(cudaMemcpyAsync(&n_groups, sc->gbase + sub.n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CB2_CUDA(cudaStreamSynchronize(st));
+        // the previous batch's rows go to the host now: enqueued after this batch's 8-byte read-back so that the small
+        // copy never queues behind the big one on the copy engine (that stall cost the whole overlap)
+        if (pend_bytes) {
+            CB2_CUDA(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream));
+            pend_bytes = 0;
+        }
         const size_t rec_bytes = (size_t)n_groups * std::max(n_comp, 1) * REC_FLOATS_PER_COMP * sizeof(float);
         if (rec_bytes > rec_cap_bytes && sub.n_rays > 128) {     // too many samples in this batch: halve it and retry
             batch = std::max<int64_t>(128, (sub.n_rays / 2 + 127) / 128 * 128);
@@ -770,10 +778,12 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
             // overlap the device -> host copy of this batch's rows with the next batch's kernels
             CB2_CUDA(cudaEventRecord(sc->copy_ev, st));
             CB2_CUDA(cudaStreamWaitEvent(sc->copy_stream, sc->copy_ev, 0));
-            CB2_CUDA(cudaMemcpyAsync((char*)sc->d2h_host + (size_t)r0 * S.bins * esz, o, (size_t)sub.n_rays * S.bins * esz,
-                                     cudaMemcpyDeviceToHost, sc->copy_stream));
+            pend_dst = (char*)sc->d2h_host + (size_t)r0 * S.bins * esz;
+            pend_src = o;
+            pend_bytes = (size_t)sub.n_rays * S.bins * esz;
         }
         r0 += sub.n_rays;
     }
+    if (pend_bytes) CB2_CUDA(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream));
     return CB2_OK;
 }
