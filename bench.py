@@ -257,14 +257,21 @@ def main():
     # ---- e2e: host buffers through the C-ABI call (H2D rays + kernel + [NCCL gather] + D2H frame) ----
     e2e = None
     if not args.no_e2e:
-        host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
         e2e_steps = args.steps
-        # warm the staging buffers once
-        scene.render(host_rays[0], out=host_frame)
-        gathered = None
+        if world == 1:
+            host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
+            scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
+        gathered = host_full = full = None
         if world > 1:
+            # NCCL only gathers the frame: every rank's tile rows land in one device buffer on rank 0, which reads the whole
+            # frame back into pinned host memory with a single copy
             counts = [rank_pixels(args.pixels, r, world).size for r in range(world)]
-            gathered = [torch.empty((c, args.bins), dtype=torch.float32, device=dev) for c in counts] if rank == 0 else None
+            cmax = max(counts)
+            send = frame if pix.size == cmax else torch.zeros((cmax, args.bins), dtype=torch.float32, device=dev)
+            if rank == 0:
+                full = torch.empty((world * cmax, args.bins), dtype=torch.float32, device=dev)
+                gathered = [full[r * cmax:(r + 1) * cmax] for r in range(world)]
+                host_full = torch.empty((world * cmax, args.bins), dtype=torch.float32, pin_memory=True)
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -276,11 +283,13 @@ def main():
                 e2e_samples += s["samples"]
             else:
                 # per rank: rays H2D + kernel on device, gather tiles to rank 0 over NCCL, rank 0 reads the frame back
-                dr = DeviceRays(r, device=dev)
+                dr = DeviceRays(r, device=dev, pin=True)
                 scene.render_device(dr, frame, scale=1.0, accumulate=False, stats=stats)
-                dist.gather(frame, gathered, dst=0)
+                if send is not frame:
+                    send[:pix.size].copy_(frame)
+                dist.gather(send, gathered, dst=0)
                 if rank == 0:
-                    host_frame[:] = gathered[0].cpu().numpy()
+                    host_full.copy_(full, non_blocking=True)
                 torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -294,7 +303,8 @@ def main():
         h2d = sum(host_rays[(args.warmup + k) % len(host_rays)].origin.nbytes * 2 + host_rays[(args.warmup + k) % len(host_rays)].seg_offset.nbytes
                   + host_rays[(args.warmup + k) % len(host_rays)].seg_t0.nbytes * 2 for k in range(e2e_steps)) // max(e2e_steps, 1)
         e2e = {"value": e2e_samples / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(pix.size * args.bins * 4 + 48), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+               "d2h_bytes_per_step": int((pix.size if world == 1 else world * max(counts)) * args.bins * 4 + 48), "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3}
 
     if rank == 0:
         fixed = fixed_flops_per_sample(flat)

@@ -110,7 +110,8 @@ PRODUCT_SYMBOLS = [
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcherab_b200.so")
+# CB2_LIB selects an alternative in-tree build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("CB2_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcherab_b200.so")
 _lib = None
 
 

@@ -465,8 +465,11 @@ __global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays 
 // ------------------------------------------------------------------------------------------------------------------
 // K1a: per-sample plasma state -> line records + Bremsstrahlung moments
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef CB2_STATE_MINB
+#define CB2_STATE_MINB 5
+#endif
 template <int NW, int MOM, int AXONLY>
-__global__ void __launch_bounds__(NW * 32, 640 / (NW * 32))
+__global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int dbg_skip) {
     extern __shared__ double smem_d[];

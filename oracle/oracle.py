@@ -19,8 +19,15 @@ _lib = None
 def build(force=False):
     src = os.path.join(_HERE, "cb2_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "cherab_b200.h")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    # content hash, not file times: times do not survive the copy to the GPU box
+    import hashlib
+    want = hashlib.sha256(open(src, "rb").read() + open(hdr, "rb").read()).hexdigest()
+    stamp = LIB_PATH + ".sha"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if force or not os.path.exists(LIB_PATH) or have != want:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libcb2_oracle.so"], stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(want)
 
 
 def lib():
