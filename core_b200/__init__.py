@@ -10,7 +10,7 @@ from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, Synthet
 from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
-                     RecombinationLine, StarkBroadenedLine, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
+                     RecombinationLine, StarkBroadenedLine, ThermalCXLine, TotalRadiatedPower, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
 from .plasma import (AxisymBlend, AxisymBlendVector, AxisymContext, Constant3D, ConstantVector3D, EFITEquilibrium,
                      EFITMagneticField, GaussianVolume, Maxwellian, NumericalIntegrator, Plasma, SlabIonFunction,
                      SlabNeutralFunction, Species)

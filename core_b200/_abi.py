@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -19,7 +19,7 @@ STATUS_EXC = {-1: ValueError, -2: RuntimeError, -3: TypeError, -4: NotImplemente
 FIELD_CONSTANT, FIELD_GAUSSIAN_VOLUME, FIELD_AXISYM_BLEND, FIELD_SLAB_ION, FIELD_SLAB_NEUTRAL = range(5)
 SHAPE_GAUSSIAN, SHAPE_MULTIPLET, SHAPE_ZEEMAN_TRIPLET, SHAPE_PARAM_ZEEMAN, SHAPE_ZEEMAN_MULTIPLET, SHAPE_STARK = range(6)
 POL_PI, POL_SIGMA, POL_NO = range(3)
-MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG = range(3)
+MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG, MODEL_THERMAL_CX_LINE, MODEL_TOTAL_RADIATED_POWER = range(5)
 RT_CYLINDRICAL, RT_CARTESIAN = range(2)
 
 
@@ -70,9 +70,21 @@ class LineShape(C.Structure):
                 ("b_grid", c_double_p), ("zeeman_wavelength", c_double_p), ("zeeman_ratio", c_double_p)]
 
 
+class Rate3D(C.Structure):
+    _fields_ = [("n_ne", C.c_int32), ("n_te", C.c_int32), ("n_td", C.c_int32), ("_pad", C.c_int32), ("ne", c_double_p), ("te", c_double_p),
+                ("td", c_double_p), ("rate", c_double_p), ("constant", C.c_double), ("extrapolate", C.c_int32), ("_pad2", C.c_int32)]
+
+
+class ModelExt(C.Structure):
+    _fields_ = [("n_donors", C.c_int32), ("_pad", C.c_int32), ("donor_species", c_int32_p), ("donor_rates", C.POINTER(Rate3D)),
+                ("line_rad_species", C.c_int32), ("recom_species", C.c_int32), ("n_hydrogen", C.c_int32), ("has_plt", C.c_int32),
+                ("has_prb", C.c_int32), ("has_prc", C.c_int32), ("hydrogen_species", c_int32_p),
+                ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D)]
+
+
 class ModelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("species", C.c_int32), ("wavelength", C.c_double), ("atomic_weight", C.c_double),
-                ("pec", Rate2D), ("shape", LineShape)]
+                ("pec", Rate2D), ("shape", LineShape), ("ext", C.POINTER(ModelExt))]
 
 
 class SceneDesc(C.Structure):

@@ -89,6 +89,18 @@ class AtomicData:
     def recombination_pec(self, ion, charge, transition):
         raise NotImplementedError("The recombination() virtual method is not implemented for this atomic data source.")
 
+    def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+        raise NotImplementedError("The thermal_cx_pec() virtual method is not implemented for this atomic data source.")
+
+    def line_radiated_power_rate(self, ion, charge):
+        raise NotImplementedError("The line_radiated_power_rate() virtual method is not implemented for this atomic data source.")
+
+    def continuum_radiated_power_rate(self, ion, charge):
+        raise NotImplementedError("The continuum_radiated_power_rate() virtual method is not implemented for this atomic data source.")
+
+    def cx_radiated_power_rate(self, ion, charge):
+        raise NotImplementedError("The cx_radiated_power_rate() virtual method is not implemented for this atomic data source.")
+
     def free_free_gaunt_factor(self):
         """MaxwellianFreeFreeGauntFactor table (cherab/core/atomic/gaunt.pyx:143-158): (u, gamma2, gaunt_factor)."""
         t = np.load(os.path.join(_DATA, "atomic_tables.npz"))

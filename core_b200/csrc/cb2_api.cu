@@ -448,7 +448,47 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     o.shape = m.shape.kind;
     o.polarisation = m.shape.polarisation;
     if (m.kind == CB2_MODEL_BREMSSTRAHLUNG) return CB2_OK;
-    if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE)
+    if (m.kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
+        // total_radiated_power.pyx:120-163: resolved species and the three power coefficients, log-log cubic in (ne, te)
+        const cb2_model_ext* x = m.ext;
+        if (!x) return cb2_fail(CB2_ERR_RUNTIME, "TotalRadiatedPower needs its resolved species and rates");
+        if (x->line_rad_species < 0 || x->line_rad_species >= d.n_species || x->recom_species < 0 || x->recom_species >= d.n_species)
+            return cb2_fail(CB2_ERR_RUNTIME, "The plasma object does not contain the required ion species for calculating total radiated power");
+        if (x->n_hydrogen < 0 || x->n_hydrogen > 3) return cb2_fail(CB2_ERR_VALUE, "at most three hydrogen isotopes");
+        DevModelExt e;
+        memset(&e, 0, sizeof e);
+        e.line_rad = x->line_rad_species; e.recom = x->recom_species; e.n_hyd = x->n_hydrogen;
+        for (int k = 0; k < x->n_hydrogen; k++) {
+            if (x->hydrogen_species[k] < 0 || x->hydrogen_species[k] >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "hydrogen species index out of range");
+            e.hyd[k] = x->hydrogen_species[k];
+        }
+        const cb2_rate2d* r[3] = {&x->plt, &x->prb, &x->prc};
+        const int has[3] = {x->has_plt, x->has_prb, x->has_prc};
+        for (int k = 0; k < 3; k++) {
+            e.has[k] = has[k];
+            if (!has[k]) continue;
+            e.extrapolate[k] = r[k]->extrapolate;
+            if (r[k]->n_ne <= 0) {
+                e.is_const[k] = 1;
+                e.lconst[k] = r[k]->constant > 0 ? (float)(log10(r[k]->constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+                continue;
+            }
+            const int nn = r[k]->n_ne, nt = r[k]->n_te;
+            if (nn < 2 || nt < 2) return cb2_fail(CB2_ERR_VALUE, "rate tables need at least 2x2 points");
+            std::vector<double> lne(nn), lte(nt), lr((size_t)nn * nt);
+            for (int i = 0; i < nn; i++) lne[i] = log10(r[k]->ne[i]);
+            for (int j = 0; j < nt; j++) lte[j] = log10(r[k]->te[j]);
+            for (size_t q = 0; q < lr.size(); q++) {
+                if (!(r[k]->rate[q] > 0)) return cb2_fail(CB2_ERR_VALUE, "rate table values must be positive (log10 interpolation)");
+                lr[q] = log10(r[k]->rate[q]) + CB2_PEC_LOG_OFFSET;
+            }
+            e.tab[k] = make_table2d(A, lne.data(), lte.data(), lr.data(), nn, nt);
+        }
+        o.ext = A.upload(std::vector<DevModelExt>(1, e));
+        S.has_flat = 1;
+        return A.rc;
+    }
+    if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE && m.kind != CB2_MODEL_THERMAL_CX_LINE)
         return cb2_fail(CB2_ERR_TYPE, "unsupported model kind %d", m.kind);
     if (m.species < 0 || m.species >= d.n_species)
         return cb2_fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified line");
@@ -460,7 +500,24 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     for (int k = 0; k < 3; k++) o.param[k] = (float)m.shape.param[k];
     // rate table: log10(PhotonToJ(rate, wavelength)) + 38 on (log10 ne, log10 te)   (pec.pyx:59-68)
     o.pec_grid = -1;
-    if (m.pec.n_ne <= 0) {
+    if (m.kind == CB2_MODEL_THERMAL_CX_LINE) {
+        // thermal_cx.pyx:140-148: one rate per donor species; only constant rates so far
+        const cb2_model_ext* x = m.ext;
+        if (!x) return cb2_fail(CB2_ERR_RUNTIME, "ThermalCXLine needs its resolved donors");
+        if (x->n_donors < 0 || x->n_donors > CB2_MAX_SPECIES) return cb2_fail(CB2_ERR_VALUE, "too many CX donors");
+        DevModelExt e;
+        memset(&e, 0, sizeof e);
+        e.n_donors = x->n_donors;
+        for (int k = 0; k < x->n_donors; k++) {
+            if (x->donor_species[k] < 0 || x->donor_species[k] >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "donor species index out of range");
+            if (x->donor_rates[k].n_ne > 0) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "tabulated (3-D) thermal CX rates are not supported yet");
+            e.donor_species[k] = x->donor_species[k];
+            e.donor_lrate[k] = x->donor_rates[k].constant > 0 ? (float)(log10(x->donor_rates[k].constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+        }
+        o.ext = A.upload(std::vector<DevModelExt>(1, e));
+        o.pec_const = 1;
+        o.pec_value = -INFINITY;
+    } else if (m.pec.n_ne <= 0) {
         o.pec_const = 1;
         o.pec_value = (m.pec.constant > 0) ? (float)(log10(m.pec.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
     } else {
@@ -906,6 +963,7 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         S.delta = (float)S.delta_d;
         S.step = d->step;
         S.min_samples = d->min_samples;
+        S.inv_range = (float)(1.0 / (d->grid.max_wavelength - d->grid.min_wavelength));
         for (int k = 0; k < 12; k++) S.w2p[k] = d->world_to_plasma[k];
         if ((rc = convert_scalar(A, d->electron_density, d->axisym, CB2_DENSITY_SCALE, S.ne)) != CB2_OK) break;
         if ((rc = convert_scalar(A, d->electron_temperature, d->axisym, 1.0, S.te)) != CB2_OK) break;
@@ -927,8 +985,9 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         bool need_b = false;
         for (int m = 0; m < d->n_models; m++) {
             if ((rc = convert_model(A, *d, d->models[m], S, S.models[m])) != CB2_OK) break;
-            const int sh = d->models[m].shape.kind;
-            if (d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && sh != CB2_SHAPE_GAUSSIAN && sh != CB2_SHAPE_MULTIPLET) need_b = true;
+            const int sh = d->models[m].shape.kind, kd = d->models[m].kind;
+            const bool is_line = kd == CB2_MODEL_EXCITATION_LINE || kd == CB2_MODEL_RECOMBINATION_LINE || kd == CB2_MODEL_THERMAL_CX_LINE;
+            if (is_line && sh != CB2_SHAPE_GAUSSIAN && sh != CB2_SHAPE_MULTIPLET) need_b = true;
         }
         if (rc != CB2_OK) break;
         S.need_b = need_b;
@@ -946,7 +1005,8 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)
         bool any_stark = false;
         for (int m = 0; m < d->n_models; m++)
-            any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].shape.kind == CB2_SHAPE_STARK;
+            any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].kind != CB2_MODEL_TOTAL_RADIATED_POWER &&
+                         d->models[m].shape.kind == CB2_SHAPE_STARK;
         if (any_stark && (rc = build_lorentz(A, S)) != CB2_OK) break;
         if ((rc = A.rc) != CB2_OK) break;
         void* p = nullptr;
@@ -988,6 +1048,7 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     if (sc->gbase) cudaFree(sc->gbase);
     if (sc->gmask) cudaFree(sc->gmask);
     if (sc->rec) cudaFree(sc->rec);
+    if (sc->flat) cudaFree(sc->flat);
     for (int i = 0; i < 10; i++)
         if (sc->prof_ev[i]) cudaEventDestroy(sc->prof_ev[i]);
     if (sc->copy_ev) cudaEventDestroy(sc->copy_ev);

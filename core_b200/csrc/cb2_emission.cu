@@ -558,7 +558,7 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
     extern __shared__ double smem_d[];
     const DevScene& S = *Sp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncomp = S.n_comp;
+    const int ncomp = 0;   // this kernel now serves the direct Bremsstrahlung path only; line models run in cb2_emission_warp.cu
     // dynamic shared memory: fp64 per-ray accumulators [NT*BPL], records, Bremsstrahlung records, per-group bin ranges
     double* racc = smem_d;
     double* mom = smem_d + (size_t)NT * BPL;                            // [k_pad] (BREMS == 3 only)
@@ -645,7 +645,7 @@ emission_kernel(const DevScene* __restrict__ Sp, DevRays rays, void* __restrict_
                 RecWriter W;
                 W.rec = rec; W.rng = s_rng + parity * rng_stride; W.nt = NT; W.tid = tid; W.ng = NG; W.group = warp;
                 W.bins = S.bins; W.gauss_evals = 0; W.lorentz_evals = 0;
-                sample_lines(S, in, ctx, ne, te, W, ood);
+                if (ncomp > 0) sample_lines(S, in, ctx, ne, te, W, ood);
                 n_gauss += W.gauss_evals;
                 n_lorentz += W.lorentz_evals;
                 if (BREMS == 1 || BREMS == 2) sample_brems(S, in, ctx, ne, te, brec, NT, tid, n_brems, ood);
@@ -803,7 +803,7 @@ int launch_cfg(const cb2_scene* sc, const DevRays& rays, void* out, int out_f64,
                unsigned long long* stats, float* mom, cudaStream_t st) {
     const DevScene& S = sc->host;
     const int NT = NW * 32;
-    const size_t smem = emission_smem_bytes(NW, BPL, S.n_comp, S.brems);
+    const size_t smem = emission_smem_bytes(NW, BPL, 0, S.brems);
     const int mode = !S.brems.present ? 0 : (S.brems.mode == 3 ? 3 : (BPL <= 8 ? 1 : 2));
     if (rays.n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one launch");
     dim3 grid((unsigned)rays.n_rays), block(NT);
@@ -856,23 +856,27 @@ CB2_INSTANCES(CB2_INST)
 #if CB2_IN_GROUP(0)
 int cb2_emission_config(cb2_scene* sc) {
     const DevBrems& B = sc->host.brems;
-    if (!B.present || B.mode == 3) {
-        // two-kernel line path: 4 warps per ray in the bin kernel; the warps' private accumulators are fp64 while six CTAs
-        // still fit an SM (<= 1024 bins), else fp32 (a warp adds <= ~40 group sums per bin and component; the sum over
-        // the warps and the frame stay fp64)
+    {
+        // two-kernel line path (every scene's line models run through it): 4 warps per ray in the bin kernel; the warps'
+        // private accumulators are fp64 while six CTAs still fit an SM (<= 1024 bins), else fp32 (a warp adds <= ~40 group
+        // sums per bin and component; the sum over the warps and the frame stay fp64)
         int nw = 4, f64 = cb2_warp_smem_bytes(4, 1, sc->host.bins) <= 36 * 1024;
         if (cb2_warp_smem_bytes(nw, f64, sc->host.bins) > 200 * 1024) nw = 2;
         if (cb2_warp_smem_bytes(nw, f64, sc->host.bins) > 200 * 1024)
             return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins = %d is too large for the per-ray accumulators", sc->host.bins);
         if (const char* e = getenv("CB2_NW")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) nw = v; }
         if (const char* e = getenv("CB2_ACC")) f64 = !strcmp(e, "f64");
-        sc->warp_kernel = 1;
-        sc->nw = nw;
-        sc->bpl = 0;
+        sc->bin_nw = nw;
         sc->acc_f64 = f64;
         sc->host.bins_padded = (sc->host.bins + 31) & ~31;
+    }
+    if (!B.present || B.mode == 3) {
+        sc->warp_kernel = 1;
+        sc->nw = sc->bin_nw;
+        sc->bpl = 0;
         return CB2_OK;
     }
+    // direct Bremsstrahlung: the CTA-phased kernel evaluates the continuum only (lines_off), the lines take the two-kernel path
     sc->warp_kernel = 0;
     // (warps per CTA, bins per lane) instances in order of preference per spectral size; the per-sample records live in
     // shared memory (32 B x components x samples per chunk), so scenes with many components fall back to fewer warps
@@ -883,13 +887,13 @@ int cb2_emission_config(cb2_scene* sc) {
     size_t best = (size_t)-1;
     for (auto& c : cand) {
         if (c[0] * 32 * c[1] < bins) continue;
-        const size_t need = emission_smem_bytes(c[0], c[1], sc->host.n_comp, sc->host.brems);
+        const size_t need = emission_smem_bytes(c[0], c[1], 0, sc->host.brems);
         if (need <= budget) { nw = c[0]; bpl = c[1]; break; }          // first (preferred) instance that fits
         if (need < best) { best = need; nw = c[0]; bpl = c[1]; }        // otherwise the leanest one
     }
     if (!nw) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "spectral_bins > 4096 per launch is not supported yet (got %d)", bins);
-    if (emission_smem_bytes(nw, bpl, sc->host.n_comp, sc->host.brems) > 200 * 1024)
-        return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components (%d) for %d spectral bins", sc->host.n_comp, bins);
+    if (emission_smem_bytes(nw, bpl, 0, sc->host.brems) > 200 * 1024)
+        return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "%d spectral bins do not fit the continuum kernel's shared memory", bins);
     // tuning override (experiments): CB2_NW x CB2_BPL must cover the bins and be an instantiated pair
     const char *env_nw = getenv("CB2_NW"), *env_bpl = getenv("CB2_BPL");
     if (env_nw && env_bpl) {
@@ -898,7 +902,6 @@ int cb2_emission_config(cb2_scene* sc) {
     }
     sc->nw = nw;
     sc->bpl = bpl;
-    sc->host.bins_padded = nw * 32 * bpl;
     return CB2_OK;
 }
 
@@ -907,10 +910,20 @@ static int emission_batch(cb2_scene* sc, const DevRays& rays, void* out, int out
 
 int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                         unsigned long long* stats, cudaStream_t st) {
-    if (sc->warp_kernel) return cb2_launch_emission_warp(sc, rays, out, out_f64, scale, accumulate, stats, st);
+    if (sc->warp_kernel) return cb2_launch_emission_warp(sc, rays, out, out_f64, scale, accumulate, stats, 1, st);
     const DevBrems& B = sc->host.brems;
     const bool moments = B.present && B.mode == 3;
-    if (!moments) return emission_batch(sc, rays, out, out_f64, scale, accumulate, stats, nullptr, st);
+    if (!moments) {
+        // direct Bremsstrahlung: lines (and the flat TotalRadiatedPower term) through the two-kernel path, then the continuum
+        // kernel adds to the same rows; the continuum kernel counts the samples
+        int acc = accumulate;
+        if (sc->host.n_comp > 0 || sc->host.has_flat) {
+            const int rc = cb2_launch_emission_warp(sc, rays, out, out_f64, scale, accumulate, stats, 0, st);
+            if (rc != CB2_OK) return rc;
+            acc = 1;
+        }
+        return emission_batch(sc, rays, out, out_f64, scale, acc, stats, nullptr, st);
+    }
     // moment matrix [rays][k_pad] fp32: grow-only, owned by the scene handle (one stream per handle); rays are processed in
     // batches that bound it to ~1.5 GB
     const int64_t batch = std::min(cb2_moment_batch(B.k_pad), rays.n_rays);

@@ -90,15 +90,27 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
     }
     on = on && lc.ni > 0.f;
     if (!on) return;
-    // radiance = 1/(4 pi) PEC ne ni (impact_excitation.pyx:99): exp10 of (log PEC + 38) times (ne ni 1e-38)
-    float lp;
-    if (M.pec_const) lp = M.pec_value;
-    else {
-        if (M.pec_grid != lc.grid) { lc.cell = locate2d(M.pec, lc.lne, lc.lte); lc.grid = M.pec_grid; }
-        if (!lc.cell.inside && !M.pec_extrapolate) ood++;
-        lp = eval2d(M.pec, lc.cell);
+    float radiance;
+    if (M.kind == CB2_MODEL_THERMAL_CX_LINE) {
+        // radiance = 1/(4 pi) n_receiver sum_donors n_donor q_donor(ne, te, T_donor)   (thermal_cx.pyx:103-111; constant q)
+        const DevModelExt& X = *M.ext;
+        float weighted = 0.f;
+        for (int k = 0; k < X.n_donors; k++) {
+            const float nd = eval_scalar_t<AXONLY>(S.species[X.donor_species[k]].density, ctx, in.x, in.y, in.z);
+            weighted = fmaf(nd, exp10f(X.donor_lrate[k]), weighted);
+        }
+        radiance = RECIP_4_PI * weighted * lc.ni;
+    } else {
+        // radiance = 1/(4 pi) PEC ne ni (impact_excitation.pyx:99): exp10 of (log PEC + 38) times (ne ni 1e-38)
+        float lp;
+        if (M.pec_const) lp = M.pec_value;
+        else {
+            if (M.pec_grid != lc.grid) { lc.cell = locate2d(M.pec, lc.lne, lc.lte); lc.grid = M.pec_grid; }
+            if (!lc.cell.inside && !M.pec_extrapolate) ood++;
+            lp = eval2d(M.pec, lc.cell);
+        }
+        radiance = RECIP_4_PI * exp10f(lp) * ne * lc.ni;
     }
-    const float radiance = RECIP_4_PI * exp10f(lp) * ne * lc.ni;
     mc.amp = radiance * in.weight * M.inv_delta;
     if (!(mc.amp > 0.f)) return;
     mc.dop = lc.vd * M.inv_c;                                  // doppler_shift: lambda (1 + v.d/c), doppler.pyx:29-44
@@ -167,6 +179,33 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
         }
     }
     mc.on = true;
+}
+
+// TotalRadiatedPower.emission (total_radiated_power.pyx:70-118): wavelength-independent radiance of one sample
+template <int AXONLY>
+__device__ __forceinline__ float total_radiated_power(const DevScene& S, const DevModel& M, const SampleIn& in, const AxCtx& ctx, float ne,
+                                                      float lne, float lte, unsigned& ood) {
+    const DevModelExt& X = *M.ext;
+    const float ni = eval_scalar_t<AXONLY>(S.species[X.line_rad].density, ctx, in.x, in.y, in.z);
+    const float ni_upper = eval_scalar_t<AXONLY>(S.species[X.recom].density, ctx, in.x, in.y, in.z);
+    float nhyd = 0.f;
+    for (int k = 0; k < X.n_hyd; k++) nhyd += eval_scalar_t<AXONLY>(S.species[X.hyd[k]].density, ctx, in.x, in.y, in.z);
+    const float dens[3] = {ne * ni, ne * ni_upper, nhyd * ni_upper};
+    const bool use[3] = {ni > 0.f, ni_upper > 0.f, ni_upper > 0.f && nhyd > 0.f};
+    float power = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (!X.has[k] || !use[k]) continue;
+        float lp;
+        if (X.is_const[k]) lp = X.lconst[k];
+        else {
+            const Cell2 c = locate2d(X.tab[k], lne, lte);
+            if (!c.inside && !X.extrapolate[k]) ood++;
+            lp = eval2d(X.tab[k], c);
+        }
+        power = fmaf(exp10f(lp), dens[k], power);        // rates carry +38 in the exponent, densities 1e-19 each
+    }
+    return RECIP_4_PI * power * S.inv_range * in.weight;
 }
 
 // component k of model M at this sample: type (0 Gaussian, 1 modified Lorentzian), centre cf in bins relative to the
@@ -471,8 +510,10 @@ __global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays 
 template <int NW, int MOM, int AXONLY>
 __global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
-             float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int dbg_skip) {
+             float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, double* __restrict__ flat_out,
+             int count_samples, int dbg_skip) {
     extern __shared__ double smem_d[];
+    __shared__ double flat_s;
     // the flattened scene (13 KB of model / species / table descriptors, indexed with run-time model and species numbers)
     // is staged in shared memory: indexed constant-bank loads miss the small constant cache and stall (ncu: short scoreboard)
     __shared__ __align__(16) unsigned char scene_s[sizeof(DevScene)];
@@ -487,6 +528,8 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
     double* mom = smem_d;
     if (MOM)
         for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
+    if (tid == 0) flat_s = 0.0;
+    float flat_acc = 0.f;
     __syncthreads();
 
     const int64_t ray = blockIdx.x;
@@ -551,6 +594,10 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
+                if (M.kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
+                    if (live) flat_acc += total_radiated_power<AXONLY>(S, M, in, ctx, ne, lc.lne, lc.lte, ood);
+                    continue;
+                }
                 ModelCtx mc;
                 model_setup<AXONLY>(S, M, in, ctx, ne, te, live, lc, mc, ood);
                 const bool any_on = __any_sync(FULL, mc.on);
@@ -565,11 +612,17 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
         }
         G0 += n_groups;
     }
+    if (flat_out) {
+        // per-ray wavelength-independent radiance: fp32 per thread, fp64 across the CTA
+        for (int off = 16; off > 0; off >>= 1) flat_acc += __shfl_down_sync(FULL, flat_acc, off);
+        if (lane == 0 && flat_acc != 0.f) atomicAdd(&flat_s, (double)flat_acc);
+    }
+    if (MOM || flat_out) __syncthreads();
     if (MOM) {
-        __syncthreads();
         float* row = mom_out + (size_t)ray * k_pad;
         for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
     }
+    if (flat_out && tid == 0) flat_out[ray] = flat_s;
     if (stats) {
         unsigned long long nb = n_brems, oodl = ood;
         for (int off = 16; off > 0; off >>= 1) {
@@ -580,7 +633,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             if (nb) atomicAdd(stats + 3, nb);
             if (oodl) atomicAdd(stats + 5, oodl);
         }
-        if (tid == 0 && n_samples) atomicAdd(stats + 0, n_samples);
+        if (tid == 0 && n_samples && count_samples) atomicAdd(stats + 0, n_samples);
     }
 }
 
@@ -590,8 +643,8 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
 template <int NW, typename AccT, int LOR>
 __global__ void __launch_bounds__(NW * 32, 768 / (NW * 32))
 bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __restrict__ gbase, const unsigned* __restrict__ gmask,
-           const float* __restrict__ rec, void* __restrict__ out, int out_f64, double scale, int accumulate,
-           unsigned long long* __restrict__ stats) {
+           const float* __restrict__ rec, const double* __restrict__ flat, void* __restrict__ out, int out_f64, double scale,
+           int accumulate, unsigned long long* __restrict__ stats) {
     extern __shared__ double smem_d[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bins = S.bins, bins_pad = (bins + 31) & ~31;
@@ -621,8 +674,9 @@ bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __
     }
     __syncthreads();
     // the ray's spectrum: fp64 sum of the NW private accumulators, lane-consecutive bins -> coalesced rows
+    const double flat_v = flat ? flat[ray] : 0.0;
     for (int bin = tid; bin < bins; bin += NW * 32) {
-        double v = 0.0;
+        double v = flat_v;
 #pragma unroll
         for (int w = 0; w < NW; w++) v += (double)wall[(size_t)w * bins_pad + bin];
         v *= scale;
@@ -684,17 +738,17 @@ static int launch_bin(const cb2_scene* sc, int64_t n_rays, void* out, int out_f6
     if (S.has_lorentz) {
         auto kern = bin_kernel<NW, AccT, 1>;
         if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, out, out_f64, scale, accumulate, stats);
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
     } else {
         auto kern = bin_kernel<NW, AccT, 0>;
         if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, out, out_f64, scale, accumulate, stats);
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
     }
     return cb2_cuda_check(cudaGetLastError(), "bin_kernel launch");
 }
 
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
-                             unsigned long long* stats, cudaStream_t st) {
+                             unsigned long long* stats, int count_samples, cudaStream_t st) {
     const DevScene& S = sc->host;
     const DevBrems& B = S.brems;
     const bool moments = B.present && B.mode == 3;
@@ -737,6 +791,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         if ((rc = reserve(&sc->gmask, &sc->gmask_bytes, (size_t)std::max<int64_t>(n_groups, 1) * sizeof(unsigned), st)) != CB2_OK) return rc;
         if ((rc = reserve(&sc->rec, &sc->rec_bytes, std::max<size_t>(rec_bytes, 256), st)) != CB2_OK) return rc;
         if (moments && (rc = reserve(&sc->mom, &sc->mom_bytes, (size_t)sub.n_rays * B.k_pad * sizeof(float), st)) != CB2_OK) return rc;
+        if (S.has_flat && (rc = reserve(&sc->flat, &sc->flat_bytes, (size_t)sub.n_rays * sizeof(double), st)) != CB2_OK) return rc;
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[1], st));
         // K1a
         {
@@ -745,7 +800,8 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     do {                                                                                                                          \
         auto kern = state_kernel<4, MOM, AX>;                                                                                     \
         if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, dbg);   \
+        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom,                  \
+                                                                  S.has_flat ? sc->flat : nullptr, count_samples, dbg);   \
     } while (0)
             if (moments && sc->ax_only) CB2_STATE(1, 1);
             else if (moments) CB2_STATE(1, 0);
@@ -756,9 +812,9 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         }
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[2], st));
         // K1b
-        if (sc->nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
+        if (sc->bin_nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
                                           : launch_bin<8, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
-        else if (sc->nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
+        else if (sc->bin_nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
                                                : launch_bin<2, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
         else rc = sc->acc_f64 ? launch_bin<4, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
                               : launch_bin<4, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);

@@ -96,6 +96,19 @@ struct DevComp {
     int type;         // 0 gaussian, 1 lorentzian
 };
 
+// ThermalCXLine donors / TotalRadiatedPower species and rates (device memory, referenced from DevModel::ext)
+struct DevModelExt {
+    int n_donors;
+    int donor_species[CB2_MAX_SPECIES];
+    float donor_lrate[CB2_MAX_SPECIES];   // log10(rate [W m^3]) + 38, constant rates
+    int line_rad, recom, n_hyd, hyd[3];
+    int has[3];                            // plt, prb, prc present
+    int is_const[3];
+    float lconst[3];                       // log10(rate) + 38
+    int extrapolate[3];
+    DevTable2D tab[3];                     // log10 ne[m^-3], log10 te -> log10(W m^3) + 38
+};
+
 struct DevModel {
     int kind, species, shape, polarisation;
     float wavelength;     // rest wavelength (nm)
@@ -118,6 +131,7 @@ struct DevModel {
     float b0, inv_db;             // uniform |B| grid
     const float* zee_dlambda;     // [ncomp][n_b]  lambda_j(B) - lambda0
     const float* zee_ratio;       // [ncomp][n_b]
+    const DevModelExt* ext;       // THERMAL_CX_LINE / TOTAL_RADIATED_POWER
 };
 
 struct DevBrems {
@@ -174,6 +188,8 @@ struct alignas(16) DevScene {
     DevBrems brems;
     // modified-Lorentzian (Stark) cumulative profile, universal in u = (x - centre)/FWHM (stark.pyx:52-81):
     // knots u_k = k/512 on [0, 4]: (Phi(u_k), dPhi/du(u_k)); beyond u = 4 an asymptotic tail series is used
+    int has_flat;                  // some model adds a wavelength-independent radiance (TotalRadiatedPower)
+    float inv_range;               // 1 / (max_wavelength - min_wavelength)
     int has_lorentz;
     const double2* lorentz_tab;
     double lorentz_phi_inf;
@@ -209,7 +225,8 @@ struct cb2_scene {
     void** allocs;           // device allocations to free
     int n_allocs, cap_allocs;
     // launch configuration
-    int nw, bpl, smem_bytes;
+    int nw, bpl, smem_bytes;   // CTA-phased kernel (direct Bremsstrahlung)
+    int bin_nw;                // bin_kernel warps per ray
     int warp_kernel;         // 1: warp-autonomous kernel (cb2_emission_warp.cu), 0: CTA-phased kernel with the direct Bremsstrahlung path
     int ax_only;             // every scalar field of the scene is an AXISYM_BLEND: branch-free field evaluation
     int acc_f64;             // warp kernel: private accumulators in fp64 (else fp32)
@@ -228,6 +245,8 @@ struct cb2_scene {
     size_t gmask_bytes;
     float* rec;
     size_t rec_bytes;
+    double* flat;              // per-ray wavelength-independent radiance (TotalRadiatedPower)
+    size_t flat_bytes;
     // host-buffer entry point: rows of finished ray batches are copied to the caller's buffer on a second stream while
     // the next batch computes (set for the duration of cb2_emission_render only)
     void* d2h_host;
@@ -267,7 +286,7 @@ int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f
 int cb2_emission_config(cb2_scene* sc);
 size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
-                             unsigned long long* stats, cudaStream_t stream);
+                             unsigned long long* stats, int count_samples, cudaStream_t stream);
 int64_t cb2_warp_batch_rays(const cb2_scene* sc);
 int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t stream);
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate,

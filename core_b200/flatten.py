@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _abi
 from .atomic import ConstantRate, RateTable
-from .models import Bremsstrahlung, _LineModel
+from .models import Bremsstrahlung, ThermalCXLine, TotalRadiatedPower, _LineModel
 from .plasma import AxisymBlend, AxisymBlendVector, EFITMagneticField, _as_scalar_field, _as_vector_field
 
 
@@ -46,6 +46,15 @@ def _fill_rate(r, rate, keep):
         r.extrapolate = 1 if rate.extrapolate else 0
     else:
         raise TypeError("Unsupported rate object %r (expected RateTable or ConstantRate)" % (rate,))
+
+
+def _fill_rate3(r, rate, keep):
+    if isinstance(rate, ConstantRate):
+        r.n_ne = r.n_te = r.n_td = 0
+        r.constant = rate.value
+        r.extrapolate = 1
+    else:
+        raise TypeError("Unsupported thermal CX rate object %r (the B200 path accepts ConstantRate only)" % (rate,))
 
 
 def flatten_scene(plasma, min_wavelength, max_wavelength, bins, quad_rtol=1e-5, quad_min_order=1, quad_max_order=50,
@@ -122,9 +131,39 @@ def flatten_scene(plasma, min_wavelength, max_wavelength, bins, quad_rtol=1e-5, 
             mo.species = index
             mo.wavelength = wavelength
             mo.atomic_weight = m.line.element.atomic_weight
-            _fill_rate(mo.pec, rate, keep)
+            if isinstance(m, ThermalCXLine):
+                donors = m.donors(plasma, atomic)
+                ext = _abi.ModelExt()
+                ext.n_donors = len(donors)
+                idx = np.ascontiguousarray([i for i, _ in donors], dtype=np.int32)
+                rates = (_abi.Rate3D * max(1, len(donors)))()
+                for k, (_, r3) in enumerate(donors):
+                    _fill_rate3(rates[k], r3, keep)
+                ext.donor_species = idx.ctypes.data_as(_abi.c_int32_p)
+                ext.donor_rates = C.cast(rates, C.POINTER(_abi.Rate3D))
+                keep.extend([idx, rates, ext])
+                mo.ext = C.pointer(ext)
+                mo.pec.n_ne = mo.pec.n_te = 0
+                mo.pec.constant = 0.0
+            else:
+                _fill_rate(mo.pec, rate, keep)
             shape._fill(mo.shape, keep)
             keep.append(shape)
+        elif isinstance(m, TotalRadiatedPower):
+            atomic = m.atomic_data or plasma.atomic_data
+            i_line, i_recom, hyd, plt, prb, prc = m.populate(plasma, atomic)
+            ext = _abi.ModelExt()
+            ext.line_rad_species, ext.recom_species = i_line, i_recom
+            hidx = np.ascontiguousarray(hyd, dtype=np.int32)
+            ext.n_hydrogen = hidx.size
+            ext.hydrogen_species = hidx.ctypes.data_as(_abi.c_int32_p)
+            for name, rate in (("plt", plt), ("prb", prb), ("prc", prc)):
+                setattr(ext, "has_" + name, 0 if rate is None else 1)
+                if rate is not None:
+                    _fill_rate(getattr(ext, name), rate, keep)
+            keep.extend([hidx, ext])
+            mo.species = -1
+            mo.ext = C.pointer(ext)
         elif isinstance(m, Bremsstrahlung):
             mo.species = -1
             need_gaunt = m.gaunt_factor or (m.atomic_data or plasma.atomic_data).free_free_gaunt_factor()

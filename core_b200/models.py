@@ -244,6 +244,74 @@ class RecombinationLine(_LineModel):
         return "<RecombinationLine: element={}, charge={}, transition={}>".format(self.line.element.name, self.line.charge, self.line.transition)
 
 
+class ThermalCXLine(_LineModel):
+    """thermal_cx.pyx:28-163: line emission of the receiver (element, charge + 1) after thermal charge exchange with every
+    other species of the composition that is not fully ionised."""
+    kind = _abi.MODEL_THERMAL_CX_LINE
+
+    def _target(self, plasma):
+        return self.line.element, self.line.charge + 1
+
+    def _rate(self, atomic_data):
+        return None
+
+    def donors(self, plasma, atomic_data):
+        """[(species index, rate)] — thermal_cx.pyx:140-148."""
+        receiver = plasma.composition.get(self.line.element, self.line.charge + 1)
+        out = []
+        for i, sp in enumerate(plasma.composition):
+            if sp is not receiver and sp.charge < sp.element.atomic_number:
+                out.append((i, atomic_data.thermal_cx_pec(sp.element, sp.charge, self.line.element, self.line.charge + 1, self.line.transition)))
+        return out
+
+    def __repr__(self):
+        return "<ThermalCXLine: element={}, charge={}, transition={}>".format(self.line.element.name, self.line.charge, self.line.transition)
+
+
+class TotalRadiatedPower(PlasmaModel):
+    """total_radiated_power.pyx:30-175: line + recombination/continuum + charge-exchange radiated power of one charge state,
+    spread evenly over the observed spectral range."""
+    kind = _abi.MODEL_TOTAL_RADIATED_POWER
+
+    def __init__(self, element, charge, plasma=None, atomic_data=None):
+        if not 0 <= charge < element.atomic_number:
+            raise ValueError("TotalRadiatedPower cannot be calculated for charge state (element={}, ionisation={})."
+                             "".format(element.symbol, charge))
+        super().__init__(plasma, atomic_data)
+        self.element, self.charge = element, charge
+
+    def populate(self, plasma, atomic_data):
+        """total_radiated_power.pyx:120-163 -> (line_rad index, recom index, [hydrogen indices], plt, prb, prc)."""
+        from .atomic import hydrogen, deuterium, tritium
+        if plasma is None:
+            raise RuntimeError("The emission model is not connected to a plasma object.")
+        if atomic_data is None:
+            raise RuntimeError("The emission model is not connected to an atomic data source.")
+        plt = atomic_data.line_radiated_power_rate(self.element, self.charge)
+        try:
+            i_line = plasma.composition.index(self.element, self.charge)
+        except ValueError:
+            raise RuntimeError("The plasma object does not contain the required ion species for calculating"
+                               "total line radiaton, (element={}, ionisation={}).".format(self.element.symbol, self.charge))
+        prb = atomic_data.continuum_radiated_power_rate(self.element, self.charge + 1)
+        try:
+            i_recom = plasma.composition.index(self.element, self.charge + 1)
+        except ValueError:
+            raise RuntimeError("The plasma object does not contain the required ion species for calculating"
+                               "recombination/continuum emission, (element={}, ionisation={}).".format(self.element.symbol, self.charge + 1))
+        prc = atomic_data.cx_radiated_power_rate(self.element, self.charge + 1)
+        hyd = []
+        for iso in (hydrogen, deuterium, tritium):
+            try:
+                hyd.append(plasma.composition.index(iso, 0))
+            except ValueError:
+                pass
+        return i_line, i_recom, hyd, plt, prb, prc
+
+    def __repr__(self):
+        return "<TotalRadiatedPower: element={}, charge={}>".format(self.element.name, self.charge)
+
+
 class Bremsstrahlung(PlasmaModel):
     """bremsstrahlung.pyx:93-245.  ``gaunt_factor`` may be a (u, gamma2, table) triple; default: atomic_data's."""
     kind = _abi.MODEL_BREMSSTRAHLUNG

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 1
+#define CB2_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -141,6 +141,21 @@ typedef struct cb2_rate2d {
     int32_t       _pad;
 } cb2_rate2d;
 
+/* ThermalCXPEC data dict {'ne','te','td','rate'} (cherab/openadas/rates/pec.pyx:153-192): cubic in
+ * (log10 ne, log10 te, log10 td).  n_ne == 0 -> constant rate in W m^3 (mock AtomicData of
+ * core/tests/test_line_emission.py:58-84).  Tabulated 3-D rates are declared here but not yet accepted by the CUDA
+ * library (CB2_ERR_NOT_IMPLEMENTED): only the constant form is. */
+typedef struct cb2_rate3d {
+    int32_t       n_ne, n_te, n_td, _pad;
+    const double* ne;
+    const double* te;
+    const double* td;          /* [n_td] donor temperature eV */
+    const double* rate;        /* [n_ne][n_te][n_td] photon m^3 s^-1 */
+    double        constant;
+    int32_t       extrapolate;
+    int32_t       _pad2;
+} cb2_rate3d;
+
 /* Free-free Gaunt factor table (cherab/core/atomic/gaunt.pyx:87-140; data/maxwellian_free_free_gaunt_factor.json) */
 typedef struct cb2_gaunt {
     int32_t       n_u, n_gamma2;
@@ -184,17 +199,36 @@ typedef struct cb2_lineshape {
 typedef enum cb2_model_kind {
     CB2_MODEL_EXCITATION_LINE    = 0, /* ExcitationLine.emission     impact_excitation.pyx:78-100 */
     CB2_MODEL_RECOMBINATION_LINE = 1, /* RecombinationLine.emission  recombination.pyx:78-100 */
-    CB2_MODEL_BREMSSTRAHLUNG     = 2  /* Bremsstrahlung.emission     bremsstrahlung.pyx:169-208 */
+    CB2_MODEL_BREMSSTRAHLUNG     = 2, /* Bremsstrahlung.emission     bremsstrahlung.pyx:169-208 */
+    CB2_MODEL_THERMAL_CX_LINE    = 3, /* ThermalCXLine.emission      thermal_cx.pyx:79-112 */
+    CB2_MODEL_TOTAL_RADIATED_POWER = 4 /* TotalRadiatedPower.emission total_radiated_power.pyx:70-118 */
 } cb2_model_kind;
+
+/* What ThermalCXLine._populate_cache (thermal_cx.pyx:114-155) and TotalRadiatedPower._populate_cache
+ * (total_radiated_power.pyx:120-163) resolve. */
+typedef struct cb2_model_ext {
+    /* THERMAL_CX_LINE: every species except the receiver that is not fully ionised donates (thermal_cx.pyx:142-148) */
+    int32_t           n_donors, _pad;
+    const int32_t*    donor_species;     /* [n_donors] indices into the scene species */
+    const cb2_rate3d* donor_rates;       /* [n_donors] thermal_cx_pec(donor, receiver, transition) */
+    /* TOTAL_RADIATED_POWER: species (element, charge) radiates lines, (element, charge+1) recombines / exchanges charge
+     * with the neutral hydrogen isotopes present; a missing rate is flagged by has_* = 0 */
+    int32_t           line_rad_species, recom_species;
+    int32_t           n_hydrogen, has_plt, has_prb, has_prc;
+    const int32_t*    hydrogen_species;  /* [n_hydrogen] */
+    cb2_rate2d        plt, prb, prc;     /* W m^3 on (ne, te), log-log cubic (openadas/rates/radiated_power.pyx:48-76); NOT photon rates */
+} cb2_model_ext;
 
 typedef struct cb2_model {
     int32_t       kind;            /* cb2_model_kind */
     int32_t       species;         /* index into scene species: density n_target AND lineshape target species
-                                      (excitation: (element,charge); recombination: (element,charge+1) — recombination.pyx:113-121) */
+                                      (excitation: (element,charge); recombination and thermal CX: (element,charge+1) —
+                                      recombination.pyx:113-121, thermal_cx.pyx:129-136); -1 for the continuum models */
     double        wavelength;      /* rest wavelength nm (atomic_data.wavelength) */
     double        atomic_weight;   /* line.element.atomic_weight (gaussian.pyx:137 uses the LINE's element) */
     cb2_rate2d    pec;
     cb2_lineshape shape;
+    const cb2_model_ext* ext;      /* THERMAL_CX_LINE / TOTAL_RADIATED_POWER, else NULL */
 } cb2_model;
 
 /* ------------------------------------------------------------------------------------------------

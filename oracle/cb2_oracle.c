@@ -307,6 +307,20 @@ static void pec_table_build(pec_table* t, const cb2_rate2d* p, double wavelength
 }
 static void pec_table_free(pec_table* t) { free(t->lne); free(t->lte); free(t->lrate); }
 
+/* LineRadiationPower / ContinuumPower / CXRadiationPower tables: log10(rate [W m^3]) on (log10 ne, log10 te) —
+ * openadas/rates/radiated_power.pyx:48-76 (no photon-to-energy conversion) */
+static void power_table_build(pec_table* t, const cb2_rate2d* p) {
+    memset(t, 0, sizeof *t);
+    if (p->n_ne <= 0) return;
+    t->n_ne = p->n_ne; t->n_te = p->n_te;
+    t->lne = (double*)malloc(sizeof(double) * p->n_ne);
+    t->lte = (double*)malloc(sizeof(double) * p->n_te);
+    t->lrate = (double*)malloc(sizeof(double) * p->n_ne * p->n_te);
+    for (int i = 0; i < p->n_ne; i++) t->lne[i] = log10(p->ne[i]);
+    for (int j = 0; j < p->n_te; j++) t->lte[j] = log10(p->te[j]);
+    for (int k = 0; k < p->n_ne * p->n_te; k++) t->lrate[k] = log10(p->rate[k]);
+}
+
 /* ImpactExcitationPEC.evaluate — pec.pyx:70-77 */
 static double pec_eval(const pec_table* t, const cb2_rate2d* p, double ne, double te, int64_t* ood) {
     if (p->n_ne <= 0) return p->constant;
@@ -562,6 +576,7 @@ typedef struct {
     const cb2_scene_desc* d;
     axisym_ctx ax; int has_ax;
     pec_table* pec;   /* [n_models] */
+    pec_table* trp;   /* [n_models][3] TotalRadiatedPower plt, prb, prc */
     gaunt_table gaunt;
 } scene_ctx;
 
@@ -644,6 +659,17 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
             pec_table_build(&s->pec[m], &mo->pec, mo->wavelength);
         } else if (mo->kind == CB2_MODEL_BREMSSTRAHLUNG) {
             if (d->gaunt.n_u <= 0) return fail(CB2_ERR_RUNTIME, "Bremsstrahlung needs a free-free Gaunt factor table");
+        } else if (mo->kind == CB2_MODEL_THERMAL_CX_LINE) {
+            if (mo->species < 0 || mo->species >= d->n_species || !mo->ext)
+                return fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified CX line");
+            for (int k = 0; k < mo->ext->n_donors; k++)
+                if (mo->ext->donor_rates[k].n_ne > 0) return fail(CB2_ERR_NOT_IMPLEMENTED, "tabulated thermal CX rates are not supported yet");
+        } else if (mo->kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
+            if (!mo->ext) return fail(CB2_ERR_RUNTIME, "TotalRadiatedPower needs its resolved species and rates");
+            if (!s->trp) s->trp = (pec_table*)calloc(3 * (size_t)d->n_models, sizeof(pec_table));
+            if (mo->ext->has_plt) power_table_build(&s->trp[3 * m], &mo->ext->plt);
+            if (mo->ext->has_prb) power_table_build(&s->trp[3 * m + 1], &mo->ext->prb);
+            if (mo->ext->has_prc) power_table_build(&s->trp[3 * m + 2], &mo->ext->prc);
         } else return fail(CB2_ERR_TYPE, "unsupported model kind");
     }
     gaunt_table_build(&s->gaunt, &d->gaunt);
@@ -653,6 +679,7 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
 static void scene_ctx_free(scene_ctx* s) {
     if (s->has_ax) axisym_ctx_free(&s->ax);
     if (s->pec) { for (int m = 0; m < s->d->n_models; m++) pec_table_free(&s->pec[m]); free(s->pec); }
+    if (s->trp) { for (int m = 0; m < 3 * s->d->n_models; m++) pec_table_free(&s->trp[m]); free(s->trp); }
     gaunt_table_free(&s->gaunt);
 }
 
@@ -846,6 +873,33 @@ static void emission_function(const scene_ctx* s, const double p[3], const doubl
                 lower = upper;
             }
             cn->brems += d->grid.bins;
+            continue;
+        }
+        if (mo->kind == CB2_MODEL_TOTAL_RADIATED_POWER) { /* total_radiated_power.pyx:70-118 */
+            const cb2_model_ext* x = mo->ext;
+            double ni = eval_scalar(s, &d->species[x->line_rad_species].density, p, &cn->ood);
+            double ni_upper = eval_scalar(s, &d->species[x->recom_species].density, p, &cn->ood);
+            double nhyd = 0;
+            for (int k = 0; k < x->n_hydrogen; k++) nhyd += eval_scalar(s, &d->species[x->hydrogen_species[k]].density, p, &cn->ood);
+            double power = 0;
+            if (x->has_plt && ni > 0) power += pec_eval(&s->trp[3 * m], &x->plt, ne, te, &cn->ood) * ne * ni;
+            if (x->has_prb && ni_upper > 0) power += pec_eval(&s->trp[3 * m + 1], &x->prb, ne, te, &cn->ood) * ne * ni_upper;
+            if (x->has_prc && ni_upper > 0 && nhyd > 0) power += pec_eval(&s->trp[3 * m + 2], &x->prc, ne, te, &cn->ood) * nhyd * ni_upper;
+            double radiance = RECIP_4_PI * power / (d->grid.max_wavelength - d->grid.min_wavelength);
+            for (int i = 0; i < d->grid.bins; i++) samples[i] += radiance;
+            continue;
+        }
+        if (mo->kind == CB2_MODEL_THERMAL_CX_LINE) { /* thermal_cx.pyx:79-112 */
+            const cb2_model_ext* x = mo->ext;
+            double nr = eval_scalar(s, &d->species[mo->species].density, p, &cn->ood);
+            if (nr <= 0) continue;
+            double weighted = 0;
+            for (int k = 0; k < x->n_donors; k++) {
+                double nd = eval_scalar(s, &d->species[x->donor_species[k]].density, p, &cn->ood);
+                (void)eval_scalar(s, &d->species[x->donor_species[k]].temperature, p, &cn->ood);   /* constant rates ignore it */
+                weighted += nd * x->donor_rates[k].constant;
+            }
+            add_shape(s, mo, RECIP_4_PI * weighted * nr, p, dir, samples, cn);
             continue;
         }
         /* ExcitationLine / RecombinationLine — impact_excitation.pyx:86-100, recombination.pyx:86-100 */

@@ -339,3 +339,45 @@ def test_c2_balmer_series_stark():
     assert stats["samples"] == rstats["samples"]
     assert stats["lorentzian_bin_evals"] == rstats["lorentzian_bin_evals"] > 0
     assert_parity(got, ref, what="C2 balmer series (Stark)")
+
+
+# ---- ThermalCXLine / TotalRadiatedPower ----
+def test_thermal_cx_line_slab():
+    # core/tests/test_line_emission.py:241-290 through the CUDA path
+    from test_oracle_models import thermal_cx_scene
+    flat, rays, closed = thermal_cx_scene()
+    got, ref, stats, rstats = both(flat, rays)
+    assert_parity(got, closed[None, :], what="thermal CX vs closed form")
+    assert_parity(got, ref, what="thermal CX vs oracle")
+
+
+def test_total_radiated_power_slab():
+    # core/tests/test_total_radiated_power.py:90-140 through the CUDA path
+    from test_oracle_models import total_radiated_power_scene
+    flat, rays, total = total_radiated_power_scene()
+    got, ref, stats, rstats = both(flat, rays)
+    assert abs(got[0].sum() * 25.0 / total - 1.0) < 1e-6
+    assert_parity(got, ref, what="total radiated power vs oracle")
+
+
+def test_generomak_total_radiated_power_mix(brems_mode):
+    # flat TotalRadiatedPower term + a line + Bremsstrahlung on the blended Generomak profiles, both continuum formulations
+    class PowerADAS(cb.SyntheticADAS):
+        def line_radiated_power_rate(self, ion, charge):
+            return cb.ConstantRate(2.e-33)
+
+        def continuum_radiated_power_rate(self, ion, charge):
+            return cb.ConstantRate(3.e-34)
+
+        def cx_radiated_power_rate(self, ion, charge):
+            return cb.ConstantRate(1.e-31)
+
+    plasma = generomak.get_plasma()
+    plasma.atomic_data = PowerADAS()
+    plasma.models = [cb.ExcitationLine(cb.Line(cb.hydrogen, 0, (3, 2))), cb.TotalRadiatedPower(cb.carbon, 2), cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.02)
+    flat = cb.flatten_scene(plasma, 640.0, 670.0, 200)
+    rays = generomak_camera_rays(plasma, (3, 3))
+    got, ref, stats, rstats = both(flat, rays, expect_brems=brems_mode)
+    assert stats["samples"] == rstats["samples"]
+    assert_parity(got, ref, what="generomak TRP mix " + brems_mode)

@@ -4,6 +4,7 @@ cherab/core/math/tests/test_integrators.py:68-76."""
 import ctypes as C
 
 import numpy as np
+import pytest
 from scipy import constants as const
 from scipy.special import erf, roots_legendre
 
@@ -175,3 +176,70 @@ def test_bremsstrahlung_slab():
     assert np.max(np.abs(got[0] - ref)) < 1e-10
     # scipy.constants (CODATA 2022) vs the reference's hard-coded CODATA 2018 values differ by 4e-9 relative
     assert np.max(np.abs(got[0] / ref - 1)) < 2e-8
+
+
+# ---- ThermalCXLine and TotalRadiatedPower: the reference's own known-answer tests ----
+class _PowerAtomicData(cb.AtomicData):
+    """MockAtomicData of core/tests/test_total_radiated_power.py:72-87 and test_line_emission.py:58-84."""
+
+    def wavelength(self, ion, charge, transition):
+        return 529.27
+
+    def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+        return cb.ConstantRate(1.2e-46)
+
+    def line_radiated_power_rate(self, ion, charge):
+        return cb.ConstantRate(1.e-32)
+
+    def continuum_radiated_power_rate(self, ion, charge):
+        return cb.ConstantRate(1.e-33)
+
+    def cx_radiated_power_rate(self, ion, charge):
+        return cb.ConstantRate(1.e-31)
+
+
+def thermal_cx_scene():
+    # core/tests/test_line_emission.py:241-290
+    plasma = build_constant_slab_plasma(length=1.2, width=1, height=1, electron_density=1e19, electron_temperature=1000.,
+                                        plasma_species=[(cb.carbon, 6, 1.67e18, 800., (0, 0, 0)), (cb.deuterium, 0, 1.e19, 100., (0, 0, 0))],
+                                        b_field=(0, 10., 0))
+    plasma.atomic_data = _PowerAtomicData()
+    line = cb.Line(cb.carbon, 5, (8, 7))
+    plasma.models = [cb.ThermalCXLine(line)]
+    flat = cb.flatten_scene(plasma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    radiance = 0.25 / np.pi * 1.2e-46 * 1.67e18 * 1e19 * 1.2
+    sigma = np.sqrt(800. * const.e / (cb.carbon.atomic_weight * const.physical_constants["atomic mass constant"][0])) * 529.27 / const.c
+    ref = oracle.add_gaussian_line(radiance, 529.27, sigma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    return flat, rays, ref
+
+
+def total_radiated_power_scene():
+    # core/tests/test_total_radiated_power.py:90-140
+    species = [(cb.deuterium, 0, 1.e18, 500., (0, 0, 0)), (cb.hydrogen, 0, 1.e18, 500., (0, 0, 0)),
+               (cb.nitrogen, 6, 5.e18, 1100., (0, 0, 0)), (cb.nitrogen, 7, 1.e19, 1100., (0, 0, 0))]
+    plasma = build_constant_slab_plasma(length=1.2, width=1.2, height=1.2, electron_density=1e19, electron_temperature=1000., plasma_species=species)
+    plasma.atomic_data = _PowerAtomicData()
+    plasma.models = [cb.TotalRadiatedPower(cb.nitrogen, 6)]
+    flat = cb.flatten_scene(plasma, 500., 550., 2)
+    rays = cb.ray_segments(plasma.geometry, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    total = 0.25 / np.pi * 1.2 * (1.e-32 * 1e19 * 5e18 + 1.e-33 * 1e19 * 1e19 + 1.e-31 * (1e18 + 1e18) * 1e19)
+    return flat, rays, total
+
+
+def test_thermal_cx_line_slab():
+    flat, rays, ref = thermal_cx_scene()
+    got, _ = oracle.emission_render(flat, rays)
+    assert np.max(np.abs(got[0] - ref)) < 1e-8            # the reference's delta
+
+
+def test_total_radiated_power_slab():
+    flat, rays, total = total_radiated_power_scene()
+    got, _ = oracle.emission_render(flat, rays)
+    delta = 50.0 / 2
+    assert abs(got[0].sum() * delta / total - 1.0) < 1e-8  # Spectrum.total() == sum(samples) * delta_wavelength
+
+
+def test_total_radiated_power_rejects_bare_nucleus():
+    with pytest.raises(ValueError):
+        cb.TotalRadiatedPower(cb.nitrogen, 7)
