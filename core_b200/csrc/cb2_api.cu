@@ -1247,20 +1247,14 @@ extern "C" int cb2_rt_create(const cb2_rt_desc* d, int device, cb2_rt_scene** ou
         r.voxel_map = sc->voxel_map_dev;
         cudaDeviceProp prop;
         if ((rc = cb2_cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) != CB2_OK) break;
-        // persistent warps: each owns a dense double[bins] scratch row; budget 8 GiB
-        const size_t per_warp = std::max<size_t>(r.bins, 1) * sizeof(double);
-        size_t warps = (size_t)prop.multiProcessorCount * 32;
-        const size_t budget = (size_t)8 << 30;
-        while (warps > (size_t)prop.multiProcessorCount && warps * per_warp > budget) warps /= 2;
-        sc->n_warps = (int)warps;
-        // distinct sources one ray can touch: bounded by cell-boundary crossings and by bins
+        sc->n_warps = prop.multiProcessorCount * 32;
+        // distinct sources one ray can touch: bounded by the cell-boundary crossings of a straight line (each radial
+        // boundary at most twice, z and phi are monotone along the ray) and by bins
         size_t cross = (size_t)2 * r.n0 + r.n2 + 4;
-        if (r.kind == CB2_RT_CYLINDRICAL) cross += (size_t)2 * r.n1 * (size_t)ceil(360.0 / r.period) + 2;
+        if (r.kind == CB2_RT_CYLINDRICAL) cross += (size_t)r.n1 * (size_t)ceil(360.0 / r.period) + 2;
         else cross = (size_t)r.n0 + r.n1 + r.n2 + 4;
-        sc->touch_cap = (int)std::min<size_t>(std::max<size_t>(r.bins, 1), cross * 2);
-        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->scratch, warps * per_warp), "cudaMalloc(rt scratch)")) != CB2_OK) break;
-        if ((rc = cb2_cuda_check(cudaMemset(sc->scratch, 0, warps * per_warp), "cudaMemset(rt scratch)")) != CB2_OK) break;
-        if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->touched, warps * sc->touch_cap * sizeof(int32_t)), "cudaMalloc(rt touched)")) != CB2_OK) break;
+        sc->touch_cap = (int)std::min<size_t>(std::max<size_t>(r.bins, 1), cross + 4);
+        if (sc->touch_cap > 32768) { rc = cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grids with more than 32768 distinct sources per ray are not supported"); break; }
         if ((rc = cb2_cuda_check(cudaMalloc((void**)&sc->stats_dev, sizeof(cb2_stats)), "cudaMalloc(stats)")) != CB2_OK) break;
     } while (0);
     if (rc != CB2_OK) {

@@ -11,9 +11,14 @@
 // so the position -> index arithmetic is IEEE float64 with explicit _rn intrinsics in the reference's expression
 // order (no FMA contraction: the reference is compiled for x86-64 without FMA).
 //
-// Output modes: 0 dense rows (small `bins`), 1 count distinct sources per ray, 2 fill CSR rows.  Modes 1/2 use a
-// per-warp dense double[bins] scratch row in HBM (only touched entries are visited; a touched list resets them).
+// Output modes: 0 dense rows (small `bins`, rt_kernel), 1 count distinct sources per ray, 2 fill CSR rows (rt_csr_kernel).
+// The CSR modes deduplicate a ray's sources in a per-warp open-addressing hash table in SHARED memory (key -> slot in the
+// ray's CSR row; the number of distinct sources is bounded by the cell-boundary crossings of a straight line); the lengths
+// accumulate in the row itself (fp64 atomics on a few KB that stay in L2).  The first version kept a dense double[bins]
+// scratch row per warp in HBM and was latency-bound on it (ncu: long-scoreboard 50 stall cycles per issue, issue-active 7 %).
 #include <math.h>
+
+#include <algorithm>
 
 #include "cb2_internal.h"
 
@@ -136,20 +141,138 @@ rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// CSR modes: per-warp shared-memory hash (mode 1 count, mode 2 fill)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsigned)src * 2654435761u) >> (32 - hbits); }
+
+__global__ void __launch_bounds__(256)
+rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset, int32_t* __restrict__ columns,
+              double* __restrict__ lengths, int hbits, int cap, unsigned long long* __restrict__ stats) {
+    extern __shared__ int rt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int H = 1 << hbits;
+    // per warp: keys int32[H], slots uint16[H], used uint16[cap]
+    const size_t per_warp = (size_t)H * 4 + (size_t)H * 2 + (((size_t)cap * 2 + 3) & ~(size_t)3);
+    unsigned char* base = reinterpret_cast<unsigned char*>(rt_smem) + per_warp * warp;
+    int* keys = reinterpret_cast<int*>(base);
+    unsigned short* slots = reinterpret_cast<unsigned short*>(base + (size_t)H * 4);
+    unsigned short* used = reinterpret_cast<unsigned short*>(base + (size_t)H * 6);
+    for (int i = lane; i < H; i += 32) keys[i] = -1;
+    __syncwarp();
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nwarps = (int64_t)gridDim.x * wpc;
+    unsigned long long steps = 0, overflow = 0;
+
+    for (int64_t ray = gw; ray < rays.n_rays; ray += nwarps) {
+        int count = 0;
+        const int64_t off = (mode == 2) ? row_offset[ray] : 0;
+        const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+        const double dx = rays.direction[3 * ray], dy = rays.direction[3 * ray + 1], dz = rays.direction[3 * ray + 2];
+        for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+            const double t0 = rays.seg_t0[sg], t1 = rays.seg_t1[sg];
+            // start_point = far end, end_point = near end (Raysect convention), both to local space
+            const double swx = add_rn(ox, mul_rn(t1, dx)), swy = add_rn(oy, mul_rn(t1, dy)), swz = add_rn(oz, mul_rn(t1, dz));
+            const double ewx = add_rn(ox, mul_rn(t0, dx)), ewy = add_rn(oy, mul_rn(t0, dy)), ewz = add_rn(oz, mul_rn(t0, dz));
+            double st[3], en[3], dir[3];
+            for (int k = 0; k < 3; k++) {
+                st[k] = row_point(R.w2l + 4 * k, swx, swy, swz);
+                en[k] = row_point(R.w2l + 4 * k, ewx, ewy, ewz);
+                dir[k] = add_rn(en[k], -st[k]);
+            }
+            const double length = __dsqrt_rn(add_rn(add_rn(mul_rn(dir[0], dir[0]), mul_rn(dir[1], dir[1])), mul_rn(dir[2], dir[2])));
+            if (length < mul_rn(0.1, R.step)) continue;                // emitters.pyx:104-105
+            for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+            int n = (int)__ddiv_rn(length, R.step);
+            if (n < R.min_samples) n = R.min_samples;
+            const double dt = __ddiv_rn(length, (double)n);
+            if (lane == 0) steps += (unsigned long long)n;
+            for (int it0 = 0; it0 < n; it0 += 32) {
+                const int it = it0 + lane;
+                const int src = (it < n) ? rt_source(R, st, dir, dt, it) : -2;
+                const int prev = __shfl_up_sync(FULL, src, 1);
+                const bool head = (lane == 0) || (src != prev);
+                const unsigned heads = __ballot_sync(FULL, head);
+                const bool act = head && src >= 0;
+                // phase 1: find or claim the key's table position
+                int h = 0;
+                bool is_new = false;
+                if (act) {
+                    h = (int)rt_hash(src, hbits);
+                    for (;;) {
+                        const int old = atomicCAS(&keys[h], -1, src);
+                        if (old == -1) { is_new = true; break; }
+                        if (old == src) break;
+                        h = (h + 1) & (H - 1);
+                    }
+                }
+                // phase 2: new keys take consecutive slots of the ray's row
+                const unsigned nm = __ballot_sync(FULL, is_new);
+                if (is_new) {
+                    const int slot = count + __popc(nm & ((1u << lane) - 1u));
+                    if (slot < cap) {
+                        slots[h] = (unsigned short)slot;
+                        used[slot] = (unsigned short)h;
+                        if (mode == 2) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
+                    } else overflow++;
+                }
+                count += __popc(nm);
+                __syncwarp();
+                // phase 3: run length into the row
+                if (mode == 2 && act) {
+                    const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+                    const int next = higher ? (__ffs(higher) - 1) : 32;
+                    const int slot = slots[h];
+                    if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)(next - lane), dt));
+                }
+            }
+        }
+        // reset the touched table positions for the next ray
+        __syncwarp();
+        const int cnt = min(count, cap);
+        for (int pos = lane; pos < cnt; pos += 32) keys[used[pos]] = -1;
+        if (mode == 1 && lane == 0) row_offset[ray] = cnt;
+        __syncwarp();
+    }
+    if (mode == 1 && gw == 0 && lane == 0) row_offset[rays.n_rays] = 0;
+    if (stats) {
+        for (int o = 16; o > 0; o >>= 1) overflow += __shfl_down_sync(FULL, overflow, o);
+        if (lane == 0) {
+            if (steps) atomicAdd(stats + 4, steps);
+            if (overflow) atomicAdd(stats + 5, overflow);
+        }
+    }
+}
+
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate, int64_t* row_offset,
                   int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t st) {
     (void)accumulate;
-    const int threads = 256;
-    int64_t warps_needed = rays.n_rays;
-    int64_t warps = mode == 0 ? warps_needed : (warps_needed < sc->n_warps ? warps_needed : sc->n_warps);
-    if (mode == 0 && warps > (int64_t)sc->n_warps * 4) warps = (int64_t)sc->n_warps * 4;
-    int64_t blocks = (warps * 32 + threads - 1) / threads;
-    if (mode != 0 && blocks * (threads / 32) > sc->n_warps) blocks = sc->n_warps / (threads / 32);
+    if (mode == 0) {
+        const int threads = 256;
+        int64_t warps = rays.n_rays;
+        if (warps > (int64_t)sc->n_warps * 4) warps = (int64_t)sc->n_warps * 4;
+        int64_t blocks = (warps * 32 + threads - 1) / threads;
+        if (blocks < 1) blocks = 1;
+        rt_kernel<<<(unsigned)blocks, threads, 0, st>>>(sc->rt, rays, mode, dense_out, row_offset, columns, lengths, nullptr, nullptr,
+                                                        sc->touch_cap, stats_dev);
+        return cb2_cuda_check(cudaGetLastError(), "rt_kernel launch");
+    }
+    // CSR: per-warp hash table in shared memory sized from the bound on distinct sources per ray
+    const int cap = sc->touch_cap;
+    int hbits = 8;
+    while ((1 << hbits) < 2 * cap && hbits < 16) hbits++;
+    const size_t per_warp = ((size_t)6 << hbits) + (((size_t)cap * 2 + 3) & ~(size_t)3);
+    int wpc = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+    if (wpc < 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grid too large for the shared-memory source table (%d distinct sources per ray)", cap);
+    const size_t smem = per_warp * wpc;
+    CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device);
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+    int64_t blocks = std::min<int64_t>((rays.n_rays + wpc - 1) / wpc, (int64_t)sms * ctas_per_sm);
     if (blocks < 1) blocks = 1;
-    rt_kernel<<<(unsigned)blocks, threads, 0, st>>>(sc->rt, rays, mode, dense_out, row_offset, columns, lengths,
-                                                    mode == 0 ? nullptr : sc->scratch, mode == 0 ? nullptr : sc->touched,
-                                                    sc->touch_cap, stats_dev);
-    return cb2_cuda_check(cudaGetLastError(), "rt_kernel launch");
+    rt_csr_kernel<<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+    return cb2_cuda_check(cudaGetLastError(), "rt_csr_kernel launch");
 }
 
 // in-place exclusive scan of int64 counts (single block; n is at most a few million rays)
