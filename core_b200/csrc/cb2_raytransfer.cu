@@ -147,7 +147,7 @@ rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* 
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsigned)src * 2654435761u) >> (32 - hbits); }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset, int32_t* __restrict__ columns,
               double* __restrict__ lengths, int hbits, int cap, unsigned long long* __restrict__ stats) {
     extern __shared__ int rt_smem[];
@@ -260,9 +260,9 @@ int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double*
     // CSR: per-warp hash table in shared memory sized from the bound on distinct sources per ray
     const int cap = sc->touch_cap;
     int hbits = 8;
-    while ((1 << hbits) < 2 * cap && hbits < 16) hbits++;
+    while ((1 << hbits) < cap + cap / 4 + 8 && hbits < 16) hbits++;     // load factor <= 0.8 even for a ray that reaches the bound
     const size_t per_warp = ((size_t)6 << hbits) + (((size_t)cap * 2 + 3) & ~(size_t)3);
-    int wpc = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+    int wpc = (int)std::min<size_t>(16, (208 * 1024) / per_warp);
     if (wpc < 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grid too large for the shared-memory source table (%d distinct sources per ray)", cap);
     const size_t smem = per_warp * wpc;
     CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
