@@ -11,8 +11,9 @@ from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
                      RecombinationLine, StarkBroadenedLine, ThermalCXLine, TotalRadiatedPower, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
+from .notify import Notifier
 from .plasma import (AxisymBlend, AxisymBlendVector, AxisymContext, Constant3D, ConstantVector3D, EFITEquilibrium,
-                     EFITMagneticField, GaussianVolume, Maxwellian, NumericalIntegrator, Plasma, SlabIonFunction,
+                     EFITMagneticField, GaussianVolume, Maxwellian, ModelManager, NumericalIntegrator, Plasma, SlabIonFunction,
                      SlabNeutralFunction, Species)
 
 __version__ = "0.1.0"

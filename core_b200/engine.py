@@ -87,6 +87,45 @@ class EmissionScene:
         return out
 
 
+class PlasmaRenderer:
+    """The scene-plumbing seam: keeps the device scene of a Plasma for one spectral grid and rebuilds it
+    only after the plasma told its notifier that something changed (Plasma._modified, cherab/core/plasma/node.pyx:545-554 —
+    composition, models, distributions, geometry, integrator, atomic data).  The flattening that the reference spreads
+    over every model's lazy ``_populate_cache`` happens once per change, on the first render after it."""
+
+    def __init__(self, plasma, min_wavelength, max_wavelength, bins, device=0, **flatten_kwargs):
+        self.plasma = plasma
+        self.grid = (float(min_wavelength), float(max_wavelength), int(bins))
+        self.device = int(device)
+        self.flatten_kwargs = flatten_kwargs
+        self._scene = None
+        self.rebuilds = 0
+        plasma.notifier.add(self._invalidate)
+
+    def _invalidate(self):
+        if self._scene is not None:
+            self._scene.close()
+        self._scene = None
+
+    @property
+    def scene(self):
+        if self._scene is None:
+            from .flatten import flatten_scene
+            self._scene = EmissionScene(flatten_scene(self.plasma, *self.grid, **self.flatten_kwargs), device=self.device)
+            self.rebuilds += 1
+        return self._scene
+
+    def render(self, rays, **kw):
+        return self.scene.render(rays, **kw)
+
+    def render_device(self, dev_rays, out, **kw):
+        return self.scene.render_device(dev_rays, out, **kw)
+
+    def close(self):
+        self.plasma.notifier.remove(self._invalidate)
+        self._invalidate()
+
+
 class DeviceRays:
     """A RayBatch resident in device memory (torch tensors)."""
 

@@ -7,6 +7,8 @@ no CPU fallback).  An unsupported field raises TypeError at flatten time.
 """
 import numpy as np
 
+from .notify import Notifier
+
 from . import _abi
 
 
@@ -235,10 +237,11 @@ class NumericalIntegrator:
 
 
 class Composition:
-    """cherab/core/plasma/node.pyx:33-163 (set/add/get/clear by (element, charge))."""
+    """cherab/core/plasma/node.pyx:33-163 (set/add/get/clear by (element, charge)); every change notifies (:75,:96,:141)."""
 
     def __init__(self):
         self._species = []
+        self.notifier = Notifier()
 
     def __iter__(self):
         return iter(self._species)
@@ -253,11 +256,16 @@ class Composition:
                 raise TypeError("The composition must consist of a sequence of Species objects.")
         self._species = []
         for s in species:
-            self.add(s)
+            self._species = [o for o in self._species if not (o.element is s.element and o.charge == s.charge)]
+            self._species.append(s)
+        self.notifier.notify()
 
     def add(self, species):
+        if not isinstance(species, Species):
+            raise TypeError("Only Species objects can be added to a composition.")
         self._species = [s for s in self._species if not (s.element is species.element and s.charge == species.charge)]
         self._species.append(species)
+        self.notifier.notify()
 
     def get(self, element, charge):
         for s in self._species:
@@ -273,24 +281,83 @@ class Composition:
 
     def clear(self):
         self._species = []
+        self.notifier.notify()
+
+
+class ModelManager:
+    """cherab/core/plasma/node.pyx:166-198: the list of emission models attached to a plasma; every change notifies."""
+
+    def __init__(self):
+        self._models = []
+        self.notifier = Notifier()
+
+    def __iter__(self):
+        return iter(self._models)
+
+    def __len__(self):
+        return len(self._models)
+
+    def __getitem__(self, i):
+        return self._models[i]
+
+    def set(self, models):
+        models = list(models)
+        for m in models:
+            if not hasattr(m, "kind"):
+                raise TypeError("The model list must consist of only PlasmaModel objects.")
+        self._models = models
+        self.notifier.notify()
+
+    def add(self, model):
+        if not hasattr(model, "kind"):
+            raise TypeError("The model list must consist of only PlasmaModel objects.")
+        self._models.append(model)
+        self.notifier.notify()
+
+    def clear(self):
+        self._models = []
+        self.notifier.notify()
 
 
 class Plasma:
     """cherab/core/plasma/node.pyx:201-554, Raysect-free: geometry is a primitive from core_b200.geometry,
     geometry_transform a 4x4 (or 3x4) world<-plasma affine matrix."""
 
+    # attributes whose change invalidates anything cached from this plasma (node.pyx:323-331, 464-509, 545-554)
+    _NOTIFYING = ("b_field", "electron_distribution", "atomic_data", "geometry", "geometry_transform", "transform", "integrator", "axisym")
+
     def __init__(self, name="Plasma"):
+        self.__dict__["notifier"] = Notifier()
         self.name = name
+        self._composition = Composition()
+        self._composition.notifier.add(self._modified)
+        self._models = ModelManager()
+        self._models.notifier.add(self._modified)
         self.b_field = ConstantVector3D(0, 0, 0)
         self.electron_distribution = None
-        self._composition = Composition()
-        self.models = []
         self.atomic_data = None
         self.geometry = None
         self.geometry_transform = None  # geometry-local -> plasma space (node.pyx:535-540)
         self.transform = None           # plasma space -> world (the Node transform); None = identity
         self.integrator = NumericalIntegrator(step=0.001)
         self.axisym = None
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in self._NOTIFYING:
+            self._modified()
+
+    def _modified(self):
+        """Plasma._modified (node.pyx:545-554): tell every registered observer that cached data is stale."""
+        self.notifier.notify()
+
+    @property
+    def models(self):
+        return self._models
+
+    @models.setter
+    def models(self, values):
+        self._models.set(values)
 
     def geometry_to_world(self):
         """4x4 matrix taking the geometry primitive's local frame to world space."""
