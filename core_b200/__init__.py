@@ -12,6 +12,7 @@ from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_s
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
                      RecombinationLine, StarkBroadenedLine, ThermalCXLine, TotalRadiatedPower, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
 from .notify import Notifier
+from .openadas import OpenADAS
 from .plasma import (AxisymBlend, AxisymBlendVector, AxisymContext, Constant3D, ConstantVector3D, EFITEquilibrium,
                      EFITMagneticField, GaussianVolume, Maxwellian, ModelManager, NumericalIntegrator, Plasma, SlabIonFunction,
                      SlabNeutralFunction, Species)

@@ -33,7 +33,12 @@ class FlatScene:
 
 
 def _fill_rate(r, rate, keep):
-    if isinstance(rate, ConstantRate):
+    if rate is None:
+        # a Null rate (OpenADAS(missing_rates_return_null=True), openadas/rates/pec.pyx:80-90): always zero
+        r.n_ne = r.n_te = 0
+        r.constant = 0.0
+        r.extrapolate = 1
+    elif isinstance(rate, ConstantRate):
         r.n_ne = r.n_te = 0
         r.constant = rate.value
         r.extrapolate = 1
