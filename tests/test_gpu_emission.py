@@ -381,3 +381,48 @@ def test_generomak_total_radiated_power_mix(brems_mode):
     got, ref, stats, rstats = both(flat, rays, expect_brems=brems_mode)
     assert stats["samples"] == rstats["samples"]
     assert_parity(got, ref, what="generomak TRP mix " + brems_mode)
+
+
+# ---- ragged / empty inputs and ray batching of the two-kernel pipeline ----
+def test_ragged_rays_and_batch_splitting(monkeypatch):
+    """Rays that miss the plasma (no segments), zero-length segments and two-segment rays, rendered in one batch and
+    in batches of 128 rays: identical results, identical counters; an empty ray set is a no-op."""
+    plasma = generomak.get_plasma()
+    lines = [cb.Line(cb.hydrogen, 0, (3, 2))]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.01)
+    flat = cb.flatten_scene(plasma, 640.0, 670.0, 100)
+    # a wide camera inside the vessel (rays crossing the central hole have two segments) plus rays that miss the plasma
+    cam = cb.PinholeCamera((20, 20), fov=120, transform=cb.look_at((2.3, 0, 1.25), (1.0, 0.8, -0.5)))
+    o, d = cam.rays()
+    o = np.concatenate([o[:150], np.tile([[0.0, 0.0, 10.0]], (7, 1)), o[150:]])
+    d = np.concatenate([d[:150], np.tile([[0.0, 0.0, 1.0]], (7, 1)), d[150:]])
+    rays = cb.ray_segments(plasma.geometry, o, d, plasma.geometry_to_world())
+    nseg = np.diff(rays.seg_offset)
+    assert (nseg == 0).any() and (nseg >= 1).any()
+    # add a degenerate zero-length segment to the first ray that has one
+    r0 = int(np.argmax(nseg >= 1))
+    t0, t1 = rays.seg_t0.copy(), rays.seg_t1.copy()
+    s0 = rays.seg_offset[r0]
+    seg_t0 = np.insert(t0, s0, t0[s0])
+    seg_t1 = np.insert(t1, s0, t0[s0])
+    off = rays.seg_offset.copy()
+    off[r0 + 1:] += 1
+    rays = cb.RayBatch(rays.origin, rays.direction, off, seg_t0, seg_t1)
+    scene = EmissionScene(flat)
+    one, st_one = scene.render(rays)
+    monkeypatch.setenv("CB2_BATCH_RAYS", "128")
+    many, st_many = scene.render(rays)
+    acc = one.copy()
+    scene.render(rays, out=acc, scale=2.0, accumulate=True)
+    empty = cb.RayBatch(np.zeros((0, 3)), np.zeros((0, 3)) + [1.0, 0, 0], [0], [], [])
+    e, st_e = scene.render(empty)
+    scene.close()
+    monkeypatch.delenv("CB2_BATCH_RAYS")
+    ref, rst = oracle.emission_render(flat, rays)
+    assert e.shape == (0, 100) and st_e["samples"] == 0
+    assert st_one == st_many and st_one["samples"] == rst["samples"]
+    assert np.allclose(one, many, rtol=1e-12, atol=0)          # same kernels, fp64 atomics order aside
+    assert np.all(one[nseg == 0] == 0.0)
+    assert_parity(one, ref, what="ragged rays")
+    assert_parity(acc, 3.0 * ref, what="ragged rays, accumulate over batches")
