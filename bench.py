@@ -261,35 +261,46 @@ def main():
         if world == 1:
             host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
             scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
-        gathered = host_full = full = None
+        n_chunks = 4
         if world > 1:
-            # NCCL only gathers the frame: every rank's tile rows land in one device buffer on rank 0, which reads the whole
-            # frame back into pinned host memory with a single copy
+            # NCCL only gathers the frame.  The rank's rays are cut into chunks: while chunk c+1 renders, chunk c is gathered
+            # into one device buffer on rank 0 (NCCL stream) and read back into pinned host memory (copy stream), so the
+            # single PCIe link of rank 0 works in the shadow of the compute.
             counts = [rank_pixels(args.pixels, r, world).size for r in range(world)]
-            cmax = max(counts)
-            send = frame if pix.size == cmax else torch.zeros((cmax, args.bins), dtype=torch.float32, device=dev)
+            cmax = -(-max(counts) // n_chunks)                 # rows per chunk (last chunk of a rank may be shorter: padded)
+            bounds = [min(c * cmax, pix.size) for c in range(n_chunks + 1)]
+            chunk_rays = [[hr.subset(np.arange(bounds[c], bounds[c + 1])) for c in range(n_chunks)] for hr in host_rays]
+            send = [torch.zeros((cmax, args.bins), dtype=torch.float32, device=dev) for _ in range(n_chunks)]
+            full = host_full = gathered = None
             if rank == 0:
-                full = torch.empty((world * cmax, args.bins), dtype=torch.float32, device=dev)
-                gathered = [full[r * cmax:(r + 1) * cmax] for r in range(world)]
-                host_full = torch.empty((world * cmax, args.bins), dtype=torch.float32, pin_memory=True)
+                full = [torch.empty((world * cmax, args.bins), dtype=torch.float32, device=dev) for _ in range(n_chunks)]
+                gathered = [[f[r * cmax:(r + 1) * cmax] for r in range(world)] for f in full]
+                host_full = torch.empty((n_chunks, world * cmax, args.bins), dtype=torch.float32, pin_memory=True)
+            copy_stream = torch.cuda.Stream(device=dev)
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e2e_samples = 0
         for k in range(e2e_steps):
-            r = host_rays[(args.warmup + k) % len(host_rays)]
             if world == 1:
+                r = host_rays[(args.warmup + k) % len(host_rays)]
                 _, s = scene.render(r, out=host_frame)
                 e2e_samples += s["samples"]
             else:
-                # per rank: rays H2D + kernel on device, gather tiles to rank 0 over NCCL, rank 0 reads the frame back
-                dr = DeviceRays(r, device=dev, pin=True)
-                scene.render_device(dr, frame, scale=1.0, accumulate=False, stats=stats)
-                if send is not frame:
-                    send[:pix.size].copy_(frame)
-                dist.gather(send, gathered, dst=0)
-                if rank == 0:
-                    host_full.copy_(full, non_blocking=True)
+                works = []
+                for c in range(n_chunks):
+                    rc_ = chunk_rays[(args.warmup + k) % len(host_rays)][c]
+                    if rc_.n_rays:
+                        dr = DeviceRays(rc_, device=dev)
+                        scene.render_device(dr, send[c][:rc_.n_rays], scale=1.0, accumulate=False, stats=stats)
+                    w = dist.gather(send[c], gathered[c] if rank == 0 else None, dst=0, async_op=True)
+                    if rank == 0:
+                        with torch.cuda.stream(copy_stream):
+                            w.wait()                              # the copy stream (not the compute stream) waits for the gather
+                            host_full[c].copy_(full[c], non_blocking=True)
+                    works.append(w)
+                for w in works:
+                    w.wait()
                 torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -303,7 +314,7 @@ def main():
         h2d = sum(host_rays[(args.warmup + k) % len(host_rays)].origin.nbytes * 2 + host_rays[(args.warmup + k) % len(host_rays)].seg_offset.nbytes
                   + host_rays[(args.warmup + k) % len(host_rays)].seg_t0.nbytes * 2 for k in range(e2e_steps)) // max(e2e_steps, 1)
         e2e = {"value": e2e_samples / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int((pix.size if world == 1 else world * max(counts)) * args.bins * 4 + 48), "steps": e2e_steps,
+               "d2h_bytes_per_step": int((pix.size if world == 1 else n_chunks * world * cmax) * args.bins * 4 + 48), "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3}
 
     if rank == 0:
