@@ -196,6 +196,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the frame gather overlaps the next chunk's kernels: keep NCCL's (spin-waiting) send/recv kernels on a few SMs
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
+        os.environ.setdefault("NCCL_MIN_CTAS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     plasma, flat = build_scene(args.bins)
@@ -261,7 +264,7 @@ def main():
         if world == 1:
             host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
             scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
-        n_chunks = 4
+        n_chunks = 8
         if world > 1:
             # NCCL only gathers the frame.  The rank's rays are cut into chunks: while chunk c+1 renders, chunk c is gathered
             # into one device buffer on rank 0 (NCCL stream) and read back into pinned host memory (copy stream), so the
@@ -276,7 +279,10 @@ def main():
                 full = [torch.empty((world * cmax, args.bins), dtype=torch.float32, device=dev) for _ in range(n_chunks)]
                 gathered = [[f[r * cmax:(r + 1) * cmax] for r in range(world)] for f in full]
                 host_full = torch.empty((n_chunks, world * cmax, args.bins), dtype=torch.float32, pin_memory=True)
+            # neither the compute nor the copy may run on the legacy default stream: it synchronises implicitly with every
+            # other blocking stream, which would serialise render, gather and read-back
             copy_stream = torch.cuda.Stream(device=dev)
+            compute_stream = torch.cuda.Stream(device=dev)
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -288,19 +294,20 @@ def main():
                 e2e_samples += s["samples"]
             else:
                 works = []
-                for c in range(n_chunks):
-                    rc_ = chunk_rays[(args.warmup + k) % len(host_rays)][c]
-                    if rc_.n_rays:
-                        dr = DeviceRays(rc_, device=dev)
-                        scene.render_device(dr, send[c][:rc_.n_rays], scale=1.0, accumulate=False, stats=stats)
-                    w = dist.gather(send[c], gathered[c] if rank == 0 else None, dst=0, async_op=True)
-                    if rank == 0:
-                        with torch.cuda.stream(copy_stream):
-                            w.wait()                              # the copy stream (not the compute stream) waits for the gather
-                            host_full[c].copy_(full[c], non_blocking=True)
-                    works.append(w)
-                for w in works:
-                    w.wait()
+                with torch.cuda.stream(compute_stream):
+                    for c in range(n_chunks):
+                        rc_ = chunk_rays[(args.warmup + k) % len(host_rays)][c]
+                        if rc_.n_rays:
+                            dr = DeviceRays(rc_, device=dev)
+                            scene.render_device(dr, send[c][:rc_.n_rays], scale=1.0, accumulate=False, stats=stats)
+                        w = dist.gather(send[c], gathered[c] if rank == 0 else None, dst=0, async_op=True)
+                        if rank == 0:
+                            with torch.cuda.stream(copy_stream):
+                                w.wait()                          # the copy stream (not the compute stream) waits for the gather
+                                host_full[c].copy_(full[c], non_blocking=True)
+                        works.append(w)
+                    for w in works:
+                        w.wait()
                 torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

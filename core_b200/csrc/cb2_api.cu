@@ -1049,6 +1049,7 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     if (sc->gmask) cudaFree(sc->gmask);
     if (sc->rec) cudaFree(sc->rec);
     if (sc->flat) cudaFree(sc->flat);
+    if (sc->total_host) cudaFreeHost(sc->total_host);
     for (int i = 0; i < 10; i++)
         if (sc->prof_ev[i]) cudaEventDestroy(sc->prof_ev[i]);
     if (sc->copy_ev) cudaEventDestroy(sc->copy_ev);

@@ -498,6 +498,10 @@ __global__ void count_groups_kernel(const __grid_constant__ DevScene S, DevRays 
     counts[ray] = n;
 }
 
+// the scan's total goes to a host-mapped word: a device->host memcpy of 8 bytes would queue on the copy engine behind a
+// frame read-back that may be in flight on another stream and stall the next batch
+__global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile int64_t* __restrict__ dst) { *dst = *src; }
+
 // record layout: rec[((group * n_comp + comp) * 3 + field) * 32 + lane], field 0 centre, 1 width, 2 amplitude
 #define REC_FLOATS_PER_COMP 96
 
@@ -774,9 +778,13 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         count_groups_kernel<<<(unsigned)((sub.n_rays + 1 + 127) / 128), 128, 0, st>>>(S, sub, sc->gbase);
         if ((rc = cb2_cuda_check(cudaGetLastError(), "count_groups_kernel launch")) != CB2_OK) return rc;
         if ((rc = cb2_launch_scan(sc->gbase, sub.n_rays + 1, st)) != CB2_OK) return rc;
-        int64_t n_groups = 0;
-        CB2_CUDA(cudaMemcpyAsync(&n_groups, sc->gbase + sub.n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        if (!sc->total_host) {
+            CB2_CUDA(cudaHostAlloc((void**)&sc->total_host, sizeof(int64_t), cudaHostAllocMapped));
+            CB2_CUDA(cudaHostGetDevicePointer((void**)&sc->total_dev, sc->total_host, 0));
+        }
+        publish_total_kernel<<<1, 1, 0, st>>>(sc->gbase + sub.n_rays, sc->total_dev);
         CB2_CUDA(cudaStreamSynchronize(st));
+        const int64_t n_groups = *(volatile int64_t*)sc->total_host;
         // the previous batch's rows go to the host now: enqueued after this batch's 8-byte read-back so that the small
         // copy never queues behind the big one on the copy engine (that stall cost the whole overlap)
         if (pend_bytes) {

@@ -247,6 +247,8 @@ struct cb2_scene {
     size_t rec_bytes;
     double* flat;              // per-ray wavelength-independent radiance (TotalRadiatedPower)
     size_t flat_bytes;
+    int64_t* total_host;       // pinned, device-mapped word: the batch's group total reaches the host without a copy-engine transfer
+    int64_t* total_dev;
     // host-buffer entry point: rows of finished ray batches are copied to the caller's buffer on a second stream while
     // the next batch computes (set for the duration of cb2_emission_render only)
     void* d2h_host;
