@@ -7,6 +7,8 @@ No CPU fallback: calls fail loudly if the CUDA library or a GPU is missing.
 """
 from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, SyntheticADAS, carbon, deuterium, helium,
                      hydrogen, neon, nitrogen, tritium)
+from .beam import (Beam, BeamCXLine, BeamCXTable, BeamStoppingTable, ConstantBeamCXPEC, SingleRayAttenuator, beam_ray_segments,
+                   flatten_beam_scene)
 from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,

@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -19,7 +19,7 @@ STATUS_EXC = {-1: ValueError, -2: RuntimeError, -3: TypeError, -4: NotImplemente
 FIELD_CONSTANT, FIELD_GAUSSIAN_VOLUME, FIELD_AXISYM_BLEND, FIELD_SLAB_ION, FIELD_SLAB_NEUTRAL = range(5)
 SHAPE_GAUSSIAN, SHAPE_MULTIPLET, SHAPE_ZEEMAN_TRIPLET, SHAPE_PARAM_ZEEMAN, SHAPE_ZEEMAN_MULTIPLET, SHAPE_STARK = range(6)
 POL_PI, POL_SIGMA, POL_NO = range(3)
-MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG, MODEL_THERMAL_CX_LINE, MODEL_TOTAL_RADIATED_POWER = range(5)
+MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG, MODEL_THERMAL_CX_LINE, MODEL_TOTAL_RADIATED_POWER, MODEL_BEAM_CX_LINE = range(6)
 RT_CYLINDRICAL, RT_CARTESIAN = range(2)
 
 
@@ -75,11 +75,30 @@ class Rate3D(C.Structure):
                 ("td", c_double_p), ("rate", c_double_p), ("constant", C.c_double), ("extrapolate", C.c_int32), ("_pad2", C.c_int32)]
 
 
+class BeamRate(C.Structure):
+    _fields_ = [("n_e", C.c_int32), ("n_n", C.c_int32), ("n_t", C.c_int32), ("_pad", C.c_int32), ("e", c_double_p), ("n", c_double_p),
+                ("t", c_double_p), ("sen", c_double_p), ("st", c_double_p), ("sref", C.c_double), ("constant", C.c_double)]
+
+
+class CXRate(C.Structure):
+    _fields_ = [("n_eb", C.c_int32), ("n_ti", C.c_int32), ("n_ni", C.c_int32), ("n_z", C.c_int32), ("n_b", C.c_int32), ("_pad", C.c_int32),
+                ("eb", c_double_p), ("ti", c_double_p), ("ni", c_double_p), ("z", c_double_p), ("b", c_double_p),
+                ("qeb", c_double_p), ("qti", c_double_p), ("qni", c_double_p), ("qz", c_double_p), ("qb", c_double_p),
+                ("qref", C.c_double), ("constant", C.c_double)]
+
+
+class BeamDesc(C.Structure):
+    _fields_ = [("beam_to_plasma", C.c_double * 12), ("energy", C.c_double), ("power", C.c_double), ("temperature", C.c_double),
+                ("atomic_weight", C.c_double), ("sigma", C.c_double), ("divergence_x", C.c_double), ("divergence_y", C.c_double),
+                ("length", C.c_double), ("attenuator_step", C.c_double), ("clamp_sigma", C.c_double), ("clamp_to_zero", C.c_int32),
+                ("n_stopping", C.c_int32), ("stopping_species", c_int32_p), ("stopping_rates", C.POINTER(BeamRate))]
+
+
 class ModelExt(C.Structure):
     _fields_ = [("n_donors", C.c_int32), ("_pad", C.c_int32), ("donor_species", c_int32_p), ("donor_rates", C.POINTER(Rate3D)),
                 ("line_rad_species", C.c_int32), ("recom_species", C.c_int32), ("n_hydrogen", C.c_int32), ("has_plt", C.c_int32),
                 ("has_prb", C.c_int32), ("has_prc", C.c_int32), ("hydrogen_species", c_int32_p),
-                ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D)]
+                ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D), ("n_cx", C.c_int32), ("_pad3", C.c_int32), ("cx", C.POINTER(CXRate))]
 
 
 class ModelDesc(C.Structure):
@@ -93,7 +112,8 @@ class SceneDesc(C.Structure):
                 ("electron_density", ScalarField), ("electron_temperature", ScalarField),
                 ("species", C.POINTER(SpeciesDesc)), ("models", C.POINTER(ModelDesc)), ("axisym", C.POINTER(Axisym)),
                 ("b_field_kind", C.c_int32), ("brems_quadrature", C.c_int32), ("b_field", C.c_double * 3),
-                ("gaunt", Gaunt), ("quad_rtol", C.c_double), ("quad_max_order", C.c_int32), ("quad_min_order", C.c_int32)]
+                ("gaunt", Gaunt), ("quad_rtol", C.c_double), ("quad_max_order", C.c_int32), ("quad_min_order", C.c_int32),
+                ("beam", C.POINTER(BeamDesc))]
 
 
 class Rays(C.Structure):
@@ -118,7 +138,7 @@ class RTDesc(C.Structure):
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
-    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile",
+    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
 ]
 
@@ -150,6 +170,7 @@ def load_library():
     lib.cb2_scene_info.argtypes = [vp, C.c_int]
     lib.cb2_scene_info.restype = C.c_int64
     lib.cb2_scene_profile.argtypes = [vp, C.c_int, c_double_p, c_int64_p]
+    lib.cb2_beam_sample.argtypes = [vp, c_double_p, C.c_int64, c_double_p]
     lib.cb2_rt_create.argtypes = [C.POINTER(RTDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_rt_destroy.argtypes = [vp]
     lib.cb2_rt_render_dense.argtypes = [vp, C.POINTER(Rays), c_double_p, C.c_int, C.POINTER(Stats)]

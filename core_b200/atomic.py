@@ -101,6 +101,13 @@ class AtomicData:
     def cx_radiated_power_rate(self, ion, charge):
         raise NotImplementedError("The cx_radiated_power_rate() virtual method is not implemented for this atomic data source.")
 
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        """List of effective CX emission coefficients, one per donor metastable (interface.pyx:86-95)."""
+        raise NotImplementedError("The cxs_rates() virtual method is not implemented for this atomic data source.")
+
+    def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+        raise NotImplementedError("The beam_stopping() virtual method is not implemented for this atomic data source.")
+
     def free_free_gaunt_factor(self):
         """MaxwellianFreeFreeGauntFactor table (cherab/core/atomic/gaunt.pyx:143-158): (u, gamma2, gaunt_factor)."""
         t = np.load(os.path.join(_DATA, "atomic_tables.npz"))

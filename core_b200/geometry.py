@@ -58,7 +58,7 @@ def _slab_interval(o, d, axis, lo, hi):
         tb = (hi - o[:, axis]) / d[:, axis]
     t0, t1 = np.minimum(ta, tb), np.maximum(ta, tb)
     par = d[:, axis] == 0
-    inside = (o[:, axis] > lo) & (o[:, axis] < hi)
+    inside = (o[:, axis] >= lo) & (o[:, axis] <= hi)      # a ray lying in a face plane counts as inside (test_beamcxline.py)
     t0 = np.where(par, np.where(inside, -np.inf, np.inf), t0)
     t1 = np.where(par, np.where(inside, np.inf, -np.inf), t1)
     return t0, t1

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 2
+#define CB2_ABI_VERSION 3
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -156,6 +156,55 @@ typedef struct cb2_rate3d {
     int32_t       _pad2;
 } cb2_rate3d;
 
+/* BeamStoppingRate data dict {'e','n','t','sen','st','sref'} (cherab/openadas/rates/beam.pyx:40-103):
+ * rate = 10 ** (cubic2d[log10 E, log10 n](log10 sen) + cubic1d[log10 T](log10(st/sref))).  n_e == 0 -> constant rate
+ * (the mock AtomicData of core/tests/test_beam.py:33-52).  Outside the tabulated range the CUDA path and the oracle clamp to
+ * the edge and count the sample as out of domain (the reference extrapolates linearly/quadratically if permitted). */
+typedef struct cb2_beam_rate {
+    int32_t       n_e, n_n, n_t, _pad;
+    const double* e;           /* [n_e] interaction energy eV/amu */
+    const double* n;           /* [n_n] target equivalent electron density m^-3 */
+    const double* t;           /* [n_t] target temperature eV */
+    const double* sen;         /* [n_e][n_n] m^3 s^-1 */
+    const double* st;          /* [n_t] m^3 s^-1 */
+    double        sref;
+    double        constant;
+} cb2_beam_rate;
+
+/* BeamCXPEC data dict {'eb','ti','ni','z','b','qeb','qti','qni','qz','qb','qref'} (cherab/openadas/rates/cx.pyx:66-142):
+ * rate = 10**cubic[log10 E](log10 PhotonToJ(qeb)) * cubic[Ti](qti/qref) * cubic[ni](qni/qref) * cubic[Zeff](qz/qref) *
+ * cubic[B](qb/qref), zero as soon as a partial product is <= 0.  n_eb == 0 -> constant rate in W m^3
+ * (core/tests/test_beamcxline.py:34-46).  A grid with a single point is a constant factor (Constant1D). */
+typedef struct cb2_cx_rate {
+    int32_t       n_eb, n_ti, n_ni, n_z, n_b, _pad;
+    const double *eb, *ti, *ni, *z, *b;
+    const double *qeb, *qti, *qni, *qz, *qb;
+    double        qref;
+    double        constant;
+} cb2_cx_rate;
+
+/* Beam node + SingleRayAttenuator (cherab/core/beam/node.pyx:100-583, model/attenuator/singleray.pyx:36-346).
+ * A scene with a beam renders BEAM models only; its ray segments are the chords through the beam's bounding primitive and
+ * its integrator settings (step, min_samples) are the beam's (beam/node.pyx:212). */
+typedef struct cb2_beam_desc {
+    double  beam_to_plasma[12];  /* row-major 3x4 affine: beam frame (z along the beam, origin at the source) -> plasma space
+                                    (beam.to(plasma), beam/material.pyx:62).  In a beam scene cb2_scene_desc.world_to_plasma
+                                    holds world -> BEAM frame: the integrator marches in the beam primitive's local space */
+    double  energy;              /* eV/amu */
+    double  power;               /* W */
+    double  temperature;         /* eV (line width of beam emission; unused by BeamCXLine) */
+    double  atomic_weight;       /* beam.element.atomic_weight */
+    double  sigma;               /* Gaussian width at the origin, m */
+    double  divergence_x, divergence_y;   /* degrees */
+    double  length;              /* m */
+    double  attenuator_step;     /* SingleRayAttenuator.step (default 0.01 m) */
+    double  clamp_sigma;         /* default 5 */
+    int32_t clamp_to_zero;
+    int32_t n_stopping;          /* species the beam is stopped by: the whole composition (singleray.pyx:337-340) */
+    const int32_t*       stopping_species;   /* [n_stopping] */
+    const cb2_beam_rate* stopping_rates;     /* [n_stopping] beam_stopping_rate(beam.element, species.element, species.charge) */
+} cb2_beam_desc;
+
 /* Free-free Gaunt factor table (cherab/core/atomic/gaunt.pyx:87-140; data/maxwellian_free_free_gaunt_factor.json) */
 typedef struct cb2_gaunt {
     int32_t       n_u, n_gamma2;
@@ -201,7 +250,8 @@ typedef enum cb2_model_kind {
     CB2_MODEL_RECOMBINATION_LINE = 1, /* RecombinationLine.emission  recombination.pyx:78-100 */
     CB2_MODEL_BREMSSTRAHLUNG     = 2, /* Bremsstrahlung.emission     bremsstrahlung.pyx:169-208 */
     CB2_MODEL_THERMAL_CX_LINE    = 3, /* ThermalCXLine.emission      thermal_cx.pyx:79-112 */
-    CB2_MODEL_TOTAL_RADIATED_POWER = 4 /* TotalRadiatedPower.emission total_radiated_power.pyx:70-118 */
+    CB2_MODEL_TOTAL_RADIATED_POWER = 4, /* TotalRadiatedPower.emission total_radiated_power.pyx:70-118 */
+    CB2_MODEL_BEAM_CX_LINE       = 5  /* BeamCXLine.emission         model/beam/charge_exchange.pyx:117-167 (needs cb2_scene_desc.beam) */
 } cb2_model_kind;
 
 /* What ThermalCXLine._populate_cache (thermal_cx.pyx:114-155) and TotalRadiatedPower._populate_cache
@@ -217,6 +267,11 @@ typedef struct cb2_model_ext {
     int32_t           n_hydrogen, has_plt, has_prb, has_prc;
     const int32_t*    hydrogen_species;  /* [n_hydrogen] */
     cb2_rate2d        plt, prb, prc;     /* W m^3 on (ne, te), log-log cubic (openadas/rates/radiated_power.pyx:48-76); NOT photon rates */
+    /* BEAM_CX_LINE: beam_cx_pec(beam.element, line.element, line.charge + 1, transition) — one rate per donor metastable
+     * (charge_exchange.pyx:311-349); only the ground state (n_cx == 1) is accepted so far, excited-state populations
+     * (BeamPopulationRate) return CB2_ERR_NOT_IMPLEMENTED */
+    int32_t            n_cx, _pad3;
+    const cb2_cx_rate* cx;
 } cb2_model_ext;
 
 typedef struct cb2_model {
@@ -254,6 +309,7 @@ typedef struct cb2_scene_desc {
     /* oracle-only knobs of GaussianQuadrature (integrators1d.pyx:73-92): relative_tolerance, max_order, min_order */
     double             quad_rtol;
     int32_t            quad_max_order, quad_min_order;
+    const cb2_beam_desc* beam;              /* NULL unless the models are BEAM models */
 } cb2_scene_desc;
 
 /* Ray segments: what Raysect's tracer hands to VolumeIntegrator.integrate(start_point, end_point)
@@ -314,6 +370,9 @@ int cb2_emission_render_device(cb2_scene* scene, const cb2_rays* rays, void* out
  * ne, te, then per species (density, temperature, vx, vy, vz), then Bx, By, Bz.  HOST buffers. */
 int cb2_sample_state(cb2_scene* scene, const double* points, int64_t n, double* out);
 int cb2_state_width(const cb2_scene* scene);
+/* Beam.density / Beam.direction at n points given in BEAM coordinates (beam/node.pyx:214-279): out[n][4] =
+ * (density m^-3, direction x, y, z in the beam frame).  Parity probe for the reference's test_beam.py. */
+int cb2_beam_sample(cb2_scene* scene, const double* beam_points, int64_t n, double* out);
 
 /* Launch-plan introspection (no reference counterpart; used by the benchmark and the parity tests to report which
  * formulation a scene runs).  key: 0 warps per CTA, 1 bins per lane, 2 Bremsstrahlung formulation (0 none, 1 direct
@@ -379,6 +438,7 @@ int cb2o_emission_render(const cb2_scene_desc* desc, const cb2_rays* rays, doubl
                          double scale, int accumulate, int n_threads, cb2_stats* stats);
 int cb2o_sample_state(const cb2_scene_desc* desc, const double* points, int64_t n, double* out);
 int cb2o_state_width(const cb2_scene_desc* desc);
+int cb2o_beam_sample(const cb2_scene_desc* desc, const double* beam_points, int64_t n, double* out);   /* beam/node.pyx:214-279 */
 int cb2o_rt_render_dense(const cb2_rt_desc* desc, const cb2_rays* rays, double* out, int accumulate,
                          int n_threads, cb2_stats* stats);
 /* building blocks exposed so the reference's own unit tests can be replayed against the oracle */

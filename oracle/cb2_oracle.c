@@ -578,6 +578,8 @@ typedef struct {
     pec_table* pec;   /* [n_models] */
     pec_table* trp;   /* [n_models][3] TotalRadiatedPower plt, prb, prc */
     gaunt_table gaunt;
+    /* SingleRayAttenuator axis table (singleray.pyx:182-224): z_k = linspace(0, length, n_axis), density on the axis */
+    int n_axis; double* axis_z; double* axis_density; double tanxdiv, tanydiv;
 } scene_ctx;
 
 static double eval_scalar(const scene_ctx* s, const cb2_scalar_field* f, const double p[3], int64_t* ood) {
@@ -645,6 +647,8 @@ static void eval_b_field(const scene_ctx* s, const double p[3], double out[3], i
     rotate_axisym(b2, p, out);
 }
 
+static int beam_ctx_build(scene_ctx* s);
+
 static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
     memset(s, 0, sizeof *s);
     if (d->abi_version != CB2_ABI_VERSION) return fail(CB2_ERR_VALUE, "abi_version mismatch");
@@ -670,9 +674,20 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
             if (mo->ext->has_plt) power_table_build(&s->trp[3 * m], &mo->ext->plt);
             if (mo->ext->has_prb) power_table_build(&s->trp[3 * m + 1], &mo->ext->prb);
             if (mo->ext->has_prc) power_table_build(&s->trp[3 * m + 2], &mo->ext->prc);
+        } else if (mo->kind == CB2_MODEL_BEAM_CX_LINE) {
+            if (!d->beam) return fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
+            if (mo->species < 0 || mo->species >= d->n_species || !mo->ext || mo->ext->n_cx < 1)
+                return fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified CX line");
+            if (mo->ext->n_cx > 1) return fail(CB2_ERR_NOT_IMPLEMENTED, "excited donor metastables are not supported yet");
         } else return fail(CB2_ERR_TYPE, "unsupported model kind");
     }
     gaunt_table_build(&s->gaunt, &d->gaunt);
+    if (d->beam) {
+        for (int m = 0; m < d->n_models; m++)
+            if (d->models[m].kind != CB2_MODEL_BEAM_CX_LINE) return fail(CB2_ERR_TYPE, "a beam scene renders beam models only");
+        if (!(d->beam->energy > 0)) return fail(CB2_ERR_VALUE, "Beam energy must be positive");
+        return beam_ctx_build(s);
+    }
     return CB2_OK;
 }
 
@@ -681,6 +696,166 @@ static void scene_ctx_free(scene_ctx* s) {
     if (s->pec) { for (int m = 0; m < s->d->n_models; m++) pec_table_free(&s->pec[m]); free(s->pec); }
     if (s->trp) { for (int m = 0; m < 3 * s->d->n_models; m++) pec_table_free(&s->trp[m]); free(s->trp); }
     gaunt_table_free(&s->gaunt);
+    free(s->axis_z); free(s->axis_density);
+}
+
+static void xform_point(const double m[12], const double p[3], double o[3]);
+static void xform_vector(const double m[12], const double p[3], double o[3]);
+
+/* =================================================================================================
+ * Beam: rates, attenuation, density, direction (beam/node.pyx, attenuator/singleray.pyx, openadas/rates/{beam,cx}.pyx)
+ * ============================================================================================== */
+#define EVAMU_TO_MS2 (2.0 * ELEMENTARY_CHARGE / ATOMIC_MASS)   /* EvAmuToMS.conversion_factor, conversion.py:31 */
+
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* BeamStoppingRate.evaluate — openadas/rates/beam.pyx:93-103; outside the tables: clamped to the edge and counted */
+static double beam_rate_eval(const cb2_beam_rate* r, double energy, double density, double temperature, int64_t* ood) {
+    if (r->n_e <= 0) return r->constant;
+    if (energy <= 0 || density <= 0 || temperature <= 0) return 0.0;
+    double le = log10(energy), ln = log10(density), lt = log10(temperature);
+    double lo, hi;
+    double *xe = (double*)malloc(sizeof(double) * (r->n_e + r->n_n + r->n_t + r->n_e * r->n_n + r->n_t));
+    double *xn = xe + r->n_e, *xt = xn + r->n_n, *lsen = xt + r->n_t, *lst = lsen + r->n_e * r->n_n;
+    for (int i = 0; i < r->n_e; i++) xe[i] = log10(r->e[i]);
+    for (int i = 0; i < r->n_n; i++) xn[i] = log10(r->n[i]);
+    for (int i = 0; i < r->n_t; i++) xt[i] = log10(r->t[i]);
+    for (int i = 0; i < r->n_e * r->n_n; i++) lsen[i] = log10(r->sen[i]);
+    for (int i = 0; i < r->n_t; i++) lst[i] = log10(r->st[i] / r->sref);
+    lo = xe[0]; hi = xe[r->n_e - 1]; if (le < lo || le > hi) { (*ood)++; le = clampd(le, lo, hi); }
+    lo = xn[0]; hi = xn[r->n_n - 1]; if (ln < lo || ln > hi) { (*ood)++; ln = clampd(ln, lo, hi); }
+    lo = xt[0]; hi = xt[r->n_t - 1]; if (lt < lo || lt > hi) { (*ood)++; lt = clampd(lt, lo, hi); }
+    double a;
+    if (r->n_e == 1 && r->n_n == 1) a = lsen[0];
+    else if (r->n_e == 1) a = cb2o_interp1d_cubic(xn, lsen, r->n_n, ln, 1);
+    else if (r->n_n == 1) a = cb2o_interp1d_cubic(xe, lsen, r->n_e, le, 1);
+    else a = cb2o_interp2d_cubic(xe, xn, lsen, r->n_e, r->n_n, le, ln, 1);
+    double b = r->n_t > 1 ? cb2o_interp1d_cubic(xt, lst, r->n_t, lt, 1) : lst[0];
+    free(xe);
+    return pow(10.0, a + b);
+}
+
+static double cx_factor(const double* x, const double* q, int n, double scale, double v, int64_t* ood) {
+    if (n == 1) return q[0] * scale;               /* Constant1D */
+    if (v < x[0] || v > x[n - 1]) { (*ood)++; v = clampd(v, x[0], x[n - 1]); }
+    double* f = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; i++) f[i] = q[i] * scale;
+    double r = cb2o_interp1d_cubic(x, f, n, v, 1);
+    free(f);
+    return r;
+}
+
+/* BeamCXPEC.evaluate — openadas/rates/cx.pyx:104-142 */
+static double cx_rate_eval(const cb2_cx_rate* r, double wavelength, double energy, double temperature, double density, double zeff,
+                           double bmag, int64_t* ood) {
+    if (r->n_eb <= 0) return r->constant;
+    if (energy <= 0) return 0.0;
+    double rate;
+    {
+        double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9;      /* PhotonToJ */
+        double* x = (double*)malloc(sizeof(double) * 2 * r->n_eb);
+        double* f = x + r->n_eb;
+        for (int i = 0; i < r->n_eb; i++) { x[i] = log10(r->eb[i]); f[i] = log10(r->qeb[i] / wavelength * conv); }
+        double le = log10(energy);
+        if (r->n_eb == 1) rate = pow(10.0, f[0]);
+        else {
+            if (le < x[0] || le > x[r->n_eb - 1]) { (*ood)++; le = clampd(le, x[0], x[r->n_eb - 1]); }
+            rate = pow(10.0, cb2o_interp1d_cubic(x, f, r->n_eb, le, 1));
+        }
+        free(x);
+    }
+    rate *= cx_factor(r->ti, r->qti, r->n_ti, 1.0 / r->qref, temperature, ood);
+    if (rate <= 0) return 0.0;
+    rate *= cx_factor(r->ni, r->qni, r->n_ni, 1.0 / r->qref, density, ood);
+    if (rate <= 0) return 0.0;
+    rate *= cx_factor(r->z, r->qz, r->n_z, 1.0 / r->qref, zeff, ood);
+    if (rate <= 0) return 0.0;
+    rate *= cx_factor(r->b, r->qb, r->n_b, 1.0 / r->qref, bmag, ood);
+    if (rate <= 0) return 0.0;
+    return rate;
+}
+
+/* SingleRayAttenuator._beam_stopping — singleray.pyx:266-313 (species with charge 0 are skipped, SURVEY A.7 caveat) */
+static double beam_stopping(const scene_ctx* s, const double p[3], const double beam_velocity[3], int64_t* ood) {
+    const cb2_scene_desc* d = s->d;
+    const cb2_beam_desc* b = d->beam;
+    double density_sum = 0;
+    for (int k = 0; k < b->n_stopping; k++) {
+        const cb2_species* sp = &d->species[b->stopping_species[k]];
+        density_sum += (double)sp->charge * sp->charge * eval_scalar(s, &sp->density, p, ood);
+    }
+    double coeff = 0;
+    for (int k = 0; k < b->n_stopping; k++) {
+        const cb2_species* sp = &d->species[b->stopping_species[k]];
+        if (sp->charge == 0) continue;
+        double target_ne = eval_scalar(s, &sp->density, p, ood) * sp->charge;
+        double target_ti = eval_scalar(s, &sp->temperature, p, ood);
+        double tv[3];
+        eval_vector(s, &sp->velocity, p, tv, ood);
+        double iv[3] = {beam_velocity[0] - tv[0], beam_velocity[1] - tv[1], beam_velocity[2] - tv[2]};
+        double speed = sqrt(iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2]);
+        double energy = speed * speed / EVAMU_TO_MS2;
+        coeff += target_ne * beam_rate_eval(&b->stopping_rates[k], energy, density_sum / sp->charge, target_ti, ood);
+    }
+    return coeff;
+}
+
+/* SingleRayAttenuator._calc_attenuation / _beam_attenuation — singleray.pyx:182-264 */
+static int beam_ctx_build(scene_ctx* s) {
+    const cb2_beam_desc* b = s->d->beam;
+    int64_t ood = 0;
+    int n = 1 + (int)ceil(b->length / b->attenuator_step);
+    if (n < 4) n = 4;
+    s->n_axis = n;
+    s->axis_z = (double*)malloc(sizeof(double) * n);
+    s->axis_density = (double*)malloc(sizeof(double) * n);
+    double* stop = (double*)malloc(sizeof(double) * n);
+    double axis[3] = {0, 0, 1}, dir[3];
+    xform_vector(b->beam_to_plasma, axis, dir);
+    double dl = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    double speed = sqrt(b->energy * EVAMU_TO_MS2);
+    double bv[3] = {dir[0] / dl * speed, dir[1] / dl * speed, dir[2] / dl * speed};
+    double n0 = b->power / (b->energy * b->atomic_weight * ELEMENTARY_CHARGE) / speed;
+    for (int k = 0; k < n; k++) {
+        s->axis_z[k] = (n > 1) ? b->length * k / (n - 1) : 0.0;      /* np.linspace(0, length, nbeam) */
+        if (k == n - 1) s->axis_z[k] = b->length;
+        double pb[3] = {0, 0, s->axis_z[k]}, pp[3];
+        xform_point(b->beam_to_plasma, pb, pp);
+        stop[k] = beam_stopping(s, pp, bv, &ood);
+    }
+    double cum = 0;                                                   /* cumulative_trapezoid(..., initial=0) */
+    for (int k = 0; k < n; k++) {
+        if (k > 0) cum += 0.5 * (stop[k] + stop[k - 1]) * (s->axis_z[k] - s->axis_z[k - 1]);
+        s->axis_density[k] = n0 * exp(-cum / speed);
+    }
+    free(stop);
+    s->tanxdiv = tan(b->divergence_x * M_PI / 180.0);
+    s->tanydiv = tan(b->divergence_y * M_PI / 180.0);
+    return CB2_OK;
+}
+
+/* Beam.density (beam/node.pyx:214-234) -> SingleRayAttenuator.density (singleray.pyx:107-168) */
+static double beam_density(const scene_ctx* s, const double pb[3]) {
+    const cb2_beam_desc* b = s->d->beam;
+    double x = pb[0], y = pb[1], z = pb[2];
+    if (z < 0 || z > b->length) return 0.0;
+    double s0 = b->sigma * b->sigma;
+    double sx = sqrt(s0 + (z * s->tanxdiv) * (z * s->tanxdiv)), sy = sqrt(s0 + (z * s->tanydiv) * (z * s->tanydiv));
+    double nr2 = (x / sx) * (x / sx) + (y / sy) * (y / sy);
+    if (b->clamp_to_zero && nr2 > b->clamp_sigma * b->clamp_sigma) return 0.0;
+    double g = exp(-0.5 * nr2) / (2 * M_PI * sx * sy);
+    return interp1d_linear(s->axis_z, s->axis_density, s->n_axis, z) * g;
+}
+
+/* Beam.direction — beam/node.pyx:236-279 */
+static void beam_direction(const scene_ctx* s, const double pb[3], double out[3]) {
+    const cb2_beam_desc* b = s->d->beam;
+    double x = pb[0], y = pb[1], z = pb[2];
+    if (z <= 0) { out[0] = 0; out[1] = 0; out[2] = 1; return; }
+    double ztx = z * z * s->tanxdiv * s->tanxdiv, zty = z * z * s->tanydiv * s->tanydiv, s0 = b->sigma * b->sigma;
+    double ex = x * ztx / (s0 + ztx), ey = y * zty / (s0 + zty);
+    double l = sqrt(ex * ex + ey * ey + z * z);
+    out[0] = ex / l; out[1] = ey / l; out[2] = z / l;
 }
 
 /* =================================================================================================
@@ -849,8 +1024,50 @@ static double brems_eval(double wvl, void* ctx) {
 }
 
 /* PlasmaMaterial.emission_function — plasma/material.pyx:48-63: all models at one (plasma-space) point */
+/* BeamMaterial.emission_function (beam/material.pyx:49-71) + BeamCXLine.emission (charge_exchange.pyx:117-167): pb and dirb
+ * are the sample point and the ray direction in the BEAM frame */
+static void beam_emission_function(const scene_ctx* s, const double pb[3], const double dirb[3], double* samples, counters* cn) {
+    const cb2_scene_desc* d = s->d;
+    const cb2_beam_desc* b = d->beam;
+    double bdir_b[3], bdir[3], p[3], obs[3];
+    beam_direction(s, pb, bdir_b);
+    xform_point(b->beam_to_plasma, pb, p);
+    xform_vector(b->beam_to_plasma, bdir_b, bdir);
+    xform_vector(b->beam_to_plasma, dirb, obs);
+    for (int m = 0; m < d->n_models; m++) {
+        const cb2_model* mo = &d->models[m];
+        double donor = beam_density(s, pb);
+        if (donor == 0.0) continue;
+        double nr = eval_scalar(s, &d->species[mo->species].density, p, &cn->ood);
+        if (nr == 0) continue;
+        double tr = eval_scalar(s, &d->species[mo->species].temperature, p, &cn->ood);
+        if (tr == 0) continue;
+        double vr[3];
+        eval_vector(s, &d->species[mo->species].velocity, p, vr, &cn->ood);
+        double bl = sqrt(bdir[0] * bdir[0] + bdir[1] * bdir[1] + bdir[2] * bdir[2]);
+        double speed = sqrt(b->energy * EVAMU_TO_MS2);
+        double iv[3] = {bdir[0] / bl * speed - vr[0], bdir[1] / bl * speed - vr[1], bdir[2] / bl * speed - vr[2]};
+        double ispeed = sqrt(iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2]);
+        double energy = ispeed * ispeed / EVAMU_TO_MS2;
+        /* _composite_cx_rate, ground state only (charge_exchange.pyx:204-236); Plasma.ion_density / z_effective (node.pyx:396-462) */
+        double ion_density = 0, snz = 0, snz2 = 0;
+        for (int i = 0; i < d->n_species; i++) {
+            double n = eval_scalar(s, &d->species[i].density, p, &cn->ood);
+            ion_density += n;
+            if (d->species[i].charge > 0) { snz += n * d->species[i].charge; snz2 += n * d->species[i].charge * d->species[i].charge; }
+        }
+        double zeff = snz > 0 ? snz2 / snz : 0.0;
+        double bf[3];
+        eval_b_field(s, p, bf, &cn->ood);
+        double bmag = sqrt(bf[0] * bf[0] + bf[1] * bf[1] + bf[2] * bf[2]);
+        double rate = cx_rate_eval(&mo->ext->cx[0], mo->wavelength, energy, tr, ion_density, zeff, bmag, &cn->ood);
+        add_shape(s, mo, RECIP_4_PI * donor * nr * rate, p, obs, samples, cn);
+    }
+}
+
 static void emission_function(const scene_ctx* s, const double p[3], const double dir[3], double* samples, counters* cn) {
     const cb2_scene_desc* d = s->d;
+    if (d->beam) { beam_emission_function(s, p, dir, samples, cn); return; }
     for (int m = 0; m < d->n_models; m++) {
         const cb2_model* mo = &d->models[m];
         double ne = eval_scalar(s, &d->electron_density, p, &cn->ood);
@@ -980,6 +1197,20 @@ int cb2o_emission_render(const cb2_scene_desc* desc, const cb2_rays* rays, doubl
         memset(stats, 0, sizeof *stats);
         stats->samples = tot_samples; stats->gaussian_bin_evals = tot_g; stats->lorentzian_bin_evals = tot_l;
         stats->brems_bin_evals = tot_b; stats->out_of_domain = tot_ood;
+    }
+    scene_ctx_free(&s);
+    return CB2_OK;
+}
+
+/* Beam.density / Beam.direction at points given in beam coordinates: out[n][4] */
+int cb2o_beam_sample(const cb2_scene_desc* desc, const double* beam_points, int64_t n, double* out) {
+    scene_ctx s;
+    int rc = scene_ctx_build(&s, desc);
+    if (rc != CB2_OK) { scene_ctx_free(&s); return rc; }
+    if (!desc->beam) { scene_ctx_free(&s); return fail(CB2_ERR_VALUE, "the scene has no beam"); }
+    for (int64_t i = 0; i < n; i++) {
+        out[4 * i] = beam_density(&s, beam_points + 3 * i);
+        beam_direction(&s, beam_points + 3 * i, out + 4 * i + 1);
     }
     scene_ctx_free(&s);
     return CB2_OK;

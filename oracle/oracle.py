@@ -10,7 +10,7 @@ from core_b200 import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcb2_oracle.so")
-ORACLE_SYMBOLS = ["cb2o_abi_version", "cb2o_last_error", "cb2o_emission_render", "cb2o_sample_state", "cb2o_state_width",
+ORACLE_SYMBOLS = ["cb2o_abi_version", "cb2o_last_error", "cb2o_emission_render", "cb2o_sample_state", "cb2o_state_width", "cb2o_beam_sample",
                   "cb2o_rt_render_dense", "cb2o_add_gaussian_line", "cb2o_add_lorentzian_line", "cb2o_interp1d_cubic",
                   "cb2o_interp2d_cubic", "cb2o_gauss_legendre", "cb2o_gaunt_factor", "cb2o_pec_evaluate"]
 _lib = None
@@ -41,6 +41,7 @@ def lib():
         l.cb2o_emission_render.argtypes = [C.POINTER(_abi.SceneDesc), C.POINTER(_abi.Rays), dp, C.c_double, C.c_int, C.c_int, C.POINTER(_abi.Stats)]
         l.cb2o_sample_state.argtypes = [C.POINTER(_abi.SceneDesc), dp, C.c_int64, dp]
         l.cb2o_state_width.argtypes = [C.POINTER(_abi.SceneDesc)]
+        l.cb2o_beam_sample.argtypes = [C.POINTER(_abi.SceneDesc), dp, C.c_int64, dp]
         l.cb2o_rt_render_dense.argtypes = [C.POINTER(_abi.RTDesc), C.POINTER(_abi.Rays), dp, C.c_int, C.c_int, C.POINTER(_abi.Stats)]
         l.cb2o_add_gaussian_line.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(_abi.SpectralGrid), dp]
         l.cb2o_add_lorentzian_line.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(_abi.SpectralGrid), dp, C.c_double, C.c_int, C.c_int]
@@ -83,6 +84,15 @@ def sample_state(flat, points):
     out = np.zeros((pts.shape[0], w), dtype=np.float64)
     _abi.check(l, l.cb2o_sample_state(C.byref(flat.desc), _dp(pts), pts.shape[0], _dp(out)), "cb2o_last_error")
     return out
+
+
+def beam_sample(flat, beam_points):
+    """Beam.density / Beam.direction at points in beam coordinates -> (density[n], direction[n, 3])."""
+    l = lib()
+    pts = np.ascontiguousarray(beam_points, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((pts.shape[0], 4), dtype=np.float64)
+    _abi.check(l, l.cb2o_beam_sample(C.byref(flat.desc), _dp(pts), pts.shape[0], _dp(out)), "cb2o_last_error")
+    return out[:, 0], out[:, 1:]
 
 
 def rt_render_dense(rt_desc, rays, n_threads=0):

@@ -1,0 +1,98 @@
+"""Pin the oracle's beam path against the reference's own known-answer tests: cherab/core/tests/test_beam.py:64-158
+(SingleRayAttenuator density with a constant stopping rate, Beam.direction) and test_beamcxline.py:85-137 (BeamCXLine
+radiance against a midpoint sum of Beam.density)."""
+import numpy as np
+import pytest
+from scipy import constants as const
+
+import core_b200 as cb
+from core_b200.slab import build_constant_slab_plasma
+from oracle import oracle
+
+from helpers import ATOMIC_MASS as AMU, ELEMENTARY_CHARGE as QE
+# the reference takes e and m_u for EvAmuToMS / EvToJ from scipy.constants (cherab/core/utility/conversion.py:24-31), whose
+# CODATA release depends on the installed scipy (2018 vs 2022 differ by 1.4e-9 in m_u); the oracle and the CUDA library pin the
+# CODATA-2018 values of cherab/core/utility/constants.pyx:22-37, so the closed forms below use those
+
+
+class BeamMockData(cb.AtomicData):
+    def __init__(self, stopping, cx=3.4e-34):
+        self.stopping, self.cx = stopping, cx
+
+    def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+        return cb.ConstantRate(self.stopping)
+
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        return [cb.ConstantBeamCXPEC(1, self.cx)]
+
+    def wavelength(self, ion, charge, transition):
+        return 656.104
+
+
+def beam_scene(stopping, density=1e19, temperature=1e3, models=(), **beam_kw):
+    atomic = BeamMockData(stopping)
+    plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=density, electron_temperature=temperature,
+                                        plasma_species=[(cb.deuterium, 1, density, temperature, (0, 0, 0))], b_field=(0, 10.0, 0))
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.translate(0.5, 0, 0))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 50000, 1e6, 10, cb.deuterium
+    for k, v in beam_kw.items():
+        setattr(beam, k, v)
+    beam.models = list(models)
+    return plasma, beam
+
+
+def test_beam_density_and_direction():
+    # test_beam.py:64-158
+    plasma, beam = beam_scene(1e-13, sigma=0.2, divergence_x=1.0, divergence_y=2.0, length=10.0)
+    flat = cb.flatten_beam_scene(beam, 655.1, 657.1, 16)
+    z0, x0, y0 = 0.8, 0.5, 0.5
+    dens, dirs = oracle.beam_sample(flat, [[0, 0, z0], [x0, y0, z0], [0, 0, -1]])
+    speed = np.sqrt(2 * 50000 * QE / AMU)
+    attenuation = np.exp(-z0 * 1e19 * 1e-13 / speed)
+    rate = 1e6 / (50000 * cb.deuterium.atomic_weight * QE)
+    tx, ty = np.tan(np.deg2rad(1.0)), np.tan(np.deg2rad(2.0))
+    sx, sy = np.sqrt(0.2 ** 2 + (z0 * tx) ** 2), np.sqrt(0.2 ** 2 + (z0 * ty) ** 2)
+    on = rate / speed / (2 * np.pi * sx * sy) * attenuation
+    off = on * np.exp(-0.5 * ((x0 / sx) ** 2 + (y0 / sy) ** 2))
+    assert abs(dens[0] / on - 1) < 1e-12 and abs(dens[1] / off - 1) < 1e-12 and dens[2] == 0
+    ex, ey = x0 * (z0 * tx) ** 2 / (0.2 ** 2 + (z0 * tx) ** 2), y0 * (z0 * ty) ** 2 / (0.2 ** 2 + (z0 * ty) ** 2)
+    ref = np.array([ex, ey, z0]) / np.linalg.norm([ex, ey, z0])
+    assert np.array_equal(dirs[0], [0, 0, 1]) and np.array_equal(dirs[2], [0, 0, 1])
+    assert np.max(np.abs(dirs[1] - ref)) < 1e-12
+
+
+def cx_case(shape=None):
+    # test_beamcxline.py:85-137: D-alpha, ray along -x through the beam origin plane, 512 bins on [655.1, 657.1]
+    line = cb.Line(cb.deuterium, 0, (3, 2))
+    plasma, beam = beam_scene(0.0, temperature=200.0, models=[cb.BeamCXLine(line, lineshape=shape)])
+    flat = cb.flatten_beam_scene(beam, 655.1, 657.1, 512)
+    rays = cb.beam_ray_segments(beam, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    return plasma, beam, flat, rays
+
+
+def test_beam_cx_line_default_lineshape():
+    plasma, beam, flat, rays = cx_case()
+    got, stats = oracle.emission_render(flat, rays)
+    dx = beam.integrator.step
+    xs = dx * (np.arange(-int(0.5 / dx), int(0.5 / dx)) + 0.5)
+    dens, _ = oracle.beam_sample(flat, np.stack([xs, np.zeros_like(xs), np.zeros_like(xs)], axis=1))
+    radiance = 0.25 * 3.4e-34 * 1e19 * dens.sum() * dx / np.pi
+    sigma = np.sqrt(200.0 * QE / (cb.deuterium.atomic_weight * AMU)) * 656.104 / const.c
+    ref = oracle.add_gaussian_line(radiance, 656.104, sigma, 655.1, 657.1, 512)
+    assert stats["samples"] == 1001
+    assert np.max(np.abs(got[0] - ref)) < 1e-8              # the reference's delta
+
+
+def test_beam_scene_validation():
+    plasma, beam = beam_scene(0.0)
+    beam.models = [cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    with pytest.raises(RuntimeError):
+        cb.flatten_beam_scene(beam, 500, 550, 8)             # no C6+ in the plasma
+    with pytest.raises(ValueError):
+        beam.sigma = 0.0
+    beam.attenuator = None
+    with pytest.raises(ValueError):
+        cb.flatten_beam_scene(beam, 500, 550, 8)
