@@ -175,6 +175,30 @@ class SyntheticADAS(AtomicData):
         rate = s * 1e-14 * (te / 10.0) ** -0.5 * np.exp(-e_n / te) * (1.0 + 0.1 * np.log10(ne / 1e19))
         return RateTable(self.ne, self.te, rate, self.permit_extrapolation)
 
+    def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+        """Synthetic ADF21-shaped stopping coefficient: sen[e 25 x n 26], st[t 16], smooth and positive."""
+        from .beam import BeamStoppingTable
+        if charge == 0:
+            return None                       # no beam stopping data for neutrals (NullBeamStoppingRate)
+        e, n, t = np.logspace(3.5, 5.5, 25), np.logspace(17.0, 21.5, 26), np.logspace(0.0, 4.5, 16)
+        sref = 1.0e-13
+        sen = sref * (1 + 0.05 * charge) * (e[:, None] / 4e4) ** -0.35 * (1 + 0.08 * np.log10(n[None, :] / 1e19))
+        st = sref * (1 + 0.05 * np.log10(t / 1e3))
+        return BeamStoppingTable(e, n, t, sen, st, sref)
+
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        """Synthetic ADF12-shaped effective CX emission coefficient: eb[24], ti[12], ni[24], zeff[12], b[12]."""
+        from .beam import BeamCXTable
+        eb, ti, ni = np.logspace(3.3, 5.6, 24), np.logspace(0.5, 4.5, 12), np.logspace(17.0, 21.5, 24)
+        z, b = np.linspace(1.0, 6.0, 12), np.linspace(0.0, 12.0, 12)
+        qref = 2.0e-15
+        qeb = qref * np.exp(-0.5 * (np.log(eb / 4e4) / 1.2) ** 2) + 1e-18
+        qti = qref * (1 + 0.1 * np.log10(ti / 1e3))
+        qni = qref * (1 - 0.05 * np.log10(ni / 1e19))
+        qz = qref * (1 + 0.03 * (z - 2.0))
+        qb = qref * (1 + 0.004 * b)
+        return [BeamCXTable(1, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref)]
+
     def recombination_pec(self, ion, charge, transition):
         s, _ = self._scale(transition)
         ne, te = self.ne[:, None], self.te[None, :]

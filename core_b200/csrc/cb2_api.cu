@@ -441,6 +441,190 @@ static void set_comp(DevScene& S, int slot, double lambda, int type) {
     S.comps[slot].type = type;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Beam: host-side fp64 rate evaluation and the SingleRayAttenuator axis table (singleray.pyx:182-313)
+// ------------------------------------------------------------------------------------------------------------------
+static double host_cubic1d(const double* x, const double* f, int n, double v) {
+    // Interpolator1DArray 'cubic' restated (local Hermite, 3-point knot derivatives), 'nearest' outside the knots
+    if (n == 1) return f[0];
+    v = fmin(fmax(v, x[0]), x[n - 1]);
+    int i = (int)(std::upper_bound(x, x + n, v) - x) - 1;
+    i = std::min(std::max(i, 0), n - 2);
+    const double h = x[i + 1] - x[i], t = (v - x[i]) / h;
+    double a[4];
+    hermite_coef(f[i], f[i + 1], d1(x, f, n, 1, i) * h, d1(x, f, n, 1, i + 1) * h, a);
+    return a[0] + t * (a[1] + t * (a[2] + t * a[3]));
+}
+
+static double host_cubic2d(const double* x, const double* y, const std::vector<double>& coef, int nx, int ny, double vx, double vy) {
+    vx = fmin(fmax(vx, x[0]), x[nx - 1]);
+    vy = fmin(fmax(vy, y[0]), y[ny - 1]);
+    int i = (int)(std::upper_bound(x, x + nx, vx) - x) - 1, j = (int)(std::upper_bound(y, y + ny, vy) - y) - 1;
+    i = std::min(std::max(i, 0), nx - 2);
+    j = std::min(std::max(j, 0), ny - 2);
+    const double t = (vx - x[i]) / (x[i + 1] - x[i]), u = (vy - y[j]) / (y[j + 1] - y[j]);
+    const double* c = &coef[((size_t)i * (ny - 1) + j) * 16];
+    double v = 0.0;
+    for (int p = 3; p >= 0; p--) v = v * t + (c[4 * p] + u * (c[4 * p + 1] + u * (c[4 * p + 2] + u * c[4 * p + 3])));
+    return v;
+}
+
+struct HostBeamRate {     // BeamStoppingRate in log space (openadas/rates/beam.pyx:62-103)
+    bool constant;
+    double value;
+    std::vector<double> le, ln, lt, lsen, lst, coef;
+    double eval(double energy, double density, double temperature) const {
+        if (constant) return value;
+        if (energy <= 0 || density <= 0 || temperature <= 0) return 0.0;
+        const double e = log10(energy), n = log10(density), t = log10(temperature);
+        double a;
+        const int ne = (int)le.size(), nn = (int)ln.size();
+        if (ne == 1 && nn == 1) a = lsen[0];
+        else if (ne == 1) a = host_cubic1d(ln.data(), lsen.data(), nn, n);
+        else if (nn == 1) a = host_cubic1d(le.data(), lsen.data(), ne, e);
+        else a = host_cubic2d(le.data(), ln.data(), coef, ne, nn, e, n);
+        const double b = lt.size() > 1 ? host_cubic1d(lt.data(), lst.data(), (int)lt.size(), t) : lst[0];
+        return pow(10.0, a + b);
+    }
+};
+
+static void mat_mul_point(const double m[12], const double p[3], double o[3]) {
+    for (int i = 0; i < 3; i++) o[i] = m[4 * i] * p[0] + m[4 * i + 1] * p[1] + m[4 * i + 2] * p[2] + m[4 * i + 3];
+}
+
+// called once the scene's tables are on the device: plasma state along the beam axis comes from the device's own field
+// evaluation (sample_state_kernel), the stopping sum, cumulative trapezium and exponential are fp64 on the host
+static int build_beam(Arena& A, const cb2_scene_desc& d, cb2_scene* sc) {
+    DevScene& S = sc->host;
+    const cb2_beam_desc& b = *d.beam;
+    DevBeam& o = S.beam;
+    memset(&o, 0, sizeof o);
+    if (!(b.energy > 0)) return cb2_fail(CB2_ERR_VALUE, "Beam energy must be positive");
+    if (!(b.sigma > 0) || !(b.length > 0) || !(b.attenuator_step > 0) || !(b.clamp_sigma > 0))
+        return cb2_fail(CB2_ERR_VALUE, "Beam sigma, length, attenuator step and clamp_sigma must be positive");
+    if (b.n_stopping < 0 || b.n_stopping > CB2_MAX_SPECIES) return cb2_fail(CB2_ERR_VALUE, "invalid number of stopping species");
+    o.present = 1;
+    for (int k = 0; k < 12; k++) o.l2p[k] = b.beam_to_plasma[k];
+    const double evamu = 2.0 * ELEMENTARY_CHARGE / ATOMIC_MASS;       // EvAmuToMS.conversion_factor (conversion.py:31)
+    const double speed = sqrt(b.energy * evamu);
+    o.speed = (float)speed;
+    o.length = (float)b.length;
+    o.sigma2 = (float)(b.sigma * b.sigma);
+    o.tanx = (float)tan(b.divergence_x * M_PI / 180.0);
+    o.tany = (float)tan(b.divergence_y * M_PI / 180.0);
+    o.clamp_to_zero = b.clamp_to_zero;
+    o.clamp2 = (float)(b.clamp_sigma * b.clamp_sigma);
+    int n = 1 + (int)ceil(b.length / b.attenuator_step);
+    if (n < 4) n = 4;
+    o.n_axis = n;
+    o.inv_dz = (float)((n - 1) / b.length);
+    // stopping rates
+    std::vector<HostBeamRate> rates(b.n_stopping);
+    for (int k = 0; k < b.n_stopping; k++) {
+        const cb2_beam_rate& r = b.stopping_rates[k];
+        if (b.stopping_species[k] < 0 || b.stopping_species[k] >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "stopping species index out of range");
+        HostBeamRate& h = rates[k];
+        h.constant = r.n_e <= 0;
+        h.value = r.constant;
+        if (h.constant) continue;
+        if (r.n_e < 1 || r.n_n < 1 || r.n_t < 1 || !(r.sref > 0)) return cb2_fail(CB2_ERR_VALUE, "invalid beam stopping table");
+        h.le.resize(r.n_e); h.ln.resize(r.n_n); h.lt.resize(r.n_t); h.lsen.resize((size_t)r.n_e * r.n_n); h.lst.resize(r.n_t);
+        for (int i = 0; i < r.n_e; i++) h.le[i] = log10(r.e[i]);
+        for (int i = 0; i < r.n_n; i++) h.ln[i] = log10(r.n[i]);
+        for (int i = 0; i < r.n_t; i++) { h.lt[i] = log10(r.t[i]); h.lst[i] = log10(r.st[i] / r.sref); }
+        for (size_t i = 0; i < h.lsen.size(); i++) h.lsen[i] = log10(r.sen[i]);
+        if (r.n_e > 1 && r.n_n > 1) build_coef2d(h.le.data(), h.ln.data(), h.lsen.data(), r.n_e, r.n_n, h.coef);
+    }
+    // plasma state on the axis points (plasma space), evaluated by the device
+    std::vector<double> pts((size_t)n * 3), z(n);
+    for (int k = 0; k < n; k++) {
+        z[k] = (k == n - 1) ? b.length : b.length * k / (n - 1);     // np.linspace(0, length, nbeam)
+        const double pb[3] = {0.0, 0.0, z[k]};
+        mat_mul_point(b.beam_to_plasma, pb, &pts[3 * k]);
+    }
+    const int w = 2 + 5 * S.n_species + 3;
+    std::vector<double> state((size_t)n * w);
+    {
+        double *dp = nullptr, *ds = nullptr;
+        CB2_CUDA(cudaMalloc((void**)&dp, pts.size() * sizeof(double)));
+        int rc = cb2_cuda_check(cudaMalloc((void**)&ds, state.size() * sizeof(double)), "cudaMalloc(axis state)");
+        if (rc == CB2_OK) rc = cb2_cuda_check(cudaMemcpy(dp, pts.data(), pts.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(axis)");
+        if (rc == CB2_OK) rc = cb2_launch_sample_state(sc, dp, n, ds, 1, 0);
+        if (rc == CB2_OK) rc = cb2_cuda_check(cudaMemcpy(state.data(), ds, state.size() * sizeof(double), cudaMemcpyDeviceToHost), "cudaMemcpy(axis state)");
+        cudaFree(dp);
+        if (ds) cudaFree(ds);
+        if (rc != CB2_OK) return rc;
+    }
+    // beam velocity in plasma space: BEAM_AXIS transformed as a vector, normalised, times the speed
+    double ax[3] = {b.beam_to_plasma[2], b.beam_to_plasma[6], b.beam_to_plasma[10]};
+    const double al = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    for (int k = 0; k < 3; k++) ax[k] = ax[k] / al * speed;
+    std::vector<double> stop(n, 0.0);
+    for (int k = 0; k < n; k++) {
+        const double* st = &state[(size_t)k * w];
+        double density_sum = 0.0;
+        for (int q = 0; q < b.n_stopping; q++) {
+            const int sp = b.stopping_species[q];
+            density_sum += (double)d.species[sp].charge * d.species[sp].charge * st[2 + 5 * sp];
+        }
+        for (int q = 0; q < b.n_stopping; q++) {
+            const int sp = b.stopping_species[q], zc = d.species[sp].charge;
+            if (zc == 0) continue;                                   // no beam stopping data for neutrals (SURVEY A.7 caveat)
+            const double ne_t = st[2 + 5 * sp] * zc, ti = st[3 + 5 * sp];
+            const double iv[3] = {ax[0] - st[4 + 5 * sp], ax[1] - st[5 + 5 * sp], ax[2] - st[6 + 5 * sp]};
+            const double sp2 = iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2];
+            stop[k] += ne_t * rates[q].eval(sp2 / evamu, density_sum / zc, ti);
+        }
+    }
+    const double n0 = b.power / (b.energy * b.atomic_weight * ELEMENTARY_CHARGE) / speed;
+    std::vector<float> dens(n);
+    double cum = 0.0;
+    for (int k = 0; k < n; k++) {
+        if (k > 0) cum += 0.5 * (stop[k] + stop[k - 1]) * (z[k] - z[k - 1]);   // cumulative_trapezoid(..., initial=0)
+        dens[k] = (float)(n0 * exp(-cum / speed) * CB2_DENSITY_SCALE);
+    }
+    o.axis_density = A.upload(dens);
+    return A.rc;
+}
+
+// BeamCXPEC tables of a BEAM_CX_LINE model (openadas/rates/cx.pyx:66-103)
+static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevModelExt& e) {
+    if (r.n_eb <= 0) {
+        e.cx_const = 1;
+        e.cx_lconst = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+        return CB2_OK;
+    }
+    if (!(r.qref > 0)) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC qref must be positive");
+    const int nn[5] = {r.n_eb, r.n_ti, r.n_ni, r.n_z, r.n_b};
+    const double* xs[5] = {r.eb, r.ti, r.ni, r.z, r.b};
+    const double* qs[5] = {r.qeb, r.qti, r.qni, r.qz, r.qb};
+    const double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9;
+    for (int k = 0; k < 5; k++) {
+        const int n = nn[k];
+        if (n < 1) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC grids need at least one point");
+        std::vector<double> x(n), f(n);
+        for (int i = 0; i < n; i++) {
+            if (k == 0) {
+                if (!(qs[k][i] > 0)) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC qeb must be positive (log10 interpolation)");
+                x[i] = log10(xs[k][i]);
+                f[i] = log10(qs[k][i] / wavelength * conv) + CB2_PEC_LOG_OFFSET;
+            } else {
+                x[i] = xs[k][i] * (k == 2 ? CB2_DENSITY_SCALE : 1.0);     // n_ion knots in 1e19 m^-3
+                f[i] = qs[k][i] / r.qref;
+            }
+            if (i > 0 && !(x[i] > x[i - 1])) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC grids must be increasing");
+        }
+        e.cx_n[k] = n;
+        e.cx_single[k] = (float)f[0];
+        if (n > 1) {
+            e.cx_t[k] = make_knots1d(A, x.data(), n);
+            e.cx_c[k] = make_coef1d(A, x.data(), f.data(), n, 1.0);
+        }
+    }
+    return A.rc;
+}
+
 static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, DevScene& S, DevModel& o) {
     memset(&o, 0, sizeof o);
     o.kind = m.kind;
@@ -488,8 +672,10 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
         S.has_flat = 1;
         return A.rc;
     }
-    if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE && m.kind != CB2_MODEL_THERMAL_CX_LINE)
+    if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE && m.kind != CB2_MODEL_THERMAL_CX_LINE &&
+        m.kind != CB2_MODEL_BEAM_CX_LINE)
         return cb2_fail(CB2_ERR_TYPE, "unsupported model kind %d", m.kind);
+    if (m.kind == CB2_MODEL_BEAM_CX_LINE && !d.beam) return cb2_fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
     if (m.species < 0 || m.species >= d.n_species)
         return cb2_fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified line");
     if (!(m.wavelength > 0)) return cb2_fail(CB2_ERR_VALUE, "line wavelength must be positive");
@@ -500,7 +686,19 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     for (int k = 0; k < 3; k++) o.param[k] = (float)m.shape.param[k];
     // rate table: log10(PhotonToJ(rate, wavelength)) + 38 on (log10 ne, log10 te)   (pec.pyx:59-68)
     o.pec_grid = -1;
-    if (m.kind == CB2_MODEL_THERMAL_CX_LINE) {
+    if (m.kind == CB2_MODEL_BEAM_CX_LINE) {
+        // charge_exchange.pyx:311-349: effective emission coefficients per donor metastable; ground state only so far
+        const cb2_model_ext* x = m.ext;
+        if (!x || x->n_cx < 1) return cb2_fail(CB2_ERR_RUNTIME, "BeamCXLine needs its resolved CX rates");
+        if (x->n_cx > 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "excited donor metastables (BeamPopulationRate) are not supported yet");
+        DevModelExt e;
+        memset(&e, 0, sizeof e);
+        const int rc = convert_cx(A, x->cx[0], m.wavelength, e);
+        if (rc != CB2_OK) return rc;
+        o.ext = A.upload(std::vector<DevModelExt>(1, e));
+        o.pec_const = 1;
+        o.pec_value = -INFINITY;
+    } else if (m.kind == CB2_MODEL_THERMAL_CX_LINE) {
         // thermal_cx.pyx:140-148: one rate per donor species; only constant rates so far
         const cb2_model_ext* x = m.ext;
         if (!x) return cb2_fail(CB2_ERR_RUNTIME, "ThermalCXLine needs its resolved donors");
@@ -986,8 +1184,11 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         for (int m = 0; m < d->n_models; m++) {
             if ((rc = convert_model(A, *d, d->models[m], S, S.models[m])) != CB2_OK) break;
             const int sh = d->models[m].shape.kind, kd = d->models[m].kind;
-            const bool is_line = kd == CB2_MODEL_EXCITATION_LINE || kd == CB2_MODEL_RECOMBINATION_LINE || kd == CB2_MODEL_THERMAL_CX_LINE;
+            const bool is_line = kd == CB2_MODEL_EXCITATION_LINE || kd == CB2_MODEL_RECOMBINATION_LINE || kd == CB2_MODEL_THERMAL_CX_LINE ||
+                                 kd == CB2_MODEL_BEAM_CX_LINE;
             if (is_line && sh != CB2_SHAPE_GAUSSIAN && sh != CB2_SHAPE_MULTIPLET) need_b = true;
+            if (kd == CB2_MODEL_BEAM_CX_LINE) need_b = true;           // the CX rate depends on |B| (charge_exchange.pyx:222)
+            if ((kd == CB2_MODEL_BEAM_CX_LINE) != (d->beam != nullptr)) { rc = cb2_fail(CB2_ERR_TYPE, "a beam scene renders beam models only, and beam models need a beam"); break; }
         }
         if (rc != CB2_OK) break;
         S.need_b = need_b;
@@ -1017,6 +1218,11 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         if ((rc = cb2_cuda_check(cudaMalloc(&p, sizeof(cb2_stats)), "cudaMalloc(stats)")) != CB2_OK) break;
         A.ptrs.push_back(p);
         sc->stats_dev = (unsigned long long*)p;
+        if (d->beam) {
+            // the attenuation table needs the plasma state on the beam axis, which the device evaluates from the tables just uploaded
+            if ((rc = build_beam(A, *d, sc)) != CB2_OK) break;
+            if ((rc = cb2_cuda_check(cudaMemcpy(sc->dev, &S, sizeof(DevScene), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) != CB2_OK) break;
+        }
     } while (0);
     if (rc != CB2_OK) {
         A.release();
@@ -1192,6 +1398,20 @@ extern "C" int cb2_scene_profile(cb2_scene* sc, int enable, double* ms_out, int6
     return CB2_OK;
 }
 
+extern "C" int cb2_beam_sample(cb2_scene* sc, const double* beam_points, int64_t n, double* out) {
+    if (!sc || !beam_points || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    if (!sc->host.beam.present) return cb2_fail(CB2_ERR_VALUE, "the scene has no beam");
+    if (n <= 0) return CB2_OK;
+    CB2_CUDA(cudaSetDevice(sc->device));
+    int rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 6, (size_t)n * 3 * sizeof(double))) != CB2_OK) return rc;
+    if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 7, (size_t)n * 4 * sizeof(double))) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpy(sc->stage[6], beam_points, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    if ((rc = cb2_launch_beam_sample(sc, (const double*)sc->stage[6], n, (double*)sc->stage[7], 0)) != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpy(out, sc->stage[7], (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB2_OK;
+}
+
 extern "C" int cb2_state_width(const cb2_scene* sc) { return sc ? 2 + 5 * sc->host.n_species + 3 : 0; }
 
 extern "C" int cb2_sample_state(cb2_scene* sc, const double* points, int64_t n, double* out) {
@@ -1203,7 +1423,7 @@ extern "C" int cb2_sample_state(cb2_scene* sc, const double* points, int64_t n, 
     if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 6, (size_t)n * 3 * sizeof(double))) != CB2_OK) return rc;
     if ((rc = stage_reserve(sc->stage, sc->stage_bytes, 7, (size_t)n * w * sizeof(double))) != CB2_OK) return rc;
     CB2_CUDA(cudaMemcpy(sc->stage[6], points, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
-    if ((rc = cb2_launch_sample_state(sc, (const double*)sc->stage[6], n, (double*)sc->stage[7], 0)) != CB2_OK) return rc;
+    if ((rc = cb2_launch_sample_state(sc, (const double*)sc->stage[6], n, (double*)sc->stage[7], 0, 0)) != CB2_OK) return rc;
     CB2_CUDA(cudaMemcpy(out, sc->stage[7], (size_t)n * w * sizeof(double), cudaMemcpyDeviceToHost));
     return CB2_OK;
 }

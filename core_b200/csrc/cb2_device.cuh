@@ -123,6 +123,7 @@ struct AxCtx {
     // branch-free Blend2D: value = we * edge[tri_c] + wc * core(ci, ct)
     float we, wc;
     int tri_c;
+    bool b_outside;  // the B-field was taken from the clamped psi grid (counted as out of domain only if B is actually used)
 };
 
 __device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py) {
@@ -173,7 +174,7 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd
     const float inv_r = c.R > 0.f ? 1.0f / c.R : 0.f;
     c.cphi = c.R > 0.f ? x * inv_r : 1.f;
     c.sphi = y * inv_r;
-    c.m = 0.f; c.tri = -1; c.ci = 0; c.ct = 0.f; c.psi = 0.f; c.in_lcfs = false;
+    c.m = 0.f; c.tri = -1; c.ci = 0; c.ct = 0.f; c.psi = 0.f; c.in_lcfs = false; c.b_outside = false;
     c.br = c.bt = c.bz = 0.f;
     if (!A.present) return;
     const bool in_poly = polygon_contains(A, c.R, c.Z);
@@ -206,7 +207,7 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd
     if (want_pol) {
         if (!have_cell) {
             cell = locate2d(A.psin, c.R, c.Z);
-            if (!cell.inside) ood++;
+            c.b_outside = !cell.inside;
         }
         c.br = -eval2d(A.dpsi_dz, cell) * inv_r;   // MagneticField.evaluate, efit.pyx:443-445
         c.bz = eval2d(A.dpsi_dr, cell) * inv_r;
@@ -308,7 +309,33 @@ struct SampleIn {
     float x, y, z;       // plasma-space position
     float dx, dy, dz;    // unit ray direction in plasma space
     float weight;        // trapezium weight (h or h/2), metres
+    // beam scenes: donor density (1e19 m^-3) and donor velocity (m/s, plasma frame) at the sample
+    float donor, bvx, bvy, bvz;
 };
+
+// Beam.density -> SingleRayAttenuator.density (beam/node.pyx:214-234, singleray.pyx:152-168), beam coordinates, 1e19 m^-3
+__device__ __forceinline__ float beam_density(const DevBeam& B, float x, float y, float z) {
+    if (z < 0.f || z > B.length) return 0.f;
+    const float sx2 = fmaf(z * B.tanx, z * B.tanx, B.sigma2), sy2 = fmaf(z * B.tany, z * B.tany, B.sigma2);
+    const float nr2 = x * x / sx2 + y * y / sy2;
+    if (B.clamp_to_zero && nr2 > B.clamp2) return 0.f;
+    const float g = __expf(-0.5f * nr2) * 0.15915494309189535f * rsqrtf(sx2 * sy2);
+    // Interpolator1DArray(beam_z, beam_density, 'linear', 'nearest')
+    const float f = fminf(fmaxf(z * B.inv_dz, 0.f), (float)(B.n_axis - 1));
+    const int i = min((int)f, B.n_axis - 2);
+    const float t = f - (float)i;
+    const float a = __ldg(B.axis_density + i), b = __ldg(B.axis_density + i + 1);
+    return fmaf(t, b - a, a) * g;
+}
+
+// Beam.direction (beam/node.pyx:236-279), beam coordinates
+__device__ __forceinline__ float3 beam_direction(const DevBeam& B, float x, float y, float z) {
+    if (z <= 0.f) return make_float3(0.f, 0.f, 1.f);
+    const float ztx = z * z * B.tanx * B.tanx, zty = z * z * B.tany * B.tany;
+    const float ex = x * ztx / (B.sigma2 + ztx), ey = y * zty / (B.sigma2 + zty);
+    const float inv = rsqrtf(ex * ex + ey * ey + z * z);
+    return make_float3(ex * inv, ey * inv, z * inv);
+}
 
 __device__ __forceinline__ double xform_row(const double* m, double x, double y, double z, bool point) {
     // ((m0 x + m1 y) + m2 z) (+ m3), separate roundings like the reference's compiled C

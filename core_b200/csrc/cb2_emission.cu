@@ -964,13 +964,15 @@ static int emission_batch(cb2_scene* sc, const DevRays& rays, void* out, int out
 // ------------------------------------------------------------------------------------------------------------------
 // per-point plasma state (parity tests of the flattened function tree)
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void sample_state_kernel(const DevScene* __restrict__ Sp, const double* __restrict__ pts, int64_t n, double* __restrict__ out) {
+__global__ void sample_state_kernel(const DevScene* __restrict__ Sp, const double* __restrict__ pts, int64_t n, double* __restrict__ out,
+                                    int in_plasma_space) {
     const DevScene& S = *Sp;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    double pd[3];
-    for (int k = 0; k < 3; k++) pd[k] = xform_row(S.w2p + 4 * k, px, py, pz, true);
+    double pd[3] = {px, py, pz};
+    if (!in_plasma_space)
+        for (int k = 0; k < 3; k++) pd[k] = xform_row(S.w2p + 4 * k, px, py, pz, true);
     const float p[3] = {(float)pd[0], (float)pd[1], (float)pd[2]};
     AxCtx ctx;
     unsigned ood = 0;
@@ -990,7 +992,26 @@ __global__ void sample_state_kernel(const DevScene* __restrict__ Sp, const doubl
     o[2 + 5 * S.n_species] = b.x; o[3 + 5 * S.n_species] = b.y; o[4 + 5 * S.n_species] = b.z;
 }
 
-int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t st) {
+// Beam.density / Beam.direction probe: out[n][4]
+__global__ void beam_sample_kernel(const DevScene* __restrict__ Sp, const double* __restrict__ pts, int64_t n, double* __restrict__ out) {
+    const DevScene& S = *Sp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = (float)pts[3 * i], y = (float)pts[3 * i + 1], z = (float)pts[3 * i + 2];
+    const float3 dv = beam_direction(S.beam, x, y, z);
+    out[4 * i] = (double)beam_density(S.beam, x, y, z) * (1.0 / CB2_DENSITY_SCALE);
+    out[4 * i + 1] = dv.x; out[4 * i + 2] = dv.y; out[4 * i + 3] = dv.z;
+}
+
+int cb2_launch_beam_sample(const cb2_scene* sc, const double* beam_points_dev, int64_t n, double* out_dev, cudaStream_t st) {
+    const int bs = 128;
+    beam_sample_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(sc->dev, beam_points_dev, n, out_dev);
+    int rc = cb2_cuda_check(cudaGetLastError(), "beam_sample_kernel launch");
+    if (rc == CB2_OK) rc = cb2_cuda_check(cudaStreamSynchronize(st), "beam_sample sync");
+    return rc;
+}
+
+int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, int in_plasma_space, cudaStream_t st) {
     // the state probe always wants B and the poloidal direction: use a scene copy with the flags forced on
     DevScene tmp = sc->host;
     tmp.need_b = 1;
@@ -1000,7 +1021,7 @@ int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64
     int rc = cb2_cuda_check(cudaMemcpyAsync(dtmp, &tmp, sizeof(DevScene), cudaMemcpyHostToDevice, st), "cudaMemcpy(scene)");
     if (rc == CB2_OK) {
         const int bs = 128;
-        sample_state_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(dtmp, points_dev, n, out_dev);
+        sample_state_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(dtmp, points_dev, n, out_dev, in_plasma_space);
         rc = cb2_cuda_check(cudaGetLastError(), "sample_state_kernel launch");
         if (rc == CB2_OK) rc = cb2_cuda_check(cudaStreamSynchronize(st), "sample_state sync");
     }

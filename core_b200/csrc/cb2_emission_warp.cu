@@ -64,8 +64,9 @@ struct ModelCtx {
     float rnorm[3];          // ZeemanStructure ratio normalisation per polarisation group
 };
 
-__device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, const AxCtx& ctx, LineCache& lc) {
+__device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, const AxCtx& ctx, LineCache& lc, unsigned& ood) {
     if (lc.have_b) return;
+    if (S.b_kind != 0 && ctx.b_outside) ood++;
     const float3 bf = eval_b_field(S, ctx);
     lc.bm = sqrtf(bf.x * bf.x + bf.y * bf.y + bf.z * bf.z);
     const float c = lc.bm > 0.f ? (bf.x * in.dx + bf.y * in.dy + bf.z * in.dz) / lc.bm : 0.f;
@@ -80,6 +81,7 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
                                             bool live, LineCache& lc, ModelCtx& mc, unsigned& ood) {
     mc.on = false;
     bool on = live;
+    if (M.kind == CB2_MODEL_BEAM_CX_LINE) on = in.weight > 0.f && in.donor > 0.f;    // no ne / te condition on the beam path
     if (on && M.species != lc.cur) {
         lc.cur = M.species;
         const DevSpecies& sp = S.species[lc.cur];
@@ -88,10 +90,54 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
         const float3 v = eval_vector(sp.velocity, ctx);
         lc.vd = v.x * in.dx + v.y * in.dy + v.z * in.dz;   // velocity projected on the (unit) ray direction
     }
-    on = on && lc.ni > 0.f;
+    on = on && (lc.ni > 0.f);
     if (!on) return;
     float radiance;
-    if (M.kind == CB2_MODEL_THERMAL_CX_LINE) {
+    if (M.kind == CB2_MODEL_BEAM_CX_LINE) {
+        // BeamCXLine.emission (charge_exchange.pyx:117-167), ground-state donor: radiance = 1/(4 pi) n_beam n_rec q_eff
+        if (!(in.donor > 0.f) || lc.ni == 0.f || lc.ts == 0.f) return;
+        const DevModelExt& X = *M.ext;
+        float lq;                                             // log10(q_eff) + 38, then the linear factors
+        float factor = 1.0f;
+        if (X.cx_const) lq = X.cx_lconst;
+        else {
+            const float3 vr = eval_vector(S.species[M.species].velocity, ctx);
+            const float ivx = in.bvx - vr.x, ivy = in.bvy - vr.y, ivz = in.bvz - vr.z;
+            const float energy = (ivx * ivx + ivy * ivy + ivz * ivz) * 5.18213506e-9f;    // m_u / (2 e): (m/s)^2 -> eV/amu
+            // Plasma.ion_density / z_effective (plasma/node.pyx:396-462)
+            float n_ion = 0.f, snz = 0.f, snz2 = 0.f;
+            for (int sidx = 0; sidx < S.n_species; sidx++) {
+                const float n = eval_scalar_t<AXONLY>(S.species[sidx].density, ctx, in.x, in.y, in.z);
+                const float zc = (float)S.species[sidx].charge;
+                n_ion += n;
+                snz = fmaf(n, zc, snz);
+                snz2 = fmaf(n * zc, zc, snz2);
+            }
+            const float zeff = snz > 0.f ? snz2 / snz : 0.f;
+            need_b(S, in, ctx, lc, ood);
+            if (!(energy > 0.f)) return;
+            const float args[5] = {log10f(energy), lc.ts, n_ion, zeff, lc.bm};
+            lq = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                float v;
+                if (X.cx_n[k] == 1) v = X.cx_single[k];
+                else {
+                    // (a few fp32 ulps of slack: Zeff of a Z = 1 plasma must not count as below a table that starts at 1)
+                    if (args[k] < X.cx_t[k].xmin - 4e-6f * fabsf(X.cx_t[k].xmin) || args[k] > X.cx_t[k].xmax + 4e-6f * fabsf(X.cx_t[k].xmax)) ood++;
+                    int ci; float ct;
+                    locate1d(X.cx_t[k], args[k], ci, ct);
+                    v = horner4(__ldg(X.cx_c[k] + ci), ct);
+                }
+                if (k == 0) lq = v;
+                else {
+                    factor *= v;
+                    if (!(factor > 0.f)) return;              // the reference returns 0 as soon as a partial product is <= 0
+                }
+            }
+        }
+        radiance = RECIP_4_PI * exp10f(lq) * factor * in.donor * lc.ni;
+    } else if (M.kind == CB2_MODEL_THERMAL_CX_LINE) {
         // radiance = 1/(4 pi) n_receiver sum_donors n_donor q_donor(ne, te, T_donor)   (thermal_cx.pyx:103-111; constant q)
         const DevModelExt& X = *M.ext;
         float weighted = 0.f;
@@ -148,7 +194,7 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
         if (M.shape == CB2_SHAPE_GAUSSIAN || M.shape == CB2_SHAPE_MULTIPLET) { mc.on = true; return; }
     }
     // Zeeman family and Stark: field strength and angle to the line of sight (zeeman.pyx:125-131)
-    need_b(S, in, ctx, lc);
+    need_b(S, in, ctx, lc, ood);
     mc.bzero = lc.bm == 0.f;
     const float cos_sqr = lc.cos_sqr, sin_sqr = 1.0f - cos_sqr;
     mc.a_pi = 0.5f * sin_sqr * mc.amp;
@@ -540,10 +586,18 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
     const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
     const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
     SampleIn in;
+    in.donor = 0.f; in.bvx = in.bvy = in.bvz = 0.f;
+    const bool has_beam = S.beam.present != 0;
     {
-        // ray direction in plasma space (direction.transform(local_to_plasma), normalised inside doppler_shift)
-        const double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
-                     d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        // ray direction in plasma space (direction.transform(local_to_plasma), normalised inside doppler_shift); in a beam
+        // scene w2p is world -> beam and the observation direction goes on to plasma space (beam/material.pyx:62-65)
+        double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
+               d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        if (has_beam) {
+            const double e0 = xform_row(S.beam.l2p, d0, d1, d2, false), e1 = xform_row(S.beam.l2p + 4, d0, d1, d2, false),
+                         e2 = xform_row(S.beam.l2p + 8, d0, d1, d2, false);
+            d0 = e0; d1 = e1; d2 = e2;
+        }
         const double dl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
         in.dx = (float)(d0 / dl); in.dy = (float)(d1 / dl); in.dz = (float)(d2 / dl);
     }
@@ -568,20 +622,33 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             const int k = g * 32 + lane;
             const bool active = k <= iv;
             const double tk = __dmul_rn((double)k, sgm.h);
-            const double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
-                         pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
-            in.x = (float)pxd; in.y = (float)pyd; in.z = (float)pzd;
+            double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
+                   pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
             in.weight = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
+            if (has_beam) {
+                // the sample is in beam coordinates: donor density and velocity there, then on to plasma space
+                const float xb = (float)pxd, yb = (float)pyd, zb = (float)pzd;
+                in.donor = active ? beam_density(S.beam, xb, yb, zb) : 0.f;
+                const float3 bd = beam_direction(S.beam, xb, yb, zb);
+                const double* L = S.beam.l2p;
+                float vx = (float)L[0] * bd.x + (float)L[1] * bd.y + (float)L[2] * bd.z, vy = (float)L[4] * bd.x + (float)L[5] * bd.y + (float)L[6] * bd.z,
+                      vz = (float)L[8] * bd.x + (float)L[9] * bd.y + (float)L[10] * bd.z;
+                const float sc_ = S.beam.speed * rsqrtf(vx * vx + vy * vy + vz * vz);
+                in.bvx = vx * sc_; in.bvy = vy * sc_; in.bvz = vz * sc_;
+                const double qx = xform_row(L, pxd, pyd, pzd, true), qy = xform_row(L + 4, pxd, pyd, pzd, true), qz = xform_row(L + 8, pxd, pyd, pzd, true);
+                pxd = qx; pyd = qy; pzd = qz;
+            }
+            in.x = (float)pxd; in.y = (float)pyd; in.z = (float)pzd;
             AxCtx ctx;
             float ne = 0.f, te = 0.f;
-            if (active) {
+            if (active && (!has_beam || in.donor > 0.f)) {        // beam scenes: nothing is evaluated where the beam density is zero
                 ax_setup(S, pxd, pyd, pzd, ctx, ood);
                 ne = eval_scalar_t<AXONLY>(S.ne, ctx, in.x, in.y, in.z);
                 te = eval_scalar_t<AXONLY>(S.te, ctx, in.x, in.y, in.z);
             } else {
-                ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false;
+                ctx.m = 0.f; ctx.tri = -1; ctx.in_lcfs = false; ctx.b_outside = false;
             }
-            const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+            const bool live = has_beam ? (in.weight > 0.f && in.donor > 0.f) : (ne > 0.f && te > 0.f && in.weight > 0.f);
             const unsigned live_mask = __ballot_sync(FULL, live);
             const int64_t G = G0 + g;
             if (lane == 0) gmask[G] = live_mask;
@@ -590,7 +657,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             LineCache lc;
             lc.cur = -1; lc.ni = lc.ts = lc.vd = 0.f; lc.have_b = false; lc.bm = lc.cos_sqr = 0.f; lc.grid = -2;
             lc.lne = lc.lte = 0.f;
-            if (live) {
+            if (live && ne > 0.f && te > 0.f) {
                 lc.lne = log10f(ne) + 19.0f;                       // densities are stored in units of 1e19 m^-3
                 lc.lte = log10f(te);
             }

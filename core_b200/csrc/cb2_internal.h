@@ -102,6 +102,13 @@ struct DevModelExt {
     int donor_species[CB2_MAX_SPECIES];
     float donor_lrate[CB2_MAX_SPECIES];   // log10(rate [W m^3]) + 38, constant rates
     int line_rad, recom, n_hyd, hyd[3];
+    // BEAM_CX_LINE (ground-state donor): rate = 10^c0(log10 E) c1(Ti) c2(n_ion) c3(Zeff) c4(|B|)   (openadas/rates/cx.pyx:104-142)
+    int cx_const;                          // 1: constant rate
+    float cx_lconst;                       // log10(rate [W m^3]) + 38
+    int cx_n[5];                           // knots per factor (1: constant factor cx_single)
+    float cx_single[5];
+    DevTable1D cx_t[5];                    // knots: log10 E[eV/amu], Ti[eV], n_ion[1e19 m^-3], Zeff, |B|[T]
+    const float4* cx_c[5];
     int has[3];                            // plt, prb, prc present
     int is_const[3];
     float lconst[3];                       // log10(rate) + 38
@@ -169,6 +176,20 @@ struct DevBrems {
 };
 #define CB2_MAX_BREMS_Z 8
 
+// Beam + SingleRayAttenuator (beam/node.pyx, attenuator/singleray.pyx): in a beam scene the integrator marches in the beam
+// frame (DevScene::w2p holds world -> beam) and l2p takes the sample to plasma space
+struct DevBeam {
+    int present;
+    double l2p[12];                // beam -> plasma
+    float speed;                   // sqrt(2 E e / m_u), m/s
+    float length, sigma2, tanx, tany;
+    int clamp_to_zero;
+    float clamp2;                  // clamp_sigma^2
+    int n_axis;                    // attenuation table on z = linspace(0, length, n_axis)
+    float inv_dz;
+    const float* axis_density;     // [n_axis] in units of 1e19 m^-3
+};
+
 struct alignas(16) DevScene {
     int n_species, n_models, n_comp;
     int bins, bins_padded;
@@ -186,6 +207,7 @@ struct alignas(16) DevScene {
     DevComp comps[CB2_MAX_COMP];
     DevAxisym ax;
     DevBrems brems;
+    DevBeam beam;
     // modified-Lorentzian (Stark) cumulative profile, universal in u = (x - centre)/FWHM (stark.pyx:52-81):
     // knots u_k = k/512 on [0, 4]: (Phi(u_k), dPhi/du(u_k)); beyond u = 4 an asymptotic tail series is used
     int has_flat;                  // some model adds a wavelength-independent radiance (TotalRadiatedPower)
@@ -290,7 +312,9 @@ size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                              unsigned long long* stats, int count_samples, cudaStream_t stream);
 int64_t cb2_warp_batch_rays(const cb2_scene* sc);
-int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, cudaStream_t stream);
+int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, int points_in_plasma_space,
+                            cudaStream_t stream);
+int cb2_launch_beam_sample(const cb2_scene* sc, const double* beam_points_dev, int64_t n, double* out_dev, cudaStream_t stream);
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate,
                   int64_t* row_offset, int32_t* columns, double* lengths, unsigned long long* stats_dev, cudaStream_t stream);
 int cb2_launch_scan(int64_t* counts_inout, int64_t n, cudaStream_t stream);

@@ -1,0 +1,82 @@
+"""GPU parity tests of the beam path: Beam.density / direction, SingleRayAttenuator and BeamCXLine through
+the CUDA library vs the oracle and vs the reference's closed forms (cherab/core/tests/test_beam.py, test_beamcxline.py)."""
+import numpy as np
+import pytest
+
+import core_b200 as cb
+from core_b200 import _abi, generomak
+from core_b200.engine import EmissionScene
+from oracle import oracle
+from test_oracle_beam import beam_scene, cx_case
+
+pytestmark = pytest.mark.gpu
+
+
+def parity(got, ref, rtol=1e-4, floor=1e-9):
+    tol = rtol * np.abs(ref) + floor * np.abs(ref).max(axis=-1, keepdims=True)
+    return float(np.max(np.abs(got - ref) / (tol + 1e-300)))
+
+
+def beam_sample(scene, pts):
+    import ctypes as C
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((pts.shape[0], 4))
+    _abi.check(scene._lib, scene._lib.cb2_beam_sample(scene._h, pts.ctypes.data_as(_abi.c_double_p), pts.shape[0], out.ctypes.data_as(_abi.c_double_p)))
+    return out[:, 0], out[:, 1:]
+
+
+def test_beam_density_and_direction():
+    plasma, beam = beam_scene(1e-13, sigma=0.2, divergence_x=1.0, divergence_y=2.0, length=10.0)
+    flat = cb.flatten_beam_scene(beam, 655.1, 657.1, 16)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([[[0, 0, 0.8], [0.5, 0.5, 0.8], [0, 0, -1.0], [0, 0, 10.5]],
+                          np.stack([rng.uniform(-1, 1, 200), rng.uniform(-1, 1, 200), rng.uniform(0, 10, 200)], axis=1)])
+    scene = EmissionScene(flat)
+    dens, dirs = beam_sample(scene, pts)
+    scene.close()
+    rd, rdir = oracle.beam_sample(flat, pts)
+    assert dens[2] == 0 and dens[3] == 0 and np.array_equal(dens == 0, rd == 0)
+    nz = rd > 0
+    assert np.max(np.abs(dens[nz] / rd[nz] - 1)) < 2e-5          # fp32 evaluation
+    assert np.max(np.abs(dirs - rdir)) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [None, cb.ZeemanTriplet])
+def test_beam_cx_line_slab(shape):
+    # test_beamcxline.py:85-173 through the CUDA path
+    plasma, beam, flat, rays = cx_case(shape)
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"] == 1001
+    assert parity(got, ref) <= 1.0
+
+
+def test_beam_cx_generomak_tabulated_rates():
+    # config C5 shape at small size: diverging, attenuated beam through the Generomak plasma, ADF12/ADF21-shaped synthetic
+    # tables, C5+ n = 8 -> 7 CX line observed by a fan of sight lines crossing the beam
+    plasma = generomak.get_plasma()
+    atomic = cb.SyntheticADAS()
+    atomic.wavelength = lambda ion, charge, transition: 529.05
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.look_at((3.2, -0.4, 0.0), (1.0, 0.3, 0.05)))       # z axis points into the plasma
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.05, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.0025, min_samples=10)
+    beam.models = [cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    flat = cb.flatten_beam_scene(beam, 526.0, 532.0, 256)
+    # sight lines from above towards points on the beam axis
+    axis_pts = (np.asarray(beam.transform) @ np.stack([np.zeros(12), np.zeros(12), np.linspace(0.6, 2.4, 12), np.ones(12)]))[:3].T
+    origin = np.tile([[1.8, 0.2, 1.6]], (12, 1))
+    rays = cb.beam_ray_segments(beam, origin, axis_pts - origin)
+    assert rays.n_segments == 12
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"] and ref.max() > 0
+    assert abs(st["out_of_domain"] - rst["out_of_domain"]) <= 4     # a few edge samples leave the tabulated ranges: clamped and counted
+    assert parity(got, ref) <= 1.0
