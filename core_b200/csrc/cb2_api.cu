@@ -1201,6 +1201,10 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
             for (int i = 0; i < d->n_species; i++)
                 ax_only = ax_only && d->species[i].density.kind == CB2_FIELD_AXISYM_BLEND && d->species[i].temperature.kind == CB2_FIELD_AXISYM_BLEND;
             sc->ax_only = ax_only;
+            sc->feat = d->beam != nullptr;
+            for (int m = 0; m < d->n_models; m++)
+                sc->feat |= d->models[m].kind == CB2_MODEL_THERMAL_CX_LINE || d->models[m].kind == CB2_MODEL_TOTAL_RADIATED_POWER ||
+                            d->models[m].kind == CB2_MODEL_BEAM_CX_LINE;
         }
         if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;  // decides the Bremsstrahlung mode (direct / moments)
         if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)

@@ -76,12 +76,12 @@ __device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, co
 
 // ExcitationLine / RecombinationLine .emission up to the add_line call (impact_excitation.pyx:86-100) plus the
 // component-independent part of LineShapeModel.add_line
-template <int AXONLY>
+template <int AXONLY, int FEAT>
 __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M, const SampleIn& in, const AxCtx& ctx, float ne, float te,
                                             bool live, LineCache& lc, ModelCtx& mc, unsigned& ood) {
     mc.on = false;
     bool on = live;
-    if (M.kind == CB2_MODEL_BEAM_CX_LINE) on = in.weight > 0.f && in.donor > 0.f;    // no ne / te condition on the beam path
+    if (FEAT && M.kind == CB2_MODEL_BEAM_CX_LINE) on = in.weight > 0.f && in.donor > 0.f;    // no ne / te condition on the beam path
     if (on && M.species != lc.cur) {
         lc.cur = M.species;
         const DevSpecies& sp = S.species[lc.cur];
@@ -93,7 +93,7 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
     on = on && (lc.ni > 0.f);
     if (!on) return;
     float radiance;
-    if (M.kind == CB2_MODEL_BEAM_CX_LINE) {
+    if (FEAT && M.kind == CB2_MODEL_BEAM_CX_LINE) {
         // BeamCXLine.emission (charge_exchange.pyx:117-167), ground-state donor: radiance = 1/(4 pi) n_beam n_rec q_eff
         if (!(in.donor > 0.f) || lc.ni == 0.f || lc.ts == 0.f) return;
         const DevModelExt& X = *M.ext;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
             }
         }
         radiance = RECIP_4_PI * exp10f(lq) * factor * in.donor * lc.ni;
-    } else if (M.kind == CB2_MODEL_THERMAL_CX_LINE) {
+    } else if (FEAT && M.kind == CB2_MODEL_THERMAL_CX_LINE) {
         // radiance = 1/(4 pi) n_receiver sum_donors n_donor q_donor(ne, te, T_donor)   (thermal_cx.pyx:103-111; constant q)
         const DevModelExt& X = *M.ext;
         float weighted = 0.f;
@@ -557,7 +557,9 @@ __global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile i
 #ifndef CB2_STATE_MINB
 #define CB2_STATE_MINB 5
 #endif
-template <int NW, int MOM, int AXONLY>
+// FEAT = 0: plasma line models and Bremsstrahlung only (the benchmark's scene); FEAT = 1 adds the beam frame / BeamCXLine,
+// ThermalCXLine and TotalRadiatedPower branches (kept out of the common instance: they cost registers and instruction cache)
+template <int NW, int MOM, int AXONLY, int FEAT>
 __global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, double* __restrict__ flat_out,
@@ -587,7 +589,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
     const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
     SampleIn in;
     in.donor = 0.f; in.bvx = in.bvy = in.bvz = 0.f;
-    const bool has_beam = S.beam.present != 0;
+    const bool has_beam = FEAT && S.beam.present != 0;
     {
         // ray direction in plasma space (direction.transform(local_to_plasma), normalised inside doppler_shift); in a beam
         // scene w2p is world -> beam and the observation direction goes on to plasma space (beam/material.pyx:62-65)
@@ -665,12 +667,12 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
-                if (M.kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
+                if (FEAT && M.kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
                     if (live) flat_acc += total_radiated_power<AXONLY>(S, M, in, ctx, ne, lc.lne, lc.lte, ood);
                     continue;
                 }
                 ModelCtx mc;
-                model_setup<AXONLY>(S, M, in, ctx, ne, te, live, lc, mc, ood);
+                model_setup<AXONLY, FEAT>(S, M, in, ctx, ne, te, live, lc, mc, ood);
                 const bool any_on = __any_sync(FULL, mc.on);
                 for (int kc = 0; kc < M.ncomp; kc++) {
                     float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
@@ -683,17 +685,17 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
         }
         G0 += n_groups;
     }
-    if (flat_out) {
+    if (FEAT && flat_out) {
         // per-ray wavelength-independent radiance: fp32 per thread, fp64 across the CTA
         for (int off = 16; off > 0; off >>= 1) flat_acc += __shfl_down_sync(FULL, flat_acc, off);
         if (lane == 0 && flat_acc != 0.f) atomicAdd(&flat_s, (double)flat_acc);
     }
-    if (MOM || flat_out) __syncthreads();
+    if (MOM || (FEAT && flat_out)) __syncthreads();
     if (MOM) {
         float* row = mom_out + (size_t)ray * k_pad;
         for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
     }
-    if (flat_out && tid == 0) flat_out[ray] = flat_s;
+    if (FEAT && flat_out && tid == 0) flat_out[ray] = flat_s;
     if (stats) {
         unsigned long long nb = n_brems, oodl = ood;
         for (int off = 16; off > 0; off >>= 1) {
@@ -871,17 +873,24 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         // K1a
         {
             const size_t smem = moments ? (size_t)B.k_pad * sizeof(double) : 0;
-#define CB2_STATE(MOM, AX)                                                                                                        \
+#define CB2_STATE(MOM, AX, FT)                                                                                                    \
     do {                                                                                                                          \
-        auto kern = state_kernel<4, MOM, AX>;                                                                                     \
+        auto kern = state_kernel<4, MOM, AX, FT>;                                                                                 \
         if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom,                  \
-                                                                  S.has_flat ? sc->flat : nullptr, count_samples, dbg);   \
+        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom,          \
+                                                                  S.has_flat ? sc->flat : nullptr, count_samples, dbg);           \
     } while (0)
-            if (moments && sc->ax_only) CB2_STATE(1, 1);
-            else if (moments) CB2_STATE(1, 0);
-            else if (sc->ax_only) CB2_STATE(0, 1);
-            else CB2_STATE(0, 0);
+            const int sel = (moments ? 4 : 0) | (sc->ax_only ? 2 : 0) | (sc->feat ? 1 : 0);
+            switch (sel) {
+            case 0: CB2_STATE(0, 0, 0); break;
+            case 1: CB2_STATE(0, 0, 1); break;
+            case 2: CB2_STATE(0, 1, 0); break;
+            case 3: CB2_STATE(0, 1, 1); break;
+            case 4: CB2_STATE(1, 0, 0); break;
+            case 5: CB2_STATE(1, 0, 1); break;
+            case 6: CB2_STATE(1, 1, 0); break;
+            default: CB2_STATE(1, 1, 1); break;
+            }
 #undef CB2_STATE
             if ((rc = cb2_cuda_check(cudaGetLastError(), "state_kernel launch")) != CB2_OK) return rc;
         }

@@ -250,6 +250,7 @@ struct cb2_scene {
     int nw, bpl, smem_bytes;   // CTA-phased kernel (direct Bremsstrahlung)
     int bin_nw;                // bin_kernel warps per ray
     int warp_kernel;         // 1: warp-autonomous kernel (cb2_emission_warp.cu), 0: CTA-phased kernel with the direct Bremsstrahlung path
+    int feat;                // the scene needs the general state kernel (beam, ThermalCXLine, TotalRadiatedPower)
     int ax_only;             // every scalar field of the scene is an AXISYM_BLEND: branch-free field evaluation
     int acc_f64;             // warp kernel: private accumulators in fp64 (else fp32)
     // staging buffers for the host-buffer entry point
