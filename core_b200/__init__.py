@@ -7,7 +7,7 @@ No CPU fallback: calls fail loudly if the CUDA library or a GPU is missing.
 """
 from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, SyntheticADAS, carbon, deuterium, helium,
                      hydrogen, neon, nitrogen, tritium)
-from .beam import (Beam, BeamCXLine, BeamCXTable, BeamStoppingTable, ConstantBeamCXPEC, SingleRayAttenuator, beam_ray_segments,
+from .beam import (Beam, BeamCXLine, BeamEmissionLine, BeamCXTable, BeamStoppingTable, ConstantBeamCXPEC, SingleRayAttenuator, beam_ray_segments,
                    flatten_beam_scene)
 from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate

@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -19,7 +19,7 @@ STATUS_EXC = {-1: ValueError, -2: RuntimeError, -3: TypeError, -4: NotImplemente
 FIELD_CONSTANT, FIELD_GAUSSIAN_VOLUME, FIELD_AXISYM_BLEND, FIELD_SLAB_ION, FIELD_SLAB_NEUTRAL = range(5)
 SHAPE_GAUSSIAN, SHAPE_MULTIPLET, SHAPE_ZEEMAN_TRIPLET, SHAPE_PARAM_ZEEMAN, SHAPE_ZEEMAN_MULTIPLET, SHAPE_STARK = range(6)
 POL_PI, POL_SIGMA, POL_NO = range(3)
-MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG, MODEL_THERMAL_CX_LINE, MODEL_TOTAL_RADIATED_POWER, MODEL_BEAM_CX_LINE = range(6)
+MODEL_EXCITATION_LINE, MODEL_RECOMBINATION_LINE, MODEL_BREMSSTRAHLUNG, MODEL_THERMAL_CX_LINE, MODEL_TOTAL_RADIATED_POWER, MODEL_BEAM_CX_LINE, MODEL_BEAM_EMISSION_LINE = range(7)
 RT_CYLINDRICAL, RT_CARTESIAN = range(2)
 
 
@@ -98,7 +98,9 @@ class ModelExt(C.Structure):
     _fields_ = [("n_donors", C.c_int32), ("_pad", C.c_int32), ("donor_species", c_int32_p), ("donor_rates", C.POINTER(Rate3D)),
                 ("line_rad_species", C.c_int32), ("recom_species", C.c_int32), ("n_hydrogen", C.c_int32), ("has_plt", C.c_int32),
                 ("has_prb", C.c_int32), ("has_prc", C.c_int32), ("hydrogen_species", c_int32_p),
-                ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D), ("n_cx", C.c_int32), ("_pad3", C.c_int32), ("cx", C.POINTER(CXRate))]
+                ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D), ("n_cx", C.c_int32), ("_pad3", C.c_int32), ("cx", C.POINTER(CXRate)),
+                ("n_bes", C.c_int32), ("_pad4", C.c_int32), ("bes_species", c_int32_p), ("bes_rates", C.POINTER(BeamRate)),
+                ("mse_ratios", C.c_double * 4)]
 
 
 class ModelDesc(C.Structure):

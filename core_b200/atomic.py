@@ -105,6 +105,9 @@ class AtomicData:
         """List of effective CX emission coefficients, one per donor metastable (interface.pyx:86-95)."""
         raise NotImplementedError("The cxs_rates() virtual method is not implemented for this atomic data source.")
 
+    def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
+        raise NotImplementedError("The beam_emission() virtual method is not implemented for this atomic data source.")
+
     def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
         raise NotImplementedError("The beam_stopping() virtual method is not implemented for this atomic data source.")
 
@@ -184,6 +187,17 @@ class SyntheticADAS(AtomicData):
         sref = 1.0e-13
         sen = sref * (1 + 0.05 * charge) * (e[:, None] / 4e4) ** -0.35 * (1 + 0.08 * np.log10(n[None, :] / 1e19))
         st = sref * (1 + 0.05 * np.log10(t / 1e3))
+        return BeamStoppingTable(e, n, t, sen, st, sref)
+
+    def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
+        """Synthetic ADF22-shaped beam emission coefficient (photon m^3 s^-1): same grids as the stopping coefficient."""
+        from .beam import BeamStoppingTable
+        if charge == 0:
+            return None
+        e, n, t = np.logspace(3.5, 5.5, 25), np.logspace(17.0, 21.5, 26), np.logspace(0.0, 4.5, 16)
+        sref = 3.0e-15
+        sen = sref * (1 + 0.03 * charge) * (e[:, None] / 4e4) ** 0.2 * (1 - 0.06 * np.log10(n[None, :] / 1e19))
+        st = sref * (1 + 0.04 * np.log10(t / 1e3))
         return BeamStoppingTable(e, n, t, sen, st, sref)
 
     def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):

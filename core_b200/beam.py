@@ -109,6 +109,44 @@ class BeamCXLine(BeamModel):
         return "<BeamCXLine: element={}, charge={}, transition={}>".format(self.line.element.name, self.line.charge, self.line.transition)
 
 
+class BeamEmissionLine(BeamModel):
+    """beam_emission.pyx:36-98: Balmer-series emission of the beam atoms excited by the plasma, with the motional-Stark-effect
+    multiplet line shape (mse.pyx).  The intensity ratios must be constants here (the reference also accepts functions)."""
+    kind = _abi.MODEL_BEAM_EMISSION_LINE
+
+    def __init__(self, line, beam=None, plasma=None, atomic_data=None, sigma_to_pi=0.56, sigma1_to_sigma0=0.7060001671878492,
+                 pi2_to_pi3=0.3140003593919741, pi4_to_pi3=0.7279994935840365):
+        super().__init__(beam, plasma, atomic_data)
+        if not isinstance(line, Line):
+            raise TypeError("line must be a Line")
+        self.line = line
+        for v in (sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3):
+            if callable(v):
+                raise TypeError("function-valued MSE intensity ratios are not supported on the B200 path")
+        self.ratios = (float(sigma_to_pi), float(sigma1_to_sigma0), float(pi2_to_pi3), float(pi4_to_pi3))
+
+    def populate(self, beam, plasma, atomic_data):
+        """beam_emission.pyx:178-216 -> (wavelength, [(species index, rate)])."""
+        if beam is None:
+            raise RuntimeError("The emission model is not connected to a beam object.")
+        if plasma is None:
+            raise RuntimeError("The emission model is not connected to a plasma object.")
+        if atomic_data is None:
+            raise RuntimeError("The emission model is not connected to an atomic data source.")
+        if beam.element is not self.line.element:
+            raise TypeError("The specified line element '{}' is incompatible with the attached neutral "
+                            "beam element '{}'.".format(self.line.element.symbol, beam.element.symbol))
+        if self.line.charge != 0:
+            raise TypeError("The transition specified does not belong to a neutral atom.")
+        wavelength = atomic_data.wavelength(beam.element, 0, self.line.transition)
+        rates = [(i, atomic_data.beam_emission_pec(beam.element, sp.element, sp.charge, self.line.transition))
+                 for i, sp in enumerate(plasma.composition)]
+        return wavelength, rates
+
+    def __repr__(self):
+        return "<BeamEmissionLine: element={}, charge={}, transition={}>".format(self.line.element.name, self.line.charge, self.line.transition)
+
+
 class Beam:
     """beam/node.pyx:100-212, Raysect-free: ``transform`` is the beam -> world 4x4 matrix (z along the beam axis, origin at
     the source).  Defaults as in the reference: energy 0 eV/amu, power 0 W, temperature 0 eV, sigma 0.1 m, no divergence,
@@ -240,9 +278,32 @@ def flatten_beam_scene(beam, min_wavelength, max_wavelength, bins):
     models = list(beam.models)
     mo_arr = (_abi.ModelDesc * max(1, len(models)))()
     for i, mdl in enumerate(models):
+        mo = mo_arr[i]
+        if isinstance(mdl, BeamEmissionLine):
+            wavelength, bes = mdl.populate(beam, plasma, mdl.atomic_data or beam.atomic_data)
+            mo.kind = mdl.kind
+            mo.species = -1
+            mo.wavelength = wavelength
+            mo.atomic_weight = beam.element.atomic_weight       # the multiplet is broadened by the BEAM temperature (mse.pyx:100-102)
+            mo.pec.n_ne = mo.pec.n_te = 0
+            mo.pec.constant = 0.0
+            mo.shape.kind = _abi.SHAPE_GAUSSIAN
+            mo.shape.polarisation = _abi.POL_NO
+            ext = _abi.ModelExt()
+            bidx = np.ascontiguousarray([k for k, _ in bes], dtype=np.int32)
+            barr = (_abi.BeamRate * max(1, len(bes)))()
+            for k, (_, r) in enumerate(bes):
+                _fill_beam_rate(barr[k], r, keep)
+            ext.n_bes = len(bes)
+            ext.bes_species = bidx.ctypes.data_as(_abi.c_int32_p)
+            ext.bes_rates = C.cast(barr, C.POINTER(_abi.BeamRate))
+            for k in range(4):
+                ext.mse_ratios[k] = mdl.ratios[k]
+            keep.extend([bidx, barr, ext])
+            mo.ext = C.pointer(ext)
+            continue
         if not isinstance(mdl, BeamCXLine):
             raise TypeError("Unsupported BeamModel for the B200 path: %r" % (mdl,))
-        mo = mo_arr[i]
         index, cx_rates, wavelength, shape = mdl.populate(beam, plasma, mdl.atomic_data or beam.atomic_data)
         mo.kind = mdl.kind
         mo.species = index

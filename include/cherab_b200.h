@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 3
+#define CB2_ABI_VERSION 4
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -251,7 +251,9 @@ typedef enum cb2_model_kind {
     CB2_MODEL_BREMSSTRAHLUNG     = 2, /* Bremsstrahlung.emission     bremsstrahlung.pyx:169-208 */
     CB2_MODEL_THERMAL_CX_LINE    = 3, /* ThermalCXLine.emission      thermal_cx.pyx:79-112 */
     CB2_MODEL_TOTAL_RADIATED_POWER = 4, /* TotalRadiatedPower.emission total_radiated_power.pyx:70-118 */
-    CB2_MODEL_BEAM_CX_LINE       = 5  /* BeamCXLine.emission         model/beam/charge_exchange.pyx:117-167 (needs cb2_scene_desc.beam) */
+    CB2_MODEL_BEAM_CX_LINE       = 5, /* BeamCXLine.emission         model/beam/charge_exchange.pyx:117-167 (needs cb2_scene_desc.beam) */
+    CB2_MODEL_BEAM_EMISSION_LINE = 6  /* BeamEmissionLine.emission   model/beam/beam_emission.pyx:100-176 + BeamEmissionMultiplet.add_line
+                                         (model/lineshape/beam/mse.pyx:62-135); cb2_model.shape is ignored */
 } cb2_model_kind;
 
 /* What ThermalCXLine._populate_cache (thermal_cx.pyx:114-155) and TotalRadiatedPower._populate_cache
@@ -272,6 +274,14 @@ typedef struct cb2_model_ext {
      * (BeamPopulationRate) return CB2_ERR_NOT_IMPLEMENTED */
     int32_t            n_cx, _pad3;
     const cb2_cx_rate* cx;
+    /* BEAM_EMISSION_LINE: beam_emission_pec(beam.element, species.element, species.charge, transition) for every plasma
+     * species (beam_emission.pyx:207-212; same table shape as the stopping rate, 'sen' in photon m^3 s^-1, a constant rate in
+     * W m^3) and the constant MSE intensity ratios sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3 (beam_emission.pyx:47-50;
+     * function-valued ratios are not supported) */
+    int32_t              n_bes, _pad4;
+    const int32_t*       bes_species;
+    const cb2_beam_rate* bes_rates;
+    double               mse_ratios[4];
 } cb2_model_ext;
 
 typedef struct cb2_model {

@@ -679,12 +679,16 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
             if (mo->species < 0 || mo->species >= d->n_species || !mo->ext || mo->ext->n_cx < 1)
                 return fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified CX line");
             if (mo->ext->n_cx > 1) return fail(CB2_ERR_NOT_IMPLEMENTED, "excited donor metastables are not supported yet");
+        } else if (mo->kind == CB2_MODEL_BEAM_EMISSION_LINE) {
+            if (!d->beam) return fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
+            if (!mo->ext) return fail(CB2_ERR_RUNTIME, "BeamEmissionLine needs its resolved rates");
         } else return fail(CB2_ERR_TYPE, "unsupported model kind");
     }
     gaunt_table_build(&s->gaunt, &d->gaunt);
     if (d->beam) {
         for (int m = 0; m < d->n_models; m++)
-            if (d->models[m].kind != CB2_MODEL_BEAM_CX_LINE) return fail(CB2_ERR_TYPE, "a beam scene renders beam models only");
+            if (d->models[m].kind != CB2_MODEL_BEAM_CX_LINE && d->models[m].kind != CB2_MODEL_BEAM_EMISSION_LINE)
+                return fail(CB2_ERR_TYPE, "a beam scene renders beam models only");
         if (!(d->beam->energy > 0)) return fail(CB2_ERR_VALUE, "Beam energy must be positive");
         return beam_ctx_build(s);
     }
@@ -710,7 +714,8 @@ static void xform_vector(const double m[12], const double p[3], double o[3]);
 static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 /* BeamStoppingRate.evaluate — openadas/rates/beam.pyx:93-103; outside the tables: clamped to the edge and counted */
-static double beam_rate_eval(const cb2_beam_rate* r, double energy, double density, double temperature, int64_t* ood) {
+/* wavelength > 0: BeamEmissionPEC, 'sen' is converted from photon m^3/s to W m^3 first (beam.pyx:229-239) */
+static double beam_rate_eval_w(const cb2_beam_rate* r, double wavelength, double energy, double density, double temperature, int64_t* ood) {
     if (r->n_e <= 0) return r->constant;
     if (energy <= 0 || density <= 0 || temperature <= 0) return 0.0;
     double le = log10(energy), ln = log10(density), lt = log10(temperature);
@@ -720,7 +725,10 @@ static double beam_rate_eval(const cb2_beam_rate* r, double energy, double densi
     for (int i = 0; i < r->n_e; i++) xe[i] = log10(r->e[i]);
     for (int i = 0; i < r->n_n; i++) xn[i] = log10(r->n[i]);
     for (int i = 0; i < r->n_t; i++) xt[i] = log10(r->t[i]);
-    for (int i = 0; i < r->n_e * r->n_n; i++) lsen[i] = log10(r->sen[i]);
+    {
+        double conv = wavelength > 0 ? PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9 / wavelength : 1.0;   /* PhotonToJ */
+        for (int i = 0; i < r->n_e * r->n_n; i++) lsen[i] = log10(r->sen[i] * conv);
+    }
     for (int i = 0; i < r->n_t; i++) lst[i] = log10(r->st[i] / r->sref);
     lo = xe[0]; hi = xe[r->n_e - 1]; if (le < lo || le > hi) { (*ood)++; le = clampd(le, lo, hi); }
     lo = xn[0]; hi = xn[r->n_n - 1]; if (ln < lo || ln > hi) { (*ood)++; ln = clampd(ln, lo, hi); }
@@ -733,6 +741,10 @@ static double beam_rate_eval(const cb2_beam_rate* r, double energy, double densi
     double b = r->n_t > 1 ? cb2o_interp1d_cubic(xt, lst, r->n_t, lt, 1) : lst[0];
     free(xe);
     return pow(10.0, a + b);
+}
+
+static double beam_rate_eval(const cb2_beam_rate* r, double energy, double density, double temperature, int64_t* ood) {
+    return beam_rate_eval_w(r, 0.0, energy, density, temperature, ood);
 }
 
 static double cx_factor(const double* x, const double* q, int n, double scale, double v, int64_t* ood) {
@@ -1038,6 +1050,49 @@ static void beam_emission_function(const scene_ctx* s, const double pb[3], const
         const cb2_model* mo = &d->models[m];
         double donor = beam_density(s, pb);
         if (donor == 0.0) continue;
+        if (mo->kind == CB2_MODEL_BEAM_EMISSION_LINE) {
+            /* BeamEmissionLine.emission / _beam_emission_rate (beam_emission.pyx:100-176); neutrals are skipped */
+            const cb2_model_ext* x = mo->ext;
+            double bl = sqrt(bdir[0] * bdir[0] + bdir[1] * bdir[1] + bdir[2] * bdir[2]);
+            double speed = sqrt(b->energy * EVAMU_TO_MS2);
+            double bv[3] = {bdir[0] / bl * speed, bdir[1] / bl * speed, bdir[2] / bl * speed};
+            double density_sum = 0, rate = 0;
+            for (int k = 0; k < x->n_bes; k++) {
+                const cb2_species* sp = &d->species[x->bes_species[k]];
+                density_sum += (double)sp->charge * sp->charge * eval_scalar(s, &sp->density, p, &cn->ood);
+            }
+            for (int k = 0; k < x->n_bes; k++) {
+                const cb2_species* sp = &d->species[x->bes_species[k]];
+                if (sp->charge == 0) continue;
+                double target_ne = eval_scalar(s, &sp->density, p, &cn->ood) * sp->charge;
+                double target_ti = eval_scalar(s, &sp->temperature, p, &cn->ood);
+                double tv[3];
+                eval_vector(s, &sp->velocity, p, tv, &cn->ood);
+                double iv[3] = {bv[0] - tv[0], bv[1] - tv[1], bv[2] - tv[2]};
+                double e_int = (iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2]) / EVAMU_TO_MS2;
+                rate += target_ne * beam_rate_eval_w(&x->bes_rates[k], mo->wavelength, e_int, density_sum / sp->charge, target_ti, &cn->ood);
+            }
+            double radiance = RECIP_4_PI * donor * rate;
+            /* BeamEmissionMultiplet.add_line — mse.pyx:62-135 */
+            double te = eval_scalar(s, &d->electron_temperature, p, &cn->ood);
+            if (te <= 0) continue;
+            double ne = eval_scalar(s, &d->electron_density, p, &cn->ood);
+            if (ne <= 0) continue;
+            double bf[3];
+            eval_b_field(s, p, bf, &cn->ood);
+            double cx_[3] = {bv[1] * bf[2] - bv[2] * bf[1], bv[2] * bf[0] - bv[0] * bf[2], bv[0] * bf[1] - bv[1] * bf[0]};
+            double stark = fabs(2.77e-8 * sqrt(cx_[0] * cx_[0] + cx_[1] * cx_[1] + cx_[2] * cx_[2]));
+            double central = doppler_shift(mo->wavelength, obs, bv);
+            double sigma = thermal_broadening(mo->wavelength, b->temperature, b->atomic_weight);
+            double s2p = x->mse_ratios[0], s1s0 = x->mse_ratios[1], p23 = x->mse_ratios[2], p43 = x->mse_ratios[3];
+            double dd = 1 / (1 + s2p), isig = s2p * dd * radiance, ipi = 0.5 * dd * radiance;
+            double is0 = 1 / (s1s0 + 1), is1 = 0.5 * s1s0 * is0;
+            double ip3 = 1 / (1 + p23 + p43), ip2 = p23 * ip3, ip4 = p43 * ip3;
+            const double amp[9] = {isig * is0, isig * is1, isig * is1, ipi * ip2, ipi * ip2, ipi * ip3, ipi * ip3, ipi * ip4, ipi * ip4};
+            const double off[9] = {0, 1, -1, 2, -2, 3, -3, 4, -4};
+            for (int k = 0; k < 9; k++) cn->gauss += add_gaussian_line(amp[k], central + off[k] * stark, sigma, &d->grid, samples);
+            continue;
+        }
         double nr = eval_scalar(s, &d->species[mo->species].density, p, &cn->ood);
         if (nr == 0) continue;
         double tr = eval_scalar(s, &d->species[mo->species].temperature, p, &cn->ood);

@@ -96,3 +96,63 @@ def test_beam_scene_validation():
     beam.attenuator = None
     with pytest.raises(ValueError):
         cb.flatten_beam_scene(beam, 500, 550, 8)
+
+
+# ---- BeamEmissionLine + MSE multiplet ----
+class BesMockData(BeamMockData):
+    def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
+        return cb.ConstantRate(2.0e-35)
+
+
+def mse_case():
+    """Inputs of core/tests/test_lineshapes.py:391-472 (D-alpha 656.104 nm, beam 60 keV/amu at 10 eV, B = (0, 5, 0) T,
+    ne 1e19, line of sight (-1, 1, 0)/sqrt 2, 512 bins on +-3 nm) replayed through the whole path: a parallel beam along +z
+    through the slab, so every sample has the same multiplet shape and the spectrum is (integrated radiance) x (unit shape)."""
+    atomic = BesMockData(0.0)
+    plasma = build_constant_slab_plasma(length=1, width=1, height=1, electron_density=1e19, electron_temperature=20.,
+                                        plasma_species=[(cb.deuterium, 1, 1.e18, 5., (2.e4, 0, 0)), (cb.nitrogen, 1, 1.e17, 10., (1.e4, 5.e4, 0))],
+                                        b_field=(0, 5., 0))
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.translate(0.5, 0.0, -0.5))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 1e6, 10, cb.deuterium
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2)))]
+    flat = cb.flatten_beam_scene(beam, 656.104 - 3, 656.104 + 3, 512)
+    d = np.array([-1.0, 1.0, 0.0]) / np.sqrt(2)
+    rays = cb.beam_ray_segments(beam, [np.array([0.5, 0.0, 0.0]) - 2.0 * d], [d])
+    return flat, rays, d
+
+
+def mse_unit_shape(direction):
+    from scipy.special import erf
+    wavelength, s2p, s1s0, p23, p43 = 656.104, 0.56, 0.7060001671878492, 0.3140003593919741, 0.7279994935840365
+    bv = np.array([0, 0, 1.0]) * np.sqrt(2 * 60000 * QE / AMU)
+    stark = abs(2.77e-8 * np.linalg.norm(np.cross(bv, [0, 5.0, 0])))
+    central = wavelength * (1 + bv.dot(direction) / const.c)
+    sigma = np.sqrt(10 * QE / (cb.deuterium.atomic_weight * AMU)) * wavelength / const.c
+    wl, delta = np.linspace(wavelength - 3, wavelength + 3, 513, retstep=True)
+    g = lambda c: 0.5 * np.diff(erf((wl - c) / (np.sqrt(2.) * sigma))) / delta
+    dd = 1 / (1 + s2p)
+    isig, ipi = s2p * dd, 0.5 * dd
+    is0 = 1 / (s1s0 + 1)
+    is1 = 0.5 * s1s0 * is0
+    ip3 = 1 / (1 + p23 + p43)
+    out = isig * is0 * g(central) + isig * is1 * (g(central + stark) + g(central - stark))
+    for k, a in ((2, p23 * ip3), (3, ip3), (4, p43 * ip3)):
+        out += ipi * a * (g(central + k * stark) + g(central - k * stark))
+    return out, delta
+
+
+def test_beam_emission_multiplet():
+    flat, rays, d = mse_case()
+    got, stats = oracle.emission_render(flat, rays)
+    shape, delta = mse_unit_shape(d)
+    total = got[0].sum() * delta                     # integrated radiance (the multiplet integrates to isig + 2 ipi (..) = 1 x radiance)
+    assert total > 0 and stats["samples"] > 100
+    assert np.max(np.abs(got[0] / total - shape / (shape.sum() * delta))) < 1e-10
+    # beam emission rate: radiance = 1/(4 pi) n_beam sum_s (n_s Z_s) q_s, constant q = 2e-35 W m^3 for both singly charged species
+    dens, _ = oracle.beam_sample(flat, [[0, 0, 0.5]])
+    sigma_b = 0.1
+    expected = 0.25 / np.pi * (1e18 + 1e17) * 2.0e-35 * dens[0] * np.sqrt(2 * np.pi) * sigma_b   # chord through the axis of the round Gaussian beam
+    assert abs(total / expected - 1) < 2e-3           # trapezium sum of a Gaussian over a chord clipped at 5 sigma
