@@ -672,6 +672,62 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
         S.has_flat = 1;
         return A.rc;
     }
+    if (m.kind == CB2_MODEL_BEAM_EMISSION_LINE) {
+        // beam_emission.pyx:178-216 + mse.pyx:62-135: nine Gaussians around the Doppler-shifted line, split by the motional
+        // Stark effect, broadened by the BEAM temperature
+        const cb2_model_ext* x = m.ext;
+        if (!d.beam) return cb2_fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
+        if (!x) return cb2_fail(CB2_ERR_RUNTIME, "BeamEmissionLine needs its resolved rates");
+        if (x->n_bes < 0 || x->n_bes > CB2_MAX_SPECIES) return cb2_fail(CB2_ERR_VALUE, "invalid number of beam emission rates");
+        if (!(m.wavelength > 0)) return cb2_fail(CB2_ERR_VALUE, "line wavelength must be positive");
+        o.wavelength = (float)m.wavelength;
+        o.inv_delta = (float)(1.0 / S.delta_d);
+        o.inv_c = (float)(1.0 / SPEED_OF_LIGHT);
+        o.shape = CB2_SHAPE_GAUSSIAN;
+        o.pec_const = 1;
+        o.pec_value = -INFINITY;
+        o.pec_grid = -1;
+        DevModelExt e;
+        memset(&e, 0, sizeof e);
+        e.n_bes = x->n_bes;
+        const double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9 / m.wavelength;     // PhotonToJ (beam.pyx:238)
+        for (int k = 0; k < x->n_bes; k++) {
+            const cb2_beam_rate& r = x->bes_rates[k];
+            const int sp = x->bes_species[k];
+            if (sp < 0 || sp >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "beam emission species index out of range");
+            e.bes_species[k] = sp;
+            e.bes_charge[k] = d.species[sp].charge;
+            if (r.n_e <= 0) {
+                e.bes_const[k] = 1;
+                e.bes_lconst[k] = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+                continue;
+            }
+            if (r.n_e < 2 || r.n_n < 2 || r.n_t < 2 || !(r.sref > 0))
+                return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "beam emission tables need at least 2 points per axis on the device path");
+            std::vector<double> le(r.n_e), ln(r.n_n), lt(r.n_t), lsen((size_t)r.n_e * r.n_n), lst(r.n_t);
+            for (int i = 0; i < r.n_e; i++) le[i] = log10(r.e[i]);
+            for (int i = 0; i < r.n_n; i++) ln[i] = log10(r.n[i]);
+            for (int i = 0; i < r.n_t; i++) { lt[i] = log10(r.t[i]); lst[i] = log10(r.st[i] / r.sref); }
+            for (size_t i = 0; i < lsen.size(); i++) lsen[i] = log10(r.sen[i] * conv) + CB2_PEC_LOG_OFFSET;
+            e.bes_a[k] = make_table2d(A, le.data(), ln.data(), lsen.data(), r.n_e, r.n_n);
+            e.bes_tk[k] = make_knots1d(A, lt.data(), r.n_t);
+            e.bes_tc[k] = make_coef1d(A, lt.data(), lst.data(), r.n_t, 1.0);
+        }
+        const double s2p = x->mse_ratios[0], s1s0 = x->mse_ratios[1], p23 = x->mse_ratios[2], p43 = x->mse_ratios[3];
+        const double dd = 1 / (1 + s2p), isig = s2p * dd, ipi = 0.5 * dd, is0 = 1 / (s1s0 + 1), is1 = 0.5 * s1s0 * is0;
+        const double ip3 = 1 / (1 + p23 + p43), ip2 = p23 * ip3, ip4 = p43 * ip3;
+        const double amp[9] = {isig * is0, isig * is1, isig * is1, ipi * ip2, ipi * ip2, ipi * ip3, ipi * ip3, ipi * ip4, ipi * ip4};
+        for (int k = 0; k < 9; k++) e.mse_amp[k] = (float)amp[k];
+        e.mse_sigma_b = (float)(sqrt(d.beam->temperature * ELEMENTARY_CHARGE / (d.beam->atomic_weight * ATOMIC_MASS)) * m.wavelength /
+                                SPEED_OF_LIGHT / S.delta_d);
+        o.ext = A.upload(std::vector<DevModelExt>(1, e));
+        o.comp0 = S.n_comp;
+        o.ncomp = 9;
+        if (S.n_comp + 9 > CB2_MAX_COMP) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "too many line components (max %d)", CB2_MAX_COMP);
+        S.n_comp += 9;
+        for (int k = 0; k < 9; k++) set_comp(S, o.comp0 + k, m.wavelength, 0);
+        return A.rc;
+    }
     if (m.kind != CB2_MODEL_EXCITATION_LINE && m.kind != CB2_MODEL_RECOMBINATION_LINE && m.kind != CB2_MODEL_THERMAL_CX_LINE &&
         m.kind != CB2_MODEL_BEAM_CX_LINE)
         return cb2_fail(CB2_ERR_TYPE, "unsupported model kind %d", m.kind);
@@ -1187,8 +1243,8 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
             const bool is_line = kd == CB2_MODEL_EXCITATION_LINE || kd == CB2_MODEL_RECOMBINATION_LINE || kd == CB2_MODEL_THERMAL_CX_LINE ||
                                  kd == CB2_MODEL_BEAM_CX_LINE;
             if (is_line && sh != CB2_SHAPE_GAUSSIAN && sh != CB2_SHAPE_MULTIPLET) need_b = true;
-            if (kd == CB2_MODEL_BEAM_CX_LINE) need_b = true;           // the CX rate depends on |B| (charge_exchange.pyx:222)
-            if ((kd == CB2_MODEL_BEAM_CX_LINE) != (d->beam != nullptr)) { rc = cb2_fail(CB2_ERR_TYPE, "a beam scene renders beam models only, and beam models need a beam"); break; }
+            if (kd == CB2_MODEL_BEAM_CX_LINE || kd == CB2_MODEL_BEAM_EMISSION_LINE) need_b = true;   // q_eff(|B|); v x B
+            if ((kd == CB2_MODEL_BEAM_CX_LINE || kd == CB2_MODEL_BEAM_EMISSION_LINE) != (d->beam != nullptr)) { rc = cb2_fail(CB2_ERR_TYPE, "a beam scene renders beam models only, and beam models need a beam"); break; }
         }
         if (rc != CB2_OK) break;
         S.need_b = need_b;
@@ -1204,14 +1260,14 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
             sc->feat = d->beam != nullptr;
             for (int m = 0; m < d->n_models; m++)
                 sc->feat |= d->models[m].kind == CB2_MODEL_THERMAL_CX_LINE || d->models[m].kind == CB2_MODEL_TOTAL_RADIATED_POWER ||
-                            d->models[m].kind == CB2_MODEL_BEAM_CX_LINE;
+                            d->models[m].kind == CB2_MODEL_BEAM_CX_LINE || d->models[m].kind == CB2_MODEL_BEAM_EMISSION_LINE;
         }
         if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;  // decides the Bremsstrahlung mode (direct / moments)
         if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)
         bool any_stark = false;
         for (int m = 0; m < d->n_models; m++)
             any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].kind != CB2_MODEL_TOTAL_RADIATED_POWER &&
-                         d->models[m].shape.kind == CB2_SHAPE_STARK;
+                         d->models[m].kind != CB2_MODEL_BEAM_EMISSION_LINE && d->models[m].shape.kind == CB2_SHAPE_STARK;
         if (any_stark && (rc = build_lorentz(A, S)) != CB2_OK) break;
         if ((rc = A.rc) != CB2_OK) break;
         void* p = nullptr;

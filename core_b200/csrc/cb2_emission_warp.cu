@@ -45,6 +45,7 @@ struct LineCache {
     float ni, ts, vd;
     bool have_b;
     float bm, cos_sqr;
+    float bfx, bfy, bfz;     // B in plasma space (the MSE multiplet needs v x B)
     int grid;                // PEC knot set whose cell is cached
     Cell2 cell;
 };
@@ -68,6 +69,7 @@ __device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, co
     if (lc.have_b) return;
     if (S.b_kind != 0 && ctx.b_outside) ood++;
     const float3 bf = eval_b_field(S, ctx);
+    lc.bfx = bf.x; lc.bfy = bf.y; lc.bfz = bf.z;
     lc.bm = sqrtf(bf.x * bf.x + bf.y * bf.y + bf.z * bf.z);
     const float c = lc.bm > 0.f ? (bf.x * in.dx + bf.y * in.dy + bf.z * in.dz) / lc.bm : 0.f;
     lc.cos_sqr = c * c;
@@ -252,6 +254,53 @@ __device__ __forceinline__ float total_radiated_power(const DevScene& S, const D
         power = fmaf(exp10f(lp), dens[k], power);        // rates carry +38 in the exponent, densities 1e-19 each
     }
     return RECIP_4_PI * power * S.inv_range * in.weight;
+}
+
+// BeamEmissionLine.emission (beam_emission.pyx:100-176) + BeamEmissionMultiplet.add_line (mse.pyx:62-135) at one sample:
+// amplitude (radiance * weight / delta), Doppler shift of the beam atoms and Stark splitting, both in bins
+template <int AXONLY>
+__device__ __forceinline__ void beam_emission_setup(const DevScene& S, const DevModel& M, const SampleIn& in, const AxCtx& ctx, float ne,
+                                                    float te, LineCache& lc, float& amp, float& shift_b, float& split_b, unsigned& ood) {
+    amp = 0.f; shift_b = 0.f; split_b = 0.f;
+    if (!(in.weight > 0.f) || !(in.donor > 0.f) || !(ne > 0.f) || !(te > 0.f)) return;
+    const DevModelExt& X = *M.ext;
+    float density_sum = 0.f;
+    for (int k = 0; k < X.n_bes; k++) {
+        const float zc = (float)X.bes_charge[k];
+        density_sum = fmaf(zc * zc, eval_scalar_t<AXONLY>(S.species[X.bes_species[k]].density, ctx, in.x, in.y, in.z), density_sum);
+    }
+    float rate = 0.f;
+    for (int k = 0; k < X.n_bes; k++) {
+        const int zc = X.bes_charge[k];
+        if (zc == 0) continue;                                       // no beam emission data for neutrals
+        const DevSpecies& sp = S.species[X.bes_species[k]];
+        const float target_ne = eval_scalar_t<AXONLY>(sp.density, ctx, in.x, in.y, in.z) * (float)zc;
+        if (!(target_ne > 0.f)) continue;
+        float lq;
+        if (X.bes_const[k]) lq = X.bes_lconst[k];
+        else {
+            const float ti = eval_scalar_t<AXONLY>(sp.temperature, ctx, in.x, in.y, in.z);
+            const float3 v = eval_vector(sp.velocity, ctx);
+            const float ivx = in.bvx - v.x, ivy = in.bvy - v.y, ivz = in.bvz - v.z;
+            const float energy = (ivx * ivx + ivy * ivy + ivz * ivz) * 5.18213506e-9f;
+            const float n_eq = density_sum / (float)zc;
+            if (!(energy > 0.f) || !(n_eq > 0.f) || !(ti > 0.f)) continue;
+            const Cell2 c = locate2d(X.bes_a[k], log10f(energy), log10f(n_eq) + 19.0f);
+            if (!c.inside) ood++;
+            const float lt = log10f(ti);
+            if (lt < X.bes_tk[k].xmin || lt > X.bes_tk[k].xmax) ood++;
+            int ci; float ct;
+            locate1d(X.bes_tk[k], lt, ci, ct);
+            lq = eval2d(X.bes_a[k], c) + horner4(__ldg(X.bes_tc[k] + ci), ct);
+        }
+        rate = fmaf(target_ne, exp10f(lq), rate);
+    }
+    amp = RECIP_4_PI * in.donor * rate * in.weight * M.inv_delta;
+    if (!(amp > 0.f)) { amp = 0.f; return; }
+    need_b(S, in, ctx, lc, ood);
+    const float cx = in.bvy * lc.bfz - in.bvz * lc.bfy, cy = in.bvz * lc.bfx - in.bvx * lc.bfz, cz = in.bvx * lc.bfy - in.bvy * lc.bfx;
+    split_b = fabsf(2.77e-8f * sqrtf(cx * cx + cy * cy + cz * cz)) * M.inv_delta;            // STARK_SPLITTING_FACTOR, mse.pyx:33
+    shift_b = M.wavelength * (in.bvx * in.dx + in.bvy * in.dy + in.bvz * in.dz) * M.inv_c * M.inv_delta;
 }
 
 // component k of model M at this sample: type (0 Gaussian, 1 modified Lorentzian), centre cf in bins relative to the
@@ -667,6 +716,20 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
+                if (FEAT && M.kind == CB2_MODEL_BEAM_EMISSION_LINE) {
+                    float amp, shift_b, split_b;
+                    beam_emission_setup<AXONLY>(S, M, in, ctx, ne, te, lc, amp, shift_b, split_b, ood);
+                    const bool any_amp = __any_sync(FULL, amp > 0.f);
+                    const DevModelExt& X = *M.ext;
+                    for (int kc = 0; kc < 9; kc++) {
+                        float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
+                        // component order: sigma0, sigma1 +-, pi2 +-, pi3 +-, pi4 +-  (mse.pyx:113-133)
+                        const float off = kc == 0 ? 0.f : (float)((kc + 1) >> 1) * ((kc & 1) ? 1.f : -1.f);
+                        r[64] = amp * X.mse_amp[kc];
+                        if (any_amp) { r[0] = S.comps[M.comp0 + kc].c0_frac + shift_b + off * split_b; r[32] = X.mse_sigma_b; }
+                    }
+                    continue;
+                }
                 if (FEAT && M.kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
                     if (live) flat_acc += total_radiated_power<AXONLY>(S, M, in, ctx, ne, lc.lne, lc.lte, ood);
                     continue;

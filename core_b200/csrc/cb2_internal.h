@@ -109,6 +109,17 @@ struct DevModelExt {
     float cx_single[5];
     DevTable1D cx_t[5];                    // knots: log10 E[eV/amu], Ti[eV], n_ion[1e19 m^-3], Zeff, |B|[T]
     const float4* cx_c[5];
+    // BEAM_EMISSION_LINE: rate = sum_s (n_s Z_s) 10^(A_s(log10 E, log10 n_eq) + B_s(log10 T_s))   (beam_emission.pyx:131-176)
+    int n_bes;
+    int bes_species[CB2_MAX_SPECIES];
+    int bes_charge[CB2_MAX_SPECIES];
+    int bes_const[CB2_MAX_SPECIES];
+    float bes_lconst[CB2_MAX_SPECIES];     // log10(rate [W m^3]) + 38
+    DevTable2D bes_a[CB2_MAX_SPECIES];     // (log10 E[eV/amu], log10 n_eq[m^-3]) -> log10(sen [W m^3]) + 38
+    DevTable1D bes_tk[CB2_MAX_SPECIES];    // log10 T[eV] knots
+    const float4* bes_tc[CB2_MAX_SPECIES]; // -> log10(st / sref)
+    float mse_amp[9];                      // relative intensities of the 9 multiplet components (mse.pyx:105-133)
+    float mse_sigma_b;                     // sigma in bins from the beam temperature and mass
     int has[3];                            // plt, prb, prc present
     int is_const[3];
     float lconst[3];                       // log10(rate) + 38

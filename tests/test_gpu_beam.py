@@ -80,3 +80,45 @@ def test_beam_cx_generomak_tabulated_rates():
     assert st["samples"] == rst["samples"] and ref.max() > 0
     assert abs(st["out_of_domain"] - rst["out_of_domain"]) <= 4     # a few edge samples leave the tabulated ranges: clamped and counted
     assert parity(got, ref) <= 1.0
+
+
+def test_beam_emission_multiplet_slab():
+    # core/tests/test_lineshapes.py:391-472 inputs through the CUDA path: the MSE multiplet against the reference's closed form
+    from test_oracle_beam import mse_case, mse_unit_shape
+    flat, rays, d = mse_case()
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"]
+    assert parity(got, ref) <= 1.0
+    shape, delta = mse_unit_shape(d)
+    total = got[0].sum() * delta
+    assert parity((got[0] / total)[None, :], (shape / (shape.sum() * delta))[None, :]) <= 1.0
+
+
+def test_beam_cx_and_emission_generomak_tabulated_rates():
+    # both beam models on the Generomak plasma with ADF12 / ADF21 / ADF22-shaped synthetic tables (BASELINE config C5 shape)
+    plasma = generomak.get_plasma()
+    atomic = cb.SyntheticADAS()
+    balmer = atomic.wavelength
+    atomic.wavelength = lambda ion, charge, transition: 529.05 if ion is cb.carbon else balmer(ion, charge, transition)
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.look_at((3.2, -0.4, 0.0), (1.0, 0.3, 0.05)))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.05, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.0025, min_samples=10)
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2))), cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    axis_pts = (np.asarray(beam.transform) @ np.stack([np.zeros(16), np.zeros(16), np.linspace(0.6, 2.4, 16), np.ones(16)]))[:3].T
+    origin = np.tile([[1.8, 0.2, 1.6]], (16, 1))
+    rays = cb.beam_ray_segments(beam, origin, axis_pts - origin)
+    for lo, hi, bins in ((526.0, 532.0, 256), (650.0, 662.0, 1024)):       # the CX line window and the Balmer-alpha / MSE window
+        flat = cb.flatten_beam_scene(beam, lo, hi, bins)
+        scene = EmissionScene(flat)
+        got, st = scene.render(rays)
+        scene.close()
+        ref, rst = oracle.emission_render(flat, rays)
+        assert st["samples"] == rst["samples"] and ref.max() > 0
+        assert parity(got, ref) <= 1.0, (lo, hi)
