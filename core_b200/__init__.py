@@ -11,6 +11,7 @@ from .beam import (Beam, BeamCXLine, BeamEmissionLine, BeamCXTable, BeamStopping
                    flatten_beam_scene)
 from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
+from .inversions import SartSolver, invert_constrained_sart, invert_sart
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
                      RecombinationLine, StarkBroadenedLine, ThermalCXLine, TotalRadiatedPower, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
 from .notify import Notifier

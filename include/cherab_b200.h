@@ -440,6 +440,56 @@ int cb2_rt_render_csr_device(cb2_rt_scene* scene, const cb2_rays* rays, int64_t*
                              cb2_stats* stats_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SART inversion on the device-resident geometry matrix (replaces
+ * cherab/tools/inversions/sart.pyx:26-155 invert_sart, :161-302 invert_constrained_sart and the OpenCL solver
+ * cherab/tools/inversions/opencl/sart_opencl.py:33-318 + sart_kernels.cl:28-148).
+ * The matrix is held as CSR and CSC on the device (what copy_column_major=True keeps, sart_opencl.py:120-125);
+ * arithmetic is float64 (the CPU reference's), the stored matrix values float32 or float64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cb2_sart_desc {
+    int32_t        abi_version;
+    int32_t        value_f64;         /* device storage of the matrix values: 1 = float64 (sart.pyx), 0 = float32 (sart_opencl.py:99-100) */
+    int64_t        n_detectors;       /* N_d rows */
+    int64_t        n_sources;         /* N_s columns */
+    /* geometry matrix, ONE of: dense row-major [n_detectors][n_sources] ... */
+    const void*    dense;             /* float32 (dense_f64 == 0) or float64 (dense_f64 == 1); NULL if CSR is given */
+    int32_t        dense_f64;
+    int32_t        memory;            /* 0: all pointers below and `dense` are HOST memory; 1: the CSR arrays are DEVICE memory
+                                         (the output of cb2_rt_render_csr_device) and are copied device-to-device */
+    /* ... or CSR as cb2_rt_render_csr produces it */
+    const int64_t* row_offset;        /* [n_detectors + 1] */
+    const int32_t* columns;           /* [nnz] */
+    const double*  values;            /* [nnz] */
+    /* optional Laplacian regularisation operator [n_sources][n_sources]: dense float64 row-major, or CSR; HOST memory */
+    const double*  laplacian_dense;
+    const int64_t* lap_row_offset;
+    const int32_t* lap_columns;
+    const double*  lap_values;
+} cb2_sart_desc;
+
+typedef struct cb2_sart cb2_sart;
+
+int cb2_sart_create(const cb2_sart_desc* desc, int device, cb2_sart** out);
+int cb2_sart_destroy(cb2_sart* solver);
+/* Replaces the Laplacian (SartOpencl.update_laplacian_matrix, sart_opencl.py:186-196); same pointer rules as at create. */
+int cb2_sart_set_laplacian(cb2_sart* solver, const double* dense, const int64_t* row_offset, const int32_t* columns, const double* values);
+
+/* Inverts n_frames measurement vectors at once (HOST buffers): measurements[n_frames][n_detectors],
+ * initial_guess[n_frames][n_sources] or NULL (then every cell starts at initial_value; the reference default is exp(-1),
+ * sart.pyx:88-89), solution[n_frames][n_sources], convergence[n_frames][max_iterations] (entries past a frame's last
+ * iteration are left untouched), n_iterations[n_frames].  Per frame this is exactly the reference loop: update every
+ * cell from the previous estimate, clamp at zero, forward-project, record (|m|^2 - |y_hat|^2)/|m|^2 and stop once two
+ * successive records differ by less than conv_tol (sart.pyx:116-153); beta_laplace is ignored without a Laplacian.
+ * The matrix is streamed from HBM twice per iteration whatever n_frames is. */
+int cb2_sart_solve(cb2_sart* solver, const double* measurements, int64_t n_frames, const double* initial_guess,
+                   double initial_value, int max_iterations, double relaxation, double beta_laplace, double conv_tol,
+                   double* solution, double* convergence, int32_t* n_iterations);
+/* [0] nnz of the geometry matrix, [1] nnz of the Laplacian, [2] bytes of matrix values+indices streamed per iteration
+ * (CSR pass + CSC pass), [3] device milliseconds spent in the iteration kernels of the last solve, [4] iterations
+ * launched by the last solve (>= the largest n_iterations: the stop test is read back every few iterations) */
+double cb2_sart_info(const cb2_sart* solver, int what);
+
+/* ------------------------------------------------------------------------------------------------
  * Oracle (libcb2_oracle.so) — same descriptors, fp64 scalar restatement of the reference. TEST INFRASTRUCTURE.
  * ---------------------------------------------------------------------------------------------- */
 int         cb2o_abi_version(void);
