@@ -4,12 +4,15 @@
 // solver cherab/tools/inversions/opencl/sart_opencl.py:33-318.  Not a translation of either: the reference walks a dense
 // matrix cell by cell; here the matrix is sparse (what the ray-transfer kernel produces), stored once as CSR and once as
 // CSC, and one iteration is two HBM streams over it,
-//     backward (CSC, one warp per source):   x_j <- max(0, x_j + omega/W_+j * sum_i W_ij w_i - beta (L x)_j)
-//     forward  (CSR, one warp per detector): y_i = sum_j W_ij x_j ;  w_i = (m_i - y_i) / W_i+ ;  sum_i y_i^2
-// for FR measurement frames at a time, so the bytes streamed per iteration do not grow with the number of frames.
-// The stop test of the reference (sart.pyx:147-153) runs on the device in the last CTA of the forward pass; once a frame
-// has stopped, later launches leave its solution untouched, so the host only reads the flags back every few iterations.
-// All reductions have a fixed order (warp butterflies, per-CTA partials summed by one warp): results are reproducible.
+//     backward (CSC):  x_j <- max(0, x_j + omega/W_+j * sum_i W_ij w_i - beta (L x)_j)
+//     forward  (CSR):  y_i = sum_j W_ij x_j ;  w_i = (m_i - y_i) / W_i+ ;  sum_i y_i^2
+// for up to four measurement frames at a time, so the bytes streamed per iteration do not grow with the number of frames.
+// Each pass is sart_dot_kernel (one warp per chunk of <= 2048 stored entries: a pinhole's own cell is crossed by every ray
+// of the frame, so whole rows / columns cannot be the unit of work) followed by a small finishing kernel that adds the chunk
+// sums of every row in order.  The stop test of the reference (sart.pyx:147-153) runs on the device in the last CTA of the
+// forward finishing kernel; once a frame has stopped, later launches leave its solution untouched, so the host only reads
+// the flags back every few iterations.  All sums have a fixed order (lane-strided entries, warp butterflies, chunk sums in
+// chunk order, per-CTA partials summed by one warp): results are reproducible and do not depend on how frames are grouped.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -28,12 +31,18 @@ namespace {
 constexpr int SART_THREADS = 256;              // 8 warps per CTA
 constexpr int SART_WARPS = SART_THREADS / 32;
 constexpr int SART_CHECK_EVERY = 8;            // iterations between read-backs of the stop flags
-constexpr int SART_FR = 4;                     // frames per pass
+constexpr int SART_CHUNK = 2048;               // stored entries per warp task: long rows / columns are cut into chunks
+constexpr int SART_FIN_GRID = 296;             // fixed grid of the finishing kernels => fixed summation order of |y_hat|^2
 
-struct SartMatrix {                            // one sparse operand: CSR rows or CSC columns
+// One sparse operand (CSR rows of W, CSC columns of W): rows are cut into chunks of at most SART_CHUNK entries so
+// that one warp task is bounded whatever the row length (the cell holding a pinhole is crossed by every ray of the frame).
+struct SartMatrix {
     int64_t* offset = nullptr;                 // [n + 1]
     int32_t* index = nullptr;                  // [nnz]
     void* value = nullptr;                     // [nnz] float or double
+    int64_t* chunk_off = nullptr;              // [n + 1] first chunk of every row
+    int32_t* chunk_row = nullptr;              // [n_chunks]
+    int64_t n_chunks = 0;
 };
 
 template <typename VT>
@@ -47,125 +56,137 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// acc[f] = sum over the entries [e0, e1) of value * vec[index * FR + f]; lanes stride the entries, 4 loads in flight
+// part[c][f] = sum over the entries of chunk c of value * vec[index][f]; lanes stride the entries with 4 loads in flight,
+// then a butterfly: the order of the additions depends on nothing but the chunk.
 template <typename VT, int FR>
-__device__ __forceinline__ void sparse_dot(const int32_t* __restrict__ index, const void* __restrict__ value, int64_t e0, int64_t e1,
-                                           const double* __restrict__ vec, int lane, double (&acc)[FR]) {
+__global__ void __launch_bounds__(SART_THREADS) sart_dot_kernel(SartMatrix mat, const double* __restrict__ vec, double* __restrict__ part,
+                                                                const int32_t* __restrict__ flags) {
+    if (flags[2] == 0) return;                 // every frame has stopped
+    const int32_t* __restrict__ index = mat.index;
+    const void* __restrict__ value = mat.value;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * SART_WARPS;
+    for (int64_t c = (int64_t)blockIdx.x * SART_WARPS + (threadIdx.x >> 5); c < mat.n_chunks; c += n_warps) {
+        const int32_t r = __ldg(mat.chunk_row + c);
+        const int64_t e0 = __ldg(mat.offset + r) + (c - __ldg(mat.chunk_off + r)) * SART_CHUNK;
+        const int64_t row_end = __ldg(mat.offset + r + 1);
+        const int64_t e1 = e0 + SART_CHUNK < row_end ? e0 + SART_CHUNK : row_end;
+        double acc[FR];
 #pragma unroll
-    for (int f = 0; f < FR; f++) acc[f] = 0.0;
-    int64_t e = e0 + lane;
-    for (; e + 96 < e1; e += 128) {
-        int32_t c[4];
-        double v[4];
+        for (int f = 0; f < FR; f++) acc[f] = 0.0;
+        int64_t e = e0 + lane;
+        for (; e + 96 < e1; e += 128) {
+            int32_t ci[4];
+            double v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            c[u] = __ldg(index + e + 32 * u);
-            v[u] = load_value<VT>(value, e + 32 * u);
+            for (int u = 0; u < 4; u++) {
+                ci[u] = __ldg(index + e + 32 * u);
+                v[u] = load_value<VT>(value, e + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int f = 0; f < FR; f++) acc[f] = fma(v[u], vec[(int64_t)ci[u] * FR + f], acc[f]);
+        }
+        for (; e < e1; e += 32) {
+            const int32_t ci = __ldg(index + e);
+            const double v = load_value<VT>(value, e);
+#pragma unroll
+            for (int f = 0; f < FR; f++) acc[f] = fma(v, vec[(int64_t)ci * FR + f], acc[f]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int f = 0; f < FR; f++) acc[f] = warp_sum(acc[f]);
+        if (lane < FR) {
+            double a = acc[0];
 #pragma unroll
-            for (int f = 0; f < FR; f++) acc[f] = fma(v[u], vec[(int64_t)c[u] * FR + f], acc[f]);
+            for (int f = 1; f < FR; f++) a = lane == f ? acc[f] : a;
+            part[c * FR + lane] = a;
+        }
     }
-    for (; e < e1; e += 32) {
-        const int32_t c = __ldg(index + e);
-        const double v = load_value<VT>(value, e);
-#pragma unroll
-        for (int f = 0; f < FR; f++) acc[f] = fma(v, vec[(int64_t)c * FR + f], acc[f]);
-    }
-#pragma unroll
-    for (int f = 0; f < FR; f++) acc[f] = warp_sum(acc[f]);
 }
 
 // per-frame solver state on the device
 struct SartFrames {
     double* x;            // [n_sources][FR]  current estimate
+    double* x_new;        // [n_sources][FR]  next estimate (swapped with x after every backward pass)
     double* w;            // [n_detectors][FR] (m - y_hat) / ray_length
     double* m;            // [n_detectors][FR] measurements
-    double* gp;           // [n_sources][FR]  beta * L x
-    double* partial;      // [grid][FR] per-CTA sums of y_hat^2
+    double* part;         // [max chunks][FR] chunk sums of the running pass
+    double* partial;      // [SART_FIN_GRID][FR] per-CTA sums of y_hat^2
     double* conv;         // [FR][max_iterations]
     double* m_sq;         // [FR]
     int32_t* stopped;     // [FR] 0 while iterating, else the iteration count at which the frame stopped
     int32_t* flags;       // [0] ticket, [1] iteration index k of the running pass, [2] number of frames still iterating
 };
 
-// gp = beta * L x   (sart.pyx:255-256)
+// x_new_j = max(0, x_j + omega / W_+j * sum_i W_ij w_i - beta (L x)_j)   (sart.pyx:118-142, :255-285); one thread per source
 template <int FR>
-__global__ void __launch_bounds__(SART_THREADS) sart_penalty_kernel(int64_t n_sources, const int64_t* __restrict__ off,
-                                                                    const int32_t* __restrict__ idx, const void* __restrict__ val,
-                                                                    SartFrames fr, double beta) {
+__global__ void __launch_bounds__(SART_THREADS) sart_update_kernel(int64_t n_sources, const int64_t* __restrict__ chunk_off,
+                                                                   const double* __restrict__ density, SartMatrix lap, SartFrames fr,
+                                                                   double relaxation, double beta) {
     if (fr.flags[2] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = (int64_t)gridDim.x * SART_WARPS;
-    for (int64_t j = (int64_t)blockIdx.x * SART_WARPS + (threadIdx.x >> 5); j < n_sources; j += n_warps) {
-        double acc[FR];
-        sparse_dot<double, FR>(idx, val, off[j], off[j + 1], fr.x, lane, acc);
-        if (lane < FR) {
-            double a = acc[0];
-#pragma unroll
-            for (int f = 1; f < FR; f++) a = lane == f ? acc[f] : a;
-            fr.gp[j * FR + lane] = beta * a;
-        }
-    }
-}
-
-// x_j <- max(0, x_j + omega / W_+j * sum_i W_ij w_i - gp_j)   (sart.pyx:118-142, :258-285)
-template <typename VT, int FR>
-__global__ void __launch_bounds__(SART_THREADS) sart_backward_kernel(int64_t n_sources, const int64_t* __restrict__ off,
-                                                                     const int32_t* __restrict__ idx, const void* __restrict__ val,
-                                                                     const double* __restrict__ density, SartFrames fr,
-                                                                     double relaxation, int with_penalty) {
-    if (fr.flags[2] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = (int64_t)gridDim.x * SART_WARPS;
-    for (int64_t j = (int64_t)blockIdx.x * SART_WARPS + (threadIdx.x >> 5); j < n_sources; j += n_warps) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_sources; j += (int64_t)gridDim.x * blockDim.x) {
         const double dens = density[j];
-        double acc[FR];
-        if (dens > 0.0) {
-            sparse_dot<VT, FR>(idx, val, off[j], off[j + 1], fr.w, lane, acc);
-        } else {
+        double a[FR], pen[FR];
 #pragma unroll
-            for (int f = 0; f < FR; f++) acc[f] = 0.0;
+        for (int f = 0; f < FR; f++) { a[f] = 0.0; pen[f] = 0.0; }
+        for (int64_t c = chunk_off[j]; c < chunk_off[j + 1]; c++)
+#pragma unroll
+            for (int f = 0; f < FR; f++) a[f] += fr.part[c * FR + f];
+        if (lap.offset) {
+            const double* lv = reinterpret_cast<const double*>(lap.value);
+            for (int64_t e = lap.offset[j]; e < lap.offset[j + 1]; e++) {
+                const double l = lv[e];
+                const int64_t col = lap.index[e];
+#pragma unroll
+                for (int f = 0; f < FR; f++) pen[f] = fma(l, fr.x[col * FR + f], pen[f]);
+            }
         }
-        if (lane < FR && fr.stopped[lane] == 0) {
-            double a = acc[0];
 #pragma unroll
-            for (int f = 1; f < FR; f++) a = lane == f ? acc[f] : a;
-            double xn = fr.x[j * FR + lane];
-            if (dens > 0.0) xn += relaxation / dens * a;
-            if (with_penalty) xn -= fr.gp[j * FR + lane];
-            fr.x[j * FR + lane] = xn < 0.0 ? 0.0 : xn;
+        for (int f = 0; f < FR; f++) {
+            const double xo = fr.x[j * FR + f];
+            double xn = xo;
+            if (dens > 0.0) xn += relaxation / dens * a[f];
+            if (lap.offset) xn -= beta * pen[f];
+            xn = xn < 0.0 ? 0.0 : xn;
+            fr.x_new[j * FR + f] = fr.stopped[f] ? xo : xn;     // a stopped frame keeps its solution
         }
     }
 }
 
-// y_hat = W x, w = (m - y_hat)/W_i+, |y_hat|^2; the last CTA records the convergence and applies the stop test
-// (sart.pyx:96-97, :144-153).  record == 0: the initial projection before the first iteration.
-template <typename VT, int FR>
-__global__ void __launch_bounds__(SART_THREADS) sart_forward_kernel(int64_t n_detectors, const int64_t* __restrict__ off,
-                                                                    const int32_t* __restrict__ idx, const void* __restrict__ val,
-                                                                    const double* __restrict__ inv_length, SartFrames fr, int record,
-                                                                    int max_iterations, double conv_tol) {
+// y_hat_i from the chunk sums, w_i = (m_i - y_hat_i) / W_i+, |y_hat|^2; the last CTA records the convergence and applies the
+// stop test (sart.pyx:96-97, :144-153).  One thread per detector; record == 0: the projection before the first iteration.
+template <int FR>
+__global__ void __launch_bounds__(SART_THREADS) sart_residual_kernel(int64_t n_detectors, const int64_t* __restrict__ chunk_off,
+                                                                     const double* __restrict__ inv_length, SartFrames fr, int record,
+                                                                     int max_iterations, double conv_tol) {
     if (fr.flags[2] == 0) return;
     __shared__ double s_sq[SART_WARPS][FR];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_warps = (int64_t)gridDim.x * SART_WARPS;
-    double sq = 0.0;   // lane f < FR carries frame f
-    for (int64_t i = (int64_t)blockIdx.x * SART_WARPS + warp; i < n_detectors; i += n_warps) {
-        double acc[FR];
-        sparse_dot<VT, FR>(idx, val, off[i], off[i + 1], fr.x, lane, acc);
-        if (lane < FR) {
-            double y = acc[0];
+    double sq[FR];
 #pragma unroll
-            for (int f = 1; f < FR; f++) y = lane == f ? acc[f] : y;
-            fr.w[i * FR + lane] = (fr.m[i * FR + lane] - y) * inv_length[i];   // inv_length is 0 for rays of zero length (sart.pyx:127-128)
-            sq = fma(y, y, sq);
+    for (int f = 0; f < FR; f++) sq[f] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_detectors; i += (int64_t)gridDim.x * blockDim.x) {
+        double y[FR];
+#pragma unroll
+        for (int f = 0; f < FR; f++) y[f] = 0.0;
+        for (int64_t c = chunk_off[i]; c < chunk_off[i + 1]; c++)
+#pragma unroll
+            for (int f = 0; f < FR; f++) y[f] += fr.part[c * FR + f];
+        const double il = inv_length[i];                         // 0 for rays of zero length (sart.pyx:127-128)
+#pragma unroll
+        for (int f = 0; f < FR; f++) {
+            fr.w[i * FR + f] = (fr.m[i * FR + f] - y[f]) * il;
+            sq[f] = fma(y[f], y[f], sq[f]);
         }
     }
     if (!record) return;
-    if (lane < FR) s_sq[warp][lane] = sq;
+#pragma unroll
+    for (int f = 0; f < FR; f++) {
+        const double t = warp_sum(sq[f]);
+        if (lane == 0) s_sq[warp][f] = t;
+    }
     __syncthreads();
     if (threadIdx.x < FR) {
         double t = 0.0;
@@ -198,6 +219,18 @@ __global__ void __launch_bounds__(SART_THREADS) sart_forward_kernel(int64_t n_de
         fr.flags[1] = k + 1;
         fr.flags[2] = still;
     }
+}
+
+// chunk table of a sparse operand
+__global__ void chunk_count_kernel(int64_t n, const int64_t* __restrict__ off, int64_t* __restrict__ chunk_off) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t len = r < n ? off[r + 1] - off[r] : 0;
+        chunk_off[r] = r < n ? (len > SART_CHUNK ? (len + SART_CHUNK - 1) / SART_CHUNK : 1) : 0;
+    }
+}
+__global__ void chunk_fill_kernel(int64_t n, const int64_t* __restrict__ chunk_off, int32_t* __restrict__ chunk_row) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t c = chunk_off[r]; c < chunk_off[r + 1]; c++) chunk_row[c] = (int32_t)r;
 }
 
 template <typename T>
@@ -256,14 +289,29 @@ struct cb2_sart {
 namespace {
 
 void free_matrix(SartMatrix& m) {
-    cudaFree(m.offset); cudaFree(m.index); cudaFree(m.value);
+    cudaFree(m.offset); cudaFree(m.index); cudaFree(m.value); cudaFree(m.chunk_off); cudaFree(m.chunk_row);
     m = SartMatrix();
 }
 
-int grid_for(const cb2_sart* s, int64_t rows) {
-    int64_t need = (rows + SART_WARPS - 1) / SART_WARPS;
-    int64_t cap = (int64_t)s->sm_count * 8;     // 8 CTAs of 256 threads per SM: every warp slot filled, fixed grid => fixed reduction order
+int dot_grid(const cb2_sart* s, int64_t n_chunks) {
+    int64_t need = (n_chunks + SART_WARPS - 1) / SART_WARPS;
+    int64_t cap = (int64_t)s->sm_count * 32;      // a few waves of 8-warp CTAs; chunk results do not depend on the grid
     return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+// chunk table (chunk_off, chunk_row) of an operand whose offset array is on the device
+int build_chunks(cb2_sart* s, SartMatrix& m, int64_t n) {
+    cudaStream_t st = s->stream;
+    CB2_CUDA(cudaMalloc((void**)&m.chunk_off, (n + 1) * sizeof(int64_t)));
+    const int blocks = s->sm_count * 4;
+    chunk_count_kernel<<<blocks, 256, 0, st>>>(n, m.offset, m.chunk_off);
+    int rc = cb2_launch_scan(m.chunk_off, n + 1, st);
+    if (rc != CB2_OK) return rc;
+    CB2_CUDA(cudaMemcpyAsync(&m.n_chunks, m.chunk_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA(cudaStreamSynchronize(st));
+    CB2_CUDA(cudaMalloc((void**)&m.chunk_row, (m.n_chunks ? m.n_chunks : 1) * sizeof(int32_t)));
+    chunk_fill_kernel<<<blocks, 256, 0, st>>>(n, m.chunk_off, m.chunk_row);
+    return cb2_cuda_check(cudaGetLastError(), "SART chunk table");
 }
 
 // dense row-major host matrix -> host CSR (exact zeros dropped: they add nothing to any sum of the reference loop)
@@ -344,6 +392,8 @@ int build_operands(cb2_sart* s, const double* val64) {
         row_sums_kernel<VT><<<blocks, 256, 0, st>>>(s->n_det, s->csr.offset, s->csr.value, s->inv_length, 1);
         row_sums_kernel<VT><<<blocks, 256, 0, st>>>(s->n_src, s->csc.offset, s->csc.value, s->density, 0);
         if ((rc = cb2_cuda_check(cudaGetLastError(), "SART operand kernels")) != CB2_OK) break;
+        if ((rc = build_chunks(s, s->csr, s->n_det)) != CB2_OK) break;
+        if ((rc = build_chunks(s, s->csc, s->n_src)) != CB2_OK) break;
         rc = cb2_cuda_check(cudaStreamSynchronize(st), "SART operand build");
     } while (0);
     cudaFree(rows); cudaFree(iota); cudaFree(keys_out); cudaFree(perm); cudaFree(tmp);
@@ -448,16 +498,17 @@ extern "C" double cb2_sart_info(const cb2_sart* s, int what) {
 
 namespace {
 
-template <typename VT>
+template <typename VT, int FR>
 int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, const double* guess, double initial_value,
                 int max_iterations, double relaxation, double beta, double conv_tol, double* solution, double* convergence,
                 int32_t* n_iterations) {
-    constexpr int FR = SART_FR;
     const int nf = (int)((n_frames - f0) < FR ? (n_frames - f0) : FR);
     const int64_t nd = s->n_det, ns = s->n_src;
     cudaStream_t st = s->stream;
-    const int g_fwd = grid_for(s, nd), g_bwd = grid_for(s, ns);
-    const bool penal = s->lap.offset != nullptr;
+    const int g_fwd = dot_grid(s, s->csr.n_chunks), g_bwd = dot_grid(s, s->csc.n_chunks);
+    const int g_upd = (int)((ns + SART_THREADS - 1) / SART_THREADS < (int64_t)s->sm_count * 8 ? (ns + SART_THREADS - 1) / SART_THREADS : (int64_t)s->sm_count * 8);
+    const int g_res = (int)((nd + SART_THREADS - 1) / SART_THREADS < SART_FIN_GRID ? (nd + SART_THREADS - 1) / SART_THREADS : SART_FIN_GRID);
+    const int64_t max_chunks = s->csr.n_chunks > s->csc.n_chunks ? s->csr.n_chunks : s->csc.n_chunks;
     // host staging, frames innermost
     std::vector<double> h_m((size_t)nd * FR, 0.0), h_x((size_t)ns * FR, 0.0), h_msq(FR, 1.0);
     std::vector<int32_t> h_stop(FR, 1);
@@ -475,10 +526,11 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
     do {
 #define SART_TRY(call) if ((rc = cb2_cuda_check((call), #call)) != CB2_OK) break
         SART_TRY(cudaMalloc((void**)&fr.x, (size_t)ns * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.gp, (size_t)ns * FR * sizeof(double)));
+        SART_TRY(cudaMalloc((void**)&fr.x_new, (size_t)ns * FR * sizeof(double)));
         SART_TRY(cudaMalloc((void**)&fr.w, (size_t)nd * FR * sizeof(double)));
         SART_TRY(cudaMalloc((void**)&fr.m, (size_t)nd * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.partial, (size_t)g_fwd * FR * sizeof(double)));
+        SART_TRY(cudaMalloc((void**)&fr.part, (size_t)(max_chunks ? max_chunks : 1) * FR * sizeof(double)));
+        SART_TRY(cudaMalloc((void**)&fr.partial, (size_t)SART_FIN_GRID * FR * sizeof(double)));
         SART_TRY(cudaMalloc((void**)&fr.conv, (size_t)FR * max_iterations * sizeof(double)));
         SART_TRY(cudaMalloc((void**)&fr.m_sq, FR * sizeof(double)));
         SART_TRY(cudaMalloc((void**)&fr.stopped, FR * sizeof(int32_t)));
@@ -489,19 +541,19 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
         SART_TRY(cudaMemcpyAsync(fr.stopped, h_stop.data(), FR * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         SART_TRY(cudaMemcpyAsync(fr.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, st));
         SART_TRY(cudaMemsetAsync(fr.conv, 0, (size_t)FR * max_iterations * sizeof(double), st));
-        SART_TRY(cudaMemsetAsync(fr.gp, 0, (size_t)ns * FR * sizeof(double), st));
         SART_TRY(cudaEventRecord(s->ev0, st));
-        sart_forward_kernel<VT, FR><<<g_fwd, SART_THREADS, 0, st>>>(nd, s->csr.offset, s->csr.index, s->csr.value, s->inv_length, fr, 0,
-                                                                    max_iterations, conv_tol);
+        // y_hat of the initial guess (sart.pyx:96-97)
+        sart_dot_kernel<VT, FR><<<g_fwd, SART_THREADS, 0, st>>>(s->csr, fr.x, fr.part, fr.flags);
+        sart_residual_kernel<FR><<<g_res, SART_THREADS, 0, st>>>(nd, s->csr.chunk_off, s->inv_length, fr, 0, max_iterations, conv_tol);
         int launched = 0;
         while (launched < max_iterations) {
             const int chunk = (max_iterations - launched) < SART_CHECK_EVERY ? (max_iterations - launched) : SART_CHECK_EVERY;
             for (int c = 0; c < chunk; c++) {
-                if (penal) sart_penalty_kernel<FR><<<g_bwd, SART_THREADS, 0, st>>>(ns, s->lap.offset, s->lap.index, s->lap.value, fr, beta);
-                sart_backward_kernel<VT, FR><<<g_bwd, SART_THREADS, 0, st>>>(ns, s->csc.offset, s->csc.index, s->csc.value, s->density, fr,
-                                                                             relaxation, penal ? 1 : 0);
-                sart_forward_kernel<VT, FR><<<g_fwd, SART_THREADS, 0, st>>>(nd, s->csr.offset, s->csr.index, s->csr.value, s->inv_length, fr, 1,
-                                                                            max_iterations, conv_tol);
+                sart_dot_kernel<VT, FR><<<g_bwd, SART_THREADS, 0, st>>>(s->csc, fr.w, fr.part, fr.flags);
+                sart_update_kernel<FR><<<g_upd, SART_THREADS, 0, st>>>(ns, s->csc.chunk_off, s->density, s->lap, fr, relaxation, beta);
+                double* t = fr.x; fr.x = fr.x_new; fr.x_new = t;
+                sart_dot_kernel<VT, FR><<<g_fwd, SART_THREADS, 0, st>>>(s->csr, fr.x, fr.part, fr.flags);
+                sart_residual_kernel<FR><<<g_res, SART_THREADS, 0, st>>>(nd, s->csr.chunk_off, s->inv_length, fr, 1, max_iterations, conv_tol);
             }
             launched += chunk;
             SART_TRY(cudaGetLastError());
@@ -511,10 +563,14 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
         }
         if (rc != CB2_OK) break;
         SART_TRY(cudaEventRecord(s->ev1, st));
-        SART_TRY(cudaMemcpyAsync(h_x.data(), fr.x, h_x.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
         SART_TRY(cudaMemcpyAsync(h_stop.data(), fr.stopped, FR * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         std::vector<double> h_conv((size_t)FR * max_iterations);
         SART_TRY(cudaMemcpyAsync(h_conv.data(), fr.conv, h_conv.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SART_TRY(cudaStreamSynchronize(st));
+        // the host swapped the buffers once per launched iteration, the device only wrote x_new while a frame was still
+        // iterating (h_flags[1] iterations): undo the swaps of the launches that returned at once
+        if ((launched - h_flags[1]) & 1) { double* t = fr.x; fr.x = fr.x_new; fr.x_new = t; }
+        SART_TRY(cudaMemcpyAsync(h_x.data(), fr.x, h_x.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
         SART_TRY(cudaStreamSynchronize(st));
         float ms = 0.f;
         SART_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -528,9 +584,26 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
         }
 #undef SART_TRY
     } while (0);
-    cudaFree(fr.x); cudaFree(fr.gp); cudaFree(fr.w); cudaFree(fr.m); cudaFree(fr.partial); cudaFree(fr.conv); cudaFree(fr.m_sq);
-    cudaFree(fr.stopped); cudaFree(fr.flags);
+    cudaFree(fr.x); cudaFree(fr.x_new); cudaFree(fr.w); cudaFree(fr.m); cudaFree(fr.part); cudaFree(fr.partial); cudaFree(fr.conv);
+    cudaFree(fr.m_sq); cudaFree(fr.stopped); cudaFree(fr.flags);
     return rc;
+}
+
+template <typename VT>
+int solve_all(cb2_sart* s, const double* meas, int64_t n_frames, const double* guess, double initial_value, int max_iterations,
+              double relaxation, double beta, double conv_tol, double* solution, double* convergence, int32_t* n_iterations) {
+    int64_t f0 = 0;
+    while (f0 < n_frames) {
+        // groups of four frames share every pass over the matrix; a last single frame runs with one-wide vectors
+        const bool four = n_frames - f0 >= 2;
+        int rc = four ? solve_group<VT, 4>(s, meas, n_frames, f0, guess, initial_value, max_iterations, relaxation, beta, conv_tol, solution,
+                                           convergence, n_iterations)
+                      : solve_group<VT, 1>(s, meas, n_frames, f0, guess, initial_value, max_iterations, relaxation, beta, conv_tol, solution,
+                                           convergence, n_iterations);
+        if (rc != CB2_OK) return rc;
+        f0 += four ? 4 : 1;
+    }
+    return CB2_OK;
 }
 
 }  // namespace
@@ -544,12 +617,8 @@ extern "C" int cb2_sart_solve(cb2_sart* s, const double* measurements, int64_t n
     CB2_CUDA(cudaSetDevice(s->device));
     s->last_ms = 0.0;
     s->last_iterations = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += SART_FR) {
-        int rc = s->value_f64 ? solve_group<double>(s, measurements, n_frames, f0, initial_guess, initial_value, max_iterations, relaxation,
-                                                    beta_laplace, conv_tol, solution, convergence, n_iterations)
-                              : solve_group<float>(s, measurements, n_frames, f0, initial_guess, initial_value, max_iterations, relaxation,
-                                                   beta_laplace, conv_tol, solution, convergence, n_iterations);
-        if (rc != CB2_OK) return rc;
-    }
-    return CB2_OK;
+    return s->value_f64 ? solve_all<double>(s, measurements, n_frames, initial_guess, initial_value, max_iterations, relaxation, beta_laplace,
+                                            conv_tol, solution, convergence, n_iterations)
+                        : solve_all<float>(s, measurements, n_frames, initial_guess, initial_value, max_iterations, relaxation, beta_laplace,
+                                           conv_tol, solution, convergence, n_iterations);
 }

@@ -59,7 +59,7 @@ def main():
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    hbm = float(peaks.get("hbm_gbps", peaks.get("hbm_GBps", 0)) or 0) or 6547.5
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
     out = {"metric": "sart_iterations_per_second", "value": it * a.frames / (ms * 1e-3), "unit": "frame-iterations/s",
            "config": {"workload": "C4 geometry matrix %dx%d rays x %d sources" % (a.pixels, a.pixels, rtc.bins), "nnz": int(info["nnz"]),
                       "frames": a.frames, "iterations": int(it), "value_dtype": "f32" if a.f32 else "f64"},
