@@ -5,7 +5,7 @@ mirror of the reference's operator interface for this path (Plasma, Species, Max
 RecombinationLine, Bremsstrahlung, line shapes, RayTransferCylinder/Box and the RayTransferPipelines).
 No CPU fallback: calls fail loudly if the CUDA library or a GPU is missing.
 """
-from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, SyntheticADAS, carbon, deuterium, helium,
+from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, RateTable3D, SyntheticADAS, carbon, deuterium, helium,
                      hydrogen, neon, nitrogen, tritium)
 from .beam import (Beam, BeamCXLine, BeamEmissionLine, BeamCXTable, BeamStoppingTable, ConstantBeamCXPEC, SingleRayAttenuator, beam_ray_segments,
                    flatten_beam_scene)

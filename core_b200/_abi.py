@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -99,6 +99,7 @@ class ModelExt(C.Structure):
                 ("line_rad_species", C.c_int32), ("recom_species", C.c_int32), ("n_hydrogen", C.c_int32), ("has_plt", C.c_int32),
                 ("has_prb", C.c_int32), ("has_prc", C.c_int32), ("hydrogen_species", c_int32_p),
                 ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D), ("n_cx", C.c_int32), ("_pad3", C.c_int32), ("cx", C.POINTER(CXRate)),
+                ("cx_population", C.POINTER(BeamRate)),
                 ("n_bes", C.c_int32), ("_pad4", C.c_int32), ("bes_species", c_int32_p), ("bes_rates", C.POINTER(BeamRate)),
                 ("mse_ratios", C.c_double * 4)]
 

@@ -70,6 +70,21 @@ class RateTable:
         self.extrapolate = bool(extrapolate)
 
 
+class RateTable3D:
+    """A thermal-CX PEC block: the ``data`` dict ThermalCXPEC takes, {'ne','te','td','rate'} (openadas/rates/pec.pyx:153-184)."""
+
+    def __init__(self, ne, te, td, rate, extrapolate=False):
+        self.ne = np.ascontiguousarray(ne, dtype=np.float64)
+        self.te = np.ascontiguousarray(te, dtype=np.float64)
+        self.td = np.ascontiguousarray(td, dtype=np.float64)
+        self.rate = np.ascontiguousarray(rate, dtype=np.float64)
+        if self.rate.shape != (self.ne.size, self.te.size, self.td.size):
+            raise ValueError("rate must have shape (len(ne), len(te), len(td))")
+        if min(self.rate.shape) < 2:
+            raise ValueError("thermal CX rate tables need at least 2 knots per axis")
+        self.extrapolate = bool(extrapolate)
+
+
 class ConstantRate:
     """Constant-valued rate in W m^3, as the mock AtomicData of core/tests/test_line_emission.py:32-88 returns."""
 
@@ -104,6 +119,11 @@ class AtomicData:
     def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
         """List of effective CX emission coefficients, one per donor metastable (interface.pyx:86-95)."""
         raise NotImplementedError("The cxs_rates() virtual method is not implemented for this atomic data source.")
+
+    def beam_population_rate(self, beam_ion, metastable, plasma_ion, charge):
+        """Population of a beam metastable relative to the ground state (interface.pyx:97-107); a BeamStoppingTable-shaped
+        dimensionless table, a ConstantRate or None (NullBeamPopulationRate)."""
+        raise NotImplementedError("The beam_population() virtual method is not implemented for this atomic data source.")
 
     def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
         raise NotImplementedError("The beam_emission() virtual method is not implemented for this atomic data source.")
@@ -212,6 +232,15 @@ class SyntheticADAS(AtomicData):
         qz = qref * (1 + 0.03 * (z - 2.0))
         qb = qref * (1 + 0.004 * b)
         return [BeamCXTable(1, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref)]
+
+    def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+        """Synthetic ThermalCXPEC-shaped table on (ne[24], te[29], td[12]): smooth, positive, falling with the donor charge."""
+        s, _ = self._scale(transition)
+        td = np.logspace(-0.7, 4.0, 12)
+        ne, te, tdd = self.ne[:, None, None], self.te[None, :, None], td[None, None, :]
+        rate = (s * 2e-15 / (1.0 + donor_charge) * (tdd / 10.0) ** 0.3 / (1.0 + tdd / 3e3) * (te / 10.0) ** -0.1
+                * (1.0 + 0.05 * np.log10(ne / 1e19)))
+        return RateTable3D(self.ne, self.te, td, rate, self.permit_extrapolation)
 
     def recombination_pec(self, ion, charge, transition):
         s, _ = self._scale(transition)

@@ -100,6 +100,16 @@ class BeamCXLine(BeamModel):
             raise RuntimeError("The plasma object does not contain the ion species for the specified CX line "
                                "(element={}, ionisation={}).".format(element.symbol, charge))
         rates = list(atomic_data.beam_cx_pec(beam.element, element, charge, self.line.transition))
+        ground = [r for r in rates if r.donor_metastable == 1]
+        if len(ground) != 1:
+            raise RuntimeError("beam_cx_pec must return exactly one rate for the ground-state donor (metastable 1).")
+        excited = [r for r in rates if r.donor_metastable != 1]
+        if len(excited) > 3:
+            raise ValueError("At most three excited donor metastables are supported.")
+        # charge_exchange.pyx:341-361: every excited rate is linked with the population coefficients of all plasma species
+        self.population = [[atomic_data.beam_population_rate(beam.element, r.donor_metastable, sp.element, sp.charge)
+                            for sp in plasma.composition] for r in excited]
+        rates = ground + excited
         wavelength = atomic_data.wavelength(element, charge - 1, self.line.transition)
         species = plasma.composition.get(element, charge)
         shape = self.lineshape_class(self.line, wavelength, species, plasma, atomic_data, *self.lineshape_args, **self.lineshape_kwargs)
@@ -318,6 +328,14 @@ def flatten_beam_scene(beam, min_wavelength, max_wavelength, bins):
             _fill_cx_rate(arr[k], r, keep)
         ext.n_cx = len(cx_rates)
         ext.cx = C.cast(arr, C.POINTER(_abi.CXRate))
+        if len(cx_rates) > 1:
+            n_sp = len(list(plasma.composition))
+            parr = (_abi.BeamRate * ((len(cx_rates) - 1) * n_sp))()
+            for k, row in enumerate(mdl.population):
+                for s_i, r in enumerate(row):
+                    _fill_beam_rate(parr[k * n_sp + s_i], r, keep)
+            ext.cx_population = C.cast(parr, C.POINTER(_abi.BeamRate))
+            keep.append(parr)
         keep.extend([shape, arr, ext])
         mo.ext = C.pointer(ext)
     keep.append(mo_arr)

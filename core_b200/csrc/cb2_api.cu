@@ -207,6 +207,83 @@ static DevTable2D make_table2d(Arena& A, const double* x, const double* y, const
     return t;
 }
 
+// four-corner cross difference on a strided 2-D slice (rows: knots a, stride sa; columns: knots b, stride sb)
+static double d2s(const double* a, const double* b, const double* f, int na, int nb, size_t sa, size_t sb, int i, int j) {
+    const int il = i > 0 ? i - 1 : i, ih = i < na - 1 ? i + 1 : i;
+    const int jl = j > 0 ? j - 1 : j, jh = j < nb - 1 ? j + 1 : j;
+    if (il == ih || jl == jh) return 0.0;
+    return (f[ih * sa + jh * sb] - f[ih * sa + jl * sb] - f[il * sa + jh * sb] + f[il * sa + jl * sb]) / ((a[ih] - a[il]) * (b[jh] - b[jl]));
+}
+
+// Tricubic Hermite table (raysect Interpolator3DArray 'cubic', restated): f and its seven first / cross derivatives at the
+// knots (3-point first derivatives, four- and eight-corner cross differences), reduced per cell to the 64 monomial
+// coefficients of t^p u^q w^r in fp64 and stored as 16 float4 (the powers of w innermost).
+static DevTable3D make_table3d(Arena& A, const double* x, const double* y, const double* z, const double* f, int nx, int ny, int nz) {
+    DevTable3D T;
+    memset(&T, 0, sizeof T);
+    T.nx = nx; T.ny = ny; T.nz = nz;
+    const size_t sx = (size_t)ny * nz, sy = (size_t)nz, n = (size_t)nx * sx;
+    // D[ox][oy][oz]: derivative of order (ox, oy, oz) at every knot
+    std::vector<double> D[2][2][2];
+    for (int a = 0; a < 8; a++) D[a >> 2][(a >> 1) & 1][a & 1].resize(n);
+    for (int i = 0; i < nx; i++)
+        for (int j = 0; j < ny; j++)
+            for (int k = 0; k < nz; k++) {
+                const size_t o = i * sx + j * sy + k;
+                D[0][0][0][o] = f[o];
+                D[1][0][0][o] = d1(x, f + j * sy + k, nx, (int)sx, i);
+                D[0][1][0][o] = d1(y, f + i * sx + k, ny, (int)sy, j);
+                D[0][0][1][o] = d1(z, f + i * sx + j * sy, nz, 1, k);
+                D[1][1][0][o] = d2s(x, y, f + k, nx, ny, sx, sy, i, j);
+                D[1][0][1][o] = d2s(x, z, f + j * sy, nx, nz, sx, 1, i, k);
+                D[0][1][1][o] = d2s(y, z, f + i * sx, ny, nz, sy, 1, j, k);
+                const int il = i > 0 ? i - 1 : i, ih = i < nx - 1 ? i + 1 : i, jl = j > 0 ? j - 1 : j, jh = j < ny - 1 ? j + 1 : j;
+                const int kl = k > 0 ? k - 1 : k, kh = k < nz - 1 ? k + 1 : k;
+                double c3 = 0.0;
+                if (il != ih && jl != jh && kl != kh) {
+                    auto F = [&](int a, int b, int c) { return f[a * sx + b * sy + c]; };
+                    c3 = (F(ih, jh, kh) - F(ih, jh, kl) - F(ih, jl, kh) + F(ih, jl, kl) - F(il, jh, kh) + F(il, jh, kl) + F(il, jl, kh) - F(il, jl, kl)) /
+                         ((x[ih] - x[il]) * (y[jh] - y[jl]) * (z[kh] - z[kl]));
+                }
+                D[1][1][1][o] = c3;
+            }
+    std::vector<float4> coef((size_t)(nx - 1) * (ny - 1) * (nz - 1) * 16);
+    for (int i = 0; i + 1 < nx; i++)
+        for (int j = 0; j + 1 < ny; j++)
+            for (int k = 0; k + 1 < nz; k++) {
+                const double h[3] = {x[i + 1] - x[i], y[j + 1] - y[j], z[k + 1] - z[k]};
+                // Hermite "quantities" along an axis: 0 value at knot 0, 1 value at knot 1, 2 scaled derivative at 0, 3 at 1
+                double cx[4][4][4];   // [qy][qz][power of t]
+                for (int qy = 0; qy < 4; qy++)
+                    for (int qz = 0; qz < 4; qz++) {
+                        const int jj = j + (qy & 1), kk = k + (qz & 1), oy = qy >> 1, oz = qz >> 1;
+                        const double sc = (oy ? h[1] : 1.0) * (oz ? h[2] : 1.0);
+                        const size_t o0 = i * sx + jj * sy + kk, o1 = o0 + sx;
+                        hermite_coef(D[0][oy][oz][o0] * sc, D[0][oy][oz][o1] * sc, D[1][oy][oz][o0] * sc * h[0], D[1][oy][oz][o1] * sc * h[0], cx[qy][qz]);
+                    }
+                for (int p = 0; p < 4; p++) {
+                    double cy[4][4];  // [qz][power of u]
+                    for (int qz = 0; qz < 4; qz++) hermite_coef(cx[0][qz][p], cx[1][qz][p], cx[2][qz][p], cx[3][qz][p], cy[qz]);
+                    for (int q = 0; q < 4; q++) {
+                        double a[4];
+                        hermite_coef(cy[0][q], cy[1][q], cy[2][q], cy[3][q], a);
+                        coef[(((size_t)i * (ny - 1) + j) * (nz - 1) + k) * 16 + 4 * p + q] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+                    }
+                }
+            }
+    auto knots = [&](const double* v, int m, const float*& kv, const float*& iw, float& lo, float& hi) {
+        std::vector<float> xs(m), w(std::max(m - 1, 1));
+        for (int q = 0; q < m; q++) xs[q] = (float)v[q];
+        for (int q = 0; q + 1 < m; q++) w[q] = (float)(1.0 / (v[q + 1] - v[q]));
+        kv = A.upload(xs); iw = A.upload(w); lo = (float)v[0]; hi = (float)v[m - 1];
+    };
+    knots(x, nx, T.x, T.inv_wx, T.xmin, T.xmax);
+    knots(y, ny, T.y, T.inv_wy, T.ymin, T.ymax);
+    knots(z, nz, T.z, T.inv_wz, T.zmin, T.zmax);
+    T.coef = A.upload(coef);
+    return T;
+}
+
 // np.gradient(f, edge_order=2) along a strided line with unit spacing (efit.pyx:187-189)
 static void np_gradient_unit(const double* f, int n, int stride, double* out, int ostride) {
     for (int i = 0; i < n; i++) {
@@ -589,10 +666,10 @@ static int build_beam(Arena& A, const cb2_scene_desc& d, cb2_scene* sc) {
 }
 
 // BeamCXPEC tables of a BEAM_CX_LINE model (openadas/rates/cx.pyx:66-103)
-static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevModelExt& e) {
+static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevCXRate& e) {
     if (r.n_eb <= 0) {
-        e.cx_const = 1;
-        e.cx_lconst = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+        e.is_const = 1;
+        e.lconst = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
         return CB2_OK;
     }
     if (!(r.qref > 0)) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC qref must be positive");
@@ -615,13 +692,37 @@ static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevMode
             }
             if (i > 0 && !(x[i] > x[i - 1])) return cb2_fail(CB2_ERR_VALUE, "BeamCXPEC grids must be increasing");
         }
-        e.cx_n[k] = n;
-        e.cx_single[k] = (float)f[0];
+        e.n[k] = n;
+        e.single[k] = (float)f[0];
         if (n > 1) {
-            e.cx_t[k] = make_knots1d(A, x.data(), n);
-            e.cx_c[k] = make_coef1d(A, x.data(), f.data(), n, 1.0);
+            e.t[k] = make_knots1d(A, x.data(), n);
+            e.c[k] = make_coef1d(A, x.data(), f.data(), n, 1.0);
         }
     }
+    return A.rc;
+}
+
+// BeamPopulationRate table (beam.pyx:143-170): log10 sen on (log10 E, log10 n), log10(st / sref) on log10 T
+static int convert_population(Arena& A, const cb2_beam_rate& r, DevPopRate& e) {
+    memset(&e, 0, sizeof e);
+    if (r.n_e <= 0) {
+        e.is_const = 1;
+        e.lconst = r.constant > 0 ? (float)log10(r.constant) : -INFINITY;
+        return CB2_OK;
+    }
+    if (r.n_e < 2 || r.n_n < 2 || r.n_t < 2 || !(r.sref > 0))
+        return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "beam population tables need at least 2 points per axis on the device path");
+    std::vector<double> le(r.n_e), ln(r.n_n), lt(r.n_t), lsen((size_t)r.n_e * r.n_n), lst(r.n_t);
+    for (int i = 0; i < r.n_e; i++) le[i] = log10(r.e[i]);
+    for (int i = 0; i < r.n_n; i++) ln[i] = log10(r.n[i]);
+    for (int i = 0; i < r.n_t; i++) { lt[i] = log10(r.t[i]); lst[i] = log10(r.st[i] / r.sref); }
+    for (size_t i = 0; i < lsen.size(); i++) {
+        if (!(r.sen[i] > 0)) return cb2_fail(CB2_ERR_VALUE, "beam population table values must be positive (log10 interpolation)");
+        lsen[i] = log10(r.sen[i]);
+    }
+    e.a = make_table2d(A, le.data(), ln.data(), lsen.data(), r.n_e, r.n_n);
+    e.tk = make_knots1d(A, lt.data(), r.n_t);
+    e.tc = make_coef1d(A, lt.data(), lst.data(), r.n_t, 1.0);
     return A.rc;
 }
 
@@ -743,19 +844,31 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
     // rate table: log10(PhotonToJ(rate, wavelength)) + 38 on (log10 ne, log10 te)   (pec.pyx:59-68)
     o.pec_grid = -1;
     if (m.kind == CB2_MODEL_BEAM_CX_LINE) {
-        // charge_exchange.pyx:311-349: effective emission coefficients per donor metastable; ground state only so far
+        // charge_exchange.pyx:311-361: effective emission coefficients per donor metastable + the populations of the excited ones
         const cb2_model_ext* x = m.ext;
         if (!x || x->n_cx < 1) return cb2_fail(CB2_ERR_RUNTIME, "BeamCXLine needs its resolved CX rates");
-        if (x->n_cx > 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "excited donor metastables (BeamPopulationRate) are not supported yet");
+        if (x->n_cx > CB2_MAX_META) return cb2_fail(CB2_ERR_VALUE, "at most %d donor metastables are supported", CB2_MAX_META);
+        if (x->n_cx > 1 && !x->cx_population) return cb2_fail(CB2_ERR_RUNTIME, "excited donor metastables need their beam population rates");
         DevModelExt e;
         memset(&e, 0, sizeof e);
-        const int rc = convert_cx(A, x->cx[0], m.wavelength, e);
-        if (rc != CB2_OK) return rc;
+        e.n_cx = x->n_cx;
+        for (int k = 0; k < x->n_cx; k++) {
+            const int rc = convert_cx(A, x->cx[k], m.wavelength, e.cx[k]);
+            if (rc != CB2_OK) return rc;
+        }
+        if (x->n_cx > 1) {
+            std::vector<DevPopRate> pop((size_t)(x->n_cx - 1) * d.n_species);
+            for (size_t q = 0; q < pop.size(); q++) {
+                const int rc = convert_population(A, x->cx_population[q], pop[q]);
+                if (rc != CB2_OK) return rc;
+            }
+            e.pop = A.upload(pop);
+        }
         o.ext = A.upload(std::vector<DevModelExt>(1, e));
         o.pec_const = 1;
         o.pec_value = -INFINITY;
     } else if (m.kind == CB2_MODEL_THERMAL_CX_LINE) {
-        // thermal_cx.pyx:140-148: one rate per donor species; only constant rates so far
+        // thermal_cx.pyx:140-148: one rate per donor species, constant or tabulated
         const cb2_model_ext* x = m.ext;
         if (!x) return cb2_fail(CB2_ERR_RUNTIME, "ThermalCXLine needs its resolved donors");
         if (x->n_donors < 0 || x->n_donors > CB2_MAX_SPECIES) return cb2_fail(CB2_ERR_VALUE, "too many CX donors");
@@ -764,9 +877,29 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
         e.n_donors = x->n_donors;
         for (int k = 0; k < x->n_donors; k++) {
             if (x->donor_species[k] < 0 || x->donor_species[k] >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "donor species index out of range");
-            if (x->donor_rates[k].n_ne > 0) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "tabulated (3-D) thermal CX rates are not supported yet");
+            const cb2_rate3d& r3 = x->donor_rates[k];
             e.donor_species[k] = x->donor_species[k];
-            e.donor_lrate[k] = x->donor_rates[k].constant > 0 ? (float)(log10(x->donor_rates[k].constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+            e.donor_lrate[k] = r3.constant > 0 ? (float)(log10(r3.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
+            if (r3.n_ne > 0) {
+                // ThermalCXPEC (pec.pyx:153-184): log10(PhotonToJ(rate)) on (log10 ne, log10 te, log10 td)
+                if (r3.n_ne < 2 || r3.n_te < 2 || r3.n_td < 2) return cb2_fail(CB2_ERR_VALUE, "thermal CX rate tables need at least 2 knots per axis");
+                if (!r3.ne || !r3.te || !r3.td || !r3.rate) return cb2_fail(CB2_ERR_VALUE, "thermal CX rate table pointers missing");
+                std::vector<double> lx(r3.n_ne), ly(r3.n_te), lz(r3.n_td), lr((size_t)r3.n_ne * r3.n_te * r3.n_td);
+                for (int q = 0; q < r3.n_ne; q++) lx[q] = log10(r3.ne[q]);
+                for (int q = 0; q < r3.n_te; q++) ly[q] = log10(r3.te[q]);
+                for (int q = 0; q < r3.n_td; q++) lz[q] = log10(r3.td[q]);
+                for (int q = 0; q + 1 < r3.n_ne; q++) if (!(lx[q + 1] > lx[q])) return cb2_fail(CB2_ERR_VALUE, "rate table ne grid must be increasing");
+                for (int q = 0; q + 1 < r3.n_te; q++) if (!(ly[q + 1] > ly[q])) return cb2_fail(CB2_ERR_VALUE, "rate table te grid must be increasing");
+                for (int q = 0; q + 1 < r3.n_td; q++) if (!(lz[q + 1] > lz[q])) return cb2_fail(CB2_ERR_VALUE, "rate table td grid must be increasing");
+                const double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9;
+                for (size_t q = 0; q < lr.size(); q++) {
+                    if (!(r3.rate[q] > 0)) return cb2_fail(CB2_ERR_VALUE, "rate table values must be positive (log10 interpolation)");
+                    lr[q] = log10(r3.rate[q] / m.wavelength * conv) + CB2_PEC_LOG_OFFSET;
+                }
+                e.donor_tab[k] = 1;
+                e.donor_extrapolate[k] = r3.extrapolate != 0;
+                e.donor_t3[k] = make_table3d(A, lx.data(), ly.data(), lz.data(), lr.data(), r3.n_ne, r3.n_te, r3.n_td);
+            }
         }
         o.ext = A.upload(std::vector<DevModelExt>(1, e));
         o.pec_const = 1;

@@ -90,6 +90,27 @@ __device__ __forceinline__ float eval2d(const DevTable2D& T, const Cell2& c) {
     return fmaf(fmaf(fmaf(p3, c.t, p2), c.t, p1), c.t, p0);
 }
 
+// tricubic table lookup, arguments clamped to the table ('nearest'); inside = all three arguments within the table
+__device__ __forceinline__ float eval3d(const DevTable3D& T, float x, float y, float z, bool& inside) {
+    inside = (x >= T.xmin) && (x <= T.xmax) && (y >= T.ymin) && (y <= T.ymax) && (z >= T.zmin) && (z <= T.zmax);
+    x = fminf(fmaxf(x, T.xmin), T.xmax);
+    y = fminf(fmaxf(y, T.ymin), T.ymax);
+    z = fminf(fmaxf(z, T.zmin), T.zmax);
+    const int i = search_knots(T.x, T.nx, x), j = search_knots(T.y, T.ny, y), k = search_knots(T.z, T.nz, z);
+    const float t = (x - __ldg(T.x + i)) * __ldg(T.inv_wx + i);
+    const float u = (y - __ldg(T.y + j)) * __ldg(T.inv_wy + j);
+    const float w = (z - __ldg(T.z + k)) * __ldg(T.inv_wz + k);
+    const float4* q = T.coef + (((size_t)i * (T.ny - 1) + j) * (T.nz - 1) + k) * 16;
+    float r = 0.f;
+#pragma unroll
+    for (int p = 3; p >= 0; p--) {
+        const float e0 = horner4(__ldg(q + 4 * p), w), e1 = horner4(__ldg(q + 4 * p + 1), w);
+        const float e2 = horner4(__ldg(q + 4 * p + 2), w), e3 = horner4(__ldg(q + 4 * p + 3), w);
+        r = fmaf(r, t, fmaf(fmaf(fmaf(e3, u, e2), u, e1), u, e0));
+    }
+    return r;
+}
+
 // coefficients e_p(u) of t^p for a fixed second coordinate (used to turn the Gaunt bicubic into a cubic in log10 u)
 __device__ __forceinline__ float4 eval2d_rows(const DevTable2D& T, int i, int j, float u) {
     const float4* q = T.coef + ((size_t)i * (T.ny - 1) + j) * 4;

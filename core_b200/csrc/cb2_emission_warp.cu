@@ -76,6 +76,70 @@ __device__ __forceinline__ void need_b(const DevScene& S, const SampleIn& in, co
     lc.have_b = true;
 }
 
+// BeamCXPEC.evaluate (openadas/rates/cx.pyx:104-142): 10^c0(log10 E) times the four linear factors, zero as soon as a partial
+// product is <= 0; returns the rate in W m^3 scaled by 1e38.  args = log10 E (-inf: E <= 0), Ti, n_ion[1e19], Zeff, |B|.
+__device__ __forceinline__ float cx_rate_eval(const DevCXRate& R, const float (&args)[5], unsigned& ood) {
+    if (R.is_const) return exp10f(R.lconst);
+    if (!(args[0] > -INFINITY)) return 0.f;
+    float lq = 0.f, factor = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        float v;
+        if (R.n[k] == 1) v = R.single[k];
+        else {
+            // (a few fp32 ulps of slack: Zeff of a Z = 1 plasma must not count as below a table that starts at 1)
+            if (args[k] < R.t[k].xmin - 4e-6f * fabsf(R.t[k].xmin) || args[k] > R.t[k].xmax + 4e-6f * fabsf(R.t[k].xmax)) ood++;
+            int ci; float ct;
+            locate1d(R.t[k], args[k], ci, ct);
+            v = horner4(__ldg(R.c[k] + ci), ct);
+        }
+        if (k == 0) lq = v;
+        else {
+            factor *= v;
+            if (!(factor > 0.f)) return 0.f;
+        }
+    }
+    return exp10f(lq) * factor;
+}
+
+// BeamCXLine._beam_population (charge_exchange.pyx:241-292): charge-density weighted mean of the species' population
+// coefficients of one excited metastable; neutral species are skipped
+template <int AXONLY>
+__device__ __forceinline__ float beam_population(const DevScene& S, const DevPopRate* P, const SampleIn& in, const AxCtx& ctx,
+                                                 float density_sum, unsigned& ood) {
+    float pop = 0.f, total_ne = 0.f;
+    for (int sidx = 0; sidx < S.n_species; sidx++) {
+        const DevSpecies& sp = S.species[sidx];
+        if (sp.charge == 0) continue;
+        const float target_ne = eval_scalar_t<AXONLY>(sp.density, ctx, in.x, in.y, in.z) * (float)sp.charge;
+        const float ti = eval_scalar_t<AXONLY>(sp.temperature, ctx, in.x, in.y, in.z);
+        const DevPopRate& R = P[sidx];
+        float val;
+        if (R.is_const) val = exp10f(R.lconst);
+        else {
+            const float3 v = eval_vector(sp.velocity, ctx);
+            const float ivx = in.bvx - v.x, ivy = in.bvy - v.y, ivz = in.bvz - v.z;
+            const float energy = (ivx * ivx + ivy * ivy + ivz * ivz) * 5.18213506e-9f;
+            const float n_eq = density_sum / (float)sp.charge;
+            val = 0.f;
+            if (energy > 0.f && n_eq > 0.f && ti > 0.f) {
+                const float le = log10f(energy), ln = log10f(n_eq) + 19.0f, lt = log10f(ti);
+                // the oracle counts every axis that leaves its table
+                if (le < R.a.xmin || le > R.a.xmax) ood++;
+                if (ln < R.a.ymin || ln > R.a.ymax) ood++;
+                if (lt < R.tk.xmin || lt > R.tk.xmax) ood++;
+                const Cell2 c = locate2d(R.a, le, ln);
+                int ci; float ct;
+                locate1d(R.tk, lt, ci, ct);
+                val = exp10f(eval2d(R.a, c) + horner4(__ldg(R.tc + ci), ct));
+            }
+        }
+        pop = fmaf(target_ne, val, pop);
+        total_ne += target_ne;
+    }
+    return total_ne > 0.f ? pop / total_ne : 0.f;
+}
+
 // ExcitationLine / RecombinationLine .emission up to the add_line call (impact_excitation.pyx:86-100) plus the
 // component-independent part of LineShapeModel.add_line
 template <int AXONLY, int FEAT>
@@ -99,10 +163,11 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
         // BeamCXLine.emission (charge_exchange.pyx:117-167), ground-state donor: radiance = 1/(4 pi) n_beam n_rec q_eff
         if (!(in.donor > 0.f) || lc.ni == 0.f || lc.ts == 0.f) return;
         const DevModelExt& X = *M.ext;
-        float lq;                                             // log10(q_eff) + 38, then the linear factors
-        float factor = 1.0f;
-        if (X.cx_const) lq = X.cx_lconst;
-        else {
+        float args[5] = {0.f, lc.ts, 0.f, 0.f, 0.f};
+        float density_sum = 0.f;                              // sum Z^2 n over the plasma species (charge_exchange.pyx:266-268)
+        bool tabulated = false;
+        for (int k = 0; k < X.n_cx; k++) tabulated = tabulated || !X.cx[k].is_const;
+        if (tabulated || X.n_cx > 1) {
             const float3 vr = eval_vector(S.species[M.species].velocity, ctx);
             const float ivx = in.bvx - vr.x, ivy = in.bvy - vr.y, ivz = in.bvz - vr.z;
             const float energy = (ivx * ivx + ivy * ivy + ivz * ivz) * 5.18213506e-9f;    // m_u / (2 e): (m/s)^2 -> eV/amu
@@ -115,37 +180,41 @@ __device__ __forceinline__ void model_setup(const DevScene& S, const DevModel& M
                 snz = fmaf(n, zc, snz);
                 snz2 = fmaf(n * zc, zc, snz2);
             }
-            const float zeff = snz > 0.f ? snz2 / snz : 0.f;
-            need_b(S, in, ctx, lc, ood);
-            if (!(energy > 0.f)) return;
-            const float args[5] = {log10f(energy), lc.ts, n_ion, zeff, lc.bm};
-            lq = 0.f;
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                float v;
-                if (X.cx_n[k] == 1) v = X.cx_single[k];
-                else {
-                    // (a few fp32 ulps of slack: Zeff of a Z = 1 plasma must not count as below a table that starts at 1)
-                    if (args[k] < X.cx_t[k].xmin - 4e-6f * fabsf(X.cx_t[k].xmin) || args[k] > X.cx_t[k].xmax + 4e-6f * fabsf(X.cx_t[k].xmax)) ood++;
-                    int ci; float ct;
-                    locate1d(X.cx_t[k], args[k], ci, ct);
-                    v = horner4(__ldg(X.cx_c[k] + ci), ct);
-                }
-                if (k == 0) lq = v;
-                else {
-                    factor *= v;
-                    if (!(factor > 0.f)) return;              // the reference returns 0 as soon as a partial product is <= 0
-                }
-            }
+            density_sum = snz2;
+            if (tabulated) need_b(S, in, ctx, lc, ood);
+            args[0] = energy > 0.f ? log10f(energy) : -INFINITY;                           // -inf: the rate is zero (cx.pyx:118-119)
+            args[2] = n_ion;
+            args[3] = snz > 0.f ? snz2 / snz : 0.f;
+            args[4] = lc.bm;
         }
-        radiance = RECIP_4_PI * exp10f(lq) * factor * in.donor * lc.ni;
+        float rate = cx_rate_eval(X.cx[0], args, ood);                                   // W m^3 * 1e38
+        if (X.n_cx > 1) {
+            float total_population = 1.0f;
+            for (int k = 1; k < X.n_cx; k++) {
+                const float population = beam_population<AXONLY>(S, X.pop + (size_t)(k - 1) * S.n_species, in, ctx, density_sum, ood);
+                rate = fmaf(population, cx_rate_eval(X.cx[k], args, ood), rate);
+                total_population += population;
+            }
+            rate /= total_population;
+        }
+        radiance = RECIP_4_PI * rate * in.donor * lc.ni;
     } else if (FEAT && M.kind == CB2_MODEL_THERMAL_CX_LINE) {
-        // radiance = 1/(4 pi) n_receiver sum_donors n_donor q_donor(ne, te, T_donor)   (thermal_cx.pyx:103-111; constant q)
+        // radiance = 1/(4 pi) n_receiver sum_donors n_donor q_donor(ne, te, T_donor)   (thermal_cx.pyx:103-111)
         const DevModelExt& X = *M.ext;
         float weighted = 0.f;
         for (int k = 0; k < X.n_donors; k++) {
             const float nd = eval_scalar_t<AXONLY>(S.species[X.donor_species[k]].density, ctx, in.x, in.y, in.z);
-            weighted = fmaf(nd, exp10f(X.donor_lrate[k]), weighted);
+            float lq = X.donor_lrate[k];
+            if (X.donor_tab[k]) {
+                // ThermalCXPEC.evaluate (pec.pyx:186-194): zero for a non-positive donor temperature
+                const float td = eval_scalar_t<AXONLY>(S.species[X.donor_species[k]].temperature, ctx, in.x, in.y, in.z);
+                if (td > 0.f) {
+                    bool inside;
+                    lq = eval3d(X.donor_t3[k], lc.lne, lc.lte, log10f(td), inside);
+                    if (!inside && !X.donor_extrapolate[k]) ood++;
+                } else lq = -INFINITY;
+            }
+            weighted = fmaf(nd, exp10f(lq), weighted);
         }
         radiance = RECIP_4_PI * weighted * lc.ni;
     } else {

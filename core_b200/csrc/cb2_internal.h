@@ -32,6 +32,18 @@ struct DevTable2D {
     const float4* coef;     // [(nx-1)*(ny-1)*4]
 };
 
+struct DevTable3D {          // tricubic on (log10 ne, log10 te, log10 td): ThermalCXPEC (openadas/rates/pec.pyx:153-194)
+    int nx, ny, nz;
+    float xmin, xmax, ymin, ymax, zmin, zmax;
+    const float* x;          // knots
+    const float* y;
+    const float* z;
+    const float* inv_wx;     // reciprocal cell widths
+    const float* inv_wy;
+    const float* inv_wz;
+    const float4* coef;      // [(nx-1)(ny-1)(nz-1)][16]: entry 4p+q holds the powers of w multiplying t^p u^q
+};
+
 struct DevTable1D {          // knots shared, coefficients per quantity
     int n;
     int uniform;             // 1: uniform knots -> direct index, no dependent loads
@@ -96,19 +108,39 @@ struct DevComp {
     int type;         // 0 gaussian, 1 lorentzian
 };
 
+#define CB2_MAX_META 4
+// BeamCXPEC: rate = 10^c0(log10 E) c1(Ti) c2(n_ion) c3(Zeff) c4(|B|)   (openadas/rates/cx.pyx:104-142)
+struct DevCXRate {
+    int is_const;                          // 1: constant rate
+    float lconst;                          // log10(rate [W m^3]) + 38
+    int n[5];                              // knots per factor (1: constant factor `single`)
+    float single[5];
+    DevTable1D t[5];                       // knots: log10 E[eV/amu], Ti[eV], n_ion[1e19 m^-3], Zeff, |B|[T]
+    const float4* c[5];
+};
+// BeamPopulationRate: 10^(A(log10 E, log10 n_eq) + B(log10 T)), dimensionless   (openadas/rates/beam.pyx:105-189)
+struct DevPopRate {
+    int is_const;
+    float lconst;                          // log10(value), -inf for a null rate
+    DevTable2D a;                          // (log10 E[eV/amu], log10 n_eq[m^-3]) -> log10 sen
+    DevTable1D tk;                         // log10 T[eV] knots
+    const float4* tc;                      // -> log10(st / sref)
+};
+
 // ThermalCXLine donors / TotalRadiatedPower species and rates (device memory, referenced from DevModel::ext)
 struct DevModelExt {
     int n_donors;
     int donor_species[CB2_MAX_SPECIES];
     float donor_lrate[CB2_MAX_SPECIES];   // log10(rate [W m^3]) + 38, constant rates
+    int donor_tab[CB2_MAX_SPECIES];       // 1: tabulated rate in donor_t3 (log10 + 38), 0: constant
+    int donor_extrapolate[CB2_MAX_SPECIES];
+    DevTable3D donor_t3[CB2_MAX_SPECIES];
     int line_rad, recom, n_hyd, hyd[3];
-    // BEAM_CX_LINE (ground-state donor): rate = 10^c0(log10 E) c1(Ti) c2(n_ion) c3(Zeff) c4(|B|)   (openadas/rates/cx.pyx:104-142)
-    int cx_const;                          // 1: constant rate
-    float cx_lconst;                       // log10(rate [W m^3]) + 38
-    int cx_n[5];                           // knots per factor (1: constant factor cx_single)
-    float cx_single[5];
-    DevTable1D cx_t[5];                    // knots: log10 E[eV/amu], Ti[eV], n_ion[1e19 m^-3], Zeff, |B|[T]
-    const float4* cx_c[5];
+    // BEAM_CX_LINE: one effective emission coefficient per donor metastable, cx[0] the ground state, and the population of
+    // every excited metastable relative to the ground state for each plasma species (charge_exchange.pyx:204-292)
+    int n_cx;
+    DevCXRate cx[CB2_MAX_META];
+    const DevPopRate* pop;                 // [(n_cx - 1) * n_species]
     // BEAM_EMISSION_LINE: rate = sum_s (n_s Z_s) 10^(A_s(log10 E, log10 n_eq) + B_s(log10 T_s))   (beam_emission.pyx:131-176)
     int n_bes;
     int bes_species[CB2_MAX_SPECIES];

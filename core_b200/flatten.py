@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from .atomic import ConstantRate, RateTable
+from .atomic import ConstantRate, RateTable, RateTable3D
 from .models import Bremsstrahlung, ThermalCXLine, TotalRadiatedPower, _LineModel
 from .plasma import AxisymBlend, AxisymBlendVector, EFITMagneticField, _as_scalar_field, _as_vector_field
 
@@ -58,8 +58,20 @@ def _fill_rate3(r, rate, keep):
         r.n_ne = r.n_te = r.n_td = 0
         r.constant = rate.value
         r.extrapolate = 1
+    elif rate is None:                                   # NullThermalCXPEC (pec.pyx:197-205)
+        r.n_ne = r.n_te = r.n_td = 0
+        r.constant = 0.0
+        r.extrapolate = 1
+    elif isinstance(rate, RateTable3D):
+        r.n_ne, r.n_te, r.n_td = rate.ne.size, rate.te.size, rate.td.size
+        keep.extend([rate.ne, rate.te, rate.td, rate.rate])
+        r.ne = rate.ne.ctypes.data_as(_abi.c_double_p)
+        r.te = rate.te.ctypes.data_as(_abi.c_double_p)
+        r.td = rate.td.ctypes.data_as(_abi.c_double_p)
+        r.rate = rate.rate.ctypes.data_as(_abi.c_double_p)
+        r.extrapolate = 1 if rate.extrapolate else 0
     else:
-        raise TypeError("Unsupported thermal CX rate object %r (the B200 path accepts ConstantRate only)" % (rate,))
+        raise TypeError("Unsupported thermal CX rate object %r" % (rate,))
 
 
 def flatten_scene(plasma, min_wavelength, max_wavelength, bins, quad_rtol=1e-5, quad_min_order=1, quad_max_order=50,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 4
+#define CB2_ABI_VERSION 5
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -143,8 +143,8 @@ typedef struct cb2_rate2d {
 
 /* ThermalCXPEC data dict {'ne','te','td','rate'} (cherab/openadas/rates/pec.pyx:153-192): cubic in
  * (log10 ne, log10 te, log10 td).  n_ne == 0 -> constant rate in W m^3 (mock AtomicData of
- * core/tests/test_line_emission.py:58-84).  Tabulated 3-D rates are declared here but not yet accepted by the CUDA
- * library (CB2_ERR_NOT_IMPLEMENTED): only the constant form is. */
+ * core/tests/test_line_emission.py:58-84).  Tabulated rates need at least 2 knots per axis; outside the table the value is
+ * clamped to the edge ('nearest') and, when extrapolate == 0, the sample is counted in stats.out_of_domain. */
 typedef struct cb2_rate3d {
     int32_t       n_ne, n_te, n_td, _pad;
     const double* ne;
@@ -269,11 +269,15 @@ typedef struct cb2_model_ext {
     int32_t           n_hydrogen, has_plt, has_prb, has_prc;
     const int32_t*    hydrogen_species;  /* [n_hydrogen] */
     cb2_rate2d        plt, prb, prc;     /* W m^3 on (ne, te), log-log cubic (openadas/rates/radiated_power.pyx:48-76); NOT photon rates */
-    /* BEAM_CX_LINE: beam_cx_pec(beam.element, line.element, line.charge + 1, transition) — one rate per donor metastable
-     * (charge_exchange.pyx:311-349); only the ground state (n_cx == 1) is accepted so far, excited-state populations
-     * (BeamPopulationRate) return CB2_ERR_NOT_IMPLEMENTED */
+    /* BEAM_CX_LINE: beam_cx_pec(beam.element, line.element, line.charge + 1, transition) — one rate per donor metastable,
+     * cx[0] the ground state (metastable 1), cx[1..] the excited states (charge_exchange.pyx:311-349; at most 4 in all).
+     * cx_population[(k-1) * n_species + s] = beam_population_rate(beam.element, metastable of cx[k], species s): the
+     * BeamPopulationRate of every plasma species, composition order (same table shape as the stopping rate, dimensionless:
+     * openadas/rates/beam.pyx:105-189); NULL when n_cx == 1.  Neutral species are skipped in the population average (the
+     * reference divides by their zero charge there, charge_exchange.pyx:286). */
     int32_t            n_cx, _pad3;
     const cb2_cx_rate* cx;
+    const cb2_beam_rate* cx_population;
     /* BEAM_EMISSION_LINE: beam_emission_pec(beam.element, species.element, species.charge, transition) for every plasma
      * species (beam_emission.pyx:207-212; same table shape as the stopping rate, 'sen' in photon m^3 s^-1, a constant rate in
      * W m^3) and the constant MSE intensity ratios sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3 (beam_emission.pyx:47-50;
@@ -514,6 +518,9 @@ double cb2o_gauss_legendre(double (*fn)(double, void*), void* ctx, double a, dou
                            double rtol, int min_order, int max_order);                                   /* integrators1d.pyx:189-224 */
 double cb2o_gaunt_factor(const cb2_gaunt* g, double z, double te, double wavelength);                   /* gaunt.pyx:109-140 */
 double cb2o_pec_evaluate(const cb2_rate2d* pec, double wavelength, double ne, double te);               /* pec.pyx:70-77 */
+double cb2o_interp3d_cubic(const double* x, const double* y, const double* z, const double* f, int nx, int ny, int nz,
+                           double px, double py, double pz);                                             /* raysect Interpolator3DArray 'cubic' */
+double cb2o_thermal_cx_pec_evaluate(const cb2_rate3d* pec, double wavelength, double ne, double te, double td); /* pec.pyx:186-194 */
 
 #ifdef __cplusplus
 }

@@ -143,6 +143,72 @@ double cb2o_interp2d_cubic(const double* x, const double* y, const double* f, in
     return hermite(g[0], g[1], gx[0], gx[1], t);
 }
 
+/* third cross derivative at knot (i,j,k): eight-corner difference over the neighbouring knots that exist
+ * (the 3-D analogue of knot_cross_derivative; raysect _ArrayDerivative3D) */
+static double knot_cross3(const double* x, const double* y, const double* z, const double* f, int nx, int ny, int nz, int i, int j, int k) {
+    int il = i > 0 ? i - 1 : i, ih = i < nx - 1 ? i + 1 : i;
+    int jl = j > 0 ? j - 1 : j, jh = j < ny - 1 ? j + 1 : j;
+    int kl = k > 0 ? k - 1 : k, kh = k < nz - 1 ? k + 1 : k;
+    if (il == ih || jl == jh || kl == kh) return 0.0;
+#define F3(a, b, c) f[((size_t)(a) * ny + (b)) * nz + (c)]
+    double v = F3(ih, jh, kh) - F3(ih, jh, kl) - F3(ih, jl, kh) + F3(ih, jl, kl)
+             - F3(il, jh, kh) + F3(il, jh, kl) + F3(il, jl, kh) - F3(il, jl, kl);
+#undef F3
+    return v / ((x[ih] - x[il]) * (y[jh] - y[jl]) * (z[kh] - z[kl]));
+}
+
+/* four-corner cross difference of a strided 2-D slice: rows stride sa (n_a knots a), columns stride sb (n_b knots b) */
+static double knot_cross_strided(const double* a, const double* b, const double* f, int na, int nb, size_t sa, size_t sb, int i, int j) {
+    int il = i > 0 ? i - 1 : i, ih = i < na - 1 ? i + 1 : i;
+    int jl = j > 0 ? j - 1 : j, jh = j < nb - 1 ? j + 1 : j;
+    if (il == ih || jl == jh) return 0.0;
+    return (f[ih * sa + jh * sb] - f[ih * sa + jl * sb] - f[il * sa + jh * sb] + f[il * sa + jl * sb]) / ((a[ih] - a[il]) * (b[jh] - b[jl]));
+}
+
+/* Interpolator3DArray(x, y, z, f, 'cubic', ...): tricubic Hermite patch from f and its seven first/cross derivatives at
+ * the 8 cell corners, evaluated as nested 1-D Hermite cubics (z, then y, then x).  Out-of-range arguments are clamped
+ * ('nearest'); the caller counts the out-of-domain event when extrapolation is not permitted. */
+double cb2o_interp3d_cubic(const double* x, const double* y, const double* z, const double* f, int nx, int ny, int nz,
+                           double px, double py, double pz) {
+    if (px < x[0]) px = x[0];
+    if (px > x[nx - 1]) px = x[nx - 1];
+    if (py < y[0]) py = y[0];
+    if (py > y[ny - 1]) py = y[ny - 1];
+    if (pz < z[0]) pz = z[0];
+    if (pz > z[nz - 1]) pz = z[nz - 1];
+    int i = find_cell(x, nx, px), j = find_cell(y, ny, py), k = find_cell(z, nz, pz);
+    double hx = x[i + 1] - x[i], hy = y[j + 1] - y[j], hz = z[k + 1] - z[k];
+    double t = (px - x[i]) / hx, u = (py - y[j]) / hy, w = (pz - z[k]) / hz;
+    const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
+    double gx[2][2]; /* [value | d/dx * hx][x-knot] of the (y,z) patch */
+    for (int a = 0; a < 2; a++) {
+        int ia = i + a;
+        double gy[2][2][2]; /* [x-order][value | d/dy * hy][y-knot] after the z reduction */
+        for (int b = 0; b < 2; b++) {
+            int jb = j + b;
+            double q[2][2][2]; /* [x-order][y-order][z-knot] scaled derivative data, then their z-derivatives */
+            double qz[2][2][2];
+            for (int c = 0; c < 2; c++) {
+                int kc = k + c;
+                const double* f0 = f + (size_t)ia * sx + (size_t)jb * sy + kc;
+                q[0][0][c] = *f0;
+                q[1][0][c] = knot_derivative(x, f + (size_t)jb * sy + kc, nx, (int)sx, ia) * hx;
+                q[0][1][c] = knot_derivative(y, f + (size_t)ia * sx + kc, ny, (int)sy, jb) * hy;
+                q[1][1][c] = knot_cross_strided(x, y, f + kc, nx, ny, sx, sy, ia, jb) * hx * hy;
+                qz[0][0][c] = knot_derivative(z, f + (size_t)ia * sx + (size_t)jb * sy, nz, 1, kc) * hz;
+                qz[1][0][c] = knot_cross_strided(x, z, f + (size_t)jb * sy, nx, nz, sx, 1, ia, kc) * hx * hz;
+                qz[0][1][c] = knot_cross_strided(y, z, f + (size_t)ia * sx, ny, nz, sy, 1, jb, kc) * hy * hz;
+                qz[1][1][c] = knot_cross3(x, y, z, f, nx, ny, nz, ia, jb, kc) * hx * hy * hz;
+            }
+            for (int ox = 0; ox < 2; ox++)
+                for (int oy = 0; oy < 2; oy++)
+                    gy[ox][oy][b] = hermite(q[ox][oy][0], q[ox][oy][1], qz[ox][oy][0], qz[ox][oy][1], w);
+        }
+        for (int ox = 0; ox < 2; ox++) gx[ox][a] = hermite(gy[ox][0][0], gy[ox][0][1], gy[ox][1][0], gy[ox][1][1], u);
+    }
+    return hermite(gx[0][0], gx[0][1], gx[1][0], gx[1][1], t);
+}
+
 /* =================================================================================================
  * GaussianQuadrature (cherab/core/math/integrators/integrators1d.pyx:164-224)
  * ============================================================================================== */
@@ -319,6 +385,44 @@ static void power_table_build(pec_table* t, const cb2_rate2d* p) {
     for (int i = 0; i < p->n_ne; i++) t->lne[i] = log10(p->ne[i]);
     for (int j = 0; j < p->n_te; j++) t->lte[j] = log10(p->te[j]);
     for (int k = 0; k < p->n_ne * p->n_te; k++) t->lrate[k] = log10(p->rate[k]);
+}
+
+/* ThermalCXPEC (openadas/rates/pec.pyx:153-194): log10(PhotonToJ(rate)) on (log10 ne, log10 te, log10 td), tricubic */
+typedef struct tcx_table { int n_ne, n_te, n_td; double *lne, *lte, *ltd, *lrate; } tcx_table;
+
+static void tcx_table_build(tcx_table* t, const cb2_rate3d* p, double wavelength) {
+    memset(t, 0, sizeof *t);
+    if (p->n_ne <= 0) return;
+    t->n_ne = p->n_ne; t->n_te = p->n_te; t->n_td = p->n_td;
+    size_t n = (size_t)p->n_ne * p->n_te * p->n_td;
+    t->lne = (double*)malloc(sizeof(double) * p->n_ne);
+    t->lte = (double*)malloc(sizeof(double) * p->n_te);
+    t->ltd = (double*)malloc(sizeof(double) * p->n_td);
+    t->lrate = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < p->n_ne; i++) t->lne[i] = log10(p->ne[i]);
+    for (int j = 0; j < p->n_te; j++) t->lte[j] = log10(p->te[j]);
+    for (int k = 0; k < p->n_td; k++) t->ltd[k] = log10(p->td[k]);
+    double conv = PLANCK_CONSTANT * SPEED_OF_LIGHT * 1e9;
+    for (size_t k = 0; k < n; k++) t->lrate[k] = log10(p->rate[k] / wavelength * conv);
+}
+static void tcx_table_free(tcx_table* t) { free(t->lne); free(t->lte); free(t->ltd); free(t->lrate); }
+
+/* ThermalCXPEC.evaluate — pec.pyx:186-194 */
+static double tcx_eval(const tcx_table* t, const cb2_rate3d* p, double ne, double te, double td, int64_t* ood) {
+    if (p->n_ne <= 0) return p->constant;
+    if (ne <= 0 || te <= 0 || td <= 0) return 0.0;
+    double x = log10(ne), y = log10(te), z = log10(td);
+    if (!p->extrapolate && (x < t->lne[0] || x > t->lne[t->n_ne - 1] || y < t->lte[0] || y > t->lte[t->n_te - 1] ||
+                            z < t->ltd[0] || z > t->ltd[t->n_td - 1])) (*ood)++;
+    return pow(10.0, cb2o_interp3d_cubic(t->lne, t->lte, t->ltd, t->lrate, t->n_ne, t->n_te, t->n_td, x, y, z));
+}
+
+double cb2o_thermal_cx_pec_evaluate(const cb2_rate3d* pec, double wavelength, double ne, double te, double td) {
+    tcx_table t; int64_t ood = 0;
+    tcx_table_build(&t, pec, wavelength);
+    double v = tcx_eval(&t, pec, ne, te, td, &ood);
+    tcx_table_free(&t);
+    return v;
 }
 
 /* ImpactExcitationPEC.evaluate — pec.pyx:70-77 */
@@ -577,6 +681,7 @@ typedef struct {
     axisym_ctx ax; int has_ax;
     pec_table* pec;   /* [n_models] */
     pec_table* trp;   /* [n_models][3] TotalRadiatedPower plt, prb, prc */
+    struct tcx_table** tcx; /* [n_models] -> [n_donors] ThermalCXPEC log tables */
     gaunt_table gaunt;
     /* SingleRayAttenuator axis table (singleray.pyx:182-224): z_k = linspace(0, length, n_axis), density on the axis */
     int n_axis; double* axis_z; double* axis_density; double tanxdiv, tanydiv;
@@ -666,8 +771,13 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
         } else if (mo->kind == CB2_MODEL_THERMAL_CX_LINE) {
             if (mo->species < 0 || mo->species >= d->n_species || !mo->ext)
                 return fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified CX line");
-            for (int k = 0; k < mo->ext->n_donors; k++)
-                if (mo->ext->donor_rates[k].n_ne > 0) return fail(CB2_ERR_NOT_IMPLEMENTED, "tabulated thermal CX rates are not supported yet");
+            if (!s->tcx) s->tcx = (tcx_table**)calloc((size_t)d->n_models, sizeof(tcx_table*));
+            s->tcx[m] = (tcx_table*)calloc(mo->ext->n_donors > 0 ? mo->ext->n_donors : 1, sizeof(tcx_table));
+            for (int k = 0; k < mo->ext->n_donors; k++) {
+                const cb2_rate3d* r3 = &mo->ext->donor_rates[k];
+                if (r3->n_ne > 0 && (r3->n_ne < 2 || r3->n_te < 2 || r3->n_td < 2)) return fail(CB2_ERR_VALUE, "thermal CX rate tables need at least 2 knots per axis");
+                tcx_table_build(&s->tcx[m][k], r3, mo->wavelength);
+            }
         } else if (mo->kind == CB2_MODEL_TOTAL_RADIATED_POWER) {
             if (!mo->ext) return fail(CB2_ERR_RUNTIME, "TotalRadiatedPower needs its resolved species and rates");
             if (!s->trp) s->trp = (pec_table*)calloc(3 * (size_t)d->n_models, sizeof(pec_table));
@@ -678,7 +788,8 @@ static int scene_ctx_build(scene_ctx* s, const cb2_scene_desc* d) {
             if (!d->beam) return fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
             if (mo->species < 0 || mo->species >= d->n_species || !mo->ext || mo->ext->n_cx < 1)
                 return fail(CB2_ERR_RUNTIME, "The plasma object does not contain the ion species for the specified CX line");
-            if (mo->ext->n_cx > 1) return fail(CB2_ERR_NOT_IMPLEMENTED, "excited donor metastables are not supported yet");
+            if (mo->ext->n_cx > 4) return fail(CB2_ERR_VALUE, "at most four donor metastables are supported");
+            if (mo->ext->n_cx > 1 && !mo->ext->cx_population) return fail(CB2_ERR_RUNTIME, "excited donor metastables need their beam population rates");
         } else if (mo->kind == CB2_MODEL_BEAM_EMISSION_LINE) {
             if (!d->beam) return fail(CB2_ERR_RUNTIME, "The emission model is not connected to a beam object.");
             if (!mo->ext) return fail(CB2_ERR_RUNTIME, "BeamEmissionLine needs its resolved rates");
@@ -699,6 +810,11 @@ static void scene_ctx_free(scene_ctx* s) {
     if (s->has_ax) axisym_ctx_free(&s->ax);
     if (s->pec) { for (int m = 0; m < s->d->n_models; m++) pec_table_free(&s->pec[m]); free(s->pec); }
     if (s->trp) { for (int m = 0; m < 3 * s->d->n_models; m++) pec_table_free(&s->trp[m]); free(s->trp); }
+    if (s->tcx) {
+        for (int m = 0; m < s->d->n_models; m++)
+            if (s->tcx[m]) { for (int k = 0; k < s->d->models[m].ext->n_donors; k++) tcx_table_free(&s->tcx[m][k]); free(s->tcx[m]); }
+        free(s->tcx);
+    }
     gaunt_table_free(&s->gaunt);
     free(s->axis_z); free(s->axis_density);
 }
@@ -1104,7 +1220,7 @@ static void beam_emission_function(const scene_ctx* s, const double pb[3], const
         double iv[3] = {bdir[0] / bl * speed - vr[0], bdir[1] / bl * speed - vr[1], bdir[2] / bl * speed - vr[2]};
         double ispeed = sqrt(iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2]);
         double energy = ispeed * ispeed / EVAMU_TO_MS2;
-        /* _composite_cx_rate, ground state only (charge_exchange.pyx:204-236); Plasma.ion_density / z_effective (node.pyx:396-462) */
+        /* _composite_cx_rate (charge_exchange.pyx:204-236); Plasma.ion_density / z_effective (node.pyx:396-462) */
         double ion_density = 0, snz = 0, snz2 = 0;
         for (int i = 0; i < d->n_species; i++) {
             double n = eval_scalar(s, &d->species[i].density, p, &cn->ood);
@@ -1116,6 +1232,34 @@ static void beam_emission_function(const scene_ctx* s, const double pb[3], const
         eval_b_field(s, p, bf, &cn->ood);
         double bmag = sqrt(bf[0] * bf[0] + bf[1] * bf[1] + bf[2] * bf[2]);
         double rate = cx_rate_eval(&mo->ext->cx[0], mo->wavelength, energy, tr, ion_density, zeff, bmag, &cn->ood);
+        if (mo->ext->n_cx > 1) {
+            /* excited donor metastables weighted by their population relative to the ground state:
+             * _composite_cx_rate :215-234 and _beam_population :241-292 (species of charge 0 skipped) */
+            double bv[3] = {bdir[0] / bl * speed, bdir[1] / bl * speed, bdir[2] / bl * speed};
+            double density_sum = 0, total_population = 1;
+            for (int i = 0; i < d->n_species; i++)
+                density_sum += (double)d->species[i].charge * d->species[i].charge * eval_scalar(s, &d->species[i].density, p, &cn->ood);
+            for (int k = 1; k < mo->ext->n_cx; k++) {
+                double pop_coeff = 0, total_ne = 0;
+                for (int i = 0; i < d->n_species; i++) {
+                    const cb2_species* sp = &d->species[i];
+                    if (sp->charge == 0) continue;
+                    double target_ne = eval_scalar(s, &sp->density, p, &cn->ood) * sp->charge;
+                    double target_ti = eval_scalar(s, &sp->temperature, p, &cn->ood);
+                    double tv[3];
+                    eval_vector(s, &sp->velocity, p, tv, &cn->ood);
+                    double jv[3] = {bv[0] - tv[0], bv[1] - tv[1], bv[2] - tv[2]};
+                    double e_int = (jv[0] * jv[0] + jv[1] * jv[1] + jv[2] * jv[2]) / EVAMU_TO_MS2;
+                    pop_coeff += target_ne * beam_rate_eval(&mo->ext->cx_population[(size_t)(k - 1) * d->n_species + i], e_int,
+                                                            density_sum / sp->charge, target_ti, &cn->ood);
+                    total_ne += target_ne;
+                }
+                double population = total_ne > 0 ? pop_coeff / total_ne : 0.0;
+                rate += population * cx_rate_eval(&mo->ext->cx[k], mo->wavelength, energy, tr, ion_density, zeff, bmag, &cn->ood);
+                total_population += population;
+            }
+            rate /= total_population;
+        }
         add_shape(s, mo, RECIP_4_PI * donor * nr * rate, p, obs, samples, cn);
     }
 }
@@ -1168,8 +1312,8 @@ static void emission_function(const scene_ctx* s, const double p[3], const doubl
             double weighted = 0;
             for (int k = 0; k < x->n_donors; k++) {
                 double nd = eval_scalar(s, &d->species[x->donor_species[k]].density, p, &cn->ood);
-                (void)eval_scalar(s, &d->species[x->donor_species[k]].temperature, p, &cn->ood);   /* constant rates ignore it */
-                weighted += nd * x->donor_rates[k].constant;
+                double td = eval_scalar(s, &d->species[x->donor_species[k]].temperature, p, &cn->ood);
+                weighted += nd * tcx_eval(&s->tcx[m][k], &x->donor_rates[k], ne, te, td, &cn->ood);
             }
             add_shape(s, mo, RECIP_4_PI * weighted * nr, p, dir, samples, cn);
             continue;

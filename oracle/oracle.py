@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcb2_oracle.so")
 ORACLE_SYMBOLS = ["cb2o_abi_version", "cb2o_last_error", "cb2o_emission_render", "cb2o_sample_state", "cb2o_state_width", "cb2o_beam_sample",
                   "cb2o_rt_render_dense", "cb2o_add_gaussian_line", "cb2o_add_lorentzian_line", "cb2o_interp1d_cubic",
-                  "cb2o_interp2d_cubic", "cb2o_gauss_legendre", "cb2o_gaunt_factor", "cb2o_pec_evaluate"]
+                  "cb2o_interp2d_cubic", "cb2o_gauss_legendre", "cb2o_gaunt_factor", "cb2o_pec_evaluate", "cb2o_interp3d_cubic",
+                  "cb2o_thermal_cx_pec_evaluate"]
 _lib = None
 
 
@@ -53,6 +54,10 @@ def lib():
         l.cb2o_gaunt_factor.restype = C.c_double
         l.cb2o_pec_evaluate.argtypes = [C.POINTER(_abi.Rate2D), C.c_double, C.c_double, C.c_double]
         l.cb2o_pec_evaluate.restype = C.c_double
+        l.cb2o_interp3d_cubic.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        l.cb2o_interp3d_cubic.restype = C.c_double
+        l.cb2o_thermal_cx_pec_evaluate.argtypes = [C.POINTER(_abi.Rate3D), C.c_double, C.c_double, C.c_double, C.c_double]
+        l.cb2o_thermal_cx_pec_evaluate.restype = C.c_double
         for s in ORACLE_SYMBOLS:
             getattr(l, s)
         _lib = l
@@ -129,3 +134,8 @@ def interp1d_cubic(x, f, px):
 def interp2d_cubic(x, y, f, px, py):
     x, y, f = (np.ascontiguousarray(a, float) for a in (x, y, f))
     return lib().cb2o_interp2d_cubic(_dp(x), _dp(y), _dp(f), x.size, y.size, px, py, 1)
+
+
+def interp3d_cubic(x, y, z, f, px, py, pz):
+    x, y, z, f = (np.ascontiguousarray(a, float) for a in (x, y, z, f))
+    return lib().cb2o_interp3d_cubic(_dp(x), _dp(y), _dp(z), _dp(f), x.size, y.size, z.size, px, py, pz)

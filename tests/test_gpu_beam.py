@@ -122,3 +122,61 @@ def test_beam_cx_and_emission_generomak_tabulated_rates():
         ref, rst = oracle.emission_render(flat, rays)
         assert st["samples"] == rst["samples"] and ref.max() > 0
         assert parity(got, ref) <= 1.0, (lo, hi)
+
+
+def test_beam_cx_metastables_slab_and_generomak():
+    # excited donor metastables weighted by their beam populations (charge_exchange.pyx:204-292)
+    from test_oracle_beam import metastable_case
+    beam, flat, rays = metastable_case()
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"]
+    assert parity(got, ref) <= 1.0
+
+    class MetaADAS(cb.SyntheticADAS):
+        """ADF12-shaped tables for the donor ground state and n = 2, ADF22-shaped BeamPopulationRate tables per species."""
+
+        def wavelength(self, ion, charge, transition):
+            return 529.05
+
+        def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+            g = cb.SyntheticADAS.beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition)[0]
+            e = cb.BeamCXTable(2, g.eb, g.ti, g.ni, g.z, g.b, 30.0 * g.qeb * (g.eb / 4e4) ** -0.4, g.qti * 1.1, g.qni, g.qz * 0.9, g.qb, g.qref)
+            return [g, e]
+
+        def beam_population_rate(self, beam_ion, metastable, plasma_ion, charge):
+            if charge == 0:
+                return None
+            e, n, t = np.logspace(3.5, 5.5, 25), np.logspace(17.0, 21.5, 26), np.logspace(0.0, 4.5, 16)
+            sref = 4.0e-3
+            sen = sref * (1 + 0.03 * charge) * (e[:, None] / 4e4) ** 0.2 * (n[None, :] / 1e19) ** 0.1
+            st = sref * (1 + 0.04 * np.log10(t / 1e3))
+            return cb.BeamStoppingTable(e, n, t, sen, st, sref)
+
+    plasma = generomak.get_plasma()
+    atomic = MetaADAS()
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.look_at((3.2, -0.4, 0.0), (1.0, 0.3, 0.05)))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.05, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.0025, min_samples=10)
+    beam.models = [cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    flat = cb.flatten_beam_scene(beam, 526.0, 532.0, 256)
+    axis_pts = (np.asarray(beam.transform) @ np.stack([np.zeros(12), np.zeros(12), np.linspace(0.6, 2.4, 12), np.ones(12)]))[:3].T
+    origin = np.tile([[1.8, 0.2, 1.6]], (12, 1))
+    rays = cb.beam_ray_segments(beam, origin, axis_pts - origin)
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    ground_only = cb.SyntheticADAS()
+    ground_only.wavelength = atomic.wavelength
+    beam.atomic_data = plasma.atomic_data = ground_only
+    ref1, _ = oracle.emission_render(cb.flatten_beam_scene(beam, 526.0, 532.0, 256), rays)
+    assert st["samples"] == rst["samples"] and ref.max() > 0
+    assert np.abs(ref - ref1).max() > 1e-3 * ref.max()                    # the excited state does change the answer
+    assert parity(got, ref) <= 1.0

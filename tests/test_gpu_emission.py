@@ -426,3 +426,40 @@ def test_ragged_rays_and_batch_splitting(monkeypatch):
     assert np.all(one[nseg == 0] == 0.0)
     assert_parity(one, ref, what="ragged rays")
     assert_parity(acc, 3.0 * ref, what="ragged rays, accumulate over batches")
+
+
+def test_generomak_thermal_cx_tabulated_rates():
+    # ThermalCXPEC-shaped (ne, te, td) tables (openadas/rates/pec.pyx:153-194) on the blended Generomak profiles: every
+    # species that still carries an electron donates to C6+ -> C5+ (thermal_cx.pyx:140-148)
+    plasma = generomak.get_plasma()
+    atomic = cb.SyntheticADAS()
+    balmer = atomic.wavelength
+    atomic.wavelength = lambda ion, charge, transition: 529.05 if ion is cb.carbon else balmer(ion, charge, transition)
+    plasma.atomic_data = atomic
+    plasma.models = [cb.ThermalCXLine(cb.Line(cb.carbon, 5, (8, 7))), cb.ExcitationLine(cb.Line(cb.hydrogen, 0, (3, 2)))]
+    plasma.integrator = cb.NumericalIntegrator(step=0.01)
+    rays = generomak_camera_rays(plasma, (4, 4))
+    for lo, hi, bins in ((527.0, 531.0, 256), (520.0, 660.0, 700)):
+        flat = cb.flatten_scene(plasma, lo, hi, bins)
+        got, ref, stats, rstats = both(flat, rays)
+        assert stats["samples"] == rstats["samples"] and ref.max() > 0
+        assert stats["out_of_domain"] == rstats["out_of_domain"] == 0
+        assert_parity(got, ref, what="generomak tabulated thermal CX")
+
+
+def test_thermal_cx_table_out_of_domain_is_counted():
+    # a table that stops short of the plasma's donor temperatures and does not permit extrapolation: the reference raises
+    # ValueError from the interpolator; here the value is clamped to the edge and the sample counted on both paths
+    class NarrowADAS(cb.SyntheticADAS):
+        def wavelength(self, ion, charge, transition):
+            return 529.27
+
+        def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+            r = cb.SyntheticADAS.thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition)
+            return cb.RateTable3D(r.ne, r.te, r.td[:5], r.rate[:, :, :5], extrapolate=False)
+
+    from test_oracle_models import thermal_cx_scene
+    flat, rays, _ = thermal_cx_scene(atomic=NarrowADAS())
+    got, ref, stats, rstats = both(flat, rays)
+    assert rstats["out_of_domain"] > 0 and stats["out_of_domain"] == rstats["out_of_domain"]
+    assert_parity(got, ref, what="clamped thermal CX table")

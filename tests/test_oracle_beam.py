@@ -156,3 +156,36 @@ def test_beam_emission_multiplet():
     sigma_b = 0.1
     expected = 0.25 / np.pi * (1e18 + 1e17) * 2.0e-35 * dens[0] * np.sqrt(2 * np.pi) * sigma_b   # chord through the axis of the round Gaussian beam
     assert abs(total / expected - 1) < 2e-3           # trapezium sum of a Gaussian over a chord clipped at 5 sigma
+
+
+# ---- excited donor metastables: _composite_cx_rate / _beam_population (charge_exchange.pyx:204-292) ----
+class MetastableMockData(BeamMockData):
+    """Ground-state rate q1, one excited metastable with rate q2 and a constant relative population k."""
+    q2, k = 9.0e-34, 0.25
+
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        return [cb.ConstantBeamCXPEC(2, self.q2), cb.ConstantBeamCXPEC(1, self.cx)]      # any order: the ground state is found by its label
+
+    def beam_population_rate(self, beam_ion, metastable, plasma_ion, charge):
+        assert metastable == 2
+        return cb.ConstantRate(self.k)
+
+
+def metastable_case():
+    line = cb.Line(cb.deuterium, 0, (3, 2))
+    plasma, beam = beam_scene(0.0, temperature=200.0, models=[cb.BeamCXLine(line)])
+    atomic = MetastableMockData(0.0)
+    plasma.atomic_data = beam.atomic_data = atomic
+    flat = cb.flatten_beam_scene(beam, 655.1, 657.1, 512)
+    rays = cb.beam_ray_segments(beam, [[1.5, 0, 0]], [[-1.0, 0, 0]])
+    return beam, flat, rays
+
+
+def test_beam_cx_line_population_weighted_metastables():
+    beam, flat, rays = metastable_case()
+    got, stats = oracle.emission_render(flat, rays)
+    _, flat1, _ = cx_case()[1:]
+    ground, _ = oracle.emission_render(flat1, rays)                       # the same scene with the ground state alone (q1)
+    q1, q2, k = 3.4e-34, MetastableMockData.q2, MetastableMockData.k
+    composite = (q1 + k * q2) / (1 + k)                                   # charge_exchange.pyx:178
+    assert np.max(np.abs(got[0] - ground[0] * composite / q1)) <= 1e-12 * got.max()

@@ -198,12 +198,12 @@ class _PowerAtomicData(cb.AtomicData):
         return cb.ConstantRate(1.e-31)
 
 
-def thermal_cx_scene():
+def thermal_cx_scene(atomic=None):
     # core/tests/test_line_emission.py:241-290
     plasma = build_constant_slab_plasma(length=1.2, width=1, height=1, electron_density=1e19, electron_temperature=1000.,
                                         plasma_species=[(cb.carbon, 6, 1.67e18, 800., (0, 0, 0)), (cb.deuterium, 0, 1.e19, 100., (0, 0, 0))],
                                         b_field=(0, 10., 0))
-    plasma.atomic_data = _PowerAtomicData()
+    plasma.atomic_data = atomic if atomic is not None else _PowerAtomicData()
     line = cb.Line(cb.carbon, 5, (8, 7))
     plasma.models = [cb.ThermalCXLine(line)]
     flat = cb.flatten_scene(plasma, 529.27 - 1.5, 529.27 + 1.5, 512)
@@ -243,3 +243,47 @@ def test_total_radiated_power_slab():
 def test_total_radiated_power_rejects_bare_nucleus():
     with pytest.raises(ValueError):
         cb.TotalRadiatedPower(cb.nitrogen, 7)
+
+
+# ---- tabulated thermal-CX rates: Interpolator3DArray 'cubic' restated + ThermalCXPEC (openadas/rates/pec.pyx:153-194) ----
+def test_tricubic_reproduces_quadratics_and_reduces_to_the_bicubic():
+    rng = np.random.default_rng(0)
+    x, y, z = np.sort(rng.uniform(0, 3, 7)), np.sort(rng.uniform(-1, 2, 6)), np.sort(rng.uniform(0, 1, 8))
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+
+    def fn(a, b, c):
+        return 1 + 2 * a - b + 0.5 * c + a * b - 2 * b * c + a * c + a * a + 0.3 * b * b - c * c + 0.7 * a * b * c
+    f = fn(X, Y, Z)
+    for _ in range(100):        # interior cells: the 3-point knot derivatives are exact for quadratics there
+        p = rng.uniform(x[1], x[-2]), rng.uniform(y[1], y[-2]), rng.uniform(z[1], z[-2])
+        assert abs(oracle.interp3d_cubic(x, y, z, f, *p) - fn(*p)) < 1e-12
+    for i, j, k in ((0, 0, 0), (6, 5, 7), (3, 2, 4)):       # knots are reproduced
+        assert abs(oracle.interp3d_cubic(x, y, z, f, x[i], y[j], z[k]) - f[i, j, k]) < 1e-13
+    f2 = np.sin(X[:, :, 0]) + Y[:, :, 0] ** 2
+    f3 = np.repeat(f2[:, :, None], z.size, axis=2)
+    for _ in range(50):         # no dependence on the third axis -> the 2-D interpolator
+        p = rng.uniform(x[0], x[-1]), rng.uniform(y[0], y[-1]), rng.uniform(z[0], z[-1])
+        assert abs(oracle.interp3d_cubic(x, y, z, f3, *p) - oracle.interp2d_cubic(x, y, f2, p[0], p[1])) < 1e-13
+    assert oracle.interp3d_cubic(x, y, z, f, x[0] - 5, y[2], z[3]) == oracle.interp3d_cubic(x, y, z, f, x[0], y[2], z[3])   # 'nearest'
+
+
+class _PowerLawCX(_PowerAtomicData):
+    """thermal CX rate = A ne^a te^b td^c photon m^3/s: linear in log space, so the tricubic is exact everywhere."""
+    A, a, b, c = 3.0e-15, 0.1, -0.3, 0.45
+
+    def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+        ne, te, td = np.logspace(17, 21, 9), np.logspace(0, 4, 11), np.logspace(-1, 3.5, 8)
+        rate = self.A * ne[:, None, None] ** self.a * te[None, :, None] ** self.b * td[None, None, :] ** self.c
+        return cb.RateTable3D(ne, te, td, rate, extrapolate=False)
+
+
+def test_thermal_cx_line_slab_with_a_tabulated_rate():
+    flat, rays, _ = thermal_cx_scene(atomic=_PowerLawCX())
+    got, st = oracle.emission_render(flat, rays)
+    q = _PowerLawCX.A * 1e19 ** _PowerLawCX.a * 1000. ** _PowerLawCX.b * 100. ** _PowerLawCX.c       # ne, te, T(D0) of the slab
+    q *= const.h * const.c / (529.27e-9)                                                          # PhotonToJ, conversion.py:44-52
+    radiance = 0.25 / np.pi * q * 1.67e18 * 1e19 * 1.2
+    sigma = np.sqrt(800. * const.e / (cb.carbon.atomic_weight * const.physical_constants["atomic mass constant"][0])) * 529.27 / const.c
+    ref = oracle.add_gaussian_line(radiance, 529.27, sigma, 529.27 - 1.5, 529.27 + 1.5, 512)
+    assert st["out_of_domain"] == 0
+    assert np.max(np.abs(got[0] - ref)) <= 1e-9 * ref.max()
