@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -164,6 +164,19 @@ def workload_config(args, world):
             "pixels": [args.pixels, args.pixels], "bins": args.bins, "models": 9, "tiles": "16x16 px round-robin over %d rank(s)" % world,
             "l2": "the %0.1f GB fp32 frame written per step exceeds L2; scene tables (few MB) are L2-resident by design"
                   % (args.pixels * args.pixels * args.bins * 4 / 1e9)}
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The result line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -178,6 +191,13 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner at the first
+    # communicator): point file descriptor 1 at stderr for the whole run and keep the real stdout for the result line.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -401,7 +421,7 @@ def main():
                 "out_of_domain_samples": ood, "plan": plan}
         if e2e:
             line["e2e"] = e2e
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
