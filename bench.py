@@ -166,6 +166,49 @@ def workload_config(args, world):
                   % (args.pixels * args.pixels * args.bins * 4 / 1e9)}
 
 
+def shared_host_rows(rows_total, bins, row0, rows, rank, dist, torch):
+    """This rank's rows [row0, row0 + rows) of a [rows_total, bins] fp32 frame in shared host memory, page-locked for the D2H copies.
+    Falls back to a rank-local pinned buffer when /dev/shm cannot hold the frame.  Returns (numpy view, description)."""
+    import mmap
+    path = "/dev/shm/cb2_frame_%s" % os.environ.get("MASTER_PORT", "0")
+    nbytes = rows_total * bins * 4
+    ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+    view = None
+    if rank == 0:
+        try:
+            fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
+            os.posix_fallocate(fd, 0, nbytes)             # fails here, not at the first touch, if /dev/shm is too small
+            os.close(fd)
+        except OSError:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+    dist.barrier()
+    try:
+        fd = os.open(path, os.O_RDWR)
+        mm = mmap.mmap(fd, nbytes)
+        os.close(fd)
+        frame = np.frombuffer(mm, dtype=np.float32).reshape(rows_total, bins)
+        view = frame[row0:row0 + rows]
+        rc = torch.cuda.cudart().cudaHostRegister(view.ctypes.data, view.nbytes, 0)
+        if int(getattr(rc, "value", rc)) != 0:
+            view = None
+    except Exception:
+        view = None
+    ok[0] = 1 if view is not None else 0
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        try:
+            os.unlink(path)                               # the mappings keep the memory alive; nothing is left behind
+        except OSError:
+            pass
+    if int(ok.item()) == 1:
+        return view, "shared host memory (/dev/shm), every rank reads its rows back over its own PCIe link"
+    return (torch.empty((rows, bins), dtype=torch.float32, pin_memory=True).numpy(),
+            "rank-local pinned host buffers (no /dev/shm room for the frame), every rank reads its rows back over its own PCIe link")
+
+
 _RESULT_FD = None
 
 
@@ -190,6 +233,9 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=8)
     ap.add_argument("--cpu-rays", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frame", default="host", choices=["host", "gather"],
+                    help="N > 1 end-to-end path: every rank reads its shard back into the frame in shared host memory (default), "
+                         "or the frame is gathered on rank 0's GPU with NCCL and read back over rank 0's PCIe link")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner at the first
@@ -285,7 +331,18 @@ def main():
             host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
             scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
         n_chunks = 8
-        if world > 1:
+        gather = world > 1 and args.frame == "gather"
+        frame_kind = "rank-0 pinned buffer" if world == 1 else "NCCL gather to rank 0, then D2H"
+        if world > 1 and not gather:
+            # The path shards by pixel tiles and has no exchange step: every rank renders its tiles through the same host-buffer call
+            # as at N = 1 and reads them back over ITS OWN PCIe link into its rows of one frame in shared host memory
+            # (rank-major row blocks; /dev/shm file mapped by every rank, the rank's rows page-locked).  No device collective.
+            counts = [rank_pixels(args.pixels, r, world).size for r in range(world)]
+            row0 = sum(counts[:rank])
+            host_frame, frame_kind = shared_host_rows(sum(counts), args.bins, row0, counts[rank], rank, dist, torch)
+            scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
+            dist.barrier()
+        if gather:
             # NCCL only gathers the frame.  The rank's rays are cut into chunks: while chunk c+1 renders, chunk c is gathered
             # into one device buffer on rank 0 (NCCL stream) and read back into pinned host memory (copy stream), so the
             # single PCIe link of rank 0 works in the shadow of the compute.
@@ -308,7 +365,7 @@ def main():
         t0 = time.perf_counter()
         e2e_samples = 0
         for k in range(e2e_steps):
-            if world == 1:
+            if not gather:
                 r = host_rays[(args.warmup + k) % len(host_rays)]
                 _, s = scene.render(r, out=host_frame)
                 e2e_samples += s["samples"]
@@ -338,11 +395,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
             e2e_samples = samples * e2e_steps // max(args.steps, 1)
+            h2d_all = torch.tensor([sum(a.nbytes for a in (host_rays[0].origin, host_rays[0].direction, host_rays[0].seg_offset,
+                                                              host_rays[0].seg_t0, host_rays[0].seg_t1))], dtype=torch.float64, device=dev)
+            dist.all_reduce(h2d_all)
         h2d = sum(host_rays[(args.warmup + k) % len(host_rays)].origin.nbytes * 2 + host_rays[(args.warmup + k) % len(host_rays)].seg_offset.nbytes
                   + host_rays[(args.warmup + k) % len(host_rays)].seg_t0.nbytes * 2 for k in range(e2e_steps)) // max(e2e_steps, 1)
+        if world > 1:
+            h2d = int(h2d_all.item())                     # all ranks' ray shards
+        d2h_rows = n_chunks * world * cmax if gather else args.pixels * args.pixels
         e2e = {"value": e2e_samples / dt * 1e-6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int((pix.size if world == 1 else n_chunks * world * cmax) * args.bins * 4 + 48), "steps": e2e_steps,
-               "ms_per_step": dt / e2e_steps * 1e3}
+               "d2h_bytes_per_step": int(d2h_rows * args.bins * 4 + 48 * world), "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3, "frame": frame_kind}
 
     if rank == 0:
         fixed = fixed_flops_per_sample(flat)
