@@ -138,6 +138,17 @@ class RTDesc(C.Structure):
                 ("world_to_local", C.c_double * 12), ("voxel_map", c_int32_p), ("bins", C.c_int32), ("_pad", C.c_int32)]
 
 
+class PrimitiveDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("p", C.c_double * 6), ("world_to_local", C.c_double * 12)]
+
+
+class PinholeDesc(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("width", C.c_double), ("to_world", C.c_double * 12)]
+
+
+PRIM_HOLLOW_CYLINDER, PRIM_SPHERE, PRIM_BOX = range(3)
+
+
 class SartDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("value_f64", C.c_int32), ("n_detectors", C.c_int64), ("n_sources", C.c_int64),
                 ("dense", C.c_void_p), ("dense_f64", C.c_int32), ("memory", C.c_int32),
@@ -150,6 +161,7 @@ PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
     "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
+    "cb2_pinhole_rays_device",
     "cb2_sart_create", "cb2_sart_destroy", "cb2_sart_set_laplacian", "cb2_sart_solve", "cb2_sart_info",
 ]
 
@@ -187,6 +199,8 @@ def load_library():
     lib.cb2_rt_render_dense.argtypes = [vp, C.POINTER(Rays), c_double_p, C.c_int, C.POINTER(Stats)]
     lib.cb2_rt_render_csr.argtypes = [vp, C.POINTER(Rays), c_int64_p, c_int32_p, c_double_p, C.c_int64, C.POINTER(Stats)]
     lib.cb2_rt_render_csr_device.argtypes = [vp, C.POINTER(Rays), vp, vp, vp, C.c_int64, c_int64_p, vp, vp]
+    lib.cb2_pinhole_rays_device.argtypes = [C.POINTER(PinholeDesc), C.POINTER(PrimitiveDesc), vp, C.c_int64, C.c_double, C.c_double,
+                                            C.POINTER(Rays), vp]
     lib.cb2_sart_create.argtypes = [C.POINTER(SartDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_sart_destroy.argtypes = [vp]
     lib.cb2_sart_set_laplacian.argtypes = [vp, vp, vp, vp, vp]

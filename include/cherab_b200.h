@@ -444,6 +444,38 @@ int cb2_rt_render_csr_device(cb2_rt_scene* scene, const cb2_rays* rays, int64_t*
                              cb2_stats* stats_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Observer front-end on the device: the rays of a pinhole camera and their chords through the primitive that
+ * bounds the plasma / beam / ray-transfer grid, generated straight into DEVICE memory in the cb2_rays layout.  Replaces the
+ * per-pixel Python loop of raysect's PinholeCamera / Observer2D.observe() [raysect, SURVEY Appendix B.9] in front of
+ * cb2_emission_render_device and cb2_rt_render_csr_device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cb2_primitive_kind {
+    CB2_PRIM_HOLLOW_CYLINDER = 0,   /* Subtract(Cylinder(r_outer), Cylinder(r_inner)): p = r_inner (0: solid), r_outer, z_min, z_max
+                                       (generomak/plasma/plasma.py:673-681, raytransfer.py:198) */
+    CB2_PRIM_SPHERE = 1,            /* p = radius */
+    CB2_PRIM_BOX = 2                /* p = lower x, y, z, upper x, y, z (tools/plasmas/slab.pyx:255, raytransfer.py:266) */
+} cb2_primitive_kind;
+
+typedef struct cb2_primitive {
+    int32_t kind, _pad;
+    double  p[6];
+    double  world_to_local[12];     /* row-major 3x4 affine: world -> primitive-local */
+} cb2_primitive;
+
+typedef struct cb2_pinhole {
+    int32_t nx, ny;                 /* pixels; pixel p = ix * ny + iy */
+    double  width;                  /* image-plane width at unit distance: 2 tan(fov / 2) */
+    double  to_world[12];           /* row-major 3x4 affine: camera space (looking along +z) -> world */
+} cb2_pinhole;
+
+/* One ray per listed pixel (pixel_index_dev: DEVICE int64[n], or NULL for all nx * ny pixels in order) through the
+ * sub-pixel position (sub_x, sub_y) in [0, 1)^2 (0.5 = pixel centre).  out_dev: caller-allocated DEVICE arrays
+ * origin[n][3], direction[n][3], seg_offset[n+1], seg_t0[2n], seg_t1[2n]; n_rays and n_segments are filled in (one stream
+ * synchronisation for the segment total). */
+int cb2_pinhole_rays_device(const cb2_pinhole* camera, const cb2_primitive* primitive, const int64_t* pixel_index_dev, int64_t n,
+                            double sub_x, double sub_y, cb2_rays* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SART inversion on the device-resident geometry matrix (replaces
  * cherab/tools/inversions/sart.pyx:26-155 invert_sart, :161-302 invert_constrained_sart and the OpenCL solver
  * cherab/tools/inversions/opencl/sart_opencl.py:33-318 + sart_kernels.cl:28-148).

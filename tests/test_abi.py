@@ -40,7 +40,7 @@ def test_struct_sizes_match_header():
     structs = {"cb2_spectral_grid": _abi.SpectralGrid, "cb2_scalar_field": _abi.ScalarField, "cb2_vector_field": _abi.VectorField,
                "cb2_equilibrium": _abi.Equilibrium, "cb2_axisym": _abi.Axisym, "cb2_species": _abi.SpeciesDesc,
                "cb2_rate2d": _abi.Rate2D, "cb2_rate3d": _abi.Rate3D, "cb2_model_ext": _abi.ModelExt, "cb2_beam_rate": _abi.BeamRate, "cb2_cx_rate": _abi.CXRate, "cb2_beam_desc": _abi.BeamDesc, "cb2_gaunt": _abi.Gaunt, "cb2_lineshape": _abi.LineShape, "cb2_model": _abi.ModelDesc,
-               "cb2_scene_desc": _abi.SceneDesc, "cb2_rays": _abi.Rays, "cb2_stats": _abi.Stats, "cb2_rt_desc": _abi.RTDesc, "cb2_sart_desc": _abi.SartDesc}
+               "cb2_scene_desc": _abi.SceneDesc, "cb2_rays": _abi.Rays, "cb2_stats": _abi.Stats, "cb2_rt_desc": _abi.RTDesc, "cb2_sart_desc": _abi.SartDesc, "cb2_primitive": _abi.PrimitiveDesc, "cb2_pinhole": _abi.PinholeDesc}
     src = '#include <stdio.h>\n#include "cherab_b200.h"\nint main(){' + "".join(
         'printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in structs) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
