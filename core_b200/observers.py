@@ -126,3 +126,177 @@ def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None):
         rays = pinhole.rays(sx, sy, out=buf)
         scene.render_device(rays, frame, scale=1.0 / len(offsets), accumulate=True)
     return frame
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 0-D observers and their groups (cherab/tools/observers/group/{base,fibreoptic,sightline}.py)
+# ------------------------------------------------------------------------------------------------------------------
+class SightLine:
+    """raysect SightLine: one ray from the observer's origin along its +z axis; ``sensitivity`` scales power pipelines
+    (cherab/tools/observers/group/sightline.py:73-95)."""
+
+    def __init__(self, transform=None, name="", sensitivity=1.0):
+        self.transform = np.eye(4) if transform is None else np.asarray(transform, dtype=np.float64)
+        self.name, self.sensitivity = name, float(sensitivity)
+        self.spectrum = None
+
+    def rays(self):
+        m = self.transform
+        return m[:3, 3][None, :].copy(), m[:3, 2][None, :].copy(), np.ones(1)
+
+
+class FibreOptic:
+    """raysect FibreOptic: rays start on the fibre tip (disc of ``radius``) and leave within ``acceptance_angle`` degrees of the
+    +z axis.  raysect draws both at random; here the ``pixel_samples`` rays are deterministic (sunflower points on the disc,
+    Fibonacci points uniform in solid angle on the cone cap — SURVEY 8(d) C5), each weighted by cos(theta), the projected
+    tip area it sees, so the weighted mean is the etendue-averaged spectral radiance."""
+
+    def __init__(self, transform=None, name="", acceptance_angle=5.0, radius=0.001, pixel_samples=64):
+        self.transform = np.eye(4) if transform is None else np.asarray(transform, dtype=np.float64)
+        self.name = name
+        self.acceptance_angle, self.radius, self.pixel_samples = float(acceptance_angle), float(radius), int(pixel_samples)
+        self.spectrum = None
+
+    @property
+    def solid_angle(self):
+        return 2.0 * np.pi * (1.0 - np.cos(np.deg2rad(self.acceptance_angle)))
+
+    @property
+    def collection_area(self):
+        return np.pi * self.radius ** 2
+
+    def rays(self):
+        if not 0.0 < self.acceptance_angle <= 90.0:
+            raise ValueError("Acceptance angle must be in the range (0, 90] degrees.")
+        if self.radius <= 0 or self.pixel_samples < 1:
+            raise ValueError("The fibre radius and the number of pixel samples must be positive.")
+        n = self.pixel_samples
+        k = np.arange(n) + 0.5
+        golden = np.pi * (3.0 - np.sqrt(5.0))
+        cos_max = np.cos(np.deg2rad(self.acceptance_angle))
+        cos_t = 1.0 - (1.0 - cos_max) * k / n                   # uniform in solid angle on the cap
+        sin_t = np.sqrt(np.maximum(0.0, 1.0 - cos_t * cos_t))
+        phi = golden * k
+        dl = np.stack([sin_t * np.cos(phi), sin_t * np.sin(phi), cos_t], axis=1)
+        rr = self.radius * np.sqrt(k / n)                       # uniform in area on the disc, decorrelated from the directions
+        psi = golden * k * 7.0 + 1.0
+        ol = np.stack([rr * np.cos(psi), rr * np.sin(psi), np.zeros(n)], axis=1)
+        m = self.transform
+        return ol @ m[:3, :3].T + m[:3, 3], dl @ m[:3, :3].T, cos_t
+
+
+class _Observer0DGroup:
+    """Observer0DGroup (group/base.py:60-436): a set of 0-D observers rendered together.  ``observe`` clips every observer's rays
+    against the bounding primitive, renders ALL of them in one device call and reduces them per observer (weighted mean spectral
+    radiance -> ``observer.spectrum`` and ``self.spectra[i]``)."""
+    _OBSERVER_TYPE = object
+
+    def __init__(self, observers=(), name="", transform=None):
+        self.name = name
+        self.transform = np.eye(4) if transform is None else np.asarray(transform, dtype=np.float64)
+        self._observers = ()
+        self.spectra = None
+        for o in observers:
+            self.add_observer(o)
+
+    @property
+    def observers(self):
+        return self._observers
+
+    def add_observer(self, observer):
+        if not isinstance(observer, self._OBSERVER_TYPE):
+            raise ValueError("Can only add {} objects".format(self._OBSERVER_TYPE))
+        self._observers = self._observers + (observer,)
+
+    @property
+    def names(self):
+        return [o.name for o in self._observers]
+
+    @names.setter
+    def names(self, value):
+        if not isinstance(value, (list, tuple)):
+            raise TypeError("The names attribute must be a list or tuple.")
+        if len(value) != len(self._observers):
+            raise ValueError("The length of 'names' ({}) mismatches the number of observers ({}).".format(len(value), len(self._observers)))
+        for o, v in zip(self._observers, value):
+            o.name = v
+
+    def _broadcast(self, attr, value):
+        if isinstance(value, (list, tuple, np.ndarray)):
+            if len(value) != len(self._observers):
+                raise ValueError("The length of '{}' ({}) mismatches the number of observers ({}).".format(attr, len(value), len(self._observers)))
+            for o, v in zip(self._observers, value):
+                setattr(o, attr, v)
+        else:
+            for o in self._observers:
+                setattr(o, attr, value)
+
+    def gather_rays(self):
+        """(origins, directions, weights, owner index) of every observer's rays, in world space."""
+        os_, ds_, ws_, owner = [], [], [], []
+        g = self.transform
+        for i, ob in enumerate(self._observers):
+            o, d, w = ob.rays()
+            os_.append(o @ g[:3, :3].T + g[:3, 3])
+            ds_.append(d @ g[:3, :3].T)
+            ws_.append(w)
+            owner.append(np.full(o.shape[0], i))
+        return np.concatenate(os_), np.concatenate(ds_), np.concatenate(ws_), np.concatenate(owner)
+
+    def observe(self, scene, primitive, to_world=None):
+        """One device render for the whole group.  ``scene``: engine.EmissionScene / PlasmaRenderer.  Returns spectra[n_observers, bins]."""
+        from .geometry import ray_segments
+        if not self._observers:
+            raise ValueError("The group has no observers.")
+        o, d, w, owner = self.gather_rays()
+        rays = ray_segments(primitive, o, d, to_world)
+        per_ray, _ = scene.render(rays)
+        n = len(self._observers)
+        num = np.zeros((n, per_ray.shape[1]))
+        den = np.zeros(n)
+        np.add.at(num, owner, per_ray * w[:, None])
+        np.add.at(den, owner, w)
+        self.spectra = num / den[:, None]
+        for ob, s in zip(self._observers, self.spectra):
+            ob.spectrum = s
+        return self.spectra
+
+
+class SightLineGroup(_Observer0DGroup):
+    _OBSERVER_TYPE = SightLine
+
+    @property
+    def sensitivity(self):
+        return [o.sensitivity for o in self._observers]
+
+    @sensitivity.setter
+    def sensitivity(self, value):
+        self._broadcast("sensitivity", value)
+
+
+class FibreOpticGroup(_Observer0DGroup):
+    _OBSERVER_TYPE = FibreOptic
+
+    @property
+    def acceptance_angle(self):
+        return [o.acceptance_angle for o in self._observers]
+
+    @acceptance_angle.setter
+    def acceptance_angle(self, value):
+        self._broadcast("acceptance_angle", value)
+
+    @property
+    def radius(self):
+        return [o.radius for o in self._observers]
+
+    @radius.setter
+    def radius(self, value):
+        self._broadcast("radius", value)
+
+    @property
+    def pixel_samples(self):
+        return [o.pixel_samples for o in self._observers]
+
+    @pixel_samples.setter
+    def pixel_samples(self, value):
+        self._broadcast("pixel_samples", value)

@@ -82,3 +82,29 @@ def test_device_rays_feed_the_ray_transfer_kernel():
     scene.close()
     assert np.array_equal(ro.cpu().numpy(), h_ro) and np.array_equal(co.cpu().numpy(), h_co)
     np.testing.assert_allclose(le.cpu().numpy(), h_le, rtol=1e-9)
+
+
+def test_fibre_group_observes_in_one_render():
+    # demos/observers/groups.py:57-76 shape: five fibres at the pinhole position looking into the divertor, one render call
+    plasma = generomak.get_plasma()
+    plasma.atomic_data = cb.SyntheticADAS()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    plasma.integrator = cb.NumericalIntegrator(step=0.005)
+    flat = cb.flatten_scene(plasma, 655.5, 656.9, 256)
+    group = cb.FibreOpticGroup(name="Divertor Fibre Optic Array")
+    for i, ang in enumerate((-63.8, -66.5, -69.2, -71.9, -74.6)):
+        target = (2.3 - np.cos(np.deg2rad(ang)), 0.0, 1.25 + np.sin(np.deg2rad(ang)))
+        group.add_observer(cb.FibreOptic(name=str(i + 1), transform=cb.look_at((2.3, 0.0, 1.25), target, up=(0, 1, 0))))
+    group.acceptance_angle, group.radius, group.pixel_samples = 1.4, 0.001, 24
+    scene = EmissionScene(flat)
+    spectra = group.observe(scene, plasma.geometry, plasma.geometry_to_world())
+    scene.close()
+    o, d, w, owner = group.gather_rays()
+    ref_rays, _ = oracle.emission_render(flat, cb.ray_segments(plasma.geometry, o, d, plasma.geometry_to_world()))
+    for i in range(5):
+        sel = owner == i
+        ref = (ref_rays[sel] * w[sel, None]).sum(axis=0) / w[sel].sum()
+        assert ref.max() > 0
+        assert np.all(np.abs(spectra[i] - ref) <= 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max())
+        assert group.observers[i].spectrum is spectra[i] or np.array_equal(group.observers[i].spectrum, spectra[i])

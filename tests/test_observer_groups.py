@@ -1,0 +1,50 @@
+"""Host logic of the 0-D observer groups (cherab/tools/observers/group/base.py): membership, broadcast setters, ray bundles."""
+import numpy as np
+import pytest
+
+import core_b200 as cb
+
+
+def test_group_membership_and_broadcast_setters():
+    group = cb.FibreOpticGroup(name="Divertor Fibre Optic Array")
+    for i in range(3):
+        group.add_observer(cb.FibreOptic(name=str(i + 1), transform=cb.translate(2.3, 0, 1.25)))
+    with pytest.raises(ValueError):
+        group.add_observer(cb.SightLine())                       # group/base.py:106-107
+    group.acceptance_angle = 1.4
+    group.radius = [0.001, 0.002, 0.003]
+    group.pixel_samples = 50
+    assert group.acceptance_angle == [1.4] * 3 and group.radius == [0.001, 0.002, 0.003] and group.names == ["1", "2", "3"]
+    with pytest.raises(ValueError):
+        group.radius = [0.001, 0.002]                            # length mismatch
+    with pytest.raises(TypeError):
+        group.names = "abc"
+    group.names = ["a", "b", "c"]
+    assert group.observers[1].name == "b"
+
+
+def test_fibre_ray_bundle_geometry():
+    f = cb.FibreOptic(transform=cb.look_at((1.0, 2.0, 3.0), (1.0, 2.0, 0.0), up=(0, 1, 0)), acceptance_angle=10.0, radius=0.01, pixel_samples=500)
+    o, d, w = f.rays()
+    axis = np.array([0.0, 0.0, -1.0])
+    assert o.shape == d.shape == (500, 3)
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-14)
+    cos_t = d @ axis
+    assert cos_t.min() >= np.cos(np.deg2rad(10.0)) - 1e-12 and np.allclose(cos_t, w)
+    assert np.all(np.linalg.norm(o - np.array([1.0, 2.0, 3.0]), axis=1) <= 0.01 + 1e-12)
+    np.testing.assert_allclose((o - np.array([1.0, 2.0, 3.0])) @ axis, 0.0, atol=1e-12)        # origins lie in the tip plane
+    # uniform in solid angle: the mean of cos(theta) over the cap is (1 + cos_max) / 2
+    assert abs(cos_t.mean() - 0.5 * (1.0 + np.cos(np.deg2rad(10.0)))) < 1e-5
+    # uniform in area: mean squared radius is R^2 / 2
+    r2 = np.sum((o - np.array([1.0, 2.0, 3.0])) ** 2, axis=1)
+    assert abs(r2.mean() / 0.01 ** 2 - 0.5) < 2e-3
+    assert abs(f.solid_angle - 2 * np.pi * (1 - np.cos(np.deg2rad(10.0)))) < 1e-15
+
+
+def test_group_transform_applies_to_every_observer():
+    g = cb.SightLineGroup([cb.SightLine(transform=cb.translate(1, 0, 0)), cb.SightLine(transform=cb.translate(0, 1, 0))],
+                          transform=cb.translate(0, 0, 5))
+    o, d, w, owner = g.gather_rays()
+    np.testing.assert_allclose(o, [[1, 0, 5], [0, 1, 5]])
+    np.testing.assert_allclose(d, [[0, 0, 1], [0, 0, 1]])
+    assert list(owner) == [0, 1] and list(w) == [1.0, 1.0]
