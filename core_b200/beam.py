@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _abi
 from .atomic import ConstantRate, Line
-from .geometry import HollowCylinder
+from .geometry import HollowCylinder, TruncatedCone
 from .models import GaussianLine, LineShapeModel, PlasmaModel
 from .notify import Notifier
 from .plasma import NumericalIntegrator
@@ -193,14 +193,24 @@ class Beam:
 
     @property
     def geometry(self):
-        """Bounding primitive in the beam frame (beam/node.pyx:505-554).  The reference uses a cone for diverging beams; here
-        the enclosing cylinder of the far-end radius is used (the density is clamped to zero outside clamp_sigma anyway)."""
+        """Bounding primitive in the beam frame, chosen exactly as Beam._generate_geometry does (beam/node.pyx:505-554): a
+        cylinder of radius clamp_sigma * sigma without divergence — and also when a cone would save less than 10 % of the
+        volume — else the cone from clamp_sigma * sigma at the source to clamp_sigma * sqrt(sigma^2 + (length tan(div))^2)."""
         if self.attenuator is None:
             raise ValueError("The beam must have an attenuator model to provide density values.")
         ns = self.attenuator.clamp_sigma
+        if self.divergence_x == 0 and self.divergence_y == 0:
+            return HollowCylinder(0.0, ns * self.sigma, 0.0, self.length)
         drdz = np.tan(np.deg2rad(max(self.divergence_x, self.divergence_y)))
-        radius = ns * np.sqrt(self.sigma ** 2 + (self.length * drdz) ** 2) if drdz > 0 else ns * self.sigma
-        return HollowCylinder(0.0, radius, 0.0, self.length)
+        radius_start = ns * self.sigma
+        radius_end = ns * np.sqrt(self.sigma ** 2 + self.length ** 2 * drdz ** 2)
+        distance_apex = radius_start * self.length / (radius_end - radius_start)
+        cone_height = self.length + distance_apex
+        cylinder_volume = self.length * np.pi * radius_end ** 2
+        cone_volume = np.pi * (cone_height * radius_end ** 2 - distance_apex * radius_start ** 2) / 3
+        if cone_volume / cylinder_volume > 0.9:
+            return HollowCylinder(0.0, ns * self.sigma, 0.0, self.length)
+        return TruncatedCone(radius_start, radius_end, self.length)
 
 
 def _fill_beam_rate(r, rate, keep):

@@ -95,6 +95,46 @@ class HollowCylinder(Primitive):
         return [first, second]
 
 
+class TruncatedCone(Primitive):
+    """Intersect(Cone(radius_end, cone_height, translate(0, 0, length) * rotate_x(180)), Cylinder(1.01 radius_end, 1.01 length)):
+    the bounding volume of a diverging beam (cherab/core/beam/node.pyx:527-554) — radius_start at z = 0 growing linearly to
+    radius_end at z = length."""
+
+    def __init__(self, radius_start, radius_end, length, transform=None):
+        if not radius_end > radius_start > 0 or not length > 0:
+            raise ValueError("TruncatedCone needs 0 < radius_start < radius_end and a positive length")
+        self.radius_start, self.radius_end, self.length = float(radius_start), float(radius_end), float(length)
+        self.transform = transform
+
+    def intervals(self, o, d):
+        da = self.radius_start * self.length / (self.radius_end - self.radius_start)      # apex at z = -da
+        k2 = (self.radius_end / (self.length + da)) ** 2
+        zo = o[:, 2] + da
+        a = d[:, 0] ** 2 + d[:, 1] ** 2 - k2 * d[:, 2] ** 2
+        b = 2.0 * (o[:, 0] * d[:, 0] + o[:, 1] * d[:, 1] - k2 * zo * d[:, 2])
+        c = o[:, 0] ** 2 + o[:, 1] ** 2 - k2 * zo * zo
+        s0, s1 = _slab_interval(o, d, 2, 0.0, self.length)
+        s0 = np.maximum(s0, 0.0)
+        disc = b * b - 4.0 * a * c
+        lin = np.abs(a) < 1e-300
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sq = np.sqrt(np.maximum(disc, 0.0))
+            r0 = np.where(a > 0, (-b - sq) / (2 * a), (-b + sq) / (2 * a))              # smaller root
+            r1 = np.where(a > 0, (-b + sq) / (2 * a), (-b - sq) / (2 * a))              # larger root
+            tl = -c / b
+        miss = np.full(o.shape[0], np.inf), np.full(o.shape[0], -np.inf)
+        # a > 0: inside between the roots; a < 0: inside outside the roots (the lower nappe lies below the slab); a = 0: half line
+        has = disc > 0
+        f0 = np.where(lin, np.where(b > 0, s0, np.maximum(s0, tl)), np.where(a > 0, np.where(has, np.maximum(s0, r0), miss[0]), s0))
+        f1 = np.where(lin, np.where(b > 0, np.minimum(s1, tl), s1), np.where(a > 0, np.where(has, np.minimum(s1, r1), miss[1]),
+                                                                           np.where(has, np.minimum(s1, r0), s1)))
+        g0 = np.where((~lin) & (a < 0) & has, np.maximum(s0, r1), miss[0])
+        g1 = np.where((~lin) & (a < 0) & has, s1, miss[1])
+        lin_out = lin & (np.abs(b) < 1e-300) & (c > 0)
+        f0 = np.where(lin_out, miss[0], f0)
+        return [(f0, f1), (g0, g1)]
+
+
 class Sphere(Primitive):
     def __init__(self, radius, transform=None):
         self.radius, self.transform = float(radius), transform
