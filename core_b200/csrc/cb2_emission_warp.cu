@@ -673,7 +673,8 @@ __global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile i
 // K1a: per-sample plasma state -> line records + Bremsstrahlung moments
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef CB2_STATE_MINB
-#define CB2_STATE_MINB 5
+// 6 CTAs of 4 warps per SM (85 registers, ~200 B of spills): measured 3 % faster than 5 (102 registers), 4 is 6 % slower, 8 slower again
+#define CB2_STATE_MINB 6
 #endif
 // FEAT = 0: plasma line models and Bremsstrahlung only (the benchmark's scene); FEAT = 1 adds the beam frame / BeamCXLine,
 // ThermalCXLine and TotalRadiatedPower branches (kept out of the common instance: they cost registers and instruction cache)
