@@ -438,6 +438,14 @@ def main():
                     e["fp32"] = {"achieved": flop / t * 1e-12, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": flop / t * 1e-12 / peaks["fp32_tflops"]}
                 if t > 0 and sfu > 0:
                     e["sfu"] = {"achieved": sfu / t * 1e-12, "peak": peaks["sfu_tops"], "unit": "Tops/s", "frac": sfu / t * 1e-12 / peaks["sfu_tops"]}
+                if name == "contract_kernel" and plan.get("contraction_on_tensor_cores") and t > 0:
+                    # error-compensated 3xTF32: three tensor-core GEMMs per algorithmic float32 GEMM (+ the hi/lo split of the moments).
+                    # Peak = the dense TF32 rate, half the measured bf16 one (B200_PROFILING.md: 1.1 vs 2.25 PFLOP/s nominal).
+                    tf32_peak = 0.5 * float(peaks_file.get("bf16_tflops", 2250.0))
+                    e.pop("fp32", None)
+                    e["tensor"] = {"achieved": 3.0 * flop / t * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * flop / t * 1e-12 / tf32_peak,
+                                   "fp32_equivalent_tflops": flop / t * 1e-12,
+                                   "note": "cuBLAS TF32 GEMMs (tcgen05) x3, includes the tf32 hi/lo split kernel; peak = measured bf16 / 2"}
                 kernels[name] = e
             dom = max((k for k in kernels if k != "helpers"), key=lambda k: kernels[k]["ms_per_step"])
         else:

@@ -1397,6 +1397,7 @@ extern "C" int cb2_scene_create(const cb2_scene_desc* d, int device, cb2_scene**
         }
         if ((rc = convert_brems(A, *d, S)) != CB2_OK) break;  // decides the Bremsstrahlung mode (direct / moments)
         if ((rc = cb2_emission_config(sc)) != CB2_OK) break;  // sets nw, bpl, bins_padded (needs n_comp and the mode for the shared-memory budget)
+        if (S.brems.present && S.brems.mode == 3 && (rc = cb2_contract_tc_init(sc, S.brems.phi, S.brems.k_pad, S.brems.n_pad)) != CB2_OK) break;
         bool any_stark = false;
         for (int m = 0; m < d->n_models; m++)
             any_stark |= d->models[m].kind != CB2_MODEL_BREMSSTRAHLUNG && d->models[m].kind != CB2_MODEL_TOTAL_RADIATED_POWER &&
@@ -1444,6 +1445,7 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     free(sc->allocs);
     free_stage(sc->stage, sc->stage_bytes);
     if (sc->mom) cudaFree(sc->mom);
+    cb2_contract_tc_destroy(sc);
     if (sc->gbase) cudaFree(sc->gbase);
     if (sc->gmask) cudaFree(sc->gmask);
     if (sc->rec) cudaFree(sc->rec);
@@ -1569,6 +1571,7 @@ extern "C" int64_t cb2_scene_info(const cb2_scene* sc, int key) {
     case 5: return b.present && b.mode == 3 ? b.n_z : 0;
     case 6: return sc->warp_kernel ? cb2_warp_batch_rays(sc) : 0;
     case 7: return sc->warp_kernel;
+    case 8: return sc->contract_tc;
     }
     return -1;
 }

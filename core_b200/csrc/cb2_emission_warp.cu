@@ -1038,7 +1038,11 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         if (rc != CB2_OK) return rc;
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[3], st));
         // K2
-        if (moments && (rc = cb2_launch_contract(sc->mom, B.phi, sub.n_rays, B.k_pad, B.n_pad, S.bins, o, out_f64, scale, st)) != CB2_OK) return rc;
+        if (moments) {
+            rc = sc->contract_tc ? cb2_launch_contract_tc(sc, sc->mom, sub.n_rays, B.k_pad, B.n_pad, S.bins, o, out_f64, scale, st)
+                                 : cb2_launch_contract(sc->mom, B.phi, sub.n_rays, B.k_pad, B.n_pad, S.bins, o, out_f64, scale, st);
+            if (rc != CB2_OK) return rc;
+        }
         if (prof) {
             CB2_CUDA(cudaEventRecord(sc->prof_ev[4], st));
             CB2_CUDA(cudaEventSynchronize(sc->prof_ev[4]));

@@ -303,6 +303,11 @@ struct cb2_scene {
     // Bremsstrahlung moment matrix [rays][k_pad] fp32 (grow-only)
     float* mom;
     size_t mom_bytes;
+    // tensor-core contraction (cb2_contract.cu): cuBLAS handle, tf32 hi/lo parts of phi and of the moments, float32 scratch
+    int contract_tc;
+    void* blas;
+    float *phi_hi, *phi_lo, *mom_split, *tmp32;
+    size_t mom_split_bytes, tmp32_bytes;
     // two-kernel line path (cb2_emission_warp.cu), grow-only: per-ray group offsets [batch+1], per-group live masks, and
     // the per-(group, component) line records [3][32] fp32 (centre, width, amplitude)
     int64_t* gbase;
@@ -368,6 +373,10 @@ static inline int64_t cb2_moment_batch(int k_pad) {
     batch = batch / 128 * 128;
     return batch < 128 ? 128 : batch;
 }
+int cb2_contract_tc_init(cb2_scene* sc, const float* phi, int k_pad, int n_pad);
+void cb2_contract_tc_destroy(cb2_scene* sc);
+int cb2_launch_contract_tc(cb2_scene* sc, const float* mom, int64_t n_rays, int k_pad, int n_pad, int bins, void* out, int out_f64,
+                           double scale, cudaStream_t stream);
 // out[ray][bin] += scale * sum_k mom[ray][k] phi[k][bin]   (cb2_contract.cu)
 int cb2_launch_contract(const float* mom, const float* phi, int64_t n_rays, int k_pad, int n_pad, int bins, void* out, int out_f64,
                         double scale, cudaStream_t stream);

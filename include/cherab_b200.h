@@ -392,7 +392,8 @@ int cb2_beam_sample(cb2_scene* scene, const double* beam_points, int64_t n, doub
  * formulation a scene runs).  key: 0 warps per CTA, 1 bins per lane, 2 Bremsstrahlung formulation (0 none, 1 direct
  * per-(sample, bin) evaluation, 3 per-ray temperature moments + contraction), 3 moment row length k_pad,
  * 4 temperature nodes, 5 distinct ion charges, 6 rays per batch of the two-kernel line path, 7 line path (1 two-kernel
- * state/bin path, 0 CTA-phased kernel with the direct Bremsstrahlung evaluation).  Returns -1 for an unknown key. */
+ * state/bin path, 0 CTA-phased kernel with the direct Bremsstrahlung evaluation), 8 contraction of the moments (1 tensor
+ * cores, error-compensated 3xTF32 GEMMs; 0 FFMA tile kernel).  Returns -1 for an unknown key. */
 int64_t cb2_scene_info(const cb2_scene* scene, int key);
 
 /* Per-kernel device timing for the benchmark's roofline section (no reference counterpart).  enable != 0: reset the
