@@ -1100,6 +1100,15 @@ static int build_brems_moments(Arena& A, const cb2_scene_desc& d, DevScene& S) {
         b.zidx[s] = k;
     }
     if (!why && nz == 0) why = "no charged species";
+    if (!why) {
+        int cursor = 0;
+        for (int k = 0; k < nz; k++) {
+            b.zstart[k] = cursor;
+            for (int s = 0; s < b.n_charged; s++)
+                if (b.zidx[s] == k) b.zlist[cursor++] = b.charged[s];
+        }
+        for (int k = nz; k <= CB2_MAX_BREMS_Z; k++) b.zstart[k] = cursor;
+    }
     double tlo = 0, thi = 0;
     if (!why && !scalar_bounds(d.electron_temperature, d.axisym, tlo, thi)) why = "electron temperature field is not bounded away from zero";
     if (!why) {

@@ -415,18 +415,17 @@ __device__ __forceinline__ void sample_brems_moments(const DevScene& S, const Sa
         const float tm1 = t - 1.0f, tm2 = t - 2.0f, tp1 = t + 1.0f;
         const float l0 = -t * tm1 * tm2 * (1.0f / 6.0f), l1 = tp1 * tm1 * tm2 * 0.5f, l2 = -tp1 * t * tm2 * 0.5f, l3 = tp1 * t * tm1 * (1.0f / 6.0f);
         const float W = in.weight * B.pref * ne * rsqrtf(te) * __expf(-B.x_ref * tau);
-        // per distinct charge: N_z = sum of the densities of the species with that charge
+        // per distinct charge: N_z = sum of the (positive) densities of the species with that charge; the species are grouped by
+        // charge on the host, so the sums need no per-species select chain
         float nzv[CB2_MAX_BREMS_Z];
 #pragma unroll
-        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] = 0.f;
-#pragma unroll 4
-        for (int s = 0; s < B.n_charged; s++) {
-            const float ni = eval_scalar_t<AXONLY>(S.species[B.charged[s]].density, ctx, in.x, in.y, in.z);
-            const int zi = B.zidx[s];
-            if (ni > 0.f) {
-#pragma unroll
-                for (int z = 0; z < CB2_MAX_BREMS_Z; z++) nzv[z] += (z == zi) ? ni : 0.f;
+        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
+            float a = 0.f;
+            for (int s = B.zstart[z]; s < B.zstart[z + 1]; s++) {
+                const float ni = eval_scalar_t<AXONLY>(S.species[B.zlist[s]].density, ctx, in.x, in.y, in.z);
+                a += fmaxf(ni, 0.f);
             }
+            nzv[z] = a;
         }
 #pragma unroll
         for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {

@@ -17,6 +17,7 @@
 #define CB2_MAX_SPECIES 24
 #define CB2_MAX_MODELS 32
 #define CB2_MAX_COMP 96
+#define CB2_MAX_BREMS_Z 8
 #define CB2_DENSITY_SCALE 1e-19
 #define CB2_PEC_LOG_OFFSET 38.0
 
@@ -209,6 +210,8 @@ struct DevBrems {
     int mode;                     // 1/2: direct per-(sample, bin) path, 3: moments
     int n_z;                      // distinct charges (<= CB2_MAX_BREMS_Z)
     int zidx[CB2_MAX_SPECIES];    // charged[s] -> index into the distinct-charge list
+    int zlist[CB2_MAX_SPECIES];   // scene species indices grouped by distinct charge: group z is zlist[zstart[z] .. zstart[z+1])
+    int zstart[CB2_MAX_BREMS_Z + 1];
     int n_nodes;                  // temperature nodes M
     int k_pad;                    // n_z * M rounded up to a multiple of 16 (row length of the moment matrix)
     int n_pad;                    // bins rounded up to a multiple of 128 (row length of phi)
@@ -217,7 +220,6 @@ struct DevBrems {
     float te_lo, te_hi;           // temperatures covered by the node grid (samples outside are clamped and counted)
     const float* phi;             // [k_pad][n_pad]
 };
-#define CB2_MAX_BREMS_Z 8
 
 // Beam + SingleRayAttenuator (beam/node.pyx, attenuator/singleray.pyx): in a beam scene the integrator marches in the beam
 // frame (DevScene::w2p holds world -> beam) and l2p takes the sample to plasma space
