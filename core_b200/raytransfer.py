@@ -189,6 +189,38 @@ class RayTransferPipelineBase:
         return self._matrix
 
 
+class Spectrum:
+    """The slice of raysect's Spectrum the pixel processors read: ``samples[bins]`` on [min_wavelength, max_wavelength]."""
+
+    def __init__(self, min_wavelength, max_wavelength, bins):
+        self.min_wavelength, self.max_wavelength, self.bins = float(min_wavelength), float(max_wavelength), int(bins)
+        self.samples = np.zeros(self.bins)
+
+
+class RayTransferPixelProcessorBase:
+    """pipelines.py:213-222: accumulates the ray-transfer matrix row of one pixel."""
+
+    def __init__(self, bins):
+        self._matrix = np.zeros(bins)
+
+    def pack_results(self):
+        return (self._matrix, 0)
+
+
+class RadianceRayTransferPixelProcessor(RayTransferPixelProcessorBase):
+    """pipelines.py:225-231: path lengths in [m], the detector sensitivity is ignored."""
+
+    def add_sample(self, spectrum, sensitivity):
+        self._matrix += spectrum.samples
+
+
+class PowerRayTransferPixelProcessor(RayTransferPixelProcessorBase):
+    """pipelines.py:234-240: [m^3 sr], every sample multiplied by the detector sensitivity."""
+
+    def add_sample(self, spectrum, sensitivity):
+        self._matrix += spectrum.samples * sensitivity
+
+
 class RayTransferPipeline0D(RayTransferPipelineBase):
     def __init__(self, name='RayTransferPipeline0D', kind='power'):
         super().__init__(name, kind)
@@ -197,6 +229,9 @@ class RayTransferPipeline0D(RayTransferPipelineBase):
         self._samples = 0
         self._bins = spectral_bins
         self._matrix = np.zeros(spectral_bins)
+
+    def pixel_processor(self, slice_id):
+        return (PowerRayTransferPixelProcessor if self._kind == 'power' else RadianceRayTransferPixelProcessor)(self._bins)
 
     def update(self, slice_id, packed_result, pixel_samples):
         self._samples += pixel_samples
@@ -215,6 +250,9 @@ class RayTransferPipeline1D(RayTransferPipelineBase):
         self._pixels, self._samples, self._bins = pixels, pixel_samples, spectral_bins
         self._matrix = np.zeros((pixels, spectral_bins))
 
+    def pixel_processor(self, pixel, slice_id):
+        return (PowerRayTransferPixelProcessor if self._kind == 'power' else RadianceRayTransferPixelProcessor)(self._bins)
+
     def update(self, pixel, slice_id, packed_result):
         self._matrix[pixel] = packed_result[0] / self._samples
 
@@ -230,6 +268,9 @@ class RayTransferPipeline2D(RayTransferPipelineBase):
     def initialise(self, pixels, pixel_samples, min_wavelength, max_wavelength, spectral_bins, spectral_slices, quiet):
         self._pixels, self._samples, self._bins = pixels, pixel_samples, spectral_bins
         self._matrix = np.zeros((pixels[0], pixels[1], spectral_bins))
+
+    def pixel_processor(self, x, y, slice_id):
+        return (PowerRayTransferPixelProcessor if self._kind == 'power' else RadianceRayTransferPixelProcessor)(self._bins)
 
     def update(self, x, y, slice_id, packed_result):
         self._matrix[x, y] = packed_result[0] / self._samples

@@ -2,6 +2,7 @@
 (:33-89,126-164), the integration known answers (:109-118 cylinder 3-D, :166-175 box) and the 2-D cylinder case
 (:91-107, whose right-hand side in the reference is a CSG ToroidalVoxelGrid = exact chord lengths per voxel)."""
 import numpy as np
+import pytest
 
 import core_b200 as cb
 from core_b200.raytransfer import RayTransferBox, RayTransferCylinder, RayTransferPipeline2D
@@ -124,3 +125,37 @@ def test_transform_and_pipeline_2d():
     import pytest
     with pytest.raises(ValueError):
         RayTransferPipeline2D(kind="flux")
+
+
+# ---- pipelines and pixel processors: cherab/tools/tests/test_raytransfer.py:245-393 ----
+def test_pipelines_initialise_and_kind():
+    from core_b200.raytransfer import RayTransferPipeline0D, RayTransferPipeline1D, Spectrum
+    nbins, pixels, samples, sensitivity, value = 10, 20, 1, 2.0, 1.0
+    spectrum = Spectrum(1.0, 2.0, nbins)
+    spectrum.samples[:] = value
+    p0 = RayTransferPipeline0D("test_pipeline_0D", kind="power")
+    p0.initialise(0, 0, nbins, 0, 0)
+    assert p0.matrix.shape == (nbins,) and p0.name == "test_pipeline_0D" and p0.kind == "power"
+    with pytest.raises(ValueError):
+        RayTransferPipeline0D("test_pipeline_0D", "blah")
+    p1 = RayTransferPipeline1D("test_pipeline_1D", kind="radiance")
+    p1.initialise(pixels, samples, 0, 0, nbins, 1, 0)
+    assert p1.matrix.shape == (pixels, nbins) and p1.kind == "radiance" and p1._samples == samples
+    p2 = RayTransferPipeline2D("test_pipeline_2D", kind="power")
+    p2.initialise((pixels, pixels), samples, 0, 0, nbins, 1, 0)
+    assert p2.matrix.shape == (pixels, pixels, nbins)
+    for pipe, args in ((p0, (0,)), (p1, (0, 0)), (p2, (0, 0, 0))):
+        pipe.kind = "power"
+        proc = pipe.pixel_processor(*args)
+        proc.add_sample(spectrum, sensitivity)
+        assert np.all(proc.pack_results()[0] == sensitivity * value)        # multiplied by the sensitivity
+        pipe.kind = "radiance"
+        proc = pipe.pixel_processor(*args)
+        proc.add_sample(spectrum, sensitivity)
+        assert np.all(proc.pack_results()[0] == value)                      # not multiplied
+    # 0-D accumulates over update() calls and normalises at finalise (pipelines.py:111-119)
+    p0.initialise(0, 0, nbins, 0, 0)
+    p0.update(0, (np.full(nbins, 3.0), 0), 2)
+    p0.update(0, (np.full(nbins, 5.0), 0), 2)
+    p0.finalise()
+    assert np.all(p0.matrix == 2.0)
