@@ -573,12 +573,18 @@ __device__ __forceinline__ void component_pass(int type, float cf, float width, 
                     if (LOR) { R.kind = 3; R.lo = l; R.hi = h; R.kx = 1.0f / width; R.xoff = -cf * R.kx; R.s0 = amp; }  // u at edge e: e kx + xoff
                 } else {
                     gauss_evals += (unsigned)(h - l) + 1u;
-                    const float ecut = EVAL_CUTOFF_SIGMA * width;            // evaluated range: 7 sigma
+                    // Evaluated range: 7 sigma when the component's own core (centre +- 2.5 sigma) overlaps the spectral window —
+                    // the ray's largest bin is then >= e^-3.1 of this sample's peak and what lies beyond 7 sigma (e^-24.5) is
+                    // under the 1e-9 acceptance floor.  A window that only sees the far wing has no such floor: the reference's
+                    // full 10 sigma range is evaluated, with the series only where it still converges there (m h <= 0.25), else
+                    // with erfc differences (accurate in relative terms in the wing).
+                    const bool core_in = (cf + 2.5f * width > win_lo) && (cf - 2.5f * width < win_hi);
+                    const float ecut = (core_in ? EVAL_CUTOFF_SIGMA : 10.0f) * width;
                     R.lo = max(l, (int)fmaxf(floorf(cf - ecut), win_lo));
                     R.hi = min(h, (int)fminf(ceilf(cf + ecut), win_hi));
                     const float kb = 0.70710678f / width;                    // delta / (sqrt(2) sigma), per bin
                     const float hh = 0.5f * kb;
-                    if (hh <= H_SERIES_MAX) {
+                    if (hh <= (core_in ? H_SERIES_MAX : 0.035f)) {
                         const float h2 = hh * hh;
                         const float t1 = h2 * (1.0f / 6.0f), t2 = h2 * h2 * (1.0f / 120.0f), t3 = h2 * h2 * h2 * (1.0f / 5040.0f),
                                     t4 = h2 * h2 * h2 * h2 * (1.0f / 362880.0f);
