@@ -119,3 +119,45 @@ def test_c4_shape_csr_device_properties():
         assert np.array_equal(row > 0, nz)
         assert np.max(np.abs(row[nz] - ref[k][nz]) / ref[k][nz]) <= 1e-5
     scene.close()
+
+
+# ---- seeded random grids and rays: index flips move a whole step, so every corner of the index arithmetic is visited ----
+def _random_rt(rng):
+    kind = int(rng.integers(0, 3))
+    if kind == 0:                                   # axisymmetric cylinder, possibly hollow
+        n_r, n_z = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        r_in = float(rng.choice([0.0, rng.uniform(0.1, 1.0)]))
+        rt = RayTransferCylinder(radius_outer=r_in + float(rng.uniform(0.5, 2.0)), height=float(rng.uniform(0.5, 3.0)), n_radius=n_r, n_height=n_z,
+                                 radius_inner=r_in, transform=cb.translate(0, 0, float(rng.uniform(-2, 0))))
+    elif kind == 1:                                 # 3-D cylinder with a toroidal period
+        n_p = int(rng.integers(2, 9))
+        rt = RayTransferCylinder(radius_outer=float(rng.uniform(1.0, 2.5)), height=float(rng.uniform(0.5, 3.0)), n_radius=int(rng.integers(1, 12)),
+                                 n_height=int(rng.integers(1, 12)), n_polar=n_p, period=float(rng.choice([360.0, 180.0, 90.0, 45.0])),
+                                 radius_inner=float(rng.choice([0.0, 0.4])))
+    else:
+        rt = RayTransferBox(xmax=float(rng.uniform(0.5, 3)), ymax=float(rng.uniform(0.5, 3)), zmax=float(rng.uniform(0.5, 3)),
+                            nx=int(rng.integers(1, 12)), ny=int(rng.integers(1, 12)), nz=int(rng.integers(1, 12)),
+                            transform=cb.translate(*rng.uniform(-1, 1, 3)))
+    shape = rt.grid_shape if hasattr(rt, "grid_shape") else None
+    if rng.uniform() < 0.5:                         # a random voxel map with unmapped cells, or a mask
+        vm = rng.integers(-1, 25, size=tuple(rt.voxel_map.shape)).astype(np.int32)
+        rt.voxel_map = vm
+    elif rng.uniform() < 0.5:
+        rt.mask = rng.uniform(size=tuple(rt.voxel_map.shape)) < 0.7
+    rt.step = rt.step * float(10 ** rng.uniform(-1.0, 1.0))
+    n = 24
+    o = rng.uniform(-4, 4, (n, 3))
+    target = rng.uniform(-1.0, 1.0, (n, 3))
+    d = target - o
+    d[0] = (0, 0, -1); o[0] = (0.3, 0.2, 5.0)                 # parallel to the axis
+    d[1] = (-1, 0, 0); o[1] = (5.0, 0.0, 0.1)                 # through the axis
+    d[2] = (0, -1, 0); o[2] = (0.0, 5.0, 0.2)                 # along a coordinate plane
+    return rt, cb.ray_segments(rt.primitive, o, d, rt.transform)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_grids_and_rays(seed):
+    rt, rays = _random_rt(np.random.default_rng(500 + seed))
+    if rays.n_segments == 0:
+        pytest.skip("no ray hits the grid")
+    check(rt, rays)
