@@ -145,3 +145,44 @@ def test_random_continuum_scene(seed, mode, monkeypatch):
     tol = 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max(axis=1, keepdims=True)
     err = np.abs(got - ref)
     assert ref.max() > 0 and np.all(err <= tol), "seed %d (%s): worst err/tol %.3g" % (seed, used, np.max(err / (tol + 1e-300)))
+
+
+# ---- random views of the Generomak plasma (the benchmark's function tree): camera anywhere, random models and windows ----
+def _generomak_scene(rng):
+    from core_b200 import generomak
+    plasma = generomak.get_plasma()
+    h = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4, 5)]
+    shapes = [None, None, cb.ZeemanTriplet, cb.StarkBroadenedLine]
+    models = []
+    for l in h[:int(rng.integers(1, 4))]:
+        shape = shapes[int(rng.integers(0, len(shapes)))]
+        models.append((cb.ExcitationLine if rng.uniform() < 0.5 else cb.RecombinationLine)(l, lineshape=shape))
+    if rng.uniform() < 0.6:
+        models.append(cb.Bremsstrahlung())
+    plasma.models = models
+    plasma.integrator = cb.NumericalIntegrator(step=float(rng.uniform(0.004, 0.02)))
+    centre = float(rng.choice([656.28, 486.13, 434.05, 550.0]))
+    half = float(10 ** rng.uniform(-0.7, 2.0))
+    flat = cb.flatten_scene(plasma, max(centre - half, 200.0), centre + half, int(rng.choice([16, 200, 512, 1300])))
+    n = 10
+    phi = rng.uniform(0, 2 * np.pi, n)
+    r = rng.uniform(0.8, 3.2, n)                                   # inside the vessel, outside it, above it
+    o = np.stack([r * np.cos(phi), r * np.sin(phi), rng.uniform(-2.2, 2.2, n)], axis=1)
+    tphi = phi + rng.uniform(-2.5, 2.5, n)
+    tr = rng.uniform(0.75, 2.4, n)
+    target = np.stack([tr * np.cos(tphi), tr * np.sin(tphi), rng.uniform(-1.7, 1.5, n)], axis=1)
+    rays = cb.ray_segments(plasma.geometry, o, target - o, plasma.geometry_to_world())
+    return flat, rays
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_generomak_view(seed):
+    flat, rays = _generomak_scene(np.random.default_rng(9000 + seed))
+    scene = EmissionScene(flat)
+    got, stats = scene.render(rays)
+    scene.close()
+    ref, rstats = oracle.emission_render(flat, rays)
+    assert stats["samples"] == rstats["samples"] > 0
+    tol = 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(got - ref)
+    assert np.all(err <= tol), "seed %d: worst err/tol %.3g" % (seed, np.max(err / (tol + 1e-300)))
