@@ -186,3 +186,51 @@ def test_random_generomak_view(seed):
     tol = 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max(axis=1, keepdims=True)
     err = np.abs(got - ref)
     assert np.all(err <= tol), "seed %d: worst err/tol %.3g" % (seed, np.max(err / (tol + 1e-300)))
+
+
+# ---- random beam scenes: orientation, divergence, width, energy, attenuation, both beam models with tabulated rates ----
+def _beam_scene(rng):
+    density = float(10 ** rng.uniform(18.5, 20.0))
+    temperature = float(10 ** rng.uniform(1.5, 3.7))
+    plasma = build_constant_slab_plasma(length=float(rng.uniform(0.6, 1.5)), width=1.0, height=1.0, electron_density=density, electron_temperature=temperature,
+                                        plasma_species=[(cb.deuterium, 1, density, temperature, tuple(rng.uniform(-2e4, 2e4, 3))),
+                                                        (cb.carbon, 6, 0.02 * density, temperature, (0.0, 0.0, 0.0))],
+                                        b_field=tuple(rng.uniform(-3, 3, 3)))
+    atomic = cb.SyntheticADAS(permit_extrapolation=True)
+    balmer = atomic.wavelength
+    atomic.wavelength = lambda ion, charge, transition: 529.05 if ion is cb.carbon else balmer(ion, charge, transition)
+    plasma.atomic_data = atomic
+    src = (float(rng.uniform(-0.6, -0.1)), float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.2, 0.2)))
+    aim = (float(rng.uniform(0.5, 1.0)), float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.2, 0.2)))
+    beam = cb.Beam(transform=cb.look_at(src, aim))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=bool(rng.integers(0, 2)), step=float(rng.uniform(0.005, 0.02)))
+    beam.energy, beam.power, beam.temperature, beam.element = float(rng.uniform(2e4, 1e5)), 2e6, float(rng.uniform(5, 40)), cb.deuterium
+    beam.sigma, beam.length = float(rng.uniform(0.02, 0.08)), float(rng.uniform(1.5, 2.5))
+    beam.divergence_x, beam.divergence_y = float(rng.choice([0.0, rng.uniform(0.1, 2.0)])), float(rng.choice([0.0, rng.uniform(0.1, 2.0)]))
+    beam.integrator = cb.NumericalIntegrator(step=float(rng.uniform(0.002, 0.01)), min_samples=int(rng.integers(2, 12)))
+    which = int(rng.integers(0, 3))
+    cx, bes = cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7))), cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2)))
+    beam.models = [cx] if which == 0 else ([bes] if which == 1 else [bes, cx])
+    lo, hi = (526.0, 532.0) if which == 0 else (650.0, 662.0)
+    flat = cb.flatten_beam_scene(beam, lo, hi, int(rng.choice([64, 300, 1024])))
+    n = 8
+    b2w = np.asarray(beam.transform)
+    axis = (b2w @ np.stack([rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n), rng.uniform(0.3, 1.6, n), np.ones(n)]))[:3].T
+    o = np.stack([rng.uniform(-0.5, 1.5, n), rng.uniform(1.0, 2.0, n) * rng.choice([-1, 1], n), rng.uniform(-1.5, 1.5, n)], axis=1)
+    return flat, cb.beam_ray_segments(beam, o, axis - o)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_beam_scene(seed):
+    flat, rays = _beam_scene(np.random.default_rng(12000 + seed))
+    if rays.n_segments == 0:
+        pytest.skip("no sight line crosses the beam")
+    scene = EmissionScene(flat)
+    got, stats = scene.render(rays)
+    scene.close()
+    ref, rstats = oracle.emission_render(flat, rays)
+    assert stats["samples"] == rstats["samples"]
+    tol = 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(got - ref)
+    assert np.all(err <= tol), "seed %d: worst err/tol %.3g" % (seed, np.max(err / (tol + 1e-300)))
