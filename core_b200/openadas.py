@@ -8,6 +8,11 @@ radiated_power,utility}.py: the repository that ``cherab.openadas.repository.pop
     pec/excitation/<symbol>/<charge>.json          {"<upper> -> <lower>": {"ne": [...], "te": [...], "rate": [[...]]}}
     pec/recombination/<symbol>/<charge>.json       same shape (photon m^3 s^-1 on ne [m^-3] x te [eV])
     radiated_power/{line,continuum,cx}/<symbol>.json   {"<charge>": {"ne", "te", "rate" [W m^3]}}
+    pec/thermal_cx/<donor>/<donor charge>/<receiver>/<receiver charge>.json   {"<upper> -> <lower>": {"ne", "te", "td", "rate"}}
+    beam/stopping/<beam>/<target>/<charge>.json         {"e", "n", "t", "sen", "st", "sref", ...}
+    beam/population/<beam>/<metastable>/<target>/<charge>.json   same shape, dimensionless
+    beam/emission/<beam>/<target>/<charge>.json         {"<upper> -> <lower>": {"e", "n", "t", "sen", "st", "sref"}}
+    beam/cx/<donor>/<receiver>/<charge>.json            {"<upper> -> <lower>": {"<metastable>": {"eb", "ti", "ni", "z", "b", "qeb", ..., "qref"}}}
 
 This class only turns those files into the RateTable objects the scene flattener understands; the log-log cubic
 interpolation itself happens on the device (cb2_scene_create).  Rates are looked up under the ELEMENT of an isotope (ADAS
@@ -18,7 +23,7 @@ import os
 
 import numpy as np
 
-from .atomic import AtomicData, RateTable
+from .atomic import AtomicData, RateTable, RateTable3D
 
 DEFAULT_REPOSITORY_PATH = os.path.expanduser("~/.cherab/openadas/repository")
 
@@ -101,3 +106,88 @@ class OpenADAS(AtomicData):
 
     def cx_radiated_power_rate(self, ion, charge):
         return self._power("cx", ion, charge)
+
+    # ---- thermal charge exchange (repository/pec.py:364-403, openadas.py:389-430) ----
+    def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
+        donor, receiver = donor_ion.element, receiver_ion.element
+        try:
+            d = self._load("pec/thermal_cx/{}/{}/{}/{}.json".format(donor.symbol.lower(), donor_charge, receiver.symbol.lower(), receiver_charge),
+                           encode_transition(transition),
+                           "thermal charge-exchange PEC (donor={}, donor charge={}, receiver={}, receiver charge={})".format(
+                               donor.symbol, donor_charge, receiver.symbol, receiver_charge))
+        except RuntimeError:
+            if self.missing_rates_return_null:
+                return None
+            raise
+        f = lambda k: np.array(d[k], np.float64)
+        return RateTable3D(f("ne"), f("te"), f("td"), f("rate"), self.permit_extrapolation)
+
+    # ---- beam rates (repository/beam/{stopping,population,emission,cx}.py, openadas.py:164-330) ----
+    def _load_file(self, relative_path, what):
+        path = os.path.join(self.data_path, relative_path)
+        try:
+            with open(path, "r") as f:
+                return json.load(f)
+        except FileNotFoundError:
+            raise RuntimeError("Requested %s is not available." % what)
+
+    @staticmethod
+    def _beam_table(d):
+        from .beam import BeamStoppingTable
+        f = lambda k: np.array(d[k], np.float64)
+        return BeamStoppingTable(f("e"), f("n"), f("t"), f("sen"), f("st"), float(d["sref"]))
+
+    def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+        beam, target = beam_ion.element, plasma_ion.element
+        try:
+            d = self._load_file("beam/stopping/{}/{}/{}.json".format(beam.symbol.lower(), target.symbol.lower(), charge),
+                                "beam stopping rate (beam species={}, target ion={}, target charge={})".format(beam.symbol, target.symbol, charge))
+        except RuntimeError:
+            if self.missing_rates_return_null:
+                return None
+            raise
+        return self._beam_table(d)
+
+    def beam_population_rate(self, beam_ion, metastable, plasma_ion, charge):
+        beam, target = beam_ion.element, plasma_ion.element
+        try:
+            d = self._load_file("beam/population/{}/{}/{}/{}.json".format(beam.symbol.lower(), metastable, target.symbol.lower(), charge),
+                                "beam population rate (beam species={}, metastable={}, target ion={}, target charge={})".format(
+                                    beam.symbol, metastable, target.symbol, charge))
+        except RuntimeError:
+            if self.missing_rates_return_null:
+                return None
+            raise
+        return self._beam_table(d)
+
+    def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
+        beam, target = beam_ion.element, plasma_ion.element
+        try:
+            d = self._load("beam/emission/{}/{}/{}.json".format(beam.symbol.lower(), target.symbol.lower(), charge), encode_transition(transition),
+                           "beam emission rate (beam species={}, target ion={}, target charge={}, transition={})".format(
+                               beam.symbol, target.symbol, charge, transition))
+        except RuntimeError:
+            if self.missing_rates_return_null:
+                return None
+            raise
+        return self._beam_table(d)
+
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        """One BeamCXTable per donor metastable, in the file's order (repository/beam/cx.py:210-262)."""
+        from .beam import BeamCXTable, ConstantBeamCXPEC
+        donor, receiver = donor_ion.element, receiver_ion.element
+        try:
+            rates = self._load("beam/cx/{}/{}/{}.json".format(donor.symbol.lower(), receiver.symbol.lower(), receiver_charge),
+                               encode_transition(transition),
+                               "beam CX effective emission rates (donor={}, receiver={}, charge={}, transition={})".format(
+                                   donor.symbol, receiver.symbol, receiver_charge, transition))
+        except RuntimeError:
+            if self.missing_rates_return_null:
+                return [ConstantBeamCXPEC(1, 0.0)]                # [NullBeamCXPEC()], openadas.py:197-199
+            raise
+        out = []
+        for metastable, d in rates.items():
+            f = lambda k: np.array(d[k], np.float64)
+            out.append(BeamCXTable(int(metastable), f("eb"), f("ti"), f("ni"), f("z"), f("b"), f("qeb"), f("qti"), f("qni"), f("qz"), f("qb"),
+                                   float(d["qref"])))
+        return out
