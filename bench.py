@@ -141,8 +141,26 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     n_rays = args.ref_rays
     vals = []
+    # the real Cherab + Raysect API when both import on this box (tools/run_reference.py; untested where they are absent),
+    # else the oracle port
+    kind = "port"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_reference
+        if run_reference.available() is None:
+            kind = "reference"
+    except Exception:
+        kind = "port"
     for k in range(args.warmup + args.steps):
-        v, samples, dt = cpu_baseline(flat, plasma, args.pixels, n_rays, threads, seed=1234 + k)
+        if kind == "reference":
+            rng = np.random.default_rng(1234 + k)
+            pick = np.sort(rng.choice(args.pixels * args.pixels, size=n_rays, replace=False))
+            rays = make_rays(plasma, args.pixels, pick, 0)
+            length = rays.seg_t1 - rays.seg_t0
+            samples = int((np.maximum(flat.desc.min_samples - 1, np.ceil(length / flat.desc.step)) + 1).sum())
+            _, dt = run_reference.run(args.pixels, args.bins, pick, 0)
+        else:
+            v, samples, dt = cpu_baseline(flat, plasma, args.pixels, n_rays, threads, seed=1234 + k)
         if k >= args.warmup:
             vals.append((samples, dt))
     tot_s = sum(s for s, _ in vals)
@@ -153,7 +171,7 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": tot_t / max(len(vals), 1) * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
