@@ -206,6 +206,13 @@ class RayTransferScene:
             return row_offset, columns[:nnz], lengths[:nnz], st.as_dict()
         raise OverflowError("CSR capacity negotiation failed")
 
+    def render_sparse(self, rays, capacity=None):
+        """The geometry matrix as a ``scipy.sparse.csr_matrix`` of shape (n_rays, bins) — what RayTransferPipeline*.matrix holds
+        densely in the reference (pipelines.py:198); SURVEY H8: 400 x 800 cells x 512^2 rays do not fit a dense ndarray."""
+        import scipy.sparse
+        row_offset, columns, lengths, stats = self.render_csr(rays, capacity)
+        return scipy.sparse.csr_matrix((lengths, columns, row_offset), shape=(rays.n_rays, self.bins)), stats
+
     def render_csr_device(self, dev_rays, capacity):
         """Device-resident CSR build: returns torch tensors (row_offset, columns, lengths) on the rays' device."""
         import torch

@@ -27,6 +27,8 @@ def check(rt, rays):
         assert len(np.unique(c)) == len(c), "duplicate source within a CSR row"
         rebuilt[r, c] = lens[ro[r]:ro[r + 1]]
     assert np.allclose(rebuilt, dense, rtol=1e-12, atol=0)
+    sparse, _ = scene.render_sparse(rays)
+    assert sparse.shape == dense.shape and np.array_equal(sparse.toarray(), rebuilt)
     scene.close()
     return dense, ref
 
