@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -101,7 +101,8 @@ class ModelExt(C.Structure):
                 ("plt", Rate2D), ("prb", Rate2D), ("prc", Rate2D), ("n_cx", C.c_int32), ("_pad3", C.c_int32), ("cx", C.POINTER(CXRate)),
                 ("cx_population", C.POINTER(BeamRate)),
                 ("n_bes", C.c_int32), ("_pad4", C.c_int32), ("bes_species", c_int32_p), ("bes_rates", C.POINTER(BeamRate)),
-                ("mse_ratios", C.c_double * 4)]
+                ("mse_ratios", C.c_double * 4), ("n_mse", C.c_int32), ("_pad5", C.c_int32), ("mse_lne0", C.c_double), ("mse_dlne", C.c_double),
+                ("mse_ratio_tab", c_double_p)]
 
 
 class ModelDesc(C.Structure):

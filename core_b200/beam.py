@@ -121,7 +121,9 @@ class BeamCXLine(BeamModel):
 
 class BeamEmissionLine(BeamModel):
     """beam_emission.pyx:36-98: Balmer-series emission of the beam atoms excited by the plasma, with the motional-Stark-effect
-    multiplet line shape (mse.pyx).  The intensity ratios must be constants here (the reference also accepts functions)."""
+    multiplet line shape (mse.pyx).  The intensity ratios are constants or, as in the reference (mse.pyx:103-121), callables:
+    ``sigma_to_pi(ne, beam_energy)`` and ``sigma1_to_sigma0(ne)``, ``pi2_to_pi3(ne)``, ``pi4_to_pi3(ne)``.  Callables are tabulated by
+    the flattener on ``ratio_knots`` points uniform in log10(ne) over ``ratio_density_range`` (linear interpolation on the device)."""
     kind = _abi.MODEL_BEAM_EMISSION_LINE
 
     def __init__(self, line, beam=None, plasma=None, atomic_data=None, sigma_to_pi=0.56, sigma1_to_sigma0=0.7060001671878492,
@@ -130,10 +132,23 @@ class BeamEmissionLine(BeamModel):
         if not isinstance(line, Line):
             raise TypeError("line must be a Line")
         self.line = line
-        for v in (sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3):
+        self.ratio_functions = (sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3)
+        self.ratio_density_range, self.ratio_knots = (1e16, 1e22), 385
+        self.ratios = tuple(0.0 if callable(v) else float(v) for v in self.ratio_functions)
+
+    def ratio_table(self, beam_energy):
+        """None when every ratio is a constant, else (log10 ne of the first knot, knot spacing, table[4][knots])."""
+        if not any(callable(v) for v in self.ratio_functions):
+            return None
+        lo, hi = np.log10(self.ratio_density_range[0]), np.log10(self.ratio_density_range[1])
+        lne = np.linspace(lo, hi, self.ratio_knots)
+        tab = np.empty((4, self.ratio_knots))
+        for k, v in enumerate(self.ratio_functions):
             if callable(v):
-                raise TypeError("function-valued MSE intensity ratios are not supported on the B200 path")
-        self.ratios = (float(sigma_to_pi), float(sigma1_to_sigma0), float(pi2_to_pi3), float(pi4_to_pi3))
+                tab[k] = [v(n, beam_energy) if k == 0 else v(n) for n in 10.0 ** lne]
+            else:
+                tab[k] = float(v)
+        return float(lo), float(lne[1] - lne[0]), np.ascontiguousarray(tab)
 
     def populate(self, beam, plasma, atomic_data):
         """beam_emission.pyx:178-216 -> (wavelength, [(species index, rate)])."""
@@ -319,6 +334,12 @@ def flatten_beam_scene(beam, min_wavelength, max_wavelength, bins):
             ext.bes_rates = C.cast(barr, C.POINTER(_abi.BeamRate))
             for k in range(4):
                 ext.mse_ratios[k] = mdl.ratios[k]
+            table = mdl.ratio_table(beam.energy)
+            if table is not None:
+                ext.mse_lne0, ext.mse_dlne, tab = table
+                ext.n_mse = tab.shape[1]
+                ext.mse_ratio_tab = tab.ctypes.data_as(_abi.c_double_p)
+                keep.append(tab)
             keep.extend([bidx, barr, ext])
             mo.ext = C.pointer(ext)
             continue

@@ -819,6 +819,17 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
         const double ip3 = 1 / (1 + p23 + p43), ip2 = p23 * ip3, ip4 = p43 * ip3;
         const double amp[9] = {isig * is0, isig * is1, isig * is1, ipi * ip2, ipi * ip2, ipi * ip3, ipi * ip3, ipi * ip4, ipi * ip4};
         for (int k = 0; k < 9; k++) e.mse_amp[k] = (float)amp[k];
+        if (x->n_mse > 1) {
+            if (!x->mse_ratio_tab || !(x->mse_dlne > 0)) return cb2_fail(CB2_ERR_VALUE, "MSE ratio table missing or knot spacing not positive");
+            std::vector<float4> tab(x->n_mse);
+            for (int q = 0; q < x->n_mse; q++)
+                tab[q] = make_float4((float)x->mse_ratio_tab[q], (float)x->mse_ratio_tab[x->n_mse + q], (float)x->mse_ratio_tab[2 * x->n_mse + q],
+                                     (float)x->mse_ratio_tab[3 * x->n_mse + q]);
+            e.mse_n = x->n_mse;
+            e.mse_lne0 = (float)x->mse_lne0;
+            e.mse_inv_dlne = (float)(1.0 / x->mse_dlne);
+            e.mse_tab = A.upload(tab);
+        }
         e.mse_sigma_b = (float)(sqrt(d.beam->temperature * ELEMENTARY_CHARGE / (d.beam->atomic_weight * ATOMIC_MASS)) * m.wavelength /
                                 SPEED_OF_LIGHT / S.delta_d);
         o.ext = A.upload(std::vector<DevModelExt>(1, e));

@@ -797,11 +797,27 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                     beam_emission_setup<AXONLY>(S, M, in, ctx, ne, te, lc, amp, shift_b, split_b, ood);
                     const bool any_amp = __any_sync(FULL, amp > 0.f);
                     const DevModelExt& X = *M.ext;
+                    float mamp[9];
+#pragma unroll
+                    for (int kc = 0; kc < 9; kc++) mamp[kc] = X.mse_amp[kc];
+                    if (X.mse_n > 1 && amp > 0.f) {
+                        // intensity ratios as functions of ne (mse.pyx:103-121): linear in log10(ne) on the host's knots, clamped
+                        float f = fminf(fmaxf((lc.lne - X.mse_lne0) * X.mse_inv_dlne, 0.f), (float)(X.mse_n - 1));
+                        const int i0 = min((int)f, X.mse_n - 2);
+                        const float w = f - (float)i0;
+                        const float4 a = __ldg(X.mse_tab + i0), b = __ldg(X.mse_tab + i0 + 1);
+                        const float s2p = fmaf(w, b.x - a.x, a.x), s1s0 = fmaf(w, b.y - a.y, a.y), p23 = fmaf(w, b.z - a.z, a.z), p43 = fmaf(w, b.w - a.w, a.w);
+                        const float dd = 1.0f / (1.0f + s2p), isig = s2p * dd, ipi = 0.5f * dd, is0 = 1.0f / (s1s0 + 1.0f), is1 = 0.5f * s1s0 * is0;
+                        const float ip3 = 1.0f / (1.0f + p23 + p43), ip2 = p23 * ip3, ip4 = p43 * ip3;
+                        mamp[0] = isig * is0; mamp[1] = mamp[2] = isig * is1;
+                        mamp[3] = mamp[4] = ipi * ip2; mamp[5] = mamp[6] = ipi * ip3; mamp[7] = mamp[8] = ipi * ip4;
+                    }
+#pragma unroll
                     for (int kc = 0; kc < 9; kc++) {
                         float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
                         // component order: sigma0, sigma1 +-, pi2 +-, pi3 +-, pi4 +-  (mse.pyx:113-133)
                         const float off = kc == 0 ? 0.f : (float)((kc + 1) >> 1) * ((kc & 1) ? 1.f : -1.f);
-                        r[64] = amp * X.mse_amp[kc];
+                        r[64] = amp * mamp[kc];
                         if (any_amp) { r[0] = S.comps[M.comp0 + kc].c0_frac + shift_b + off * split_b; r[32] = X.mse_sigma_b; }
                     }
                     continue;

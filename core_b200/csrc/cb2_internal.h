@@ -151,7 +151,10 @@ struct DevModelExt {
     DevTable2D bes_a[CB2_MAX_SPECIES];     // (log10 E[eV/amu], log10 n_eq[m^-3]) -> log10(sen [W m^3]) + 38
     DevTable1D bes_tk[CB2_MAX_SPECIES];    // log10 T[eV] knots
     const float4* bes_tc[CB2_MAX_SPECIES]; // -> log10(st / sref)
-    float mse_amp[9];                      // relative intensities of the 9 multiplet components (mse.pyx:105-133)
+    float mse_amp[9];                      // relative intensities of the 9 multiplet components (mse.pyx:105-133), constant ratios
+    int mse_n;                             // > 1: ratios tabulated on mse_n knots uniform in log10(ne), mse_tab[knot] = the four ratios
+    float mse_lne0, mse_inv_dlne;
+    const float4* mse_tab;
     float mse_sigma_b;                     // sigma in bins from the beam temperature and mass
     int has[3];                            // plt, prb, prc present
     int is_const[3];

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 5
+#define CB2_ABI_VERSION 6
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -280,12 +280,17 @@ typedef struct cb2_model_ext {
     const cb2_beam_rate* cx_population;
     /* BEAM_EMISSION_LINE: beam_emission_pec(beam.element, species.element, species.charge, transition) for every plasma
      * species (beam_emission.pyx:207-212; same table shape as the stopping rate, 'sen' in photon m^3 s^-1, a constant rate in
-     * W m^3) and the constant MSE intensity ratios sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3 (beam_emission.pyx:47-50;
-     * function-valued ratios are not supported) */
+     * W m^3) and the MSE intensity ratios sigma_to_pi, sigma1_to_sigma0, pi2_to_pi3, pi4_to_pi3 (beam_emission.pyx:47-50): constants
+     * in mse_ratios, or — the reference also takes functions of the electron density (and, for sigma_to_pi, of the beam energy, which
+     * is one number per scene; mse.pyx:103-121) — tabulated by the host on n_mse knots uniform in log10(ne [m^-3]) from mse_lne0 in
+     * steps of mse_dlne, mse_ratio_tab[4][n_mse], interpolated linearly in log10(ne) and clamped at the ends (n_mse == 0: constants) */
     int32_t              n_bes, _pad4;
     const int32_t*       bes_species;
     const cb2_beam_rate* bes_rates;
     double               mse_ratios[4];
+    int32_t              n_mse, _pad5;
+    double               mse_lne0, mse_dlne;
+    const double*        mse_ratio_tab;
 } cb2_model_ext;
 
 typedef struct cb2_model {

@@ -1200,7 +1200,16 @@ static void beam_emission_function(const scene_ctx* s, const double pb[3], const
             double stark = fabs(2.77e-8 * sqrt(cx_[0] * cx_[0] + cx_[1] * cx_[1] + cx_[2] * cx_[2]));
             double central = doppler_shift(mo->wavelength, obs, bv);
             double sigma = thermal_broadening(mo->wavelength, b->temperature, b->atomic_weight);
-            double s2p = x->mse_ratios[0], s1s0 = x->mse_ratios[1], p23 = x->mse_ratios[2], p43 = x->mse_ratios[3];
+            double rt[4] = {x->mse_ratios[0], x->mse_ratios[1], x->mse_ratios[2], x->mse_ratios[3]};
+            if (x->n_mse > 1) { /* ratios as functions of ne (mse.pyx:103-121), tabulated on knots uniform in log10(ne) */
+                double f = (log10(ne) - x->mse_lne0) / x->mse_dlne;
+                f = f < 0 ? 0 : (f > x->n_mse - 1 ? x->n_mse - 1 : f);
+                int i0 = (int)f;
+                if (i0 > x->n_mse - 2) i0 = x->n_mse - 2;
+                double w = f - i0;
+                for (int q = 0; q < 4; q++) rt[q] = x->mse_ratio_tab[q * x->n_mse + i0] + w * (x->mse_ratio_tab[q * x->n_mse + i0 + 1] - x->mse_ratio_tab[q * x->n_mse + i0]);
+            }
+            double s2p = rt[0], s1s0 = rt[1], p23 = rt[2], p43 = rt[3];
             double dd = 1 / (1 + s2p), isig = s2p * dd * radiance, ipi = 0.5 * dd * radiance;
             double is0 = 1 / (s1s0 + 1), is1 = 0.5 * s1s0 * is0;
             double ip3 = 1 / (1 + p23 + p43), ip2 = p23 * ip3, ip4 = p43 * ip3;

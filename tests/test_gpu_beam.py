@@ -180,3 +180,38 @@ def test_beam_cx_metastables_slab_and_generomak():
     assert st["samples"] == rst["samples"] and ref.max() > 0
     assert np.abs(ref - ref1).max() > 1e-3 * ref.max()                    # the excited state does change the answer
     assert parity(got, ref) <= 1.0
+
+
+def test_beam_emission_ratio_functions():
+    # MSE intensity ratios as functions of the electron density: constant slab (equals the constant-ratio case) and the Generomak
+    # plasma, where ne varies by decades along the beam
+    from test_oracle_beam import mse_case
+    flat, rays, _ = mse_case(ratio_functions=True)
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"] and parity(got, ref) <= 1.0
+    plasma = generomak.get_plasma()
+    atomic = cb.SyntheticADAS(permit_extrapolation=True)
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.look_at((3.2, -0.4, 0.0), (1.0, 0.3, 0.05)))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.05, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.0025, min_samples=10)
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2)),
+                                       sigma_to_pi=lambda ne, e: 0.4 + 0.3 / (1.0 + (ne / 3e19) ** 0.7) + 1e-6 * e,
+                                       sigma1_to_sigma0=lambda ne: 0.7 + 0.1 * np.tanh(np.log10(ne) - 19.0), pi2_to_pi3=0.31,
+                                       pi4_to_pi3=lambda ne: 0.73 * (ne / 1e19) ** 0.05)]
+    flat = cb.flatten_beam_scene(beam, 650.0, 662.0, 1024)
+    axis_pts = (np.asarray(beam.transform) @ np.stack([np.zeros(10), np.zeros(10), np.linspace(0.6, 2.4, 10), np.ones(10)]))[:3].T
+    origin = np.tile([[1.8, 0.2, 1.6]], (10, 1))
+    rays = cb.beam_ray_segments(beam, origin, axis_pts - origin)
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["samples"] == rst["samples"] and ref.max() > 0
+    assert parity(got, ref) <= 1.0

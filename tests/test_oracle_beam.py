@@ -104,7 +104,7 @@ class BesMockData(BeamMockData):
         return cb.ConstantRate(2.0e-35)
 
 
-def mse_case():
+def mse_case(ratio_functions=False):
     """Inputs of core/tests/test_lineshapes.py:391-472 (D-alpha 656.104 nm, beam 60 keV/amu at 10 eV, B = (0, 5, 0) T,
     ne 1e19, line of sight (-1, 1, 0)/sqrt 2, 512 bins on +-3 nm) replayed through the whole path: a parallel beam along +z
     through the slab, so every sample has the same multiplet shape and the spectrum is (integrated radiance) x (unit shape)."""
@@ -117,7 +117,14 @@ def mse_case():
     beam.atomic_data, beam.plasma = atomic, plasma
     beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
     beam.energy, beam.power, beam.temperature, beam.element = 60000, 1e6, 10, cb.deuterium
-    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2)))]
+    kw = {}
+    if ratio_functions:
+        # the reference also takes functions of (ne, beam energy) / (ne) for the intensity ratios (mse.pyx:103-121); these are
+        # linear in log10(ne) (exact on the flattener's table) and give the default constants at ne = 1e19, E = 60 keV/amu
+        kw = dict(sigma_to_pi=lambda ne, e: 0.56 + 0.05 * (np.log10(ne) - 19.0) + 1e-6 * (e - 60000.0),
+                  sigma1_to_sigma0=lambda ne: 0.7060001671878492 - 0.03 * (np.log10(ne) - 19.0),
+                  pi2_to_pi3=lambda ne: 0.3140003593919741 * (1.0 + 0.1 * (np.log10(ne) - 19.0)), pi4_to_pi3=0.7279994935840365)
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2)), **kw)]
     flat = cb.flatten_beam_scene(beam, 656.104 - 3, 656.104 + 3, 512)
     d = np.array([-1.0, 1.0, 0.0]) / np.sqrt(2)
     rays = cb.beam_ray_segments(beam, [np.array([0.5, 0.0, 0.0]) - 2.0 * d], [d])
@@ -189,3 +196,13 @@ def test_beam_cx_line_population_weighted_metastables():
     q1, q2, k = 3.4e-34, MetastableMockData.q2, MetastableMockData.k
     composite = (q1 + k * q2) / (1 + k)                                   # charge_exchange.pyx:178
     assert np.max(np.abs(got[0] - ground[0] * composite / q1)) <= 1e-12 * got.max()
+
+
+def test_beam_emission_multiplet_with_ratio_functions():
+    # function-valued intensity ratios that equal the defaults at the slab's density reproduce the constant-ratio spectrum
+    flat_c, rays, _ = mse_case()
+    flat_f, _, _ = mse_case(ratio_functions=True)
+    assert flat_f.desc.models[0].ext.contents.n_mse > 1 and flat_c.desc.models[0].ext.contents.n_mse == 0
+    const_ratios, _ = oracle.emission_render(flat_c, rays)
+    functions, _ = oracle.emission_render(flat_f, rays)
+    assert np.max(np.abs(functions - const_ratios)) <= 1e-12 * const_ratios.max()
