@@ -257,8 +257,14 @@ class _Observer0DGroup:
         np.add.at(num, owner, per_ray * w[:, None])
         np.add.at(den, owner, w)
         self.spectra = num / den[:, None]
-        for ob, s in zip(self._observers, self.spectra):
-            ob.spectrum = s
+        # spectral power [W / nm] collected by each observer, what a SpectralPowerPipeline0D reports: the mean of L cos(theta) over the
+        # uniform solid-angle samples times the etendue (solid angle x collection area); a sight line scales by its sensitivity
+        counts = np.bincount(owner, minlength=n).astype(np.float64)
+        etendue = np.array([getattr(ob, "solid_angle", 1.0) * getattr(ob, "collection_area", 1.0) * getattr(ob, "sensitivity", 1.0)
+                            for ob in self._observers])
+        self.power_spectra = num / counts[:, None] * etendue[:, None]
+        for ob, s, pw in zip(self._observers, self.spectra, self.power_spectra):
+            ob.spectrum, ob.power_spectrum = s, pw
         return self.spectra
 
 

@@ -108,3 +108,6 @@ def test_fibre_group_observes_in_one_render():
         assert ref.max() > 0
         assert np.all(np.abs(spectra[i] - ref) <= 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max())
         assert group.observers[i].spectrum is spectra[i] or np.array_equal(group.observers[i].spectrum, spectra[i])
+        ob = group.observers[i]
+        power = (ref_rays[sel] * w[sel, None]).mean(axis=0) * ob.solid_angle * ob.collection_area      # etendue-weighted: W / nm
+        assert np.all(np.abs(group.power_spectra[i] - power) <= 1e-4 * np.abs(power) + 1e-9 * np.abs(power).max())
