@@ -147,14 +147,19 @@ rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* 
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsigned)src * 2654435761u) >> (32 - hbits); }
 
+// PACKED: one 32-bit word per table position, (source << 12) | slot, for grids with fewer than 2^20 sources and rays that can
+// touch fewer than 4095 of them (every BASELINE configuration): 4 bytes per position instead of 6 + a used-position list, i.e.
+// about twice the resident warps per SM for a latency-bound kernel.  The whole table is cleared after every ray.
+#define RT_PENDING 0xFFFu
+template <bool PACKED>
 __global__ void __launch_bounds__(512)
 rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset, int32_t* __restrict__ columns,
               double* __restrict__ lengths, int hbits, int cap, unsigned long long* __restrict__ stats) {
     extern __shared__ int rt_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int H = 1 << hbits;
-    // per warp: keys int32[H], slots uint16[H], used uint16[cap]
-    const size_t per_warp = (size_t)H * 4 + (size_t)H * 2 + (((size_t)cap * 2 + 3) & ~(size_t)3);
+    // per warp: keys int32[H], slots uint16[H], used uint16[cap]   |   PACKED: entries uint32[H]
+    const size_t per_warp = PACKED ? (size_t)H * 4 : (size_t)H * 4 + (size_t)H * 2 + (((size_t)cap * 2 + 3) & ~(size_t)3);
     unsigned char* base = reinterpret_cast<unsigned char*>(rt_smem) + per_warp * warp;
     int* keys = reinterpret_cast<int*>(base);
     unsigned short* slots = reinterpret_cast<unsigned short*>(base + (size_t)H * 4);
@@ -199,11 +204,21 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                 bool is_new = false;
                 if (act) {
                     h = (int)rt_hash(src, hbits);
-                    for (;;) {
-                        const int old = atomicCAS(&keys[h], -1, src);
-                        if (old == -1) { is_new = true; break; }
-                        if (old == src) break;
-                        h = (h + 1) & (H - 1);
+                    if (PACKED) {
+                        const int claim = (int)(((unsigned)src << 12) | RT_PENDING);
+                        for (;;) {
+                            const int old = atomicCAS(&keys[h], -1, claim);
+                            if (old == -1) { is_new = true; break; }
+                            if (((unsigned)old >> 12) == (unsigned)src) break;
+                            h = (h + 1) & (H - 1);
+                        }
+                    } else {
+                        for (;;) {
+                            const int old = atomicCAS(&keys[h], -1, src);
+                            if (old == -1) { is_new = true; break; }
+                            if (old == src) break;
+                            h = (h + 1) & (H - 1);
+                        }
                     }
                 }
                 // phase 2: new keys take consecutive slots of the ray's row
@@ -211,8 +226,8 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                 if (is_new) {
                     const int slot = count + __popc(nm & ((1u << lane) - 1u));
                     if (slot < cap) {
-                        slots[h] = (unsigned short)slot;
-                        used[slot] = (unsigned short)h;
+                        if (PACKED) keys[h] = (int)(((unsigned)src << 12) | (unsigned)slot);
+                        else { slots[h] = (unsigned short)slot; used[slot] = (unsigned short)h; }
                         if (mode == 2) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
                     } else overflow++;
                 }
@@ -222,7 +237,7 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                 if (mode == 2 && act) {
                     const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
                     const int next = higher ? (__ffs(higher) - 1) : 32;
-                    const int slot = slots[h];
+                    const int slot = PACKED ? (int)((unsigned)keys[h] & 0xFFFu) : (int)slots[h];
                     if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)(next - lane), dt));
                 }
             }
@@ -230,7 +245,12 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
         // reset the touched table positions for the next ray
         __syncwarp();
         const int cnt = min(count, cap);
-        for (int pos = lane; pos < cnt; pos += 32) keys[used[pos]] = -1;
+        if (PACKED) {
+            if (count > 0)
+                for (int i = lane; i < H; i += 32) keys[i] = -1;
+        } else {
+            for (int pos = lane; pos < cnt; pos += 32) keys[used[pos]] = -1;
+        }
         if (mode == 1 && lane == 0) row_offset[ray] = cnt;
         __syncwarp();
     }
@@ -261,17 +281,31 @@ int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double*
     const int cap = sc->touch_cap;
     int hbits = 8;
     while ((1 << hbits) < cap + cap / 4 + 8 && hbits < 16) hbits++;     // load factor <= 0.8 even for a ray that reaches the bound
-    const size_t per_warp = ((size_t)6 << hbits) + (((size_t)cap * 2 + 3) & ~(size_t)3);
-    int wpc = (int)std::min<size_t>(16, (208 * 1024) / per_warp);
-    if (wpc < 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grid too large for the shared-memory source table (%d distinct sources per ray)", cap);
-    const size_t smem = per_warp * wpc;
-    CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool packed = sc->rt.bins < (1 << 20) && cap < (int)RT_PENDING && getenv("CB2_RT_UNPACKED") == nullptr;
+    const size_t per_warp = packed ? ((size_t)4 << hbits) : ((size_t)6 << hbits) + (((size_t)cap * 2 + 3) & ~(size_t)3);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device);
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+    cudaFuncAttributes fa;
+    CB2_CUDA(cudaFuncGetAttributes(&fa, packed ? rt_csr_kernel<true> : rt_csr_kernel<false>));
+    const int reg_warps = fa.numRegs > 0 ? 65536 / (((fa.numRegs + 7) & ~7) * 32) : 16;   // warps per SM the register file allows (8-register granules)
+    // the kernel is latency-bound: take the CTA shape that keeps the most warps resident (shared memory and registers permitting)
+    int wpc = 0, ctas_per_sm = 1;
+    for (int c = 1; c <= 4; c++) {
+        int w = (int)std::min<size_t>(16, ((size_t)220 * 1024 / c) / per_warp);
+        w = std::min(w, reg_warps / c);
+        if (w >= 1 && w * c > wpc * ctas_per_sm) { wpc = w; ctas_per_sm = c; }
+    }
+    if (wpc < 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grid too large for the shared-memory source table (%d distinct sources per ray)", cap);
+    const size_t smem = per_warp * wpc;
     int64_t blocks = std::min<int64_t>((rays.n_rays + wpc - 1) / wpc, (int64_t)sms * ctas_per_sm);
     if (blocks < 1) blocks = 1;
-    rt_csr_kernel<<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+    if (packed) {
+        CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rt_csr_kernel<true><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+    } else {
+        CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rt_csr_kernel<false><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+    }
     return cb2_cuda_check(cudaGetLastError(), "rt_csr_kernel launch");
 }
 
