@@ -17,6 +17,8 @@
 // accumulate in the row itself (fp64 atomics on a few KB that stay in L2).  The first version kept a dense double[bins]
 // scratch row per warp in HBM and was latency-bound on it (ncu: long-scoreboard 50 stall cycles per issue, issue-active 7 %).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -151,8 +153,9 @@ __device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsig
 // touch fewer than 4095 of them (every BASELINE configuration): 4 bytes per position instead of 6 + a used-position list, i.e.
 // about twice the resident warps per SM for a latency-bound kernel.  The whole table is cleared after every ray.
 #define RT_PENDING 0xFFFu
+#define RT_CSR_MAX_WARPS 9          // 288 threads x 3 CTAs per SM: 72 registers per thread, 27 resident warps
 template <bool PACKED>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(RT_CSR_MAX_WARPS * 32, 3)
 rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset, int32_t* __restrict__ columns,
               double* __restrict__ lengths, int hbits, int cap, unsigned long long* __restrict__ stats) {
     extern __shared__ int rt_smem[];
@@ -291,9 +294,13 @@ int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double*
     // the kernel is latency-bound: take the CTA shape that keeps the most warps resident (shared memory and registers permitting)
     int wpc = 0, ctas_per_sm = 1;
     for (int c = 1; c <= 4; c++) {
-        int w = (int)std::min<size_t>(16, ((size_t)220 * 1024 / c) / per_warp);
+        int w = (int)std::min<size_t>(RT_CSR_MAX_WARPS, ((size_t)220 * 1024 / c) / per_warp);
         w = std::min(w, reg_warps / c);
         if (w >= 1 && w * c > wpc * ctas_per_sm) { wpc = w; ctas_per_sm = c; }
+    }
+    if (const char* shape = getenv("CB2_RT_SHAPE")) {     // "ctas,warps" — tuning experiments only
+        int c = 0, w = 0;
+        if (sscanf(shape, "%d,%d", &c, &w) == 2 && c >= 1 && w >= 1 && w <= RT_CSR_MAX_WARPS && (size_t)c * w * per_warp <= (size_t)220 * 1024) { ctas_per_sm = c; wpc = w; }
     }
     if (wpc < 1) return cb2_fail(CB2_ERR_NOT_IMPLEMENTED, "ray-transfer grid too large for the shared-memory source table (%d distinct sources per ray)", cap);
     const size_t smem = per_warp * wpc;
