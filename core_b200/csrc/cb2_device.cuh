@@ -173,8 +173,27 @@ __device__ __forceinline__ int mesh_locate(const DevAxisym& A, double r, double 
     // the bucket lists are in ascending triangle order, so the first hit is the lowest-numbered triangle containing the
     // point (the tie rule for points on shared edges)
     const int k1 = __ldg(A.cell_start + cell + 1);
+    const float rf = (float)r, zf = (float)z;
     for (int k = __ldg(A.cell_start + cell); k < k1; k++) {
         const int t = __ldg(A.cell_tris + k);
+        // float32 sign filter: the three edge functions from rounded coordinates, each with a bound on what the roundings can
+        // have changed (inputs: half an ulp of a coordinate < 4 m each, 2.4e-7; the arithmetic adds ~1e-7 relative).  A point
+        // clearly outside (one function certainly negative, one certainly positive) is rejected, a point clearly inside
+        // (all three certain, one sign) is inside this triangle only, so the tie rule cannot matter; everything else — a
+        // band of ~1e-6 m around the edge lines — takes the exact float64 test.
+        {
+            const float4 p = __ldg(A.trif + 2 * t), q = __ldg(A.trif + 2 * t + 1);
+            const float u1 = rf - p.z, v1 = p.y - p.w, u2 = p.x - p.z, v2 = zf - p.w;      // d1: (r - bx)(ay - by) - (ax - bx)(z - by)
+            const float u3 = rf - q.x, v3 = p.w - q.y, u4 = p.z - q.x, v4 = zf - q.y;      // d2: (r - cx)(by - cy) - (bx - cx)(z - cy)
+            const float u5 = rf - p.x, v5 = q.y - p.y, u6 = q.x - p.x, v6 = zf - p.y;      // d3: (r - ax)(cy - ay) - (cx - ax)(z - ay)
+            const float f1 = u1 * v1 - u2 * v2, f2 = u3 * v3 - u4 * v4, f3 = u5 * v5 - u6 * v6;
+            const float e1 = 1.5e-6f * (fabsf(u1) + fabsf(v1) + fabsf(u2) + fabsf(v2));
+            const float e2 = 1.5e-6f * (fabsf(u3) + fabsf(v3) + fabsf(u4) + fabsf(v4));
+            const float e3 = 1.5e-6f * (fabsf(u5) + fabsf(v5) + fabsf(u6) + fabsf(v6));
+            const bool n1 = f1 < -e1, n2 = f2 < -e2, n3 = f3 < -e3, p1 = f1 > e1, p2 = f2 > e2, p3 = f3 > e3;
+            if ((n1 || n2 || n3) && (p1 || p2 || p3)) continue;
+            if ((n1 && n2 && n3) || (p1 && p2 && p3)) return t;
+        }
         const double2 a = __ldg(A.tri + 3 * t), b = __ldg(A.tri + 3 * t + 1), c = __ldg(A.tri + 3 * t + 2);
         const double d1 = __dsub_rn(__dmul_rn(__dsub_rn(r, b.x), __dsub_rn(a.y, b.y)), __dmul_rn(__dsub_rn(a.x, b.x), __dsub_rn(z, b.y)));
         const double d2 = __dsub_rn(__dmul_rn(__dsub_rn(r, c.x), __dsub_rn(b.y, c.y)), __dmul_rn(__dsub_rn(b.x, c.x), __dsub_rn(z, c.y)));
@@ -393,46 +412,55 @@ __device__ __forceinline__ double lorentz_cdf(const double2* __restrict__ tab, d
 // the spectrum follows from one dense contraction mom . phi after the ray is finished (cb2_contract.cu).
 // Lanes = samples.  Consecutive samples mostly share the node interval, so the warp loops over the distinct intervals it
 // holds and transpose-reduces the 4 n_z (<= 32) values of each; lane 4 z + k then owns node (i - 1 + k) of charge z.
-template <typename CntT, int AXONLY = 0>
-__device__ __forceinline__ void sample_brems_moments(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te,
-                                                     double* __restrict__ mom, int lane, CntT& brems_evals, unsigned& ood) {
+// state part (per unit trapezium weight): node coordinate f (0: the sample does not emit) and U_z = pref ne/sqrt(Te) e^{-x_ref/Te} N_z
+template <int AXONLY>
+__device__ __forceinline__ void brems_state(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te, float& f,
+                                            float (&U)[CB2_MAX_BREMS_Z], unsigned& ood) {
     const DevBrems& B = S.brems;
-    const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+    f = 0.f;
+#pragma unroll
+    for (int z = 0; z < CB2_MAX_BREMS_Z; z++) U[z] = 0.f;
+    if (!(ne > 0.f && te > 0.f)) return;
+    float tc = te;
+    if (tc < B.te_lo || tc > B.te_hi) { ood++; tc = fminf(fmaxf(tc, B.te_lo), B.te_hi); }
+    const float tau = 1.0f / tc;
+    const float sv = fmaf(tau, B.inv_tau_c, -logf(tc));                 // ln(tau) + tau/tau_c
+    f = fminf(fmaxf((sv - B.s0) * B.inv_ds, 1.0f), (float)(B.n_nodes - 3) + 0.9999f);
+    const float W = B.pref * ne * rsqrtf(te) * __expf(-B.x_ref * tau);
+    // per distinct charge: N_z = sum of the (positive) densities of the species with that charge; the species are grouped by
+    // charge on the host, so the sums need no per-species select chain
+#pragma unroll
+    for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
+        float a = 0.f;
+        for (int s = B.zstart[z]; s < B.zstart[z + 1]; s++) {
+            const float ni = eval_scalar_t<AXONLY>(S.species[B.zlist[s]].density, ctx, in.x, in.y, in.z);
+            a += fmaxf(ni, 0.f);
+        }
+        U[z] = W * a;
+    }
+}
+
+// scatter part: the warp's samples (weight w, node coordinate f >= 1, U_z) go to the ray's moments.  Lanes = samples.
+// Consecutive samples mostly share the node interval, so the warp loops over the distinct intervals it holds and
+// transpose-reduces the 4 n_z (<= 32) values of each; lane 4 z + k then owns node (i - 1 + k) of charge z.
+template <typename MomT>
+__device__ __forceinline__ void brems_scatter(const DevBrems& B, bool live, float w, float f, const float (&U)[CB2_MAX_BREMS_Z],
+                                              MomT* __restrict__ mom, int lane) {
     int node = -1;
     float val[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) val[i] = 0.f;
     if (live) {
-        float tc = te;
-        if (tc < B.te_lo || tc > B.te_hi) { ood++; tc = fminf(fmaxf(tc, B.te_lo), B.te_hi); }
-        const float tau = 1.0f / tc;
-        const float sv = fmaf(tau, B.inv_tau_c, -logf(tc));                 // ln(tau) + tau/tau_c
-        float f = (sv - B.s0) * B.inv_ds;
-        f = fminf(fmaxf(f, 1.0f), (float)(B.n_nodes - 3) + 0.9999f);
         node = (int)f;
         const float t = f - (float)node;
         // cubic Lagrange weights on the nodes -1, 0, 1, 2
         const float tm1 = t - 1.0f, tm2 = t - 2.0f, tp1 = t + 1.0f;
         const float l0 = -t * tm1 * tm2 * (1.0f / 6.0f), l1 = tp1 * tm1 * tm2 * 0.5f, l2 = -tp1 * t * tm2 * 0.5f, l3 = tp1 * t * tm1 * (1.0f / 6.0f);
-        const float W = in.weight * B.pref * ne * rsqrtf(te) * __expf(-B.x_ref * tau);
-        // per distinct charge: N_z = sum of the (positive) densities of the species with that charge; the species are grouped by
-        // charge on the host, so the sums need no per-species select chain
-        float nzv[CB2_MAX_BREMS_Z];
 #pragma unroll
         for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
-            float a = 0.f;
-            for (int s = B.zstart[z]; s < B.zstart[z + 1]; s++) {
-                const float ni = eval_scalar_t<AXONLY>(S.species[B.zlist[s]].density, ctx, in.x, in.y, in.z);
-                a += fmaxf(ni, 0.f);
-            }
-            nzv[z] = a;
-        }
-#pragma unroll
-        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
-            const float v = W * nzv[z];
+            const float v = w * U[z];
             val[4 * z] = v * l0; val[4 * z + 1] = v * l1; val[4 * z + 2] = v * l2; val[4 * z + 3] = v * l3;
         }
-        brems_evals += (CntT)S.bins;
     }
     unsigned todo = __ballot_sync(FULL, live);
     while (todo) {
@@ -454,6 +482,20 @@ __device__ __forceinline__ void sample_brems_moments(const DevScene& S, const Sa
             }
         }
         const int z = lane >> 2, k = lane & 3;
-        if (z < B.n_z && part[0] != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (double)part[0]);
+        if (z < B.n_z && part[0] != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (MomT)part[0]);
     }
+}
+
+template <typename CntT, int AXONLY = 0, typename MomT = double>
+__device__ __forceinline__ void sample_brems_moments(const DevScene& S, const SampleIn& in, const AxCtx& ctx, float ne, float te,
+                                                     MomT* __restrict__ mom, int lane, CntT& brems_evals, unsigned& ood) {
+    const bool live = ne > 0.f && te > 0.f && in.weight > 0.f;
+    float f = 0.f, U[CB2_MAX_BREMS_Z];
+#pragma unroll
+    for (int z = 0; z < CB2_MAX_BREMS_Z; z++) U[z] = 0.f;
+    if (live) {
+        brems_state<AXONLY>(S, in, ctx, ne, te, f, U, ood);
+        brems_evals += (CntT)S.bins;
+    }
+    brems_scatter(S.brems, live, in.weight, f, U, mom, lane);
 }

@@ -29,6 +29,7 @@
 // Follows: cherab/core/plasma/material.pyx:48-63, model/plasma/impact_excitation.pyx:78-100, recombination.pyx:78-100,
 // model/lineshape/gaussian.pyx:40-139, doppler.pyx:29-59, multiplet.pyx:93-117, zeeman.pyx:113-365, stark.pyx:88-348,
 // tools/equilibrium/efit.pyx:219-546, generomak/plasma/plasma.py:580-638, Raysect's NumericalIntegrator.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -684,13 +685,20 @@ __global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile i
 #endif
 // FEAT = 0: plasma line models and Bremsstrahlung only (the benchmark's scene); FEAT = 1 adds the beam frame / BeamCXLine,
 // ThermalCXLine and TotalRadiatedPower branches (kept out of the common instance: they cost registers and instruction cache)
-template <int NW, int MOM, int AXONLY, int FEAT>
+#define CB2_FIX_WINDOW 32                              // groups per list round of the fix-up pass (at most 1024 flagged samples)
+template <int NW, int MOM, int AXONLY, int FEAT, int FIX>
 __global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, double* __restrict__ flat_out,
-             int count_samples, int dbg_skip) {
+             int count_samples, int dbg_skip, const unsigned* __restrict__ gblend) {
+    // FIX: fix-up pass behind state_fast_kernel — only the samples flagged there (blend zone, gblend) are evaluated, ONE WARP PER
+    // RAY: the warp gathers the flagged samples of CB2_FIX_WINDOW groups into an ordered list and takes 32 of them at a time
+    // (lanes = flagged samples of any group: no lane idles beside a partly flagged group, no block barrier, every warp of the
+    // SM busy); their record entries are overwritten one by one and their moments added to the ray's row in HBM (float atomics
+    // issued by one warp in program order: reproducible)
     extern __shared__ double smem_d[];
     __shared__ double flat_s;
+    __shared__ int fix_list_s[FIX ? NW * CB2_FIX_WINDOW * 32 : 1];
     // the flattened scene (13 KB of model / species / table descriptors, indexed with run-time model and species numbers)
     // is staged in shared memory: indexed constant-bank loads miss the small constant cache and stall (ncu: short scoreboard)
     __shared__ __align__(16) unsigned char scene_s[sizeof(DevScene)];
@@ -703,13 +711,16 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
     const DevScene& S = *reinterpret_cast<const DevScene*>(scene_s);
     const int k_pad = MOM ? Sparam.brems.k_pad : 0;
     double* mom = smem_d;
-    if (MOM)
+    if (MOM && !FIX)
         for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
     if (tid == 0) flat_s = 0.0;
     float flat_acc = 0.f;
     __syncthreads();
 
-    const int64_t ray = blockIdx.x;
+    const int64_t ray = FIX ? (int64_t)blockIdx.x * NW + warp : blockIdx.x;
+    if (FIX && ray >= rays.n_rays) return;                // (no block barrier follows in the fix-up mode)
+    int* const fix_list = fix_list_s + (FIX ? warp * CB2_FIX_WINDOW * 32 : 0);
+    float* const mom_row = MOM ? mom_out + (size_t)ray * k_pad : nullptr;
     const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
     const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
     SampleIn in;
@@ -739,15 +750,49 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
         const int iv = sgm.iv;
         if (iv <= 0) continue;
         const float hf = (float)sgm.h;
-        if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
+        if (tid == 0 && !FIX) n_samples += (unsigned long long)iv + 1ull;
         const int n_groups = iv / 32 + 1;
         int first = (warp - g_rot) % NW;
         if (first < 0) first += NW;
         g_rot = (g_rot + n_groups) % NW;
 
-        for (int g = first; g < n_groups; g += NW) {
-            const int k = g * 32 + lane;
-            const bool active = k <= iv;
+        const int n_win = FIX ? (n_groups + CB2_FIX_WINDOW - 1) / CB2_FIX_WINDOW : 1;
+        for (int win = 0; win < n_win; win++) {
+        int it0 = first, it_end = n_groups, n_list = 0;
+        if (FIX) {
+            // ordered list of the window's flagged samples: lane l owns group win * 32 + l
+            __syncwarp();                                          // the previous round's list has been consumed
+            unsigned bm = 0;
+            const int gl = win * CB2_FIX_WINDOW + lane;
+            if (gl < n_groups) bm = __ldg(gblend + G0 + gl);
+            const int cnt = __popc(bm);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            n_list = __shfl_sync(FULL, incl, 31);
+            if (!n_list) continue;
+            int at = incl - cnt;
+            while (bm) {
+                const int b = __ffs(bm) - 1;
+                bm &= bm - 1;
+                fix_list[at++] = gl * 32 + b;
+            }
+            __syncwarp();
+            it0 = 0; it_end = (n_list + 31) >> 5;
+        }
+        for (int it = it0; it < it_end; it += FIX ? 1 : NW) {
+            int k = it * 32 + lane;
+            bool sel = true;
+            if (FIX) {
+                sel = k < n_list;
+                k = sel ? fix_list[k] : 0;
+            }
+            const int g = FIX ? (k >> 5) : it;                     // FIX: per lane
+            const int rl = FIX ? (k & 31) : lane;                  // the sample's slot in its group's record rows
+            const bool active = k <= iv && sel;
             const double tk = __dmul_rn((double)k, sgm.h);
             double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
                    pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
@@ -778,9 +823,12 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
             const bool live = has_beam ? (in.weight > 0.f && in.donor > 0.f) : (ne > 0.f && te > 0.f && in.weight > 0.f);
             const unsigned live_mask = __ballot_sync(FULL, live);
             const int64_t G = G0 + g;
-            if (lane == 0) gmask[G] = live_mask;
+            if (lane == 0 && !FIX) gmask[G] = live_mask;
             if (!live_mask) continue;                              // the whole group is in vacuum
-            if (MOM && dbg_skip != 2) sample_brems_moments<unsigned, AXONLY>(S, in, ctx, ne, te, mom, lane, n_brems, ood);
+            if (MOM && dbg_skip != 2) {
+                if (FIX) sample_brems_moments<unsigned, AXONLY>(S, in, ctx, ne, te, mom_row, lane, n_brems, ood);
+                else sample_brems_moments<unsigned, AXONLY>(S, in, ctx, ne, te, mom, lane, n_brems, ood);
+            }
             LineCache lc;
             lc.cur = -1; lc.ni = lc.ts = lc.vd = 0.f; lc.have_b = false; lc.bm = lc.cos_sqr = 0.f; lc.grid = -2;
             lc.lne = lc.lte = 0.f;
@@ -788,7 +836,7 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                 lc.lne = log10f(ne) + 19.0f;                       // densities are stored in units of 1e19 m^-3
                 lc.lte = log10f(te);
             }
-            float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
+            float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + rl;
             for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
@@ -817,8 +865,8 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                         float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
                         // component order: sigma0, sigma1 +-, pi2 +-, pi3 +-, pi4 +-  (mse.pyx:113-133)
                         const float off = kc == 0 ? 0.f : (float)((kc + 1) >> 1) * ((kc & 1) ? 1.f : -1.f);
-                        r[64] = amp * mamp[kc];
-                        if (any_amp) { r[0] = S.comps[M.comp0 + kc].c0_frac + shift_b + off * split_b; r[32] = X.mse_sigma_b; }
+                        if (!FIX || sel) r[64] = amp * mamp[kc];
+                        if (FIX ? sel : any_amp) { r[0] = S.comps[M.comp0 + kc].c0_frac + shift_b + off * split_b; r[32] = X.mse_sigma_b; }
                     }
                     continue;
                 }
@@ -833,10 +881,11 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                     float* r = grec + (size_t)(M.comp0 + kc) * REC_FLOATS_PER_COMP;
                     int type; float cf = 0.f, width = 0.f, amp = 0.f;
                     if (any_on) model_component(S, M, kc, mc, type, cf, width, amp);
-                    r[64] = amp;
-                    if (__any_sync(FULL, amp > 0.f)) { r[0] = cf; r[32] = width; }
+                    if (!FIX || sel) r[64] = amp;
+                    if (FIX ? sel : __any_sync(FULL, amp > 0.f)) { r[0] = cf; r[32] = width; }
                 }
             }
+        }
         }
         G0 += n_groups;
     }
@@ -845,11 +894,9 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
         for (int off = 16; off > 0; off >>= 1) flat_acc += __shfl_down_sync(FULL, flat_acc, off);
         if (lane == 0 && flat_acc != 0.f) atomicAdd(&flat_s, (double)flat_acc);
     }
-    if (MOM || (FEAT && flat_out)) __syncthreads();
-    if (MOM) {
-        float* row = mom_out + (size_t)ray * k_pad;
-        for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
-    }
+    if (!FIX && (MOM || (FEAT && flat_out))) __syncthreads();
+    if (MOM && !FIX)
+        for (int i = tid; i < k_pad; i += NW * 32) mom_row[i] = (float)mom[i];
     if (FEAT && flat_out && tid == 0) flat_out[ray] = flat_s;
     if (stats) {
         unsigned long long nb = n_brems, oodl = ood;
@@ -863,6 +910,377 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
         }
         if (tid == 0 && n_samples && count_samples) atomicAdd(stats + 0, n_samples);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1a, table-driven (DevMemo): the state of a core sample (blend weight 1) is a row interpolated on the psi_n grid, that
+// of an edge sample (weight 0) the row of its triangle; what stays per sample is the geometry — position, (R, Z), psi_n,
+// triangle, direction of the poloidal field, v.d — the record rows and the moment scatter.  Blend-zone samples are only
+// flagged (gblend) and evaluated by state_kernel in its fix-up mode.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lerp4(const float4 a, const float4 b, float t) {
+    return make_float4(fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y), fmaf(t, b.z - a.z, a.z), fmaf(t, b.w - a.w, a.w));
+}
+
+// one table row from the generic evaluation code: which = 0 triangle `i`, 1 psi_n = (i + frac) / core_scale
+__device__ __forceinline__ void memo_row(const DevScene& S, const DevMemo& FM, int which, int i, float frac, float* row) {
+    AxCtx c;
+    c.R = c.Z = 0.f; c.cphi = 1.f; c.sphi = 0.f; c.br = c.bt = c.bz = 0.f; c.b_outside = false;
+    if (which == 0) {
+        c.m = 0.f; c.tri = i; c.tri_c = i; c.we = 1.f; c.wc = 0.f; c.ci = 0; c.ct = 0.f; c.psi = 2.f; c.in_lcfs = false;
+    } else {
+        const float psi = fminf(((float)i + frac) / FM.core_scale, FM.psi_max);
+        c.m = 1.f; c.tri = -1; c.tri_c = 0; c.we = 0.f; c.wc = 1.f; c.psi = psi; c.in_lcfs = true;
+        locate1d(S.ax.core, psi, c.ci, c.ct);
+    }
+    SampleIn in;
+    in.x = in.y = in.z = 0.f; in.dx = in.dy = 0.f; in.dz = 1.f; in.weight = 1.f; in.donor = 0.f; in.bvx = in.bvy = in.bvz = 0.f;
+    for (int k = 0; k < 4 * FM.row_f4; k++) row[k] = 0.f;
+    const float ne = eval_blend(S.ne, c), te = eval_blend(S.te, c);
+    const bool live = ne > 0.f && te > 0.f;
+    unsigned ood = 0;
+    for (int s = 0; s < FM.n_sp; s++) {
+        const DevSpecies& sp = S.species[FM.sp_species[s]];
+        const float ts = eval_blend(sp.temperature, c);
+        row[4 * s] = ts > 0.f ? sqrtf(ts) : 0.f;
+        const DevVector& f = sp.velocity;
+        if (FM.sp_const[s]) continue;
+        if (which == 0) { row[4 * s + 1] = f.c[1]; row[4 * s + 2] = f.c[0]; row[4 * s + 3] = f.c[2]; }
+        else {
+            row[4 * s + 1] = f.vtor ? horner4(__ldg(f.vtor + c.ci), c.ct) : 0.f;
+            row[4 * s + 2] = f.vpol ? horner4(__ldg(f.vpol + c.ci), c.ct) : 0.f;
+            row[4 * s + 3] = f.vnorm ? horner4(__ldg(f.vnorm + c.ci), c.ct) : 0.f;
+        }
+    }
+    LineCache lc;
+    lc.lne = lc.lte = 0.f;
+    if (live) { lc.lne = log10f(ne) + 19.0f; lc.lte = log10f(te); }
+    for (int l = 0; l < FM.n_lines; l++) {
+        lc.cur = -1; lc.ni = lc.ts = lc.vd = 0.f; lc.have_b = false; lc.bm = lc.cos_sqr = 0.f; lc.grid = -2;
+        ModelCtx mc;
+        model_setup<1, 0>(S, S.models[FM.lines[l].model], in, c, ne, te, live, lc, mc, ood);
+        row[4 * FM.off_amp + l] = mc.on ? mc.amp : 0.f;
+    }
+    float f = 0.f, U[CB2_MAX_BREMS_Z];
+#pragma unroll
+    for (int z = 0; z < CB2_MAX_BREMS_Z; z++) U[z] = 0.f;
+    if (FM.has_brems && live) brems_state<1>(S, in, c, ne, te, f, U, ood);
+    float* b = row + 4 * FM.off_brems;
+    b[0] = f; b[1] = (float)ood;
+    for (int z = 0; z < FM.n_z; z++) b[2 + z] = U[z];
+}
+
+// mode 0: write rows [0, n) of table `which`; mode 2: column maxima of |entry| (float bits, atomicMax); mode 1 (core only):
+// largest mid-interval deviation of the interpolated row from the generic evaluation, relative to the larger knot value — but
+// not less than 1e-5 of the column's maximum: an entry that small against its own values elsewhere cannot be seen in a line
+// integral — (node coordinate: 0.05 x absolute), as (error bits << 32 | entry << 24 | row) via atomicMax
+__global__ void memo_rows_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevMemo FM, int which, int n, int mode,
+                                 float4* __restrict__ tab, unsigned* __restrict__ colmax, unsigned long long* __restrict__ err_key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* t = reinterpret_cast<float*>(tab) + (size_t)i * 4 * FM.row_f4;
+    if (mode == 2) {
+        for (int k = 0; k < 4 * FM.row_f4; k++) atomicMax(colmax + k, __float_as_uint(fabsf(t[k])));
+        return;
+    }
+    float row[64];
+    memo_row(S, FM, which, i, mode ? 0.5f : 0.f, row);
+    if (!mode) {
+        for (int k = 0; k < 4 * FM.row_f4; k++) t[k] = row[k];
+        return;
+    }
+    const float* u = t + 4 * FM.row_f4;
+    float worst = 0.f;
+    int kw = 0;
+    for (int k = 0; k < 4 * FM.row_f4; k++) {
+        if (k == 4 * FM.off_brems + 1) continue;                       // out-of-domain count: taken from the lower knot
+        const float a = t[k], b = u[k], v = 0.5f * (a + b), d = fabsf(v - row[k]);
+        float e;
+        if (k == 4 * FM.off_brems) e = (a >= 1.f && b >= 1.f) ? 0.05f * d : 0.f;   // d ln(spectrum) / d f = ds d ln(Phi) / ds < 0.05
+        else e = d / (fmaxf(fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(row[k])), 1e-5f * __uint_as_float(colmax[k])) + 1e-30f);
+        if (e > worst) { worst = e; kw = k; }
+    }
+    atomicMax(err_key, ((unsigned long long)__float_as_uint(worst) << 32) | ((unsigned long long)(kw & 255) << 24) | (unsigned)(i & 0xffffff));
+}
+
+template <int NW, int MOM, int MINB, int NSP>
+__global__ void __launch_bounds__(NW * 32, MINB)
+state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevMemo FM, DevRays rays, const int64_t* __restrict__ gbase,
+                  unsigned* __restrict__ gmask, unsigned* __restrict__ gblend, float* __restrict__ rec,
+                  unsigned long long* __restrict__ stats, float* __restrict__ mom_out, int count_samples) {
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_pad = MOM ? S.brems.k_pad : 0;
+    double* mom = smem_d;
+    if (MOM) {
+        for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
+        __syncthreads();
+    }
+    const DevAxisym& A = S.ax;
+    const int64_t ray = blockIdx.x;
+    const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+    const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
+    float dx, dy, dz;
+    {
+        const double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
+                     d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        const double dl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        dx = (float)(d0 / dl); dy = (float)(d1 / dl); dz = (float)(d2 / dl);
+    }
+    float vdc[NSP];
+#pragma unroll
+    for (int s = 0; s < NSP; s++) vdc[s] = FM.sp_v[s][0] * dx + FM.sp_v[s][1] * dy + FM.sp_v[s][2] * dz;
+    unsigned long long n_samples = 0;
+    unsigned n_brems = 0, ood = 0;
+    const int n_comp = S.n_comp, row_f4 = FM.row_f4;
+    const float4* const row0 = FM.edge ? FM.edge : FM.core;
+
+    int64_t G0 = gbase[ray];
+    int g_rot = 0;
+    for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+        const SegGeom sgm = segment_geometry(S.w2p, S.step, S.min_samples, ox, oy, oz, dwx, dwy, dwz, rays.seg_t0[sg], rays.seg_t1[sg]);
+        const int iv = sgm.iv;
+        if (iv <= 0) continue;
+        const float hf = (float)sgm.h;
+        if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
+        const int n_groups = iv / 32 + 1;
+        int first = (warp - g_rot) % NW;
+        if (first < 0) first += NW;
+        g_rot = (g_rot + n_groups) % NW;
+
+        for (int g = first; g < n_groups; g += NW) {
+            const int k = g * 32 + lane;
+            const bool active = k <= iv;
+            const double tk = __dmul_rn((double)k, sgm.h);
+            const double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
+                         pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
+            float w = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
+            // (R, Z, phi) as ax_setup has them
+            const double r64 = __dsqrt_rn(__dadd_rn(__dmul_rn(pxd, pxd), __dmul_rn(pyd, pyd)));
+            const float R = (float)r64, Z = (float)pzd;
+            const float inv_r = R > 0.f ? 1.0f / R : 0.f;
+            const float cphi = R > 0.f ? (float)pxd * inv_r : 1.f, sphi = (float)pyd * inv_r;
+            int cls = 0;                                            // 0 vacuum, 1 table row, 2 blend zone
+            const float4 *pa = row0, *pb = row0;
+            float t = 0.f, ebr = 0.f, ebz = 0.f;
+            if (active) {
+                float m = 0.f, psi = 0.f;
+                Cell2 cell;
+                if (polygon_contains(A, R, Z)) {
+                    cell = locate2d(A.psin, R, Z);
+                    if (!cell.inside) ood++;
+                    psi = fmaxf(eval2d(A.psin, cell), 0.f);
+                    if (psi <= 1.0f) {
+                        m = A.mask_y[0];
+                        const float p = fminf(fmaxf(psi, A.mask_x[0]), A.mask_x[A.n_mask - 1]);
+                        for (int q = 0; q + 1 < A.n_mask; q++)
+                            if (p >= A.mask_x[q] && p <= A.mask_x[q + 1]) {
+                                m = A.mask_y[q] + (p - A.mask_x[q]) / (A.mask_x[q + 1] - A.mask_x[q]) * (A.mask_y[q + 1] - A.mask_y[q]);
+                                break;
+                            }
+                    }
+                }
+                if (m >= 1.0f && FM.core_n > 0) {
+                    cls = 1;
+                    const float fi = fminf(psi, FM.psi_max) * FM.core_scale;
+                    const int i0 = min((int)fi, FM.core_n - 1);
+                    t = fi - (float)i0;
+                    pa = FM.core + (size_t)i0 * row_f4;
+                    pb = pa + row_f4;
+                    if (S.need_pol) {
+                        const float br = -eval2d(A.dpsi_dz, cell), bz = eval2d(A.dpsi_dr, cell);
+                        const float n2 = br * br + bz * bz;
+                        if (n2 > 0.f) { const float inv = rsqrtf(n2); ebr = br * inv; ebz = bz * inv; }
+                    }
+                } else if (m > 0.f) {
+                    cls = 2;
+                } else {
+                    const int tri = mesh_locate(A, r64, pzd);
+                    if (tri >= 0) { cls = 1; pa = pb = FM.edge + (size_t)tri * row_f4; ebr = 1.f; }
+                }
+            }
+            const unsigned live_mask = __ballot_sync(FULL, cls != 0 && w > 0.f);
+            const unsigned blend_mask = __ballot_sync(FULL, cls == 2 && w > 0.f);
+            const int64_t G = G0 + g;
+            if (lane == 0) { gmask[G] = live_mask; gblend[G] = blend_mask; }
+            if (!live_mask) continue;
+            if (cls != 1) w = 0.f;
+            // species block: sqrt(Ts) and v.d
+            const float aa = cphi * dx + sphi * dy, bb = cphi * dy - sphi * dx;
+            float sq[NSP], vd[NSP];
+#pragma unroll
+            for (int s = 0; s < NSP; s++) {
+                sq[s] = 0.f; vd[s] = 0.f;
+                if (s < FM.n_sp) {
+                    const float4 q = lerp4(__ldg(pa + s), __ldg(pb + s), t);
+                    sq[s] = q.x;
+                    const float cr = ebr * q.z - ebz * q.w, cz = ebz * q.z + ebr * q.w;
+                    vd[s] = FM.sp_const[s] ? vdc[s] : fmaf(cr, aa, fmaf(q.y, bb, cz * dz));
+                }
+            }
+            float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
+            for (int l4 = 0; l4 < FM.n_lines; l4 += 4) {
+                const float4 q = lerp4(__ldg(pa + FM.off_amp + (l4 >> 2)), __ldg(pb + FM.off_amp + (l4 >> 2)), t);
+                const float av[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (l4 + j >= FM.n_lines) break;
+                    const MemoLine& L = FM.lines[l4 + j];
+                    float sqs = sq[0], vds = vd[0];
+#pragma unroll
+                    for (int s = 1; s < NSP; s++)
+                        if (L.slot == s) { sqs = sq[s]; vds = vd[s]; }
+                    float amp = av[j] * w;
+                    const float width = L.sigma_coef * sqs;
+                    if (!(amp > 0.f) || !(sqs > 0.f)) amp = 0.f;
+                    const bool any_on = __any_sync(FULL, amp > 0.f);
+                    float* r = grec + L.rec_off;
+                    if (L.shape == CB2_SHAPE_GAUSSIAN) {
+                        r[64] = amp;
+                        if (any_on) { r[0] = fmaf(L.shift_coef, vds, L.c0_frac); r[32] = width; }
+                    } else {
+                        const float dop = vds * L.inv_c;
+                        for (int kc = 0; kc < L.ncomp; kc++, r += REC_FLOATS_PER_COMP) {       // multiplet.pyx:108-115
+                            r[64] = amp * __ldg(L.mult_ratio + kc);
+                            if (any_on) { r[0] = S.comps[L.comp0 + kc].c0_frac + __ldg(L.mult_lambda + kc) * dop * L.inv_delta; r[32] = width; }
+                        }
+                    }
+                }
+            }
+            {
+                // Bremsstrahlung block (and the out-of-domain count of the row's state)
+                const float4 a0 = __ldg(pa + FM.off_brems);
+                if (w > 0.f) ood += (unsigned)a0.y;
+                if (MOM) {
+                    const float4 q0 = lerp4(a0, __ldg(pb + FM.off_brems), t);
+                    const float4 q1 = lerp4(__ldg(pa + FM.off_brems + 1), __ldg(pb + FM.off_brems + 1), t);
+                    float U[CB2_MAX_BREMS_Z] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0.f, 0.f};
+                    if (FM.n_z > 6) {
+                        const float4 q2 = lerp4(__ldg(pa + FM.off_brems + 2), __ldg(pb + FM.off_brems + 2), t);
+                        U[6] = q2.x; U[7] = q2.y;
+                    }
+                    const bool lb = w > 0.f && q0.x >= 1.0f;
+                    if (lb) n_brems += (unsigned)S.bins;
+                    brems_scatter(S.brems, lb, w, q0.x, U, mom, lane);
+                }
+            }
+        }
+        G0 += n_groups;
+    }
+    if (MOM) {
+        __syncthreads();
+        float* row = mom_out + (size_t)ray * k_pad;
+        for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
+    }
+    if (stats) {
+        unsigned long long nb = n_brems, oodl = ood;
+        for (int off = 16; off > 0; off >>= 1) {
+            nb += __shfl_down_sync(FULL, nb, off);
+            oodl += __shfl_down_sync(FULL, oodl, off);
+        }
+        if (lane == 0) {
+            if (nb) atomicAdd(stats + 3, nb);
+            if (oodl) atomicAdd(stats + 5, oodl);
+        }
+        if (tid == 0 && n_samples && count_samples) atomicAdd(stats + 0, n_samples);
+    }
+}
+
+// state tables of an eligible scene: plasma line models with Gaussian / multiplet shapes (+ Bremsstrahlung moments) over fields
+// that are all AXISYM_BLEND.  CB2_STATE_MEMO=0 keeps the generic kernel (tests run both).
+int cb2_memo_build(cb2_scene* sc) {
+    DevMemo& FM = sc->memo;
+    memset(&FM, 0, sizeof FM);
+    const DevScene& S = sc->host;
+    if (const char* e = getenv("CB2_STATE_MEMO")) if (atoi(e) == 0) return CB2_OK;
+    if (!sc->warp_kernel || !sc->ax_only || sc->feat || !S.ax.present || S.beam.present || S.need_b) return CB2_OK;
+    int n_lines = 0, n_sp = 0;
+    for (int m = 0; m < S.n_models; m++) {
+        const DevModel& M = S.models[m];
+        if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
+        if (M.kind != CB2_MODEL_EXCITATION_LINE && M.kind != CB2_MODEL_RECOMBINATION_LINE) return CB2_OK;
+        if (M.shape != CB2_SHAPE_GAUSSIAN && M.shape != CB2_SHAPE_MULTIPLET) return CB2_OK;
+        if (n_lines == CB2_MEMO_MAX_LINES) return CB2_OK;
+        int slot = -1;
+        for (int s = 0; s < n_sp; s++) if (FM.sp_species[s] == M.species) slot = s;
+        if (slot < 0) {
+            if (n_sp == CB2_MEMO_MAX_SP) return CB2_OK;
+            slot = n_sp++;
+            FM.sp_species[slot] = M.species;
+            const DevVector& v = S.species[M.species].velocity;
+            FM.sp_const[slot] = v.kind == CB2_FIELD_CONSTANT;
+            for (int k = 0; k < 3; k++) FM.sp_v[slot][k] = FM.sp_const[slot] ? v.c[k] : 0.f;
+        }
+        MemoLine& L = FM.lines[n_lines++];
+        L.model = m; L.slot = slot; L.comp0 = M.comp0; L.ncomp = M.ncomp; L.shape = M.shape;
+        L.sigma_coef = M.sigma_coef; L.wavelength = M.wavelength; L.inv_c = M.inv_c; L.inv_delta = M.inv_delta;
+        L.rec_off = M.comp0 * REC_FLOATS_PER_COMP;
+        L.c0_frac = S.comps[M.comp0].c0_frac;
+        L.shift_coef = M.wavelength * M.inv_c * M.inv_delta;
+        L.mult_ratio = M.mult_ratio; L.mult_lambda = M.mult_lambda;
+    }
+    const bool brems = S.brems.present && S.brems.mode == 3;
+    if (S.brems.present && !brems) return CB2_OK;
+    if (n_lines == 0 && !brems) return CB2_OK;
+    FM.n_lines = n_lines; FM.n_sp = n_sp; FM.has_brems = brems; FM.n_z = brems ? S.brems.n_z : 0;
+    FM.off_amp = n_sp;
+    FM.off_brems = n_sp + (n_lines + 3) / 4;
+    FM.row_f4 = FM.off_brems + (FM.n_z > 6 ? 3 : 2);
+    // the psi_n grid ends at the last mask knot with full core weight (0.94 on Generomak, plasma.py:610): beyond it the rows would
+    // never be used, and the profiles' steep fall towards the separatrix would only force a finer grid
+    FM.psi_max = 0.f;
+    for (int k = 0; k < S.ax.n_mask; k++)
+        if (S.ax.mask_y[k] >= 1.0f) FM.psi_max = std::max(FM.psi_max, std::min(S.ax.mask_x[k], 1.0f));
+    const bool want_core = FM.psi_max > 0.f;
+    const size_t row_bytes = (size_t)FM.row_f4 * sizeof(float4);
+    float4* edge = nullptr;
+    float4* core = nullptr;
+    unsigned long long* err_dev = nullptr;     // [0] error key, then the column maxima (unsigned[64])
+    int rc = CB2_OK;
+    do {
+        if (S.ax.n_tri > 0) {
+            if ((rc = cb2_cuda_check(cudaMalloc((void**)&edge, row_bytes * S.ax.n_tri), "cudaMalloc(edge state table)")) != CB2_OK) break;
+            memo_rows_kernel<<<(S.ax.n_tri + 127) / 128, 128>>>(S, FM, 0, S.ax.n_tri, 0, edge, nullptr, nullptr);
+        }
+        if ((rc = cb2_cuda_check(cudaMalloc((void**)&err_dev, sizeof(unsigned long long) + 64 * sizeof(unsigned)), "cudaMalloc")) != CB2_OK) break;
+        unsigned* colmax = reinterpret_cast<unsigned*>(err_dev + 1);
+        int n = 32768;
+        if (const char* e = getenv("CB2_MEMO_ROWS")) n = std::max(256, atoi(e));
+        const float tol = 4e-6f;
+        for (; want_core; n *= 2) {
+            FM.core_n = n;
+            FM.core_scale = (float)n / FM.psi_max;
+            if ((rc = cb2_cuda_check(cudaMalloc((void**)&core, row_bytes * (size_t)(n + 1)), "cudaMalloc(core state table)")) != CB2_OK) break;
+            memo_rows_kernel<<<(n + 1 + 127) / 128, 128>>>(S, FM, 1, n + 1, 0, core, nullptr, nullptr);
+            if ((rc = cb2_cuda_check(cudaMemset(err_dev, 0, sizeof(unsigned long long) + 64 * sizeof(unsigned)), "cudaMemset")) != CB2_OK) break;
+            memo_rows_kernel<<<(n + 1 + 127) / 128, 128>>>(S, FM, 1, n + 1, 2, core, colmax, nullptr);
+            memo_rows_kernel<<<(n + 127) / 128, 128>>>(S, FM, 1, n, 1, core, colmax, err_dev);
+            unsigned long long key = 0;
+            if ((rc = cb2_cuda_check(cudaMemcpy(&key, err_dev, sizeof key, cudaMemcpyDeviceToHost), "state table check")) != CB2_OK) break;
+            const unsigned bits = (unsigned)(key >> 32);
+            memcpy(&sc->memo_err, &bits, sizeof bits);
+            sc->memo_err_at = (int64_t)(key & 0xffffffffull);
+            if (getenv("CB2_MEMO_DEBUG")) fprintf(stderr, "state table: %d intervals, worst mid-interval error %.3g (entry %d, row %d)\n", n, sc->memo_err, (int)((key >> 24) & 255), (int)(key & 0xffffff));
+            if (sc->memo_err <= tol) break;
+            cudaFree(core);
+            core = nullptr;
+            if (n >= 262144) { FM.core_n = 0; break; }          // no acceptable table: core samples take the generic kernel too
+        }
+        if (rc != CB2_OK) break;
+        rc = cb2_cuda_check(cudaDeviceSynchronize(), "state tables");
+    } while (0);
+    if (err_dev) cudaFree(err_dev);
+    if (rc != CB2_OK) {
+        if (edge) cudaFree(edge);
+        if (core) cudaFree(core);
+        memset(&FM, 0, sizeof FM);
+        return rc;
+    }
+    FM.edge = edge;
+    FM.core = core;
+    if (!FM.edge && !FM.core) { memset(&FM, 0, sizeof FM); return CB2_OK; }
+    FM.enabled = 1;
+    return CB2_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1028,23 +1446,47 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         // K1a
         {
             const size_t smem = moments ? (size_t)B.k_pad * sizeof(double) : 0;
-#define CB2_STATE(MOM, AX, FT)                                                                                                    \
+#define CB2_STATE(MOM, AX, FT, FX, GB)                                                                                               \
     do {                                                                                                                          \
-        auto kern = state_kernel<4, MOM, AX, FT>;                                                                                 \
+        auto kern = state_kernel<4, MOM, AX, FT, FX>;                                                                             \
         if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom,          \
-                                                                  S.has_flat ? sc->flat : nullptr, count_samples, dbg);           \
+        kern<<<dim3((unsigned)((FX) ? (sub.n_rays + 3) / 4 : sub.n_rays)), dim3(128), (FX) ? 0 : smem, st>>>(                     \
+            S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, S.has_flat ? sc->flat : nullptr, (GB) ? 0 : count_samples, dbg, GB); \
     } while (0)
-            const int sel = (moments ? 4 : 0) | (sc->ax_only ? 2 : 0) | (sc->feat ? 1 : 0);
-            switch (sel) {
-            case 0: CB2_STATE(0, 0, 0); break;
-            case 1: CB2_STATE(0, 0, 1); break;
-            case 2: CB2_STATE(0, 1, 0); break;
-            case 3: CB2_STATE(0, 1, 1); break;
-            case 4: CB2_STATE(1, 0, 0); break;
-            case 5: CB2_STATE(1, 0, 1); break;
-            case 6: CB2_STATE(1, 1, 0); break;
-            default: CB2_STATE(1, 1, 1); break;
+            if (sc->memo.enabled) {
+                // table-driven state kernel, then the generic kernel on the blend-zone samples it flagged
+                if ((rc = reserve(&sc->gblend, &sc->gblend_bytes, (size_t)std::max<int64_t>(n_groups, 1) * sizeof(unsigned), st)) != CB2_OK) return rc;
+#define CB2_FAST(MOM, MINB)                                                                                                      \
+    do {                                                                                                                          \
+        auto kern = sc->memo.n_sp <= 2 ? state_fast_kernel<4, MOM, MINB, 2> : state_fast_kernel<4, MOM, MINB, CB2_MEMO_MAX_SP>;    \
+        if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kern<<<dim3((unsigned)sub.n_rays), dim3(128), smem, st>>>(S, sc->memo, sub, sc->gbase, sc->gmask, sc->gblend, sc->rec, stats, \
+                                                                  sc->mom, count_samples);                                       \
+    } while (0)
+                // resident CTAs per SM (register budget): CB2_FAST_MINB = 6 / 8 / 10 / 12 for experiments
+                static const int minb = getenv("CB2_FAST_MINB") ? atoi(getenv("CB2_FAST_MINB")) : 8;
+                if (moments) {
+                    if (minb <= 6) CB2_FAST(1, 6); else if (minb <= 8) CB2_FAST(1, 8); else if (minb <= 10) CB2_FAST(1, 10); else CB2_FAST(1, 12);
+                } else {
+                    if (minb <= 6) CB2_FAST(0, 6); else if (minb <= 8) CB2_FAST(0, 8); else if (minb <= 10) CB2_FAST(0, 10); else CB2_FAST(0, 12);
+                }
+#undef CB2_FAST
+                if ((rc = cb2_cuda_check(cudaGetLastError(), "state_fast_kernel launch")) != CB2_OK) return rc;
+                if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[5], st));
+                if (moments) CB2_STATE(1, 1, 0, 1, sc->gblend); else CB2_STATE(0, 1, 0, 1, sc->gblend);
+            } else {
+                const unsigned* none = nullptr;
+                const int sel = (moments ? 4 : 0) | (sc->ax_only ? 2 : 0) | (sc->feat ? 1 : 0);
+                switch (sel) {
+                case 0: CB2_STATE(0, 0, 0, 0, none); break;
+                case 1: CB2_STATE(0, 0, 1, 0, none); break;
+                case 2: CB2_STATE(0, 1, 0, 0, none); break;
+                case 3: CB2_STATE(0, 1, 1, 0, none); break;
+                case 4: CB2_STATE(1, 0, 0, 0, none); break;
+                case 5: CB2_STATE(1, 0, 1, 0, none); break;
+                case 6: CB2_STATE(1, 1, 0, 0, none); break;
+                default: CB2_STATE(1, 1, 1, 0, none); break;
+                }
             }
 #undef CB2_STATE
             if ((rc = cb2_cuda_check(cudaGetLastError(), "state_kernel launch")) != CB2_OK) return rc;
@@ -1073,6 +1515,11 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
                 float ms = 0.f;
                 CB2_CUDA(cudaEventElapsedTime(&ms, sc->prof_ev[i], sc->prof_ev[i + 1]));
                 sc->prof_ms[slot[i]] += ms;
+            }
+            if (sc->memo.enabled) {                             // the fix-up pass's share of the state time
+                float ms = 0.f;
+                CB2_CUDA(cudaEventElapsedTime(&ms, sc->prof_ev[5], sc->prof_ev[2]));
+                sc->prof_fixup_ms += ms;
             }
             sc->prof_launches[3] += 2; sc->prof_launches[0] += 1; sc->prof_launches[1] += 1; sc->prof_launches[2] += moments ? 1 : 0;
         }

@@ -98,6 +98,7 @@ struct DevAxisym {
     const int* cell_start;
     const int* cell_tris;
     const double2* tri;              // [n_tri*3] fp64 vertices: the containment test must decide exactly like the fp64 reference
+    const float4* trif;              // [n_tri*2] the same vertices rounded to fp32 (sign filter in front of the exact test)
     double mx0_d, my0_d, inv_cx_d, inv_cy_d;
 };
 
@@ -267,6 +268,39 @@ struct alignas(16) DevScene {
 
 static_assert(sizeof(DevScene) % 16 == 0, "DevScene is copied to shared memory as uint4");
 
+// ---- state tables ("memo"): in a scene whose scalar fields are all AXISYM_BLEND the plasma state at a sample is a
+// function of the mesh triangle alone where the blend weight is 0 (edge) and of psi_n alone where it is 1 (core).  Everything the
+// line records and the Bremsstrahlung moments need from the state is tabulated once per scene by the generic evaluation code:
+// one row per triangle (exact) and one row per knot of a fine uniform psi_n grid (linear interpolation, refined until the
+// mid-interval error against the generic evaluation is below 4e-6).  Samples in the blend zone take the generic kernel.
+// Row layout (float4 units): [n_sp x (sqrt(Ts), vtor, vpol, vnorm)] [ceil(n_lines / 4) x amplitudes per unit weight]
+// [(f, ood, U0, U1) (U2..U5) (U6, U7, -, -)]; on edge rows the velocity slots hold (v_phi, v_R, v_Z) of the constant edge vector.
+#define CB2_MEMO_MAX_LINES 16
+#define CB2_MEMO_MAX_SP 4
+struct MemoLine {
+    int model, slot, comp0, ncomp, shape;
+    int rec_off;                             // comp0 * floats per component record
+    float c0_frac;                           // fractional bin position of the (first) component's rest wavelength
+    float shift_coef;                        // wavelength / (c delta): Doppler shift in bins per m/s of v.d
+    float sigma_coef, wavelength, inv_c, inv_delta;
+    const float* mult_ratio;
+    const float* mult_lambda;
+};
+struct alignas(16) DevMemo {
+    int enabled;
+    int n_lines, n_sp, n_z, has_brems;
+    int row_f4, off_amp, off_brems;          // float4 per row, float4 offsets of the amplitude and Bremsstrahlung blocks
+    int sp_species[CB2_MEMO_MAX_SP];
+    int sp_const[CB2_MEMO_MAX_SP];           // 1: constant cartesian velocity (sp_v), nothing in the row
+    float sp_v[CB2_MEMO_MAX_SP][3];
+    int core_n;                              // intervals of the psi_n grid (core_n + 1 rows); 0: no core table
+    float core_scale;                        // core_n / psi_max
+    float psi_max;
+    const float4* core;
+    const float4* edge;                      // [n_tri] rows
+    MemoLine lines[CB2_MEMO_MAX_LINES];
+};
+
 struct DevRays {
     int64_t n_rays;
     const double* origin;
@@ -319,6 +353,11 @@ struct cb2_scene {
     size_t gbase_bytes;
     unsigned* gmask;
     size_t gmask_bytes;
+    unsigned* gblend;          // per-group masks of the samples the state tables do not cover (blend zone): generic kernel
+    size_t gblend_bytes;
+    DevMemo memo;              // state tables (memo.enabled: the table-driven state kernel runs)
+    float memo_err;            // largest mid-interval error of the accepted core table
+    int64_t memo_err_at;       // (entry << 24 | row) where it occurs
     float* rec;
     size_t rec_bytes;
     double* flat;              // per-ray wavelength-independent radiance (TotalRadiatedPower)
@@ -333,6 +372,7 @@ struct cb2_scene {
     // optional per-kernel timing (cb2_scene_profile)
     int prof_on;
     double prof_ms[4];
+    double prof_fixup_ms;      // part of prof_ms[0] spent in the generic kernel's fix-up pass behind the table-driven one
     int64_t prof_launches[4];
     cudaEvent_t prof_ev[10];
 };
@@ -366,6 +406,7 @@ size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                              unsigned long long* stats, int count_samples, cudaStream_t stream);
 int64_t cb2_warp_batch_rays(const cb2_scene* sc);
+int cb2_memo_build(cb2_scene* sc);   // state tables of an eligible scene (after the device scene is complete); frees nothing on failure
 int cb2_launch_sample_state(const cb2_scene* sc, const double* points_dev, int64_t n, double* out_dev, int points_in_plasma_space,
                             cudaStream_t stream);
 int cb2_launch_beam_sample(const cb2_scene* sc, const double* beam_points_dev, int64_t n, double* out_dev, cudaStream_t stream);
