@@ -154,8 +154,9 @@ __device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, f
     const int cls = __ldg(A.poly_cls + gi * A.pgy + gj);
     if (cls != 2) return cls == 1;
     int crossings = 0;
-    for (int i = 0; i < A.n_poly; i++) {
-        const float4 e = __ldg(A.poly + i);  // (xi, yi, yj, slope)
+    const int k1 = __ldg(A.poly_row_start + gj + 1);
+    for (int k = __ldg(A.poly_row_start + gj); k < k1; k++) {
+        const float4 e = __ldg(A.poly_row_edges + k);  // (xi, yi, yj, slope)
         if (((e.y > py) != (e.z > py)) && (px < fmaf(py - e.y, e.w, e.x))) crossings++;
     }
     return crossings & 1;

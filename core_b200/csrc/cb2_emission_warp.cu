@@ -690,7 +690,7 @@ template <int NW, int MOM, int AXONLY, int FEAT, int FIX>
 __global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, double* __restrict__ flat_out,
-             int count_samples, int dbg_skip, const unsigned* __restrict__ gblend) {
+             int count_samples, int dbg_skip, const unsigned* __restrict__ gblend, const __grid_constant__ DevMemo FM) {
     // FIX: fix-up pass behind state_fast_kernel — only the samples flagged there (blend zone, gblend) are evaluated, ONE WARP PER
     // RAY: the warp gathers the flagged samples of CB2_FIX_WINDOW groups into an ordered list and takes 32 of them at a time
     // (lanes = flagged samples of any group: no lane idles beside a partly flagged group, no block barrier, every warp of the
@@ -837,6 +837,53 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
                 lc.lte = log10f(te);
             }
             float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + rl;
+            if (FIX) {
+                // a scene with state tables holds Excitation / Recombination lines with Gaussian or multiplet shapes only (cb2_memo_build):
+                // the model loop without its generality — per species slot (ni, sqrt(Ts), v.d) once, then per line the PEC and the rows
+                float nis[CB2_MEMO_MAX_SP], sqs[CB2_MEMO_MAX_SP], vds[CB2_MEMO_MAX_SP];
+#pragma unroll
+                for (int sl = 0; sl < CB2_MEMO_MAX_SP; sl++) {
+                    nis[sl] = sqs[sl] = vds[sl] = 0.f;
+                    if (sl < FM.n_sp && live) {                       // (the context of a lane that is not live is not set up)
+                        const DevSpecies& sp = S.species[FM.sp_species[sl]];
+                        nis[sl] = eval_scalar_t<AXONLY>(sp.density, ctx, in.x, in.y, in.z);
+                        const float ts = eval_scalar_t<AXONLY>(sp.temperature, ctx, in.x, in.y, in.z);
+                        sqs[sl] = ts > 0.f ? sqrtf(ts) : 0.f;
+                        const float3 v = eval_vector(sp.velocity, ctx);
+                        vds[sl] = v.x * in.dx + v.y * in.dy + v.z * in.dz;
+                    }
+                }
+                for (int l = 0; l < FM.n_lines; l++) {
+                    const MemoLine& L = FM.lines[l];
+                    const DevModel& M = S.models[L.model];
+                    float ni = nis[0], sq = sqs[0], vd = vds[0];
+#pragma unroll
+                    for (int sl = 1; sl < CB2_MEMO_MAX_SP; sl++)
+                        if (L.slot == sl) { ni = nis[sl]; sq = sqs[sl]; vd = vds[sl]; }
+                    float amp = 0.f;
+                    if (live && ni > 0.f) {
+                        float lp;
+                        if (M.pec_const) lp = M.pec_value;
+                        else {
+                            if (M.pec_grid != lc.grid) { lc.cell = locate2d(M.pec, lc.lne, lc.lte); lc.grid = M.pec_grid; }
+                            if (!lc.cell.inside && !M.pec_extrapolate) ood++;
+                            lp = eval2d(M.pec, lc.cell);
+                        }
+                        amp = RECIP_4_PI * exp10f(lp) * ne * ni * in.weight * M.inv_delta;     // impact_excitation.pyx:99
+                        if (!(amp > 0.f) || !(sq > 0.f)) amp = 0.f;                          // gaussian.pyx:127-129
+                    }
+                    const float width = L.sigma_coef * sq;
+                    float* r = grec + L.rec_off;
+                    if (L.shape == CB2_SHAPE_GAUSSIAN) {
+                        if (sel) { r[64] = amp; r[0] = fmaf(L.shift_coef, vd, L.c0_frac); r[32] = width; }
+                    } else {
+                        const float dop = vd * L.inv_c;
+                        for (int kc = 0; kc < L.ncomp; kc++, r += REC_FLOATS_PER_COMP)
+                            if (sel) { r[64] = amp * __ldg(L.mult_ratio + kc); r[0] = S.comps[L.comp0 + kc].c0_frac + __ldg(L.mult_lambda + kc) * dop * L.inv_delta; r[32] = width; }
+                    }
+                }
+                continue;
+            }
             for (int m = 0; m < S.n_models; m++) {                 // PlasmaMaterial.emission_function loop, material.pyx:59-61
                 const DevModel& M = S.models[m];
                 if (M.kind == CB2_MODEL_BREMSSTRAHLUNG) continue;
@@ -1451,7 +1498,8 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         auto kern = state_kernel<4, MOM, AX, FT, FX>;                                                                             \
         if (smem > 32 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         kern<<<dim3((unsigned)((FX) ? (sub.n_rays + 3) / 4 : sub.n_rays)), dim3(128), (FX) ? 0 : smem, st>>>(                     \
-            S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, S.has_flat ? sc->flat : nullptr, (GB) ? 0 : count_samples, dbg, GB); \
+            S, sub, sc->gbase, sc->gmask, sc->rec, stats, sc->mom, S.has_flat ? sc->flat : nullptr, (GB) ? 0 : count_samples, dbg, GB, \
+            sc->memo);                                                                                                            \
     } while (0)
             if (sc->memo.enabled) {
                 // table-driven state kernel, then the generic kernel on the blend-zone samples it flagged

@@ -90,6 +90,8 @@ struct DevAxisym {
     int pgx, pgy;
     float p_icx, p_icy;
     const unsigned char* poly_cls;
+    const int* poly_row_start;       // [pgy + 1] per grid row: the edges that can cross a horizontal ray starting in that row
+    const float4* poly_row_edges;
     int n_mask;
     float mask_x[8], mask_y[8];
     // mesh

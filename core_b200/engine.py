@@ -61,7 +61,7 @@ class EmissionScene:
     def info(self):
         """Launch plan of this scene: CTA shape and the Bremsstrahlung formulation in use (cb2_scene_info)."""
         keys = ("warps_per_cta", "bins_per_lane", "brems_mode", "moment_row", "temperature_nodes", "distinct_charges", "batch_rays",
-                "two_kernel_line_path", "contraction_on_tensor_cores")
+                "two_kernel_line_path", "contraction_on_tensor_cores", "state_table_intervals", "state_table_error_1e9")
         d = {k: int(self._lib.cb2_scene_info(self._h, i)) for i, k in enumerate(keys)}
         d["brems_mode"] = {0: "none", 1: "direct", 3: "moments"}[d["brems_mode"]]
         return d

@@ -1,0 +1,113 @@
+"""The table-driven state kernel (state tables per mesh triangle and on a psi_n grid) against the generic
+kernel and the oracle: the Generomak scenes it takes (plasma lines with Gaussian / multiplet shapes, Bremsstrahlung moments,
+constant and flux-mapped velocities), and the scenes it must leave to the generic kernel."""
+import numpy as np
+import pytest
+
+import core_b200 as cb
+from core_b200 import generomak
+from core_b200.engine import EmissionScene
+from oracle import oracle
+from helpers import generomak_camera_rays
+
+pytestmark = pytest.mark.gpu
+RTOL, FLOOR = 1e-4, 1e-9      # |gpu - ref| <= 1e-4 |ref| + 1e-9 max_bin |ref[ray]|
+
+
+def worst_ratio(got, ref):
+    tol = RTOL * np.abs(ref) + FLOOR * np.abs(ref).max(axis=1, keepdims=True)
+    return float(np.max(np.abs(got - ref) / (tol + 1e-300)))
+
+
+def render_both_ways(flat, rays, monkeypatch, expect_tables=True):
+    monkeypatch.setenv("CB2_STATE_MEMO", "0")
+    generic = EmissionScene(flat)
+    assert generic.info()["state_table_intervals"] == 0
+    a, sa = generic.render(rays)
+    generic.close()
+    monkeypatch.setenv("CB2_STATE_MEMO", "1")
+    tabled = EmissionScene(flat)
+    info = tabled.info()
+    assert (info["state_table_intervals"] > 0) == expect_tables, info
+    if expect_tables:
+        assert info["state_table_error_1e9"] <= 4000      # accepted mid-interval error of the psi_n grid: <= 4e-6
+    b, sb = tabled.render(rays)
+    tabled.close()
+    assert sa["samples"] == sb["samples"]
+    return a, b, sa, sb
+
+
+def test_c1_halpha_tables_vs_generic_vs_oracle(monkeypatch):
+    plasma = generomak.get_plasma()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    flat = cb.flatten_scene(plasma, 651.279, 661.279, 512)
+    rays = generomak_camera_rays(plasma, (24, 24))
+    a, b, sa, sb = render_both_ways(flat, rays, monkeypatch)
+    ref, rst = oracle.emission_render(flat, rays)
+    assert sb["samples"] == rst["samples"] and sb["out_of_domain"] == 0
+    assert worst_ratio(b, ref) <= 1.0 and worst_ratio(a, ref) <= 1.0
+    assert worst_ratio(b, a) <= 0.2                        # the two kernels agree far inside the tolerance
+
+
+def test_c3_mix_with_moments(monkeypatch):
+    plasma = generomak.get_plasma()
+    lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4, 5, 6)]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.RecombinationLine(l) for l in lines] + [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.004)
+    flat = cb.flatten_scene(plasma, 390.0, 700.0, 2048)
+    rays = generomak_camera_rays(plasma, (5, 5))
+    a, b, sa, sb = render_both_ways(flat, rays, monkeypatch)
+    assert sa["brems_bin_evals"] == sb["brems_bin_evals"]
+    ref, _ = oracle.emission_render(flat, rays)
+    assert worst_ratio(b, ref) <= 1.0
+    assert worst_ratio(b, a) <= 0.2
+
+
+def test_multiplet_and_constant_velocity(monkeypatch):
+    plasma = generomak.get_plasma()
+    h0 = plasma.composition.get(cb.hydrogen, 0)
+    d = h0.distribution
+    plasma.composition.add(cb.Species(cb.hydrogen, 0, cb.Maxwellian(d.density, d.temperature, cb.ConstantVector3D(1.5e4, -2.0e4, 5.0e3), d.atomic_mass)))
+    multiplet = [[655.9, 656.1, 656.28, 656.5], [0.2, 0.5, 0.25, 0.05]]
+    l3, l4 = cb.Line(cb.hydrogen, 0, (3, 2)), cb.Line(cb.hydrogen, 0, (4, 2))
+    plasma.models = [cb.ExcitationLine(l3, lineshape=cb.MultipletLineShape, lineshape_args=[multiplet]), cb.RecombinationLine(l3),
+                     cb.ExcitationLine(l4)]
+    flat = cb.flatten_scene(plasma, 480.0, 660.0, 1024)
+    rays = generomak_camera_rays(plasma, (12, 12))
+    a, b, _, _ = render_both_ways(flat, rays, monkeypatch)
+    ref, _ = oracle.emission_render(flat, rays)
+    assert worst_ratio(b, ref) <= 1.0
+    assert worst_ratio(b, a) <= 0.2
+
+
+def test_ineligible_scenes_keep_the_generic_kernel(monkeypatch):
+    # a Zeeman shape needs the field direction against the ray: not a function of the plasma state alone
+    plasma = generomak.get_plasma()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line, lineshape=cb.ZeemanTriplet)]
+    flat = cb.flatten_scene(plasma, 651.279, 661.279, 256)
+    rays = generomak_camera_rays(plasma, (4, 4))
+    a, b, _, _ = render_both_ways(flat, rays, monkeypatch, expect_tables=False)
+    assert np.array_equal(a, b) or worst_ratio(b, a) <= 1e-3
+
+
+def test_accumulate_and_f32_frames(monkeypatch):
+    monkeypatch.setenv("CB2_STATE_MEMO", "1")
+    plasma = generomak.get_plasma()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line), cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.003)
+    flat = cb.flatten_scene(plasma, 640.0, 670.0, 300)
+    rays = generomak_camera_rays(plasma, (9, 9))
+    scene = EmissionScene(flat)
+    assert scene.info()["state_table_intervals"] > 0
+    a, _ = scene.render(rays)
+    again, _ = scene.render(rays)
+    assert np.array_equal(a, again)                        # fixed summation order: bit-reproducible
+    f32, _ = scene.render(rays, dtype=np.float32)
+    acc = a.copy()
+    scene.render(rays, out=acc, scale=0.5, accumulate=True)
+    scene.close()
+    assert np.allclose(f32, a, rtol=3e-7, atol=0)
+    assert np.allclose(acc, 1.5 * a, rtol=1e-12, atol=0)
