@@ -137,140 +137,3 @@ int cb2_launch_contract(const float* mom, const float* phi, int64_t n_rays, int 
     else contract_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(mom, phi, n_rays, k_pad, n_pad, bins, out, (float)scale, scale);
     return cb2_cuda_check(cudaGetLastError(), "contract_kernel launch");
 }
-
-// ------------------------------------------------------------------------------------------------------------------
-// Tensor-core path of the same contraction: the one GEMM-shaped step of the hot path (rays x k_pad x bins per batch).
-// float32 accuracy is required (1e-4 parity over ~1e3-term sums with cancelling Lagrange weights), so the product is the
-// error-compensated 3xTF32 form  A_hi B_hi + A_lo B_hi + A_hi B_lo  with  X_hi = tf32(X), X_lo = tf32(X - X_hi): every operand
-// is exactly representable in TF32, the tensor cores (tcgen05 kernels of cuBLAS on sm_100a) accumulate in float32, and the
-// dropped A_lo B_lo term is 2^-22 relative.  It is a plain GEMM with beta = 1, so the library GEMM is used for it; the FFMA
-// tile kernel above stays as the path when cuBLAS cannot be loaded (CB2_CONTRACT=ffma forces it).
-// cuBLAS is bound at run time (dlopen, RTLD_LOCAL): libcherab_b200.so keeps no link-time dependency on it and shares the
-// copy PyTorch may already have mapped.
-// ------------------------------------------------------------------------------------------------------------------
-#include <dlfcn.h>
-
-namespace {
-
-typedef int (*cublasCreate_t)(void**);
-typedef int (*cublasDestroy_t)(void*);
-typedef int (*cublasSetStream_t)(void*, cudaStream_t);
-typedef int (*cublasSetMathMode_t)(void*, int);
-typedef int (*cublasGemmEx_t)(void*, int, int, int, int, int, const void*, const void*, int, int, const void*, int, int, const void*,
-                              void*, int, int, int, int);
-struct BlasApi {
-    void* lib = nullptr;
-    cublasCreate_t create = nullptr;
-    cublasDestroy_t destroy = nullptr;
-    cublasSetStream_t set_stream = nullptr;
-    cublasSetMathMode_t set_math = nullptr;
-    cublasGemmEx_t gemm_ex = nullptr;
-    bool tried = false;
-};
-BlasApi g_blas;
-
-bool blas_load() {
-    if (g_blas.tried) return g_blas.gemm_ex != nullptr;
-    g_blas.tried = true;
-    const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-    for (const char* n : names) {
-        g_blas.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
-        if (g_blas.lib) break;
-    }
-    if (!g_blas.lib) return false;
-    g_blas.create = (cublasCreate_t)dlsym(g_blas.lib, "cublasCreate_v2");
-    g_blas.destroy = (cublasDestroy_t)dlsym(g_blas.lib, "cublasDestroy_v2");
-    g_blas.set_stream = (cublasSetStream_t)dlsym(g_blas.lib, "cublasSetStream_v2");
-    g_blas.set_math = (cublasSetMathMode_t)dlsym(g_blas.lib, "cublasSetMathMode");
-    g_blas.gemm_ex = (cublasGemmEx_t)dlsym(g_blas.lib, "cublasGemmEx");
-    if (!g_blas.create || !g_blas.destroy || !g_blas.set_stream || !g_blas.gemm_ex) { g_blas.gemm_ex = nullptr; return false; }
-    return true;
-}
-
-// hi = tf32(x) (round to nearest, ties away: cvt.rna), lo = tf32(x - hi); both stored as float32 bit patterns
-__global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        unsigned h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float hf = __uint_as_float(h);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hf));
-        hi[i] = hf;
-        lo[i] = __uint_as_float(l);
-    }
-}
-
-// out[ray][bin] += tmp[ray][bin]   (float64 frames: the GEMMs accumulate into a float32 scratch first)
-__global__ void add_to_f64_kernel(int64_t n, const float* __restrict__ tmp, double* __restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] += (double)tmp[i];
-}
-
-}  // namespace
-
-// called once per scene that uses the moment formulation; leaves sc->contract_tc = 0 when the tensor path is unavailable
-int cb2_contract_tc_init(cb2_scene* sc, const float* phi, int k_pad, int n_pad) {
-    sc->contract_tc = 0;
-    const char* force = getenv("CB2_CONTRACT");
-    if (force && strcmp(force, "ffma") == 0) return CB2_OK;
-    if (!blas_load()) return CB2_OK;
-    void* h = nullptr;
-    if (g_blas.create(&h) != 0 || !h) return CB2_OK;
-    if (g_blas.set_math) g_blas.set_math(h, 3 /* CUBLAS_TF32_TENSOR_OP_MATH */);
-    sc->blas = h;
-    const int64_t n = (int64_t)k_pad * n_pad;
-    CB2_CUDA(cudaMalloc((void**)&sc->phi_hi, n * sizeof(float)));
-    CB2_CUDA(cudaMalloc((void**)&sc->phi_lo, n * sizeof(float)));
-    split_tf32_kernel<<<592, 256>>>(n, phi, sc->phi_hi, sc->phi_lo);
-    CB2_CUDA(cudaGetLastError());
-    CB2_CUDA(cudaDeviceSynchronize());
-    sc->contract_tc = 1;
-    return CB2_OK;
-}
-
-void cb2_contract_tc_destroy(cb2_scene* sc) {
-    if (sc->blas && g_blas.destroy) g_blas.destroy(sc->blas);
-    sc->blas = nullptr;
-    cudaFree(sc->phi_hi); cudaFree(sc->phi_lo); cudaFree(sc->mom_split); cudaFree(sc->tmp32);
-    sc->phi_hi = sc->phi_lo = sc->mom_split = sc->tmp32 = nullptr;
-    sc->mom_split_bytes = sc->tmp32_bytes = 0;
-}
-
-static int grow(float** p, size_t* have, size_t need) {
-    if (need <= *have) return CB2_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr; *have = 0;
-    CB2_CUDA(cudaMalloc((void**)p, need));
-    *have = need;
-    return CB2_OK;
-}
-
-int cb2_launch_contract_tc(cb2_scene* sc, const float* mom, int64_t n_rays, int k_pad, int n_pad, int bins, void* out, int out_f64,
-                           double scale, cudaStream_t st) {
-    if (n_rays <= 0) return CB2_OK;
-    if (n_rays > 0x7fffffffLL) return cb2_fail(CB2_ERR_VALUE, "too many rays for one contraction launch");
-    const int64_t n_mom = n_rays * (int64_t)k_pad;
-    int rc = grow(&sc->mom_split, &sc->mom_split_bytes, (size_t)2 * n_mom * sizeof(float));
-    if (rc != CB2_OK) return rc;
-    float* mom_hi = sc->mom_split;
-    float* mom_lo = sc->mom_split + n_mom;
-    split_tf32_kernel<<<1184, 256, 0, st>>>(n_mom, mom, mom_hi, mom_lo);
-    float* c = (float*)out;
-    if (out_f64) {
-        if ((rc = grow(&sc->tmp32, &sc->tmp32_bytes, (size_t)n_rays * bins * sizeof(float))) != CB2_OK) return rc;
-        c = sc->tmp32;
-    }
-    if (g_blas.set_stream(sc->blas, st) != 0) return cb2_fail(CB2_ERR_CUDA, "cublasSetStream failed");
-    // row-major out[ray][bin] = mom[ray][k] phi[k][bin]  ==  column-major C(bins x rays) = PHI(bins x k; ld n_pad) MOM(k x rays; ld k_pad)
-    const float alpha = (float)scale, one = 1.0f, zero = 0.0f;
-    const int CUDA_R_32F_ = 0, OP_N = 0, COMPUTE_32F_FAST_TF32 = 77, GEMM_DEFAULT_TENSOR_OP = 99;
-    const float* A[3] = {sc->phi_hi, sc->phi_hi, sc->phi_lo};
-    const float* B[3] = {mom_hi, mom_lo, mom_hi};
-    for (int t = 0; t < 3; t++) {
-        const float* beta = (out_f64 && t == 0) ? &zero : &one;
-        const int st_ = g_blas.gemm_ex(sc->blas, OP_N, OP_N, bins, (int)n_rays, k_pad, &alpha, A[t], CUDA_R_32F_, n_pad, B[t], CUDA_R_32F_, k_pad,
-                                       beta, c, CUDA_R_32F_, bins, COMPUTE_32F_FAST_TF32, GEMM_DEFAULT_TENSOR_OP);
-        if (st_ != 0) return cb2_fail(CB2_ERR_CUDA, "cublasGemmEx failed with status %d", st_);
-    }
-    if (out_f64) add_to_f64_kernel<<<1184, 256, 0, st>>>(n_rays * (int64_t)bins, c, (double*)out);
-    return cb2_cuda_check(cudaGetLastError(), "tensor-core contraction");
-}

@@ -344,9 +344,9 @@ struct cb2_scene {
     // Bremsstrahlung moment matrix [rays][k_pad] fp32 (grow-only)
     float* mom;
     size_t mom_bytes;
-    // tensor-core contraction (cb2_contract.cu): cuBLAS handle, tf32 hi/lo parts of phi and of the moments, float32 scratch
+    // tensor-core contraction (cb2_contract_tc.cu): tf32 hi/lo parts of phi (transposed, K-major) and of the moments
     int contract_tc;
-    void* blas;
+    int tc_pairs;              // CTA pairs of the persistent tcgen05 kernel (SMs / 2)
     float *phi_hi, *phi_lo, *mom_split, *tmp32;
     size_t mom_split_bytes, tmp32_bytes;
     // two-kernel line path (cb2_emission_warp.cu), grow-only: per-ray group offsets [batch+1], per-group live masks, and

@@ -111,3 +111,33 @@ def test_accumulate_and_f32_frames(monkeypatch):
     scene.close()
     assert np.allclose(f32, a, rtol=3e-7, atol=0)
     assert np.allclose(acc, 1.5 * a, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("contract", ["tcgen05", "ffma"])
+def test_contraction_kernels_against_oracle(monkeypatch, contract):
+    """Both contraction kernels of the moment formulation — the tcgen05 3xTF32 kernel (default) and the FFMA tile kernel
+    (CB2_CONTRACT=ffma) — on ragged shapes: 144 rays (one 256-row tile, partly empty), 130 / 257 / 2048 bins, float32 and
+    float64 frames, accumulate."""
+    if contract == "ffma":
+        monkeypatch.setenv("CB2_CONTRACT", "ffma")
+    else:
+        monkeypatch.delenv("CB2_CONTRACT", raising=False)
+    plasma = generomak.get_plasma()
+    plasma.models = [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.02)
+    rays = generomak_camera_rays(plasma, (12, 12))
+    for lo, hi, bins in ((500.0, 600.0, 130), (500.0, 600.0, 257), (390.0, 700.0, 2048)):
+        flat = cb.flatten_scene(plasma, lo, hi, bins)
+        scene = EmissionScene(flat)
+        info = scene.info()
+        assert info["brems_mode"] == "moments"
+        assert info["contraction_on_tensor_cores"] == (1 if contract == "tcgen05" else 0)
+        a64, _ = scene.render(rays)
+        a32, _ = scene.render(rays, dtype=np.float32)
+        twice = a64.copy()
+        scene.render(rays, out=twice, scale=0.5, accumulate=True)
+        scene.close()
+        ref, _ = oracle.emission_render(flat, rays)
+        assert worst_ratio(a64, ref) <= 1.0, (contract, bins)
+        assert worst_ratio(a32.astype(np.float64), 0.5 * ref + 0.5 * ref) <= 2.0, (contract, bins)
+        assert worst_ratio(twice, 1.5 * ref) <= 1.0, (contract, bins)
