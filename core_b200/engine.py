@@ -2,7 +2,7 @@
 
 ``EmissionScene.render`` is the reference-facing call with HOST (numpy) buffers: ray segments in, spectra out,
 host<->device copies inside.  ``render_device`` takes torch CUDA tensors (PyTorch is plumbing for device memory and
-streams only) and launches on the current stream without synchronising.  There is no CPU fallback.
+streams only) and launches on the current stream.  There is no CPU fallback.
 """
 import ctypes as C
 
@@ -33,8 +33,12 @@ class EmissionScene:
         except Exception:
             pass
 
-    def render(self, rays, out=None, scale=1.0, accumulate=False, dtype=np.float64):
-        """spectra[n_rays, bins] (+)= scale * integral of the emission along every ray.  Returns (out, stats dict)."""
+    def render(self, rays, out=None, scale=1.0, accumulate=False, dtype=np.float64, out_of_domain="raise"):
+        """spectra[n_rays, bins] (+)= scale * integral of the emission along every ray.  Returns (out, stats dict).
+
+        Samples that leave a table built without extrapolation (rates, the psi grid) are clamped to the table edge and counted on
+        the device; the reference raises ValueError from the interpolator there ('none' extrapolation), so does this
+        call once the frame is back — ``out_of_domain="count"`` returns the clamped result with ``stats["out_of_domain"]`` instead."""
         if out is None:
             out = np.zeros((rays.n_rays, self.bins), dtype=dtype)
             accumulate = False
@@ -44,10 +48,18 @@ class EmissionScene:
         rs = rays.as_struct()
         _abi.check(self._lib, self._lib.cb2_emission_render(self._h, C.byref(rs), out.ctypes.data_as(C.c_void_p),
                                                             int(out.dtype == np.float64), float(scale), int(accumulate), C.byref(st)))
-        return out, st.as_dict()
+        stats = st.as_dict()
+        if out_of_domain == "raise" and stats["out_of_domain"] > 0:
+            raise ValueError("The specified value is outside of the range of the supplied data and/or extrapolation range: %d "
+                             "table lookups of this render left their tables (pass out_of_domain='count' for the clamped result)."
+                             % stats["out_of_domain"])
+        return out, stats
 
     def render_device(self, dev_rays, out, scale=1.0, accumulate=False, stats=None):
-        """Device-resident render: ``dev_rays`` is a DeviceRays, ``out`` a torch CUDA tensor [n_rays, bins] (fp32/fp64)."""
+        """Device-resident render: ``dev_rays`` is a DeviceRays, ``out`` a torch CUDA tensor [n_rays, bins] (fp32/fp64).
+        Launches on the current stream; the library synchronises that stream once per ray batch (it reads the batch's group
+        count), so the call returns with at most the last batch in flight.  A scene handle owns its scratch buffers: one
+        stream at a time per handle.  Out-of-domain lookups are only counted (``stats[5]``); the caller decides."""
         import torch
         rs = dev_rays.as_struct()
         is64 = out.dtype == torch.float64

@@ -101,7 +101,7 @@ def flatten_scene(plasma, min_wavelength, max_wavelength, bins, quad_rtol=1e-5, 
     uses_axisym = False
     _as_scalar_field(plasma.electron_distribution.density)._fill(d.electron_density, keep)
     _as_scalar_field(plasma.electron_distribution.temperature)._fill(d.electron_temperature, keep)
-    uses_axisym |= isinstance(plasma.electron_distribution.density, AxisymBlend)
+    uses_axisym |= isinstance(plasma.electron_distribution.density, AxisymBlend) or isinstance(plasma.electron_distribution.temperature, AxisymBlend)
 
     species = list(plasma.composition)
     sp_arr = (_abi.SpeciesDesc * max(1, len(species)))()

@@ -56,6 +56,16 @@ class SartSolver:
             d.row_offset, d.columns, d.values = _ptr(row_offset), _ptr(columns), _ptr(values)
         elif _device_csr is not None:
             row_offset, columns, values, n_sources = _device_csr       # torch CUDA tensors: int64, int32, float64
+            import torch
+            for t, dt, name in ((row_offset, torch.int64, "row_offset"), (columns, torch.int32, "columns"), (values, torch.float64, "values")):
+                if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous() and t.dim() == 1):
+                    raise TypeError("%s must be a contiguous 1-D CUDA tensor of dtype %s" % (name, dt))
+            if len({t.device for t in (row_offset, columns, values)}) != 1:
+                raise ValueError("the CSR tensors must live on one device")
+            if columns.numel() != values.numel() or row_offset.numel() < 1 or int(row_offset[-1].item()) != columns.numel():
+                raise ValueError("inconsistent CSR arrays")
+            if columns.numel() and (int(columns.min().item()) < 0 or int(columns.max().item()) >= int(n_sources)):
+                raise ValueError("column index out of range")
             keep += [row_offset, columns, values]
             d.n_detectors, d.n_sources = row_offset.numel() - 1, int(n_sources)
             d.memory = 1
@@ -143,6 +153,10 @@ class SartSolver:
             guess = np.ascontiguousarray(np.broadcast_to(np.asarray(initial_guess, dtype=np.float64).reshape(-1, self.n_sources),
                                                          (n_frames, self.n_sources)))
         max_iterations = int(max_iterations)
+        if max_iterations < 1:
+            # the reference's loop does not run: the seed comes back with an empty convergence list (sart.pyx:103-152)
+            seed = guess.copy() if guess is not None else np.full((n_frames, self.n_sources), value)
+            return (seed[0], []) if single else (seed, [[] for _ in range(n_frames)])
         solution = np.zeros((n_frames, self.n_sources))
         conv = np.zeros((n_frames, max(max_iterations, 1)))
         n_it = np.zeros(n_frames, dtype=np.int32)

@@ -15,7 +15,7 @@
  *
  * Build: see oracle/Makefile (gcc -O2 -fopenmp -shared -fPIC, -ffp-contract=off).
  */
-#include "../include/cherab_b200.h"
+#include "cb2_oracle.h"
 
 #include <math.h>
 #include <stdio.h>

@@ -22,7 +22,7 @@ def build(force=False):
     hdr = os.path.join(_HERE, "..", "include", "cherab_b200.h")
     # content hash, not file times: times do not survive the copy to the GPU box
     import hashlib
-    want = hashlib.sha256(open(src, "rb").read() + open(hdr, "rb").read()).hexdigest()
+    want = hashlib.sha256(open(src, "rb").read() + open(hdr, "rb").read() + open(os.path.join(_HERE, "cb2_oracle.h"), "rb").read()).hexdigest()
     stamp = LIB_PATH + ".sha"
     have = open(stamp).read().strip() if os.path.exists(stamp) else ""
     if force or not os.path.exists(LIB_PATH) or have != want:
