@@ -6,7 +6,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is usable,
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -76,12 +76,12 @@ class Rate3D(C.Structure):
 
 
 class BeamRate(C.Structure):
-    _fields_ = [("n_e", C.c_int32), ("n_n", C.c_int32), ("n_t", C.c_int32), ("_pad", C.c_int32), ("e", c_double_p), ("n", c_double_p),
+    _fields_ = [("n_e", C.c_int32), ("n_n", C.c_int32), ("n_t", C.c_int32), ("extrapolate", C.c_int32), ("e", c_double_p), ("n", c_double_p),
                 ("t", c_double_p), ("sen", c_double_p), ("st", c_double_p), ("sref", C.c_double), ("constant", C.c_double)]
 
 
 class CXRate(C.Structure):
-    _fields_ = [("n_eb", C.c_int32), ("n_ti", C.c_int32), ("n_ni", C.c_int32), ("n_z", C.c_int32), ("n_b", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("n_eb", C.c_int32), ("n_ti", C.c_int32), ("n_ni", C.c_int32), ("n_z", C.c_int32), ("n_b", C.c_int32), ("extrapolate", C.c_int32),
                 ("eb", c_double_p), ("ti", c_double_p), ("ni", c_double_p), ("z", c_double_p), ("b", c_double_p),
                 ("qeb", c_double_p), ("qti", c_double_p), ("qni", c_double_p), ("qz", c_double_p), ("qb", c_double_p),
                 ("qref", C.c_double), ("constant", C.c_double)]

@@ -207,7 +207,7 @@ class SyntheticADAS(AtomicData):
         sref = 1.0e-13
         sen = sref * (1 + 0.05 * charge) * (e[:, None] / 4e4) ** -0.35 * (1 + 0.08 * np.log10(n[None, :] / 1e19))
         st = sref * (1 + 0.05 * np.log10(t / 1e3))
-        return BeamStoppingTable(e, n, t, sen, st, sref)
+        return BeamStoppingTable(e, n, t, sen, st, sref, extrapolate=self.permit_extrapolation)
 
     def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
         """Synthetic ADF22-shaped beam emission coefficient (photon m^3 s^-1): same grids as the stopping coefficient."""
@@ -218,7 +218,7 @@ class SyntheticADAS(AtomicData):
         sref = 3.0e-15
         sen = sref * (1 + 0.03 * charge) * (e[:, None] / 4e4) ** 0.2 * (1 - 0.06 * np.log10(n[None, :] / 1e19))
         st = sref * (1 + 0.04 * np.log10(t / 1e3))
-        return BeamStoppingTable(e, n, t, sen, st, sref)
+        return BeamStoppingTable(e, n, t, sen, st, sref, extrapolate=self.permit_extrapolation)
 
     def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
         """Synthetic ADF12-shaped effective CX emission coefficient: eb[24], ti[12], ni[24], zeff[12], b[12]."""
@@ -231,7 +231,7 @@ class SyntheticADAS(AtomicData):
         qni = qref * (1 - 0.05 * np.log10(ni / 1e19))
         qz = qref * (1 + 0.03 * (z - 2.0))
         qb = qref * (1 + 0.004 * b)
-        return [BeamCXTable(1, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref)]
+        return [BeamCXTable(1, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref, extrapolate=self.permit_extrapolation)]
 
     def thermal_cx_pec(self, donor_ion, donor_charge, receiver_ion, receiver_charge, transition):
         """Synthetic ThermalCXPEC-shaped table on (ne[24], te[29], td[12]): smooth, positive, falling with the donor charge."""

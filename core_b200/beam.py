@@ -19,9 +19,12 @@ from .plasma import NumericalIntegrator
 
 
 class BeamStoppingTable:
-    """BeamStoppingRate data dict (openadas/rates/beam.pyx:40-103): e [eV/amu], n [m^-3], t [eV], sen [N x M], st [K], sref."""
+    """BeamStoppingRate data dict (openadas/rates/beam.pyx:40-103): e [eV/amu], n [m^-3], t [eV], sen [N x M], st [K], sref.
+    ``extrapolate``: 'linear' (2-D part) / 'quadratic' (1-D parts) beyond the tables (beam.pyx:73-84); without it a lookup
+    outside is the reference's ValueError (counted on the device, raised by EmissionScene.render)."""
 
-    def __init__(self, e, n, t, sen, st, sref):
+    def __init__(self, e, n, t, sen, st, sref, extrapolate=False):
+        self.extrapolate = bool(extrapolate)
         self.e, self.n, self.t = (np.ascontiguousarray(a, dtype=np.float64) for a in (e, n, t))
         self.sen = np.ascontiguousarray(sen, dtype=np.float64)
         self.st = np.ascontiguousarray(st, dtype=np.float64)
@@ -31,9 +34,11 @@ class BeamStoppingTable:
 
 
 class BeamCXTable:
-    """BeamCXPEC data dict (openadas/rates/cx.pyx:66-103): eb, ti, ni, z, b grids with qeb, qti, qni, qz, qb and qref."""
+    """BeamCXPEC data dict (openadas/rates/cx.pyx:66-103): eb, ti, ni, z, b grids with qeb, qti, qni, qz, qb and qref.
+    ``extrapolate``: 'quadratic' in log10 E, 'nearest' for the four factors (cx.pyx:96-102)."""
 
-    def __init__(self, donor_metastable, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref):
+    def __init__(self, donor_metastable, eb, ti, ni, z, b, qeb, qti, qni, qz, qb, qref, extrapolate=False):
+        self.extrapolate = bool(extrapolate)
         self.donor_metastable = int(donor_metastable)
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         self.eb, self.ti, self.ni, self.z, self.b = f(eb), f(ti), f(ni), f(z), f(b)
@@ -237,6 +242,7 @@ def _fill_beam_rate(r, rate, keep):
         r.constant = rate.value
     elif isinstance(rate, BeamStoppingTable):
         r.n_e, r.n_n, r.n_t = rate.e.size, rate.n.size, rate.t.size
+        r.extrapolate = 1 if rate.extrapolate else 0
         keep.append(rate)
         dp = lambda a: a.ctypes.data_as(_abi.c_double_p)
         r.e, r.n, r.t, r.sen, r.st, r.sref = dp(rate.e), dp(rate.n), dp(rate.t), dp(rate.sen), dp(rate.st), rate.sref
@@ -252,6 +258,7 @@ def _fill_cx_rate(r, rate, keep):
         keep.append(rate)
         dp = lambda a: a.ctypes.data_as(_abi.c_double_p)
         r.n_eb, r.n_ti, r.n_ni, r.n_z, r.n_b = rate.eb.size, rate.ti.size, rate.ni.size, rate.z.size, rate.b.size
+        r.extrapolate = 1 if rate.extrapolate else 0
         r.eb, r.ti, r.ni, r.z, r.b = dp(rate.eb), dp(rate.ti), dp(rate.ni), dp(rate.z), dp(rate.b)
         r.qeb, r.qti, r.qni, r.qz, r.qb = dp(rate.qeb), dp(rate.qti), dp(rate.qni), dp(rate.qz), dp(rate.qb)
         r.qref = rate.qref

@@ -563,9 +563,18 @@ static void set_comp(DevScene& S, int slot, double lambda, int type) {
 // ------------------------------------------------------------------------------------------------------------------
 // Beam: host-side fp64 rate evaluation and the SingleRayAttenuator axis table (singleray.pyx:182-313)
 // ------------------------------------------------------------------------------------------------------------------
-static double host_cubic1d(const double* x, const double* f, int n, double v) {
-    // Interpolator1DArray 'cubic' restated (local Hermite, 3-point knot derivatives), 'nearest' outside the knots
+static double host_cubic1d(const double* x, const double* f, int n, double v, bool quadratic = false) {
+    // Interpolator1DArray 'cubic' restated (local Hermite, 3-point knot derivatives); outside the knots 'nearest', or with
+    // `quadratic` the parabola through the edge value with the spline's slopes at both knots of the edge interval (the oracle's
+    // interp1d_cubic_quadratic)
     if (n == 1) return f[0];
+    if (quadratic && (v < x[0] || v > x[n - 1])) {
+        const int i = v < x[0] ? 0 : n - 2;
+        const double h = x[i + 1] - x[i], t = (v - x[i]) / h;
+        const double d0 = d1(x, f, n, 1, i) * h, dd1 = d1(x, f, n, 1, i + 1) * h;
+        const double a2 = v < x[0] ? f[i] : f[i + 1] - 0.5 * d0 - 0.5 * dd1;
+        return (0.5 * (dd1 - d0) * t + d0) * t + a2;
+    }
     v = fmin(fmax(v, x[0]), x[n - 1]);
     int i = (int)(std::upper_bound(x, x + n, v) - x) - 1;
     i = std::min(std::max(i, 0), n - 2);
@@ -575,9 +584,27 @@ static double host_cubic1d(const double* x, const double* f, int n, double v) {
     return a[0] + t * (a[1] + t * (a[2] + t * a[3]));
 }
 
-static double host_cubic2d(const double* x, const double* y, const std::vector<double>& coef, int nx, int ny, double vx, double vy) {
+static double host_cubic2d(const double* x, const double* y, const std::vector<double>& coef, int nx, int ny, double vx, double vy,
+                           bool linear = false) {
+    const double px = vx, py = vy;
     vx = fmin(fmax(vx, x[0]), x[nx - 1]);
     vy = fmin(fmax(vy, y[0]), y[ny - 1]);
+    if (linear && (px != vx || py != vy)) {
+        // 'linear' extrapolation: value, gradient and cross derivative of the patch at the nearest boundary point
+        int i = (int)(std::upper_bound(x, x + nx, vx) - x) - 1, j = (int)(std::upper_bound(y, y + ny, vy) - y) - 1;
+        i = std::min(std::max(i, 0), nx - 2);
+        j = std::min(std::max(j, 0), ny - 2);
+        const double hx = x[i + 1] - x[i], hy = y[j + 1] - y[j], t = (vx - x[i]) / hx, u = (vy - y[j]) / hy;
+        const double* c = &coef[((size_t)i * (ny - 1) + j) * 16];
+        double p = 0.0, pt = 0.0, pu = 0.0, ptu = 0.0;
+        for (int k = 3; k >= 0; k--) {
+            const double v = c[4 * k] + u * (c[4 * k + 1] + u * (c[4 * k + 2] + u * c[4 * k + 3]));
+            const double dv = c[4 * k + 1] + u * (2.0 * c[4 * k + 2] + 3.0 * u * c[4 * k + 3]);
+            ptu = ptu * t + pu; pt = pt * t + p; pu = pu * t + dv; p = p * t + v;
+        }
+        const double dx = (px - vx) / hx, dy = (py - vy) / hy;
+        return p + pt * dx + pu * dy + ptu * dx * dy;
+    }
     int i = (int)(std::upper_bound(x, x + nx, vx) - x) - 1, j = (int)(std::upper_bound(y, y + ny, vy) - y) - 1;
     i = std::min(std::max(i, 0), nx - 2);
     j = std::min(std::max(j, 0), ny - 2);
@@ -590,6 +617,7 @@ static double host_cubic2d(const double* x, const double* y, const std::vector<d
 
 struct HostBeamRate {     // BeamStoppingRate in log space (openadas/rates/beam.pyx:62-103)
     bool constant;
+    bool extrapolate = false;   // 'linear' / 'quadratic' beyond the tables (beam.pyx:73-84), else clamped
     double value;
     std::vector<double> le, ln, lt, lsen, lst, coef;
     double eval(double energy, double density, double temperature) const {
@@ -599,10 +627,10 @@ struct HostBeamRate {     // BeamStoppingRate in log space (openadas/rates/beam.
         double a;
         const int ne = (int)le.size(), nn = (int)ln.size();
         if (ne == 1 && nn == 1) a = lsen[0];
-        else if (ne == 1) a = host_cubic1d(ln.data(), lsen.data(), nn, n);
-        else if (nn == 1) a = host_cubic1d(le.data(), lsen.data(), ne, e);
-        else a = host_cubic2d(le.data(), ln.data(), coef, ne, nn, e, n);
-        const double b = lt.size() > 1 ? host_cubic1d(lt.data(), lst.data(), (int)lt.size(), t) : lst[0];
+        else if (ne == 1) a = host_cubic1d(ln.data(), lsen.data(), nn, n, extrapolate);
+        else if (nn == 1) a = host_cubic1d(le.data(), lsen.data(), ne, e, extrapolate);
+        else a = host_cubic2d(le.data(), ln.data(), coef, ne, nn, e, n, extrapolate);
+        const double b = lt.size() > 1 ? host_cubic1d(lt.data(), lst.data(), (int)lt.size(), t, extrapolate) : lst[0];
         return pow(10.0, a + b);
     }
 };
@@ -644,6 +672,7 @@ static int build_beam(Arena& A, const cb2_scene_desc& d, cb2_scene* sc) {
         if (b.stopping_species[k] < 0 || b.stopping_species[k] >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "stopping species index out of range");
         HostBeamRate& h = rates[k];
         h.constant = r.n_e <= 0;
+        h.extrapolate = r.extrapolate != 0;
         h.value = r.constant;
         if (h.constant) continue;
         if (r.n_e < 1 || r.n_n < 1 || r.n_t < 1 || !(r.sref > 0)) return cb2_fail(CB2_ERR_VALUE, "invalid beam stopping table");
@@ -708,6 +737,7 @@ static int build_beam(Arena& A, const cb2_scene_desc& d, cb2_scene* sc) {
 
 // BeamCXPEC tables of a BEAM_CX_LINE model (openadas/rates/cx.pyx:66-103)
 static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevCXRate& e) {
+    e.extrapolate = r.extrapolate != 0;
     if (r.n_eb <= 0) {
         e.is_const = 1;
         e.lconst = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;
@@ -746,6 +776,7 @@ static int convert_cx(Arena& A, const cb2_cx_rate& r, double wavelength, DevCXRa
 // BeamPopulationRate table (beam.pyx:143-170): log10 sen on (log10 E, log10 n), log10(st / sref) on log10 T
 static int convert_population(Arena& A, const cb2_beam_rate& r, DevPopRate& e) {
     memset(&e, 0, sizeof e);
+    e.extrapolate = r.extrapolate != 0;
     if (r.n_e <= 0) {
         e.is_const = 1;
         e.lconst = r.constant > 0 ? (float)log10(r.constant) : -INFINITY;
@@ -839,6 +870,7 @@ static int convert_model(Arena& A, const cb2_scene_desc& d, const cb2_model& m, 
             if (sp < 0 || sp >= d.n_species) return cb2_fail(CB2_ERR_VALUE, "beam emission species index out of range");
             e.bes_species[k] = sp;
             e.bes_charge[k] = d.species[sp].charge;
+            e.bes_extrapolate[k] = r.extrapolate != 0;
             if (r.n_e <= 0) {
                 e.bes_const[k] = 1;
                 e.bes_lconst[k] = r.constant > 0 ? (float)(log10(r.constant) + CB2_PEC_LOG_OFFSET) : -INFINITY;

@@ -129,6 +129,46 @@ __device__ __forceinline__ void locate1d(const DevTable1D& T, float x, int& i, f
     t = (T.n > 1) ? (x - __ldg(T.x + i)) * __ldg(T.inv_w + i) : 0.f;
 }
 
+// Interpolator2DArray 'cubic' with 'linear' extrapolation (beam.pyx:75,84; restated like the oracle's interp2d_cubic_linear): the
+// patch's value, gradient and cross derivative at the nearest boundary point.  Rare path (a sample outside a beam table).
+static __device__ __noinline__ float eval2d_linear(const DevTable2D& T, float x, float y) {
+    const Cell2 c = locate2d(T, x, y);
+    const float xc = fminf(fmaxf(x, T.xmin), T.xmax), yc = fminf(fmaxf(y, T.ymin), T.ymax);
+    const float iwx = T.uniform ? T.inv_dx : __ldg(T.inv_wx + c.i), iwy = T.uniform ? T.inv_dy : __ldg(T.inv_wy + c.j);
+    const float4* q = T.coef + ((size_t)c.i * (T.ny - 1) + c.j) * 4;
+    float p = 0.f, pt = 0.f, pu = 0.f, ptu = 0.f;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        const float4 r = __ldg(q + k);
+        const float v = horner4(r, c.u), dv = fmaf(fmaf(3.0f * r.w, c.u, 2.0f * r.z), c.u, r.y);
+        ptu = fmaf(ptu, c.t, pu);          // d/dt of the Horner recurrences, before they advance
+        pt = fmaf(pt, c.t, p);
+        pu = fmaf(pu, c.t, dv);
+        p = fmaf(p, c.t, v);
+    }
+    const float dx = (x - xc) * iwx, dy = (y - yc) * iwy;
+    return p + pt * dx + pu * dy + ptu * dx * dy;
+}
+
+// Interpolator1DArray 'cubic' with 'quadratic' extrapolation (beam.pyx:76, cx.pyx:96; oracle: interp1d_cubic_quadratic): outside the
+// knots a parabola in the edge interval's normalised coordinate through the edge value with the spline's slopes at both knots
+static __device__ __noinline__ float eval1d_quadratic(const DevTable1D& T, const float4* __restrict__ coef, float x) {
+    if (T.n < 2) return __ldg(coef).x;
+    if (x >= T.xmin && x <= T.xmax) {
+        int i; float t;
+        locate1d(T, x, i, t);
+        return horner4(__ldg(coef + i), t);
+    }
+    const bool low = x < T.xmin;
+    const int i = low ? 0 : T.n - 2;
+    const float xi = T.uniform ? T.x0 + (float)i / T.inv_dx : __ldg(T.x + i), iw = T.uniform ? T.inv_dx : __ldg(T.inv_w + i);
+    const float t = (x - xi) * iw;
+    const float4 a = __ldg(coef + i);
+    const float d0 = a.y, d1 = a.y + 2.0f * a.z + 3.0f * a.w;
+    const float a2 = low ? a.x : (a.x + a.y + a.z + a.w) - 0.5f * (d0 + d1);
+    return fmaf(fmaf(0.5f * (d1 - d0), t, d0), t, a2);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // per-sample shared context of the axisymmetric (Generomak-type) function tree — SURVEY Appendix C
 // ------------------------------------------------------------------------------------------------------------------

@@ -87,9 +87,11 @@ __device__ __forceinline__ float cx_rate_eval(const DevCXRate& R, const float (&
     for (int k = 0; k < 5; k++) {
         float v;
         if (R.n[k] == 1) v = R.single[k];
+        else if (R.extrapolate && k == 0) v = eval1d_quadratic(R.t[0], R.c[0], args[0]);      // 'quadratic' in log10 E, cx.pyx:96,98
         else {
+            // 'none': clamped and counted; with extrapolation the four factors are 'nearest' (cx.pyx:97)
             // (a few fp32 ulps of slack: Zeff of a Z = 1 plasma must not count as below a table that starts at 1)
-            if (args[k] < R.t[k].xmin - 4e-6f * fabsf(R.t[k].xmin) || args[k] > R.t[k].xmax + 4e-6f * fabsf(R.t[k].xmax)) ood++;
+            if (!R.extrapolate && (args[k] < R.t[k].xmin - 4e-6f * fabsf(R.t[k].xmin) || args[k] > R.t[k].xmax + 4e-6f * fabsf(R.t[k].xmax))) ood++;
             int ci; float ct;
             locate1d(R.t[k], args[k], ci, ct);
             v = horner4(__ldg(R.c[k] + ci), ct);
@@ -125,14 +127,19 @@ __device__ __forceinline__ float beam_population(const DevScene& S, const DevPop
             val = 0.f;
             if (energy > 0.f && n_eq > 0.f && ti > 0.f) {
                 const float le = log10f(energy), ln = log10f(n_eq) + 19.0f, lt = log10f(ti);
-                // the oracle counts every axis that leaves its table
-                if (le < R.a.xmin || le > R.a.xmax) ood++;
-                if (ln < R.a.ymin || ln > R.a.ymax) ood++;
-                if (lt < R.tk.xmin || lt > R.tk.xmax) ood++;
-                const Cell2 c = locate2d(R.a, le, ln);
-                int ci; float ct;
-                locate1d(R.tk, lt, ci, ct);
-                val = exp10f(eval2d(R.a, c) + horner4(__ldg(R.tc + ci), ct));
+                const bool out_a = le < R.a.xmin || le > R.a.xmax || ln < R.a.ymin || ln > R.a.ymax, out_t = lt < R.tk.xmin || lt > R.tk.xmax;
+                if (R.extrapolate && (out_a || out_t)) {
+                    val = exp10f(eval2d_linear(R.a, le, ln) + eval1d_quadratic(R.tk, R.tc, lt));   // beam.pyx:73-84
+                } else {
+                    // the oracle counts every axis that leaves its table
+                    if (le < R.a.xmin || le > R.a.xmax) ood++;
+                    if (ln < R.a.ymin || ln > R.a.ymax) ood++;
+                    if (out_t) ood++;
+                    const Cell2 c = locate2d(R.a, le, ln);
+                    int ci; float ct;
+                    locate1d(R.tk, lt, ci, ct);
+                    val = exp10f(eval2d(R.a, c) + horner4(__ldg(R.tc + ci), ct));
+                }
             }
         }
         pop = fmaf(target_ne, val, pop);
@@ -355,13 +362,18 @@ __device__ __forceinline__ void beam_emission_setup(const DevScene& S, const Dev
             const float energy = (ivx * ivx + ivy * ivy + ivz * ivz) * 5.18213506e-9f;
             const float n_eq = density_sum / (float)zc;
             if (!(energy > 0.f) || !(n_eq > 0.f) || !(ti > 0.f)) continue;
-            const Cell2 c = locate2d(X.bes_a[k], log10f(energy), log10f(n_eq) + 19.0f);
-            if (!c.inside) ood++;
-            const float lt = log10f(ti);
-            if (lt < X.bes_tk[k].xmin || lt > X.bes_tk[k].xmax) ood++;
-            int ci; float ct;
-            locate1d(X.bes_tk[k], lt, ci, ct);
-            lq = eval2d(X.bes_a[k], c) + horner4(__ldg(X.bes_tc[k] + ci), ct);
+            const float le = log10f(energy), ln = log10f(n_eq) + 19.0f, lt = log10f(ti);
+            const Cell2 c = locate2d(X.bes_a[k], le, ln);
+            const bool out_t = lt < X.bes_tk[k].xmin || lt > X.bes_tk[k].xmax;
+            if (X.bes_extrapolate[k] && (!c.inside || out_t)) {
+                lq = eval2d_linear(X.bes_a[k], le, ln) + eval1d_quadratic(X.bes_tk[k], X.bes_tc[k], lt);   // beam.pyx:209-221
+            } else {
+                if (!c.inside) ood++;
+                if (out_t) ood++;
+                int ci; float ct;
+                locate1d(X.bes_tk[k], lt, ci, ct);
+                lq = eval2d(X.bes_a[k], c) + horner4(__ldg(X.bes_tc[k] + ci), ct);
+            }
         }
         rate = fmaf(target_ne, exp10f(lq), rate);
     }

@@ -115,6 +115,7 @@ struct DevComp {
 #define CB2_MAX_META 4
 // BeamCXPEC: rate = 10^c0(log10 E) c1(Ti) c2(n_ion) c3(Zeff) c4(|B|)   (openadas/rates/cx.pyx:104-142)
 struct DevCXRate {
+    int extrapolate;                       // 1: 'quadratic' in log10 E, 'nearest' for the factors (cx.pyx:96-102); 0: clamp and count
     int is_const;                          // 1: constant rate
     float lconst;                          // log10(rate [W m^3]) + 38
     int n[5];                              // knots per factor (1: constant factor `single`)
@@ -124,6 +125,7 @@ struct DevCXRate {
 };
 // BeamPopulationRate: 10^(A(log10 E, log10 n_eq) + B(log10 T)), dimensionless   (openadas/rates/beam.pyx:105-189)
 struct DevPopRate {
+    int extrapolate;                       // 1: 'linear' (2-D) / 'quadratic' (1-D) extrapolation (beam.pyx:73-84); 0: clamp and count
     int is_const;
     float lconst;                          // log10(value), -inf for a null rate
     DevTable2D a;                          // (log10 E[eV/amu], log10 n_eq[m^-3]) -> log10 sen
@@ -150,6 +152,7 @@ struct DevModelExt {
     int bes_species[CB2_MAX_SPECIES];
     int bes_charge[CB2_MAX_SPECIES];
     int bes_const[CB2_MAX_SPECIES];
+    int bes_extrapolate[CB2_MAX_SPECIES];
     float bes_lconst[CB2_MAX_SPECIES];     // log10(rate [W m^3]) + 38
     DevTable2D bes_a[CB2_MAX_SPECIES];     // (log10 E[eV/amu], log10 n_eq[m^-3]) -> log10(sen [W m^3]) + 38
     DevTable1D bes_tk[CB2_MAX_SPECIES];    // log10 T[eV] knots

@@ -131,11 +131,10 @@ class OpenADAS(AtomicData):
         except FileNotFoundError:
             raise RuntimeError("Requested %s is not available." % what)
 
-    @staticmethod
-    def _beam_table(d):
+    def _beam_table(self, d):
         from .beam import BeamStoppingTable
         f = lambda k: np.array(d[k], np.float64)
-        return BeamStoppingTable(f("e"), f("n"), f("t"), f("sen"), f("st"), float(d["sref"]))
+        return BeamStoppingTable(f("e"), f("n"), f("t"), f("sen"), f("st"), float(d["sref"]), extrapolate=self.permit_extrapolation)
 
     def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
         beam, target = beam_ion.element, plasma_ion.element
@@ -189,5 +188,5 @@ class OpenADAS(AtomicData):
         for metastable, d in rates.items():
             f = lambda k: np.array(d[k], np.float64)
             out.append(BeamCXTable(int(metastable), f("eb"), f("ti"), f("ni"), f("z"), f("b"), f("qeb"), f("qti"), f("qni"), f("qz"), f("qb"),
-                                   float(d["qref"])))
+                                   float(d["qref"]), extrapolate=self.permit_extrapolation))
         return out

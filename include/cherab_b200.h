@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 6
+#define CB2_ABI_VERSION 7
 
 /* ------------------------------------------------------------------------------------------------
  * status codes.  Python shim maps them to the exception the reference raises at the same point.
@@ -158,10 +158,12 @@ typedef struct cb2_rate3d {
 
 /* BeamStoppingRate data dict {'e','n','t','sen','st','sref'} (cherab/openadas/rates/beam.pyx:40-103):
  * rate = 10 ** (cubic2d[log10 E, log10 n](log10 sen) + cubic1d[log10 T](log10(st/sref))).  n_e == 0 -> constant rate
- * (the mock AtomicData of core/tests/test_beam.py:33-52).  Outside the tabulated range the CUDA path and the oracle clamp to
- * the edge and count the sample as out of domain (the reference extrapolates linearly/quadratically if permitted). */
+ * (the mock AtomicData of core/tests/test_beam.py:33-52).  Outside the tabulated range: with `extrapolate` the reference's
+ * 'linear' / 'quadratic' extrapolation; without it ('none': the reference raises ValueError) the CUDA path and the oracle clamp
+ * to the edge and count the lookup as out of domain. */
 typedef struct cb2_beam_rate {
-    int32_t       n_e, n_n, n_t, _pad;
+    int32_t       n_e, n_n, n_t;
+    int32_t       extrapolate;  /* 1: 'linear' (2-D part) / 'quadratic' (1-D parts) extrapolation, beam.pyx:73-84; 0: 'none' */
     const double* e;           /* [n_e] interaction energy eV/amu */
     const double* n;           /* [n_n] target equivalent electron density m^-3 */
     const double* t;           /* [n_t] target temperature eV */
@@ -176,7 +178,8 @@ typedef struct cb2_beam_rate {
  * cubic[B](qb/qref), zero as soon as a partial product is <= 0.  n_eb == 0 -> constant rate in W m^3
  * (core/tests/test_beamcxline.py:34-46).  A grid with a single point is a constant factor (Constant1D). */
 typedef struct cb2_cx_rate {
-    int32_t       n_eb, n_ti, n_ni, n_z, n_b, _pad;
+    int32_t       n_eb, n_ti, n_ni, n_z, n_b;
+    int32_t       extrapolate;  /* 1: 'quadratic' in log10 E, 'nearest' for the four factors (cx.pyx:96-102); 0: 'none' */
     const double *eb, *ti, *ni, *z, *b;
     const double *qeb, *qti, *qni, *qz, *qb;
     double        qref;

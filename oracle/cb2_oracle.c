@@ -95,6 +95,30 @@ double cb2o_interp1d_cubic(const double* x, const double* f, int n, double px, i
     return hermite(f[i], f[i + 1], d0, d1, t);
 }
 
+/* derivative of hermite() with respect to t */
+static double hermite_d(double f0, double f1, double d0, double d1, double t) {
+    double a2 = 3.0 * (f1 - f0) - 2.0 * d0 - d1;
+    double a3 = 2.0 * (f0 - f1) + d0 + d1;
+    return d0 + t * (2.0 * a2 + 3.0 * t * a3);
+}
+
+/* Interpolator1DArray(x, f, 'cubic', 'quadratic', INFINITY) — the extrapolation Cherab asks for in openadas/rates/beam.pyx:76
+ * and cx.pyx:96.  [raysect, restated from memory: parity unpinned]  Outside the knots the value follows a parabola in the
+ * normalised coordinate t of the edge interval that matches the spline's value at the edge knot and its first derivative at
+ * BOTH knots of that interval: q(t) = a0 t^2 + a1 t + a2 with a0 = (d1 - d0)/2, a1 = d0 and a2 = f0 at the lower end,
+ * a2 = f1 - (d0 + d1)/2 at the upper end (d = knot derivatives scaled by the interval width). */
+static double interp1d_cubic_quadratic(const double* x, const double* f, int n, double px) {
+    if (n == 1) return f[0];
+    if (px >= x[0] && px <= x[n - 1]) return cb2o_interp1d_cubic(x, f, n, px, 1);
+    int i = px < x[0] ? 0 : n - 2;
+    double h = x[i + 1] - x[i];
+    double t = (px - x[i]) / h;
+    double d0 = knot_derivative(x, f, n, 1, i) * h, d1 = knot_derivative(x, f, n, 1, i + 1) * h;
+    double a0 = 0.5 * (d1 - d0), a1 = d0;
+    double a2 = px < x[0] ? f[i] : f[i + 1] - 0.5 * d0 - 0.5 * d1;
+    return (a0 * t + a1) * t + a2;
+}
+
 static double interp1d_linear(const double* x, const double* f, int n, double px) {
     if (n == 1) return f[0];
     if (px < x[0]) px = x[0];
@@ -141,6 +165,34 @@ double cb2o_interp2d_cubic(const double* x, const double* y, const double* f, in
         (void)gy; (void)gxy;
     }
     return hermite(g[0], g[1], gx[0], gx[1], t);
+}
+
+/* Interpolator2DArray(x, y, f, 'cubic', 'linear', INFINITY, INFINITY) — beam.pyx:75,84.  [raysect, restated from memory: parity
+ * unpinned]  Outside the grid: the spline's value, gradient and cross derivative at the nearest point of the grid boundary,
+ * f + fx dx + fy dy + fxy dx dy (dx, dy the distances beyond the boundary; one of them is zero next to an edge). */
+static double interp2d_cubic_linear(const double* x, const double* y, const double* f, int nx, int ny, double px, double py) {
+    double cx = px < x[0] ? x[0] : (px > x[nx - 1] ? x[nx - 1] : px);
+    double cy = py < y[0] ? y[0] : (py > y[ny - 1] ? y[ny - 1] : py);
+    if (cx == px && cy == py) return cb2o_interp2d_cubic(x, y, f, nx, ny, px, py, 1);
+    int i = find_cell(x, nx, cx), j = find_cell(y, ny, cy);
+    double hx = x[i + 1] - x[i], hy = y[j + 1] - y[j];
+    double t = (cx - x[i]) / hx, u = (cy - y[j]) / hy;
+    double g[2], gx[2], dg[2], dgx[2];
+    for (int a = 0; a < 2; a++) {
+        int ia = i + a;
+        double f0 = f[ia * ny + j], f1 = f[ia * ny + j + 1];
+        double dy0 = knot_derivative(y, f + ia * ny, ny, 1, j) * hy, dy1 = knot_derivative(y, f + ia * ny, ny, 1, j + 1) * hy;
+        double dx0 = knot_derivative(x, f + j, nx, ny, ia) * hx, dx1 = knot_derivative(x, f + j + 1, nx, ny, ia) * hx;
+        double dxy0 = knot_cross_derivative(x, y, f, nx, ny, ia, j) * hx * hy, dxy1 = knot_cross_derivative(x, y, f, nx, ny, ia, j + 1) * hx * hy;
+        g[a] = hermite(f0, f1, dy0, dy1, u);        dg[a] = hermite_d(f0, f1, dy0, dy1, u);
+        gx[a] = hermite(dx0, dx1, dxy0, dxy1, u);   dgx[a] = hermite_d(dx0, dx1, dxy0, dxy1, u);
+    }
+    double v = hermite(g[0], g[1], gx[0], gx[1], t);
+    double fx = hermite_d(g[0], g[1], gx[0], gx[1], t) / hx;
+    double fy = hermite(dg[0], dg[1], dgx[0], dgx[1], t) / hy;
+    double fxy = hermite_d(dg[0], dg[1], dgx[0], dgx[1], t) / (hx * hy);
+    double dx = px - cx, dy = py - cy;
+    return v + fx * dx + fy * dy + fxy * dx * dy;
 }
 
 /* third cross derivative at knot (i,j,k): eight-corner difference over the neighbouring knots that exist
@@ -829,7 +881,7 @@ static void xform_vector(const double m[12], const double p[3], double o[3]);
 
 static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-/* BeamStoppingRate.evaluate — openadas/rates/beam.pyx:93-103; outside the tables: clamped to the edge and counted */
+/* BeamStoppingRate.evaluate — openadas/rates/beam.pyx:93-103 */
 /* wavelength > 0: BeamEmissionPEC, 'sen' is converted from photon m^3/s to W m^3 first (beam.pyx:229-239) */
 static double beam_rate_eval_w(const cb2_beam_rate* r, double wavelength, double energy, double density, double temperature, int64_t* ood) {
     if (r->n_e <= 0) return r->constant;
@@ -846,15 +898,25 @@ static double beam_rate_eval_w(const cb2_beam_rate* r, double wavelength, double
         for (int i = 0; i < r->n_e * r->n_n; i++) lsen[i] = log10(r->sen[i] * conv);
     }
     for (int i = 0; i < r->n_t; i++) lst[i] = log10(r->st[i] / r->sref);
-    lo = xe[0]; hi = xe[r->n_e - 1]; if (le < lo || le > hi) { (*ood)++; le = clampd(le, lo, hi); }
-    lo = xn[0]; hi = xn[r->n_n - 1]; if (ln < lo || ln > hi) { (*ood)++; ln = clampd(ln, lo, hi); }
-    lo = xt[0]; hi = xt[r->n_t - 1]; if (lt < lo || lt > hi) { (*ood)++; lt = clampd(lt, lo, hi); }
-    double a;
-    if (r->n_e == 1 && r->n_n == 1) a = lsen[0];
-    else if (r->n_e == 1) a = cb2o_interp1d_cubic(xn, lsen, r->n_n, ln, 1);
-    else if (r->n_n == 1) a = cb2o_interp1d_cubic(xe, lsen, r->n_e, le, 1);
-    else a = cb2o_interp2d_cubic(xe, xn, lsen, r->n_e, r->n_n, le, ln, 1);
-    double b = r->n_t > 1 ? cb2o_interp1d_cubic(xt, lst, r->n_t, lt, 1) : lst[0];
+    double a, b;
+    if (r->extrapolate) {
+        /* extrapolate=True: 'linear' for the 2-D part, 'quadratic' for the 1-D parts (beam.pyx:73-84) */
+        if (r->n_e == 1 && r->n_n == 1) a = lsen[0];
+        else if (r->n_e == 1) a = interp1d_cubic_quadratic(xn, lsen, r->n_n, ln);
+        else if (r->n_n == 1) a = interp1d_cubic_quadratic(xe, lsen, r->n_e, le);
+        else a = interp2d_cubic_linear(xe, xn, lsen, r->n_e, r->n_n, le, ln);
+        b = r->n_t > 1 ? interp1d_cubic_quadratic(xt, lst, r->n_t, lt) : lst[0];
+    } else {
+        /* 'none': the reference raises ValueError; here the argument is clamped to the edge and the lookup counted */
+        lo = xe[0]; hi = xe[r->n_e - 1]; if (le < lo || le > hi) { (*ood)++; le = clampd(le, lo, hi); }
+        lo = xn[0]; hi = xn[r->n_n - 1]; if (ln < lo || ln > hi) { (*ood)++; ln = clampd(ln, lo, hi); }
+        lo = xt[0]; hi = xt[r->n_t - 1]; if (lt < lo || lt > hi) { (*ood)++; lt = clampd(lt, lo, hi); }
+        if (r->n_e == 1 && r->n_n == 1) a = lsen[0];
+        else if (r->n_e == 1) a = cb2o_interp1d_cubic(xn, lsen, r->n_n, ln, 1);
+        else if (r->n_n == 1) a = cb2o_interp1d_cubic(xe, lsen, r->n_e, le, 1);
+        else a = cb2o_interp2d_cubic(xe, xn, lsen, r->n_e, r->n_n, le, ln, 1);
+        b = r->n_t > 1 ? cb2o_interp1d_cubic(xt, lst, r->n_t, lt, 1) : lst[0];
+    }
     free(xe);
     return pow(10.0, a + b);
 }
@@ -863,9 +925,10 @@ static double beam_rate_eval(const cb2_beam_rate* r, double energy, double densi
     return beam_rate_eval_w(r, 0.0, energy, density, temperature, ood);
 }
 
-static double cx_factor(const double* x, const double* q, int n, double scale, double v, int64_t* ood) {
+static double cx_factor(const double* x, const double* q, int n, double scale, double v, int extrapolate, int64_t* ood) {
     if (n == 1) return q[0] * scale;               /* Constant1D */
-    if (v < x[0] || v > x[n - 1]) { (*ood)++; v = clampd(v, x[0], x[n - 1]); }
+    /* extrapolate=True: 'nearest' for the four linear-space factors (cx.pyx:97,99-102) */
+    if (v < x[0] || v > x[n - 1]) { if (!extrapolate) (*ood)++; v = clampd(v, x[0], x[n - 1]); }
     double* f = (double*)malloc(sizeof(double) * n);
     for (int i = 0; i < n; i++) f[i] = q[i] * scale;
     double r = cb2o_interp1d_cubic(x, f, n, v, 1);
@@ -887,18 +950,21 @@ static double cx_rate_eval(const cb2_cx_rate* r, double wavelength, double energ
         double le = log10(energy);
         if (r->n_eb == 1) rate = pow(10.0, f[0]);
         else {
-            if (le < x[0] || le > x[r->n_eb - 1]) { (*ood)++; le = clampd(le, x[0], x[r->n_eb - 1]); }
-            rate = pow(10.0, cb2o_interp1d_cubic(x, f, r->n_eb, le, 1));
+            if (r->extrapolate) rate = pow(10.0, interp1d_cubic_quadratic(x, f, r->n_eb, le));    /* 'quadratic', cx.pyx:96,98 */
+            else {
+                if (le < x[0] || le > x[r->n_eb - 1]) { (*ood)++; le = clampd(le, x[0], x[r->n_eb - 1]); }
+                rate = pow(10.0, cb2o_interp1d_cubic(x, f, r->n_eb, le, 1));
+            }
         }
         free(x);
     }
-    rate *= cx_factor(r->ti, r->qti, r->n_ti, 1.0 / r->qref, temperature, ood);
+    rate *= cx_factor(r->ti, r->qti, r->n_ti, 1.0 / r->qref, temperature, r->extrapolate, ood);
     if (rate <= 0) return 0.0;
-    rate *= cx_factor(r->ni, r->qni, r->n_ni, 1.0 / r->qref, density, ood);
+    rate *= cx_factor(r->ni, r->qni, r->n_ni, 1.0 / r->qref, density, r->extrapolate, ood);
     if (rate <= 0) return 0.0;
-    rate *= cx_factor(r->z, r->qz, r->n_z, 1.0 / r->qref, zeff, ood);
+    rate *= cx_factor(r->z, r->qz, r->n_z, 1.0 / r->qref, zeff, r->extrapolate, ood);
     if (rate <= 0) return 0.0;
-    rate *= cx_factor(r->b, r->qb, r->n_b, 1.0 / r->qref, bmag, ood);
+    rate *= cx_factor(r->b, r->qb, r->n_b, 1.0 / r->qref, bmag, r->extrapolate, ood);
     if (rate <= 0) return 0.0;
     return rate;
 }

@@ -143,7 +143,8 @@ def test_beam_cx_metastables_slab_and_generomak():
 
         def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
             g = cb.SyntheticADAS.beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition)[0]
-            e = cb.BeamCXTable(2, g.eb, g.ti, g.ni, g.z, g.b, 30.0 * g.qeb * (g.eb / 4e4) ** -0.4, g.qti * 1.1, g.qni, g.qz * 0.9, g.qb, g.qref)
+            e = cb.BeamCXTable(2, g.eb, g.ti, g.ni, g.z, g.b, 30.0 * g.qeb * (g.eb / 4e4) ** -0.4, g.qti * 1.1, g.qni, g.qz * 0.9, g.qb, g.qref,
+                               extrapolate=self.permit_extrapolation)
             return [g, e]
 
         def beam_population_rate(self, beam_ion, metastable, plasma_ion, charge):
@@ -153,7 +154,7 @@ def test_beam_cx_metastables_slab_and_generomak():
             sref = 4.0e-3
             sen = sref * (1 + 0.03 * charge) * (e[:, None] / 4e4) ** 0.2 * (n[None, :] / 1e19) ** 0.1
             st = sref * (1 + 0.04 * np.log10(t / 1e3))
-            return cb.BeamStoppingTable(e, n, t, sen, st, sref)
+            return cb.BeamStoppingTable(e, n, t, sen, st, sref, extrapolate=self.permit_extrapolation)
 
     plasma = generomak.get_plasma()
     atomic = MetaADAS()
@@ -214,4 +215,82 @@ def test_beam_emission_ratio_functions():
     scene.close()
     ref, rst = oracle.emission_render(flat, rays)
     assert st["samples"] == rst["samples"] and ref.max() > 0
+    assert parity(got, ref) <= 1.0
+
+
+class NarrowBeamADAS(cb.SyntheticADAS):
+    """Beam tables that stop short of what the Generomak beam scene asks for — interaction energy (60 keV/amu against a table
+    ending at 40), target density, temperature — so that every lookup family is taken outside its table."""
+
+    def _cut(self, r):
+        e, n, t = slice(0, 18), slice(8, 22), slice(3, 12)
+        return cb.BeamStoppingTable(r.e[e], r.n[n], r.t[t], r.sen[e, n], r.st[t], r.sref, extrapolate=r.extrapolate)
+
+    def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+        r = cb.SyntheticADAS.beam_stopping_rate(self, beam_ion, plasma_ion, charge)
+        return None if r is None else self._cut(r)
+
+    def beam_emission_pec(self, beam_ion, plasma_ion, charge, transition):
+        r = cb.SyntheticADAS.beam_emission_pec(self, beam_ion, plasma_ion, charge, transition)
+        return None if r is None else self._cut(r)
+
+    def beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition):
+        g = cb.SyntheticADAS.beam_cx_pec(self, donor_ion, receiver_ion, receiver_charge, transition)[0]
+        s = slice(0, 12)                                                       # E up to ~30 keV/amu, Ti and Zeff grids cut too
+        return [cb.BeamCXTable(1, g.eb[s], g.ti[:8], g.ni, g.z[2:], g.b, g.qeb[s], g.qti[:8], g.qni, g.qz[2:], g.qb, g.qref,
+                               extrapolate=g.extrapolate)]
+
+
+def _narrow_beam_scene(permit):
+    plasma = generomak.get_plasma()
+    atomic = NarrowBeamADAS(permit_extrapolation=permit)
+    balmer = atomic.wavelength
+    atomic.wavelength = lambda ion, charge, transition: 529.05 if ion is cb.carbon else balmer(ion, charge, transition)
+    plasma.atomic_data = atomic
+    beam = cb.Beam(transform=cb.look_at((3.2, -0.4, 0.0), (1.0, 0.3, 0.05)))
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.05, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.0025, min_samples=10)
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2))), cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    axis_pts = (np.asarray(beam.transform) @ np.stack([np.zeros(12), np.zeros(12), np.linspace(0.6, 2.4, 12), np.ones(12)]))[:3].T
+    origin = np.tile([[1.8, 0.2, 1.6]], (12, 1))
+    return beam, cb.beam_ray_segments(beam, origin, axis_pts - origin)
+
+
+def test_beam_rates_extrapolate_like_the_reference():
+    # extrapolate=True: 'linear' (2-D) / 'quadratic' (1-D) for the ADF21 / ADF22 tables, 'quadratic' in log10 E and 'nearest' for the
+    # factors of the ADF12 table (openadas/rates/beam.pyx:73-84, cx.pyx:96-102) — host attenuation, device kernels and oracle agree
+    beam, rays = _narrow_beam_scene(True)
+    z = np.linspace(0.05, 2.9, 40)
+    for lo, hi, bins in ((526.0, 532.0, 256), (650.0, 662.0, 512)):
+        flat = cb.flatten_beam_scene(beam, lo, hi, bins)
+        scene = EmissionScene(flat)
+        got, st = scene.render(rays)
+        dens, _ = beam_sample(scene, np.stack([0 * z, 0 * z, z], axis=1))
+        scene.close()
+        ref, rst = oracle.emission_render(flat, rays)
+        rd, _ = oracle.beam_sample(flat, np.stack([0 * z, 0 * z, z], axis=1))
+        assert st["out_of_domain"] == 0 and rst["out_of_domain"] == 0
+        assert ref.max() > 0 and parity(got, ref) <= 1.0, (lo, hi)
+        assert np.max(np.abs(dens / rd - 1)) < 3e-5
+    # the extrapolation matters: the clamped ('nearest') result of the same tables differs visibly
+    beam_c, _ = _narrow_beam_scene(False)
+    flat_c = cb.flatten_beam_scene(beam_c, 650.0, 662.0, 512)
+    clamped, cst = oracle.emission_render(flat_c, rays)
+    assert cst["out_of_domain"] > 0
+    assert np.max(np.abs(clamped - ref)) > 1e-3 * ref.max()
+
+
+def test_beam_rates_without_extrapolation_raise():
+    beam, rays = _narrow_beam_scene(False)
+    flat = cb.flatten_beam_scene(beam, 650.0, 662.0, 256)
+    scene = EmissionScene(flat)
+    with pytest.raises(ValueError):
+        scene.render(rays)
+    got, st = scene.render(rays, out_of_domain="count")
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)
+    assert st["out_of_domain"] > 0 and abs(st["out_of_domain"] - rst["out_of_domain"]) <= 2e-3 * rst["out_of_domain"] + 4
     assert parity(got, ref) <= 1.0

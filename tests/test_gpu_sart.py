@@ -103,8 +103,9 @@ def test_bad_arguments_raise():
     with cb.SartSolver(G) as solver:
         with pytest.raises(ValueError):
             solver(M[:-1])
-        with pytest.raises(ValueError):
-            solver(M, max_iterations=0)
+        # no iteration: the reference's loop does not run and the seed comes back with an empty convergence list (sart.pyx:103-152)
+        x0, conv0 = solver(M, max_iterations=0, initial_guess=0.25)
+        assert conv0 == [] and np.array_equal(x0, np.full(G.shape[1], 0.25))
 
 
 def test_geometry_matrix_from_the_ray_transfer_kernel_stays_on_the_device():

@@ -71,3 +71,43 @@ def test_2d_uniform_matches_tensor_catmull_rom():
     rows = [catmull_rom(F[i - 1 + a, j - 1], F[i - 1 + a, j], F[i - 1 + a, j + 1], F[i - 1 + a, j + 2], u) for a in range(4)]
     ref = catmull_rom(rows[0], rows[1], rows[2], rows[3], t)
     assert abs(oracle.interp2d_cubic(x, y, F, x[i] + t * 0.03, y[j] + u * 0.05) - ref) < 1e-12
+
+
+def test_beam_rate_extrapolation_rules():
+    """'quadratic' (1-D) and 'linear' (2-D) extrapolation as the oracle restates them for the beam tables (beam.pyx:73-84): reached
+    through the beam-density probe of a one-species slab whose stopping table is a power law in every argument — log-log linear
+    data, which both rules continue exactly — so the attenuation outside the table equals the analytic power law."""
+    import core_b200 as cb
+    from oracle import oracle
+    from test_oracle_beam import beam_scene
+
+    class PowerLawADAS(cb.AtomicData):
+        def __init__(self, extrapolate):
+            self.extrapolate = extrapolate
+
+        def beam_stopping_rate(self, beam_ion, plasma_ion, charge):
+            e, n, t = np.logspace(4.8, 5.5, 6), np.logspace(19.5, 21.0, 7), np.logspace(3.5, 4.5, 5)     # none contains the slab's state
+            sref = 1e-13
+            sen = sref * (e[:, None] / 1e5) ** -0.4 * (n[None, :] / 1e20) ** 0.1
+            st = sref * (t / 1e4) ** 0.05
+            return cb.BeamStoppingTable(e, n, t, sen, st, sref, extrapolate=self.extrapolate)
+
+    def density_on_axis(extrapolate):
+        plasma, beam = beam_scene(1e-13, sigma=0.2, divergence_x=0.0, divergence_y=0.0, length=10.0)
+        beam.atomic_data = PowerLawADAS(extrapolate)
+        flat = cb.flatten_beam_scene(beam, 655.1, 657.1, 16)
+        z = np.linspace(0.5, 9.5, 10)
+        d, _ = oracle.beam_sample(flat, np.stack([0 * z, 0 * z, z], axis=1))
+        return plasma, beam, z, d
+
+    plasma, beam, z, d = density_on_axis(True)
+    sp = [s for s in plasma.composition if s.charge > 0][0]
+    ni, ti = sp.distribution.density.value, sp.distribution.temperature.value
+    energy = beam.energy                                    # the slab species are at rest in the reference's test scene
+    rate = 1e-13 * (energy / 1e5) ** -0.4 * ((sp.charge ** 2 * ni / sp.charge) / 1e20) ** 0.1 * (ti / 1e4) ** 0.05
+    speed = np.sqrt(2 * energy * 1.602176634e-19 / 1.66053906660e-27)
+    ratio = d[1:] / d[:-1]
+    expect = np.exp(-ni * sp.charge * rate * np.diff(z) / speed)
+    assert np.allclose(ratio, expect, rtol=1e-9), (ratio, expect)
+    _, _, _, dc = density_on_axis(False)                    # clamped tables attenuate differently
+    assert not np.allclose(dc[1:] / dc[:-1], expect, rtol=1e-4)
