@@ -1,0 +1,160 @@
+"""BASELINE.json configurations at their FULL sizes on the CUDA path:
+C1 128 x 128 H-alpha frame, every pixel against the oracle; C3 16 stratified passes accumulated into the float32 frame against
+a float64 frame with float64 accumulators and against the oracle; C4 512 x 512 rays through the 400 x 800 grid, 64 rows against the
+oracle; C5 a 256-fibre bundle across the beam of demos/beam.py (D+ / He2+ / C6+ / Ne10+ Gaussian volume) with both beam models."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import core_b200 as cb
+from core_b200 import generomak
+from core_b200.engine import DeviceRays, EmissionScene, RayTransferScene
+from core_b200.raytransfer import RayTransferCylinder
+from oracle import oracle
+from helpers import generomak_camera_rays
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def worst_ratio(got, ref, rtol=1e-4, floor=1e-9):
+    tol = rtol * np.abs(ref) + floor * np.abs(ref).max(axis=1, keepdims=True)
+    return float(np.max(np.abs(got - ref) / (tol + 1e-300)))
+
+
+def test_c1_full_frame_every_pixel():
+    plasma = generomak.get_plasma()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    flat = cb.flatten_scene(plasma, 651.279, 661.279, 512)
+    rays = generomak_camera_rays(plasma, (128, 128))
+    assert rays.n_rays == 16384
+    scene = EmissionScene(flat)
+    got, st = scene.render(rays)
+    scene.close()
+    ref, rst = oracle.emission_render(flat, rays)           # ~6e7 samples on all host threads
+    assert st["samples"] == rst["samples"] > 50_000_000
+    assert worst_ratio(got, ref) <= 1.0
+
+
+def test_c3_sixteen_pass_float32_frame():
+    """The benchmark's frame: 16 stratified sub-pixel passes accumulated with weight 1/16 into a float32 frame through float32
+    per-warp accumulators (2048 bins).  Measured against the same passes into a float64 frame through float64 accumulators
+    (CB2_ACC=f64) on 4096 random pixels of the 1024 x 1024 camera, and against the oracle on two of them (32 oracle rays)."""
+    import torch
+    plasma, flat = bench.build_scene(2048)
+    rng = np.random.default_rng(11)
+    pix = np.sort(rng.choice(1024 * 1024, size=4096, replace=False))
+    passes = [bench.make_rays(plasma, 1024, pix, k) for k in range(16)]
+    frames = {}
+    for acc in ("f32", "f64"):
+        os.environ["CB2_ACC"] = acc
+        try:
+            scene = EmissionScene(flat)
+        finally:
+            del os.environ["CB2_ACC"]
+        out = torch.zeros((pix.size, 2048), dtype=torch.float32 if acc == "f32" else torch.float64, device="cuda:0")
+        for k, r in enumerate(passes):
+            scene.render_device(DeviceRays(r), out, scale=1.0 / 16, accumulate=k > 0)
+        torch.cuda.synchronize()
+        frames[acc] = out.cpu().numpy().astype(np.float64)
+        scene.close()
+    a, b = frames["f32"], frames["f64"]
+    dev = np.abs(a - b) / (np.abs(b) + 1e-9 * np.abs(b).max(axis=1, keepdims=True))
+    print("float32 frame vs float64 frame over 16 passes: max %.3g, 99.9th percentile %.3g, median %.3g" % (
+        dev.max(), np.quantile(dev, 0.999), np.median(dev)))
+    assert dev.max() <= 2e-5                                # a fifth of the parity tolerance at the very worst bin
+    assert np.quantile(dev, 0.999) <= 3e-6
+    sel = np.array([100, 3000])
+    ref = np.zeros((2, 2048))
+    for r in passes:
+        part, _ = oracle.emission_render(flat, r.subset(sel))
+        ref += part / 16
+    assert worst_ratio(a[sel], ref) <= 1.0 and worst_ratio(b[sel], ref) <= 1.0
+
+
+def test_c4_full_grid_sixty_four_rows():
+    import torch
+    rtc = RayTransferCylinder(radius_outer=2.41, height=3.35, n_radius=400, n_height=800, radius_inner=0.73,
+                              transform=cb.translate(0, 0, -1.8))
+    cam = cb.PinholeCamera((512, 512), fov=45, transform=cb.look_at((2.3, 0, 1.25), (1.0, 0.8, -0.5)))
+    o, d = cam.rays()
+    rays = cb.ray_segments(rtc.primitive, o, d, rtc.transform)
+    assert rays.n_rays == 262144
+    scene = RayTransferScene(rtc)
+    ro, cols, lens = scene.render_csr_device(DeviceRays(rays), capacity=4000 * rays.n_rays)
+    torch.cuda.synchronize()
+    ro = ro.cpu().numpy()
+    assert ro[-1] > 200_000_000
+    pick = np.sort(np.random.default_rng(4).choice(rays.n_rays, size=64, replace=False))
+    desc, keep = rtc.descriptor()
+    ref, _ = oracle.rt_render_dense(desc, rays.subset(pick))
+    for k, r in enumerate(pick):
+        c = cols[ro[r]:ro[r + 1]].cpu().numpy()
+        v = lens[ro[r]:ro[r + 1]].cpu().numpy()
+        row = np.zeros(rtc.bins)
+        row[c] = v
+        assert np.unique(c).size == c.size                  # one entry per touched source
+        nz = ref[k] > 0
+        assert np.array_equal(row > 0, nz), r
+        if nz.any():
+            assert np.max(np.abs(row[nz] - ref[k][nz]) / ref[k][nz]) <= 1e-5, r
+    scene.close()
+
+
+def demo_beam_scene():
+    """demos/beam.py:44-100: Gaussian-volume plasma of D+, He2+, C6+, Ne10+ (sigma 0.25 m, 9e19 m^-3, 1 + 4 keV, 200 km/s flow
+    along x, B = (1, 1, 1)), 60 keV/amu deuterium beam from (1, 0, 0) along -x through the plasma centre; synthetic ADF12/21/22-shaped rates."""
+    sigma, n0 = 0.25, 9e19
+    temperature = cb.GaussianVolume(4000.0, sigma, offset=1000.0)
+    flow = cb.ConstantVector3D(200e3, 0.0, 0.0)
+    plasma = cb.Plasma(name="demos/beam.py plasma")
+    species = []
+    zsum = 0.0
+    for element, charge, frac in ((cb.deuterium, 1, 0.94), (cb.helium, 2, 0.04), (cb.carbon, 6, 0.01), (cb.neon, 10, 0.01)):
+        species.append(cb.Species(element, charge, cb.Maxwellian(cb.GaussianVolume(frac * n0, sigma), temperature, flow,
+                                                                   element.atomic_weight * 1.66053906660e-27)))
+        zsum += frac * charge
+    plasma.composition = species
+    plasma.electron_distribution = cb.Maxwellian(cb.GaussianVolume(zsum * n0, sigma), temperature, flow, 9.1093837015e-31)
+    plasma.b_field = cb.ConstantVector3D(1.0, 1.0, 1.0)
+    atomic = cb.SyntheticADAS(permit_extrapolation=True)
+    balmer = atomic.wavelength
+    atomic.wavelength = lambda ion, charge, transition: 529.05 if ion is cb.carbon else balmer(ion, charge, transition)
+    plasma.atomic_data = atomic
+    plasma.geometry = cb.Sphere(sigma * 5.0)
+    beam = cb.Beam(transform=cb.look_at((1.0, 0.0, 0.0), (0.0, 0.0, 0.0)))     # translate(1, 0, 0) * rotate(90, 0, 0): z axis along -x
+    beam.atomic_data, beam.plasma = atomic, plasma
+    beam.attenuator = cb.SingleRayAttenuator(clamp_to_zero=True)
+    beam.energy, beam.power, beam.temperature, beam.element = 60000, 3e6, 10, cb.deuterium
+    beam.sigma, beam.divergence_x, beam.divergence_y, beam.length = 0.025, 0.5, 0.5, 3.0
+    beam.integrator = cb.NumericalIntegrator(step=0.02, min_samples=10)
+    beam.models = [cb.BeamEmissionLine(cb.Line(cb.deuterium, 0, (3, 2))), cb.BeamCXLine(cb.Line(cb.carbon, 5, (8, 7)))]
+    return plasma, beam
+
+
+def test_c5_fibre_bundle_on_the_demo_beam():
+    plasma, beam = demo_beam_scene()
+    group = cb.FibreOpticGroup()
+    b2w = np.asarray(beam.transform)
+    zs, xs = np.meshgrid(np.linspace(0.4, 1.6, 16), np.linspace(-0.02, 0.02, 16), indexing="ij")
+    for z, x in zip(zs.ravel(), xs.ravel()):
+        target = (b2w @ np.array([x, 0.0, z, 1.0]))[:3]
+        group.add_observer(cb.FibreOptic(transform=cb.look_at((0.2, 0.3, 1.2), tuple(target)), acceptance_angle=0.5, radius=0.001, pixel_samples=8))
+    assert len(group.observers) == 256
+    o, d, _, _ = group.gather_rays()
+    rays = cb.beam_ray_segments(beam, o, d)
+    assert rays.n_rays == 256 * 8 and rays.n_segments > 1500
+    for lo, hi, bins in ((650.0, 662.0, 1024), (526.0, 532.0, 1024)):
+        flat = cb.flatten_beam_scene(beam, lo, hi, bins)
+        scene = EmissionScene(flat)
+        got, st = scene.render(rays)
+        scene.close()
+        ref, rst = oracle.emission_render(flat, rays)
+        assert st["samples"] == rst["samples"] and ref.max() > 0
+        assert worst_ratio(got, ref) <= 1.0, (lo, hi)
