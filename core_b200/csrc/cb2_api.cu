@@ -436,17 +436,23 @@ static int convert_axisym(Arena& A, const cb2_axisym& ax, DevAxisym& o) {
         // can cross the horizontal ray of a point in that row — the same edge test on ~5 instead of all n_lcfs edges
         std::vector<int> rstart(gy + 1, 0);
         std::vector<float4> redges;
+        std::vector<double2> redges_d;
         for (int j = 0; j < gy; j++) {
             rstart[j] = (int)redges.size();
             for (int a = 0, b = e.n_lcfs - 1; a < e.n_lcfs; b = a++) {
                 const double yi = e.lcfs_polygon[2 * a + 1], yj = e.lcfs_polygon[2 * b + 1];
                 const int j0 = (int)floor((fmin(yi, yj) - pymin) * icy) - 1, j1 = (int)floor((fmax(yi, yj) - pymin) * icy) + 1;
-                if (j >= j0 && j <= j1) redges.push_back(edges[a]);
+                if (j >= j0 && j <= j1) {
+                    redges.push_back(edges[a]);
+                    redges_d.push_back(make_double2(e.lcfs_polygon[2 * a], yi));
+                    redges_d.push_back(make_double2(e.lcfs_polygon[2 * b], yj));
+                }
             }
         }
         rstart[gy] = (int)redges.size();
         o.poly_row_start = A.upload(rstart);
         o.poly_row_edges = A.upload(redges);
+        o.poly_row_edges_d = A.upload(redges_d);
     }
     if (ax.n_mask < 1 || ax.n_mask > 8) return cb2_fail(CB2_ERR_VALUE, "blend mask table must have 1..8 points");
     o.n_mask = ax.n_mask;

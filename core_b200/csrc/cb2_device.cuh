@@ -187,18 +187,40 @@ struct AxCtx {
     bool b_outside;  // the B-field was taken from the clamped psi grid (counted as out of domain only if B is actually used)
 };
 
-__device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py) {
+// the even-odd crossing test in float64 with the oracle's expression (cherab/core/math/mask.pyx:53-67 as restated there): taken by
+// the few samples whose float32 test comes within rounding of a vertex height or of an edge — the blend weight jumps at the LCFS
+// polygon (psi_n is not exactly 1 on its chords), so a sample on the wrong side shows in the pixel (found by the full C1 frame)
+static __device__ __noinline__ bool polygon_contains_exact(const DevAxisym& A, int gj, double px, double py) {
+    int crossings = 0;
+    const int k1 = __ldg(A.poly_row_start + gj + 1);
+    for (int k = __ldg(A.poly_row_start + gj); k < k1; k++) {
+        const double2 a = __ldg(A.poly_row_edges_d + 2 * k), b = __ldg(A.poly_row_edges_d + 2 * k + 1);   // (xi, yi), (xj, yj)
+        if (((a.y > py) != (b.y > py)) && (px < __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(b.x, a.x), __dsub_rn(py, a.y)), __dsub_rn(b.y, a.y)), a.x)))
+            crossings++;
+    }
+    return crossings & 1;
+}
+
+__device__ __forceinline__ bool polygon_contains(const DevAxisym& A, float px, float py, double pxd, double pyd) {
     if (px < A.poly_xmin || px > A.poly_xmax || py < A.poly_ymin || py > A.poly_ymax) return false;
     // coarse grid: only boundary cells need the edge loop (even-odd crossing test, mask.pyx:53-67)
     const int gi = min((int)((px - A.poly_xmin) * A.p_icx), A.pgx - 1), gj = min((int)((py - A.poly_ymin) * A.p_icy), A.pgy - 1);
     const int cls = __ldg(A.poly_cls + gi * A.pgy + gj);
     if (cls != 2) return cls == 1;
     int crossings = 0;
+    bool unsure = false;
     const int k1 = __ldg(A.poly_row_start + gj + 1);
     for (int k = __ldg(A.poly_row_start + gj); k < k1; k++) {
         const float4 e = __ldg(A.poly_row_edges + k);  // (xi, yi, yj, slope)
-        if (((e.y > py) != (e.z > py)) && (px < fmaf(py - e.y, e.w, e.x))) crossings++;
+        // float32 coordinates carry ~1.2e-7 m of rounding each: a decision inside 1e-6 m is left to the float64 test
+        unsure = unsure || fabsf(e.y - py) < 1e-6f || fabsf(e.z - py) < 1e-6f;
+        if ((e.y > py) != (e.z > py)) {
+            const float xi = fmaf(py - e.y, e.w, e.x);
+            unsure = unsure || fabsf(px - xi) < 1e-6f * (1.0f + fabsf(e.w));
+            if (px < xi) crossings++;
+        }
     }
+    if (unsure) return polygon_contains_exact(A, gj, pxd, pyd);
     return crossings & 1;
 }
 
@@ -258,7 +280,7 @@ __device__ __forceinline__ void ax_setup(const DevScene& S, double xd, double yd
     c.m = 0.f; c.tri = -1; c.ci = 0; c.ct = 0.f; c.psi = 0.f; c.in_lcfs = false; c.b_outside = false;
     c.br = c.bt = c.bz = 0.f;
     if (!A.present) return;
-    const bool in_poly = polygon_contains(A, c.R, c.Z);
+    const bool in_poly = polygon_contains(A, c.R, c.Z, r64, zd);
     Cell2 cell;
     bool have_cell = false;
     if (in_poly) {

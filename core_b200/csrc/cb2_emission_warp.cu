@@ -1125,7 +1125,7 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
             if (active) {
                 float m = 0.f, psi = 0.f;
                 Cell2 cell;
-                if (polygon_contains(A, R, Z)) {
+                if (polygon_contains(A, R, Z, r64, pzd)) {
                     cell = locate2d(A.psin, R, Z);
                     if (!cell.inside) ood++;
                     psi = fmaxf(eval2d(A.psin, cell), 0.f);

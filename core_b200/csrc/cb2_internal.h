@@ -92,6 +92,7 @@ struct DevAxisym {
     const unsigned char* poly_cls;
     const int* poly_row_start;       // [pgy + 1] per grid row: the edges that can cross a horizontal ray starting in that row
     const float4* poly_row_edges;
+    const double2* poly_row_edges_d; // the same edges in float64, (xi, yi), (xj, yj): exact test for samples within rounding of the boundary
     int n_mask;
     float mask_x[8], mask_y[8];
     // mesh
