@@ -463,7 +463,7 @@ def main():
                     e.pop("fp32", None)
                     e["tensor"] = {"achieved": 3.0 * flop / t * 1e-12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * flop / t * 1e-12 / tf32_peak,
                                    "fp32_equivalent_tflops": flop / t * 1e-12,
-                                   "note": "cuBLAS TF32 GEMMs (tcgen05) x3, includes the tf32 hi/lo split kernel; peak = measured bf16 / 2"}
+                                   "note": "hand-written tcgen05 kind::tf32 kernel (contract_tc_kernel: 3 MMAs per k-block on hi/lo operand tiles, frame += fused); peak = measured bf16 / 2"}
                 kernels[name] = e
             dom = max((k for k in kernels if k != "helpers"), key=lambda k: kernels[k]["ms_per_step"])
         else:

@@ -9,6 +9,7 @@ from .atomic import (AtomicData, ConstantRate, Element, Line, RateTable, RateTab
                      hydrogen, neon, nitrogen, tritium)
 from .beam import (Beam, BeamCXLine, BeamEmissionLine, BeamCXTable, BeamStoppingTable, ConstantBeamCXPEC, SingleRayAttenuator, beam_ray_segments,
                    flatten_beam_scene)
+from .first_wall import FirstWall, load_first_wall
 from .flatten import FlatScene, RayBatch, flatten_scene
 from .geometry import Box, HollowCylinder, PinholeCamera, Sphere, look_at, ray_segments, stratified_offsets, translate
 from .inversions import SartSolver, invert_constrained_sart, invert_sart

@@ -157,12 +157,17 @@ class SartDesc(C.Structure):
                 ("laplacian_dense", C.c_void_p), ("lap_row_offset", C.c_void_p), ("lap_columns", C.c_void_p), ("lap_values", C.c_void_p)]
 
 
+class WallDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("_pad", C.c_int32), ("n_triangles", C.c_int64), ("vertices", c_double_p)]
+
+
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
     "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
     "cb2_pinhole_rays_device",
+    "cb2_wall_create", "cb2_wall_destroy", "cb2_wall_hit", "cb2_wall_clip_device",
     "cb2_sart_create", "cb2_sart_destroy", "cb2_sart_set_laplacian", "cb2_sart_solve", "cb2_sart_info",
 ]
 
@@ -202,6 +207,10 @@ def load_library():
     lib.cb2_rt_render_csr_device.argtypes = [vp, C.POINTER(Rays), vp, vp, vp, C.c_int64, c_int64_p, vp, vp]
     lib.cb2_pinhole_rays_device.argtypes = [C.POINTER(PinholeDesc), C.POINTER(PrimitiveDesc), vp, C.c_int64, C.c_double, C.c_double,
                                             C.POINTER(Rays), vp]
+    lib.cb2_wall_create.argtypes = [C.POINTER(WallDesc), C.c_int, C.POINTER(vp)]
+    lib.cb2_wall_destroy.argtypes = [vp]
+    lib.cb2_wall_hit.argtypes = [vp, c_double_p, c_double_p, C.c_int64, c_double_p]
+    lib.cb2_wall_clip_device.argtypes = [vp, C.POINTER(Rays), vp, vp]
     lib.cb2_sart_create.argtypes = [C.POINTER(SartDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_sart_destroy.argtypes = [vp]
     lib.cb2_sart_set_laplacian.argtypes = [vp, vp, vp, vp, vp]

@@ -457,33 +457,76 @@ struct LineRec {
     int kind;                // 0 nothing, 1 series, 2 erfc differences, 3 modified Lorentzian
 };
 
+// Packed float32 pairs (sm_100a: add / mul / fma .f32x2 = SASS FADD2 / FMUL2 / FFMA2, one issue slot for two lanes' worth of
+// arithmetic).  bin_kernel is issue-bound, not pipe-bound (r1c ncu: issue-active 81 %, FMA pipe 47 %, XU 51 %): pairing two
+// bins per instruction takes the series evaluation from ~10 to ~6 issue slots per bin and leaves MUFU.EX2 as the bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// series coefficients of a lane's component, each duplicated into both halves of a pair
+struct SeriesPair {
+    f32x2 c0, c1, c2, c3, c4;
+};
+__device__ __forceinline__ SeriesPair series_pair(const LineRec& R, bool mine) {
+    const float c0 = mine ? R.s0 : 0.f, c1 = mine ? R.s1 : 0.f, c2 = mine ? R.s2 : 0.f, c3 = mine ? R.s3 : 0.f, c4 = mine ? R.s4 : 0.f;
+    SeriesPair P;
+    P.c0 = pack2(c0, c0); P.c1 = pack2(c1, c1); P.c2 = pack2(c2, c2); P.c3 = pack2(c3, c3); P.c4 = pack2(c4, c4);
+    return P;
+}
+// bin integrals of two bins at x' = (X.lo, X.hi): 2^(-x'^2) * poly4(x'^2)
+__device__ __forceinline__ f32x2 series_eval2(const SeriesPair& P, f32x2 X) {
+    const f32x2 m2 = mul2(X, X);
+    float a, b;
+    unpack2(m2, a, b);
+    const f32x2 e = pack2(ex2_approx(-a), ex2_approx(-b));
+    return mul2(e, fma2(fma2(fma2(fma2(P.c4, m2, P.c3), m2, P.c2), m2, P.c1), m2, P.c0));
+}
+
 // 32-bin window, series lanes, lane-permuted bin order (register r of lane l holds bin r ^ l) so that the butterfly needs
-// no selects; lane l ends up with window bin l.
+// no selects; lane l ends up with window bin l.  Registers are evaluated as the pairs (r, r + 1), r even.
 template <typename AccT>
 __device__ __forceinline__ void window_series_xor(const LineRec& R, int wbase, int c0_int, int bins, AccT* __restrict__ wacc, int lane) {
     const bool mine = R.kind == 1 && R.hi > wbase && R.lo < wbase + 32;
-    const float c0 = mine ? R.s0 : 0.f, c1 = mine ? R.s1 : 0.f, c2 = mine ? R.s2 : 0.f, c3 = mine ? R.s3 : 0.f, c4 = mine ? R.s4 : 0.f;
+    const SeriesPair P = series_pair(R, mine);
     // per-lane steps of the XOR-ordered walk: r ^ l = l + sum_{b in r} (+-)2^b
-    float db[5];
+    float db0;
+    f32x2 db[5];
 #pragma unroll
-    for (int b = 0; b < 5; b++) db[b] = ((lane >> b) & 1) ? -(float)(1 << b) * R.kx : (float)(1 << b) * R.kx;
+    for (int b = 0; b < 5; b++) {
+        const float d = ((lane >> b) & 1) ? -(float)(1 << b) * R.kx : (float)(1 << b) * R.kx;
+        if (b == 0) db0 = d;
+        db[b] = pack2(d, d);
+    }
     const float xb = fmaf((float)(wbase + lane), R.kx, R.xoff);
-    float part[32];
+    f32x2 X[16], part[16];
+    X[0] = pack2(xb, xb + db0);
 #pragma unroll
-    for (int r = 0; r < 32; r++) {
-        float x = xb;
-#pragma unroll
-        for (int b = 0; b < 5; b++)
-            if (r & (1 << b)) x += db[b];
-        const float m2 = x * x;
-        part[r] = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(c4, m2, c3), m2, c2), m2, c1), m2, c0);
+    for (int j = 1; j < 16; j++) {
+        // pair j holds registers (2j, 2j + 1): x = x of the pair without j's top bit + the step of that bit
+        int top = 3;
+        while (!(j & (1 << top))) top--;
+        X[j] = add2(X[j & ~(1 << top)], db[top + 1]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int j = 0; j < 16; j++) part[j] = series_eval2(P, X[j]);
+    // butterfly part[i] += shfl_xor(part[i + o], o) on the register index; pairs move as two 32-bit shuffles, add as one FADD2
 #pragma unroll
-        for (int i = 0; i < o; i++) part[i] += __shfl_xor_sync(FULL, part[i + o], o);
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < o; j++) {
+            float a, b;
+            unpack2(part[j + o], a, b);
+            part[j] = add2(part[j], pack2(__shfl_xor_sync(FULL, a, 2 * o), __shfl_xor_sync(FULL, b, 2 * o)));
+        }
+    float p0, p1;
+    unpack2(part[0], p0, p1);
+    p0 += __shfl_xor_sync(FULL, p1, 1);
     const int bin = c0_int + wbase + lane;
-    if (bin >= 0 && bin < bins && part[0] != 0.f) wacc[bin] += (AccT)part[0];
+    if (bin >= 0 && bin < bins && p0 != 0.f) wacc[bin] += (AccT)p0;
 }
 
 // transpose-reduce WB registers over the warp: inside each group of WB lanes a lane keeps, after the step with offset o,
@@ -509,14 +552,15 @@ __device__ __forceinline__ float reduce_window(float (&part)[WB], int lane) {
 template <int WB, typename AccT>
 __device__ __forceinline__ void window_series_tail(const LineRec& R, int wbase, int c0_int, int bins, AccT* __restrict__ wacc, int lane) {
     const bool mine = R.kind == 1 && R.hi > wbase && R.lo < wbase + WB;
-    const float c0 = mine ? R.s0 : 0.f, c1 = mine ? R.s1 : 0.f, c2 = mine ? R.s2 : 0.f, c3 = mine ? R.s3 : 0.f, c4 = mine ? R.s4 : 0.f;
+    const SeriesPair P = series_pair(R, mine);
     const float x0 = fmaf((float)wbase, R.kx, R.xoff);
+    const f32x2 k2 = pack2(2.0f * R.kx, 2.0f * R.kx);
+    f32x2 X = pack2(x0, x0 + R.kx);
     float part[WB];
 #pragma unroll
-    for (int w = 0; w < WB; w++) {
-        const float x = fmaf((float)w, R.kx, x0);
-        const float m2 = x * x;
-        part[w] = ex2_approx(-m2) * fmaf(fmaf(fmaf(fmaf(c4, m2, c3), m2, c2), m2, c1), m2, c0);
+    for (int w = 0; w < WB; w += 2) {
+        unpack2(series_eval2(P, X), part[w], part[w + 1]);
+        X = add2(X, k2);
     }
     const float v = reduce_window<WB>(part, lane);
     const int bin = c0_int + wbase + lane;

@@ -108,12 +108,13 @@ class DevicePinhole:
         return buf
 
 
-def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None):
+def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None, wall=None):
     """Mean spectral radiance per pixel over pixel_samples_side^2 stratified sub-pixel samples, on the device.
 
     ``scene``: engine.EmissionScene or engine.PlasmaRenderer; ``pinhole``: DevicePinhole.  Returns a torch tensor
     [n_pixels, bins] (float32 unless ``dtype``/``frame`` say otherwise) — ``SpectralRadiancePipeline2D.frame.mean`` of the
-    reference flow, W / (m^2 sr nm)."""
+    reference flow, W / (m^2 sr nm).  ``wall``: optional first_wall.FirstWall — every ray's chords end at its first wall hit
+    (what the opaque wall meshes do in the reference's scene graph, generomak/machine/first_wall.py:120-184)."""
     import torch
     bins = scene.scene.bins if hasattr(scene, "scene") else scene.bins
     if frame is None:
@@ -124,6 +125,8 @@ def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None):
     buf = DeviceRayBuffer(pinhole.n_rays, pinhole.device)
     for sx, sy in offsets:
         rays = pinhole.rays(sx, sy, out=buf)
+        if wall is not None:
+            wall.clip_device(rays)
         scene.render_device(rays, frame, scale=1.0 / len(offsets), accumulate=True)
     return frame
 
@@ -243,13 +246,16 @@ class _Observer0DGroup:
             owner.append(np.full(o.shape[0], i))
         return np.concatenate(os_), np.concatenate(ds_), np.concatenate(ws_), np.concatenate(owner)
 
-    def observe(self, scene, primitive, to_world=None):
-        """One device render for the whole group.  ``scene``: engine.EmissionScene / PlasmaRenderer.  Returns spectra[n_observers, bins]."""
+    def observe(self, scene, primitive, to_world=None, wall=None):
+        """One device render for the whole group.  ``scene``: engine.EmissionScene / PlasmaRenderer; ``wall``: optional
+        first_wall.FirstWall that ends every ray at its first hit.  Returns spectra[n_observers, bins]."""
         from .geometry import ray_segments
         if not self._observers:
             raise ValueError("The group has no observers.")
         o, d, w, owner = self.gather_rays()
         rays = ray_segments(primitive, o, d, to_world)
+        if wall is not None:
+            rays = wall.clip(rays)
         per_ray, _ = scene.render(rays)
         n = len(self._observers)
         num = np.zeros((n, per_ray.shape[1]))

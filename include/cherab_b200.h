@@ -485,6 +485,30 @@ int cb2_pinhole_rays_device(const cb2_pinhole* camera, const cb2_primitive* prim
                             double sub_x, double sub_y, cb2_rays* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * First-wall occlusion (replaces the role the wall meshes of cherab/generomak/machine/first_wall.py:120-184
+ * play in Raysect's tracer: a ray ends at its first opaque hit, so the volume integral of the plasma stops there).
+ * The wall is a soup of world-space triangles; a bounding-volume hierarchy is built on the host at create time and the
+ * first-hit search (float32 boxes grown by their rounding, float64 Moeller-Trumbore triangle test) runs on the device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cb2_wall_desc {
+    int32_t       abi_version;
+    int32_t       _pad;
+    int64_t       n_triangles;
+    const double* vertices;         /* HOST [n_triangles][3 vertices][3] world coordinates, m */
+} cb2_wall_desc;
+
+typedef struct cb2_wall cb2_wall;
+
+int cb2_wall_create(const cb2_wall_desc* desc, int device, cb2_wall** out);
+int cb2_wall_destroy(cb2_wall* wall);
+/* t_hit[n] (HOST): distance, in units of |direction|, from origin[i] to the first triangle hit along direction[i] (t > 0),
+ * +inf for a miss.  origin / direction: HOST [n][3]. */
+int cb2_wall_hit(cb2_wall* wall, const double* origin, const double* direction, int64_t n, double* t_hit);
+/* Clips DEVICE ray segments in place on `stream`: seg_t1 = max(seg_t0, min(seg_t1, t_hit(ray))) — a segment behind the hit
+ * becomes empty and the marcher skips it (segment counts and offsets do not change).  t_hit_dev: optional DEVICE double[n_rays]. */
+int cb2_wall_clip_device(cb2_wall* wall, const cb2_rays* rays_dev, double* t_hit_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SART inversion on the device-resident geometry matrix (replaces
  * cherab/tools/inversions/sart.pyx:26-155 invert_sart, :161-302 invert_constrained_sart and the OpenCL solver
  * cherab/tools/inversions/opencl/sart_opencl.py:33-318 + sart_kernels.cl:28-148).

@@ -1588,3 +1588,40 @@ int cb2o_rt_render_dense(const cb2_rt_desc* desc, const cb2_rays* rays, double* 
     if (stats) { memset(stats, 0, sizeof *stats); stats->rt_steps = steps; }
     return CB2_OK;
 }
+
+/* =================================================================================================
+ * First-wall occlusion — the role of the wall meshes of cherab/generomak/machine/first_wall.py:120-184 in Raysect's tracer:
+ * distance to the first opaque hit.  Brute force: every ray against every triangle, Moeller-Trumbore in float64.
+ * [raysect: its Mesh primitive stores float32 vertices and uses a watertight test — hit distances of the real reference carry
+ * float32 rounding; parity unpinned]
+ * ============================================================================================== */
+static double tri_hit(const double* v, const double o[3], const double d[3], double t_min) {
+    double e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
+    double e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+    double px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+    double det = e1x * px + e1y * py + e1z * pz;
+    if (det == 0.0) return INFINITY;
+    double inv = 1.0 / det;
+    double sx = o[0] - v[0], sy = o[1] - v[1], sz = o[2] - v[2];
+    double u = (sx * px + sy * py + sz * pz) * inv;
+    if (u < 0.0 || u > 1.0) return INFINITY;
+    double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+    double w = (d[0] * qx + d[1] * qy + d[2] * qz) * inv;
+    if (w < 0.0 || u + w > 1.0) return INFINITY;
+    double t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+    return t > t_min ? t : INFINITY;
+}
+
+int cb2o_wall_hit(const double* vertices, int64_t n_triangles, const double* origin, const double* direction, int64_t n, double* t_hit) {
+    if (!vertices || !origin || !direction || !t_hit) return fail(CB2_ERR_VALUE, "null argument");
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; i++) {
+        double best = INFINITY;
+        for (int64_t k = 0; k < n_triangles; k++) {
+            double t = tri_hit(vertices + 9 * k, origin + 3 * i, direction + 3 * i, 1e-9);
+            if (t < best) best = t;
+        }
+        t_hit[i] = best;
+    }
+    return CB2_OK;
+}

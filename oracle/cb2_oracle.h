@@ -34,6 +34,8 @@ double cb2o_interp3d_cubic(const double* x, const double* y, const double* z, co
                            double px, double py, double pz);                                             /* raysect Interpolator3DArray 'cubic' */
 double cb2o_thermal_cx_pec_evaluate(const cb2_rate3d* pec, double wavelength, double ne, double te, double td); /* pec.pyx:186-194 */
 
+/* first wall hit of n rays against n_triangles world-space triangles [n_triangles][3][3], brute force (first_wall.py:120-184) */
+int cb2o_wall_hit(const double* vertices, int64_t n_triangles, const double* origin, const double* direction, int64_t n, double* t_hit);
 #ifdef __cplusplus
 }
 #endif

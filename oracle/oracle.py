@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcb2_oracle.so")
 ORACLE_SYMBOLS = ["cb2o_abi_version", "cb2o_last_error", "cb2o_emission_render", "cb2o_sample_state", "cb2o_state_width", "cb2o_beam_sample",
                   "cb2o_rt_render_dense", "cb2o_add_gaussian_line", "cb2o_add_lorentzian_line", "cb2o_interp1d_cubic",
                   "cb2o_interp2d_cubic", "cb2o_gauss_legendre", "cb2o_gaunt_factor", "cb2o_pec_evaluate", "cb2o_interp3d_cubic",
-                  "cb2o_thermal_cx_pec_evaluate"]
+                  "cb2o_thermal_cx_pec_evaluate", "cb2o_wall_hit"]
 _lib = None
 
 
@@ -89,6 +89,18 @@ def sample_state(flat, points):
     out = np.zeros((pts.shape[0], w), dtype=np.float64)
     _abi.check(l, l.cb2o_sample_state(C.byref(flat.desc), _dp(pts), pts.shape[0], _dp(out)), "cb2o_last_error")
     return out
+
+
+def wall_hit(triangles, origin, direction):
+    """Distance to the first hit of every ray with the triangle soup [n, 3, 3] (+inf: miss), brute force in float64."""
+    l = lib()
+    tri = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 9)
+    o = np.ascontiguousarray(origin, dtype=np.float64).reshape(-1, 3)
+    d = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1, 3)
+    t = np.empty(o.shape[0])
+    l.cb2o_wall_hit.argtypes = [_abi.c_double_p, C.c_int64, _abi.c_double_p, _abi.c_double_p, C.c_int64, _abi.c_double_p]
+    _abi.check(l, l.cb2o_wall_hit(_dp(tri), tri.shape[0], _dp(o), _dp(d), o.shape[0], _dp(t)), "cb2o_last_error")
+    return t
 
 
 def beam_sample(flat, beam_points):

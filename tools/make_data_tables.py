@@ -7,6 +7,8 @@ and bench.py never read /root/reference at run time.
   core_b200/data/generomak.npz      Generomak equilibrium + edge mesh + edge/core profiles
                                     (cherab/generomak/equilibrium/data/generomak_equilibrium.json,
                                      cherab/generomak/plasma/data/{edge,core}/*.json — SURVEY Appendix D)
+  core_b200/data/generomak_first_wall.npz  the first-wall component meshes (cherab/generomak/machine/data/first_wall/*.obj: vertices
+                                    float64 [n, 3] and triangles int32 [m, 3] per component, faces fan-triangulated)
   core_b200/data/atomic_tables.npz  free-free Gaunt factor table (cherab/core/atomic/data/maxwellian_free_free_gaunt_factor.json)
                                     and the Stark model coefficients (cherab/core/atomic/data/lineshape/stark/{h,d,t}.json)
 """
@@ -67,9 +69,39 @@ def atomic_tables():
     np.savez_compressed(os.path.join(OUT, "atomic_tables.npz"), **out)
 
 
+def read_obj(path):
+    """Wavefront OBJ -> (vertices [n, 3] float64, triangles [m, 3] int32); polygons are fan-triangulated, indices may be
+    negative (relative) and may carry /vt/vn suffixes."""
+    v, f = [], []
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith("v "):
+                v.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith("f "):
+                idx = []
+                for tok in line.split()[1:]:
+                    i = int(tok.split("/")[0])
+                    idx.append(i - 1 if i > 0 else len(v) + i)
+                for k in range(1, len(idx) - 1):
+                    f.append([idx[0], idx[k], idx[k + 1]])
+    return np.asarray(v, dtype=np.float64), np.asarray(f, dtype=np.int32)
+
+
+def first_wall():
+    wdir = os.path.join(REF, "cherab/generomak/machine/data/first_wall")
+    out = {}
+    for fn in sorted(os.listdir(wdir)):
+        if fn.endswith(".obj"):
+            v, f = read_obj(os.path.join(wdir, fn))
+            out[fn[:-4] + "_vertices"] = v
+            out[fn[:-4] + "_triangles"] = f
+    np.savez_compressed(os.path.join(OUT, "generomak_first_wall.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     generomak()
     atomic_tables()
-    for fn in ("generomak.npz", "atomic_tables.npz"):
+    first_wall()
+    for fn in ("generomak.npz", "atomic_tables.npz", "generomak_first_wall.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
