@@ -147,6 +147,10 @@ class PinholeDesc(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("width", C.c_double), ("to_world", C.c_double * 12)]
 
 
+class Observer0DDesc(C.Structure):
+    _fields_ = [("to_world", C.c_double * 12), ("radius", C.c_double), ("acceptance_angle", C.c_double), ("samples", C.c_int32), ("_pad", C.c_int32)]
+
+
 PRIM_HOLLOW_CYLINDER, PRIM_SPHERE, PRIM_BOX = range(3)
 
 
@@ -166,7 +170,7 @@ PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
     "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
-    "cb2_pinhole_rays_device",
+    "cb2_pinhole_rays_device", "cb2_observer0d_rays_device", "cb2_observer0d_reduce_device",
     "cb2_wall_create", "cb2_wall_destroy", "cb2_wall_hit", "cb2_wall_clip_device",
     "cb2_sart_create", "cb2_sart_destroy", "cb2_sart_set_laplacian", "cb2_sart_solve", "cb2_sart_info",
 ]
@@ -207,6 +211,8 @@ def load_library():
     lib.cb2_rt_render_csr_device.argtypes = [vp, C.POINTER(Rays), vp, vp, vp, C.c_int64, c_int64_p, vp, vp]
     lib.cb2_pinhole_rays_device.argtypes = [C.POINTER(PinholeDesc), C.POINTER(PrimitiveDesc), vp, C.c_int64, C.c_double, C.c_double,
                                             C.POINTER(Rays), vp]
+    lib.cb2_observer0d_rays_device.argtypes = [C.POINTER(Observer0DDesc), C.c_int64, C.POINTER(PrimitiveDesc), C.POINTER(Rays), vp, vp]
+    lib.cb2_observer0d_reduce_device.argtypes = [vp, C.c_int, vp, c_int64_p, c_double_p, C.c_int64, C.c_int32, vp, vp, vp]
     lib.cb2_wall_create.argtypes = [C.POINTER(WallDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_wall_destroy.argtypes = [vp]
     lib.cb2_wall_hit.argtypes = [vp, c_double_p, c_double_p, C.c_int64, c_double_p]

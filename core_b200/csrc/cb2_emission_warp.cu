@@ -38,6 +38,9 @@
 #include "cb2_device.cuh"
 
 #define EVAL_CUTOFF_SIGMA 7.0f
+#ifndef CB2_FUSED_MINB
+#define CB2_FUSED_MINB 4
+#endif
 
 // per-sample state shared by the line models of one sample
 struct LineCache {
@@ -639,7 +642,7 @@ __device__ __forceinline__ void component_pass(int type, float cf, float width, 
                     const float ecut = (core_in ? EVAL_CUTOFF_SIGMA : 10.0f) * width;
                     R.lo = max(l, (int)fmaxf(floorf(cf - ecut), win_lo));
                     R.hi = min(h, (int)fminf(ceilf(cf + ecut), win_hi));
-                    const float kb = 0.70710678f / width;                    // delta / (sqrt(2) sigma), per bin
+                    const float kb = 0.70710678f * rcp_approx(width);         // delta / (sqrt(2) sigma), per bin
                     const float hh = 0.5f * kb;
                     if (hh <= (core_in ? H_SERIES_MAX : 0.035f)) {
                         const float h2 = hh * hh;
@@ -1289,6 +1292,221 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K1 fused (table-driven scenes): state_fast_kernel's per-sample state feeds component_pass of the same warp directly — lanes are
+// samples in both halves, so a lane's (centre, width, amplitude) never leaves the SM.  No line records cross HBM (they were 35x the
+// algorithmic bytes of the frame) and the table gathers of one warp overlap the bin arithmetic of the others.
+// The hot code stays small (table state ~ 20 KB + one rolled call site of component_pass), which the generic fused kernel of round 1
+// was not (instruction-fetch bound).  Blend-zone samples contribute nothing here: their groups are flagged (gblend) and get
+// zero-amplitude record rows, state_kernel<FIX> fills in the flagged lanes and bin_kernel adds those groups to the frame afterwards.
+// Shared memory: [moments double[k_pad]] [NW private accumulators AccT[bins_pad]] [NW x (n_lines + 2 NSP) x 32 float stage].
+// ------------------------------------------------------------------------------------------------------------------
+template <int NW, int MOM, int MINB, int NSP, typename AccT>
+__global__ void __launch_bounds__(NW * 32, MINB)
+fused_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevMemo FM, DevRays rays, const int64_t* __restrict__ gbase,
+                  unsigned* __restrict__ gblend, float* __restrict__ rec, unsigned long long* __restrict__ stats,
+                  float* __restrict__ mom_out, void* __restrict__ out, int out_f64, double scale, int accumulate, int count_samples) {
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_pad = MOM ? S.brems.k_pad : 0;
+    const int bins = S.bins, bins_pad = (bins + 31) & ~31;
+    const int n_lines = FM.n_lines;
+    double* mom = smem_d;
+    AccT* wall = reinterpret_cast<AccT*>(smem_d + k_pad);
+    AccT* wacc = wall + (size_t)warp * bins_pad;
+    float* stage = reinterpret_cast<float*>(wall + (size_t)NW * bins_pad) + (size_t)warp * (n_lines + 2 * NSP) * 32 + lane;
+    if (MOM)
+        for (int i = tid; i < k_pad; i += NW * 32) mom[i] = 0.0;
+    for (int i = lane; i < bins_pad; i += 32) wacc[i] = (AccT)0;
+    __syncthreads();
+    const DevAxisym& A = S.ax;
+    const int64_t ray = blockIdx.x;
+    const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
+    const double dwx = rays.direction[3 * ray], dwy = rays.direction[3 * ray + 1], dwz = rays.direction[3 * ray + 2];
+    float dx, dy, dz;
+    {
+        const double d0 = xform_row(S.w2p, dwx, dwy, dwz, false), d1 = xform_row(S.w2p + 4, dwx, dwy, dwz, false),
+                     d2 = xform_row(S.w2p + 8, dwx, dwy, dwz, false);
+        const double dl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        dx = (float)(d0 / dl); dy = (float)(d1 / dl); dz = (float)(d2 / dl);
+    }
+    float vdc[NSP];
+#pragma unroll
+    for (int s = 0; s < NSP; s++) vdc[s] = FM.sp_v[s][0] * dx + FM.sp_v[s][1] * dy + FM.sp_v[s][2] * dz;
+    unsigned long long n_samples = 0;
+    unsigned n_brems = 0, ood = 0, n_gauss = 0, n_lorentz = 0;
+    const int n_comp = S.n_comp, row_f4 = FM.row_f4;
+    const float4* const row0 = FM.edge ? FM.edge : FM.core;
+
+    int64_t G0 = gbase[ray];
+    int g_rot = 0;
+    for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
+        const SegGeom sgm = segment_geometry(S.w2p, S.step, S.min_samples, ox, oy, oz, dwx, dwy, dwz, rays.seg_t0[sg], rays.seg_t1[sg]);
+        const int iv = sgm.iv;
+        if (iv <= 0) continue;
+        const float hf = (float)sgm.h;
+        if (tid == 0) n_samples += (unsigned long long)iv + 1ull;
+        const int n_groups = iv / 32 + 1;
+        int first = (warp - g_rot) % NW;
+        if (first < 0) first += NW;
+        g_rot = (g_rot + n_groups) % NW;
+
+        for (int g = first; g < n_groups; g += NW) {
+            const int k = g * 32 + lane;
+            const bool active = k <= iv;
+            const double tk = __dmul_rn((double)k, sgm.h);
+            const double pxd = __dadd_rn(sgm.sx, __dmul_rn(tk, sgm.ivx)), pyd = __dadd_rn(sgm.sy, __dmul_rn(tk, sgm.ivy)),
+                         pzd = __dadd_rn(sgm.sz, __dmul_rn(tk, sgm.ivz));
+            float w = active ? ((k == 0 || k == iv) ? 0.5f * hf : hf) : 0.f;
+            const double r64 = __dsqrt_rn(__dadd_rn(__dmul_rn(pxd, pxd), __dmul_rn(pyd, pyd)));
+            const float R = (float)r64, Z = (float)pzd;
+            const float inv_r = R > 0.f ? 1.0f / R : 0.f;
+            const float cphi = R > 0.f ? (float)pxd * inv_r : 1.f, sphi = (float)pyd * inv_r;
+            int cls = 0;                                            // 0 vacuum, 1 table row, 2 blend zone
+            const float4 *pa = row0, *pb = row0;
+            float t = 0.f, ebr = 0.f, ebz = 0.f;
+            if (active) {
+                float m = 0.f, psi = 0.f;
+                Cell2 cell;
+                if (polygon_contains(A, R, Z, r64, pzd)) {
+                    cell = locate2d(A.psin, R, Z);
+                    if (!cell.inside) ood++;
+                    psi = fmaxf(eval2d(A.psin, cell), 0.f);
+                    if (psi <= 1.0f) {
+                        m = A.mask_y[0];
+                        const float p = fminf(fmaxf(psi, A.mask_x[0]), A.mask_x[A.n_mask - 1]);
+                        for (int q = 0; q + 1 < A.n_mask; q++)
+                            if (p >= A.mask_x[q] && p <= A.mask_x[q + 1]) {
+                                m = A.mask_y[q] + (p - A.mask_x[q]) / (A.mask_x[q + 1] - A.mask_x[q]) * (A.mask_y[q + 1] - A.mask_y[q]);
+                                break;
+                            }
+                    }
+                }
+                if (m >= 1.0f && FM.core_n > 0) {
+                    cls = 1;
+                    const float fi = fminf(psi, FM.psi_max) * FM.core_scale;
+                    const int i0 = min((int)fi, FM.core_n - 1);
+                    t = fi - (float)i0;
+                    pa = FM.core + (size_t)i0 * row_f4;
+                    pb = pa + row_f4;
+                    if (S.need_pol) {
+                        const float br = -eval2d(A.dpsi_dz, cell), bz = eval2d(A.dpsi_dr, cell);
+                        const float n2 = br * br + bz * bz;
+                        if (n2 > 0.f) { const float inv = rsqrtf(n2); ebr = br * inv; ebz = bz * inv; }
+                    }
+                } else if (m > 0.f) {
+                    cls = 2;
+                } else {
+                    const int tri = mesh_locate(A, r64, pzd);
+                    if (tri >= 0) { cls = 1; pa = pb = FM.edge + (size_t)tri * row_f4; ebr = 1.f; }
+                }
+            }
+            const unsigned live_mask = __ballot_sync(FULL, cls != 0 && w > 0.f);
+            const unsigned blend_mask = __ballot_sync(FULL, cls == 2 && w > 0.f);
+            const int64_t G = G0 + g;
+            if (lane == 0) gblend[G] = blend_mask;
+            if (!live_mask) continue;
+            if (cls != 1) w = 0.f;
+            // species block: sqrt(Ts) and v.d, staged per lane for the rolled component loop
+            const float aa = cphi * dx + sphi * dy, bb = cphi * dy - sphi * dx;
+#pragma unroll
+            for (int s = 0; s < NSP; s++) {
+                float sq = 0.f, vd = 0.f;
+                if (s < FM.n_sp) {
+                    const float4 q = lerp4(__ldg(pa + s), __ldg(pb + s), t);
+                    sq = q.x;
+                    const float cr = ebr * q.z - ebz * q.w, cz = ebz * q.z + ebr * q.w;
+                    vd = FM.sp_const[s] ? vdc[s] : fmaf(cr, aa, fmaf(q.y, bb, cz * dz));
+                }
+                stage[(n_lines + s) * 32] = sq;
+                stage[(n_lines + NSP + s) * 32] = vd;
+            }
+            for (int l4 = 0; l4 < n_lines; l4 += 4) {
+                const float4 q = lerp4(__ldg(pa + FM.off_amp + (l4 >> 2)), __ldg(pb + FM.off_amp + (l4 >> 2)), t);
+                stage[l4 * 32] = q.x * w;
+                if (l4 + 1 < n_lines) stage[(l4 + 1) * 32] = q.y * w;
+                if (l4 + 2 < n_lines) stage[(l4 + 2) * 32] = q.z * w;
+                if (l4 + 3 < n_lines) stage[(l4 + 3) * 32] = q.w * w;
+            }
+            {
+                // Bremsstrahlung block (and the out-of-domain count of the row's state)
+                const float4 a0 = __ldg(pa + FM.off_brems);
+                if (w > 0.f) ood += (unsigned)a0.y;
+                if (MOM) {
+                    const float4 q0 = lerp4(a0, __ldg(pb + FM.off_brems), t);
+                    const float4 q1 = lerp4(__ldg(pa + FM.off_brems + 1), __ldg(pb + FM.off_brems + 1), t);
+                    float U[CB2_MAX_BREMS_Z] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0.f, 0.f};
+                    if (FM.n_z > 6) {
+                        const float4 q2 = lerp4(__ldg(pa + FM.off_brems + 2), __ldg(pb + FM.off_brems + 2), t);
+                        U[6] = q2.x; U[7] = q2.y;
+                    }
+                    const bool lb = w > 0.f && q0.x >= 1.0f;
+                    if (lb) n_brems += (unsigned)S.bins;
+                    brems_scatter(S.brems, lb, w, q0.x, U, mom, lane);
+                }
+            }
+            if (blend_mask) {
+                // the flagged lanes' rows come from the fix-up pass; every other lane of the group must read as dark there
+                float* z = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + 64 + lane;
+                for (int c = 0; c < n_comp; c++) z[(size_t)c * REC_FLOATS_PER_COMP] = 0.f;
+            }
+            // line components of this group, straight into the warp's accumulator (one call site of component_pass)
+            for (int l = 0; l < n_lines; l++) {
+                const MemoLine& L = FM.lines[l];
+                const float sqs = stage[(n_lines + L.slot) * 32], vds = stage[(n_lines + NSP + L.slot) * 32];
+                float amp = stage[l * 32];
+                if (!(amp > 0.f) || !(sqs > 0.f)) amp = 0.f;
+                if (!__any_sync(FULL, amp > 0.f)) continue;
+                const float width = L.sigma_coef * sqs;
+                const bool gauss = L.shape == CB2_SHAPE_GAUSSIAN;
+                const float dop = vds * L.inv_c;
+                for (int kc = 0; kc < L.ncomp; kc++) {
+                    const int c = L.comp0 + kc;
+                    const float cf = gauss ? fmaf(L.shift_coef, vds, L.c0_frac)
+                                           : S.comps[c].c0_frac + __ldg(L.mult_lambda + kc) * dop * L.inv_delta;     // multiplet.pyx:108-115
+                    const float a = gauss ? amp : amp * __ldg(L.mult_ratio + kc);
+                    component_pass<AccT, 0>(0, cf, width, a, S.comps[c].c0_int, bins, wacc, lane, nullptr, 0.0, n_gauss, n_lorentz);
+                }
+            }
+        }
+        G0 += n_groups;
+    }
+    __syncthreads();
+    if (MOM) {
+        float* row = mom_out + (size_t)ray * k_pad;
+        for (int i = tid; i < k_pad; i += NW * 32) row[i] = (float)mom[i];
+    }
+    // the ray's spectrum: fp64 sum of the NW private accumulators, lane-consecutive bins -> coalesced rows
+    for (int bin = tid; bin < bins; bin += NW * 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < NW; wq++) v += (double)wall[(size_t)wq * bins_pad + bin];
+        v *= scale;
+        const size_t idx = (size_t)ray * bins + bin;
+        if (out_f64) {
+            double* p = (double*)out + idx;
+            *p = (accumulate ? *p : 0.0) + v;
+        } else {
+            float* p = (float*)out + idx;
+            *p = (float)((accumulate ? (double)*p : 0.0) + v);
+        }
+    }
+    if (stats) {
+        unsigned long long nb = n_brems, oodl = ood, ng = n_gauss;
+        for (int off = 16; off > 0; off >>= 1) {
+            nb += __shfl_down_sync(FULL, nb, off);
+            oodl += __shfl_down_sync(FULL, oodl, off);
+            ng += __shfl_down_sync(FULL, ng, off);
+        }
+        if (lane == 0) {
+            if (nb) atomicAdd(stats + 3, nb);
+            if (oodl) atomicAdd(stats + 5, oodl);
+            if (ng) atomicAdd(stats + 1, ng);
+        }
+        if (tid == 0 && n_samples && count_samples) atomicAdd(stats + 0, n_samples);
+    }
+}
+
 // state tables of an eligible scene: plasma line models with Gaussian / multiplet shapes (+ Bremsstrahlung moments) over fields
 // that are all AXISYM_BLEND.  CB2_STATE_MEMO=0 keeps the generic kernel (tests run both).
 int cb2_memo_build(cb2_scene* sc) {
@@ -1383,6 +1601,7 @@ int cb2_memo_build(cb2_scene* sc) {
     FM.core = core;
     if (!FM.edge && !FM.core) { memset(&FM, 0, sizeof FM); return CB2_OK; }
     FM.enabled = 1;
+    if (const char* e = getenv("CB2_FUSED")) sc->fused = atoi(e) != 0;
     return CB2_OK;
 }
 
@@ -1404,9 +1623,39 @@ bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __
     const int64_t ray = blockIdx.x;
     const int n_comp = S.n_comp;
     unsigned n_gauss = 0, n_lorentz = 0;
+    int touched = 0;
     const int64_t G0 = gbase[ray], G1 = gbase[ray + 1];
+    if constexpr (NW == 8) {
+    // 8-warp instances (calls with few rays): work items = (group, component) pairs dealt round-robin to the warps — a ray with few
+    // groups but many components (C2: 2 groups x 30 Stark / Zeeman components, each a serial walk over its bin range) still occupies
+    // every warp.  The next item's record is in flight while this one is binned.
+    const unsigned n_items = (unsigned)(G1 - G0) * (unsigned)n_comp;
+    unsigned it = warp;
+    float amp_n = 0.f, cf_n = 0.f, width_n = 0.f;
+    int c_n = 0;
+    auto fetch = [&](unsigned item) {
+        const unsigned g = item / (unsigned)n_comp;
+        c_n = (int)(item - g * (unsigned)n_comp);
+        amp_n = 0.f;
+        if (__ldg(gmask + G0 + g)) {
+            const float* r = rec + ((size_t)(G0 + g) * n_comp + c_n) * REC_FLOATS_PER_COMP + lane;
+            amp_n = __ldg(r + 64); cf_n = __ldg(r); width_n = __ldg(r + 32);
+        }
+    };
+    if (it < n_items) fetch(it);
+    for (; it < n_items; it += NW) {
+        const float amp = amp_n, cf = cf_n, width = width_n;
+        const int c = c_n;
+        if (it + NW < n_items) fetch(it + NW);
+        if (!__any_sync(FULL, amp > 0.f)) continue;
+        touched = 1;
+        component_pass<AccT, LOR>(S.comps[c].type, cf, width, amp, S.comps[c].c0_int, bins, wacc, lane, S.lorentz_tab,
+                                  S.lorentz_phi_inf, n_gauss, n_lorentz);
+    }
+    } else {
     for (int64_t G = G0 + warp; G < G1 && n_comp > 0; G += NW) {
         if (!__ldg(gmask + G)) continue;
+        touched = 1;
         const float* grec = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
         // software pipeline: the next component's record is in flight while this one is binned (records come from HBM/L2)
         float amp_n = __ldg(grec + 64), cf_n = __ldg(grec), width_n = __ldg(grec + 32);
@@ -1421,10 +1670,12 @@ bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __
                                       S.lorentz_phi_inf, n_gauss, n_lorentz);
         }
     }
-    __syncthreads();
-    // the ray's spectrum: fp64 sum of the NW private accumulators, lane-consecutive bins -> coalesced rows
+    }
+    // (a ray without a live group adds nothing: in accumulate mode its row is left alone — the pass over the flagged groups of the
+    // fused path touches a fraction of the rays)
+    const int any_touched = __syncthreads_or(touched);
     const double flat_v = flat ? flat[ray] : 0.0;
-    for (int bin = tid; bin < bins; bin += NW * 32) {
+    for (int bin = tid; bin < bins && (any_touched || !accumulate || flat_v != 0.0); bin += NW * 32) {
         double v = flat_v;
 #pragma unroll
         for (int w = 0; w < NW; w++) v += (double)wall[(size_t)w * bins_pad + bin];
@@ -1480,18 +1731,18 @@ static int reserve(T** p, size_t* have, size_t need, cudaStream_t st) {
 }
 
 template <int NW, typename AccT>
-static int launch_bin(const cb2_scene* sc, int64_t n_rays, void* out, int out_f64, double scale, int accumulate, unsigned long long* stats,
-                      cudaStream_t st) {
+static int launch_bin(const cb2_scene* sc, const unsigned* mask, int64_t n_rays, void* out, int out_f64, double scale, int accumulate,
+                      unsigned long long* stats, cudaStream_t st) {
     const DevScene& S = sc->host;
     const size_t smem = cb2_warp_smem_bytes(NW, sizeof(AccT) == 8, S.bins);
     if (S.has_lorentz) {
         auto kern = bin_kernel<NW, AccT, 1>;
         if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, mask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
     } else {
         auto kern = bin_kernel<NW, AccT, 0>;
         if (smem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, sc->gmask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
+        kern<<<dim3((unsigned)n_rays), dim3(NW * 32), smem, st>>>(S, n_rays, sc->gbase, mask, sc->rec, S.has_flat ? sc->flat : nullptr, out, out_f64, scale, accumulate, stats);
     }
     return cb2_cuda_check(cudaGetLastError(), "bin_kernel launch");
 }
@@ -1503,6 +1754,13 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     const bool moments = B.present && B.mode == 3;
     const int n_comp = S.n_comp;
     static const int dbg = getenv("CB2_DBG_SKIP") ? atoi(getenv("CB2_DBG_SKIP")) : 0;
+    // table-driven scenes, CB2_FUSED=1 at scene creation: state and binning in one kernel (no line records through HBM, no record
+    // buffer; measured 10 % slower than state_fast_kernel -> records -> bin_kernel on C3: 16 resident warps per SM instead of 24)
+    const int fused_env = sc->fused;
+    const int fused_nsp = sc->memo.n_sp <= 2 ? 2 : CB2_MEMO_MAX_SP;
+    const size_t fsmem = (moments ? (size_t)B.k_pad * sizeof(double) : 0) + cb2_warp_smem_bytes(4, sc->acc_f64, S.bins) +
+                         4 * (size_t)(sc->memo.n_lines + 2 * fused_nsp) * 32 * sizeof(float);
+    const bool fused = fused_env && sc->memo.enabled && sc->bin_nw == 4 && !S.has_lorentz && !S.has_flat && fsmem <= 200 * 1024;
     const size_t esz = out_f64 ? sizeof(double) : sizeof(float);
     const size_t rec_cap_bytes = (size_t)24 << 30;            // bound on the record buffer; batches shrink to respect it
     int64_t batch = std::min(cb2_warp_batch_rays(sc), rays.n_rays);
@@ -1569,7 +1827,28 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     } while (0)
                 // resident CTAs per SM (register budget): CB2_FAST_MINB = 6 / 8 / 10 / 12 for experiments
                 static const int minb = getenv("CB2_FAST_MINB") ? atoi(getenv("CB2_FAST_MINB")) : 8;
-                if (moments) {
+                if (fused) {
+                    const int nsp = fused_nsp;
+#define CB2_FUSED_K(MOM, NSPV, ACC)                                                                                              \
+    do {                                                                                                                          \
+        auto kern = fused_fast_kernel<4, MOM, CB2_FUSED_MINB, NSPV, ACC>;                                                         \
+        if (fsmem > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));    \
+        kern<<<dim3((unsigned)sub.n_rays), dim3(128), fsmem, st>>>(S, sc->memo, sub, sc->gbase, sc->gblend, sc->rec, stats, sc->mom, o,  \
+                                                                   out_f64, scale, accumulate, count_samples);                    \
+    } while (0)
+                    const int sel = (moments ? 4 : 0) | (nsp > 2 ? 2 : 0) | (sc->acc_f64 ? 1 : 0);
+                    switch (sel) {
+                    case 0: CB2_FUSED_K(0, 2, float); break;
+                    case 1: CB2_FUSED_K(0, 2, double); break;
+                    case 2: CB2_FUSED_K(0, CB2_MEMO_MAX_SP, float); break;
+                    case 3: CB2_FUSED_K(0, CB2_MEMO_MAX_SP, double); break;
+                    case 4: CB2_FUSED_K(1, 2, float); break;
+                    case 5: CB2_FUSED_K(1, 2, double); break;
+                    case 6: CB2_FUSED_K(1, CB2_MEMO_MAX_SP, float); break;
+                    default: CB2_FUSED_K(1, CB2_MEMO_MAX_SP, double); break;
+                    }
+#undef CB2_FUSED_K
+                } else if (moments) {
                     if (minb <= 6) CB2_FAST(1, 6); else if (minb <= 8) CB2_FAST(1, 8); else if (minb <= 10) CB2_FAST(1, 10); else CB2_FAST(1, 12);
                 } else {
                     if (minb <= 6) CB2_FAST(0, 6); else if (minb <= 8) CB2_FAST(0, 8); else if (minb <= 10) CB2_FAST(0, 10); else CB2_FAST(0, 12);
@@ -1597,12 +1876,19 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         }
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[2], st));
         // K1b
-        if (sc->bin_nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
-                                          : launch_bin<8, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
-        else if (sc->bin_nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
-                                               : launch_bin<2, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
-        else rc = sc->acc_f64 ? launch_bin<4, double>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st)
-                              : launch_bin<4, float>(sc, sub.n_rays, o, out_f64, scale, accumulate, stats, st);
+        // (fused path: the frame rows exist already; only the groups with blend-zone samples are binned, on top of them)
+        const unsigned* bmask = fused ? sc->gblend : sc->gmask;
+        const int bacc = fused ? 1 : accumulate;
+        // a call that cannot fill the GPU with one CTA per ray (0-D observer groups: C2 has 64 rays) takes 8 warps per ray; decided
+        // on the call's ray count, not the batch's, so a ray's bits do not depend on where the batches are cut
+        int bin_nw = sc->bin_nw;
+        if (bin_nw == 4 && rays.n_rays < 1024 && cb2_warp_smem_bytes(8, sc->acc_f64, S.bins) <= 200 * 1024) bin_nw = 8;
+        if (bin_nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
+                                          : launch_bin<8, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);
+        else if (bin_nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
+                                               : launch_bin<2, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);
+        else rc = sc->acc_f64 ? launch_bin<4, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
+                              : launch_bin<4, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);
         if (rc != CB2_OK) return rc;
         if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[3], st));
         // K2

@@ -337,6 +337,7 @@ struct cb2_scene {
     // launch configuration
     int nw, bpl, smem_bytes;   // CTA-phased kernel (direct Bremsstrahlung)
     int bin_nw;                // bin_kernel warps per ray
+    int fused;                 // table-driven scenes: fused_fast_kernel instead of state_fast_kernel + bin_kernel (CB2_FUSED=1)
     int warp_kernel;         // 1: warp-autonomous kernel (cb2_emission_warp.cu), 0: CTA-phased kernel with the direct Bremsstrahlung path
     int feat;                // the scene needs the general state kernel (beam, ThermalCXLine, TotalRadiatedPower)
     int ax_only;             // every scalar field of the scene is an AXISYM_BLEND: branch-free field evaluation

@@ -246,9 +246,78 @@ class _Observer0DGroup:
             owner.append(np.full(o.shape[0], i))
         return np.concatenate(os_), np.concatenate(ds_), np.concatenate(ws_), np.concatenate(owner)
 
-    def observe(self, scene, primitive, to_world=None, wall=None):
-        """One device render for the whole group.  ``scene``: engine.EmissionScene / PlasmaRenderer; ``wall``: optional
-        first_wall.FirstWall that ends every ray at its first hit.  Returns spectra[n_observers, bins]."""
+    def _descs(self):
+        """cb2_observer0d array of the group (group transform applied) and the per-observer ray offsets / etendues."""
+        n = len(self._observers)
+        arr = (_abi.Observer0DDesc * n)()
+        offs = np.zeros(n + 1, dtype=np.int64)
+        etendue = np.ones(n, dtype=np.float64)
+        g = self.transform
+        for i, ob in enumerate(self._observers):
+            m = g @ ob.transform
+            for r in range(3):
+                for c in range(4):
+                    arr[i].to_world[4 * r + c] = m[r, c]
+            if isinstance(ob, FibreOptic):
+                if not 0.0 < ob.acceptance_angle <= 90.0:
+                    raise ValueError("Acceptance angle must be in the range (0, 90] degrees.")
+                if ob.radius <= 0 or ob.pixel_samples < 1:
+                    raise ValueError("The fibre radius and the number of pixel samples must be positive.")
+                arr[i].radius, arr[i].acceptance_angle, arr[i].samples = ob.radius, ob.acceptance_angle, ob.pixel_samples
+                etendue[i] = ob.solid_angle * ob.collection_area
+            else:
+                arr[i].radius, arr[i].acceptance_angle, arr[i].samples = 0.0, 0.0, 1
+                etendue[i] = ob.sensitivity
+            offs[i + 1] = offs[i] + arr[i].samples
+        return arr, offs, etendue
+
+    def observe(self, scene, primitive, to_world=None, wall=None, device=0):
+        """The whole group in one pass on the device: ray generation (cb2_observer0d_rays_device), optional first-wall clip, one
+        render of all rays, per-observer reduction (cb2_observer0d_reduce_device); only the [n_observers, bins] results cross PCIe.
+        ``scene``: engine.EmissionScene / PlasmaRenderer; ``wall``: optional first_wall.FirstWall that ends every ray at its first
+        hit.  Returns spectra[n_observers, bins] (mean spectral radiance, W / (m^2 sr nm)); ``self.power_spectra`` holds the
+        spectral power [W / nm] a SpectralPowerPipeline0D reports: the mean of L cos(theta) over the uniform solid-angle samples
+        times the etendue (solid angle x collection area); a sight line scales by its sensitivity."""
+        import torch
+        if not self._observers:
+            raise ValueError("The group has no observers.")
+        lib = _abi.load_library()
+        arr, offs, etendue = self._descs()
+        n_obs, n_rays = len(self._observers), int(offs[-1])
+        dev = torch.device("cuda", int(device))
+        bins = scene.scene.bins if hasattr(scene, "scene") else scene.bins
+        prim = _primitive_desc(primitive, to_world)
+        buf = DeviceRayBuffer(n_rays, dev)
+        weight = torch.empty(n_rays, dtype=torch.float64, device=dev)
+        rs = buf.as_struct()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _abi.check(lib, lib.cb2_observer0d_rays_device(arr, n_obs, C.byref(prim), C.byref(rs), C.c_void_p(weight.data_ptr()), C.c_void_p(stream)))
+            buf.n_rays, buf.n_segments = int(rs.n_rays), int(rs.n_segments)
+            if wall is not None:
+                wall.clip_device(buf)
+            per_ray = torch.zeros((n_rays, bins), dtype=torch.float64, device=dev)
+            stats = torch.zeros(8, dtype=torch.int64, device=dev)
+            scene.render_device(buf, per_ray, stats=stats)
+            out = torch.empty((2, n_obs, bins), dtype=torch.float64, device=dev)
+            _abi.check(lib, lib.cb2_observer0d_reduce_device(C.c_void_p(per_ray.data_ptr()), 1, C.c_void_p(weight.data_ptr()),
+                                                             offs.ctypes.data_as(_abi.c_int64_p), etendue.ctypes.data_as(_abi.c_double_p),
+                                                             n_obs, bins, C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                                             C.c_void_p(stream)))
+            host = out.cpu().numpy()
+            ood = int(stats[5].item())
+        if ood > 0:
+            raise ValueError("The specified value is outside of the range of the supplied data and/or extrapolation range: %d table "
+                             "lookups of this render left their tables." % ood)
+        self.spectra, self.power_spectra = host[0], host[1]
+        self.last_rays = buf
+        for ob, s, pw in zip(self._observers, self.spectra, self.power_spectra):
+            ob.spectrum, ob.power_spectrum = s, pw
+        return self.spectra
+
+    def observe_host_rays(self, scene, primitive, to_world=None, wall=None):
+        """The same observation from host-generated rays (gather_rays + geometry.ray_segments) through the host-buffer render call and a
+        numpy reduction — the explicit-ray-list path; tests compare the device pass with it."""
         from .geometry import ray_segments
         if not self._observers:
             raise ValueError("The group has no observers.")
@@ -262,16 +331,10 @@ class _Observer0DGroup:
         den = np.zeros(n)
         np.add.at(num, owner, per_ray * w[:, None])
         np.add.at(den, owner, w)
-        self.spectra = num / den[:, None]
-        # spectral power [W / nm] collected by each observer, what a SpectralPowerPipeline0D reports: the mean of L cos(theta) over the
-        # uniform solid-angle samples times the etendue (solid angle x collection area); a sight line scales by its sensitivity
         counts = np.bincount(owner, minlength=n).astype(np.float64)
         etendue = np.array([getattr(ob, "solid_angle", 1.0) * getattr(ob, "collection_area", 1.0) * getattr(ob, "sensitivity", 1.0)
                             for ob in self._observers])
-        self.power_spectra = num / counts[:, None] * etendue[:, None]
-        for ob, s, pw in zip(self._observers, self.spectra, self.power_spectra):
-            ob.spectrum, ob.power_spectrum = s, pw
-        return self.spectra
+        return num / den[:, None], num / counts[:, None] * etendue[:, None]
 
 
 class SightLineGroup(_Observer0DGroup):

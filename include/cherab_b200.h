@@ -484,6 +484,33 @@ typedef struct cb2_pinhole {
 int cb2_pinhole_rays_device(const cb2_pinhole* camera, const cb2_primitive* primitive, const int64_t* pixel_index_dev, int64_t n,
                             double sub_x, double sub_y, cb2_rays* out_dev, void* stream);
 
+/* 0-D observers (raysect SightLine / FibreOptic as cherab/tools/observers/group/{sightline,fibreoptic}.py:73-95,98-160 place them):
+ * a sight line is one ray from the observer's origin along its +z axis; a fibre's `samples` rays start on the tip disc of `radius`
+ * (sunflower points, uniform in area) and leave within `acceptance_angle` degrees of +z (Fibonacci points, uniform in solid angle
+ * on the cone cap) — the deterministic stand-in for raysect's random ConeUniformSampler / DiskSampler that
+ * core_b200/observers.py::FibreOptic.rays defines.  weight = cos(theta): the projected tip area a direction sees. */
+typedef struct cb2_observer0d {
+    double  to_world[12];           /* row-major 3x4 affine: observer space (looking along +z) -> world */
+    double  radius;                 /* fibre tip radius, m; 0 = sight line */
+    double  acceptance_angle;       /* degrees, (0, 90]; ignored by a sight line */
+    int32_t samples;                /* rays of this observer (1 for a sight line) */
+    int32_t _pad;
+} cb2_observer0d;
+
+/* Rays of n_observers 0-D observers (HOST array) and their chords through `primitive`, observer after observer, into
+ * caller-allocated DEVICE arrays sized for n = sum(samples) rays (origin[n][3], direction[n][3], seg_offset[n+1], seg_t0[2n],
+ * seg_t1[2n]); weight_dev[n] (DEVICE double) receives cos(theta) of every ray.  One stream synchronisation (segment total). */
+int cb2_observer0d_rays_device(const cb2_observer0d* observers, int64_t n_observers, const cb2_primitive* primitive,
+                               cb2_rays* out_dev, double* weight_dev, void* stream);
+
+/* Per-observer reduction of per-ray spectra (what raysect's pixel loop + SpectralRadiancePipeline0D / SpectralPowerPipeline0D do,
+ * cherab/tools/observers/group/base.py:130-135,399-436): observer i owns rays [ray_offset[i], ray_offset[i+1]) (HOST int64[n+1]);
+ * radiance_dev[i][bin] = sum_r w_r S[r][bin] / sum_r w_r, power_dev[i][bin] = etendue[i] * sum_r w_r S[r][bin] / rays_i
+ * (etendue: HOST double[n_observers]; either output may be NULL).  spectra_dev: [n_rays][bins] float32 / float64. */
+int cb2_observer0d_reduce_device(const void* spectra_dev, int spectra_f64, const double* weight_dev, const int64_t* ray_offset,
+                                 const double* etendue, int64_t n_observers, int32_t bins, double* radiance_dev, double* power_dev,
+                                 void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * First-wall occlusion (replaces the role the wall meshes of cherab/generomak/machine/first_wall.py:120-184
  * play in Raysect's tracer: a ray ends at its first opaque hit, so the volume integral of the plasma stops there).

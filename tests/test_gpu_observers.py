@@ -111,3 +111,67 @@ def test_fibre_group_observes_in_one_render():
         ob = group.observers[i]
         power = (ref_rays[sel] * w[sel, None]).mean(axis=0) * ob.solid_angle * ob.collection_area      # etendue-weighted: W / nm
         assert np.all(np.abs(group.power_spectra[i] - power) <= 1e-4 * np.abs(power) + 1e-9 * np.abs(power).max())
+
+
+def _fibre_fan(n_fibres=7, samples=24):
+    group = cb.FibreOpticGroup(name="fan", transform=cb.translate(0.0, 0.02, -0.01))
+    for i, ang in enumerate(np.linspace(-60.0, -80.0, n_fibres)):
+        target = (2.3 - np.cos(np.deg2rad(ang)), 0.05 * i, 1.25 + np.sin(np.deg2rad(ang)))
+        group.add_observer(cb.FibreOptic(name=str(i), transform=cb.look_at((2.3, 0.0, 1.25), target, up=(0, 1, 0)),
+                                         acceptance_angle=1.0 + 0.3 * i, radius=0.001 * (1 + i), pixel_samples=samples + i))
+    return group
+
+
+def test_group_rays_on_the_device_match_the_host_bundles():
+    # cb2_observer0d_rays_device against FibreOptic.rays / SightLine.rays + geometry.ray_segments (cos / sin of the device's libm: 1e-14)
+    import ctypes as C
+    import torch
+    from core_b200 import _abi
+    from core_b200.observers import DeviceRayBuffer, _primitive_desc
+    prim = cb.HollowCylinder(0.73, 2.41, -1.8, 1.55)
+    sight = cb.SightLineGroup([cb.SightLine(transform=cb.look_at((2.3, 0.1 * k, 1.25), (1.0, 0.5, -0.5 + 0.1 * k)), sensitivity=1.0 + k) for k in range(5)])
+    for group in (_fibre_fan(), sight):
+        o, d, w, owner = group.gather_rays()
+        host = cb.ray_segments(prim, o, d)
+        arr, offs, etendue = group._descs()
+        assert offs[-1] == o.shape[0] and np.array_equal(np.searchsorted(offs, np.arange(offs[-1]), side="right") - 1, owner)
+        lib = _abi.load_library()
+        buf = DeviceRayBuffer(int(offs[-1]), "cuda:0")
+        weight = torch.empty(int(offs[-1]), dtype=torch.float64, device="cuda:0")
+        rs = buf.as_struct()
+        pd = _primitive_desc(prim)
+        _abi.check(lib, lib.cb2_observer0d_rays_device(arr, len(group.observers), C.byref(pd), C.byref(rs), C.c_void_p(weight.data_ptr()), None))
+        buf.n_rays, buf.n_segments = int(rs.n_rays), int(rs.n_segments)
+        dev = buf.to_host()
+        assert np.array_equal(dev.seg_offset, host.seg_offset) and host.n_segments > 0
+        np.testing.assert_allclose(dev.origin, host.origin, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(dev.direction, host.direction, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(dev.seg_t0, host.seg_t0, rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(dev.seg_t1, host.seg_t1, rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(weight.cpu().numpy(), w, rtol=0, atol=1e-15)
+
+
+def test_group_observe_on_the_device_matches_the_host_ray_path():
+    plasma = generomak.get_plasma()
+    plasma.atomic_data = cb.SyntheticADAS()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    plasma.integrator = cb.NumericalIntegrator(step=0.005)
+    flat = cb.flatten_scene(plasma, 655.5, 656.9, 200)
+    scene = EmissionScene(flat)
+    group = _fibre_fan()
+    spectra = group.observe(scene, plasma.geometry, plasma.geometry_to_world())
+    ref_rad, ref_pow = group.observe_host_rays(scene, plasma.geometry, plasma.geometry_to_world())
+    assert spectra.shape == (7, 200) and ref_rad.max() > 0
+    np.testing.assert_allclose(spectra, ref_rad, rtol=1e-9, atol=1e-12 * ref_rad.max())
+    np.testing.assert_allclose(group.power_spectra, ref_pow, rtol=1e-9, atol=1e-12 * ref_pow.max())
+    # sight lines: one ray each, power = radiance x sensitivity
+    sight = cb.SightLineGroup([cb.SightLine(transform=cb.look_at((2.3, 0.0, 1.25), (1.0, 0.1 * k, -0.9)), sensitivity=2.0 + k) for k in range(4)])
+    rad = sight.observe(scene, plasma.geometry, plasma.geometry_to_world())
+    o, d, w, owner = sight.gather_rays()
+    ref, _ = oracle.emission_render(flat, cb.ray_segments(plasma.geometry, o, d, plasma.geometry_to_world()))
+    scene.close()
+    assert np.all(np.abs(rad - ref) <= 1e-4 * np.abs(ref) + 1e-9 * np.abs(ref).max(axis=1, keepdims=True)) and ref.max() > 0
+    np.testing.assert_allclose(sight.power_spectra, rad * np.array(sight.sensitivity)[:, None], rtol=1e-14)
+    with pytest.raises(ValueError):
+        cb.FibreOpticGroup().observe(scene, plasma.geometry)

@@ -141,3 +141,29 @@ def test_contraction_kernels_against_oracle(monkeypatch, contract):
         assert worst_ratio(a64, ref) <= 1.0, (contract, bins)
         assert worst_ratio(a32.astype(np.float64), 0.5 * ref + 0.5 * ref) <= 2.0, (contract, bins)
         assert worst_ratio(twice, 1.5 * ref) <= 1.0, (contract, bins)
+
+
+def test_fused_kernel_matches_the_two_kernel_path(monkeypatch):
+    # CB2_FUSED=1: state and binning of the table-driven scene in one kernel (no line records through HBM), blend-zone samples
+    # through the fix-up pass and a bin pass over the flagged groups; C3's model mix with the moment contraction
+    plasma = generomak.get_plasma()
+    lines = [cb.Line(cb.hydrogen, 0, (n, 2)) for n in (3, 4)]
+    plasma.models = [cb.ExcitationLine(l) for l in lines] + [cb.RecombinationLine(l) for l in lines] + [cb.Bremsstrahlung()]
+    plasma.integrator = cb.NumericalIntegrator(step=0.003)
+    flat = cb.flatten_scene(plasma, 390.0, 700.0, 2048)
+    rays = generomak_camera_rays(plasma, (10, 10))
+    monkeypatch.setenv("CB2_FUSED", "0")
+    two = EmissionScene(flat)
+    a, sa = two.render(rays)
+    two.close()
+    monkeypatch.setenv("CB2_FUSED", "1")
+    one = EmissionScene(flat)
+    b, sb = one.render(rays)
+    acc, _ = one.render(rays, out=b.copy(), accumulate=True)
+    one.close()
+    for k in ("samples", "gaussian_bin_evals", "brems_bin_evals", "out_of_domain"):
+        assert sa[k] == sb[k], k
+    assert worst_ratio(b, a) <= 0.05                     # same arithmetic per sample; only the summation order of a ray's groups differs
+    assert worst_ratio(acc, 2 * b) <= 0.05
+    ref, _ = oracle.emission_render(flat, rays)
+    assert worst_ratio(b, ref) <= 1.0
