@@ -184,14 +184,15 @@ def workload_config(args, world):
                   % (args.pixels * args.pixels * args.bins * 4 / 1e9)}
 
 
-def shared_host_rows(rows_total, bins, row0, rows, rank, dist, torch):
-    """This rank's rows [row0, row0 + rows) of a [rows_total, bins] fp32 frame in shared host memory, page-locked for the D2H copies.
-    Falls back to a rank-local pinned buffer when /dev/shm cannot hold the frame.  Returns (numpy view, description)."""
+def shared_host_frame(rows_total, bins, rank, dist, torch):
+    """The whole [rows_total, bins] fp32 frame in shared host memory (/dev/shm), mapped and page-locked by every rank: each rank's
+    strided D2H copies put its tiles on their pixels, so the frame a consumer maps is in image order.  Returns (numpy frame or
+    None, description); None when /dev/shm cannot hold the frame or the mapping cannot be page-locked on some rank."""
     import mmap
     path = "/dev/shm/cb2_frame_%s" % os.environ.get("MASTER_PORT", "0")
     nbytes = rows_total * bins * 4
     ok = torch.zeros(1, dtype=torch.int32, device="cuda")
-    view = None
+    frame = None
     if rank == 0:
         try:
             fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
@@ -208,13 +209,12 @@ def shared_host_rows(rows_total, bins, row0, rows, rank, dist, torch):
         mm = mmap.mmap(fd, nbytes)
         os.close(fd)
         frame = np.frombuffer(mm, dtype=np.float32).reshape(rows_total, bins)
-        view = frame[row0:row0 + rows]
-        rc = torch.cuda.cudart().cudaHostRegister(view.ctypes.data, view.nbytes, 0)
+        rc = torch.cuda.cudart().cudaHostRegister(frame.ctypes.data, frame.nbytes, 0)
         if int(getattr(rc, "value", rc)) != 0:
-            view = None
+            frame = None
     except Exception:
-        view = None
-    ok[0] = 1 if view is not None else 0
+        frame = None
+    ok[0] = 1 if frame is not None else 0
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         try:
@@ -222,9 +222,9 @@ def shared_host_rows(rows_total, bins, row0, rows, rank, dist, torch):
         except OSError:
             pass
     if int(ok.item()) == 1:
-        return view, "shared host memory (/dev/shm), every rank reads its rows back over its own PCIe link"
-    return (torch.empty((rows, bins), dtype=torch.float32, pin_memory=True).numpy(),
-            "rank-local pinned host buffers (no /dev/shm room for the frame), every rank reads its rows back over its own PCIe link")
+        return frame, ("image-ordered frame [nx*ny, bins] (pixel ix*ny+iy) in shared host memory (/dev/shm): every rank writes its tiles to "
+                       "their pixels over its own PCIe link (strided D2H inside the timed region)")
+    return None, ""
 
 
 _RESULT_FD = None
@@ -345,20 +345,27 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.steps
+        # The frame the consumer gets is in IMAGE order at every N: row p = ix * ny + iy of a [nx * ny, bins] float32 array.  The rays are
+        # listed tile by tile (16 x 16 pixels), so the host-buffer call takes the destination row of every ray (cb2_emission_render_rows)
+        # and copies each tile to its pixels with strided D2H copies that overlap the next batch's kernels.
+        rows = pix
         if world == 1:
-            host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
-            scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
+            host_frame = torch.empty((args.pixels * args.pixels, args.bins), dtype=torch.float32, pin_memory=True).numpy()
+            scene.render(host_rays[0], out=host_frame, rows=rows)      # warm the staging buffers once
         n_chunks = 8
         gather = world > 1 and args.frame == "gather"
-        frame_kind = "rank-0 pinned buffer" if world == 1 else "NCCL gather to rank 0, then D2H"
+        frame_kind = ("image-ordered frame [nx*ny, bins] (pixel ix*ny+iy) in rank 0's pinned host memory, tiles copied to their pixels with "
+                      "strided D2H inside the timed region") if world == 1 else "NCCL gather to rank 0, then D2H (rank-major tile order)"
         if world > 1 and not gather:
             # The path shards by pixel tiles and has no exchange step: every rank renders its tiles through the same host-buffer call
-            # as at N = 1 and reads them back over ITS OWN PCIe link into its rows of one frame in shared host memory
-            # (rank-major row blocks; /dev/shm file mapped by every rank, the rank's rows page-locked).  No device collective.
-            counts = [rank_pixels(args.pixels, r, world).size for r in range(world)]
-            row0 = sum(counts[:rank])
-            host_frame, frame_kind = shared_host_rows(sum(counts), args.bins, row0, counts[rank], rank, dist, torch)
-            scene.render(host_rays[0], out=host_frame)      # warm the staging buffers once
+            # as at N = 1 and writes them over ITS OWN PCIe link to their pixels of one frame in shared host memory (/dev/shm file
+            # mapped and page-locked by every rank).  No device collective.
+            host_frame, frame_kind = shared_host_frame(args.pixels * args.pixels, args.bins, rank, dist, torch)
+            if host_frame is None:
+                host_frame = torch.empty((pix.size, args.bins), dtype=torch.float32, pin_memory=True).numpy()
+                rows = np.arange(pix.size)
+                frame_kind = "rank-local pinned host buffers in the rank's tile order (no /dev/shm room for the frame)"
+            scene.render(host_rays[0], out=host_frame, rows=rows)      # warm the staging buffers once
             dist.barrier()
         if gather:
             # NCCL only gathers the frame.  The rank's rays are cut into chunks: while chunk c+1 renders, chunk c is gathered
@@ -385,7 +392,7 @@ def main():
         for k in range(e2e_steps):
             if not gather:
                 r = host_rays[(args.warmup + k) % len(host_rays)]
-                _, s = scene.render(r, out=host_frame)
+                _, s = scene.render(r, out=host_frame, rows=rows)
                 e2e_samples += s["samples"]
             else:
                 works = []

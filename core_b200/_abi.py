@@ -167,8 +167,8 @@ class WallDesc(C.Structure):
 
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
-    "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_scene_create", "cb2_scene_destroy",
-    "cb2_emission_render", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
+    "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_measure_peak_fp64", "cb2_scene_create", "cb2_scene_destroy",
+    "cb2_emission_render", "cb2_emission_render_rows", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
     "cb2_pinhole_rays_device", "cb2_observer0d_rays_device", "cb2_observer0d_reduce_device",
     "cb2_wall_create", "cb2_wall_destroy", "cb2_wall_hit", "cb2_wall_clip_device",
@@ -197,6 +197,7 @@ def load_library():
     lib.cb2_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_scene_destroy.argtypes = [vp]
     lib.cb2_emission_render.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, C.POINTER(Stats)]
+    lib.cb2_emission_render_rows.argtypes = [vp, C.POINTER(Rays), c_int64_p, vp, C.c_int, C.c_double, C.POINTER(Stats)]
     lib.cb2_emission_render_device.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, vp, vp]
     lib.cb2_sample_state.argtypes = [vp, c_double_p, C.c_int64, c_double_p]
     lib.cb2_state_width.argtypes = [vp]
@@ -213,6 +214,7 @@ def load_library():
                                             C.POINTER(Rays), vp]
     lib.cb2_observer0d_rays_device.argtypes = [C.POINTER(Observer0DDesc), C.c_int64, C.POINTER(PrimitiveDesc), C.POINTER(Rays), vp, vp]
     lib.cb2_observer0d_reduce_device.argtypes = [vp, C.c_int, vp, c_int64_p, c_double_p, C.c_int64, C.c_int32, vp, vp, vp]
+    lib.cb2_measure_peak_fp64.argtypes = [C.c_int, c_double_p]
     lib.cb2_wall_create.argtypes = [C.POINTER(WallDesc), C.c_int, C.POINTER(vp)]
     lib.cb2_wall_destroy.argtypes = [vp]
     lib.cb2_wall_hit.argtypes = [vp, c_double_p, c_double_p, C.c_int64, c_double_p]

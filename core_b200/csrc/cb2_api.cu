@@ -11,6 +11,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "cb2_internal.h"
@@ -1563,6 +1566,109 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
 }
 
 // grow-only device staging buffer
+// ------------------------------------------------------------------------------------------------------------------
+// Device -> pageable host memory, large transfers: cudaMemcpy into pageable memory runs at the speed of one CPU thread copying out of
+// the driver's staging buffer and faulting the destination pages in (measured 3.3 GB/s: 935 ms for the 3 GB CSR of C4).  Here the
+// transfer is cut into chunks that go through a ring of pinned buffers at PCIe speed while worker threads copy finished chunks to
+// their destination in parallel (each thread a slice of every chunk, so the first-touch faults are spread too).  A pinned
+// (cudaHostAlloc / cudaHostRegister) destination takes one plain asynchronous copy.  The stream is synchronised on return.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int D2H_RING = 4;
+constexpr size_t D2H_CHUNK = (size_t)32 << 20;
+struct D2HRing {
+    std::mutex lock;
+    void* buf[D2H_RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[D2H_RING] = {nullptr, nullptr, nullptr, nullptr};
+};
+D2HRing g_d2h;
+}  // namespace
+
+int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
+    if (!bytes) return CB2_OK;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    static const bool chunked = !(getenv("CB2_D2H_CHUNKED") && atoi(getenv("CB2_D2H_CHUNKED")) == 0);
+    if (pinned || bytes < 2 * D2H_CHUNK || !chunked) {
+        CB2_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        CB2_CUDA(cudaStreamSynchronize(st));
+        return CB2_OK;
+    }
+    std::lock_guard<std::mutex> guard(g_d2h.lock);
+    for (int b = 0; b < D2H_RING; b++) {
+        if (!g_d2h.buf[b]) CB2_CUDA(cudaHostAlloc(&g_d2h.buf[b], D2H_CHUNK, cudaHostAllocDefault));
+        if (!g_d2h.ev[b]) CB2_CUDA(cudaEventCreateWithFlags(&g_d2h.ev[b], cudaEventDisableTiming));
+    }
+    const size_t n_chunks = (bytes + D2H_CHUNK - 1) / D2H_CHUNK;
+    const int T = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::atomic<size_t> issued(0);                       // chunks whose copy has been enqueued and whose event has been recorded
+    std::vector<std::atomic<int>> done(n_chunks);        // worker slices finished per chunk
+    for (auto& d : done) d.store(0);
+    std::atomic<int> failed(0);
+    int device = 0;
+    cudaGetDevice(&device);
+    auto worker = [&](int t) {
+        cudaSetDevice(device);
+        for (size_t i = 0; i < n_chunks; i++) {
+            while (issued.load(std::memory_order_acquire) <= i && !failed.load()) std::this_thread::yield();
+            if (failed.load()) return;
+            if (cudaEventSynchronize(g_d2h.ev[i % D2H_RING]) != cudaSuccess) { failed.store(1); return; }
+            const size_t len = std::min(D2H_CHUNK, bytes - i * D2H_CHUNK);
+            const size_t a = len * (size_t)t / T / 64 * 64, b = (t + 1 == T) ? len : len * (size_t)(t + 1) / T / 64 * 64;
+            if (b > a) memcpy((char*)dst + i * D2H_CHUNK + a, (const char*)g_d2h.buf[i % D2H_RING] + a, b - a);
+            done[i].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) pool.emplace_back(worker, t);
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i < n_chunks && err == cudaSuccess; i++) {
+        if (i >= (size_t)D2H_RING)                       // the ring slot is free once every worker has copied its previous content out
+            while (done[i - D2H_RING].load(std::memory_order_acquire) < T && !failed.load()) std::this_thread::yield();
+        if (failed.load()) break;
+        const size_t len = std::min(D2H_CHUNK, bytes - i * D2H_CHUNK);
+        err = cudaMemcpyAsync(g_d2h.buf[i % D2H_RING], (const char*)src_dev + i * D2H_CHUNK, len, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaEventRecord(g_d2h.ev[i % D2H_RING], st);
+        if (err == cudaSuccess) issued.store(i + 1, std::memory_order_release);
+    }
+    if (err != cudaSuccess) failed.store(1);
+    for (auto& th : pool) th.join();
+    if (err != cudaSuccess) return cb2_cuda_check(err, "chunked device -> host copy");
+    if (failed.load()) return cb2_fail(CB2_ERR_CUDA, "chunked device -> host copy failed");
+    CB2_CUDA(cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
+// Rows src_dev[i] (i < n, row_bytes each) to dst_base + dest_row[i] * row_bytes, asynchronously on `st`: consecutive destination
+// rows form a run; runs of equal length at a constant pitch form one cudaMemcpy2DAsync (a 16 x 16 tile of a pixel-ordered frame:
+// 16 runs of 16 rows, pitch = ny rows).
+int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st) {
+    int64_t i = 0;
+    while (i < n) {
+        int64_t len = 1;
+        while (i + len < n && dest_row[i + len] == dest_row[i] + len) len++;
+        // how many following runs have this length and a constant pitch?
+        int64_t h = 1, pitch = 0;
+        while (i + (h + 1) * len <= n) {
+            const int64_t j = i + h * len;
+            const int64_t p = dest_row[j] - dest_row[j - len];
+            if (h == 1) { if (p <= len) break; pitch = p; } else if (p != pitch) break;
+            bool run = true;
+            for (int64_t k = 1; k < len && run; k++) run = dest_row[j + k] == dest_row[j] + k;
+            if (!run) break;
+            h++;
+        }
+        char* d = (char*)dst_base + (size_t)dest_row[i] * row_bytes;
+        const char* s = (const char*)src_dev + (size_t)i * row_bytes;
+        if (h == 1) CB2_CUDA(cudaMemcpyAsync(d, s, (size_t)len * row_bytes, cudaMemcpyDeviceToHost, st));
+        else CB2_CUDA(cudaMemcpy2DAsync(d, (size_t)pitch * row_bytes, s, (size_t)len * row_bytes, (size_t)len * row_bytes, (size_t)h,
+                                        cudaMemcpyDeviceToHost, st));
+        i += h * len;
+    }
+    return CB2_OK;
+}
+
 static int stage_reserve(void** stage, size_t* bytes, int slot, size_t need) {
     if (bytes[slot] >= need && stage[slot]) return CB2_OK;
     if (stage[slot]) cudaFree(stage[slot]);
@@ -1627,14 +1733,17 @@ extern "C" int cb2_emission_render_device(cb2_scene* sc, const cb2_rays* rays, v
     return cb2_launch_emission(sc, as_dev_rays(rays), out, out_f64, scale, accumulate, (unsigned long long*)stats_dev, (cudaStream_t)stream);
 }
 
-extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* out, int out_f64, double scale, int accumulate,
-                                   cb2_stats* stats) {
+static int emission_render_host(cb2_scene* sc, const cb2_rays* rays, const int64_t* dest_row, void* out, int out_f64, double scale,
+                                int accumulate, cb2_stats* stats) {
     if (!sc || !out) return cb2_fail(CB2_ERR_VALUE, "null argument");
     int rc = check_rays(rays);
     if (rc != CB2_OK) return rc;
     CB2_CUDA(cudaSetDevice(sc->device));
     if (stats) memset(stats, 0, sizeof *stats);
     if (rays->n_rays == 0) return CB2_OK;
+    if (dest_row)
+        for (int64_t i = 0; i < rays->n_rays; i++)
+            if (dest_row[i] < 0) return cb2_fail(CB2_ERR_VALUE, "negative destination row for ray %lld", (long long)i);
     cudaStream_t st = 0;
     DevRays dr;
     if ((rc = upload_rays(sc->stage, sc->stage_bytes, rays, dr, st)) != CB2_OK) return rc;
@@ -1649,17 +1758,32 @@ extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* ou
         if (!sc->copy_stream) CB2_CUDA(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
         if (!sc->copy_ev) CB2_CUDA(cudaEventCreateWithFlags(&sc->copy_ev, cudaEventDisableTiming));
         sc->d2h_host = out;
+        sc->d2h_rows = dest_row;
         rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st);
         sc->d2h_host = nullptr;
+        sc->d2h_rows = nullptr;
         if (rc != CB2_OK) { cudaStreamSynchronize(sc->copy_stream); return rc; }
         CB2_CUDA(cudaStreamSynchronize(sc->copy_stream));
     } else {
         if ((rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st)) != CB2_OK) return rc;
-        CB2_CUDA(cudaMemcpyAsync(out, sc->stage[5], obytes, cudaMemcpyDeviceToHost, st));
+        if (dest_row) {
+            if ((rc = cb2_d2h_rows(out, dest_row, rays->n_rays, sc->stage[5], (size_t)sc->host.bins * esz, st)) != CB2_OK) return rc;
+        } else if ((rc = cb2_d2h(out, sc->stage[5], obytes, st)) != CB2_OK) return rc;
     }
     if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
     CB2_CUDA(cudaStreamSynchronize(st));
     return CB2_OK;
+}
+
+extern "C" int cb2_emission_render(cb2_scene* sc, const cb2_rays* rays, void* out, int out_f64, double scale, int accumulate,
+                                   cb2_stats* stats) {
+    return emission_render_host(sc, rays, nullptr, out, out_f64, scale, accumulate, stats);
+}
+
+extern "C" int cb2_emission_render_rows(cb2_scene* sc, const cb2_rays* rays, const int64_t* dest_row, void* out, int out_f64, double scale,
+                                        cb2_stats* stats) {
+    if (!dest_row) return cb2_fail(CB2_ERR_VALUE, "null argument");
+    return emission_render_host(sc, rays, dest_row, out, out_f64, scale, 0, stats);
 }
 
 extern "C" int64_t cb2_scene_info(const cb2_scene* sc, int key) {
@@ -1795,6 +1919,8 @@ extern "C" int cb2_rt_destroy(cb2_rt_scene* sc) {
     if (sc->voxel_map_dev) cudaFree(sc->voxel_map_dev);
     if (sc->scratch) cudaFree(sc->scratch);
     if (sc->touched) cudaFree(sc->touched);
+    if (sc->row_cols) cudaFree(sc->row_cols);
+    if (sc->row_len) cudaFree(sc->row_len);
     if (sc->stats_dev) cudaFree(sc->stats_dev);
     free_stage(sc->stage, sc->stage_bytes);
     free(sc);
@@ -1836,6 +1962,34 @@ extern "C" int cb2_rt_render_csr_device(cb2_rt_scene* sc, const cb2_rays* rays, 
         CB2_CUDA(cudaMemsetAsync(row_offset, 0, sizeof(int64_t), st));
         return CB2_OK;
     }
+    // Single traversal when the strided scratch rows fit (n_rays x touch_cap x 12 B; C4: 5 GB of the 180 GB): every ray's row is
+    // built once in its scratch row, the counts are scanned and the rows move to their places — the grid is walked once, not twice.
+    const bool one_pass = !(getenv("CB2_RT_TWO_PASS") && atoi(getenv("CB2_RT_TWO_PASS")) != 0);
+    const size_t row_bytes = (size_t)rays->n_rays * sc->touch_cap * (sizeof(int32_t) + sizeof(double));
+    bool have_rows = one_pass && row_bytes <= ((size_t)24 << 30);
+    if (have_rows && sc->row_cap_rays < (size_t)rays->n_rays) {
+        CB2_CUDA(cudaStreamSynchronize(st));
+        if (sc->row_cols) cudaFree(sc->row_cols);
+        if (sc->row_len) cudaFree(sc->row_len);
+        sc->row_cols = nullptr; sc->row_len = nullptr; sc->row_cap_rays = 0;
+        if (cudaMalloc((void**)&sc->row_cols, (size_t)rays->n_rays * sc->touch_cap * sizeof(int32_t)) != cudaSuccess ||
+            cudaMalloc((void**)&sc->row_len, (size_t)rays->n_rays * sc->touch_cap * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();                                   // not enough memory for the scratch rows: two traversals
+            if (sc->row_cols) cudaFree(sc->row_cols);
+            sc->row_cols = nullptr; sc->row_len = nullptr;
+            have_rows = false;
+        } else sc->row_cap_rays = (size_t)rays->n_rays;
+    }
+    if (have_rows) {
+        if ((rc = cb2_launch_rt(sc, dr, 3, nullptr, 0, row_offset, sc->row_cols, sc->row_len, (unsigned long long*)stats_dev, st)) != CB2_OK) return rc;
+        if ((rc = cb2_launch_scan(row_offset, rays->n_rays + 1, st)) != CB2_OK) return rc;
+        CB2_CUDA(cudaMemcpyAsync(nnz_host, row_offset + rays->n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CB2_CUDA(cudaStreamSynchronize(st));
+        if (*nnz_host > capacity) return cb2_fail(CB2_ERR_OVERFLOW, "CSR capacity %lld too small, need %lld", (long long)capacity, (long long)*nnz_host);
+        if (*nnz_host == 0) return CB2_OK;
+        if (!columns || !lengths) return cb2_fail(CB2_ERR_VALUE, "null CSR arrays");
+        return cb2_launch_rt_compact(rays->n_rays, sc->touch_cap, row_offset, sc->row_cols, sc->row_len, columns, lengths, st);
+    }
     // pass 1: distinct sources per ray -> row_offset[r]; exclusive scan; pass 2: fill
     if ((rc = cb2_launch_rt(sc, dr, 1, nullptr, 0, row_offset, nullptr, nullptr, nullptr, st)) != CB2_OK) return rc;
     if ((rc = cb2_launch_scan(row_offset, rays->n_rays + 1, st)) != CB2_OK) return rc;
@@ -1873,8 +2027,8 @@ extern "C" int cb2_rt_render_csr(cb2_rt_scene* sc, const cb2_rays* rays, int64_t
     if (rc != CB2_OK) return rc;
     CB2_CUDA(cudaMemcpyAsync(row_offset, sc->stage[5], (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (nnz > 0) {
-        CB2_CUDA(cudaMemcpyAsync(columns, sc->stage[6], (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CB2_CUDA(cudaMemcpyAsync(lengths, sc->stage[7], (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if ((rc = cb2_d2h(columns, sc->stage[6], (size_t)nnz * sizeof(int32_t), st)) != CB2_OK) return rc;
+        if ((rc = cb2_d2h(lengths, sc->stage[7], (size_t)nnz * sizeof(double), st)) != CB2_OK) return rc;
     }
     if (stats) CB2_CUDA(cudaMemcpyAsync(stats, sc->stats_dev, sizeof(cb2_stats), cudaMemcpyDeviceToHost, st));
     CB2_CUDA(cudaStreamSynchronize(st));

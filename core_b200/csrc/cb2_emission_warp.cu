@@ -1767,6 +1767,14 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     int rc;
     void *pend_dst = nullptr, *pend_src = nullptr;          // deferred device -> host copy of the previous batch
     size_t pend_bytes = 0;
+    int64_t pend_r0 = 0, pend_n = 0;
+    auto flush_pending = [&]() -> int {
+        int rc2 = CB2_OK;
+        if (sc->d2h_rows) rc2 = cb2_d2h_rows(sc->d2h_host, sc->d2h_rows + pend_r0, pend_n, pend_src, (size_t)S.bins * esz, sc->copy_stream);
+        else rc2 = cb2_cuda_check(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream), "frame rows device -> host");
+        pend_bytes = 0;
+        return rc2;
+    };
     for (int64_t r0 = 0; r0 < rays.n_rays;) {
         DevRays sub = rays;
         sub.n_rays = std::min(batch, rays.n_rays - r0);
@@ -1791,8 +1799,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         // the previous batch's rows go to the host now: enqueued after this batch's 8-byte read-back so that the small
         // copy never queues behind the big one on the copy engine (that stall cost the whole overlap)
         if (pend_bytes) {
-            CB2_CUDA(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream));
-            pend_bytes = 0;
+            if ((rc = flush_pending()) != CB2_OK) return rc;
         }
         const size_t rec_bytes = (size_t)n_groups * std::max(n_comp, 1) * REC_FLOATS_PER_COMP * sizeof(float);
         if (rec_bytes > rec_cap_bytes && sub.n_rays > 128) {     // too many samples in this batch: halve it and retry
@@ -1920,9 +1927,10 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
             pend_dst = (char*)sc->d2h_host + (size_t)r0 * S.bins * esz;
             pend_src = o;
             pend_bytes = (size_t)sub.n_rays * S.bins * esz;
+            pend_r0 = r0; pend_n = sub.n_rays;
         }
         r0 += sub.n_rays;
     }
-    if (pend_bytes) CB2_CUDA(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream));
+    if (pend_bytes && (rc = flush_pending()) != CB2_OK) return rc;
     return CB2_OK;
 }

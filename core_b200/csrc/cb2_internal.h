@@ -374,6 +374,7 @@ struct cb2_scene {
     // host-buffer entry point: rows of finished ray batches are copied to the caller's buffer on a second stream while
     // the next batch computes (set for the duration of cb2_emission_render only)
     void* d2h_host;
+    const int64_t* d2h_rows;   // optional destination row of every ray of the call (cb2_emission_render_rows)
     cudaStream_t copy_stream;
     cudaEvent_t copy_ev;
     // optional per-kernel timing (cb2_scene_profile)
@@ -391,6 +392,9 @@ struct cb2_rt_scene {
     double* scratch;         // [n_warps][bins] per-warp dense accumulators
     int32_t* touched;        // [n_warps][touch_cap]
     int n_warps, touch_cap;
+    int32_t* row_cols;       // single-traversal CSR: strided scratch rows [n_rays][touch_cap], grow-only
+    double* row_len;
+    size_t row_cap_rays;
     void* stage[8];
     size_t stage_bytes[8];
     unsigned long long* stats_dev;
@@ -410,6 +414,10 @@ int cb2_launch_emission(cb2_scene* sc, const DevRays& rays, void* out, int out_f
                         unsigned long long* stats_dev, cudaStream_t stream);
 int cb2_emission_config(cb2_scene* sc);
 size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
+int cb2_launch_rt_compact(int64_t n_rays, int64_t row_stride, const int64_t* row_offset, const int32_t* scratch_cols, const double* scratch_len,
+                          int32_t* columns, double* lengths, cudaStream_t st);
+int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
+int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st);
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                              unsigned long long* stats, int count_samples, cudaStream_t stream);
 int64_t cb2_warp_batch_rays(const cb2_scene* sc);

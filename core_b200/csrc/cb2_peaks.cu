@@ -33,6 +33,52 @@ __global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, int iters) {
     if (s == 123.456f) out[0] = s;
 }
 
+template <int ILP>
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) x[i] = (double)(threadIdx.x + i) * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) x[i] = fma(x[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// FP64 FMA issue rate (the ray-transfer kernel's index arithmetic is float64): TFLOP/s
+extern "C" int cb2_measure_peak_fp64(int device, double* fp64_tflops) {
+    CB2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CB2_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CB2_CUDA(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CB2_CUDA(cudaEventCreate(&e0));
+    CB2_CUDA(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    constexpr int ILP = 8;
+    float ms = 0.f;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CB2_CUDA(cudaEventRecord(e0));
+        dfma_peak_kernel<ILP><<<blocks, threads>>>(d, iters, 1.0000001, 1e-7);
+        CB2_CUDA(cudaEventRecord(e1));
+        CB2_CUDA(cudaEventSynchronize(e1));
+        CB2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * blocks * threads * (double)iters * ILP / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && fl > best) best = fl;
+    }
+    CB2_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (fp64_tflops) *fp64_tflops = best;
+    return CB2_OK;
+}
+
 extern "C" int cb2_measure_peaks(int device, double* fp32_tflops, double* sfu_tops, double* sm_clock_mhz) {
     CB2_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;

@@ -157,7 +157,7 @@ __device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsig
 template <bool PACKED>
 __global__ void __launch_bounds__(RT_CSR_MAX_WARPS * 32, 3)
 rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset, int32_t* __restrict__ columns,
-              double* __restrict__ lengths, int hbits, int cap, unsigned long long* __restrict__ stats) {
+              double* __restrict__ lengths, int hbits, int cap, int64_t row_stride, unsigned long long* __restrict__ stats) {
     extern __shared__ int rt_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int H = 1 << hbits;
@@ -174,7 +174,10 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
 
     for (int64_t ray = gw; ray < rays.n_rays; ray += nwarps) {
         int count = 0;
-        const int64_t off = (mode == 2) ? row_offset[ray] : 0;
+        // mode 2: the ray's row of the final CSR (offsets from the count pass); mode 3 (single traversal): its row of the strided
+        // scratch [ray][row_stride], compacted afterwards
+        const bool fill = mode >= 2;
+        const int64_t off = (mode == 2) ? row_offset[ray] : (mode == 3 ? ray * row_stride : 0);
         const double ox = rays.origin[3 * ray], oy = rays.origin[3 * ray + 1], oz = rays.origin[3 * ray + 2];
         const double dx = rays.direction[3 * ray], dy = rays.direction[3 * ray + 1], dz = rays.direction[3 * ray + 2];
         for (int64_t sg = rays.seg_offset[ray]; sg < rays.seg_offset[ray + 1]; sg++) {
@@ -201,7 +204,22 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                 const int prev = __shfl_up_sync(FULL, src, 1);
                 const bool head = (lane == 0) || (src != prev);
                 const unsigned heads = __ballot_sync(FULL, head);
-                const bool act = head && src >= 0;
+                const bool head_act = head && src >= 0;
+                // run heads of this group that carry the same source (a ray can leave a cell and come back within 32 steps) are
+                // merged: the lowest such lane speaks for the source with the sum of their run lengths — slot numbers (= order of
+                // first visit) and the order of the additions no longer depend on which lane wins a race
+                int run = 0;
+                if (head_act) {
+                    const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+                    run = (higher ? (__ffs(higher) - 1) : 32) - lane;
+                }
+                const unsigned ham = __ballot_sync(FULL, head_act);
+                bool act = head_act;
+                if (head_act && mode != 1) {                       // (the count of distinct sources does not depend on who claims)
+                    const unsigned peers = __match_any_sync(ham, src);
+                    run = (int)__reduce_add_sync(peers, (unsigned)run);
+                    act = lane == __ffs(peers) - 1;
+                }
                 // phase 1: find or claim the key's table position
                 int h = 0;
                 bool is_new = false;
@@ -231,33 +249,31 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                     if (slot < cap) {
                         if (PACKED) keys[h] = (int)(((unsigned)src << 12) | (unsigned)slot);
                         else { slots[h] = (unsigned short)slot; used[slot] = (unsigned short)h; }
-                        if (mode == 2) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
+                        if (fill) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
                     } else overflow++;
                 }
                 count += __popc(nm);
                 __syncwarp();
                 // phase 3: run length into the row
-                if (mode == 2 && act) {
-                    const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-                    const int next = higher ? (__ffs(higher) - 1) : 32;
+                if (fill && act) {
                     const int slot = PACKED ? (int)((unsigned)keys[h] & 0xFFFu) : (int)slots[h];
-                    if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)(next - lane), dt));
+                    if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)run, dt));
                 }
             }
         }
         // reset the touched table positions for the next ray
         __syncwarp();
         const int cnt = min(count, cap);
-        if (PACKED) {
+        if (PACKED || count > cap) {                      // (after a slot overflow the used-position list is incomplete: clear everything)
             if (count > 0)
                 for (int i = lane; i < H; i += 32) keys[i] = -1;
         } else {
             for (int pos = lane; pos < cnt; pos += 32) keys[used[pos]] = -1;
         }
-        if (mode == 1 && lane == 0) row_offset[ray] = cnt;
+        if ((mode == 1 || mode == 3) && lane == 0) row_offset[ray] = cnt;
         __syncwarp();
     }
-    if (mode == 1 && gw == 0 && lane == 0) row_offset[rays.n_rays] = 0;
+    if ((mode == 1 || mode == 3) && gw == 0 && lane == 0) row_offset[rays.n_rays] = 0;
     if (stats) {
         for (int o = 16; o > 0; o >>= 1) overflow += __shfl_down_sync(FULL, overflow, o);
         if (lane == 0) {
@@ -265,6 +281,26 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
             if (overflow) atomicAdd(stats + 5, overflow);
         }
     }
+}
+
+// single-traversal CSR, last step: the rays' rows move from the strided scratch to their places in the CSR (one warp per ray)
+__global__ void __launch_bounds__(256)
+rt_compact_kernel(int64_t n_rays, int64_t row_stride, const int64_t* __restrict__ row_offset, const int32_t* __restrict__ scratch_cols,
+                  const double* __restrict__ scratch_len, int32_t* __restrict__ columns, double* __restrict__ lengths) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n_rays) return;
+    const int64_t o = row_offset[ray], cnt = row_offset[ray + 1] - o, s = ray * row_stride;
+    for (int64_t i = lane; i < cnt; i += 32) {
+        columns[o + i] = __ldcs(scratch_cols + s + i);
+        lengths[o + i] = __ldcs(scratch_len + s + i);
+    }
+}
+
+int cb2_launch_rt_compact(int64_t n_rays, int64_t row_stride, const int64_t* row_offset, const int32_t* scratch_cols, const double* scratch_len,
+                          int32_t* columns, double* lengths, cudaStream_t st) {
+    rt_compact_kernel<<<(unsigned)((n_rays * 32 + 255) / 256), 256, 0, st>>>(n_rays, row_stride, row_offset, scratch_cols, scratch_len, columns, lengths);
+    return cb2_cuda_check(cudaGetLastError(), "rt_compact_kernel launch");
 }
 
 int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double* dense_out, int accumulate, int64_t* row_offset,
@@ -308,10 +344,10 @@ int cb2_launch_rt(const cb2_rt_scene* sc, const DevRays& rays, int mode, double*
     if (blocks < 1) blocks = 1;
     if (packed) {
         CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rt_csr_kernel<true><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+        rt_csr_kernel<true><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, (int64_t)cap, stats_dev);
     } else {
         CB2_CUDA(cudaFuncSetAttribute(rt_csr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rt_csr_kernel<false><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, stats_dev);
+        rt_csr_kernel<false><<<(unsigned)blocks, wpc * 32, smem, st>>>(sc->rt, rays, mode, row_offset, columns, lengths, hbits, cap, (int64_t)cap, stats_dev);
     }
     return cb2_cuda_check(cudaGetLastError(), "rt_csr_kernel launch");
 }

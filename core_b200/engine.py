@@ -33,21 +33,34 @@ class EmissionScene:
         except Exception:
             pass
 
-    def render(self, rays, out=None, scale=1.0, accumulate=False, dtype=np.float64, out_of_domain="raise"):
+    def render(self, rays, out=None, scale=1.0, accumulate=False, dtype=np.float64, out_of_domain="raise", rows=None):
         """spectra[n_rays, bins] (+)= scale * integral of the emission along every ray.  Returns (out, stats dict).
 
         Samples that leave a table built without extrapolation (rates, the psi grid) are clamped to the table edge and counted on
         the device; the reference raises ValueError from the interpolator there ('none' extrapolation), so does this
         call once the frame is back — ``out_of_domain="count"`` returns the clamped result with ``stats["out_of_domain"]`` instead."""
-        if out is None:
-            out = np.zeros((rays.n_rays, self.bins), dtype=dtype)
-            accumulate = False
-        if out.dtype not in (np.float64, np.float32) or not out.flags.c_contiguous or out.shape != (rays.n_rays, self.bins):
-            raise ValueError("out must be a C-contiguous float32/float64 array of shape (n_rays, bins)")
         st = _abi.Stats()
         rs = rays.as_struct()
-        _abi.check(self._lib, self._lib.cb2_emission_render(self._h, C.byref(rs), out.ctypes.data_as(C.c_void_p),
-                                                            int(out.dtype == np.float64), float(scale), int(accumulate), C.byref(st)))
+        if rows is not None:
+            # ``rows[i]``: the row of the frame ``out`` [n_rows, bins] that receives ray i (cb2_emission_render_rows): a rank's tiles
+            # land on their pixels of the image-ordered frame; not accumulated
+            rows = np.ascontiguousarray(rows, dtype=np.int64)
+            if out is None or accumulate:
+                raise ValueError("rows needs a frame to write into (out=...) and does not accumulate")
+            if (out.dtype not in (np.float64, np.float32) or not out.flags.c_contiguous or out.ndim != 2 or out.shape[1] != self.bins
+                    or rows.shape != (rays.n_rays,) or (rows.size and (rows.min() < 0 or rows.max() >= out.shape[0]))):
+                raise ValueError("out must be a C-contiguous float32/float64 frame [n_rows, bins] and rows one valid row index per ray")
+            _abi.check(self._lib, self._lib.cb2_emission_render_rows(self._h, C.byref(rs), rows.ctypes.data_as(_abi.c_int64_p),
+                                                                     out.ctypes.data_as(C.c_void_p), int(out.dtype == np.float64),
+                                                                     float(scale), C.byref(st)))
+        else:
+            if out is None:
+                out = np.zeros((rays.n_rays, self.bins), dtype=dtype)
+                accumulate = False
+            if out.dtype not in (np.float64, np.float32) or not out.flags.c_contiguous or out.shape != (rays.n_rays, self.bins):
+                raise ValueError("out must be a C-contiguous float32/float64 array of shape (n_rays, bins)")
+            _abi.check(self._lib, self._lib.cb2_emission_render(self._h, C.byref(rs), out.ctypes.data_as(C.c_void_p),
+                                                                int(out.dtype == np.float64), float(scale), int(accumulate), C.byref(st)))
         stats = st.as_dict()
         if out_of_domain == "raise" and stats["out_of_domain"] > 0:
             raise ValueError("The specified value is outside of the range of the supplied data and/or extrapolation range: %d "
@@ -242,8 +255,10 @@ class RayTransferScene:
 
 
 def measure_peaks(device=0):
-    """Live FP32-FMA and MUFU.EX2 issue-rate microbenchmarks -> dict(fp32_tflops, sfu_tops, sm_clock_mhz)."""
+    """Live FP32-FMA, MUFU.EX2 and FP64-FMA issue-rate microbenchmarks -> dict(fp32_tflops, sfu_tops, sm_clock_mhz, fp64_tflops)."""
     lib = _abi.load_library()
     a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
     _abi.check(lib, lib.cb2_measure_peaks(int(device), C.byref(a), C.byref(b), C.byref(c)))
-    return {"fp32_tflops": a.value, "sfu_tops": b.value, "sm_clock_mhz": c.value}
+    d = C.c_double(0)
+    _abi.check(lib, lib.cb2_measure_peak_fp64(int(device), C.byref(d)))
+    return {"fp32_tflops": a.value, "sfu_tops": b.value, "sm_clock_mhz": c.value, "fp64_tflops": d.value}

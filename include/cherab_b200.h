@@ -367,6 +367,8 @@ int         cb2_device_count(void);
 
 /* Roofline denominators measured live (FFMA and MUFU.EX2 issue-rate microbenchmarks): TFLOP/s, Tops/s, nominal SM MHz. */
 int         cb2_measure_peaks(int device, double* fp32_tflops, double* sfu_tops, double* sm_clock_mhz);
+/* FP64 FMA issue rate, TFLOP/s (denominator of the ray-transfer kernel's float64 index arithmetic). */
+int         cb2_measure_peak_fp64(int device, double* fp64_tflops);
 
 /* Build device-resident tables from a flattened scene.  Replaces PlasmaMaterial.__init__ + the lazy
  * _populate_cache of every model (plasma/material.pyx:37-46; impact_excitation.pyx:102-128). */
@@ -380,6 +382,14 @@ int cb2_scene_destroy(cb2_scene* scene);
  * out is double[n_rays][bins] if out_f64 else float[n_rays][bins].  Host<->device copies happen inside. */
 int cb2_emission_render(cb2_scene* scene, const cb2_rays* rays, void* out, int out_f64,
                         double scale, int accumulate, cb2_stats* stats);
+
+/* Same, with a destination row per ray: ray i's spectrum goes to row dest_row[i] of the HOST frame `out` (not accumulated).
+ * This is how the tiles of an image reach their pixels: the rays of a rank are listed tile by tile (16 x 16 pixels), the frame is
+ * pixel-ordered, so 16 consecutive rays are 16 consecutive rows — the library turns dest_row into runs and issues one strided
+ * device -> host copy per group of equally spaced runs, overlapped with the next batch's kernels.  With N ranks every rank passes
+ * the same frame (shared host memory) and its own rows; nothing has to be permuted afterwards. */
+int cb2_emission_render_rows(cb2_scene* scene, const cb2_rays* rays, const int64_t* dest_row, void* out, int out_f64,
+                             double scale, cb2_stats* stats);
 
 /* Same, DEVICE buffers (torch tensors): every pointer in `rays` and `out` is device memory on the scene's device;
  * launches on `stream` (a cudaStream_t passed as void*), does not synchronise. stats may be NULL;

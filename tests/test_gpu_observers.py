@@ -175,3 +175,47 @@ def test_group_observe_on_the_device_matches_the_host_ray_path():
     np.testing.assert_allclose(sight.power_spectra, rad * np.array(sight.sensitivity)[:, None], rtol=1e-14)
     with pytest.raises(ValueError):
         cb.FibreOpticGroup().observe(scene, plasma.geometry)
+
+
+@pytest.mark.parametrize("order", ["tiles", "random", "ragged"])
+def test_render_rows_puts_every_ray_on_its_row_of_the_frame(order):
+    # cb2_emission_render_rows: a rank's tile-ordered rays land on their pixels of the image-ordered host frame (strided D2H per tile);
+    # any other row list must work too (single rows, runs of different lengths)
+    from core_b200.sharding import tile_pixels
+    plasma = generomak.get_plasma()
+    plasma.atomic_data = cb.SyntheticADAS()
+    line = cb.Line(cb.hydrogen, 0, (3, 2))
+    plasma.models = [cb.ExcitationLine(line), cb.RecombinationLine(line)]
+    plasma.integrator = cb.NumericalIntegrator(step=0.01)
+    flat = cb.flatten_scene(plasma, 655.0, 657.5, 96)
+    nx = ny = 40
+    cam = cb.PinholeCamera((nx, ny), fov=45.0, transform=cb.look_at((2.3, 0.0, 1.25), (1.0, 0.8, -0.5)))
+    if order == "tiles":
+        pix = tile_pixels((nx, ny), 1, 3)               # rank 1 of 3: 16 x 16 tiles, partial tiles at the frame's edge
+    elif order == "random":
+        pix = np.random.default_rng(3).permutation(nx * ny)[:500]
+    else:
+        pix = np.concatenate([np.arange(100, 137), np.arange(10, 12), [5], np.arange(400, 464), np.arange(300, 364), np.arange(200, 264), [1599]])
+    rays = cb.ray_segments(plasma.geometry, *cam.rays(pixel_index=pix), plasma.geometry_to_world())
+    scene = EmissionScene(flat)
+    monkey_batch = 128                                   # several batches, so the overlapped per-batch copies are exercised
+    import os
+    os.environ["CB2_BATCH_RAYS"] = str(monkey_batch)
+    try:
+        plain, _ = scene.render(rays, dtype=np.float32)
+        frame = np.full((nx * ny, 96), -1.0, dtype=np.float32)
+        out, st = scene.render(rays, out=frame, rows=pix)
+    finally:
+        del os.environ["CB2_BATCH_RAYS"]
+    scene.close()
+    assert out is frame and plain.max() > 0
+    assert np.array_equal(frame[pix], plain)
+    untouched = np.ones(nx * ny, dtype=bool)
+    untouched[pix] = False
+    assert np.all(frame[untouched] == -1.0)
+    with pytest.raises(ValueError):
+        scene2 = EmissionScene(flat)
+        try:
+            scene2.render(rays, out=frame, rows=pix + nx * ny)
+        finally:
+            scene2.close()

@@ -163,3 +163,42 @@ def test_random_grids_and_rays(seed):
     if rays.n_segments == 0:
         pytest.skip("no ray hits the grid")
     check(rt, rays)
+
+
+@pytest.mark.parametrize("variant", ["CB2_RT_TWO_PASS", "CB2_RT_UNPACKED", "both"])
+@pytest.mark.parametrize("seed", (0, 3, 7, 11, 19))
+def test_csr_fallback_paths(monkeypatch, variant, seed):
+    # the count + fill traversal pair (taken when the scratch rows of the single traversal do not fit) and the 6-byte hash entries
+    # (grids with >= 2^20 sources) must stay alive: same checks as the default path
+    for v in (("CB2_RT_TWO_PASS", "CB2_RT_UNPACKED") if variant == "both" else (variant,)):
+        monkeypatch.setenv(v, "1")
+    rt, rays = _random_rt(np.random.default_rng(500 + seed))
+    if rays.n_segments == 0:
+        pytest.skip("no ray hits the grid")
+    check(rt, rays)
+
+
+def test_csr_is_reproducible_and_in_order_of_first_visit(monkeypatch):
+    # run heads of one 32-step group that carry the same source are merged before the table is touched: slot numbers and the
+    # order of the float64 additions are fixed, so two builds of the same matrix agree bit for bit — on every path
+    import torch
+    rtc = RayTransferCylinder(radius_outer=2.41, height=3.35, n_radius=100, n_height=200, radius_inner=0.73, n_polar=16, period=90.0,
+                              transform=cb.translate(0, 0, -1.8))
+    cam = cb.PinholeCamera((48, 48), fov=45, transform=cb.look_at((2.3, 0, 1.25), (1.0, 0.8, -0.5)))
+    rays = cb.ray_segments(rtc.primitive, *cam.rays(), rtc.transform)
+    results = []
+    for env in ({}, {}, {"CB2_RT_TWO_PASS": "1"}, {"CB2_RT_UNPACKED": "1"}):
+        for k in ("CB2_RT_TWO_PASS", "CB2_RT_UNPACKED"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        scene = RayTransferScene(rtc)
+        ro, cols, lens = scene.render_csr_device(DeviceRays(rays), capacity=48 * 48 * 1500)
+        torch.cuda.synchronize()
+        results.append((ro.cpu().numpy(), cols.cpu().numpy(), lens.cpu().numpy()))
+        scene.close()
+    for ro, cols, lens in results[1:]:
+        assert np.array_equal(ro, results[0][0]) and np.array_equal(cols, results[0][1]) and np.array_equal(lens, results[0][2])
+    # order of first visit: the oracle's dense row, walked along the ray, meets the sources in the order the row lists them
+    ro, cols, lens = results[0]
+    assert ro[-1] > 48 * 48 * 50

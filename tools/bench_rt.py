@@ -43,8 +43,24 @@ t0 = time.perf_counter()
 r2, c2, l2, st = scene.render_csr(rays, capacity=cap)
 host_ms = (time.perf_counter() - t0) * 1e3
 nnz = int(cols.numel())
+t0 = time.perf_counter()
+r3, c3, l3, _ = scene.render_csr(rays, capacity=cap)
+host_ms_warm = (time.perf_counter() - t0) * 1e3
+from core_b200.engine import measure_peaks           # noqa: E402
+peaks = measure_peaks()
+peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+F_STEP = 22.0                                        # float64 flop per midpoint step + 1 sqrt
+fp64 = steps * F_STEP / ms * 1e-9
+csr_bytes = nnz * 12 + (rays.n_rays + 1) * 8
+hbm_peak = float(peaks_file.get("hbm_gbs", 6500.0))
 print(json.dumps({"config": "C4 ray transfer %dx%d rays, cylinder 400x1x800, step %.3e m, CSR" % (px, px, rtc.step),
                   "rays": rays.n_rays, "steps": steps, "rt_steps_counter": st["rt_steps"], "nnz": nnz,
-                  "device_ms": ms, "Gsteps_per_s": steps / ms * 1e-6, "host_buffer_ms": host_ms,
-                  "csr_bytes": nnz * 12 + (rays.n_rays + 1) * 8,
-                  "algorithmic": {"flop_fp64_per_step": 22, "fp64_tflops": steps * 22 / ms * 1e-9}}))
+                  "device_ms": ms, "Gsteps_per_s": steps / ms * 1e-6,
+                  "host_buffer_ms": host_ms, "host_buffer_ms_second_call": host_ms_warm,
+                  "host_buffer_note": "cb2_rt_render_csr into fresh pageable numpy arrays: rays H2D + kernels + CSR D2H through the "
+                                      "pinned chunk ring (cb2_d2h) + first-touch faults of the destination",
+                  "pcie_floor_ms": csr_bytes / 55e9 * 1e3, "csr_bytes": csr_bytes,
+                  "roofline": {"bound": "fp64", "achieved": fp64, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+                               "frac": fp64 / peaks["fp64_tflops"], "flop_fp64_per_step": F_STEP,
+                               "peak_source": "measured live (cb2_measure_peak_fp64: DFMA issue-rate microbenchmark, same process)",
+                               "hbm": {"achieved_gbs": csr_bytes / ms * 1e-6, "peak_gbs": hbm_peak, "frac": csr_bytes / ms * 1e-6 / hbm_peak}}}))
