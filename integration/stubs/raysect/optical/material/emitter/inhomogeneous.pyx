@@ -1,0 +1,14 @@
+# cython: language_level=3
+from raysect.optical cimport World, Ray, Primitive, Point3D, Spectrum, AffineMatrix3D
+
+
+cdef class InhomogeneousVolumeEmitter:
+    def __init__(self, VolumeIntegrator integrator=None):
+        self.integrator = integrator
+
+
+cdef class VolumeIntegrator:
+    cpdef Spectrum integrate(self, Spectrum spectrum, World world, Ray ray, Primitive primitive,
+                             InhomogeneousVolumeEmitter material, Point3D start_point, Point3D end_point,
+                             AffineMatrix3D world_to_primitive, AffineMatrix3D primitive_to_world):
+        raise NotImplementedError("Virtual method integrate() has not been implemented.")
