@@ -1691,6 +1691,11 @@ static int check_rays(const cb2_rays* r) {
 static int upload_rays(void** stage, size_t* bytes, const cb2_rays* r, DevRays& dr, cudaStream_t st) {
     const size_t n = (size_t)r->n_rays, ns = (size_t)r->n_segments;
     int rc;
+    // the kernels index seg_t0 / seg_t1 with these: a list that is not monotone inside [0, n_segments] would read out of bounds
+    if (r->seg_offset[0] < 0 || r->seg_offset[n] > r->n_segments) return cb2_fail(CB2_ERR_VALUE, "seg_offset leaves [0, n_segments]");
+    for (size_t i = 0; i < n; i++)
+        if (r->seg_offset[i + 1] < r->seg_offset[i]) return cb2_fail(CB2_ERR_VALUE, "seg_offset is not monotone at ray %lld", (long long)i);
+    if (ns && (!r->seg_t0 || !r->seg_t1)) return cb2_fail(CB2_ERR_VALUE, "null segment arrays");
     if ((rc = stage_reserve(stage, bytes, 0, n * 3 * sizeof(double))) != CB2_OK) return rc;
     if ((rc = stage_reserve(stage, bytes, 1, n * 3 * sizeof(double))) != CB2_OK) return rc;
     if ((rc = stage_reserve(stage, bytes, 2, (n + 1) * sizeof(int64_t))) != CB2_OK) return rc;
