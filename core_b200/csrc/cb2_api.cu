@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1594,6 +1595,12 @@ int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
         CB2_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
         CB2_CUDA(cudaStreamSynchronize(st));
         return CB2_OK;
+    }
+    {
+        // fresh destination memory is faulted in page by page as the workers write it (732 000 faults for the 3 GB CSR of C4): ask for
+        // transparent huge pages on the part of the range that is 2 MB aligned (a hint; ignored where THP is off or the pages exist)
+        const uintptr_t a = ((uintptr_t)dst + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), e = ((uintptr_t)dst + bytes) & ~(((uintptr_t)2 << 20) - 1);
+        if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
     }
     std::lock_guard<std::mutex> guard(g_d2h.lock);
     for (int b = 0; b < D2H_RING; b++) {

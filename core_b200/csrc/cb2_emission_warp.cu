@@ -1625,8 +1625,8 @@ bin_kernel(const __grid_constant__ DevScene S, int64_t n_rays, const int64_t* __
     unsigned n_gauss = 0, n_lorentz = 0;
     int touched = 0;
     const int64_t G0 = gbase[ray], G1 = gbase[ray + 1];
-    if constexpr (NW == 8) {
-    // 8-warp instances (calls with few rays): work items = (group, component) pairs dealt round-robin to the warps — a ray with few
+    if constexpr (NW >= 8) {
+    // 8- and 16-warp instances (calls with few rays): work items = (group, component) pairs dealt round-robin to the warps — a ray with few
     // groups but many components (C2: 2 groups x 30 Stark / Zeeman components, each a serial walk over its bin range) still occupies
     // every warp.  The next item's record is in flight while this one is binned.
     const unsigned n_items = (unsigned)(G1 - G0) * (unsigned)n_comp;
@@ -1711,7 +1711,9 @@ size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins) {
 }
 
 int64_t cb2_warp_batch_rays(const cb2_scene* sc) {
-    int64_t b = 16384;
+    // rays per batch: every kernel launch ends with a partly filled wave of CTAs (148 SMs x 6..8 resident), so bigger batches waste
+    // less — C3: 48.4 ms per 65 536 rays at 16 384, 47.3 at 32 768, 46.7 at 65 536 (record buffer 3.9 GB per 16 384 rays)
+    int64_t b = 65536;
     if (const char* e = getenv("CB2_BATCH_RAYS")) { const long v = atol(e); if (v >= 128) b = v / 128 * 128; }
     if (sc->host.brems.present && sc->host.brems.mode == 3) b = std::min(b, cb2_moment_batch(sc->host.brems.k_pad));
     return b;
@@ -1764,6 +1766,9 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     const size_t esz = out_f64 ? sizeof(double) : sizeof(float);
     const size_t rec_cap_bytes = (size_t)24 << 30;            // bound on the record buffer; batches shrink to respect it
     int64_t batch = std::min(cb2_warp_batch_rays(sc), rays.n_rays);
+    // host-buffer calls copy a finished batch's rows back while the next batch computes: at least eight batches per call keep the
+    // copy of the last one (which nothing hides) small
+    if (sc->d2h_host && !getenv("CB2_BATCH_RAYS")) batch = std::min(batch, std::max<int64_t>(16384, (rays.n_rays / 8 + 127) / 128 * 128));
     int rc;
     void *pend_dst = nullptr, *pend_src = nullptr;          // deferred device -> host copy of the previous batch
     size_t pend_bytes = 0;
@@ -1886,11 +1891,14 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
         // (fused path: the frame rows exist already; only the groups with blend-zone samples are binned, on top of them)
         const unsigned* bmask = fused ? sc->gblend : sc->gmask;
         const int bacc = fused ? 1 : accumulate;
-        // a call that cannot fill the GPU with one CTA per ray (0-D observer groups: C2 has 64 rays) takes 8 warps per ray; decided
+        // a call that cannot fill the GPU with one CTA per ray (0-D observer groups: C2 has 64 rays) takes 8 or 16 warps per ray; decided
         // on the call's ray count, not the batch's, so a ray's bits do not depend on where the batches are cut
         int bin_nw = sc->bin_nw;
         if (bin_nw == 4 && rays.n_rays < 1024 && cb2_warp_smem_bytes(8, sc->acc_f64, S.bins) <= 200 * 1024) bin_nw = 8;
-        if (bin_nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
+        if (bin_nw == 8 && rays.n_rays < 256 && cb2_warp_smem_bytes(16, sc->acc_f64, S.bins) <= 200 * 1024) bin_nw = 16;
+        if (bin_nw == 16) rc = sc->acc_f64 ? launch_bin<16, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
+                                           : launch_bin<16, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);
+        else if (bin_nw == 8) rc = sc->acc_f64 ? launch_bin<8, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
                                           : launch_bin<8, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);
         else if (bin_nw == 2) rc = sc->acc_f64 ? launch_bin<2, double>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st)
                                                : launch_bin<2, float>(sc, bmask, sub.n_rays, o, out_f64, scale, bacc, stats, st);

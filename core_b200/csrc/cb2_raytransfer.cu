@@ -153,6 +153,9 @@ __device__ __forceinline__ unsigned rt_hash(int src, int hbits) { return ((unsig
 // touch fewer than 4095 of them (every BASELINE configuration): 4 bytes per position instead of 6 + a used-position list, i.e.
 // about twice the resident warps per SM for a latency-bound kernel.  The whole table is cleared after every ray.
 #define RT_PENDING 0xFFFu
+#ifndef RT_STEPS_PER_LANE
+#define RT_STEPS_PER_LANE 4
+#endif
 #define RT_CSR_MAX_WARPS 9          // 288 threads x 3 CTAs per SM: 72 registers per thread, 27 resident warps
 template <bool PACKED>
 __global__ void __launch_bounds__(RT_CSR_MAX_WARPS * 32, 3)
@@ -198,66 +201,112 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
             if (n < R.min_samples) n = R.min_samples;
             const double dt = __ddiv_rn(length, (double)n);
             if (lane == 0) steps += (unsigned long long)n;
-            for (int it0 = 0; it0 < n; it0 += 32) {
-                const int it = it0 + lane;
-                const int src = (it < n) ? rt_source(R, st, dir, dt, it) : -2;
-                const int prev = __shfl_up_sync(FULL, src, 1);
-                const bool head = (lane == 0) || (src != prev);
-                const unsigned heads = __ballot_sync(FULL, head);
-                const bool head_act = head && src >= 0;
-                // run heads of this group that carry the same source (a ray can leave a cell and come back within 32 steps) are
-                // merged: the lowest such lane speaks for the source with the sum of their run lengths — slot numbers (= order of
-                // first visit) and the order of the additions no longer depend on which lane wins a race
-                int run = 0;
-                if (head_act) {
-                    const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-                    run = (higher ? (__ffs(higher) - 1) : 32) - lane;
+            // 32 K consecutive steps per iteration: lane l owns steps it0 + K l + j, j < K.  The bookkeeping below — run heads, merge,
+            // hash probe, slot numbering — is warp-wide work per iteration, not per step: K steps per lane divide it by K (it was
+            // ~ 2/3 of the kernel's instructions with one step per lane; C4: 37.3 ms at K = 1, 29.8 at K = 2, 28.8 at K = 4).  Tried and
+            // dropped: index decisions by reciprocal multiplication and squared cell faces with the IEEE division / square-root chain
+            // as the fallback near a face — bit-identical, but no faster (31.9 ms at K = 4): the chain is not what the kernel waits for.
+            constexpr int K = RT_STEPS_PER_LANE;
+            for (int it0 = 0; it0 < n; it0 += 32 * K) {
+                int sj[K];
+                unsigned mj[K];
+                bool hj[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const int it = it0 + K * lane + j;
+                    sj[j] = (it < n) ? rt_source(R, st, dir, dt, it) : -2;
                 }
-                const unsigned ham = __ballot_sync(FULL, head_act);
-                bool act = head_act;
-                if (head_act && mode != 1) {                       // (the count of distinct sources does not depend on who claims)
-                    const unsigned peers = __match_any_sync(ham, src);
-                    run = (int)__reduce_add_sync(peers, (unsigned)run);
-                    act = lane == __ffs(peers) - 1;
+                const int prev = __shfl_up_sync(FULL, sj[K - 1], 1);
+                unsigned many = 0u;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    hj[j] = j == 0 ? ((lane == 0) || (sj[0] != prev)) : (sj[j] != sj[j - 1]);
+                    mj[j] = __ballot_sync(FULL, hj[j]);
+                    many |= mj[j];
                 }
-                // phase 1: find or claim the key's table position
-                int h = 0;
-                bool is_new = false;
-                if (act) {
-                    h = (int)rt_hash(src, hbits);
-                    if (PACKED) {
-                        const int claim = (int)(((unsigned)src << 12) | RT_PENDING);
-                        for (;;) {
-                            const int old = atomicCAS(&keys[h], -1, claim);
-                            if (old == -1) { is_new = true; break; }
-                            if (((unsigned)old >> 12) == (unsigned)src) break;
-                            h = (h + 1) & (H - 1);
-                        }
-                    } else {
-                        for (;;) {
-                            const int old = atomicCAS(&keys[h], -1, src);
-                            if (old == -1) { is_new = true; break; }
-                            if (old == src) break;
-                            h = (h + 1) & (H - 1);
-                        }
+                // first head position (in steps within the iteration, 0 .. 32 K - 1) after this lane's steps
+                const unsigned later = (lane == 31) ? 0u : (many & ~((2u << lane) - 1u));
+                int next = 32 * K;
+                if (later) {
+                    const int nl = __ffs(later) - 1;
+                    int first = K - 1;
+#pragma unroll
+                    for (int j = K - 2; j >= 0; j--)
+                        if ((mj[j] >> nl) & 1u) first = j;
+                    next = K * nl + first;
+                }
+                // run length of every head of this lane: up to the lane's next head, else up to `next`
+                int runj[K];
+                int live = 0;                                      // bit j: head j is live (a mapped source starts a run there)
+                {
+                    int end = next - K * lane;                     // position of the next head relative to this lane's first step
+#pragma unroll
+                    for (int j = K - 1; j >= 0; j--) {
+                        runj[j] = end - j;
+                        if (hj[j]) { end = j; if (sj[j] >= 0) live |= 1 << j; }
                     }
                 }
-                // phase 2: new keys take consecutive slots of the ray's row
-                const unsigned nm = __ballot_sync(FULL, is_new);
-                if (is_new) {
-                    const int slot = count + __popc(nm & ((1u << lane) - 1u));
-                    if (slot < cap) {
-                        if (PACKED) keys[h] = (int)(((unsigned)src << 12) | (unsigned)slot);
-                        else { slots[h] = (unsigned short)slot; used[slot] = (unsigned short)h; }
-                        if (fill) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
-                    } else overflow++;
-                }
-                count += __popc(nm);
-                __syncwarp();
-                // phase 3: run length into the row
-                if (fill && act) {
-                    const int slot = PACKED ? (int)((unsigned)keys[h] & 0xFFFu) : (int)slots[h];
-                    if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)run, dt));
+                // a lane with several live heads (runs shorter than K steps) takes them in further passes, in step order
+                for (int pass = 0; pass < K; pass++) {
+                    const bool head_act = live != 0;
+                    const unsigned ham = __ballot_sync(FULL, head_act);
+                    if (!ham) break;
+                    int src = -1, run = 0;
+                    if (head_act) {
+                        const int j0 = __ffs(live) - 1;
+                        live &= live - 1;
+#pragma unroll
+                        for (int j = 0; j < K; j++)
+                            if (j == j0) { src = sj[j]; run = runj[j]; }
+                    }
+                    // run heads of this pass that carry the same source (a ray can leave a cell and come back within 64 steps) are
+                    // merged: the lowest such lane speaks for the source with the sum of their run lengths — slot numbers (= order
+                    // of first visit) and the order of the additions do not depend on which lane wins a race
+                    bool act = head_act;
+                    if (head_act && mode != 1) {                   // (the count of distinct sources does not depend on who claims)
+                        const unsigned peers = __match_any_sync(ham, src);
+                        run = (int)__reduce_add_sync(peers, (unsigned)run);
+                        act = lane == __ffs(peers) - 1;
+                    }
+                    // phase 1: find or claim the key's table position
+                    int h = 0;
+                    bool is_new = false;
+                    if (act) {
+                        h = (int)rt_hash(src, hbits);
+                        if (PACKED) {
+                            const int claim = (int)(((unsigned)src << 12) | RT_PENDING);
+                            for (;;) {
+                                const int old = atomicCAS(&keys[h], -1, claim);
+                                if (old == -1) { is_new = true; break; }
+                                if (((unsigned)old >> 12) == (unsigned)src) break;
+                                h = (h + 1) & (H - 1);
+                            }
+                        } else {
+                            for (;;) {
+                                const int old = atomicCAS(&keys[h], -1, src);
+                                if (old == -1) { is_new = true; break; }
+                                if (old == src) break;
+                                h = (h + 1) & (H - 1);
+                            }
+                        }
+                    }
+                    // phase 2: new keys take consecutive slots of the ray's row
+                    const unsigned nm = __ballot_sync(FULL, is_new);
+                    if (is_new) {
+                        const int slot = count + __popc(nm & ((1u << lane) - 1u));
+                        if (slot < cap) {
+                            if (PACKED) keys[h] = (int)(((unsigned)src << 12) | (unsigned)slot);
+                            else { slots[h] = (unsigned short)slot; used[slot] = (unsigned short)h; }
+                            if (fill) { columns[off + slot] = src; lengths[off + slot] = 0.0; }
+                        } else overflow++;
+                    }
+                    count += __popc(nm);
+                    __syncwarp();
+                    // phase 3: run length into the row
+                    if (fill && act) {
+                        const int slot = PACKED ? (int)((unsigned)keys[h] & 0xFFFu) : (int)slots[h];
+                        if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)run, dt));
+                    }
                 }
             }
         }

@@ -202,3 +202,4 @@ def test_csr_is_reproducible_and_in_order_of_first_visit(monkeypatch):
     # order of first visit: the oracle's dense row, walked along the ray, meets the sources in the order the row lists them
     ro, cols, lens = results[0]
     assert ro[-1] > 48 * 48 * 50
+
