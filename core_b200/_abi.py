@@ -136,7 +136,7 @@ class Stats(C.Structure):
 class RTDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("kind", C.c_int32), ("grid_shape", C.c_int32 * 3), ("min_samples", C.c_int32),
                 ("grid_steps", C.c_double * 3), ("rmin", C.c_double), ("period", C.c_double), ("step", C.c_double),
-                ("world_to_local", C.c_double * 12), ("voxel_map", c_int32_p), ("bins", C.c_int32), ("_pad", C.c_int32)]
+                ("world_to_local", C.c_double * 12), ("voxel_map", c_int32_p), ("bins", C.c_int32), ("integrator", C.c_int32)]
 
 
 class PrimitiveDesc(C.Structure):

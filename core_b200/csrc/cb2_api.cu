@@ -1875,6 +1875,7 @@ extern "C" int cb2_rt_create(const cb2_rt_desc* d, int device, cb2_rt_scene** ou
     *out = nullptr;
     if (d->abi_version != CB2_ABI_VERSION) return cb2_fail(CB2_ERR_VALUE, "abi_version mismatch");
     if (d->kind != CB2_RT_CYLINDRICAL && d->kind != CB2_RT_CARTESIAN) return cb2_fail(CB2_ERR_TYPE, "unsupported ray-transfer grid kind %d", d->kind);
+    if (d->integrator != 0 && d->integrator != 1) return cb2_fail(CB2_ERR_TYPE, "unsupported ray-transfer integrator %d", d->integrator);
     for (int k = 0; k < 3; k++) {
         if (d->grid_shape[k] < 1) return cb2_fail(CB2_ERR_VALUE, "Number of grid cells must be > 0.");
         if (!(d->grid_steps[k] > 0)) return cb2_fail(CB2_ERR_VALUE, "Grid steps must be > 0.");
@@ -1896,6 +1897,7 @@ extern "C" int cb2_rt_create(const cb2_rt_desc* d, int device, cb2_rt_scene** ou
     r.bins = d->bins;
     r.s0 = d->grid_steps[0]; r.s1 = d->grid_steps[1]; r.s2 = d->grid_steps[2];
     r.rmin = d->rmin; r.period = d->period; r.step = d->step;
+    r.trapezium = d->integrator == 1;
     for (int k = 0; k < 12; k++) r.w2l[k] = d->world_to_local[k];
     const size_t ncell = (size_t)r.n0 * r.n1 * r.n2;
     for (size_t k = 0; k < ncell; k++)

@@ -324,6 +324,7 @@ struct DevRT {
     int bins;
     double s0, s1, s2;      // grid steps
     double rmin, period, step;
+    int trapezium;          // 1: NumericalIntegrator sampling over the emitter's emission_function (cb2_rt_desc.integrator)
     double w2l[12];
     const int32_t* voxel_map;
 };

@@ -35,7 +35,8 @@ __device__ __forceinline__ double row_point(const double* m, double x, double y,
 }
 
 __device__ __forceinline__ int rt_source(const DevRT& R, const double* st, const double* dir, double dt, int it) {
-    const double t = mul_rn(add_rn((double)it, 0.5), dt);
+    // RayTransferIntegrator: midpoints (it + 1/2) dt (emitters.pyx:118); NumericalIntegrator: the trapezium nodes it * h
+    const double t = R.trapezium ? mul_rn((double)it, dt) : mul_rn(add_rn((double)it, 0.5), dt);
     const double x = add_rn(st[0], mul_rn(dir[0], t));
     const double y = add_rn(st[1], mul_rn(dir[1], t));
     const double z = add_rn(st[2], mul_rn(dir[2], t));
@@ -88,11 +89,28 @@ rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* 
                 dir[k] = add_rn(en[k], -st[k]);
             }
             const double length = __dsqrt_rn(add_rn(add_rn(mul_rn(dir[0], dir[0]), mul_rn(dir[1], dir[1])), mul_rn(dir[2], dir[2])));
-            if (length < mul_rn(0.1, R.step)) continue;                // emitters.pyx:104-105
-            for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
-            int n = (int)__ddiv_rn(length, R.step);
-            if (n < R.min_samples) n = R.min_samples;
-            const double dt = __ddiv_rn(length, (double)n);
+            int n;
+            double dt;
+            if (R.trapezium) {
+                // NumericalIntegrator [raysect]: intervals = max(min_samples - 1, ceil(L / step)), samples at k L / intervals, k = 0 .. intervals
+                if (!(length > 0.0)) continue;
+                for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+                int iv = (int)ceil(__ddiv_rn(length, R.step));
+                if (iv < R.min_samples - 1) iv = R.min_samples - 1;
+                if (iv < 1) iv = 1;
+                dt = __ddiv_rn(length, (double)iv);
+                n = iv + 1;
+            } else {
+                if (length < mul_rn(0.1, R.step)) continue;            // emitters.pyx:104-105
+                for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+                n = (int)__ddiv_rn(length, R.step);
+                if (n < R.min_samples) n = R.min_samples;
+                dt = __ddiv_rn(length, (double)n);
+            }
+            // a run of `run` samples starting at sample `first` weighs (2 run - [first == 0] - [first + run == n]) half steps under
+            // the trapezium rule, 2 run under the midpoint rule
+            const double half = mul_rn(0.5, dt);
+            const int trap = R.trapezium;
             if (lane == 0) steps += (unsigned long long)n;
             for (int it0 = 0; it0 < n; it0 += 32) {
                 const int it = it0 + lane;
@@ -104,7 +122,9 @@ rt_kernel(DevRT R, DevRays rays, int mode, double* __restrict__ dense, int64_t* 
                 if (head && src >= 0) {
                     const unsigned higher = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
                     const int next = higher ? (__ffs(higher) - 1) : 32;
-                    const double add = mul_rn((double)(next - lane), dt);
+                    const int run = next - lane, first_it = it0 + lane;
+                    const int halves = 2 * run - (trap ? ((first_it == 0) + (first_it + run == n)) : 0);
+                    const double add = mul_rn((double)halves, half);
                     const double old = atomicAdd(row + src, add);
                     first = (mode != 0) && (old == 0.0);
                 }
@@ -195,11 +215,28 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                 dir[k] = add_rn(en[k], -st[k]);
             }
             const double length = __dsqrt_rn(add_rn(add_rn(mul_rn(dir[0], dir[0]), mul_rn(dir[1], dir[1])), mul_rn(dir[2], dir[2])));
-            if (length < mul_rn(0.1, R.step)) continue;                // emitters.pyx:104-105
-            for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
-            int n = (int)__ddiv_rn(length, R.step);
-            if (n < R.min_samples) n = R.min_samples;
-            const double dt = __ddiv_rn(length, (double)n);
+            int n;
+            double dt;
+            if (R.trapezium) {
+                // NumericalIntegrator [raysect]: intervals = max(min_samples - 1, ceil(L / step)), samples at k L / intervals, k = 0 .. intervals
+                if (!(length > 0.0)) continue;
+                for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+                int iv = (int)ceil(__ddiv_rn(length, R.step));
+                if (iv < R.min_samples - 1) iv = R.min_samples - 1;
+                if (iv < 1) iv = 1;
+                dt = __ddiv_rn(length, (double)iv);
+                n = iv + 1;
+            } else {
+                if (length < mul_rn(0.1, R.step)) continue;            // emitters.pyx:104-105
+                for (int k = 0; k < 3; k++) dir[k] = __ddiv_rn(dir[k], length);
+                n = (int)__ddiv_rn(length, R.step);
+                if (n < R.min_samples) n = R.min_samples;
+                dt = __ddiv_rn(length, (double)n);
+            }
+            // a run of `run` samples starting at sample `first` weighs (2 run - [first == 0] - [first + run == n]) half steps under
+            // the trapezium rule, 2 run under the midpoint rule
+            const double half = mul_rn(0.5, dt);
+            const int trap = R.trapezium;
             if (lane == 0) steps += (unsigned long long)n;
             // 32 K consecutive steps per iteration: lane l owns steps it0 + K l + j, j < K.  The bookkeeping below — run heads, merge,
             // hash probe, slot numbering — is warp-wide work per iteration, not per step: K steps per lane divide it by K (it was
@@ -242,7 +279,8 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                     int end = next - K * lane;                     // position of the next head relative to this lane's first step
 #pragma unroll
                     for (int j = K - 1; j >= 0; j--) {
-                        runj[j] = end - j;
+                        const int run = end - j, first_it = it0 + K * lane + j;
+                        runj[j] = 2 * run - (trap ? ((first_it == 0) + (first_it + run >= n)) : 0);     // in half steps
                         if (hj[j]) { end = j; if (sj[j] >= 0) live |= 1 << j; }
                     }
                 }
@@ -305,7 +343,7 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
                     // phase 3: run length into the row
                     if (fill && act) {
                         const int slot = PACKED ? (int)((unsigned)keys[h] & 0xFFFu) : (int)slots[h];
-                        if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)run, dt));
+                        if (slot < cap) atomicAdd(lengths + off + slot, mul_rn((double)run, half));
                     }
                 }
             }

@@ -34,6 +34,10 @@ class RayTransferObject:
         self.step = step
         self.min_samples = min_samples
         self.transform = transform
+        # None: the emitter's own RayTransferIntegrator(step, min_samples) (emitters.pyx:88-224).  A plasma.NumericalIntegrator here is
+        # the "foreign integrator" case of the reference — Raysect's trapezium rule over RayTransferEmitter.emission_function, unit
+        # emissivity in the cell of every sample (emitters.pyx:452-473, 557-571) — with that integrator's step and min_samples
+        self.integrator = None
         if voxel_map is None:
             self.mask = mask
         else:
@@ -96,6 +100,26 @@ class RayTransferObject:
     def invert_voxel_map(self):
         return [np.where(self._voxel_map == i) for i in range(self._bins)]
 
+    def emission_function(self, point, direction, spectrum, *_unused):
+        """RayTransferEmitter.emission_function (emitters.pyx:452-473, 557-571) for one point in the object's local space: unit
+        emissivity in the light source the point's cell maps to — ``spectrum`` (array of ``bins`` samples) is added to and returned.
+        The protocol method foreign integrators call; whole rays go through the device (``integrator`` attribute)."""
+        x, y, z = (float(c) for c in point)
+        if self.kind == _abi.RT_CYLINDRICAL:
+            i2 = int(z / self.grid_steps[2])
+            i0 = int((np.sqrt(x * x + y * y) - getattr(self, "rmin", 0.0)) / self.grid_steps[0])
+            if self.grid_shape[1] == 1:
+                i1 = 0
+            else:
+                phi = ((180.0 / np.pi) * np.arctan2(y, x) + 360.0) % getattr(self, "period", 360.0)
+                i1 = int(phi / self.grid_steps[1])
+        else:
+            i0, i1, i2 = int(x / self.grid_steps[0]), int(y / self.grid_steps[1]), int(z / self.grid_steps[2])
+        isource = self._voxel_map[i0, i1, i2]           # (IndexError outside the grid, as in the reference)
+        if isource >= 0:
+            spectrum[isource] += 1.0
+        return spectrum
+
     def descriptor(self):
         """(cb2_rt_desc, keepalive) in the layout of include/cherab_b200.h."""
         d = _abi.RTDesc()
@@ -108,6 +132,14 @@ class RayTransferObject:
         d.rmin = getattr(self, "rmin", 0.0)
         d.period = getattr(self, "period", 360.0)
         d.step = self._step
+        d.integrator = 0
+        if self.integrator is not None:
+            from .plasma import NumericalIntegrator
+            if not isinstance(self.integrator, NumericalIntegrator):
+                raise TypeError("integrator must be None (the ray-transfer integrator) or a NumericalIntegrator, not %r" % (self.integrator,))
+            d.integrator = 1
+            d.step = float(self.integrator.step)
+            d.min_samples = max(2, int(self.integrator.min_samples))
         w2l = np.eye(4) if self.transform is None else affine_inverse(self.transform)
         for i in range(3):
             for j in range(4):

@@ -438,7 +438,10 @@ typedef struct cb2_rt_desc {
     double         world_to_local[12];/* row-major 3x4 affine world -> primitive-local (z in [0,height]) */
     const int32_t* voxel_map;         /* [shape0][shape1][shape2], -1 = unmapped */
     int32_t        bins;              /* voxel_map.max()+1 */
-    int32_t        _pad;
+    int32_t        integrator;        /* 0: the emitter's own RayTransferIntegrator (midpoint samples, emitters.pyx:88-224);
+                                         1: a foreign NumericalIntegrator(step, min_samples) [raysect] over the emitter's
+                                            emission_function (unit emissivity in the sample's cell, emitters.pyx:452-473,557-571):
+                                            trapezium rule, intervals = max(min_samples - 1, ceil(L / step)) */
 } cb2_rt_desc;
 
 typedef struct cb2_rt_scene cb2_rt_scene;

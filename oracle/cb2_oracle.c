@@ -1526,12 +1526,45 @@ static int64_t rt_integrate(const cb2_rt_desc* d, const double o[3], const doubl
     xform_point(d->world_to_local, ew, end);
     double dir[3] = {end[0] - start[0], end[1] - start[1], end[2] - start[2]};
     double length = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    int n0 = d->grid_shape[0], n1 = d->grid_shape[1], n2 = d->grid_shape[2];
+    if (d->integrator == 1) {
+        /* a foreign NumericalIntegrator [raysect, SURVEY Appendix B.2] over emission_function (emitters.pyx:452-473, 557-571):
+           unit emissivity in the cell of every sample, trapezium rule */
+        if (length == 0) return 0;
+        for (int k = 0; k < 3; k++) dir[k] /= length;
+        int intervals = (int)ceil(length / d->step);
+        if (intervals < d->min_samples - 1) intervals = d->min_samples - 1;
+        if (intervals < 1) intervals = 1;
+        double h = length / intervals;
+        for (int k = 0; k <= intervals; k++) {
+            double t = k * h;
+            double x = start[0] + t * dir[0], y = start[1] + t * dir[1], z = start[2] + t * dir[2];
+            int i0, i1, i2;
+            if (d->kind == CB2_RT_CYLINDRICAL) {
+                i2 = (int)(z / d->grid_steps[2]);
+                double r = sqrt(x * x + y * y);
+                i0 = (int)((r - d->rmin) / d->grid_steps[0]);
+                if (n1 == 1) i1 = 0;
+                else {
+                    double phi = (180. / M_PI) * atan2(y, x);
+                    phi = fmod(phi + 360., d->period);
+                    i1 = (int)(phi / d->grid_steps[1]);
+                }
+            } else {
+                i0 = (int)(x / d->grid_steps[0]); i1 = (int)(y / d->grid_steps[1]); i2 = (int)(z / d->grid_steps[2]);
+            }
+            if (i0 < 0 || i0 >= n0 || i1 < 0 || i1 >= n1 || i2 < 0 || i2 >= n2) continue;   /* (the reference does not check bounds here) */
+            int src = d->voxel_map[((int64_t)i0 * n1 + i1) * n2 + i2];
+            if (src < 0) continue;
+            samples[src] += (k == 0 || k == intervals) ? 0.5 * h : h;
+        }
+        return (int64_t)intervals + 1;
+    }
     if (length < 0.1 * d->step) return 0;
     for (int k = 0; k < 3; k++) dir[k] /= length;
     int n = (int)(length / d->step);
     if (n < d->min_samples) n = d->min_samples;
     double dt = length / n;
-    int n0 = d->grid_shape[0], n1 = d->grid_shape[1], n2 = d->grid_shape[2];
     int i0c = -1, i1c = -1, i2c = -1, isource = -1, isource_current = -1;
     double res = 0;
     for (int it = 0; it < n; it++) {

@@ -203,3 +203,20 @@ def test_csr_is_reproducible_and_in_order_of_first_visit(monkeypatch):
     ro, cols, lens = results[0]
     assert ro[-1] > 48 * 48 * 50
 
+
+@pytest.mark.parametrize("seed", (1, 4, 9, 14, 20))
+def test_foreign_numerical_integrator_matches_the_oracle(seed):
+    # RayTransferEmitter.emission_function under a NumericalIntegrator (emitters.pyx:452-473, 557-571): trapezium nodes and end weights
+    # on the device (dense rows and CSR) against the oracle, on the random grids / voxel maps / masks of the suite
+    rt, rays = _random_rt(np.random.default_rng(500 + seed))
+    if rays.n_segments == 0:
+        pytest.skip("no ray hits the grid")
+    rt.integrator = cb.NumericalIntegrator(step=rt.step * 1.7, min_samples=5)
+    dense, ref = check(rt, rays)
+    assert ref.sum() > 0
+    # and it is a different quadrature: the midpoint sampler of the same grid gives other numbers
+    rt.integrator = None
+    scene = RayTransferScene(rt)
+    mid, _ = scene.render_dense(rays)
+    scene.close()
+    assert not np.array_equal(mid, dense)

@@ -159,3 +159,30 @@ def test_pipelines_initialise_and_kind():
     p0.update(0, (np.full(nbins, 5.0), 0), 2)
     p0.finalise()
     assert np.all(p0.matrix == 2.0)
+
+
+def test_foreign_numerical_integrator_over_the_emitter():
+    # emitters.pyx:452-473, 557-571: RayTransferEmitter.emission_function puts unit emissivity into the sample's cell, so a
+    # NumericalIntegrator [raysect] over it gives the trapezium-rule path lengths: along the x axis of a 3 x 3 x 3 box of unit cells,
+    # step 0.25 -> 12 intervals, nodes at 0, 0.25 .. 3.0; the node on a cell face belongs to the upper cell (truncation), the end
+    # nodes weigh h / 2
+    rtb = RayTransferBox(xmax=3.0, ymax=3.0, zmax=3.0, nx=3, ny=3, nz=3)
+    rtb.integrator = cb.NumericalIntegrator(step=0.25, min_samples=2)
+    rays = cb.ray_segments(rtb.primitive, np.array([[-1.0, 0.5, 0.5]]), np.array([[1.0, 0.0, 0.0]]))
+    desc, keep = rtb.descriptor()
+    assert desc.integrator == 1 and desc.step == 0.25
+    row, st = oracle.rt_render_dense(desc, rays)
+    assert st["rt_steps"] == 13
+    h = (rays.seg_t1[0] - rays.seg_t0[0]) / 12
+    # marching from the far end (x = 3 - eps) to the near end: cell 2 holds nodes 0..3 (+ half of node 0), cell 1 nodes 4..7 ...
+    got = row[0][[rtb.voxel_map[i, 0, 0] for i in range(3)]]
+    assert abs(got.sum() - 12 * h) < 1e-12
+    np.testing.assert_allclose(sorted(got), sorted([3.5 * h, 4 * h, 4.5 * h]), rtol=1e-9)
+    # the emitter's own integrator on the same ray: midpoints of 29 steps (the eps-shrunk chord is a hair under 3 m): 9 or 10 per cell
+    rtb.integrator = None
+    desc, keep = rtb.descriptor()
+    row2, _ = oracle.rt_render_dense(desc, rays)
+    np.testing.assert_allclose(row2[0][[rtb.voxel_map[i, 0, 0] for i in range(3)]], 1.0, atol=0.11)
+    with pytest.raises(TypeError):
+        rtb.integrator = "trapezium"
+        rtb.descriptor()
