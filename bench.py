@@ -289,7 +289,7 @@ def main():
     scene = EmissionScene(flat, device=local_rank)
     pix = rank_pixels(args.pixels, rank, world)
     n_pass = args.warmup + args.steps
-    host_rays = [make_rays(plasma, args.pixels, pix, k) for k in range(min(n_pass, 16))]
+    host_rays = [make_rays(plasma, args.pixels, pix, k).pin() for k in range(min(n_pass, 16))]     # inputs of the e2e leg: pinned host memory
     dev_rays = [DeviceRays(r, device=dev) for r in host_rays]
     frame = torch.zeros((pix.size, args.bins), dtype=torch.float32, device=dev)
     stats = torch.zeros(6, dtype=torch.int64, device=dev)

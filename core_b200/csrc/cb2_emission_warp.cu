@@ -1783,6 +1783,9 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     for (int64_t r0 = 0; r0 < rays.n_rays;) {
         DevRays sub = rays;
         sub.n_rays = std::min(batch, rays.n_rays - r0);
+        // host-buffer calls: nothing hides the copy of the last batch's rows, so the call ends on a geometric run of small batches
+        // (... 1/2, 1/4, ... down to 4096 rays: 33 MB of float32 rows at 2048 bins instead of a whole batch)
+        if (sc->d2h_host && sub.n_rays == rays.n_rays - r0 && sub.n_rays >= 8192) sub.n_rays = (sub.n_rays / 2 + 127) / 128 * 128;
         sub.origin = rays.origin + 3 * r0;
         sub.direction = rays.direction + 3 * r0;
         sub.seg_offset = rays.seg_offset + r0;                  // entries are absolute segment indices

@@ -177,8 +177,9 @@ def test_group_observe_on_the_device_matches_the_host_ray_path():
         cb.FibreOpticGroup().observe(scene, plasma.geometry)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("order", ["tiles", "random", "ragged"])
-def test_render_rows_puts_every_ray_on_its_row_of_the_frame(order):
+def test_render_rows_puts_every_ray_on_its_row_of_the_frame(order, pinned):
     # cb2_emission_render_rows: a rank's tile-ordered rays land on their pixels of the image-ordered host frame (strided D2H per tile);
     # any other row list must work too (single rows, runs of different lengths)
     from core_b200.sharding import tile_pixels
@@ -203,7 +204,12 @@ def test_render_rows_puts_every_ray_on_its_row_of_the_frame(order):
     os.environ["CB2_BATCH_RAYS"] = str(monkey_batch)
     try:
         plain, _ = scene.render(rays, dtype=np.float32)
-        frame = np.full((nx * ny, 96), -1.0, dtype=np.float32)
+        if pinned:                                       # a page-locked frame is written by the scatter kernel through its device mapping,
+            import torch                                 # a pageable one by strided copies
+            keep = torch.full((nx * ny, 96), -1.0, dtype=torch.float32).pin_memory()
+            frame = keep.numpy()
+        else:
+            frame = np.full((nx * ny, 96), -1.0, dtype=np.float32)
         out, st = scene.render(rays, out=frame, rows=pix)
     finally:
         del os.environ["CB2_BATCH_RAYS"]
