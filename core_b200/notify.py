@@ -5,7 +5,7 @@ from types import BuiltinMethodType, MethodType
 from weakref import ref
 
 
-class Notifier:
+class _Notifier:
 
     def __init__(self):
         self._callbacks_refs = []
@@ -56,3 +56,11 @@ class Notifier:
         for reference in dead:
             if reference in self._callbacks_refs:
                 self._callbacks_refs.remove(reference)
+
+
+# Where Cherab itself is importable its own class is the one in use (host plumbing to reuse as it is); the class
+# above is its stand-in for environments without Cherab / Raysect, like the build image.
+try:
+    from cherab.core.utility import Notifier            # noqa: F401
+except Exception:                                       # ImportError, or a Cherab that fails to load without Raysect
+    Notifier = _Notifier

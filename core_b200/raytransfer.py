@@ -309,3 +309,15 @@ class RayTransferPipeline2D(RayTransferPipelineBase):
 
     def finalise(self):
         pass
+
+
+# The pipelines and pixel processors above are protocol classes (initialise / pixel_processor / update / finalise, pack_results):
+# where Cherab and Raysect are importable the reference's own classes replace them, so frames produced here feed the very objects a
+# Cherab user holds (cherab/tools/raytransfer/pipelines.py:28-240, pixelprocessors.pyx).
+try:
+    from cherab.tools.raytransfer.pipelines import (RayTransferPipeline0D, RayTransferPipeline1D,     # noqa: F401,F811
+                                                    RayTransferPipeline2D)
+    from cherab.tools.raytransfer.pixelprocessors import (PowerRayTransferPixelProcessor,             # noqa: F401,F811
+                                                          RadianceRayTransferPixelProcessor)
+except Exception:
+    pass
