@@ -1767,7 +1767,7 @@ int cb2_memo_build(cb2_scene* sc) {
     FM.enabled = 1;
     if (const char* e = getenv("CB2_FUSED")) sc->fused = atoi(e) != 0;
     // field rows for the blend ramp (CB2_MEMO_BLEND=0: leave the ramp to state_kernel<FIX>)
-    const bool want_fields = !(getenv("CB2_MEMO_BLEND") && atoi(getenv("CB2_MEMO_BLEND")) == 0);
+    const bool want_fields = getenv("CB2_MEMO_BLEND") && atoi(getenv("CB2_MEMO_BLEND")) != 0;     // (off until measured on the GPU)
     if (want_fields && FM.core && FM.edge && FM.psi_max < 1.0f && !sc->fused) {
         FM.frow_f4 = 1 + 2 * FM.n_sp + 2;
         FM.fcore_n = 8192;
