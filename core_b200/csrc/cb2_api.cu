@@ -1553,8 +1553,6 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
     if (sc->gbase) cudaFree(sc->gbase);
     if (sc->gmask) cudaFree(sc->gmask);
     if (sc->gblend) cudaFree(sc->gblend);
-    if (sc->memo.fcore) cudaFree((void*)sc->memo.fcore);
-    if (sc->memo.fedge) cudaFree((void*)sc->memo.fedge);
     if (sc->memo.core) cudaFree((void*)sc->memo.core);
     if (sc->memo.edge) cudaFree((void*)sc->memo.edge);
     if (sc->rec) cudaFree(sc->rec);

@@ -1025,7 +1025,10 @@ state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_
 // K1a, table-driven (DevMemo): the state of a core sample (blend weight 1) is a row interpolated on the psi_n grid, that
 // of an edge sample (weight 0) the row of its triangle; what stays per sample is the geometry — position, (R, Z), psi_n,
 // triangle, direction of the poloidal field, v.d — the record rows and the moment scatter.  Blend-zone samples are only
-// flagged (gblend) and evaluated by state_kernel in its fix-up mode.
+// flagged (gblend) and evaluated by state_kernel in its fix-up mode.  (Tried: field rows — ne, te, n_i, T_s, velocities, N_z per
+// triangle and on a psi_n grid over the ramp — blended per sample inside this kernel, rates on the blended state.  Correct, 0.004 of
+// the tolerance from the fix-up path, but the divergent block costs more than the pass it replaces: state 16.7 -> 18.8 ms per
+// 65 536 rays inlined, 19.9 ms as a call.  Dropped.)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 lerp4(const float4 a, const float4 b, float t) {
     return make_float4(fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y), fmaf(t, b.z - a.z, a.z), fmaf(t, b.w - a.w, a.w));
@@ -1112,52 +1115,6 @@ __global__ void memo_rows_kernel(const __grid_constant__ DevScene S, const __gri
     atomicMax(err_key, ((unsigned long long)__float_as_uint(worst) << 32) | ((unsigned long long)(kw & 255) << 24) | (unsigned)(i & 0xffffff));
 }
 
-// field rows of the blend ramp: which = 0 triangle `i`, 1 psi_n = fpsi0 + i / fscale (see DevMemo)
-__global__ void memo_field_rows_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevMemo FM, int which, int n,
-                                       float4* __restrict__ tab) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    AxCtx c;
-    c.R = c.Z = 0.f; c.cphi = 1.f; c.sphi = 0.f; c.br = c.bt = c.bz = 0.f; c.b_outside = false;
-    if (which == 0) {
-        c.m = 0.f; c.tri = i; c.tri_c = i; c.we = 1.f; c.wc = 0.f; c.ci = 0; c.ct = 0.f; c.psi = 2.f; c.in_lcfs = false;
-    } else {
-        const float psi = FM.fpsi0 + (float)i / FM.fscale;
-        c.m = 1.f; c.tri = -1; c.tri_c = 0; c.we = 0.f; c.wc = 1.f; c.psi = psi; c.in_lcfs = true;
-        locate1d(S.ax.core, psi, c.ci, c.ct);
-    }
-    float row[4 * (1 + 2 * CB2_MEMO_MAX_SP + 2)];
-    for (int k = 0; k < 4 * FM.frow_f4; k++) row[k] = 0.f;
-    row[0] = eval_blend(S.ne, c);
-    row[1] = eval_blend(S.te, c);
-    for (int s = 0; s < FM.n_sp; s++) {
-        const DevSpecies& sp = S.species[FM.sp_species[s]];
-        float* a = row + 4 * (1 + 2 * s);
-        a[0] = eval_blend(sp.density, c);
-        a[1] = eval_blend(sp.temperature, c);
-        const DevVector& f = sp.velocity;
-        if (FM.sp_const[s]) continue;
-        float* v = a + 4;                               // (toroidal; R | poloidal; Z | normal) as the state rows hold them
-        if (which == 0) { v[0] = f.c[1]; v[1] = f.c[0]; v[2] = f.c[2]; }
-        else {
-            v[0] = f.vtor ? horner4(__ldg(f.vtor + c.ci), c.ct) : 0.f;
-            v[1] = f.vpol ? horner4(__ldg(f.vpol + c.ci), c.ct) : 0.f;
-            v[2] = f.vnorm ? horner4(__ldg(f.vnorm + c.ci), c.ct) : 0.f;
-        }
-    }
-    if (FM.has_brems) {
-        const DevBrems& B = S.brems;
-        float* nz = row + 4 * (1 + 2 * FM.n_sp);
-        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
-            float a = 0.f;
-            for (int q = B.zstart[z]; q < B.zstart[z + 1]; q++) a += fmaxf(eval_blend(S.species[B.zlist[q]].density, c), 0.f);
-            nz[z] = a;
-        }
-    }
-    float* t = reinterpret_cast<float*>(tab) + (size_t)i * 4 * FM.frow_f4;
-    for (int k = 0; k < 4 * FM.frow_f4; k++) t[k] = row[k];
-}
-
 template <int NW, int MOM, int MINB, int NSP>
 __global__ void __launch_bounds__(NW * 32, MINB)
 state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ DevMemo FM, DevRays rays, const int64_t* __restrict__ gbase,
@@ -1218,8 +1175,6 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
             int cls = 0;                                            // 0 vacuum, 1 table row, 2 blend zone
             const float4 *pa = row0, *pb = row0;
             float t = 0.f, ebr = 0.f, ebz = 0.f;
-            float bm = 0.f, bpsi = 0.f;                             // blend ramp: mask value, psi_n, triangle
-            int btri = -1;
             if (active) {
                 float m = 0.f, psi = 0.f;
                 Cell2 cell;
@@ -1251,15 +1206,6 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
                     }
                 } else if (m > 0.f) {
                     cls = 2;
-                    bm = m; bpsi = psi;
-                    if (FM.f_enabled) {
-                        btri = mesh_locate(A, r64, pzd);
-                        if (S.need_pol) {
-                            const float br = -eval2d(A.dpsi_dz, cell), bz = eval2d(A.dpsi_dr, cell);
-                            const float n2 = br * br + bz * bz;
-                            if (n2 > 0.f) { const float inv = rsqrtf(n2); ebr = br * inv; ebz = bz * inv; }
-                        }
-                    }
                 } else {
                     const int tri = mesh_locate(A, r64, pzd);
                     if (tri >= 0) { cls = 1; pa = pb = FM.edge + (size_t)tri * row_f4; ebr = 1.f; }
@@ -1268,105 +1214,8 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
             const unsigned live_mask = __ballot_sync(FULL, cls != 0 && w > 0.f);
             const unsigned blend_mask = __ballot_sync(FULL, cls == 2 && w > 0.f);
             const int64_t G = G0 + g;
-            if (lane == 0) { gmask[G] = live_mask; gblend[G] = FM.f_enabled ? 0u : blend_mask; }
+            if (lane == 0) { gmask[G] = live_mask; gblend[G] = blend_mask; }
             if (!live_mask) continue;
-            // blend ramp (Blend2D with 0 < mask < 1, plasma.py:622-636): the FIELDS are blended — field rows of the sample's triangle and
-            // of its psi_n — and the rates evaluated on the blended state, as the function tree does; the lane writes its own record
-            // entries and joins the others at the moment scatter.  (Without field tables the lanes are flagged for state_kernel<FIX>.)
-            float bf = 0.f, bU[CB2_MAX_BREMS_Z];
-#pragma unroll
-            for (int z = 0; z < CB2_MAX_BREMS_Z; z++) bU[z] = 0.f;
-            const bool blend_here = FM.f_enabled && cls == 2 && w > 0.f;
-            if (blend_here) {
-                const int frow = FM.frow_f4;
-                const float fi = fminf(fmaxf((bpsi - FM.fpsi0) * FM.fscale, 0.f), (float)FM.fcore_n);
-                const int i0 = min((int)fi, FM.fcore_n - 1);
-                const float tt = fi - (float)i0;
-                const float4* ca = FM.fcore + (size_t)i0 * frow;
-                const float4* cb = ca + frow;
-                const float4* ea = btri >= 0 ? FM.fedge + (size_t)btri * frow : nullptr;
-                const float we = btri >= 0 ? 1.0f - bm : 0.f, wc = bm;
-                auto field = [&](int kq) {
-                    const float4 cq = lerp4(__ldg(ca + kq), __ldg(cb + kq), tt);
-                    const float4 eq = ea ? __ldg(ea + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    return make_float4(fmaf(wc, cq.x, we * eq.x), fmaf(wc, cq.y, we * eq.y), fmaf(wc, cq.z, we * eq.z), fmaf(wc, cq.w, we * eq.w));
-                };
-                const float4 q0 = field(0);
-                const float ne = q0.x, te = q0.y;
-                const bool live = ne > 0.f && te > 0.f;
-                float lne = 0.f, lte = 0.f;
-                if (live) { lne = log10f(ne) + 19.0f; lte = log10f(te); }
-                const float aa = cphi * dx + sphi * dy, bb = cphi * dy - sphi * dx;
-                float nis[NSP], sqs[NSP], vds[NSP];
-#pragma unroll
-                for (int s = 0; s < NSP; s++) {
-                    nis[s] = sqs[s] = vds[s] = 0.f;
-                    if (s < FM.n_sp) {
-                        const float4 qa = field(1 + 2 * s);
-                        nis[s] = qa.x;
-                        sqs[s] = qa.y > 0.f ? sqrtf(qa.y) : 0.f;
-                        if (FM.sp_const[s]) vds[s] = vdc[s];
-                        else {
-                            // the edge vector is (R, phi, Z); the core vector is flux-aligned (efit.pyx:521-546): blend in (R, phi, Z)
-                            const float4 cq = lerp4(__ldg(ca + 2 + 2 * s), __ldg(cb + 2 + 2 * s), tt);
-                            const float4 eq = ea ? __ldg(ea + 2 + 2 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float we_v = 1.0f - bm;                              // (the edge vector is a constant: no mesh lookup)
-                            const float cr = ebr * cq.y - ebz * cq.z, cz = ebz * cq.y + ebr * cq.z;
-                            const float vr = fmaf(bm, cr, we_v * eq.y), vp = fmaf(bm, cq.x, we_v * eq.x), vz = fmaf(bm, cz, we_v * eq.z);
-                            vds[s] = fmaf(vr, aa, fmaf(vp, bb, vz * dz));
-                        }
-                    }
-                }
-                float* grec_b = rec + (size_t)G * n_comp * REC_FLOATS_PER_COMP + lane;
-                int cur_grid = -2;
-                Cell2 pcell;
-                for (int l = 0; l < FM.n_lines; l++) {
-                    const MemoLine& L = FM.lines[l];
-                    const DevModel& M = S.models[L.model];
-                    float ni = nis[0], sq = sqs[0], vd = vds[0];
-#pragma unroll
-                    for (int s = 1; s < NSP; s++)
-                        if (L.slot == s) { ni = nis[s]; sq = sqs[s]; vd = vds[s]; }
-                    float amp = 0.f;
-                    if (live && ni > 0.f) {
-                        float lp;
-                        if (M.pec_const) lp = M.pec_value;
-                        else {
-                            if (M.pec_grid != cur_grid) { pcell = locate2d(M.pec, lne, lte); cur_grid = M.pec_grid; }
-                            if (!pcell.inside && !M.pec_extrapolate) ood++;
-                            lp = eval2d(M.pec, pcell);
-                        }
-                        amp = RECIP_4_PI * exp10f(lp) * ne * ni * w * M.inv_delta;              // impact_excitation.pyx:99
-                        if (!(amp > 0.f) || !(sq > 0.f)) amp = 0.f;                            // gaussian.pyx:127-129
-                    }
-                    const float width = L.sigma_coef * sq;
-                    float* r = grec_b + L.rec_off;
-                    if (L.shape == CB2_SHAPE_GAUSSIAN) {
-                        r[64] = amp; r[0] = fmaf(L.shift_coef, vd, L.c0_frac); r[32] = width;
-                    } else {
-                        const float dop = vd * L.inv_c;
-                        for (int kc = 0; kc < L.ncomp; kc++, r += REC_FLOATS_PER_COMP) {
-                            r[64] = amp * __ldg(L.mult_ratio + kc);
-                            r[0] = S.comps[L.comp0 + kc].c0_frac + __ldg(L.mult_lambda + kc) * dop * L.inv_delta;
-                            r[32] = width;
-                        }
-                    }
-                }
-                if (MOM && live) {
-                    // brems_state on the blended ne, te and the blended N_z
-                    const DevBrems& B = S.brems;
-                    float tc = te;
-                    if (tc < B.te_lo || tc > B.te_hi) { ood++; tc = fminf(fmaxf(tc, B.te_lo), B.te_hi); }
-                    const float tau = 1.0f / tc;
-                    const float sv = fmaf(tau, B.inv_tau_c, -logf(tc));
-                    bf = fminf(fmaxf((sv - B.s0) * B.inv_ds, 1.0f), (float)(B.n_nodes - 3) + 0.9999f);
-                    const float W = B.pref * ne * rsqrtf(te) * __expf(-B.x_ref * tau);
-                    const float4 n0 = field(1 + 2 * FM.n_sp), n1 = field(2 + 2 * FM.n_sp);
-                    bU[0] = W * n0.x; bU[1] = W * n0.y; bU[2] = W * n0.z; bU[3] = W * n0.w;
-                    bU[4] = W * n1.x; bU[5] = W * n1.y; bU[6] = W * n1.z; bU[7] = W * n1.w;
-                }
-            }
-            const float wb = blend_here ? w : 0.f;                  // the blend lane's trapezium weight, for the moment scatter
             if (cls != 1) w = 0.f;
             // species block: sqrt(Ts) and v.d
             const float aa = cphi * dx + sphi * dy, bb = cphi * dy - sphi * dx;
@@ -1398,7 +1247,6 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
                     if (!(amp > 0.f) || !(sqs > 0.f)) amp = 0.f;
                     const bool any_on = __any_sync(FULL, amp > 0.f);
                     float* r = grec + L.rec_off;
-                    if (blend_here) continue;                       // (this lane's entries are written: blend ramp)
                     if (L.shape == CB2_SHAPE_GAUSSIAN) {
                         r[64] = amp;
                         if (any_on) { r[0] = fmaf(L.shift_coef, vds, L.c0_frac); r[32] = width; }
@@ -1423,15 +1271,9 @@ state_fast_kernel(const __grid_constant__ DevScene S, const __grid_constant__ De
                         const float4 q2 = lerp4(__ldg(pa + FM.off_brems + 2), __ldg(pb + FM.off_brems + 2), t);
                         U[6] = q2.x; U[7] = q2.y;
                     }
-                    bool lb = w > 0.f && q0.x >= 1.0f;
-                    float fw = w, ff = q0.x;
-                    if (blend_here) {
-                        lb = bf >= 1.0f; fw = wb; ff = bf;
-#pragma unroll
-                        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) U[z] = bU[z];
-                    }
+                    const bool lb = w > 0.f && q0.x >= 1.0f;
                     if (lb) n_brems += (unsigned)S.bins;
-                    brems_scatter(S.brems, lb, fw, ff, U, mom, lane);
+                    brems_scatter(S.brems, lb, w, q0.x, U, mom, lane);
                 }
             }
         }
@@ -1766,24 +1608,6 @@ int cb2_memo_build(cb2_scene* sc) {
     if (!FM.edge && !FM.core) { memset(&FM, 0, sizeof FM); return CB2_OK; }
     FM.enabled = 1;
     if (const char* e = getenv("CB2_FUSED")) sc->fused = atoi(e) != 0;
-    // field rows for the blend ramp (CB2_MEMO_BLEND=0: leave the ramp to state_kernel<FIX>)
-    const bool want_fields = getenv("CB2_MEMO_BLEND") && atoi(getenv("CB2_MEMO_BLEND")) != 0;     // (off until measured on the GPU)
-    if (want_fields && FM.core && FM.edge && FM.psi_max < 1.0f && !sc->fused) {
-        FM.frow_f4 = 1 + 2 * FM.n_sp + 2;
-        FM.fcore_n = 8192;
-        FM.fpsi0 = FM.psi_max;
-        FM.fscale = (float)FM.fcore_n / (1.0f - FM.psi_max);
-        const size_t frow_bytes = (size_t)FM.frow_f4 * sizeof(float4);
-        float4 *fe = nullptr, *fc = nullptr;
-        if (cudaMalloc((void**)&fe, frow_bytes * S.ax.n_tri) == cudaSuccess && cudaMalloc((void**)&fc, frow_bytes * (size_t)(FM.fcore_n + 1)) == cudaSuccess) {
-            memo_field_rows_kernel<<<(S.ax.n_tri + 127) / 128, 128>>>(S, FM, 0, S.ax.n_tri, fe);
-            memo_field_rows_kernel<<<(FM.fcore_n + 1 + 127) / 128, 128>>>(S, FM, 1, FM.fcore_n + 1, fc);
-            if (cudaDeviceSynchronize() == cudaSuccess) { FM.fedge = fe; FM.fcore = fc; FM.f_enabled = 1; fe = fc = nullptr; }
-        }
-        cudaGetLastError();
-        if (fe) cudaFree(fe);
-        if (fc) cudaFree(fc);
-    }
     return CB2_OK;
 }
 
@@ -2053,9 +1877,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
 #undef CB2_FAST
                 if ((rc = cb2_cuda_check(cudaGetLastError(), "state_fast_kernel launch")) != CB2_OK) return rc;
                 if (prof) CB2_CUDA(cudaEventRecord(sc->prof_ev[5], st));
-                if (!sc->memo.f_enabled || fused) {             // (with field tables the blend ramp is done inside state_fast_kernel)
-                    if (moments) CB2_STATE(1, 1, 0, 1, sc->gblend); else CB2_STATE(0, 1, 0, 1, sc->gblend);
-                }
+                if (moments) CB2_STATE(1, 1, 0, 1, sc->gblend); else CB2_STATE(0, 1, 0, 1, sc->gblend);
             } else {
                 const unsigned* none = nullptr;
                 const int sel = (moments ? 4 : 0) | (sc->ax_only ? 2 : 0) | (sc->feat ? 1 : 0);

@@ -304,12 +304,6 @@ struct alignas(16) DevMemo {
     float psi_max;
     const float4* core;
     const float4* edge;                      // [n_tri] rows
-    // blend ramp (0 < mask < 1): FIELD rows — ne, te; per species slot n_i, T_s and the velocity components; N_z per charge — per
-    // triangle and on a psi_n grid over the ramp, blended per sample before the rates are evaluated (frow_f4 = 1 + 2 n_sp + 2)
-    int f_enabled, frow_f4, fcore_n;
-    float fpsi0, fscale;                     // row index = (psi_n - fpsi0) * fscale
-    const float4* fcore;
-    const float4* fedge;
     MemoLine lines[CB2_MEMO_MAX_LINES];
 };
 
