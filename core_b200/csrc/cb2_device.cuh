@@ -509,21 +509,43 @@ __device__ __forceinline__ void brems_state(const DevScene& S, const SampleIn& i
 template <typename MomT>
 __device__ __forceinline__ void brems_scatter(const DevBrems& B, bool live, float w, float f, const float (&U)[CB2_MAX_BREMS_Z],
                                               MomT* __restrict__ mom, int lane) {
+    // Element e = 4 z + k of a lane is w U_z L_k.  The transpose-reduction runs in the lane-permuted order of bin_kernel's windows —
+    // register r of lane l holds element r ^ l, so `part[i] += shfl_xor(part[i + o], o)` needs no selects and leaves element l on
+    // lane l — and since r ^ l = 4 ((r >> 2) ^ (l >> 2)) + ((r & 3) ^ (l & 3)), the permuted elements are products of the lane's own
+    // U and L arrays permuted once by XOR swaps (32 selects per group instead of 94 per distinct node).
     int node = -1;
-    float val[32];
+    float L[4] = {0.f, 0.f, 0.f, 0.f}, V[CB2_MAX_BREMS_Z];
 #pragma unroll
-    for (int i = 0; i < 32; i++) val[i] = 0.f;
+    for (int z = 0; z < CB2_MAX_BREMS_Z; z++) V[z] = 0.f;
     if (live) {
         node = (int)f;
         const float t = f - (float)node;
         // cubic Lagrange weights on the nodes -1, 0, 1, 2
         const float tm1 = t - 1.0f, tm2 = t - 2.0f, tp1 = t + 1.0f;
-        const float l0 = -t * tm1 * tm2 * (1.0f / 6.0f), l1 = tp1 * tm1 * tm2 * 0.5f, l2 = -tp1 * t * tm2 * 0.5f, l3 = tp1 * t * tm1 * (1.0f / 6.0f);
+        L[0] = -t * tm1 * tm2 * (1.0f / 6.0f); L[1] = tp1 * tm1 * tm2 * 0.5f; L[2] = -tp1 * t * tm2 * 0.5f; L[3] = tp1 * t * tm1 * (1.0f / 6.0f);
 #pragma unroll
-        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) {
-            const float v = w * U[z];
-            val[4 * z] = v * l0; val[4 * z + 1] = v * l1; val[4 * z + 2] = v * l2; val[4 * z + 3] = v * l3;
-        }
+        for (int z = 0; z < CB2_MAX_BREMS_Z; z++) V[z] = w * U[z];
+    }
+    static_assert(CB2_MAX_BREMS_Z == 8, "the XOR permutation below is written for 8 charges x 4 nodes = 32 elements");
+#pragma unroll
+    for (int bit = 0; bit < 2; bit++) {                // L'[k] = L[k ^ (lane & 3)]
+        const bool sw = (lane >> bit) & 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (!(k & (1 << bit))) {
+                const float x = L[k], y = L[k | (1 << bit)];
+                L[k] = sw ? y : x; L[k | (1 << bit)] = sw ? x : y;
+            }
+    }
+#pragma unroll
+    for (int bit = 0; bit < 3; bit++) {                // V'[z] = V[z ^ (lane >> 2)]
+        const bool sw = (lane >> (bit + 2)) & 1;
+#pragma unroll
+        for (int z = 0; z < 8; z++)
+            if (!(z & (1 << bit))) {
+                const float x = V[z], y = V[z | (1 << bit)];
+                V[z] = sw ? y : x; V[z | (1 << bit)] = sw ? x : y;
+            }
     }
     unsigned todo = __ballot_sync(FULL, live);
     while (todo) {
@@ -531,19 +553,16 @@ __device__ __forceinline__ void brems_scatter(const DevBrems& B, bool live, floa
         const int nd = __shfl_sync(FULL, node, leader);
         const bool mine = node == nd;
         todo &= ~__ballot_sync(FULL, mine);
+        float Lm[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Lm[k] = mine ? L[k] : 0.f;
         float part[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) part[i] = mine ? val[i] : 0.f;
+        for (int r = 0; r < 32; r++) part[r] = V[r >> 2] * Lm[r & 3];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const bool upper = (lane & o) != 0;
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int i = 0; i < o; i++) {
-                const float send = upper ? part[i] : part[i + o];
-                const float keep = upper ? part[i + o] : part[i];
-                part[i] = keep + __shfl_xor_sync(FULL, send, o);
-            }
-        }
+            for (int i = 0; i < o; i++) part[i] += __shfl_xor_sync(FULL, part[i + o], o);
         const int z = lane >> 2, k = lane & 3;
         if (z < B.n_z && part[0] != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (MomT)part[0]);
     }
