@@ -552,21 +552,46 @@ __device__ __forceinline__ float reduce_window(float (&part)[WB], int lane) {
     return part[0];
 }
 
-// WB-bin tail window for series lanes in natural bin order
+// WB-bin tail window (WB = 8, 16) for series lanes, in the same lane-permuted order: register r of lane l holds bin r ^ (l % WB), the
+// butterfly over the register index needs no selects, the 32 / WB lane groups are folded at the end; lane l < WB holds window bin l.
 template <int WB, typename AccT>
 __device__ __forceinline__ void window_series_tail(const LineRec& R, int wbase, int c0_int, int bins, AccT* __restrict__ wacc, int lane) {
+    constexpr int BITS = WB == 16 ? 4 : 3;
     const bool mine = R.kind == 1 && R.hi > wbase && R.lo < wbase + WB;
     const SeriesPair P = series_pair(R, mine);
-    const float x0 = fmaf((float)wbase, R.kx, R.xoff);
-    const f32x2 k2 = pack2(2.0f * R.kx, 2.0f * R.kx);
-    f32x2 X = pack2(x0, x0 + R.kx);
-    float part[WB];
+    const int lw = lane & (WB - 1);
+    float db0;
+    f32x2 db[BITS];
 #pragma unroll
-    for (int w = 0; w < WB; w += 2) {
-        unpack2(series_eval2(P, X), part[w], part[w + 1]);
-        X = add2(X, k2);
+    for (int b = 0; b < BITS; b++) {
+        const float d = ((lw >> b) & 1) ? -(float)(1 << b) * R.kx : (float)(1 << b) * R.kx;
+        if (b == 0) db0 = d;
+        db[b] = pack2(d, d);
     }
-    const float v = reduce_window<WB>(part, lane);
+    const float xb = fmaf((float)(wbase + lw), R.kx, R.xoff);
+    f32x2 X[WB / 2], part[WB / 2];
+    X[0] = pack2(xb, xb + db0);
+#pragma unroll
+    for (int j = 1; j < WB / 2; j++) {
+        int top = BITS - 2;
+        while (!(j & (1 << top))) top--;
+        X[j] = add2(X[j & ~(1 << top)], db[top + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < WB / 2; j++) part[j] = series_eval2(P, X[j]);
+#pragma unroll
+    for (int o = WB / 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < o; j++) {
+            float a, b;
+            unpack2(part[j + o], a, b);
+            part[j] = add2(part[j], pack2(__shfl_xor_sync(FULL, a, 2 * o), __shfl_xor_sync(FULL, b, 2 * o)));
+        }
+    float v, p1;
+    unpack2(part[0], v, p1);
+    v += __shfl_xor_sync(FULL, p1, 1);
+#pragma unroll
+    for (int o = WB; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
     const int bin = c0_int + wbase + lane;
     __syncwarp();
     if (lane < WB && bin >= 0 && bin < bins && v != 0.f) wacc[bin] += (AccT)v;
