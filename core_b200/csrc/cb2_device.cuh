@@ -43,6 +43,16 @@ __device__ __forceinline__ float half_erfc(float a) {
     return q * s * ex2_approx(a * a * -L2E);
 }
 
+// Packed float32 pairs (sm_100a: add / mul / fma .f32x2 = SASS FADD2 / FMUL2 / FFMA2, one issue slot for two lanes' worth of
+// arithmetic).  bin_kernel is issue-bound, not pipe-bound (r1c ncu: issue-active 81 %, FMA pipe 47 %, XU 51 %): pairing two
+// bins per instruction takes the series evaluation from ~10 to ~6 issue slots per bin and leaves MUFU.EX2 as the bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 __device__ __forceinline__ float horner4(const float4 c, float t) { return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x); }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -556,15 +566,24 @@ __device__ __forceinline__ void brems_scatter(const DevBrems& B, bool live, floa
         float Lm[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) Lm[k] = mine ? L[k] : 0.f;
-        float part[32];
+        // registers (2 j, 2 j + 1) as one packed pair: 16 FMUL2 for the products, FADD2 in the butterfly
+        const f32x2 L01 = pack2(Lm[0], Lm[1]), L23 = pack2(Lm[2], Lm[3]);
+        f32x2 part[16];
 #pragma unroll
-        for (int r = 0; r < 32; r++) part[r] = V[r >> 2] * Lm[r & 3];
+        for (int j = 0; j < 16; j++) part[j] = mul2(pack2(V[j >> 1], V[j >> 1]), (j & 1) ? L23 : L01);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-            for (int i = 0; i < o; i++) part[i] += __shfl_xor_sync(FULL, part[i + o], o);
+            for (int j = 0; j < o; j++) {
+                float a, b;
+                unpack2(part[j + o], a, b);
+                part[j] = add2(part[j], pack2(__shfl_xor_sync(FULL, a, 2 * o), __shfl_xor_sync(FULL, b, 2 * o)));
+            }
+        float p0, p1;
+        unpack2(part[0], p0, p1);
+        p0 += __shfl_xor_sync(FULL, p1, 1);
         const int z = lane >> 2, k = lane & 3;
-        if (z < B.n_z && part[0] != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (MomT)part[0]);
+        if (z < B.n_z && p0 != 0.f) atomicAdd(&mom[z * B.n_nodes + nd - 1 + k], (MomT)p0);
     }
 }
 

@@ -460,16 +460,6 @@ struct LineRec {
     int kind;                // 0 nothing, 1 series, 2 erfc differences, 3 modified Lorentzian
 };
 
-// Packed float32 pairs (sm_100a: add / mul / fma .f32x2 = SASS FADD2 / FMUL2 / FFMA2, one issue slot for two lanes' worth of
-// arithmetic).  bin_kernel is issue-bound, not pipe-bound (r1c ncu: issue-active 81 %, FMA pipe 47 %, XU 51 %): pairing two
-// bins per instruction takes the series evaluation from ~10 to ~6 issue slots per bin and leaves MUFU.EX2 as the bound.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 // series coefficients of a lane's component, each duplicated into both halves of a pair
 struct SeriesPair {
     f32x2 c0, c1, c2, c3, c4;
