@@ -48,3 +48,24 @@ def test_group_transform_applies_to_every_observer():
     np.testing.assert_allclose(o, [[1, 0, 5], [0, 1, 5]])
     np.testing.assert_allclose(d, [[0, 0, 1], [0, 0, 1]])
     assert list(owner) == [0, 1] and list(w) == [1.0, 1.0]
+
+
+def test_device_descriptors_of_a_group():
+    # what cb2_observer0d_rays_device / _reduce_device receive: one cb2_observer0d per observer (group transform applied), the rays'
+    # offsets and the etendue (solid angle x collection area for a fibre, the sensitivity for a sight line)
+    g = cb.FibreOpticGroup(transform=cb.translate(0.0, 0.0, 1.0))
+    g.add_observer(cb.FibreOptic(transform=cb.translate(1.0, 2.0, 3.0), acceptance_angle=10.0, radius=0.002, pixel_samples=7))
+    g.add_observer(cb.FibreOptic(transform=cb.translate(-1.0, 0.0, 0.0), acceptance_angle=5.0, radius=0.001, pixel_samples=3))
+    arr, offs, etendue = g._descs()
+    assert list(offs) == [0, 7, 10]
+    assert [arr[i].samples for i in range(2)] == [7, 3] and arr[0].radius == 0.002 and arr[1].acceptance_angle == 5.0
+    assert (arr[0].to_world[3], arr[0].to_world[7], arr[0].to_world[11]) == (1.0, 2.0, 4.0)            # group translation on top
+    ob = g.observers[0]
+    np.testing.assert_allclose(etendue[0], 2 * np.pi * (1 - np.cos(np.deg2rad(10.0))) * np.pi * 0.002 ** 2, rtol=1e-14)
+    assert etendue[0] == ob.solid_angle * ob.collection_area
+    s = cb.SightLineGroup([cb.SightLine(sensitivity=2.5), cb.SightLine()])
+    arr, offs, etendue = s._descs()
+    assert list(offs) == [0, 1, 2] and list(etendue) == [2.5, 1.0] and arr[0].radius == 0.0 and arr[1].samples == 1
+    g.acceptance_angle = 95.0
+    with pytest.raises(ValueError):
+        g._descs()
