@@ -1562,6 +1562,7 @@ extern "C" int cb2_scene_destroy(cb2_scene* sc) {
         if (sc->prof_ev[i]) cudaEventDestroy(sc->prof_ev[i]);
     if (sc->copy_ev) cudaEventDestroy(sc->copy_ev);
     if (sc->copy_stream) cudaStreamDestroy(sc->copy_stream);
+    if (sc->copy_stream2) cudaStreamDestroy(sc->copy_stream2);
     free(sc);
     return CB2_OK;
 }
@@ -1650,9 +1651,11 @@ int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
 // Rows src_dev[i] (i < n, row_bytes each) to dst_base + dest_row[i] * row_bytes, asynchronously on `st`: consecutive destination
 // rows form a run; runs of equal length at a constant pitch form one cudaMemcpy2DAsync (a 16 x 16 tile of a pixel-ordered frame:
 // 16 runs of 16 rows, pitch = ny rows).
-int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st) {
+int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st, cudaStream_t st2) {
     int64_t i = 0;
+    int turn = 0;
     while (i < n) {
+        cudaStream_t cs = (st2 && (turn++ & 1)) ? st2 : st;
         int64_t len = 1;
         while (i + len < n && dest_row[i + len] == dest_row[i] + len) len++;
         // how many following runs have this length and a constant pitch?
@@ -1668,9 +1671,9 @@ int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void*
         }
         char* d = (char*)dst_base + (size_t)dest_row[i] * row_bytes;
         const char* s = (const char*)src_dev + (size_t)i * row_bytes;
-        if (h == 1) CB2_CUDA(cudaMemcpyAsync(d, s, (size_t)len * row_bytes, cudaMemcpyDeviceToHost, st));
+        if (h == 1) CB2_CUDA(cudaMemcpyAsync(d, s, (size_t)len * row_bytes, cudaMemcpyDeviceToHost, cs));
         else CB2_CUDA(cudaMemcpy2DAsync(d, (size_t)pitch * row_bytes, s, (size_t)len * row_bytes, (size_t)len * row_bytes, (size_t)h,
-                                        cudaMemcpyDeviceToHost, st));
+                                        cudaMemcpyDeviceToHost, cs));
         i += h * len;
     }
     return CB2_OK;
@@ -1768,14 +1771,16 @@ static int emission_render_host(cb2_scene* sc, const cb2_rays* rays, const int64
     if (sc->warp_kernel && overlap) {
         // the two-kernel path works in ray batches: each batch's rows go back to the host while the next batch computes
         if (!sc->copy_stream) CB2_CUDA(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+        if (!sc->copy_stream2 && !(getenv("CB2_D2H_ONE_STREAM") && atoi(getenv("CB2_D2H_ONE_STREAM")))) CB2_CUDA(cudaStreamCreateWithFlags(&sc->copy_stream2, cudaStreamNonBlocking));
         if (!sc->copy_ev) CB2_CUDA(cudaEventCreateWithFlags(&sc->copy_ev, cudaEventDisableTiming));
         sc->d2h_host = out;
         sc->d2h_rows = dest_row;
         rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st);
         sc->d2h_host = nullptr;
         sc->d2h_rows = nullptr;
-        if (rc != CB2_OK) { cudaStreamSynchronize(sc->copy_stream); return rc; }
+        if (rc != CB2_OK) { cudaStreamSynchronize(sc->copy_stream); if (sc->copy_stream2) cudaStreamSynchronize(sc->copy_stream2); return rc; }
         CB2_CUDA(cudaStreamSynchronize(sc->copy_stream));
+        if (sc->copy_stream2) CB2_CUDA(cudaStreamSynchronize(sc->copy_stream2));
     } else {
         if ((rc = cb2_launch_emission(sc, dr, sc->stage[5], out_f64, scale, accumulate, sc->stats_dev, st)) != CB2_OK) return rc;
         if (dest_row) {

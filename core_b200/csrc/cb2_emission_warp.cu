@@ -1796,7 +1796,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
     int64_t pend_r0 = 0, pend_n = 0;
     auto flush_pending = [&]() -> int {
         int rc2 = CB2_OK;
-        if (sc->d2h_rows) rc2 = cb2_d2h_rows(sc->d2h_host, sc->d2h_rows + pend_r0, pend_n, pend_src, (size_t)S.bins * esz, sc->copy_stream);
+        if (sc->d2h_rows) rc2 = cb2_d2h_rows(sc->d2h_host, sc->d2h_rows + pend_r0, pend_n, pend_src, (size_t)S.bins * esz, sc->copy_stream, sc->copy_stream2);
         else rc2 = cb2_cuda_check(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, sc->copy_stream), "frame rows device -> host");
         pend_bytes = 0;
         return rc2;
@@ -1956,6 +1956,7 @@ int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int 
             // overlap the device -> host copy of this batch's rows with the next batch's kernels
             CB2_CUDA(cudaEventRecord(sc->copy_ev, st));
             CB2_CUDA(cudaStreamWaitEvent(sc->copy_stream, sc->copy_ev, 0));
+            if (sc->copy_stream2) CB2_CUDA(cudaStreamWaitEvent(sc->copy_stream2, sc->copy_ev, 0));
             pend_dst = (char*)sc->d2h_host + (size_t)r0 * S.bins * esz;
             pend_src = o;
             pend_bytes = (size_t)sub.n_rays * S.bins * esz;

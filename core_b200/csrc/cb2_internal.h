@@ -377,6 +377,7 @@ struct cb2_scene {
     void* d2h_host;
     const int64_t* d2h_rows;   // optional destination row of every ray of the call (cb2_emission_render_rows)
     cudaStream_t copy_stream;
+    cudaStream_t copy_stream2;  // strided row copies alternate between two streams (two copy engines)
     cudaEvent_t copy_ev;
     // optional per-kernel timing (cb2_scene_profile)
     int prof_on;
@@ -418,7 +419,7 @@ size_t cb2_warp_smem_bytes(int nw, int acc_f64, int bins);
 int cb2_launch_rt_compact(int64_t n_rays, int64_t row_stride, const int64_t* row_offset, const int32_t* scratch_cols, const double* scratch_len,
                           int32_t* columns, double* lengths, cudaStream_t st);
 int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
-int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st);
+int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st, cudaStream_t st2 = nullptr);
 int cb2_launch_emission_warp(cb2_scene* sc, const DevRays& rays, void* out, int out_f64, double scale, int accumulate,
                              unsigned long long* stats, int count_samples, cudaStream_t stream);
 int64_t cb2_warp_batch_rays(const cb2_scene* sc);
