@@ -488,13 +488,13 @@ def main():
         step_flop = per_step(fixed * samples + F_MOMENT * live + F_GAUSS_BIN * gauss) + (2.0 * pix.size * plan["moment_row"] * (-(-args.bins // 128) * 128) if kernel_ms else per_step(10.0 * brems))
         frame_bytes = pix.size * args.bins * 4.0
         # DRAM bytes per launch of the dominant kernel from one `ncu --set full` capture at the default configuration
-        # (profiles/r2b_bin_kernel_c3_ncu_summary.txt: 3.88 GB read = the line records the state kernels hand over, 0.132 GB written =
+        # (profiles/r2q_bin_kernel_c3_ncu_summary.txt: 3.88 GB read = the line records the state kernels hand over, 0.132 GB written =
         # the batch's spectra); unknown for any other size
         traffic = None
         if dom == "bin_kernel" and args.pixels == 1024 and args.bins == 2048 and world == 1:
             # (captured on a 16 384-ray launch; a launch of batch_rays rays moves proportionally more)
             traffic = {"bytes_per_launch": 4.014e9 * plan["batch_rays"] / 16384.0, "algorithmic_bytes_per_launch": plan["batch_rays"] * args.bins * 4.0,
-                       "source": "profiles/r2b_bin_kernel_c3_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
+                       "source": "profiles/r2q_bin_kernel_c3_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
                        "note": "the line records handed from the state kernels to bin_kernel are re-read from HBM (0.5 TB/s, 8 % of the HBM peak): "
                                "not the bound of an issue-bound kernel; the opt-in fused kernel (CB2_FUSED=1) moves 0.30 GB per launch "
                                "(profiles/r2b_fused_kernel_ncu_summary.txt) at 10 % more time"}
