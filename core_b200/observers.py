@@ -132,6 +132,64 @@ def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None, wall=N
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# 0-D pipelines: what an observer's result is packed into [raysect SpectralRadiancePipeline0D / SpectralPowerPipeline0D /
+# RadiancePipeline0D / PowerPipeline0D], as the groups forward them (cherab/tools/observers/group/base.py:130-135, 383-436)
+# ------------------------------------------------------------------------------------------------------------------
+class _Stats:
+    """The part of raysect's StatsArray1D / StatsBin a consumer reads: mean, variance, samples (rays), errors()."""
+
+    def __init__(self, mean, samples):
+        self.mean = mean
+        self.variance = np.zeros_like(mean)          # deterministic ray sets: no Monte-Carlo variance estimate
+        self.samples = samples
+
+    def errors(self):
+        return np.zeros_like(self.mean)
+
+
+class _Pipeline0D:
+    _POWER = False
+
+    def __init__(self, name=None, accumulate=True, display_progress=False):
+        self.name = name or type(self).__name__
+        self.accumulate, self.display_progress = accumulate, display_progress
+        self.min_wavelength = self.max_wavelength = self.delta_wavelength = None
+        self.bins = 0
+        self.wavelengths = None
+
+    def _set_grid(self, min_wavelength, max_wavelength, bins):
+        self.min_wavelength, self.max_wavelength, self.bins = float(min_wavelength), float(max_wavelength), int(bins)
+        self.delta_wavelength = (self.max_wavelength - self.min_wavelength) / self.bins
+        self.wavelengths = self.min_wavelength + (np.arange(self.bins) + 0.5) * self.delta_wavelength
+
+
+class SpectralRadiancePipeline0D(_Pipeline0D):
+    """``samples.mean[bins]``: mean spectral radiance over the observer's rays, W / (m^2 sr nm)."""
+
+    def _fill(self, min_wavelength, max_wavelength, radiance, power, n_rays):
+        self._set_grid(min_wavelength, max_wavelength, radiance.size)
+        self.samples = _Stats((power if self._POWER else radiance).copy(), int(n_rays))
+
+
+class SpectralPowerPipeline0D(SpectralRadiancePipeline0D):
+    """``samples.mean[bins]``: spectral power collected by the observer (etendue-weighted), W / nm."""
+    _POWER = True
+
+
+class RadiancePipeline0D(_Pipeline0D):
+    """``value.mean``: the spectral radiance integrated over the spectral range, W / (m^2 sr)."""
+
+    def _fill(self, min_wavelength, max_wavelength, radiance, power, n_rays):
+        self._set_grid(min_wavelength, max_wavelength, radiance.size)
+        self.value = _Stats(np.float64((power if self._POWER else radiance).sum() * self.delta_wavelength), int(n_rays))
+
+
+class PowerPipeline0D(RadiancePipeline0D):
+    """``value.mean``: the collected power integrated over the spectral range, W."""
+    _POWER = True
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # 0-D observers and their groups (cherab/tools/observers/group/{base,fibreoptic,sightline}.py)
 # ------------------------------------------------------------------------------------------------------------------
 class SightLine:
@@ -142,6 +200,7 @@ class SightLine:
         self.transform = np.eye(4) if transform is None else np.asarray(transform, dtype=np.float64)
         self.name, self.sensitivity = name, float(sensitivity)
         self.spectrum = None
+        self.pipelines = []
 
     def rays(self):
         m = self.transform
@@ -159,6 +218,7 @@ class FibreOptic:
         self.name = name
         self.acceptance_angle, self.radius, self.pixel_samples = float(acceptance_angle), float(radius), int(pixel_samples)
         self.spectrum = None
+        self.pipelines = []
 
     @property
     def solid_angle(self):
@@ -233,6 +293,37 @@ class _Observer0DGroup:
         else:
             for o in self._observers:
                 setattr(o, attr, value)
+
+    @property
+    def pipelines(self):
+        """The pipelines of every observer (a list of lists, group/base.py:383-396)."""
+        return [ob.pipelines for ob in self._observers]
+
+    @pipelines.setter
+    def pipelines(self, pipelist):
+        if len(pipelist) == len(self._observers):
+            for ob, p in zip(self._observers, pipelist):
+                ob.pipelines = p
+        else:
+            raise ValueError('Length of pipelines list do not match number of observers in the group.')
+
+    def connect_pipelines(self, pipeline_classes, keywords_list=None, suppress_display_progress=True):
+        """A new set of the given pipeline classes on every observer (group/base.py:398-436)."""
+        if keywords_list is None:
+            keywords_list = [dict() for _ in pipeline_classes]
+        if len(pipeline_classes) != len(keywords_list):
+            raise ValueError('The number of given pipeline classes does not match the number of dicts in keyword list.')
+        for ob in self._observers:
+            pipelines = []
+            for cls, kwargs in zip(pipeline_classes, keywords_list):
+                p = cls(**kwargs)
+                if suppress_display_progress:
+                    try:
+                        p.display_progress = False
+                    except AttributeError:
+                        pass
+                pipelines.append(p)
+            ob.pipelines = pipelines
 
     def gather_rays(self):
         """(origins, directions, weights, owner index) of every observer's rays, in world space."""
@@ -311,8 +402,11 @@ class _Observer0DGroup:
                              "lookups of this render left their tables." % ood)
         self.spectra, self.power_spectra = host[0], host[1]
         self.last_rays = buf
-        for ob, s, pw in zip(self._observers, self.spectra, self.power_spectra):
+        grid = (scene.scene if hasattr(scene, "scene") else scene).flat.desc.grid
+        for i, (ob, s, pw) in enumerate(zip(self._observers, self.spectra, self.power_spectra)):
             ob.spectrum, ob.power_spectrum = s, pw
+            for p in ob.pipelines:                      # result packing into the observer's pipelines
+                p._fill(grid.min_wavelength, grid.max_wavelength, s, pw, offs[i + 1] - offs[i])
         return self.spectra
 
     def observe_host_rays(self, scene, primitive, to_world=None, wall=None):

@@ -160,9 +160,18 @@ def test_group_observe_on_the_device_matches_the_host_ray_path():
     flat = cb.flatten_scene(plasma, 655.5, 656.9, 200)
     scene = EmissionScene(flat)
     group = _fibre_fan()
+    group.connect_pipelines([cb.SpectralRadiancePipeline0D, cb.SpectralPowerPipeline0D, cb.RadiancePipeline0D, cb.PowerPipeline0D])
     spectra = group.observe(scene, plasma.geometry, plasma.geometry_to_world())
     ref_rad, ref_pow = group.observe_host_rays(scene, plasma.geometry, plasma.geometry_to_world())
     assert spectra.shape == (7, 200) and ref_rad.max() > 0
+    # the results packed into every observer's pipelines (group/base.py:383-436)
+    for i, ob in enumerate(group.observers):
+        rad, pw, tot, totp = ob.pipelines
+        assert (rad.min_wavelength, rad.max_wavelength, rad.bins) == (655.5, 656.9, 200) and rad.samples.samples == ob.pixel_samples
+        np.testing.assert_allclose(rad.wavelengths, 655.5 + (np.arange(200) + 0.5) * 0.007, rtol=1e-12)
+        assert np.array_equal(rad.samples.mean, spectra[i]) and np.array_equal(pw.samples.mean, group.power_spectra[i])
+        np.testing.assert_allclose(tot.value.mean, spectra[i].sum() * 0.007, rtol=1e-12)
+        np.testing.assert_allclose(totp.value.mean, group.power_spectra[i].sum() * 0.007, rtol=1e-12)
     np.testing.assert_allclose(spectra, ref_rad, rtol=1e-9, atol=1e-12 * ref_rad.max())
     np.testing.assert_allclose(group.power_spectra, ref_pow, rtol=1e-9, atol=1e-12 * ref_pow.max())
     # sight lines: one ray each, power = radiance x sensitivity

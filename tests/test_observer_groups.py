@@ -69,3 +69,19 @@ def test_device_descriptors_of_a_group():
     g.acceptance_angle = 95.0
     with pytest.raises(ValueError):
         g._descs()
+
+
+def test_group_pipelines_api():
+    # group/base.py:383-436: pipelines as a list of lists, connect_pipelines builds a fresh set per observer
+    g = cb.FibreOpticGroup([cb.FibreOptic(), cb.FibreOptic(), cb.FibreOptic()])
+    assert g.pipelines == [[], [], []]
+    g.connect_pipelines([cb.SpectralRadiancePipeline0D, cb.SpectralPowerPipeline0D], [{"name": "MySpectralPipeline"}, {}])
+    assert [[type(p).__name__ for p in ps] for ps in g.pipelines] == [["SpectralRadiancePipeline0D", "SpectralPowerPipeline0D"]] * 3
+    assert g.pipelines[0][0] is not g.pipelines[1][0] and g.pipelines[2][0].name == "MySpectralPipeline"
+    assert all(p.display_progress is False for ps in g.pipelines for p in ps)
+    with pytest.raises(ValueError):
+        g.connect_pipelines([cb.RadiancePipeline0D], [{}, {}])
+    with pytest.raises(ValueError):
+        g.pipelines = [[cb.RadiancePipeline0D()]]
+    g.pipelines = [[cb.RadiancePipeline0D()], [], [cb.PowerPipeline0D()]]
+    assert len(g.observers[0].pipelines) == 1 and g.observers[1].pipelines == []
