@@ -16,8 +16,8 @@ from .inversions import SartSolver, invert_constrained_sart, invert_sart
 from .models import (Bremsstrahlung, ExcitationLine, GaussianLine, MultipletLineShape, ParametrisedZeemanTriplet,
                      RecombinationLine, StarkBroadenedLine, ThermalCXLine, TotalRadiatedPower, ZeemanMultiplet, ZeemanStructure, ZeemanTriplet)
 from .notify import Notifier
-from .observers import (DevicePinhole, DeviceRayBuffer, FibreOptic, FibreOpticGroup, PowerPipeline0D, RadiancePipeline0D, SightLine, SightLineGroup,
-                        SpectralPowerPipeline0D, SpectralRadiancePipeline0D, observe)
+from .observers import (DevicePinhole, DeviceRayBuffer, FibreOptic, FibreOpticGroup, PowerPipeline0D, RadiancePipeline0D, RadiancePipeline2D,
+                        SightLine, SightLineGroup, SpectralPowerPipeline0D, SpectralRadiancePipeline0D, SpectralRadiancePipeline2D, observe)
 from .openadas import OpenADAS
 from .plasma import (AxisymBlend, AxisymBlendVector, AxisymContext, Constant3D, ConstantVector3D, EFITEquilibrium,
                      EFITMagneticField, GaussianVolume, Maxwellian, ModelManager, NumericalIntegrator, Plasma, SlabIonFunction,

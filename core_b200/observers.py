@@ -108,13 +108,14 @@ class DevicePinhole:
         return buf
 
 
-def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None, wall=None):
+def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None, wall=None, pipelines=()):
     """Mean spectral radiance per pixel over pixel_samples_side^2 stratified sub-pixel samples, on the device.
 
     ``scene``: engine.EmissionScene or engine.PlasmaRenderer; ``pinhole``: DevicePinhole.  Returns a torch tensor
     [n_pixels, bins] (float32 unless ``dtype``/``frame`` say otherwise) — ``SpectralRadiancePipeline2D.frame.mean`` of the
     reference flow, W / (m^2 sr nm).  ``wall``: optional first_wall.FirstWall — every ray's chords end at its first wall hit
-    (what the opaque wall meshes do in the reference's scene graph, generomak/machine/first_wall.py:120-184)."""
+    (what the opaque wall meshes do in the reference's scene graph, generomak/machine/first_wall.py:120-184).  ``pipelines``:
+    SpectralRadiancePipeline2D / RadiancePipeline2D objects that receive the frame on the host."""
     import torch
     bins = scene.scene.bins if hasattr(scene, "scene") else scene.bins
     if frame is None:
@@ -128,6 +129,15 @@ def observe(scene, pinhole, pixel_samples_side=1, frame=None, dtype=None, wall=N
         if wall is not None:
             wall.clip_device(rays)
         scene.render_device(rays, frame, scale=1.0 / len(offsets), accumulate=True)
+    if pipelines:
+        # result packing into 2-D pipelines (one D2H of the frame): only for a camera that renders all of its pixels
+        if pinhole.pixel_index is not None:
+            raise ValueError("pipelines need the whole frame: the pinhole was built with a pixel subset")
+        nx, ny = pinhole.camera.pixels
+        host = frame.cpu().numpy().reshape(nx, ny, bins)
+        grid = (scene.scene if hasattr(scene, "scene") else scene).flat.desc.grid
+        for p in pipelines:
+            p._fill_frame(grid.min_wavelength, grid.max_wavelength, host, len(offsets))
     return frame
 
 
@@ -187,6 +197,22 @@ class RadiancePipeline0D(_Pipeline0D):
 class PowerPipeline0D(RadiancePipeline0D):
     """``value.mean``: the collected power integrated over the spectral range, W."""
     _POWER = True
+
+
+class SpectralRadiancePipeline2D(_Pipeline0D):
+    """``frame.mean[nx, ny, bins]``: mean spectral radiance per pixel over the pixel samples, W / (m^2 sr nm) [raysect]."""
+
+    def _fill_frame(self, min_wavelength, max_wavelength, frame, pixel_samples):
+        self._set_grid(min_wavelength, max_wavelength, frame.shape[-1])
+        self.frame = _Stats(frame, int(pixel_samples))
+
+
+class RadiancePipeline2D(_Pipeline0D):
+    """``frame.mean[nx, ny]``: radiance per pixel integrated over the spectral range, W / (m^2 sr) [raysect]."""
+
+    def _fill_frame(self, min_wavelength, max_wavelength, frame, pixel_samples):
+        self._set_grid(min_wavelength, max_wavelength, frame.shape[-1])
+        self.frame = _Stats(frame.sum(axis=-1) * self.delta_wavelength, int(pixel_samples))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -59,8 +59,12 @@ def test_observe_frame_mean_over_pixel_samples():
     pin = cb.DevicePinhole(cam, plasma.geometry, to_world=plasma.geometry_to_world())
     scene = EmissionScene(flat)
     import torch
-    frame = cb.observe(scene, pin, pixel_samples_side=2, dtype=torch.float64).cpu().numpy()
+    spectral, total = cb.SpectralRadiancePipeline2D(), cb.RadiancePipeline2D()
+    frame = cb.observe(scene, pin, pixel_samples_side=2, dtype=torch.float64, pipelines=[spectral, total]).cpu().numpy()
     scene.close()
+    assert spectral.frame.mean.shape == (6, 5, 128) and spectral.frame.samples == 4 and spectral.bins == 128
+    assert np.array_equal(spectral.frame.mean.reshape(30, 128), frame)
+    np.testing.assert_allclose(total.frame.mean, frame.reshape(6, 5, 128).sum(axis=2) * (10.0 / 128), rtol=1e-12)
     ref = np.zeros_like(frame)
     for sx, sy in cb.stratified_offsets(2):
         rays = cb.ray_segments(plasma.geometry, *cam.rays(sx, sy), plasma.geometry_to_world())
