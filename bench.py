@@ -188,27 +188,18 @@ def shared_host_frame(rows_total, bins, rank, dist, torch):
     """The whole [rows_total, bins] fp32 frame in shared host memory (/dev/shm), mapped and page-locked by every rank: each rank's
     strided D2H copies put its tiles on their pixels, so the frame a consumer maps is in image order.  Returns (numpy frame or
     None, description); None when /dev/shm cannot hold the frame or the mapping cannot be page-locked on some rank."""
-    import mmap
-    path = "/dev/shm/cb2_frame_%s" % os.environ.get("MASTER_PORT", "0")
-    nbytes = rows_total * bins * 4
+    from core_b200.sharding import open_shared_frame, unlink_shared_frame
+    name = "cb2_frame_%s" % os.environ.get("MASTER_PORT", "0")
     ok = torch.zeros(1, dtype=torch.int32, device="cuda")
     frame = None
     if rank == 0:
         try:
-            fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
-            os.posix_fallocate(fd, 0, nbytes)             # fails here, not at the first touch, if /dev/shm is too small
-            os.close(fd)
+            open_shared_frame(name, rows_total, bins, create=True)
         except OSError:
-            try:
-                os.unlink(path)
-            except OSError:
-                pass
+            pass
     dist.barrier()
     try:
-        fd = os.open(path, os.O_RDWR)
-        mm = mmap.mmap(fd, nbytes)
-        os.close(fd)
-        frame = np.frombuffer(mm, dtype=np.float32).reshape(rows_total, bins)
+        frame, _mm = open_shared_frame(name, rows_total, bins, create=False)
         rc = torch.cuda.cudart().cudaHostRegister(frame.ctypes.data, frame.nbytes, 0)
         if int(getattr(rc, "value", rc)) != 0:
             frame = None
@@ -217,10 +208,7 @@ def shared_host_frame(rows_total, bins, rank, dist, torch):
     ok[0] = 1 if frame is not None else 0
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        try:
-            os.unlink(path)                               # the mappings keep the memory alive; nothing is left behind
-        except OSError:
-            pass
+        unlink_shared_frame(name)                         # the mappings keep the memory alive; nothing is left behind
     if int(ok.item()) == 1:
         return frame, ("image-ordered frame [nx*ny, bins] (pixel ix*ny+iy) in shared host memory (/dev/shm): every rank writes its tiles to "
                        "their pixels over its own PCIe link (strided D2H inside the timed region)")

@@ -49,3 +49,37 @@ def gather_frame(local_rows, pixels, dst=0):
     for r, b in enumerate(bufs):
         frame[torch.from_numpy(tile_pixels((nx, ny), r, world)).to(local_rows.device)] = b
     return frame.reshape(nx, ny, bins)
+
+
+def open_shared_frame(name, rows, bins, create):
+    """The [rows, bins] float32 frame in shared host memory (/dev/shm/<name>) every rank of a node writes its tiles into — the
+    image-ordered frame of the N > 1 end-to-end path.  ``create``: allocate the file (one rank, before the others open it;
+    posix_fallocate fails here, not at the first touch, when /dev/shm is too small).  Returns (numpy frame, mmap object)."""
+    import mmap
+    import os
+    path = os.path.join("/dev/shm", name)
+    nbytes = int(rows) * int(bins) * 4
+    if create:
+        fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
+        try:
+            os.posix_fallocate(fd, 0, nbytes)
+        except OSError:
+            os.close(fd)
+            os.unlink(path)
+            raise
+        os.close(fd)
+    fd = os.open(path, os.O_RDWR)
+    try:
+        mm = mmap.mmap(fd, nbytes)
+    finally:
+        os.close(fd)
+    return np.frombuffer(mm, dtype=np.float32).reshape(int(rows), int(bins)), mm
+
+
+def unlink_shared_frame(name):
+    """Remove the file; existing mappings keep the memory alive."""
+    import os
+    try:
+        os.unlink(os.path.join("/dev/shm", name))
+    except OSError:
+        pass

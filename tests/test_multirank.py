@@ -50,3 +50,44 @@ def test_gloo_world2_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def _shared_worker(rank, world, port, pixels, bins, out):
+    # the N > 1 end-to-end layout: every rank writes its tiles to their pixels of ONE image-ordered frame in shared host memory
+    from core_b200.sharding import open_shared_frame, unlink_shared_frame
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    name = "cb2_test_frame_%d" % port
+    n = pixels[0] * pixels[1]
+    if rank == 0:
+        open_shared_frame(name, n, bins, create=True)
+    dist.barrier()
+    frame, mm = open_shared_frame(name, n, bins, create=False)
+    dist.barrier()
+    if rank == 0:
+        unlink_shared_frame(name)
+    pix = tile_pixels(pixels, rank, world)                       # destination rows of this rank's rays (cb2_emission_render_rows)
+    frame[pix] = pix[:, None].astype(np.float32) * np.arange(1, bins + 1, dtype=np.float32)[None, :]
+    dist.barrier()
+    if rank == 0:
+        expect = np.arange(n, dtype=np.float32)[:, None] * np.arange(1, bins + 1, dtype=np.float32)[None, :]
+        out.put(bool(np.array_equal(frame, expect)) and not os.path.exists("/dev/shm/" + name))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_image_ordered_shared_frame():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, (40, 56), 5, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
