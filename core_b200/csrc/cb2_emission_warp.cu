@@ -756,6 +756,11 @@ __global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile i
 // ------------------------------------------------------------------------------------------------------------------
 // K1a: per-sample plasma state -> line records + Bremsstrahlung moments
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef CB2_FIX_MINB
+// the fix-up instance (one warp per ray over the flagged samples): 5 CTAs per SM (102 registers, no spills) — 2.70 ms per 65 536 C3
+// rays against 2.79 at 6, 2.90 at 4, 3.26 at 8 (64 registers, spills)
+#define CB2_FIX_MINB 5
+#endif
 #ifndef CB2_STATE_MINB
 // 6 CTAs of 4 warps per SM (85 registers, ~200 B of spills): measured 3 % faster than 5 (102 registers), 4 is 6 % slower, 8 slower again
 #define CB2_STATE_MINB 6
@@ -764,7 +769,7 @@ __global__ void publish_total_kernel(const int64_t* __restrict__ src, volatile i
 // ThermalCXLine and TotalRadiatedPower branches (kept out of the common instance: they cost registers and instruction cache)
 #define CB2_FIX_WINDOW 32                              // groups per list round of the fix-up pass (at most 1024 flagged samples)
 template <int NW, int MOM, int AXONLY, int FEAT, int FIX>
-__global__ void __launch_bounds__(NW * 32, CB2_STATE_MINB)
+__global__ void __launch_bounds__(NW * 32, FIX ? CB2_FIX_MINB : CB2_STATE_MINB)
 state_kernel(const __grid_constant__ DevScene Sparam, DevRays rays, const int64_t* __restrict__ gbase, unsigned* __restrict__ gmask,
              float* __restrict__ rec, unsigned long long* __restrict__ stats, float* __restrict__ mom_out, double* __restrict__ flat_out,
              int count_samples, int dbg_skip, const unsigned* __restrict__ gblend, const __grid_constant__ DevMemo FM) {
