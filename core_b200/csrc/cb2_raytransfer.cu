@@ -240,7 +240,7 @@ rt_csr_kernel(DevRT R, DevRays rays, int mode, int64_t* __restrict__ row_offset,
             if (lane == 0) steps += (unsigned long long)n;
             // 32 K consecutive steps per iteration: lane l owns steps it0 + K l + j, j < K.  The bookkeeping below — run heads, merge,
             // hash probe, slot numbering — is warp-wide work per iteration, not per step: K steps per lane divide it by K (it was
-            // ~ 2/3 of the kernel's instructions with one step per lane; C4: 37.3 ms at K = 1, 29.8 at K = 2, 28.8 at K = 4).  Tried and
+            // ~ 2/3 of the kernel's instructions with one step per lane; C4: 37.3 ms at K = 1, 29.8 at K = 2, 27.5 at K = 4, 29.8 at K = 8).  Tried and
             // dropped: index decisions by reciprocal multiplication and squared cell faces with the IEEE division / square-root chain
             // as the fallback near a face — bit-identical, but no faster (31.9 ms at K = 4): the chain is not what the kernel waits for.
             constexpr int K = RT_STEPS_PER_LANE;
