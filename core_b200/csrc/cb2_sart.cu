@@ -284,6 +284,8 @@ struct cb2_sart {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     int64_t last_iterations = 0;
+    char* work = nullptr;           // the frames' work arrays of solve_group: one grow-only allocation kept by the handle
+    size_t work_bytes = 0;
 };
 
 namespace {
@@ -446,6 +448,7 @@ extern "C" int cb2_sart_destroy(cb2_sart* s) {
     cudaSetDevice(s->device);
     free_matrix(s->csr); free_matrix(s->csc); free_matrix(s->lap);
     cudaFree(s->density); cudaFree(s->inv_length);
+    cudaFree(s->work);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -525,16 +528,24 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
     int rc = CB2_OK;
     do {
 #define SART_TRY(call) if ((rc = cb2_cuda_check((call), #call)) != CB2_OK) break
-        SART_TRY(cudaMalloc((void**)&fr.x, (size_t)ns * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.x_new, (size_t)ns * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.w, (size_t)nd * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.m, (size_t)nd * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.part, (size_t)(max_chunks ? max_chunks : 1) * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.partial, (size_t)SART_FIN_GRID * FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.conv, (size_t)FR * max_iterations * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.m_sq, FR * sizeof(double)));
-        SART_TRY(cudaMalloc((void**)&fr.stopped, FR * sizeof(int32_t)));
-        SART_TRY(cudaMalloc((void**)&fr.flags, 3 * sizeof(int32_t)));
+        // the work arrays live in one allocation owned by the handle (grow-only): a solve allocates nothing after the first
+        const size_t sizes[10] = {(size_t)ns * FR * sizeof(double), (size_t)ns * FR * sizeof(double), (size_t)nd * FR * sizeof(double),
+                                  (size_t)nd * FR * sizeof(double), (size_t)(max_chunks ? max_chunks : 1) * FR * sizeof(double),
+                                  (size_t)SART_FIN_GRID * FR * sizeof(double), (size_t)FR * max_iterations * sizeof(double),
+                                  FR * sizeof(double), FR * sizeof(int32_t), 3 * sizeof(int32_t)};
+        size_t off[11] = {0};
+        for (int k = 0; k < 10; k++) off[k + 1] = off[k] + ((sizes[k] + 255) & ~(size_t)255);
+        if (s->work_bytes < off[10]) {
+            SART_TRY(cudaStreamSynchronize(st));
+            cudaFree(s->work);
+            s->work = nullptr; s->work_bytes = 0;
+            SART_TRY(cudaMalloc((void**)&s->work, off[10]));
+            s->work_bytes = off[10];
+        }
+        fr.x = (double*)(s->work + off[0]); fr.x_new = (double*)(s->work + off[1]); fr.w = (double*)(s->work + off[2]);
+        fr.m = (double*)(s->work + off[3]); fr.part = (double*)(s->work + off[4]); fr.partial = (double*)(s->work + off[5]);
+        fr.conv = (double*)(s->work + off[6]); fr.m_sq = (double*)(s->work + off[7]); fr.stopped = (int32_t*)(s->work + off[8]);
+        fr.flags = (int32_t*)(s->work + off[9]);
         SART_TRY(cudaMemcpyAsync(fr.x, h_x.data(), h_x.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         SART_TRY(cudaMemcpyAsync(fr.m, h_m.data(), h_m.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         SART_TRY(cudaMemcpyAsync(fr.m_sq, h_msq.data(), FR * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -584,8 +595,6 @@ int solve_group(cb2_sart* s, const double* meas, int64_t n_frames, int64_t f0, c
         }
 #undef SART_TRY
     } while (0);
-    cudaFree(fr.x); cudaFree(fr.x_new); cudaFree(fr.w); cudaFree(fr.m); cudaFree(fr.part); cudaFree(fr.partial); cudaFree(fr.conv);
-    cudaFree(fr.m_sq); cudaFree(fr.stopped); cudaFree(fr.flags);
     return rc;
 }
 
