@@ -168,7 +168,7 @@ class WallDesc(C.Structure):
 # every symbol include/cherab_b200.h declares for the product library
 PRODUCT_SYMBOLS = [
     "cb2_abi_version", "cb2_last_error", "cb2_device_count", "cb2_measure_peaks", "cb2_measure_peak_fp64", "cb2_scene_create", "cb2_scene_destroy",
-    "cb2_emission_render", "cb2_emission_render_rows", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
+    "cb2_emission_render", "cb2_emission_render_rows", "cb2_rows_plan", "cb2_emission_render_device", "cb2_sample_state", "cb2_state_width", "cb2_scene_info", "cb2_scene_profile", "cb2_beam_sample",
     "cb2_rt_create", "cb2_rt_destroy", "cb2_rt_render_dense", "cb2_rt_render_csr", "cb2_rt_render_csr_device",
     "cb2_pinhole_rays_device", "cb2_observer0d_rays_device", "cb2_observer0d_reduce_device",
     "cb2_wall_create", "cb2_wall_destroy", "cb2_wall_hit", "cb2_wall_clip_device",
@@ -198,6 +198,8 @@ def load_library():
     lib.cb2_scene_destroy.argtypes = [vp]
     lib.cb2_emission_render.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, C.POINTER(Stats)]
     lib.cb2_emission_render_rows.argtypes = [vp, C.POINTER(Rays), c_int64_p, vp, C.c_int, C.c_double, C.POINTER(Stats)]
+    lib.cb2_rows_plan.argtypes = [c_int64_p, C.c_int64, c_int64_p, C.c_int64]
+    lib.cb2_rows_plan.restype = C.c_int64
     lib.cb2_emission_render_device.argtypes = [vp, C.POINTER(Rays), vp, C.c_int, C.c_double, C.c_int, vp, vp]
     lib.cb2_sample_state.argtypes = [vp, c_double_p, C.c_int64, c_double_p]
     lib.cb2_state_width.argtypes = [vp]

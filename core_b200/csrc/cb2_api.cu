@@ -1651,24 +1651,42 @@ int cb2_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
 // Rows src_dev[i] (i < n, row_bytes each) to dst_base + dest_row[i] * row_bytes, asynchronously on `st`: consecutive destination
 // rows form a run; runs of equal length at a constant pitch form one cudaMemcpy2DAsync (a 16 x 16 tile of a pixel-ordered frame:
 // 16 runs of 16 rows, pitch = ny rows).
+// the copy that starts at ray i: `len` consecutive destination rows, repeated `h` times at a constant `pitch` (in rows)
+static void rows_next_op(const int64_t* dest_row, int64_t n, int64_t i, int64_t& len, int64_t& h, int64_t& pitch) {
+    len = 1;
+    while (i + len < n && dest_row[i + len] == dest_row[i] + len) len++;
+    h = 1; pitch = 0;
+    while (i + (h + 1) * len <= n) {
+        const int64_t j = i + h * len;
+        const int64_t p = dest_row[j] - dest_row[j - len];
+        if (h == 1) { if (p <= len) break; pitch = p; } else if (p != pitch) break;
+        bool run = true;
+        for (int64_t k = 1; k < len && run; k++) run = dest_row[j + k] == dest_row[j] + k;
+        if (!run) break;
+        h++;
+    }
+}
+
+// The copy plan of cb2_emission_render_rows for a destination-row list, without a device: plan[4 k .. 4 k + 3] = (first ray, run
+// length, repeats, pitch in rows) of copy k.  Returns the number of copies (the plan is filled up to `capacity` of them).
+extern "C" int64_t cb2_rows_plan(const int64_t* dest_row, int64_t n, int64_t* plan, int64_t capacity) {
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; k++) {
+        int64_t len, h, pitch;
+        rows_next_op(dest_row, n, i, len, h, pitch);
+        if (plan && k < capacity) { plan[4 * k] = i; plan[4 * k + 1] = len; plan[4 * k + 2] = h; plan[4 * k + 3] = pitch; }
+        i += h * len;
+    }
+    return k;
+}
+
 int cb2_d2h_rows(void* dst_base, const int64_t* dest_row, int64_t n, const void* src_dev, size_t row_bytes, cudaStream_t st, cudaStream_t st2) {
     int64_t i = 0;
     int turn = 0;
     while (i < n) {
         cudaStream_t cs = (st2 && (turn++ & 1)) ? st2 : st;
-        int64_t len = 1;
-        while (i + len < n && dest_row[i + len] == dest_row[i] + len) len++;
-        // how many following runs have this length and a constant pitch?
-        int64_t h = 1, pitch = 0;
-        while (i + (h + 1) * len <= n) {
-            const int64_t j = i + h * len;
-            const int64_t p = dest_row[j] - dest_row[j - len];
-            if (h == 1) { if (p <= len) break; pitch = p; } else if (p != pitch) break;
-            bool run = true;
-            for (int64_t k = 1; k < len && run; k++) run = dest_row[j + k] == dest_row[j] + k;
-            if (!run) break;
-            h++;
-        }
+        int64_t len, h, pitch;
+        rows_next_op(dest_row, n, i, len, h, pitch);
         char* d = (char*)dst_base + (size_t)dest_row[i] * row_bytes;
         const char* s = (const char*)src_dev + (size_t)i * row_bytes;
         if (h == 1) CB2_CUDA(cudaMemcpyAsync(d, s, (size_t)len * row_bytes, cudaMemcpyDeviceToHost, cs));

@@ -391,6 +391,10 @@ int cb2_emission_render(cb2_scene* scene, const cb2_rays* rays, void* out, int o
 int cb2_emission_render_rows(cb2_scene* scene, const cb2_rays* rays, const int64_t* dest_row, void* out, int out_f64,
                              double scale, cb2_stats* stats);
 
+/* The copy plan cb2_emission_render_rows follows for a destination-row list (no device needed; introspection / tests):
+ * plan[4k..4k+3] = (first ray, run length, repeats, pitch in rows) of copy k, up to `capacity` copies; returns the number of copies. */
+int64_t cb2_rows_plan(const int64_t* dest_row, int64_t n, int64_t* plan, int64_t capacity);
+
 /* Same, DEVICE buffers (torch tensors): every pointer in `rays` and `out` is device memory on the scene's device;
  * launches on `stream` (a cudaStream_t passed as void*), does not synchronise. stats may be NULL;
  * if not NULL it must be device memory (filled asynchronously). */

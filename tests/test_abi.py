@@ -81,3 +81,40 @@ def test_product_does_not_import_oracle():
     for fn in os.listdir(os.path.join(pkg, "csrc")):
         if fn.endswith((".cu", ".h")):
             assert "cb2o_" not in open(os.path.join(pkg, "csrc", fn)).read(), fn
+
+
+def test_rows_plan_covers_every_ray_once():
+    # cb2_rows_plan: the strided-copy plan of cb2_emission_render_rows (host logic, no device): a rank's tile-ordered rays become one
+    # 2-D copy per 16 x 16 tile; any other row list decomposes into runs that cover every ray exactly once
+    import ctypes as C
+    import numpy as np
+    from core_b200 import _abi
+    from core_b200.sharding import tile_pixels
+    lib = _abi.load_library()
+
+    def plan(rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros(4 * max(rows.size, 1), dtype=np.int64)
+        k = lib.cb2_rows_plan(rows.ctypes.data_as(_abi.c_int64_p), rows.size, out.ctypes.data_as(_abi.c_int64_p), rows.size)
+        ops = out[:4 * k].reshape(k, 4)
+        # replay: copy k moves rays [first + r len, first + (r + 1) len) to rows dest[first] + r pitch + [0, len)
+        seen = np.full(rows.size, -1, dtype=np.int64)
+        for first, length, repeats, pitch in ops:
+            for r in range(repeats):
+                idx = first + r * length + np.arange(length)
+                assert np.all(seen[idx] == -1)
+                seen[idx] = rows[first] + r * pitch + np.arange(length)
+        assert np.array_equal(seen, rows)
+        return ops
+
+    ops = plan(tile_pixels((64, 48), 1, 3))                       # 4 x 3 tiles dealt to 3 ranks: rank 1 holds the middle tile of
+    assert ops.tolist() == [[0, 16, 64, 48]]                      # every tile row — one pitch throughout, a single 2-D copy
+    ops = plan(tile_pixels((64, 48), 1, 4))                       # rank 1 of 4: tiles (0, 1), (1, 2), (3, 0)
+    assert len(ops) == 3 and np.all(ops[:, 1] == 16) and np.all(ops[:, 2] == 16) and np.all(ops[:, 3] == 48)
+    ops = plan(tile_pixels((40, 24), 0, 1))                       # ragged tiles at the frame's edge (40 = 2.5 tiles, 24 = 1.5 tiles)
+    assert ops[:, 1].max() == 16 and ops[:, 1].min() == 8
+    assert len(plan(np.arange(1000))) == 1                        # one contiguous run
+    rng = np.random.default_rng(11)
+    plan(rng.permutation(5000)[:700])                             # single rows
+    plan(np.concatenate([np.arange(100, 137), np.arange(10, 12), [5], np.arange(400, 464), np.arange(300, 364), np.arange(200, 264), [1599]]))
+    assert lib.cb2_rows_plan(None, 0, None, 0) == 0
