@@ -186,3 +186,22 @@ def test_foreign_numerical_integrator_over_the_emitter():
     with pytest.raises(TypeError):
         rtb.integrator = "trapezium"
         rtb.descriptor()
+
+
+def test_row_sums_are_chord_lengths_under_both_integrators():
+    # size-independent property: with every cell mapped, a ray's path lengths add up to its chord through the grid — exactly (to
+    # rounding) under the trapezium rule (weights h/2, h, ..., h/2 sum to L) and under the midpoint rule (n dt = L)
+    rng = np.random.default_rng(42)
+    rtc = RayTransferCylinder(radius_outer=2.0, height=3.0, n_radius=13, n_height=17, radius_inner=0.5, n_polar=5, period=72.0,
+                              transform=cb.translate(0, 0, -1.5))
+    o = rng.uniform(-4, 4, (40, 3))
+    d = rng.uniform(-1, 1, (40, 3)) - o
+    rays = cb.ray_segments(rtc.primitive, o, d, rtc.transform)
+    assert rays.n_segments > 10
+    chord = np.zeros(rays.n_rays)
+    np.add.at(chord, np.repeat(np.arange(rays.n_rays), np.diff(rays.seg_offset)), rays.seg_t1 - rays.seg_t0)
+    for integrator in (None, cb.NumericalIntegrator(step=0.013, min_samples=7)):
+        rtc.integrator = integrator
+        desc, keep = rtc.descriptor()
+        rows, _ = oracle.rt_render_dense(desc, rays)
+        np.testing.assert_allclose(rows.sum(axis=1), chord, rtol=1e-12, atol=1e-12)
